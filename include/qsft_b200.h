@@ -1,0 +1,113 @@
+/* qsft_b200.h -- C ABI of libqsft_b200.so: the B200 (sm_100a) kernels of the q-SFT transform path.
+ *
+ * The reference (basics-lab/qsft) is pure Python and has NO FFI of its own; the boundary a maintainer would bind is
+ * its Python object API (QSFT.transform / SubsampledSignal.subsample / query_args).  Each entry point below replaces
+ * one numerical call site of that path; the reference file:line it replaces is cited.  INTEGRATION.md shows the
+ * ctypes stub.  Conventions:
+ *   - every function returns 0 on success or a negative QSFT_E* code; qsft_last_error() gives a thread-local text.
+ *   - all data pointers are DEVICE pointers owned by the caller (e.g. torch tensors' data_ptr()); sizes explicit;
+ *     no allocation inside unless stated; `stream` is a cudaStream_t passed as void* (NULL = default stream); calls
+ *     are asynchronous on that stream unless stated.
+ *   - digit vectors are int8, MSB first (digit 0 is the most significant base-q digit, as qsft/utils.py:74-76).
+ *   - complex values are interleaved float (re, im) = complex64.
+ *   - decimal indices are unsigned little-endian-in-limbs: limbs==1 -> one uint64; limbs==2 -> {hi, lo} uint64 pair.
+ */
+#ifndef QSFT_B200_H
+#define QSFT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSFT_OK 0
+#define QSFT_EINVAL (-1)   /* bad argument (message in qsft_last_error)          */
+#define QSFT_ECUDA (-2)    /* CUDA runtime error                                  */
+#define QSFT_EUNSUPPORTED (-3)
+
+const char* qsft_last_error(void);
+int qsft_version(void);
+/* number of kernels launched by this library since load / since the last reset (bench.py "gpu_launches"). */
+int64_t qsft_launch_count(void);
+void qsft_reset_launch_count(void);
+
+/* K1 -- query lattice.  Replaces SubsampledSignal._get_qsft_query_indices (qsft/input_signal_subsampled.py:183-206)
+ * + qary_ints (qsft/utils.py:107-108) + qary_vec_to_dec (qsft/utils.py:74-76).
+ *   M (n, b) int8 row-major, D (P, n) int8.  For every delay row p and every l in Z_q^b (column index = base-q value
+ *   of l, l_0 most significant) writes dec((M l + d_p) mod q):
+ *   out_idx  (P, q^b, limbs) uint64   (may be NULL)
+ *   out_dig  (P, q^b, ld) int8 digit rows, zero padded to ld >= n, ld % 16 == 0   (may be NULL)           */
+int qsft_query_lattice(const int8_t* M, const int8_t* D, int q, int n, int b, int P,
+                       uint64_t* out_idx, int limbs, int8_t* out_dig, int ld, void* stream);
+
+/* dec_to_qary_vec (qsft/utils.py:79-84) on device: idx (N, limbs) uint64 -> dig (N, ld) int8, zero padded. */
+int qsft_dec_to_qary(const uint64_t* idx, int limbs, int64_t N, int q, int n, int8_t* dig, int ld, void* stream);
+/* qary_vec_to_dec (qsft/utils.py:74-76) on device: dig (N, ld) -> idx (N, limbs). */
+int qsft_qary_to_dec(const int8_t* dig, int ld, int64_t N, int q, int n, uint64_t* idx, int limbs, void* stream);
+
+/* K2 -- synthetic sparse signal evaluation.  Replaces SyntheticSubsampledSignal.subsample / sampling_function
+ * (synt_exp/synt_src/synthetic_signal.py:100-118):  out[m] = sum_s strengths[s] * w^(<qdig[m], loc[s]> mod q).
+ *   qdig (N, ld) int8, loc (S, ld) int8 (support digit rows, zero padded), strengths (S) complex64, out (N) complex64.
+ *   impl: 0 = best available for the shape, 1 = SIMT (dp4a) kernel, 2 = tcgen05 int8 GEMM + fused epilogue.   */
+int qsft_eval_synth(const int8_t* qdig, int64_t N, const int8_t* loc, const float* strengths, int64_t S,
+                    int q, int n, int ld, float* out, int impl, void* stream);
+
+/* K3 -- batched b-dimensional length-q DFT, forward sign, scaled by 1/q^b, in place.  Replaces
+ * SubsampledSignal._compute_subtransform + gwht (qsft/input_signal_subsampled.py:264-266, qsft/utils.py:31-36).
+ *   x (batch, q^b) complex64.  Index <-> digits MSB first on both sides (C-order reshape [q]*b).            */
+int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stream);
+
+/* K4 -- peeling decoder.  Replaces the loop of QSFT.transform (qsft/qsft.py:151-241) and the singleton detectors
+ * (qsft/reconstruct.py:12-31, 100-113, 34-51 + qsft/ReedSolomon.py:26-48).
+ *
+ * Problem description shared by the peel entry points. */
+typedef struct {
+    int q, n, b;          /* alphabet, signal dimension, subsampling dimension (B = q^b bins per group)            */
+    int C, P, P_src;      /* groups, delay rows per group (P = R * P_src), rows of the source delay matrix         */
+    int channel;          /* 0 = identity (noiseless angles, reconstruct.py:12-31), 1 = nso1 (reconstruct.py:100-113) */
+    int source;           /* 0 = identity, 1 = coded (Reed-Solomon syndrome decode, ReedSolomon.py:26-48)          */
+    int rs_t, rs_s;       /* coded only: error capability t, extension degree s (P_src = 2*t*s + 1)                */
+    int ld;               /* row stride (bytes) of MT, D and find_k digit rows: >= n, multiple of 16, zero padded  */
+    float cutoff;         /* per-delay energy threshold, qsft.py:124-126                                           */
+    const int8_t* MT;     /* (C, b, ld)  row i of group c = column i of M_c                                        */
+    const int8_t* D;      /* (C, P, ld)                                                                            */
+    const int32_t* rs_exp;/* coded only: GF(q^s) antilog table, 2*(q^s-1) entries (device)                         */
+    const int32_t* rs_log;/* coded only: GF(q^s) log table, q^s entries (device)                                   */
+} qsft_peel_desc;
+
+/* One classification pass over bins [j_begin, j_end) of every group (qsft.py:162-188).
+ *   U (C, P, B) complex64.  For every singleton appends a find f = counters[0]++ (atomic, not zeroed here):
+ *   find_cj[f] = c * B + j, find_k (f, ld) digits, find_rho (f) complex64, find_round[f] = round (may be NULL);
+ *   find_id (C, B) int32 gets the find number, or -1 for zerotons / multitons.
+ *   counters[1] += number of multitons.  Finds beyond max_finds are counted but not stored (caller must check). */
+int qsft_peel_classify(const qsft_peel_desc* d, const float* U, int64_t j_begin, int64_t j_end,
+                       int64_t* find_cj, int8_t* find_k, float* find_rho, int32_t* find_round, int32_t* find_id,
+                       int64_t max_finds, int round, unsigned long long* counters, void* stream);
+
+/* Peel finds [f_begin, f_begin + n_finds) off U (qsft.py:209-241).  With dedupe != 0 a find is applied only if it
+ * is the LAST find of its k in (c, j) order (ball_values "last wins", qsft.py:215), checked through find_id /
+ * find_k of the higher groups; with dedupe == 0 every listed find is applied.  Only bins in [j_begin, j_end) are
+ * touched (bin-sharded multi-GPU peeling).  owner_count (may be NULL) += number of finds applied.               */
+int qsft_peel_apply(const qsft_peel_desc* d, float* U, int64_t j_begin, int64_t j_end,
+                    const int64_t* find_cj, const int8_t* find_k, const float* find_rho,
+                    const int32_t* find_id, int64_t f_begin, int64_t n_finds, int dedupe,
+                    unsigned long long* owner_count, void* stream);
+
+/* Whole single-GPU peel loop (qsft.py:151-241): classify / apply rounds until the reference's stop rule
+ * (no multitons or no singletons, or 15 rounds, or q^n peels).  SYNCHRONOUS (reads round counters back).
+ *   Outputs: finds grouped by round (order inside a round is unspecified): find_cj / find_k / find_rho /
+ *   find_round as above.  *n_finds_out = total finds, *n_rounds_out = rounds.  Workspaces: find_id (C, B) int32,
+ *   counters (>= 4 x u64, device).                                                                              */
+int qsft_peel(const qsft_peel_desc* d, float* U, int64_t* find_cj, int8_t* find_k, float* find_rho,
+              int32_t* find_round, int32_t* find_id, int64_t max_finds, unsigned long long* counters,
+              int64_t* n_finds_out, int* n_rounds_out, void* stream);
+
+/* Closed-form bins (verification helper): U[p][j] = sum_{s: M^T k_s = j} a_s w^{<d_p,k_s>}.
+ * Used by tests and by the peel benchmark to fill U without sampling.  U (P, B) must be zeroed by the caller. */
+int qsft_closed_form_bins(const int8_t* MT /* (b, ld) */, const int8_t* D /* (P, ld) */, int q, int n, int b, int P,
+                          const int8_t* loc, int ld, const float* strengths, int64_t S, float* U, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

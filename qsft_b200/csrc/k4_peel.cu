@@ -1,0 +1,584 @@
+// K4: peeling decoder.  Replaces the round loop of QSFT.transform (qsft/qsft.py:151-241), the singleton detectors
+// (qsft/reconstruct.py:12-31 noiseless, :100-113 nso1, :34-51 coded) and the Reed-Solomon syndrome decoder
+// (qsft/ReedSolomon.py:26-48, arithmetic of galois' decode_jit restated: Berlekamp-Massey + Chien + Forney).
+//
+// Layout: U (C, P, B) complex64 with the bin index j contiguous.  Classification maps one THREAD to one bin with lanes
+// over consecutive j, so every load of a delay row is a fully coalesced 256-byte warp request (HBM bound: one read of
+// U per round).  Rounds are synchronous like the reference: classify on a frozen U, then subtract.
+#include "common.cuh"
+
+namespace {
+
+constexpr int K4_THREADS = 128;
+constexpr int RS_MAX_2T = 32;
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+
+struct PeelDev {
+    int q, n, b, C, P, P_src, R, channel, source, rs_t, rs_s, ld;
+    long long B;
+    double thresh;            // cutoff * P
+    const int8_t* MT;         // (C, b, ld)   rows = columns of M, zero padded
+    const int8_t* D;          // (C, P, ld)
+    const int32_t* rs_exp;
+    const int32_t* rs_log;
+    int rs_order;             // q^s
+};
+
+__device__ __forceinline__ int dp4a_u(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// <row, k> mod q; `row` has ld bytes (ld % 16 == 0), kw holds the digits of k four per word (zero padded)
+template <int NW>
+__device__ __forceinline__ int dot_mod(const int8_t* row, int ld, const uint32_t (&kw)[NW], int q) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(row);
+    const int nv = ld >> 4;
+    int acc = 0;
+#pragma unroll
+    for (int w = 0; w < NW / 4; ++w) {
+        if (w >= nv) break;
+        uint4 v = __ldg(r4 + w);
+        acc = dp4a_u(v.x, kw[4 * w + 0], acc);
+        acc = dp4a_u(v.y, kw[4 * w + 1], acc);
+        acc = dp4a_u(v.z, kw[4 * w + 2], acc);
+        acc = dp4a_u(v.w, kw[4 * w + 3], acc);
+    }
+    return acc % q;
+}
+
+// bin hash j = dec(M_c^T k mod q), b digits MSB first (qsft.py:178, :227)
+template <int NW>
+__device__ __forceinline__ long long hash_bin(const PeelDev& d, int c, const uint32_t (&kw)[NW]) {
+    long long j = 0;
+    const int8_t* mt = d.MT + (size_t)c * d.b * d.ld;
+    for (int i = 0; i < d.b; ++i) j = j * d.q + dot_mod<NW>(mt + (size_t)i * d.ld, d.ld, kw, d.q);
+    return j;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GF(p^s) helpers for the coded path; elements are ints whose base-p digits are polynomial coefficients.
+// ---------------------------------------------------------------------------------------------------------
+struct GF {
+    int p, s, order;
+    const int32_t* ex;
+    const int32_t* lg;
+    __device__ __forceinline__ int add(int a, int b) const {
+        int out = 0, w = 1;
+        for (int i = 0; i < s; ++i) {
+            int da = a % p, db = b % p;
+            a /= p; b /= p;
+            int v = da + db;
+            v = v >= p ? v - p : v;
+            out += v * w;
+            w *= p;
+        }
+        return out;
+    }
+    __device__ __forceinline__ int neg(int a) const {
+        int out = 0, w = 1;
+        for (int i = 0; i < s; ++i) {
+            int da = a % p;
+            a /= p;
+            out += (da ? p - da : 0) * w;
+            w *= p;
+        }
+        return out;
+    }
+    __device__ __forceinline__ int sub(int a, int b) const { return add(a, neg(b)); }
+    __device__ __forceinline__ int mul(int a, int b) const {
+        if (a == 0 || b == 0) return 0;
+        return __ldg(ex + __ldg(lg + a) + __ldg(lg + b));
+    }
+    __device__ __forceinline__ int inv(int a) const { return __ldg(ex + (order - 1 - __ldg(lg + a)) % (order - 1)); }
+    __device__ __forceinline__ int alpha_pow(int e) const {
+        e %= (order - 1);
+        if (e < 0) e += order - 1;
+        return __ldg(ex + e);
+    }
+};
+
+// Syndrome decode: sym (2ts symbols of Z_q) -> k digits (n), returns false on decoder failure (k left all zero,
+// like galois returning the unchanged zero codeword with n_errors = -1).
+__device__ bool rs_decode(const PeelDev& d, const uint8_t* sym, uint8_t* kout) {
+    GF F{d.q, d.rs_s, d.rs_order, d.rs_exp, d.rs_log};
+    const int t = d.rs_t, s = d.rs_s, n = d.n, nt = d.rs_order - 1;
+    const int T2 = 2 * t;
+    int S[RS_MAX_2T];
+    bool any = false;
+    for (int i = 0; i < T2; ++i) {
+        int v = 0;
+        for (int u = 0; u < s; ++u) v = v * d.q + sym[s * i + u];
+        S[i] = v;
+        any |= (v != 0);
+    }
+    for (int i = 0; i < n; ++i) kout[i] = 0;
+    if (!any) return true;
+    int Lam[RS_MAX_2T + 2], Bp[RS_MAX_2T + 2], Nw[RS_MAX_2T + 2];
+    for (int i = 0; i < T2 + 2; ++i) Lam[i] = Bp[i] = 0;
+    Lam[0] = Bp[0] = 1;
+    int L = 0, m = 1, bb = 1, lenL = 1, lenB = 1;
+    for (int r = 0; r < T2; ++r) {
+        int dd = S[r];
+        for (int i = 1; i <= L; ++i)
+            if (i < lenL) dd = F.add(dd, F.mul(Lam[i], S[r - i]));
+        if (dd == 0) {
+            ++m;
+            continue;
+        }
+        int coef = F.mul(dd, F.inv(bb));
+        int lenN = max(lenL, lenB + m);
+        if (lenN > T2 + 2) return false;
+        for (int i = 0; i < lenN; ++i) Nw[i] = i < lenL ? Lam[i] : 0;
+        for (int i = 0; i < lenB; ++i) Nw[i + m] = F.sub(Nw[i + m], F.mul(coef, Bp[i]));
+        if (2 * L <= r) {
+            for (int i = 0; i < lenL; ++i) Bp[i] = Lam[i];
+            lenB = lenL;
+            bb = dd;
+            L = r + 1 - L;
+            m = 1;
+        } else {
+            ++m;
+        }
+        for (int i = 0; i < lenN; ++i) Lam[i] = Nw[i];
+        lenL = lenN;
+    }
+    while (lenL > 1 && Lam[lenL - 1] == 0) --lenL;
+    const int deg = lenL - 1;
+    if (deg != L || deg > t || deg == 0) return false;
+    // Omega = S(x) Lambda(x) mod x^2t
+    int Om[RS_MAX_2T];
+    for (int a = 0; a < T2; ++a) {
+        int v = 0;
+        for (int i = 0; i <= deg && i <= a; ++i) v = F.add(v, F.mul(Lam[i], S[a - i]));
+        Om[a] = v;
+    }
+    int found = 0;
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) {
+        const int e = n - 1 - i;              // locator X = alpha^e for retained coordinate i
+        const int xinv = F.alpha_pow(-e);
+        int acc = 0, pw = 1;
+        for (int c = 0; c <= deg; ++c) {
+            acc = F.add(acc, F.mul(Lam[c], pw));
+            pw = F.mul(pw, xinv);
+        }
+        if (acc != 0) continue;
+        ++found;
+        int num = 0;
+        pw = 1;
+        for (int c = 0; c < T2; ++c) {
+            num = F.add(num, F.mul(Om[c], pw));
+            pw = F.mul(pw, xinv);
+        }
+        int den = 0;
+        pw = 1;
+        for (int c = 1; c <= deg; ++c) {
+            int term = 0;
+            for (int u = 0; u < c % d.q; ++u) term = F.add(term, Lam[c]);
+            den = F.add(den, F.mul(term, pw));
+            pw = F.mul(pw, xinv);
+        }
+        if (den == 0) {
+            ok = false;
+            break;
+        }
+        const int val = F.neg(F.mul(num, F.inv(den)));
+        if (val >= d.q) ok = false;            // error value must be in the prime subfield
+        kout[i] = (uint8_t)val;
+    }
+    (void)nt;
+    if (!ok || found != deg) {
+        for (int i = 0; i < n; ++i) kout[i] = 0;
+        return false;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// classification: one thread per bin
+// ---------------------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(K4_THREADS)
+k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, long long j_end,
+                   long long* __restrict__ find_cj, int8_t* __restrict__ find_k, float2* __restrict__ find_rho,
+                   int32_t* __restrict__ find_round, int32_t* __restrict__ find_id, long long max_finds, int round,
+                   unsigned long long* __restrict__ counters) {
+    __shared__ double2 s_tw[QSFT_MAX_Q + 1];   // w^t = (cos, sin)(2 pi t / q)
+    if (threadIdx.x < d.q) {
+        double sn, cs;
+        sincospi(2.0 * (double)threadIdx.x / (double)d.q, &sn, &cs);
+        s_tw[threadIdx.x] = make_double2(cs, sn);
+    }
+    __syncthreads();
+    const int c = blockIdx.y;
+    const long long j = j_begin + (long long)blockIdx.x * K4_THREADS + threadIdx.x;
+    if (j >= j_end) return;
+    const float2* Uc = U + (size_t)c * d.P * d.B + j;
+    const long long B = d.B;
+
+    // energy test (qsft.py:164)
+    double energy = 0.0;
+    for (int p = 0; p < d.P; ++p) {
+        float2 v = Uc[(size_t)p * B];
+        energy += (double)v.x * v.x + (double)v.y * v.y;
+    }
+    if (!(energy > d.thresh)) {
+        find_id[(size_t)c * B + j] = -1;
+        return;
+    }
+
+    // singleton detection -> symbols (reconstruct.py)
+    const int nsym = d.P_src - 1;
+    uint8_t sym[QSFT_MAX_N];
+    const double qd = (double)d.q;
+    if (d.channel == 0) {
+        float2 v0 = Uc[0];
+        const double a0 = atan2((double)v0.y, (double)v0.x);
+        for (int i = 1; i <= nsym; ++i) {
+            float2 v = Uc[(size_t)i * B];
+            const double a = atan2((double)v.y, (double)v.x);
+            const double val = qd * (a - a0) / kTwoPi;
+            long long r = (long long)rint(val);          // half-to-even like np.round
+            int m = (int)(r % d.q);
+            sym[i - 1] = (uint8_t)(m < 0 ? m + d.q : m);
+        }
+    } else {
+        const double step = kTwoPi / qd;
+        float2 zc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) zc[r] = r < d.R ? Uc[(size_t)(r * d.P_src) * B] : make_float2(0.f, 0.f);
+        for (int i = 1; i <= nsym; ++i) {
+            double ar = 0.0, ai = 0.0;
+            for (int r = 0; r < d.R; ++r) {
+                float2 z = r < 8 ? zc[r] : Uc[(size_t)(r * d.P_src) * B];
+                float2 v = Uc[(size_t)(r * d.P_src + i) * B];
+                // z * conj(v)
+                ar += (double)z.x * v.x + (double)z.y * v.y;
+                ai += (double)z.y * v.x - (double)z.x * v.y;
+            }
+            ar /= d.R;
+            ai /= d.R;
+            double th = atan2(ai, ar);
+            if (th < 0.0) th += kTwoPi;                  // numpy: angle % (2 pi)
+            if (th >= kTwoPi) th -= kTwoPi;
+            int best = 0;
+            double bd = fabs(0.0 - th);
+            for (int m = 1; m <= d.q; ++m) {
+                double dist = fabs(step * (double)m - th);
+                if (dist < bd) {
+                    bd = dist;
+                    best = m;
+                }
+            }
+            sym[i - 1] = (uint8_t)(best % d.q);
+        }
+    }
+    uint8_t kd[QSFT_MAX_N];
+    if (d.source == 1) {
+        rs_decode(d, sym, kd);
+    } else {
+        for (int i = 0; i < d.n; ++i) kd[i] = sym[i];
+    }
+    uint32_t kw[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            int i = 4 * w + t;
+            if (i < d.n) word |= (uint32_t)kd[i] << (8 * t);
+        }
+        kw[w] = word;
+    }
+
+    // rho = <signature, col> / P with signature_p = w^(D_p . k)  (qsft.py:174-175)
+    double rr = 0.0, ri = 0.0;
+    const int8_t* Dc = d.D + (size_t)c * d.P * d.ld;
+    for (int p = 0; p < d.P; ++p) {
+        const int t = dot_mod<NW>(Dc + (size_t)p * d.ld, d.ld, kw, d.q);
+        const double cs = s_tw[t].x, sn = s_tw[t].y;
+        float2 v = Uc[(size_t)p * B];
+        // conj(sig) * v
+        rr += cs * v.x + sn * v.y;
+        ri += cs * v.y - sn * v.x;
+    }
+    rr /= d.P;
+    ri /= d.P;
+    // ||col - rho sig||^2 = ||col||^2 - P |rho|^2 exactly (rho is the projection, |sig_p| = 1); fp64 keeps it accurate
+    const double res = energy - (double)d.P * (rr * rr + ri * ri);
+    const bool match = hash_bin<NW>(d, c, kw) == j;      // qsft.py:178-179
+    if (!match || res > d.thresh) {                      // qsft.py:183
+        find_id[(size_t)c * B + j] = -1;
+        atomicAdd(&counters[1], 1ull);
+        return;
+    }
+    const unsigned long long f = atomicAdd(&counters[0], 1ull);
+    if ((long long)f < max_finds) {
+        find_cj[f] = (long long)c * B + j;
+        uint32_t* ko = reinterpret_cast<uint32_t*>(find_k + (size_t)f * d.ld);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) ko[w] = kw[w];
+        for (int w = NW; w < d.ld / 4; ++w) ko[w] = 0;
+        find_rho[f] = make_float2((float)rr, (float)ri);
+        if (find_round) find_round[f] = round;
+        find_id[(size_t)c * B + j] = (int32_t)f;
+    } else {
+        find_id[(size_t)c * B + j] = -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// apply: one warp per find
+// ---------------------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(K4_THREADS)
+k4_apply_kernel(PeelDev d, float2* __restrict__ U, long long j_begin, long long j_end,
+                const long long* __restrict__ find_cj, const int8_t* __restrict__ find_k,
+                const float2* __restrict__ find_rho, const int32_t* __restrict__ find_id, long long f_begin,
+                long long n_finds, long long id_limit, int dedupe, unsigned long long* __restrict__ owner_count) {
+    const int lane = threadIdx.x & 31;
+    const long long f = f_begin + (long long)blockIdx.x * (K4_THREADS / 32) + (threadIdx.x >> 5);
+    if (f >= f_begin + n_finds) return;
+    const long long cj = find_cj[f];
+    const int c = (int)(cj / d.B);
+    uint32_t kw[NW];
+    const uint32_t* kin = reinterpret_cast<const uint32_t*>(find_k + (size_t)f * d.ld);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) kw[w] = (w < d.ld / 4) ? kin[w] : 0u;
+
+    if (dedupe) {
+        // ball_values "last (i, j) wins" (qsft.py:215): skip when a higher group found the same k this round
+        for (int c2 = c + 1; c2 < d.C; ++c2) {
+            const long long j2 = hash_bin<NW>(d, c2, kw);
+            const int32_t f2 = find_id[(size_t)c2 * d.B + j2];
+            if (f2 >= 0 && (long long)f2 < id_limit) {
+                const uint32_t* k2 = reinterpret_cast<const uint32_t*>(find_k + (size_t)f2 * d.ld);
+                bool same = true;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) same &= ((w < d.ld / 4) ? k2[w] : 0u) == kw[w];
+                if (same) return;
+            }
+        }
+    }
+    if (owner_count && lane == 0) atomicAdd(owner_count, 1ull);   // distinct balls peeled (num_peeling, qsft.py:224)
+    const float2 rho = find_rho[f];
+    const double qd = (double)d.q;
+    for (int l = 0; l < d.C; ++l) {
+        const long long j = hash_bin<NW>(d, l, kw);
+        if (j < j_begin || j >= j_end) continue;
+        float2* Ul = U + (size_t)l * d.P * d.B + j;
+        const int8_t* Dl = d.D + (size_t)l * d.P * d.ld;
+        for (int p = lane; p < d.P; p += 32) {
+            const int t = dot_mod<NW>(Dl + (size_t)p * d.ld, d.ld, kw, d.q);
+            float sn, cs;
+            sincospif(2.0f * (float)t / (float)qd, &sn, &cs);
+            // rho * w^t
+            const float vr = rho.x * cs - rho.y * sn;
+            const float vi = rho.x * sn + rho.y * cs;
+            float* dst = reinterpret_cast<float*>(Ul + (size_t)p * d.B);
+            atomicAdd(dst, -vr);
+            atomicAdd(dst + 1, -vi);
+        }
+    }
+}
+
+__global__ void k4_closed_form_kernel(const int8_t* __restrict__ MT, const int8_t* __restrict__ D, int q, int n, int b,
+                                      int P, long long B, int ld, const int8_t* __restrict__ loc,
+                                      const float2* __restrict__ a, long long S, float2* __restrict__ U) {
+    const int lane = threadIdx.x & 31;
+    const long long s = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (s >= S) return;
+    const int8_t* k = loc + (size_t)s * ld;
+    long long j = 0;
+    for (int i = 0; i < b; ++i) {
+        int acc = 0;
+        for (int u = 0; u < n; ++u) acc += (int)MT[(size_t)i * ld + u] * (int)k[u];
+        j = j * q + acc % q;
+    }
+    const float2 as = a[s];
+    for (int p = lane; p < P; p += 32) {
+        int acc = 0;
+        for (int u = 0; u < n; ++u) acc += (int)D[(size_t)p * ld + u] * (int)k[u];
+        float sn, cs;
+        sincospif(2.0f * (float)(acc % q) / (float)q, &sn, &cs);
+        float* dst = reinterpret_cast<float*>(U + (size_t)p * B + j);
+        atomicAdd(dst, as.x * cs - as.y * sn);
+        atomicAdd(dst + 1, as.x * sn + as.y * cs);
+    }
+}
+
+int make_dev(const qsft_peel_desc* h, PeelDev* d) {
+    QSFT_CHECK_ARG(h != nullptr, "null descriptor");
+    QSFT_CHECK_ARG(h->q >= 2 && h->q <= QSFT_MAX_Q, "q=%d out of range", h->q);
+    QSFT_CHECK_ARG(h->n >= 1 && h->n <= QSFT_MAX_N, "n=%d out of range", h->n);
+    QSFT_CHECK_ARG(h->b >= 1 && h->b <= QSFT_MAX_B, "b=%d out of range", h->b);
+    QSFT_CHECK_ARG(h->C >= 1 && h->C <= 65535, "C=%d out of range", h->C);
+    QSFT_CHECK_ARG(h->P_src >= 2 && h->P >= h->P_src && h->P % h->P_src == 0, "P=%d must be a positive multiple of P_src=%d", h->P, h->P_src);
+    QSFT_CHECK_ARG(h->channel == 0 || h->channel == 1, "channel must be 0 (identity) or 1 (nso)");
+    QSFT_CHECK_ARG(h->source == 0 || h->source == 1, "source must be 0 (identity) or 1 (coded)");
+    QSFT_CHECK_ARG(h->ld >= h->n && h->ld % 16 == 0 && h->ld <= 128, "ld=%d must be >= n, a multiple of 16 and <= 128", h->ld);
+    QSFT_CHECK_ARG(h->MT && h->D, "null M/D");
+    if (h->channel == 0) QSFT_CHECK_ARG(h->P == h->P_src, "identity channel decoding needs num_repeat == 1");
+    if (h->source == 0) {
+        QSFT_CHECK_ARG(h->P_src - 1 == h->n, "identity source decoding needs P_src = n + 1 (got P_src=%d, n=%d)", h->P_src, h->n);
+    } else {
+        QSFT_CHECK_ARG(h->rs_t >= 1 && 2 * h->rs_t <= RS_MAX_2T && h->rs_s >= 1, "bad Reed-Solomon parameters");
+        QSFT_CHECK_ARG(h->P_src - 1 == 2 * h->rs_t * h->rs_s, "coded source needs P_src = 2ts + 1");
+        QSFT_CHECK_ARG(h->P_src - 1 <= QSFT_MAX_N, "too many syndrome symbols");
+        QSFT_CHECK_ARG(h->rs_exp && h->rs_log, "null GF tables");
+    }
+    d->q = h->q; d->n = h->n; d->b = h->b; d->C = h->C; d->P = h->P; d->P_src = h->P_src; d->R = h->P / h->P_src;
+    d->channel = h->channel; d->source = h->source; d->rs_t = h->rs_t; d->rs_s = h->rs_s; d->ld = h->ld;
+    d->B = ipow64(h->q, h->b);
+    d->thresh = (double)h->cutoff * (double)h->P;
+    d->MT = h->MT; d->D = h->D; d->rs_exp = h->rs_exp; d->rs_log = h->rs_log;
+    d->rs_order = h->source ? (int)ipow64(h->q, h->rs_s) : 0;
+    return QSFT_OK;
+}
+
+template <int NW>
+int classify_nw(const PeelDev& d, const float2* U, long long jb, long long je, long long* cj, int8_t* fk, float2* rho,
+                int32_t* frd, int32_t* fid, long long maxf, int round, unsigned long long* counters, cudaStream_t st) {
+    dim3 grid((unsigned)((je - jb + K4_THREADS - 1) / K4_THREADS), (unsigned)d.C);
+    k4_classify_kernel<NW><<<grid, K4_THREADS, 0, st>>>(d, U, jb, je, cj, fk, rho, frd, fid, maxf, round, counters);
+    QSFT_LAUNCHED();
+    return QSFT_OK;
+}
+
+template <int NW>
+int apply_nw(const PeelDev& d, float2* U, long long jb, long long je, const long long* cj, const int8_t* fk,
+             const float2* rho, const int32_t* fid, long long f_begin, long long nf, long long id_limit, int dedupe,
+             unsigned long long* owners, cudaStream_t st) {
+    const int wpb = K4_THREADS / 32;
+    k4_apply_kernel<NW><<<(unsigned)((nf + wpb - 1) / wpb), K4_THREADS, 0, st>>>(d, U, jb, je, cj, fk, rho, fid, f_begin,
+                                                                               nf, id_limit, dedupe, owners);
+    QSFT_LAUNCHED();
+    return QSFT_OK;
+}
+
+#define QSFT_NW_DISPATCH(fn, ...)                          \
+    do {                                                   \
+        const int nw__ = d.ld / 4;                         \
+        if (nw__ <= 4) return fn<4>(__VA_ARGS__);          \
+        if (nw__ <= 8) return fn<8>(__VA_ARGS__);          \
+        if (nw__ <= 16) return fn<16>(__VA_ARGS__);        \
+        return fn<32>(__VA_ARGS__);                        \
+    } while (0)
+
+int do_classify(const PeelDev& d, const float2* U, long long jb, long long je, long long* cj, int8_t* fk, float2* rho,
+                int32_t* frd, int32_t* fid, long long maxf, int round, unsigned long long* counters, cudaStream_t st) {
+    QSFT_NW_DISPATCH(classify_nw, d, U, jb, je, cj, fk, rho, frd, fid, maxf, round, counters, st);
+}
+
+int do_apply(const PeelDev& d, float2* U, long long jb, long long je, const long long* cj, const int8_t* fk,
+             const float2* rho, const int32_t* fid, long long f_begin, long long nf, long long id_limit, int dedupe,
+             unsigned long long* owners, cudaStream_t st) {
+    QSFT_NW_DISPATCH(apply_nw, d, U, jb, je, cj, fk, rho, fid, f_begin, nf, id_limit, dedupe, owners, st);
+}
+
+}  // namespace
+
+extern "C" int qsft_peel_classify(const qsft_peel_desc* h, const float* U, int64_t j_begin, int64_t j_end,
+                                  int64_t* find_cj, int8_t* find_k, float* find_rho, int32_t* find_round,
+                                  int32_t* find_id, int64_t max_finds, int round, unsigned long long* counters,
+                                  void* stream) {
+    PeelDev d;
+    if (int rc = make_dev(h, &d)) return rc;
+    QSFT_CHECK_ARG(U && find_cj && find_k && find_rho && find_id && counters, "null pointer");
+    QSFT_CHECK_ARG(0 <= j_begin && j_begin <= j_end && j_end <= d.B, "bad bin range");
+    if (j_begin == j_end) return QSFT_OK;
+    return do_classify(d, reinterpret_cast<const float2*>(U), j_begin, j_end, (long long*)find_cj, find_k,
+                       reinterpret_cast<float2*>(find_rho), find_round, find_id, max_finds, round, counters,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int qsft_peel_apply(const qsft_peel_desc* h, float* U, int64_t j_begin, int64_t j_end,
+                               const int64_t* find_cj, const int8_t* find_k, const float* find_rho,
+                               const int32_t* find_id, int64_t f_begin, int64_t n_finds, int dedupe,
+                               unsigned long long* owner_count, void* stream) {
+    PeelDev d;
+    if (int rc = make_dev(h, &d)) return rc;
+    QSFT_CHECK_ARG(U && find_cj && find_k && find_rho && (find_id || !dedupe), "null pointer");
+    QSFT_CHECK_ARG(0 <= j_begin && j_begin <= j_end && j_end <= d.B, "bad bin range");
+    QSFT_CHECK_ARG(f_begin >= 0, "negative f_begin");
+    if (n_finds <= 0) return QSFT_OK;
+    return do_apply(d, reinterpret_cast<float2*>(U), j_begin, j_end, (const long long*)find_cj, find_k,
+                    reinterpret_cast<const float2*>(find_rho), find_id, f_begin, n_finds, f_begin + n_finds, dedupe,
+                    owner_count, (cudaStream_t)stream);
+}
+
+extern "C" int qsft_peel(const qsft_peel_desc* h, float* U, int64_t* find_cj, int8_t* find_k, float* find_rho,
+                         int32_t* find_round, int32_t* find_id, int64_t max_finds, unsigned long long* counters,
+                         int64_t* n_finds_out, int* n_rounds_out, void* stream) {
+    PeelDev d;
+    if (int rc = make_dev(h, &d)) return rc;
+    QSFT_CHECK_ARG(U && find_cj && find_k && find_rho && find_round && find_id && counters && n_finds_out && n_rounds_out,
+                   "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    // `num_peeling < q ** n` (qsft.py:151) can only bind when q^n is tiny: at most C*B balls are peeled per round
+    const double peeling_max = pow((double)d.q, (double)d.n);
+    const bool guard_can_bind = peeling_max <= 15.0 * (double)d.C * (double)d.B;
+    unsigned long long* host = nullptr;
+    QSFT_CUDA(cudaMallocHost(&host, 4 * sizeof(unsigned long long)));
+    long long total = 0;
+    double num_peeling = 0;
+    int round = 0;
+    int rc = QSFT_OK;
+    cudaError_t ce = cudaSuccess;
+    bool cont = true;
+    // counters: [0] finds (running), [1] multitons of the round, [2] distinct balls peeled (running)
+    ce = cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st);
+    while (ce == cudaSuccess && rc == QSFT_OK && cont && num_peeling < peeling_max && round < 15) {
+        ++round;
+        if ((ce = cudaMemsetAsync(counters + 1, 0, sizeof(unsigned long long), st)) != cudaSuccess) break;
+        if ((rc = do_classify(d, reinterpret_cast<const float2*>(U), 0, d.B, (long long*)find_cj, find_k,
+                              reinterpret_cast<float2*>(find_rho), find_round, find_id, max_finds, round, counters, st)) != 0) break;
+        if ((ce = cudaMemcpyAsync(host, counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+        if ((ce = cudaStreamSynchronize(st)) != cudaSuccess) break;
+        const long long now = (long long)host[0];
+        const long long multis = (long long)host[1];
+        if (now > max_finds) {
+            cudaFreeHost(host);
+            qsft_set_error("find buffer too small: %lld finds > max_finds=%lld", now, (long long)max_finds);
+            return QSFT_EINVAL;
+        }
+        const long long nf = now - total;
+        if (multis == 0 || nf == 0) cont = false;          // qsft.py:204-205
+        // the reference also subtracts after its last round, but nothing reads U afterwards: skip unless the q^n guard needs the count
+        if (nf > 0 && (cont || guard_can_bind)) {
+            if ((rc = do_apply(d, reinterpret_cast<float2*>(U), 0, d.B, (const long long*)find_cj, find_k,
+                               reinterpret_cast<const float2*>(find_rho), find_id, total, nf, now, 1, counters + 2, st)) != 0) break;
+            if (guard_can_bind) {
+                if ((ce = cudaMemcpyAsync(host + 2, counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+                if ((ce = cudaStreamSynchronize(st)) != cudaSuccess) break;
+                num_peeling = (double)host[2];
+            }
+        }
+        total = now;
+    }
+    cudaFreeHost(host);
+    if (ce != cudaSuccess) {
+        qsft_set_error("CUDA error in peel loop: %s", cudaGetErrorString(ce));
+        return QSFT_ECUDA;
+    }
+    if (rc != QSFT_OK) return rc;
+    *n_finds_out = total;
+    *n_rounds_out = round;
+    return QSFT_OK;
+}
+
+extern "C" int qsft_closed_form_bins(const int8_t* MT, const int8_t* D, int q, int n, int b, int P, const int8_t* loc,
+                                     int ld, const float* strengths, int64_t S, float* U, void* stream) {
+    QSFT_CHECK_ARG(MT && D && loc && strengths && U, "null pointer");
+    QSFT_CHECK_ARG(q >= 2 && q <= QSFT_MAX_Q && n >= 1 && n <= QSFT_MAX_N && b >= 1 && b <= QSFT_MAX_B && P >= 1, "bad shape");
+    QSFT_CHECK_ARG(ld >= n && ld % 16 == 0, "bad ld");
+    if (S <= 0) return QSFT_OK;
+    const int wpb = 4;
+    k4_closed_form_kernel<<<(unsigned)((S + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        MT, D, q, n, b, P, ipow64(q, b), ld, loc, reinterpret_cast<const float2*>(strengths), S,
+        reinterpret_cast<float2*>(U));
+    QSFT_LAUNCHED();
+    return QSFT_OK;
+}

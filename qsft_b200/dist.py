@@ -1,0 +1,101 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL on the GPU box, gloo in the CPU tests).
+
+Sharding: the C*R*P_src delay rows are independent for sampling + FFT -> block partitioned over ranks;
+U is all-gathered once; peeling is bin-sharded (each rank classifies and updates bins j in its range of every
+group) with ONE all-gather of the round's finds per round -- the only collective type on the path."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+
+class DistContext:
+    def __init__(self, group=None):
+        if not td.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group
+        self.rank = td.get_rank(group)
+        self.world_size = td.get_world_size(group)
+
+    def all_gather_rows_(self, buf, rows_per_rank):
+        """buf (world*rows_per_rank, W): every rank has filled its own row block; gather all blocks in place."""
+        mine = buf[self.rank * rows_per_rank:(self.rank + 1) * rows_per_rank].clone()
+        flat = torch.view_as_real(buf) if buf.is_complex() else buf
+        minef = torch.view_as_real(mine) if mine.is_complex() else mine
+        td.all_gather_into_tensor(flat.reshape(-1), minef.reshape(-1), group=self.group)
+
+    def all_gather_var(self, tensors, count, cap):
+        """All-gather `count` leading rows of each tensor in `tensors` (fixed capacity `cap` per rank).
+        Returns (list of concatenated tensors, counts per rank)."""
+        dev = tensors[0].device
+        cnt = torch.tensor([count], dtype=torch.int64, device=dev)
+        counts = torch.empty(self.world_size, dtype=torch.int64, device=dev)
+        td.all_gather_into_tensor(counts, cnt, group=self.group)
+        counts = counts.cpu().tolist()
+        m = max(counts)
+        outs = []
+        for t in tensors:
+            real = torch.view_as_real(t) if t.is_complex() else t
+            send = real[:m].contiguous()
+            recv = torch.empty((self.world_size,) + tuple(send.shape), dtype=send.dtype, device=dev)
+            td.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+            parts = [recv[r, :counts[r]] for r in range(self.world_size)]
+            cat = torch.cat(parts, dim=0)
+            outs.append(torch.view_as_complex(cat) if t.is_complex() else cat)
+        return outs, counts
+
+    def barrier(self):
+        td.barrier(group=self.group)
+
+
+def bin_range(B, rank, world):
+    per = -(-B // world)
+    lo = min(B, rank * per)
+    return lo, min(B, lo + per)
+
+
+def peel_sharded(prob, U, dist, max_rounds=15):
+    """Bin-sharded peeling loop (qsft.py:151-241 semantics).  Every rank holds the full U but only classifies and
+    updates bins in its own j-range; finds are exchanged with one all-gather per round.
+    Returns (cj, k, rho, round, n_rounds) as NumPy arrays, identical on every rank."""
+    q, n, C, B = prob.q, prob.n, prob.C, prob.B
+    dev = prob.device
+    jb, je = bin_range(B, dist.rank, dist.world_size)
+    cap = max(1024, 2 * C * (je - jb))
+    prob.alloc(max_finds=cap)
+    find_id_full = torch.empty((C, B), dtype=torch.int32, device=dev)
+    all_cj, all_k, all_rho, all_round = [], [], [], []
+    peeling_max = float(q) ** n
+    num_peeling, rnd, cont = 0, 0, True
+    while cont and num_peeling < peeling_max and rnd < max_rounds:
+        rnd += 1
+        prob.counters.zero_()
+        prob.classify(U, jb, je, rnd)
+        cnts = prob.counters.cpu().tolist()
+        nf_local, multi_local = int(cnts[0]), int(cnts[1])
+        if nf_local > cap:
+            raise RuntimeError("find buffer overflow in sharded peel")
+        (cj, k, rho), counts = dist.all_gather_var([prob.find_cj, prob.find_k, prob.find_rho], nf_local, cap)
+        tot = torch.tensor([multi_local], dtype=torch.int64, device=dev)
+        td.all_reduce(tot, group=dist.group)          # number of multitons this round (scalar; stop rule only)
+        nf = int(sum(counts))
+        if int(tot.item()) == 0 or nf == 0:
+            cont = False
+        if nf > 0:
+            all_cj.append(cj.cpu().numpy())
+            all_k.append(k[:, :n].cpu().numpy())
+            all_rho.append(rho.cpu().numpy())
+            all_round.append(np.full(nf, rnd, dtype=np.int32))
+            if cont:
+                # rebuild the (C, B) find table for the whole round so "last (i, j) wins" can be checked locally
+                find_id_full.fill_(-1)
+                find_id_full.view(-1)[cj] = torch.arange(nf, dtype=torch.int32, device=dev)
+                owners = torch.zeros(1, dtype=torch.int64, device=dev)
+                prob.apply(U, jb, je, cj.contiguous(), k.contiguous(), rho.contiguous(), find_id_full, 0, nf,
+                           dedupe=True, owner_count=owners)
+                if peeling_max <= 15.0 * C * B:
+                    num_peeling += int(owners.item())
+    if all_cj:
+        return (np.concatenate(all_cj), np.concatenate(all_k), np.concatenate(all_rho), np.concatenate(all_round), rnd)
+    return (np.zeros(0, np.int64), np.zeros((0, n), np.int8), np.zeros(0, np.complex64), np.zeros(0, np.int32), rnd)

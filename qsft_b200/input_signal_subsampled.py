@@ -1,0 +1,220 @@
+"""SubsampledSignal: query generation -> sampling -> batched q-ary DFT, on the GPU.
+
+Drop-in for qsft/input_signal_subsampled.py:12-269: same constructor kwargs / query_args keys, same attributes
+(Ms, Ds, Us, transformTimes, ...), same get_MDU / get_source_parity, same abstract subsample(query_indices).
+Differences that matter to callers:
+  * Us[i][j][b] is a CUDA complex64 tensor (P_src, q^b) (a view into one HBM-resident buffer) instead of a list
+    of NumPy complex128 rows.
+  * subclasses that can evaluate on the device set `device_subsample = True` and implement
+    `subsample_device(digits, idx)`; otherwise subsample() is called with host Python ints exactly like the
+    reference (K1 still generates the indices on the GPU).
+  * `dist=` (qsft_b200.dist.DistContext) shards the delay rows over ranks; U is all-gathered once at the end.
+"""
+from __future__ import annotations
+
+import random
+import time
+from math import floor
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import ops
+from .input_signal import Signal
+from .query import get_Ms_and_Ds
+from .utils import index_limbs, limbs_to_ints, load_data, padded_ld, qary_ints, save_data
+
+
+class SubsampledSignal(Signal):
+    device_subsample = False
+
+    def _set_params(self, **kwargs):
+        self.n = kwargs.get("n")
+        self.q = kwargs.get("q")
+        self.N = self.q ** self.n
+        self.signal_w = kwargs.get("signal_w")
+        self.query_args = kwargs.get("query_args")
+        self.b = self.query_args.get("b")
+        self.all_bs = self.query_args.get("all_bs", [self.b])
+        self.num_subsample = self.query_args.get("num_subsample")
+        if "num_repeat" not in self.query_args:
+            self.query_args["num_repeat"] = 1
+        self.num_repeat = self.query_args.get("num_repeat")
+        self.subsampling_method = self.query_args.get("subsampling_method")
+        self.delays_method_source = self.query_args.get("delays_method_source")
+        self.delays_method_channel = self.query_args.get("delays_method_channel")
+        self.L = None
+        self.foldername = kwargs.get("folder")
+        dev = kwargs.get("device")
+        if dev is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("qsft_b200 needs a CUDA device (there is no CPU fallback)")
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(dev)
+        self.dist = kwargs.get("dist")
+        self.ld = padded_ld(self.n)
+        self.limbs = index_limbs(self.q, self.n)
+        self.sample_time = 0.0
+
+    def _init_signal(self):
+        if self.subsampling_method == "uniform":
+            self._subsample_uniform()
+        else:
+            self._set_Ms_and_Ds_qsft()
+            self._subsample_qsft()
+
+    # ------------------------------------------------------------------------------------------------
+    def _set_Ms_and_Ds_qsft(self):
+        """Ms / Ds from `folder`/Ms_and_Ds.pickle when present (reference cache format), else generated."""
+        if self.foldername:
+            Path(f"{self.foldername}").mkdir(exist_ok=True)
+            path = Path(f"{self.foldername}/Ms_and_Ds.pickle")
+            if path.is_file():
+                self.Ms, self.Ds = load_data(path)
+            else:
+                self.Ms, self.Ds = get_Ms_and_Ds(self.n, self.q, **self.query_args)
+                save_data((self.Ms, self.Ds), path)
+        else:
+            self.Ms, self.Ds = get_Ms_and_Ds(self.n, self.q, **self.query_args)
+
+    def _row_shard(self, total_rows):
+        """Contiguous slice of the flattened (c, r, p) delay rows owned by this rank."""
+        if self.dist is None or self.dist.world_size == 1:
+            return 0, total_rows, total_rows
+        per = -(-total_rows // self.dist.world_size)
+        lo = min(total_rows, self.dist.rank * per)
+        return lo, min(total_rows, lo + per), per
+
+    def _subsample_qsft(self):
+        """Sample + transform every (M_i, D_ij) block (input_signal_subsampled.py:107-155)."""
+        C, R = len(self.Ms), len(self.Ds[0])
+        P_src = self.Ds[0][0].shape[0]
+        B = self.q ** self.b
+        G = C * R * P_src
+        lo, hi, per = self._row_shard(G)
+        world = 1 if self.dist is None else self.dist.world_size
+        rows_alloc = per * world
+        dev = self.device
+        # one HBM buffer per b: rows = flattened (c, r, p), padded to a multiple of the world size
+        self._Ubuf = {bb: torch.zeros((rows_alloc, self.q ** bb), dtype=torch.complex64, device=dev) for bb in self.all_bs}
+        self.Us = [[{} for _ in range(R)] for _ in range(C)]
+        self.transformTimes = [[{} for _ in range(R)] for _ in range(C)]
+        events = []
+        t_sample0 = time.time()
+        for i in range(C):
+            for j in range(R):
+                g0 = (i * R + j) * P_src
+                p0, p1 = max(lo, g0) - g0, min(hi, g0 + P_src) - g0
+                if p1 > p0:
+                    samples = self._sample_rows(self.Ms[i], np.asarray(self.Ds[i][j])[p0:p1])       # (p1-p0, B)
+                    for bb in self.all_bs:
+                        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        ev0.record()
+                        self._Ubuf[bb][g0 + p0:g0 + p1] = self._compute_subtransform(samples, bb)
+                        ev1.record()
+                        events.append((i, j, bb, ev0, ev1))
+                    del samples
+        if world > 1:
+            for bb in self.all_bs:
+                self.dist.all_gather_rows_(self._Ubuf[bb], per)
+        torch.cuda.synchronize(dev)
+        fft_total = 0.0
+        for i in range(C):
+            for j in range(R):
+                g0 = (i * R + j) * P_src
+                for bb in self.all_bs:
+                    self.Us[i][j][bb] = self._Ubuf[bb][g0:g0 + P_src]
+                    self.transformTimes[i][j][bb] = 0.0
+        for (i, j, bb, ev0, ev1) in events:
+            dt = ev0.elapsed_time(ev1) * 1e-3
+            self.transformTimes[i][j][bb] += dt
+            fft_total += dt
+        self.sample_time = time.time() - t_sample0 - fft_total
+
+    def _sample_rows(self, M, D_rows):
+        """Samples of the lattices {M l + d_p} for the given delay rows -> complex64 tensor (rows, B)."""
+        B = self.q ** self.b
+        rows = D_rows.shape[0]
+        if self.device_subsample:
+            idx, dig = ops.query_lattice(M, D_rows, self.q, device=self.device, want_idx=False, want_digits=True,
+                                         ld=self.ld)
+            return self.subsample_device(dig.view(rows * B, self.ld)).view(rows, B)
+        # generic black-box signal: indices to the host as Python ints, user callback, upload (host bound by design)
+        query_indices = self._get_qsft_query_indices(M, D_rows)
+        out = np.zeros((rows, B), dtype=complex)
+        if B > 10000:
+            for k in range(rows):
+                out[k] = self.subsample(query_indices[k])
+        else:
+            flat = np.asarray(self.subsample(np.concatenate(query_indices)))
+            out[:] = flat.reshape(rows, B)
+        return torch.from_numpy(out.astype(np.complex64)).to(self.device)
+
+    def _compute_subtransform(self, samples, b):
+        """gwht of every row restricted to the sub-lattice of the first b columns of M
+        (input_signal_subsampled.py:264-266): stride q^(self.b - b), then the b-dimensional DFT."""
+        if b == self.b:
+            x = samples.clone() if len(self.all_bs) > 1 else samples
+        else:
+            x = samples[:, :: self.q ** (self.b - b)].contiguous()
+        return ops.gwht_batch_(x, self.q, b)
+
+    # ------------------------------------------------------------------------------------------------
+    def _subsample_uniform(self):
+        """Uniform random sampling (for LASSO-style consumers; input_signal_subsampled.py:157-173)."""
+        if self.foldername:
+            Path(f"{self.foldername}").mkdir(exist_ok=True)
+        sample_file = Path(f"{self.foldername}/signal_t.pickle")
+        if self.foldername and sample_file.is_file():
+            signal_t = load_data(sample_file)
+        else:
+            query_indices = self._get_random_query_indices(self.query_args["n_samples"])
+            samples = self.subsample(query_indices)
+            signal_t = dict(zip(query_indices, samples))
+            if self.foldername:
+                save_data(signal_t, sample_file)
+        self.signal_t = signal_t
+
+    def get_all_qary_vectors(self):
+        if self.L is None:
+            self.L = np.array(qary_ints(self.b, self.q))
+        return self.L
+
+    def subsample(self, query_indices):
+        raise NotImplementedError
+
+    def _get_qsft_query_indices(self, M, D_sub):
+        """List (one entry per delay row) of object arrays of Python-int decimal indices -- computed by K1 on the
+        GPU, bit-exact with the reference (input_signal_subsampled.py:183-206)."""
+        idx, _ = ops.query_lattice(M, D_sub, self.q, device=self.device, want_idx=True, want_digits=False,
+                                   limbs=self.limbs)
+        host = idx.cpu().numpy().view(np.uint64)
+        return [limbs_to_ints(host[p]) for p in range(host.shape[0])]
+
+    def _get_random_query_indices(self, n_samples):
+        return [floor(random.uniform(0, 1) * self.N) for _ in range(n_samples)]
+
+    def get_MDU(self, ret_num_subsample, ret_num_repeat, b, trans_times=False):
+        """Effective Ms, Ds, Us for the decoder: random sub-selection of groups / repeats
+        (input_signal_subsampled.py:225-262; consumes np.random.choice twice like the reference)."""
+        Ms_ret, Ds_ret, Us_ret, Ts_ret = [], [], [], []
+        if ret_num_subsample <= self.num_subsample and ret_num_repeat <= self.num_repeat and b <= self.b:
+            subsample_idx = np.random.choice(self.num_subsample, ret_num_subsample, replace=False)
+            delay_idx = np.random.choice(self.num_repeat, ret_num_repeat, replace=False)
+            for i in subsample_idx:
+                Ms_ret.append(self.Ms[i][:, :b])
+                Ds_ret.append([])
+                Us_ret.append([])
+                Ts_ret.append([])
+                for j in delay_idx:
+                    Ds_ret[-1].append(self.Ds[i][j])
+                    Us_ret[-1].append(self.Us[i][j][b])
+                    Ts_ret[-1].append(self.transformTimes[i][j][b])
+            if trans_times:
+                return Ms_ret, Ds_ret, Us_ret, Ts_ret
+            return Ms_ret, Ds_ret, Us_ret
+        raise ValueError("There are not enough Ms or Ds.")
+
+    def get_source_parity(self):
+        return self.Ds[0][0].shape[0]

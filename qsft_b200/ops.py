@@ -1,0 +1,206 @@
+"""Thin Python wrappers over the C ABI (include/qsft_b200.h).  PyTorch tensors are used ONLY as device buffers
+(data_ptr) and for the current CUDA stream; every computation happens in libqsft_b200.so.  No fallbacks."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .utils import index_limbs, padded_ld
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise ValueError("expected contiguous CUDA tensors")
+
+
+def pad_digits(rows, ld, device):
+    """(N, n) integer digit rows (numpy / tensor) -> zero padded int8 device tensor (N, ld)."""
+    a = np.asarray(rows)
+    out = np.zeros((a.shape[0], ld), dtype=np.int8)
+    out[:, : a.shape[1]] = a
+    return torch.from_numpy(out).to(device)
+
+
+def query_lattice(M, D, q, *, device, want_idx=True, want_digits=False, limbs=None, ld=None):
+    """K1.  M (n, b), D (P, n) integer arrays.  Returns (idx, dig): idx int64 tensor (P, B) or (P, B, 2) holding the
+    uint64 limbs (hi, lo) bit patterns, dig int8 (P, B, ld)."""
+    M = np.ascontiguousarray(M, dtype=np.int8)
+    D = np.ascontiguousarray(D, dtype=np.int8)
+    n, b = M.shape
+    P = D.shape[0]
+    if D.shape[1] != n:
+        raise ValueError("D must have n columns")
+    B = q ** b
+    limbs = limbs or index_limbs(q, n)
+    ld = ld or padded_ld(n)
+    Md, Dd = torch.from_numpy(M).to(device), torch.from_numpy(D).to(device)
+    idx = dig = None
+    if want_idx:
+        idx = torch.empty((P, B) if limbs == 1 else (P, B, 2), dtype=torch.int64, device=device)
+    if want_digits:
+        dig = torch.empty((P, B, ld), dtype=torch.int8, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().qsft_query_lattice(_ptr(Md), _ptr(Dd), q, n, b, P, _ptr(idx), limbs, _ptr(dig), ld, _stream()))
+    return idx, dig
+
+
+def dec_to_qary(idx, q, n, ld=None):
+    """idx: int64 tensor (N,) or (N, 2) of uint64 limb bit patterns -> int8 digit rows (N, ld)."""
+    _need_cuda(idx)
+    limbs = 2 if idx.dim() == 2 else 1
+    N = idx.shape[0]
+    ld = ld or padded_ld(n)
+    dig = torch.empty((N, ld), dtype=torch.int8, device=idx.device)
+    with torch.cuda.device(idx.device):
+        _lib.check(_lib.lib().qsft_dec_to_qary(_ptr(idx), limbs, N, q, n, _ptr(dig), ld, _stream()))
+    return dig
+
+
+def qary_to_dec(dig, q, n, limbs=None):
+    _need_cuda(dig)
+    N, ld = dig.shape
+    limbs = limbs or index_limbs(q, n)
+    idx = torch.empty((N,) if limbs == 1 else (N, 2), dtype=torch.int64, device=dig.device)
+    with torch.cuda.device(dig.device):
+        _lib.check(_lib.lib().qsft_qary_to_dec(_ptr(dig), ld, N, q, n, _ptr(idx), limbs, _stream()))
+    return idx
+
+
+def eval_synth(qdig, loc, strengths, q, n, out=None, impl=0):
+    """K2.  qdig (N, ld) int8, loc (S, ld) int8, strengths (S,) complex64 -> (N,) complex64."""
+    _need_cuda(qdig, loc, strengths)
+    N, ld = qdig.shape
+    S = loc.shape[0]
+    if S and loc.shape[1] != ld:
+        raise ValueError("query and support digit rows must share the row stride")
+    if strengths.dtype != torch.complex64:
+        raise ValueError("strengths must be complex64")
+    if out is None:
+        out = torch.empty((N,), dtype=torch.complex64, device=qdig.device)
+    with torch.cuda.device(qdig.device):
+        _lib.check(_lib.lib().qsft_eval_synth(_ptr(qdig), N, _ptr(loc), _ptr(strengths), S, q, n, ld, _ptr(out), impl, _stream()))
+    return out
+
+
+def gwht_batch_(x, q, b):
+    """K3, in place.  x (..., q^b) complex64 contiguous."""
+    _need_cuda(x)
+    if x.dtype != torch.complex64 or x.shape[-1] != q ** b:
+        raise ValueError("x must be complex64 with last dimension q^b")
+    batch = x.numel() // (q ** b)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().qsft_gwht_batch(_ptr(x), batch, q, b, _stream()))
+    return x
+
+
+class PeelProblem:
+    """Device-side description of one peeling problem (qsft_peel_desc) + its workspaces."""
+
+    def __init__(self, q, n, b, Ms, Ds, P_src, channel, source, cutoff, device, rs=None):
+        """Ms: list of C (n, b) arrays; Ds: array (C, P, n)."""
+        self.q, self.n, self.b = q, n, b
+        self.C = len(Ms)
+        Ds = np.asarray(Ds)
+        self.P = Ds.shape[1]
+        self.P_src = P_src
+        self.B = q ** b
+        self.ld = padded_ld(n)
+        self.device = device
+        MT = np.zeros((self.C, b, self.ld), dtype=np.int8)
+        for c, M in enumerate(Ms):
+            MT[c, :, :n] = np.asarray(M).T
+        Dp = np.zeros((self.C, self.P, self.ld), dtype=np.int8)
+        Dp[:, :, :n] = Ds
+        self.MT = torch.from_numpy(MT).to(device)
+        self.D = torch.from_numpy(Dp).to(device)
+        self.rs_exp = self.rs_log = None
+        rs_t = rs_s = 0
+        if source == "coded":
+            if rs is None:
+                raise ValueError("coded source decoding needs the ReedSolomon object (source_decoder)")
+            e, l = rs.device_tables()
+            self.rs_exp, self.rs_log = torch.from_numpy(e).to(device), torch.from_numpy(l).to(device)
+            rs_t, rs_s = rs.t, rs.s
+        chan = {"identity": 0, "nso": 1}.get(channel)
+        if chan is None:
+            raise NotImplementedError(f"reconstruct_method_channel={channel!r} is not supported (identity | nso)")
+        src = {"identity": 0, "coded": 1}.get(source)
+        if src is None:
+            raise NotImplementedError(f"reconstruct_method_source={source!r} is not supported (identity | coded)")
+        self.desc = _lib.PeelDesc(q=q, n=n, b=b, C=self.C, P=self.P, P_src=P_src, channel=chan, source=src,
+                                  rs_t=rs_t, rs_s=rs_s, ld=self.ld, cutoff=float(cutoff),
+                                  MT=self.MT.data_ptr(), D=self.D.data_ptr(),
+                                  rs_exp=0 if self.rs_exp is None else self.rs_exp.data_ptr(),
+                                  rs_log=0 if self.rs_log is None else self.rs_log.data_ptr())
+
+    def alloc(self, max_finds):
+        dev = self.device
+        self.max_finds = int(max_finds)
+        self.find_cj = torch.empty(self.max_finds, dtype=torch.int64, device=dev)
+        self.find_k = torch.empty((self.max_finds, self.ld), dtype=torch.int8, device=dev)
+        self.find_rho = torch.empty(self.max_finds, dtype=torch.complex64, device=dev)
+        self.find_round = torch.empty(self.max_finds, dtype=torch.int32, device=dev)
+        self.find_id = torch.empty((self.C, self.B), dtype=torch.int32, device=dev)
+        self.counters = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    # -- whole loop on one GPU -------------------------------------------------------------------------
+    def peel(self, U):
+        """Runs the full round loop in the library.  U (C, P, B) complex64 is modified in place.
+        Returns (n_finds, n_rounds); finds are in self.find_* [0:n_finds]."""
+        _need_cuda(U)
+        assert U.shape == (self.C, self.P, self.B) and U.dtype == torch.complex64
+        nf, nr = C.c_int64(0), C.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().qsft_peel(C.byref(self.desc), _ptr(U), _ptr(self.find_cj), _ptr(self.find_k),
+                                            _ptr(self.find_rho), _ptr(self.find_round), _ptr(self.find_id),
+                                            self.max_finds, _ptr(self.counters), C.byref(nf), C.byref(nr), _stream()))
+        return nf.value, nr.value
+
+    # -- single steps (bin-sharded multi-GPU loop drives these) ----------------------------------------
+    def classify(self, U, j_begin, j_end, round_no):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().qsft_peel_classify(C.byref(self.desc), _ptr(U), j_begin, j_end, _ptr(self.find_cj),
+                                                     _ptr(self.find_k), _ptr(self.find_rho), _ptr(self.find_round),
+                                                     _ptr(self.find_id), self.max_finds, round_no, _ptr(self.counters),
+                                                     _stream()))
+
+    def apply(self, U, j_begin, j_end, find_cj, find_k, find_rho, find_id, f_begin, n_finds, dedupe=True,
+              owner_count=None):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().qsft_peel_apply(C.byref(self.desc), _ptr(U), j_begin, j_end, _ptr(find_cj), _ptr(find_k),
+                                                  _ptr(find_rho), _ptr(find_id), f_begin, n_finds, 1 if dedupe else 0,
+                                                  _ptr(owner_count), _stream()))
+
+
+def closed_form_bins(M, D, q, loc, strengths, out=None):
+    """Verification helper: bins of one (M, D block) from the support directly.  M (n, b), D (P, n) arrays;
+    loc (S, ld) int8 device, strengths (S,) complex64 device.  Returns (P, B) complex64."""
+    M = np.asarray(M)
+    D = np.asarray(D)
+    n, b = M.shape
+    P = D.shape[0]
+    ld = loc.shape[1]
+    dev = loc.device
+    MT = np.zeros((b, ld), dtype=np.int8)
+    MT[:, :n] = M.T
+    Dp = np.zeros((P, ld), dtype=np.int8)
+    Dp[:, :n] = D
+    MTd, Dd = torch.from_numpy(MT).to(dev), torch.from_numpy(Dp).to(dev)
+    if out is None:
+        out = torch.zeros((P, q ** b), dtype=torch.complex64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().qsft_closed_form_bins(_ptr(MTd), _ptr(Dd), q, n, b, P, _ptr(loc), ld, _ptr(strengths),
+                                                    loc.shape[0], _ptr(out), _stream()))
+    return out

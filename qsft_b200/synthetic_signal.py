@@ -1,0 +1,100 @@
+"""Synthetic sparse signals evaluated on the GPU (mirror of synt_exp/synt_src/synthetic_signal.py).
+
+The support (locq) and strengths are drawn on the host with NumPy in the reference's RNG order; evaluation
+x[m] = sum_s a_s w^<m, k_s> runs in libqsft_b200 (K2)."""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from . import ops
+from .input_signal_subsampled import SubsampledSignal
+from .utils import ints_to_limbs, random_signal_strength_model, sort_qary_vecs
+
+
+def generate_signal_w(n, q, sparsity, a_min, a_max, noise_sd=0, full=True, max_weight=None):
+    """Random sparse spectrum (synthetic_signal.py:10-38).  Only full=False (dict) is supported: a dense q^n
+    spectrum is outside the subsampled path."""
+    if full:
+        raise NotImplementedError("full=True builds a dense q^n signal; use the subsampled path (full=False)")
+    max_weight = n if max_weight is None else max_weight
+    if max_weight == n:
+        locq = sort_qary_vecs(np.random.randint(q, size=(n, sparsity)).T).T
+    else:
+        vals = np.random.randint(q - 1, size=(max_weight, sparsity)) + 1
+        pos = np.random.choice(a=n, size=(sparsity, max_weight))
+        locq = np.zeros((n, sparsity), dtype=int)
+        for i in range(sparsity):
+            locq[pos[i, :], i] = vals[:, i]
+        locq = sort_qary_vecs(locq.T).T
+    strengths = random_signal_strength_model(sparsity, a_min, a_max)
+    signal_w = dict(zip(list(map(tuple, locq.T)), strengths))
+    return signal_w, locq, strengths
+
+
+def get_random_subsampled_signal(n, q, noise_sd, sparsity, a_min, a_max, query_args, max_weight=None, **kwargs):
+    """synthetic_signal.py:70-85.  Extra kwargs (device=, dist=, noise_rng=, eval_impl=) go to the signal."""
+    start_time = time.time()
+    signal_w, locq, strengths = generate_signal_w(n, q, sparsity, a_min, a_max, noise_sd, full=False,
+                                                  max_weight=max_weight)
+    print(f"Generation Time:{time.time() - start_time}", flush=True)
+    return SyntheticSubsampledSignal(signal_w=signal_w, locq=locq, strengths=strengths, noise_sd=noise_sd,
+                                     n=n, q=q, query_args=query_args, **kwargs)
+
+
+class SyntheticSubsampledSignal(SubsampledSignal):
+    """SubsampledSignal whose samples are computed on the fly from a known sparse spectrum
+    (synthetic_signal.py:88-130)."""
+    device_subsample = True
+
+    def __init__(self, **kwargs):
+        self.q = kwargs["q"]
+        self.n = kwargs["n"]
+        self.locq = kwargs["locq"]
+        self.noise_sd = kwargs["noise_sd"]
+        self.strengths = np.asarray(kwargs["strengths"])
+        # "numpy": host normals in the reference's RNG order (seed parity); "device": torch.randn on the GPU
+        self.noise_rng = kwargs.get("noise_rng", "numpy")
+        self.eval_impl = kwargs.get("eval_impl", 0)
+        super().__init__(**kwargs)
+
+    def _set_params(self, **kwargs):
+        super()._set_params(**kwargs)
+        self.noise_sd = kwargs["noise_sd"]
+        self._loc_dev = ops.pad_digits(np.asarray(self.locq).T, self.ld, self.device)            # (S, ld)
+        self._a_dev = torch.from_numpy(self.strengths.astype(np.complex64)).to(self.device)
+
+    def subsample_device(self, digits):
+        """digits (N, ld) int8 on the device -> complex64 samples (N,)."""
+        return ops.eval_synth(digits, self._loc_dev, self._a_dev, self.q, self.n, impl=self.eval_impl)
+
+    def subsample(self, query_indices):
+        """Signal values at decimal indices (Python ints, any width up to 128 bits), like the reference;
+        returns a NumPy complex array.  A CUDA int64 limb tensor is also accepted and returns a CUDA tensor."""
+        if isinstance(query_indices, torch.Tensor):
+            return self.subsample_device(ops.dec_to_qary(query_indices, self.q, self.n, self.ld))
+        limbs = ints_to_limbs(query_indices, self.limbs)
+        if limbs.shape[0] == 0:
+            return np.zeros(0, dtype=complex)
+        idx = torch.from_numpy(limbs.view(np.int64)).to(self.device)
+        out = self.subsample_device(ops.dec_to_qary(idx, self.q, self.n, self.ld))
+        return out.cpu().numpy().astype(complex)
+
+    def get_MDU(self, ret_num_subsample, ret_num_repeat, b, trans_times=False):
+        """Adds the synthetic measurement noise after the transform (synthetic_signal.py:120-130):
+        independent N(0, noise_sd^2 / (2 q^b)) on the real and imaginary part of every bin."""
+        mdu = super().get_MDU(ret_num_subsample, ret_num_repeat, b, trans_times)
+        nu = self.noise_sd / np.sqrt(2 * self.q ** b)
+        for i in range(len(mdu[2])):
+            for j in range(len(mdu[2][i])):
+                u = mdu[2][i][j]
+                if self.noise_rng == "numpy":
+                    noise = np.random.normal(0, nu, size=tuple(u.shape) + (2,))
+                    noise = (noise[..., 0] + 1j * noise[..., 1]).astype(np.complex64)
+                    mdu[2][i][j] = u + torch.from_numpy(noise).to(u.device)
+                elif nu > 0:
+                    g = torch.randn(tuple(u.shape) + (2,), dtype=torch.float32, device=u.device) * float(nu)
+                    mdu[2][i][j] = u + torch.view_as_complex(g)
+        return mdu

@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the committed reference fixtures.
+Bit-exact for integer / index work; complex64 values within rtol 1e-5 of the reference's complex128."""
+import numpy as np
+import pytest
+import torch
+
+import qsft_oracle as orc
+from conftest import FULL_CASES, INDEX_CASES, case_params, load_golden, u128_to_ints
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import qsft_b200
+    from qsft_b200 import ops, utils
+    DEV = torch.device("cuda", 0)
+
+
+def _build_signal(p, **kw):
+    np.random.seed(p["seed"])
+    return qsft_b200.get_random_subsampled_signal(n=p["n"], q=p["q"], sparsity=p["S"], a_min=1, a_max=1,
+                                                  noise_sd=p["noise_sd"], query_args=dict(p["query_args"]),
+                                                  max_weight=p["max_weight"], **kw)
+
+
+# ---- K1 ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", INDEX_CASES)
+def test_k1_lattice_bit_exact_wide(name):
+    g = load_golden(name)
+    q, n, b, P = (int(v) for v in g["meta"])
+    idx, dig = ops.query_lattice(g["M"], g["D"], q, device=DEV, want_idx=True, want_digits=True)
+    host = idx.cpu().numpy().view(np.uint64)
+    limbs = utils.index_limbs(q, n)
+    if limbs == 2:
+        assert np.array_equal(host[..., 0], g["hi"]) and np.array_equal(host[..., 1], g["lo"])
+    else:
+        assert np.array_equal(host, g["lo"]) and not g["hi"].any()
+    want_dig = orc.query_digits(g["M"], g["D"], q).transpose(0, 2, 1)          # (P, B, n)
+    got = dig.cpu().numpy()
+    assert np.array_equal(got[..., :n], want_dig) and not got[..., n:].any()
+    # device codecs round trip
+    flat = idx.reshape(-1, 2) if limbs == 2 else idx.reshape(-1)
+    d2 = ops.dec_to_qary(flat.contiguous(), q, n)
+    assert torch.equal(d2, dig.reshape(-1, dig.shape[-1]))
+    i2 = ops.qary_to_dec(d2, q, n)
+    assert torch.equal(i2, flat)
+    assert np.array_equal(d2[:64, :n].cpu().numpy().T, g["digits64"])
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_k1_lattice_matches_reference_group00(name):
+    g = load_golden(name)
+    p = case_params(g)
+    idx, _ = ops.query_lattice(g["Ms"][0], g["Ds"][0], p["q"], device=DEV)
+    host = idx.cpu().numpy().view(np.uint64)
+    assert np.array_equal(host, g["idx00_lo"]) and not g["idx00_hi"].any()
+
+
+def test_k1_large_lattice_properties():
+    """Full-size lattice (q=4, n=40, b=10): every index decodes back to (M l + d) mod q -- checked on device."""
+    rng = np.random.default_rng(0)
+    q, n, b, P = 4, 40, 10, 3
+    M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
+    idx, dig = ops.query_lattice(M, D, q, device=DEV, want_idx=True, want_digits=True)
+    back = ops.dec_to_qary(idx.reshape(-1, 2), q, n)
+    assert torch.equal(back, dig.reshape(-1, dig.shape[-1]))
+    # spot check 1000 random lattice points against the oracle formula
+    ls = rng.integers(0, q ** b, 1000)
+    L = np.stack([(ls // q ** (b - 1 - i)) % q for i in range(b)])
+    want = ((M @ L) % q + D[1][:, None]) % q
+    assert np.array_equal(dig[1][torch.from_numpy(ls).to(DEV)][:, :n].cpu().numpy().T, want)
+
+
+# ---- K2 ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("q,n,S,N", [(4, 10, 100, 3000), (3, 30, 257, 1001), (4, 40, 1000, 5000), (2, 100, 64, 777),
+                                     (7, 22, 300, 512), (5, 6, 1, 10), (4, 20, 513, 1)])
+def test_k2_eval_vs_oracle(impl, q, n, S, N):
+    rng = np.random.default_rng(q * 1000 + n)
+    qd, loc = rng.integers(0, q, (N, n)), rng.integers(0, q, (n, S))
+    a = rng.uniform(0.5, 2, S) * np.exp(1j * rng.uniform(0, 2 * np.pi, S))
+    want = orc.synth_eval_digits(qd, loc, a, q)
+    ld = utils.padded_ld(n)
+    got = ops.eval_synth(ops.pad_digits(qd, ld, DEV), ops.pad_digits(loc.T, ld, DEV),
+                         torch.from_numpy(a.astype(np.complex64)).to(DEV), q, n, impl=impl).cpu().numpy()
+    scale = np.sqrt(np.sum(np.abs(a) ** 2))
+    assert np.max(np.abs(got - want)) <= 2e-6 * scale + 1e-6 * np.max(np.abs(want))
+
+
+def test_k2_edge_cases():
+    ld = 32
+    z = torch.zeros((0, ld), dtype=torch.int8, device=DEV)
+    a0 = torch.zeros(0, dtype=torch.complex64, device=DEV)
+    assert ops.eval_synth(z, z, a0, 4, 10).numel() == 0
+    qd = torch.ones((5, ld), dtype=torch.int8, device=DEV)
+    out = ops.eval_synth(qd, z, a0, 4, 10)              # empty support -> zeros
+    assert torch.equal(out, torch.zeros(5, dtype=torch.complex64, device=DEV))
+    with pytest.raises(qsft_b200.QsftError):
+        ops.eval_synth(qd, z, a0, 1, 10)                # q out of range
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_k2_subsample_matches_reference_samples(name):
+    """SyntheticSubsampledSignal.subsample(python ints) against samples produced by the reference."""
+    g = load_golden(name)
+    p = case_params(g)
+    sig = _build_signal(p)
+    ints = u128_to_ints(g["idx00_hi"][1], g["idx00_lo"][1])
+    got = sig.subsample(ints)
+    want = g["samples00_row1"]
+    assert np.max(np.abs(got - want)) <= 1e-5 * max(1.0, np.max(np.abs(want)))
+    assert sig.subsample([]).shape == (0,)
+
+
+# ---- K3 ---------------------------------------------------------------------------------------------------
+def test_k3_gwht_units_vs_reference():
+    g = load_golden("gwht_units")
+    for key in g.files:
+        if key.startswith("x_"):
+            _, qs, bs = key.split("_")
+            q, b = int(qs[1:]), int(bs[1:])
+            x = torch.from_numpy(g[key].astype(np.complex64)).to(DEV).reshape(1, -1).contiguous()
+            y = ops.gwht_batch_(x, q, b).cpu().numpy()[0]
+            want = g["y" + key[1:]]
+            assert np.max(np.abs(y - want)) <= 1e-6 * np.max(np.abs(g[key])), key
+
+
+@pytest.mark.parametrize("q,b,batch", [(4, 7, 5), (3, 8, 3), (4, 8, 2), (2, 13, 3), (5, 6, 2), (11, 3, 4), (4, 10, 2),
+                                       (3, 9, 1), (6, 4, 2)])
+def test_k3_gwht_multi_pass_vs_oracle(q, b, batch):
+    rng = np.random.default_rng(b)
+    x = rng.normal(size=(batch, q ** b)) + 1j * rng.normal(size=(batch, q ** b))
+    want = np.stack([orc.gwht(r, q, b) for r in x])
+    got = ops.gwht_batch_(torch.from_numpy(x.astype(np.complex64)).to(DEV), q, b).cpu().numpy()
+    assert np.max(np.abs(got - want)) <= 2e-6 * np.max(np.abs(x)) / np.sqrt(q ** b) * np.sqrt(b) + 1e-7
+
+
+def test_k3_linearity_and_delta_full_size():
+    """Size-independent properties at BASELINE size 4^10: transform of a delta is a pure character / q^b;
+    linearity."""
+    q, b = 4, 10
+    B = q ** b
+    x = torch.zeros((2, B), dtype=torch.complex64, device=DEV)
+    l0 = 123457
+    x[0, l0] = 1.0
+    x[1] = torch.randn(B, device=DEV) + 1j * torch.randn(B, device=DEV)
+    x1 = x[1].clone()
+    y = ops.gwht_batch_(x.clone(), q, b)
+    js = torch.arange(B, device=DEV)
+    dots = torch.zeros(B, dtype=torch.int64, device=DEV)
+    for i in range(b):
+        dots += ((js // q ** i) % q) * ((l0 // q ** i) % q)
+    want = torch.exp(-2j * np.pi * (dots % q).to(torch.float32) / q) / B
+    assert torch.max(torch.abs(y[0] - want)) < 1e-9
+    z = x.clone()
+    z[0] = 2.5 * x[0] - 1j * x1
+    yz = ops.gwht_batch_(z, q, b)
+    assert torch.max(torch.abs(yz[0] - (2.5 * y[0] - 1j * y[1]))) < 1e-8
+
+
+# ---- construct (K1 + K2 + K3) against the reference's Us ----------------------------------------------------
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_construct_matches_reference_Us(name):
+    g = load_golden(name)
+    p = case_params(g)
+    sig = _build_signal(p)
+    assert np.array_equal(np.array(sig.Ms), g["Ms"]) and np.array_equal(np.array(sig.Ds[0]), g["Ds"])
+    for bb in sig.all_bs:
+        mine = np.array([[sig.Us[i][j][bb].cpu().numpy() for j in range(p["R"])] for i in range(p["C"])])
+        want = g[f"Us_b{bb}"]
+        assert np.max(np.abs(mine - want)) <= 1e-5 * np.max(np.abs(want)), bb
+    assert sig.get_source_parity() == p["P_src"]
+    with pytest.raises(ValueError):
+        sig.get_MDU(p["C"] + 1, 1, p["b"])
+
+
+# ---- K4: peel from the reference's own bins --------------------------------------------------------------
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_k4_peel_from_reference_bins(name):
+    g = load_golden(name)
+    p = case_params(g)
+    q, n = p["q"], p["n"]
+    U = torch.from_numpy(np.ascontiguousarray(g["mdu_Us"].reshape(p["trC"], -1, q ** p["trb"])).astype(np.complex64)).to(DEV)
+    D = g["mdu_Ds"].reshape(p["trC"], -1, n)
+    cutoff = 1e-9 + 1.5 * p["noise_sd"] ** 2 / q ** p["trb"]
+    prob = ops.PeelProblem(q, n, p["trb"], list(g["mdu_Ms"]), D, p["P_src"], p["chan"], p["src"], cutoff, DEV)
+    prob.alloc(4 * U.shape[0] * U.shape[2])
+    nf, nr = prob.peel(U)
+    gw, keys = qsft_b200.QSFT._finds_to_dict(prob.find_cj[:nf].cpu().numpy(), prob.find_k[:nf, :n].cpu().numpy(),
+                                              prob.find_rho[:nf].cpu().numpy(), prob.find_round[:nf].cpu().numpy())
+    want_keys = [tuple(int(v) for v in k) for k in g["res_keys"]]
+    assert list(gw.keys()) == want_keys                   # same support, same first-seen order
+    got = np.array([gw[k] for k in want_keys])
+    assert np.max(np.abs(got - g["res_vals"])) <= 1e-5 * np.max(np.abs(g["res_vals"]))
+
+
+# ---- end to end with the same seed ----------------------------------------------------------------------
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_end_to_end_same_seed(name):
+    g = load_golden(name)
+    p = case_params(g)
+    sig = _build_signal(p)
+    sft = qsft_b200.QSFT(num_subsample=p["trC"], num_repeat=p["trR"], b=p["trb"],
+                         reconstruct_method_source=p["src"], reconstruct_method_channel=p["chan"])
+    res = sft.transform(sig, report=True, sort=True)
+    assert np.random.random() == float(g["rng_probe"])           # RNG consumed exactly like the reference
+    want_keys = [tuple(int(v) for v in k) for k in g["res_keys"]]
+    true_w = dict(zip(map(tuple, g["locq"].T.tolist()), g["strengths"]))
+    ref_gw = dict(zip(want_keys, g["res_vals"]))
+    if p["noise_sd"] == 0:
+        assert list(res["gwht"].keys()) == want_keys
+        got = np.array([res["gwht"][k] for k in want_keys])
+        assert np.max(np.abs(got - g["res_vals"])) <= 1e-5
+        assert np.array_equal(np.array(res["locations"]), g["locations"])
+    else:
+        assert set(res["gwht"].keys()) == set(want_keys)
+        got = np.array([res["gwht"][k] for k in want_keys])
+        assert np.max(np.abs(got - g["res_vals"])) <= 1e-4
+        nm_ref, nm_got = orc.nmse(ref_gw, true_w), orc.nmse(res["gwht"], true_w)
+        assert abs(nm_got - nm_ref) <= 0.01 * nm_ref + 1e-12
+    assert res["n_samples"] == int(g["n_samples"])
+    assert res["max_hamming_weight"] == int(g["max_hw"])
+
+
+def test_coded_reed_solomon_end_to_end_vs_oracle():
+    """Config-3 shaped (reduced): q=3 coded delays.  Parity for D generation is UNPINNED (galois absent); the test
+    checks CUDA == oracle on the same D and exact support recovery."""
+    n, q, S, b, C, t = 20, 3, 60, 4, 3, 3
+    qa = {"query_method": "complex", "num_subsample": C, "delays_method_source": "coded", "subsampling_method": "qsft",
+          "delays_method_channel": "nso", "num_repeat": 2, "b": b, "t": t}
+    np.random.seed(8)
+    sig = qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=1, a_max=1, noise_sd=0.0,
+                                                  query_args=dict(qa), max_weight=t)
+    np.random.seed(8)
+    sw, locq, strengths = orc.generate_signal_w(n, q, S, 1, 1, max_weight=t)
+    osig = orc.OracleSignal(n, q, dict(qa), locq, strengths, noise_sd=0.0, signal_w=sw)
+    assert np.array_equal(np.array(sig.Ds[0]), np.array(osig.Ds[0]))
+    st = np.random.get_state()
+    want = orc.transform(osig, C, 2, b, "coded", "nso", source_decoder=orc.get_reed_solomon_dec(n, t, q))
+    np.random.set_state(st)
+    sft = qsft_b200.QSFT(num_subsample=C, num_repeat=2, b=b, reconstruct_method_source="coded",
+                         reconstruct_method_channel="nso", source_decoder=qsft_b200.get_reed_solomon_dec(n, t, q))
+    got = sft.transform(sig)
+    assert list(got.keys()) == list(want.keys())
+    assert set(got.keys()) == set(sw.keys())
+    assert max(abs(got[k] - want[k]) for k in want) < 1e-5
+
+
+def test_peel_large_closed_form_exact_recovery():
+    """BASELINE config-5 shape (q=4, n=40, b=10, C=3, nso R=1) at reduced sparsity: bins from the closed form,
+    device peel must recover the support exactly (size-independent property: result == signal_w)."""
+    q, n, b, C, R, S = 4, 40, 10, 3, 1, 20000
+    np.random.seed(1)
+    sw, locq, strengths = qsft_b200.generate_signal_w(n, q, S, 1, 1, 0, full=False)
+    Ms, Ds = qsft_b200.get_Ms_and_Ds(n, q, query_method="complex", num_subsample=C, delays_method_source="identity",
+                                     delays_method_channel="nso", num_repeat=R, b=b)
+    ld = utils.padded_ld(n)
+    loc = ops.pad_digits(locq.T, ld, DEV)
+    a = torch.from_numpy(strengths.astype(np.complex64)).to(DEV)
+    U = torch.stack([torch.cat([ops.closed_form_bins(Ms[c], Ds[c][r], q, loc, a) for r in range(R)]) for c in range(C)])
+    D = np.stack([np.vstack(Ds[c]) for c in range(C)])
+    prob = ops.PeelProblem(q, n, b, Ms, D, n + 1, "nso", "identity", 1e-9, DEV)
+    prob.alloc(4 * C * q ** b)
+    nf, nr = prob.peel(U.contiguous())
+    gw, _ = qsft_b200.QSFT._finds_to_dict(prob.find_cj[:nf].cpu().numpy(), prob.find_k[:nf, :n].cpu().numpy(),
+                                           prob.find_rho[:nf].cpu().numpy(), prob.find_round[:nf].cpu().numpy())
+    assert set(gw.keys()) == set(sw.keys())
+    err = max(abs(gw[k] - v) for k, v in sw.items())
+    assert err < 1e-5, err

@@ -1,0 +1,132 @@
+"""CPU tests of the product's host logic and of the C-ABI surface (no compute calls: there is no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import FULL_CASES, INDEX_CASES, ROOT, case_params, load_golden, u128_to_ints
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import qsft_b200
+    from qsft_b200 import _lib
+    L = qsft_b200.lib()
+    header = open(os.path.join(ROOT, "include", "qsft_b200.h")).read()
+    declared = set(re.findall(r"\b(qsft_[a-z0-9_]+)\s*\(", header))
+    declared.discard("qsft_peel_desc")
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/qsft_b200.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert L.qsft_version() >= 100
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    import qsft_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    qa = {"query_method": "complex", "num_subsample": 2, "delays_method_source": "identity",
+          "subsampling_method": "qsft", "delays_method_channel": "identity", "num_repeat": 1, "b": 2}
+    with pytest.raises(RuntimeError):
+        qsft_b200.get_random_subsampled_signal(n=4, q=2, noise_sd=0, sparsity=3, a_min=1, a_max=1, query_args=qa)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "qsft_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "qsft_oracle" not in src and "import oracle" not in src and "/root/reference" not in src, f
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_host_rng_order_matches_reference(name):
+    """generate_signal_w -> get_Ms_and_Ds consume np.random like the reference (same seed, same arrays)."""
+    from qsft_b200.synthetic_signal import generate_signal_w
+    from qsft_b200.query import get_Ms_and_Ds
+    g = load_golden(name)
+    p = case_params(g)
+    np.random.seed(p["seed"])
+    signal_w, locq, strengths = generate_signal_w(p["n"], p["q"], p["S"], 1, 1, p["noise_sd"], full=False,
+                                                  max_weight=p["max_weight"])
+    Ms, Ds = get_Ms_and_Ds(p["n"], p["q"], **p["query_args"])
+    assert np.array_equal(locq, g["locq"])
+    assert np.array_equal(strengths, g["strengths"])
+    assert np.array_equal(np.array(Ms), g["Ms"])
+    assert np.array_equal(np.array(Ds[0]), g["Ds"])
+    assert all(d is Ds[0] for d in Ds)
+
+
+@pytest.mark.parametrize("name", INDEX_CASES)
+def test_host_codecs(name):
+    from qsft_b200 import utils
+    g = load_golden(name)
+    q, n, b, P = (int(v) for v in g["meta"])
+    ints = u128_to_ints(g["hi"], g["lo"])
+    limbs = utils.index_limbs(q, n)
+    arr = utils.ints_to_limbs(ints, limbs)
+    assert [int(v) for v in utils.limbs_to_ints(arr)] == ints
+    dig = utils.dec_to_qary_vec(ints[:64], q, n)
+    assert np.array_equal(dig, g["digits64"])
+    assert [int(v) for v in utils.qary_vec_to_dec(dig, q)] == ints[:64]
+
+
+def test_index_limbs_and_ld():
+    from qsft_b200 import utils
+    assert utils.index_limbs(4, 32) == 1 and utils.index_limbs(4, 33) == 2 and utils.index_limbs(4, 64) == 2
+    assert utils.index_limbs(2, 128) == 2
+    with pytest.raises(ValueError):
+        utils.index_limbs(4, 65)
+    assert utils.padded_ld(10) == 32 and utils.padded_ld(40) == 64 and utils.padded_ld(64) == 64 and utils.padded_ld(100) == 128
+
+
+def test_query_errors_like_reference():
+    from qsft_b200 import query
+    with pytest.raises(ValueError):
+        query.get_Ms(12, 4, 2, num_to_get=4, method="simple")
+    with pytest.raises(NotImplementedError):
+        query.get_D(6, q=3, delays_method_source="identity", delays_method_channel="coded")
+    with pytest.raises(NotImplementedError):
+        query.get_reed_solomon_dec(10, 2, 4)
+    Ms = query.get_Ms(12, 4, 2, num_to_get=3, method="simple")
+    assert np.array_equal(Ms[0][8:12], np.eye(4)) and np.array_equal(Ms[2][0:4], np.eye(4))
+
+
+def test_reed_solomon_host_matches_oracle():
+    import qsft_oracle as orc
+    from qsft_b200.reed_solomon import ReedSolomon
+    for (n, t, q) in [(30, 4, 3), (20, 3, 5), (12, 2, 2)]:
+        a, o = ReedSolomon(n, t, q), orc.RSCode(n, t, q)
+        D = a.get_delay_matrix()
+        assert np.array_equal(D, o.get_delay_matrix())
+        rng = np.random.default_rng(n)
+        for it in range(100):
+            if it % 2:
+                syn = rng.integers(0, q, 2 * t * a.s)
+            else:
+                k = np.zeros(n, dtype=int)
+                w = int(rng.integers(0, t + 1))
+                k[rng.choice(n, w, replace=False)] = rng.integers(1, q, w)
+                syn = (D[1:] @ k) % q
+            r1, r2 = a.syndrome_decode(list(syn)), o.syndrome_decode(list(syn))
+            assert np.array_equal(r1[0], r2[0]) and r1[1] == r2[1]
+
+
+def test_finds_to_dict_matches_reference_averaging():
+    from qsft_b200.qsft import QSFT
+    # two rounds; k A found twice in round 1 (groups 0 and 2) and once in round 2, k B once
+    kA, kB = [1, 0, 2], [0, 3, 3]
+    cj = np.array([5, 40, 17, 9])
+    k = np.array([kA, kA, kB, kA], dtype=np.int8)
+    rho = np.array([1 + 1j, 3 + 1j, 2j, 5 + 4j], dtype=np.complex64)
+    rnd = np.array([1, 1, 1, 2], dtype=np.int32)
+    perm = np.array([3, 1, 0, 2])     # device order is arbitrary
+    gw, keys = QSFT._finds_to_dict(cj[perm], k[perm], rho[perm], rnd[perm])
+    assert list(gw.keys()) == [tuple(kA), tuple(kB)]
+    assert abs(gw[tuple(kA)] - (1 + 1j + 3 + 1j + 5 + 4j) / 3) < 1e-6 and abs(gw[tuple(kB)] - 2j) < 1e-6
+    assert keys.tolist() == [kA, kB]
+    gw0, keys0 = QSFT._finds_to_dict(np.zeros(0, np.int64), np.zeros((0, 3), np.int8), np.zeros(0, np.complex64), np.zeros(0, np.int32))
+    assert gw0 == {} and len(keys0) == 0
