@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the q-SFT transform path (sample + FFT + peel) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--repeat R] [--sparsity S]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4], the config the north-star target is quoted on): synthetic sparse signal
+q=4, n=40, b=10, S=1e5, C=3 random subsampling matrices, identity source delays + NSO channel delays,
+num_repeat=R (default in DEFAULT_REPEAT), noiseless; one *step* = one full transform of one fresh signal:
+query lattice (K1) -> synthetic evaluation (K2) -> batched q-ary DFT (K3) -> peeling (K4), exact support recovery
+checked on the last step.  Prints ONE JSON line (see README / DESIGN.md for the keys).
+
+`--impl reference` times the CPU oracle port of the reference NumPy path (oracle/qsft_oracle.py; the reference is
+pure Python and cannot travel to the GPU box) on bounded samples of the same workload and extrapolates.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+Q, N_DIM, B_DIM, SPARSITY, C_SUB = 4, 40, 10, 100_000, 3
+DEFAULT_REPEAT = 1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--repeat", type=int, default=DEFAULT_REPEAT, help="num_repeat R of the NSO delays")
+    ap.add_argument("--sparsity", type=int, default=SPARSITY)
+    ap.add_argument("--b", type=int, default=B_DIM)
+    ap.add_argument("--n", type=int, default=N_DIM)
+    ap.add_argument("--eval-impl", type=int, default=0, help="K2 kernel: 0 auto, 1 SIMT, 2 tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def query_args(R, b):
+    return {"query_method": "complex", "num_subsample": C_SUB, "delays_method_source": "identity",
+            "subsampling_method": "qsft", "delays_method_channel": "nso", "num_repeat": R, "b": b}
+
+
+def workload_name(a):
+    return (f"synthetic q={Q} n={a.n} b={a.b} S={a.sparsity} C={C_SUB} identity/nso num_repeat={a.repeat} noiseless "
+            f"(BASELINE configs[4])")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(s) > 2 + i and s[2 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU baseline = oracle port of the reference NumPy path, bounded samples, extrapolated
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_transform_seconds(a, budget_s=20.0, seed=0):
+    """Returns (estimated seconds per full transform on this host, detail dict)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import qsft_oracle as orc
+    cores = os.cpu_count() or 1
+    R, b, n, S = a.repeat, a.b, a.n, a.sparsity
+    P = R * (n + 1)
+    B = Q ** b
+    G = C_SUB * P
+    rng_state = np.random.get_state()
+    np.random.seed(seed)
+    sw, locq, strengths = orc.generate_signal_w(n, Q, S, 1, 1)
+    Ms, Ds = orc.get_Ms_and_Ds(n, Q, **query_args(R, b))
+    # (1) sampling: time batches of 10 000 queries (the reference's batch size) of the first lattice, all cores
+    dig = orc.query_digits(Ms[0], Ds[0][0][:1], Q)[0].T                     # (B, n) digit rows of delay row 0
+    idx = orc.qary_vec_to_dec(dig[: min(B, 200_000)].T, Q)
+    t0 = time.time()
+    done = 0
+    chunk = 10_000 * cores
+    while time.time() - t0 < budget_s * 0.6 and done < len(idx):
+        orc.synth_subsample(idx[done:done + chunk], locq, strengths, Q, n, threads=cores)
+        done += min(chunk, len(idx) - done)
+    t_sample = time.time() - t0
+    pairs_per_s = done * S / t_sample
+    est_sampling = G * B * S / pairs_per_s
+    # (2) index generation for one delay row (python big ints) and (3) FFT of one q^b block
+    t0 = time.time()
+    orc.qary_vec_to_dec(dig.T, Q)
+    t_idx = time.time() - t0
+    x = np.random.normal(size=B) + 1j * np.random.normal(size=B)
+    t0 = time.time()
+    orc.gwht(x, Q, b)
+    t_fft = time.time() - t0
+    # (4) peel on a reduced-sparsity instance of the same shape (cost is proportional to the number of balls)
+    S_peel = max(100, min(S, 5000))
+    sw2, locq2, st2 = orc.generate_signal_w(n, Q, S_peel, 1, 1)
+    osig = orc.OracleSignal(n, Q, query_args(R, b), locq2, st2, 0.0, sw2, Ms=Ms, Ds=Ds, use_closed_form=True)
+    t0 = time.time()
+    res = orc.transform(osig, C_SUB, R, b, "identity", "nso")
+    t_peel = (time.time() - t0) * (S / S_peel)
+    np.random.set_state(rng_state)
+    total = est_sampling + G * (t_idx + t_fft) + t_peel
+    detail = {"sampling_pairs_per_s": pairs_per_s, "sampled_queries": done, "est_sampling_s": est_sampling,
+              "index_s_per_row": t_idx, "fft_s_per_block": t_fft, "est_peel_s": t_peel,
+              "peel_sample_recovered": len(res) == len(sw2)}
+    sample = (f"{done} queries x S={S} timed in {t_sample:.1f}s on {cores} threads (extrapolated to G*B={G * B} queries)"
+              f" + 1 index row + 1 q^b FFT (x{G}) + peel at S={S_peel} scaled x{S / S_peel:.0f}")
+    return total, detail, sample, cores
+
+
+# ------------------------------------------------------------------------------------------------------------
+def make_inputs(a, steps, seed0=1000):
+    """Host-side synthetic inputs per step (support + strengths + Ms/Ds), generated outside the timed regions."""
+    from qsft_b200.synthetic_signal import generate_signal_w
+    from qsft_b200.query import get_Ms_and_Ds
+    out = []
+    for s in range(steps):
+        np.random.seed(seed0 + s)
+        sw, locq, strengths = generate_signal_w(a.n, Q, a.sparsity, 1, 1, 0, full=False)
+        Ms, Ds = get_Ms_and_Ds(a.n, Q, **query_args(a.repeat, a.b))
+        out.append((sw, locq, strengths, Ms, Ds))
+    return out
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as td
+    import qsft_b200
+    from qsft_b200 import _lib, ops
+    from qsft_b200.dist import DistContext
+    from qsft_b200.utils import padded_ld
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {a.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group("nccl", device_id=dev)
+        dist = DistContext()
+
+    def barrier():
+        if dist is not None:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    R, b, n, S = a.repeat, a.b, a.n, a.sparsity
+    P = R * (n + 1)
+    B = Q ** b
+    G = C_SUB * P
+    ld = padded_ld(n)
+    total_steps = a.warmup + a.steps
+    inputs = make_inputs(a, total_steps)
+    qa = query_args(R, b)
+
+    def build_signal(inp, resident):
+        sw, locq, strengths, Ms, Ds = inp
+        kw = {}
+        if resident is not None:
+            kw = {"loc_dev": resident[0], "a_dev": resident[1]}
+        # Ms / Ds were drawn in make_inputs (outside the timed region) and are handed over as kwargs
+        sig = qsft_b200.SyntheticSubsampledSignal(signal_w=sw, locq=locq, strengths=strengths, noise_sd=0.0, n=n, q=Q,
+                                                  query_args=dict(qa), device=dev, dist=dist, Ms=Ms, Ds=Ds,
+                                                  noise_rng="device", eval_impl=a.eval_impl, **kw)
+        return sig
+
+    def transform(sig, device_result):
+        sft = qsft_b200.QSFT(num_subsample=C_SUB, num_repeat=R, b=b, reconstruct_method_source="identity",
+                             reconstruct_method_channel="nso")
+        return sft.transform(sig, device_result=device_result), sft
+
+    # ---- loop A: inputs resident in HBM, CUDA-event timed -------------------------------------------------
+    resident = []
+    for inp in inputs:
+        resident.append((ops.pad_digits(np.asarray(inp[1]).T, ld, dev),
+                         torch.from_numpy(np.asarray(inp[2]).astype(np.complex64)).to(dev)))
+    for s in range(a.warmup):
+        transform(build_signal(inputs[s], resident[s]), True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    ops.TIMERS.reset(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for s in range(a.warmup, total_steps):
+        out, sft = transform(build_signal(inputs[s], resident[s]), True)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count()
+    kt = ops.TIMERS.totals()
+    ops.TIMERS.reset(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / a.steps
+
+    # ---- loop B: end to end through the public API with host buffers (H2D + D2H inside) -------------------
+    h2d = S * ld + S * 8 + C_SUB * (n * b + P * ld + b * ld)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    d2h = 0
+    last = None
+    for s in range(a.warmup, total_steps):
+        sig = build_signal(inputs[s], None)
+        res, sft = transform(sig, False)
+        d2h = sft.last_stats["finds"] * (8 + n + 8 + 4)
+        last = (res, inputs[s][0])
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.time() - t_wall0) * 1e3)
+    if dist is not None:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_ms_per_step = e2e_ms / a.steps
+    res, sw = last
+    recovered = set(res.keys()) == set(sw.keys())
+    max_err = max(abs(res[k] - v) for k, v in sw.items()) if recovered else None
+
+    if rank != 0:
+        if dist is not None:
+            td.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K2 evaluation) ---------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "2 x measured sustained bf16 (MEASURED_PEAKS.json), no int8 figure measured" if peaks else "2 x fallback 1.4 PF"
+    k2_ms, k2_calls, k2_pairs = kt.get("k2_eval", (0.0, 0, 0))
+    ops_per_launch = 2.0 * n * (k2_pairs / max(1, k2_calls))          # algorithmic int8 ops (unpadded K = n)
+    achieved = ops_per_launch / (k2_ms / max(1, k2_calls) * 1e-3) / 1e12 if k2_ms > 0 else 0.0
+    roofline = {"kernel": "k2_eval (synthetic evaluation, int8 contraction + root-of-unity epilogue)", "bound": "tensor",
+                "achieved": achieved, "peak": 2 * bf16, "unit": "TFLOP/s", "frac": achieved / (2 * bf16),
+                "traffic": None, "peak_source": peak_src,
+                "share_of_step": (k2_ms / a.steps) / ms_per_step if ms_per_step else None,
+                "per_kernel_ms_per_step": {k: v[0] / a.steps for k, v in kt.items()}}
+    k3_ms, k3_calls, k3_elems = kt.get("k3_gwht", (0.0, 0, 0))
+    if k3_ms > 0:
+        gbs = 16.0 * k3_elems / (k3_ms * 1e-3) / 1e9
+        roofline["k3_gwht_hbm"] = {"achieved": gbs, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
+                                   "frac": gbs / peaks.get("hbm_gbs", 6650.0)}
+
+    line = {
+        "metric": "q-SFT transforms/sec (sample + FFT + peel)", "value": 1e3 / ms_per_step, "unit": "transforms/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 contraction + complex64 (fp32)",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "groups_G": G, "bins_B": B, "samples": G * B,
+                   "l2": "inputs larger than L2 (per-step working set >= 1 GB)", "support_recovered_exactly": recovered,
+                   "max_coeff_err": max_err, "eval_impl": a.eval_impl,
+                   "parallelism": f"delay rows sharded over {a.gpus} GPU(s), bin-sharded peel" if a.gpus > 1 else "single GPU"},
+        "e2e": {"value": 1e3 / e2e_ms_per_step, "unit": "transforms/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "sample_fft_gbs": (24.0 * G * B) / ((k2_ms + k3_ms) / a.steps * 1e-3) / 1e9 if (k2_ms + k3_ms) > 0 else None,
+    }
+    if a.gpus == 1 and not a.no_cpu_baseline:
+        secs, detail, sample, cores = cpu_reference_transform_seconds(a)
+        line["cpu_baseline"] = {"value": 1.0 / secs, "unit": "transforms/s", "cores": cores, "kind": "port",
+                                "sample": sample, "detail": detail}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        td.destroy_process_group()
+
+
+def run_reference(a):
+    """Reference arm: the oracle port of the reference's CPU path, rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    times = []
+    detail = sample = None
+    cores = os.cpu_count() or 1
+    for s in range(a.warmup + a.steps):
+        secs, detail, sample, cores = cpu_reference_transform_seconds(a, budget_s=8.0, seed=s)
+        if s >= a.warmup:
+            times.append(secs)
+    secs = float(np.mean(times))
+    value = 1.0 / secs
+    line = {"impl": "reference", "metric": "q-SFT transforms/sec (sample + FFT + peel)", "value": value,
+            "unit": "transforms/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": secs * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex128 / int64 (NumPy)",
+            "data": "synthetic", "config": {"workload": workload_name(a)},
+            "cpu_baseline": {"value": value, "unit": "transforms/s", "cores": cores, "kind": "port", "sample": sample,
+                             "detail": detail},
+            "e2e": {"value": value, "unit": "transforms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -42,13 +42,14 @@ def qary_vec_to_dec(x, q):
 
 
 def dec_to_qary_vec(x, q, n):
-    """Decimal indices (sequence of python ints) -> (n, N) int digit array, MSB first.  qsft/utils.py:79-84."""
-    vals = [int(v) for v in x]
-    out = np.zeros((n, len(vals)), dtype=np.int64)
-    for col, v in enumerate(vals):
-        for i in range(n - 1, -1, -1):
-            v, r = divmod(v, q)
-            out[i, col] = r
+    """Decimal indices (sequence of python ints) -> (n, N) int digit array, MSB first.  qsft/utils.py:79-84
+    (object-dtype arithmetic so that indices wider than 64 bits stay exact)."""
+    v = np.array([int(t) for t in x], dtype=object)
+    out = np.zeros((n, len(v)), dtype=np.int64)
+    for i in range(n - 1, -1, -1):
+        if len(v):
+            out[i] = (v % q).astype(np.int64)
+            v = v // q
     return out
 
 

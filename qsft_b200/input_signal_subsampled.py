@@ -53,6 +53,7 @@ class SubsampledSignal(Signal):
             dev = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(dev)
         self.dist = kwargs.get("dist")
+        self._preset_MD = (kwargs.get("Ms"), kwargs.get("Ds"))     # optional: caller-provided matrices
         self.ld = padded_ld(self.n)
         self.limbs = index_limbs(self.q, self.n)
         self.sample_time = 0.0
@@ -66,8 +67,11 @@ class SubsampledSignal(Signal):
 
     # ------------------------------------------------------------------------------------------------
     def _set_Ms_and_Ds_qsft(self):
-        """Ms / Ds from `folder`/Ms_and_Ds.pickle when present (reference cache format), else generated."""
-        if self.foldername:
+        """Ms / Ds from the `Ms=` / `Ds=` kwargs, else from `folder`/Ms_and_Ds.pickle when present (reference cache
+        format), else generated (consuming np.random like the reference)."""
+        if self._preset_MD[0] is not None:
+            self.Ms, self.Ds = self._preset_MD
+        elif self.foldername:
             Path(f"{self.foldername}").mkdir(exist_ok=True)
             path = Path(f"{self.foldername}/Ms_and_Ds.pickle")
             if path.is_file():

@@ -15,6 +15,47 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class KernelTimers:
+    """Optional CUDA-event timing of the library calls (bench.py roofline): events are recorded on the launching
+    stream around each call; totals() synchronises and sums per kernel name."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []
+
+    def reset(self, enabled=True):
+        self.enabled = enabled
+        self.records = []
+
+    def totals(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, work in self.records:
+            ms, n, w = out.get(name, (0.0, 0, 0))
+            out[name] = (ms + e0.elapsed_time(e1), n + 1, w + work)
+        return out
+
+
+TIMERS = KernelTimers()
+
+
+class _timed:
+    def __init__(self, name, work=0):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if TIMERS.enabled:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if TIMERS.enabled:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            TIMERS.records.append((self.name, self.e0, e1, self.work))
+        return False
+
+
 def _ptr(t):
     return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
 
@@ -51,7 +92,7 @@ def query_lattice(M, D, q, *, device, want_idx=True, want_digits=False, limbs=No
         idx = torch.empty((P, B) if limbs == 1 else (P, B, 2), dtype=torch.int64, device=device)
     if want_digits:
         dig = torch.empty((P, B, ld), dtype=torch.int8, device=device)
-    with torch.cuda.device(device):
+    with torch.cuda.device(device), _timed("k1_lattice", P * B):
         _lib.check(_lib.lib().qsft_query_lattice(_ptr(Md), _ptr(Dd), q, n, b, P, _ptr(idx), limbs, _ptr(dig), ld, _stream()))
     return idx, dig
 
@@ -89,7 +130,7 @@ def eval_synth(qdig, loc, strengths, q, n, out=None, impl=0):
         raise ValueError("strengths must be complex64")
     if out is None:
         out = torch.empty((N,), dtype=torch.complex64, device=qdig.device)
-    with torch.cuda.device(qdig.device):
+    with torch.cuda.device(qdig.device), _timed("k2_eval", N * S):
         _lib.check(_lib.lib().qsft_eval_synth(_ptr(qdig), N, _ptr(loc), _ptr(strengths), S, q, n, ld, _ptr(out), impl, _stream()))
     return out
 
@@ -100,7 +141,7 @@ def gwht_batch_(x, q, b):
     if x.dtype != torch.complex64 or x.shape[-1] != q ** b:
         raise ValueError("x must be complex64 with last dimension q^b")
     batch = x.numel() // (q ** b)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("k3_gwht", x.numel()):
         _lib.check(_lib.lib().qsft_gwht_batch(_ptr(x), batch, q, b, _stream()))
     return x
 
@@ -162,7 +203,7 @@ class PeelProblem:
         _need_cuda(U)
         assert U.shape == (self.C, self.P, self.B) and U.dtype == torch.complex64
         nf, nr = C.c_int64(0), C.c_int(0)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _timed("k4_peel", U.numel()):
             _lib.check(_lib.lib().qsft_peel(C.byref(self.desc), _ptr(U), _ptr(self.find_cj), _ptr(self.find_k),
                                             _ptr(self.find_rho), _ptr(self.find_round), _ptr(self.find_id),
                                             self.max_finds, _ptr(self.counters), C.byref(nf), C.byref(nr), _stream()))

@@ -64,6 +64,11 @@ class QSFT:
         else:
             prob.alloc(max_finds=min(15 * C * B, max(4096, 4 * C * B)))
             n_finds, n_rounds = prob.peel(U)
+            if kwargs.get("device_result", False):
+                # raw finds left in HBM (no host copy, no dict): used by the device-resident benchmark loop
+                self.last_stats = {"rounds": n_rounds, "finds": n_finds, "cutoff": float(cutoff)}
+                return {"find_cj": prob.find_cj[:n_finds], "find_k": prob.find_k[:n_finds, :n],
+                        "find_rho": prob.find_rho[:n_finds], "find_round": prob.find_round[:n_finds]}
             finds = (prob.find_cj[:n_finds].cpu().numpy(), prob.find_k[:n_finds, :n].cpu().numpy(),
                      prob.find_rho[:n_finds].cpu().numpy(), prob.find_round[:n_finds].cpu().numpy(), n_rounds)
         gwht, loc_arr = self._finds_to_dict(*finds[:4])

@@ -63,8 +63,14 @@ class SyntheticSubsampledSignal(SubsampledSignal):
     def _set_params(self, **kwargs):
         super()._set_params(**kwargs)
         self.noise_sd = kwargs["noise_sd"]
-        self._loc_dev = ops.pad_digits(np.asarray(self.locq).T, self.ld, self.device)            # (S, ld)
-        self._a_dev = torch.from_numpy(self.strengths.astype(np.complex64)).to(self.device)
+        # support table on the device: (S, ld) int8 digit rows + (S,) complex64; `loc_dev` / `a_dev` kwargs let a
+        # caller hand over tensors that are already resident in HBM
+        self._loc_dev = kwargs.get("loc_dev")
+        self._a_dev = kwargs.get("a_dev")
+        if self._loc_dev is None:
+            self._loc_dev = ops.pad_digits(np.asarray(self.locq).T, self.ld, self.device)
+        if self._a_dev is None:
+            self._a_dev = torch.from_numpy(self.strengths.astype(np.complex64)).to(self.device)
 
     def subsample_device(self, digits):
         """digits (N, ld) int8 on the device -> complex64 samples (N,)."""
