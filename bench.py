@@ -30,6 +30,11 @@ Q, N_DIM, B_DIM, SPARSITY, C_SUB = 4, 40, 10, 100_000, 3
 DEFAULT_REPEAT = 1
 
 
+def log(msg):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -111,11 +116,14 @@ def cpu_reference_transform_seconds(a, budget_s=20.0, seed=0):
     # (1) sampling: time batches of 10 000 queries (the reference's batch size) of the first lattice, all cores
     dig = orc.query_digits(Ms[0], Ds[0][0][:1], Q)[0].T                     # (B, n) digit rows of delay row 0
     idx = orc.qary_vec_to_dec(dig[: min(B, 200_000)].T, Q)
+    # the reference evaluates 10 000 queries per batch (a 10 000 x S complex128 matrix = 16 GB at S = 1e5); the port
+    # uses the same arithmetic on smaller batches so that `cores` threads fit in a few GB
+    batch = int(max(1, min(10_000, 2e7 // S)))
     t0 = time.time()
     done = 0
-    chunk = 10_000 * cores
+    chunk = batch * cores
     while time.time() - t0 < budget_s * 0.6 and done < len(idx):
-        orc.synth_subsample(idx[done:done + chunk], locq, strengths, Q, n, threads=cores)
+        orc.synth_subsample(idx[done:done + chunk], locq, strengths, Q, n, batch=batch, threads=cores)
         done += min(chunk, len(idx) - done)
     t_sample = time.time() - t0
     pairs_per_s = done * S / t_sample
@@ -128,20 +136,24 @@ def cpu_reference_transform_seconds(a, budget_s=20.0, seed=0):
     t0 = time.time()
     orc.gwht(x, Q, b)
     t_fft = time.time() - t0
-    # (4) peel on a reduced-sparsity instance of the same shape (cost is proportional to the number of balls)
-    S_peel = max(100, min(S, 5000))
+    # (4) peel on a reduced instance with the same bin load S/B (b-2 => 16x fewer bins and balls; the reference loop
+    #     costs time proportional to bins + balls), scaled back.  Keeps the host memory of the baseline small.
+    b_s = max(2, b - 2)
+    scale = (Q ** b) / (Q ** b_s)
+    S_peel = max(50, int(S / scale))
     sw2, locq2, st2 = orc.generate_signal_w(n, Q, S_peel, 1, 1)
-    osig = orc.OracleSignal(n, Q, query_args(R, b), locq2, st2, 0.0, sw2, Ms=Ms, Ds=Ds, use_closed_form=True)
+    Ms_s = [M[:, :b_s] for M in Ms]
+    osig = orc.OracleSignal(n, Q, query_args(R, b_s), locq2, st2, 0.0, sw2, Ms=Ms_s, Ds=Ds, use_closed_form=True)
     t0 = time.time()
-    res = orc.transform(osig, C_SUB, R, b, "identity", "nso")
-    t_peel = (time.time() - t0) * (S / S_peel)
+    res = orc.transform(osig, C_SUB, R, b_s, "identity", "nso")
+    t_peel = (time.time() - t0) * scale
     np.random.set_state(rng_state)
     total = est_sampling + G * (t_idx + t_fft) + t_peel
     detail = {"sampling_pairs_per_s": pairs_per_s, "sampled_queries": done, "est_sampling_s": est_sampling,
               "index_s_per_row": t_idx, "fft_s_per_block": t_fft, "est_peel_s": t_peel,
               "peel_sample_recovered": len(res) == len(sw2)}
     sample = (f"{done} queries x S={S} timed in {t_sample:.1f}s on {cores} threads (extrapolated to G*B={G * B} queries)"
-              f" + 1 index row + 1 q^b FFT (x{G}) + peel at S={S_peel} scaled x{S / S_peel:.0f}")
+              f" + 1 index row + 1 q^b FFT (x{G}) + peel at b={b_s}, S={S_peel} (same bin load) scaled x{scale:.0f}")
     return total, detail, sample, cores
 
 
@@ -215,8 +227,12 @@ def run_ours(a):
     for inp in inputs:
         resident.append((ops.pad_digits(np.asarray(inp[1]).T, ld, dev),
                          torch.from_numpy(np.asarray(inp[2]).astype(np.complex64)).to(dev)))
+    log(f"inputs ready; warm-up x{a.warmup}")
     for s in range(a.warmup):
+        t0 = time.time()
         transform(build_signal(inputs[s], resident[s]), True)
+        torch.cuda.synchronize()
+        log(f"warm-up step {s}: {time.time() - t0:.2f}s")
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -239,6 +255,7 @@ def run_ours(a):
         td.all_reduce(t, op=td.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_per_step = ms_total / a.steps
+    log(f"device-resident loop: {ms_per_step:.1f} ms/step; kernels: " + ", ".join(f"{k}={v[0] / a.steps:.1f}ms" for k, v in kt.items()))
 
     # ---- loop B: end to end through the public API with host buffers (H2D + D2H inside) -------------------
     h2d = S * ld + S * 8 + C_SUB * (n * b + P * ld + b * ld)
@@ -261,6 +278,7 @@ def run_ours(a):
         td.all_reduce(t, op=td.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_ms_per_step = e2e_ms / a.steps
+    log(f"end-to-end loop: {e2e_ms_per_step:.1f} ms/step")
     res, sw = last
     recovered = set(res.keys()) == set(sw.keys())
     max_err = max(abs(res[k] - v) for k, v in sw.items()) if recovered else None
@@ -309,6 +327,7 @@ def run_ours(a):
         "sample_fft_gbs": (24.0 * G * B) / ((k2_ms + k3_ms) / a.steps * 1e-3) / 1e9 if (k2_ms + k3_ms) > 0 else None,
     }
     if a.gpus == 1 and not a.no_cpu_baseline:
+        log("timing the CPU oracle port (bounded sample)")
         secs, detail, sample, cores = cpu_reference_transform_seconds(a)
         line["cpu_baseline"] = {"value": 1.0 / secs, "unit": "transforms/s", "cores": cores, "kind": "port",
                                 "sample": sample, "detail": detail}

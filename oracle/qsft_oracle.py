@@ -169,10 +169,10 @@ def generate_signal_w(n, q, sparsity, a_min, a_max, max_weight=None):
 
 
 def synth_eval_digits(digits, locq, strengths, q):
-    """x[m] = sum_s a_s exp(2 pi i <m, k_s> / q) for query digit rows (N, n).  synthetic_signal.py:100-102.
-    The exponent is reduced mod q first (exact: the phase only depends on it)."""
-    t = (np.asarray(digits, dtype=np.int64) @ np.asarray(locq, dtype=np.int64)) % q
-    return np.exp(1j * TWO_PI / q * t) @ strengths
+    """x[m] = sum_s a_s exp(2 pi i <m, k_s> / q) for query digit rows (N, n): the reference's sampling_function
+    (synthetic_signal.py:95,100-102) -- integer digits times the complex frequency matrix, np.exp, times strengths."""
+    freq = (2j * np.pi / q) * np.asarray(locq)
+    return np.exp(np.asarray(digits) @ freq) @ strengths
 
 
 def synth_subsample(query_idx, locq, strengths, q, n, batch=10000, threads=None):
@@ -181,7 +181,7 @@ def synth_subsample(query_idx, locq, strengths, q, n, batch=10000, threads=None)
     query_idx = list(query_idx)
     if not query_idx:
         return np.zeros(0, dtype=complex)
-    nb = len(query_idx) // batch + 1
+    nb = len(query_idx) // batch + 1          # np.array_split(query_indices, len // batch + 1)
     bounds = np.linspace(0, len(query_idx), nb + 1).astype(int)
     chunks = [query_idx[bounds[i]:bounds[i + 1]] for i in range(nb)]
 
