@@ -1,6 +1,8 @@
 // K2 (tensor-core variant): synthetic sparse signal evaluation as a tcgen05 int8 GEMM with a fused epilogue.
 //   D[m, s] = <qdig[m], loc[s]>            (UTCIMMA, kind::i8, int32 accumulators in TMEM, K = ld)
 //   out[m]  = sum_s a_s * w^(D[m, s] mod q)  (epilogue: tcgen05.ld -> mod q -> root-of-unity table in smem -> complex add)
+// q = 4 fast path: the support digits are pre-scaled by 8 (values 0..24), so (D & 24) is directly the byte offset of
+// the rotated strength a_s * i^t inside a 32-byte table entry: LOP3 + LDS.64 + 2 FADD per (query, support) pair.
 // Replaces synt_exp/synt_src/synthetic_signal.py:100-118 (exp(Q @ 2 pi i locq / q) @ strengths).
 //
 // One CTA owns 128 query rows (UMMA M = 128, cta_group::1) and streams the support in tiles of 256 rows (UMMA N = 256)
@@ -9,14 +11,18 @@
 // quarter each).  Operand tiles are K-major rows of `LD` bytes with the LD-byte TMA/UMMA swizzle.
 #include <cuda.h>
 
+#include <utility>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int TC_BM = 128;          // query rows per CTA
 constexpr int TC_BN = 256;          // support rows per tile
-constexpr int TC_THREADS = 192;
-constexpr int TC_EPI_THREADS = 128;
+constexpr int TC_EPI_WARPS = 8;     // two warps per TMEM lane quarter, each reduces half of the tile's columns
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
+constexpr int TC_COLS_PER_WARP = TC_BN / (TC_EPI_WARPS / 4);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -79,6 +85,27 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// q = 4 epilogue step for column (CH*32 + J) of this warp's column range: the table entry of a column is 32 bytes
+// (a, ia, -a, -ia); `v & 24` selects the rotation, `base` (32-byte aligned, so OR == ADD) is the table address of the
+// warp's first column and the column offset is an immediate of the LDS: LOP3 + LDS.64 + 2 FADD per pair.
+template <int OFF>
+__device__ __forceinline__ float2 lds_f2_off(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+template <int CH, int J>
+__device__ __forceinline__ void q4_step(uint32_t v, uint32_t base, float (&pr)[4], float (&pi)[4]) {
+    const float2 w = lds_f2_off<(CH * 32 + J) * 32>((v & 24u) | base);
+    pr[J & 3] += w.x;
+    pi[J & 3] += w.y;
+}
+template <int CH, int... J>
+__device__ __forceinline__ void q4_chunk(const uint32_t (&r)[32], uint32_t base, float (&pr)[4], float (&pi)[4],
+                                         std::integer_sequence<int, J...>) {
+    (q4_step<CH, J>(r[J], base, pr, pi), ...);
+}
+
 // K-major operand tile, rows of LD bytes, LD-byte swizzle: SBO = 8 rows * LD bytes, LBO unused (=1), version 1
 template <int LD>
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -97,9 +124,8 @@ struct TcSmem {
     static constexpr int kStages = (LD == 128) ? 4 : (LD == 64) ? 6 : 12;   // >= 114 KB smem: one CTA (one 512-column TMEM allocation) per SM
     static constexpr int kABytes = TC_BM * LD;
     static constexpr int kBBytes = TC_BN * LD;
-    static constexpr int kTabEntries = 2 * TC_BN * 4;  // float2, both accumulators, 4 rotations (Q4) or 1 (generic)
-    static constexpr size_t kBytes = 1024 /*align slack*/ + kABytes + (size_t)kStages * kBBytes + kTabEntries * 8 +
-                                     (QSFT_MAX_Q + 1) * 8 + 32 * 8 + 16;
+    static constexpr size_t kBytes = 1024 /*align slack*/ + kABytes + (size_t)kStages * kBBytes +
+                                     (QSFT_MAX_Q + 1) * 8 + 32 * 8 + 16 + TC_BM * 16;
 };
 
 template <int LD, bool Q4>
@@ -112,9 +138,12 @@ k2_eval_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = base;
     uint8_t* sB = sA + L::kABytes;
-    float2* sTab = reinterpret_cast<float2*>(sB + (size_t)L::kStages * L::kBBytes);
-    float2* sTw = sTab + L::kTabEntries;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sTw + QSFT_MAX_Q + 1);
+    // strength tables for the two accumulators: static so that their shared address is a link-time constant
+    // (the epilogue's LDS then needs no address arithmetic beyond one LOP3)
+    __shared__ __align__(1024) float2 sTab[2 * TC_BN * 4];
+    float2* sTw = reinterpret_cast<float2*>(sB + (size_t)L::kStages * L::kBBytes);
+    double2* sRed = reinterpret_cast<double2*>(sTw + QSFT_MAX_Q + 1);           // [TC_BM] partial sums of column half 1
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + TC_BM);
     uint64_t* full = bars;                       // [kStages]
     uint64_t* empty = bars + L::kStages;         // [kStages]
     uint64_t* tfull = bars + 2 * L::kStages;     // [2]
@@ -133,7 +162,7 @@ k2_eval_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);
+            mbar_init(&tempty[i], TC_EPI_WARPS);
         }
         mbar_init(afull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -195,14 +224,16 @@ k2_eval_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     } else {
-        const int e = threadIdx.x - 64;                 // 0..127 inside the epilogue group
+        const int e = threadIdx.x - 64;                 // 0..TC_EPI_THREADS-1 inside the epilogue group
         const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;               // which column half of the tile this warp reduces
         const int row = quarter * 32 + lane;
+        const int c0 = half * TC_COLS_PER_WARP;
         double xr = 0.0, xi = 0.0;
         for (int it = 0; it < ntiles; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-            // stage the strengths (and, for q = 4, their four rotations) of this tile
+            // stage the strengths (for q = 4: their four rotations a, ia, -a, -ia) of this tile
             float2* tab = sTab + acc * (TC_BN * 4);
 #pragma unroll
             for (int h = 0; h < TC_BN / TC_EPI_THREADS; ++h) {
@@ -217,45 +248,64 @@ k2_eval_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     tab[c] = a;
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
-            float pr = 0.f, pi = 0.f;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_BN);
-#pragma unroll 1
-            for (int ch = 0; ch < TC_BN / 32; ++ch) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + (uint32_t)(ch * 32), r);
-                tmem_ld_wait();
+            float pr[4] = {0.f, 0.f, 0.f, 0.f}, pi[4] = {0.f, 0.f, 0.f, 0.f};   // independent chains hide FADD latency
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_BN + c0);
+            const uint32_t tabq = smem_u32(sTab) + (uint32_t)(acc * TC_BN + c0) * 32u;   // 32-byte aligned
+            const float2* tabg = sTab + acc * (TC_BN * 4) + c0;
+            uint32_t r0[32], r1[32];
+            static_assert(TC_COLS_PER_WARP == 128, "epilogue below is written for four 32-column chunks per warp");
+            auto generic_chunk = [&](const uint32_t (&r)[32], int ch) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int c = ch * 32 + j;
-                    if (Q4) {
-                        const float2 v = tab[c * 4 + (r[j] & 3u)];
-                        pr += v.x;
-                        pi += v.y;
-                    } else {
-                        const uint32_t t = r[j] - __umulhi(r[j], qmagic) * (uint32_t)q;
-                        const float2 tw = sTw[t];
-                        const float2 a = tab[c];
-                        pr = fmaf(a.x, tw.x, fmaf(-a.y, tw.y, pr));
-                        pi = fmaf(a.x, tw.y, fmaf(a.y, tw.x, pi));
-                    }
+                    const uint32_t v = r[j];
+                    const uint32_t t = v - __umulhi(v, qmagic) * (uint32_t)q;
+                    const float2 tw = sTw[t];
+                    const float2 a = tabg[ch * 32 + j];
+                    pr[j & 3] = fmaf(a.x, tw.x, fmaf(-a.y, tw.y, pr[j & 3]));
+                    pi[j & 3] = fmaf(a.x, tw.y, fmaf(a.y, tw.x, pi[j & 3]));
                 }
-            }
+            };
+            using Seq = std::make_integer_sequence<int, 32>;
+            tmem_ld_32x32(taddr, r0);
+            tmem_ld_wait();
+            tmem_ld_32x32(taddr + 32u, r1);
+            if (Q4) q4_chunk<0>(r0, tabq, pr, pi, Seq{}); else generic_chunk(r0, 0);
+            tmem_ld_wait();
+            tmem_ld_32x32(taddr + 64u, r0);
+            if (Q4) q4_chunk<1>(r1, tabq, pr, pi, Seq{}); else generic_chunk(r1, 1);
+            tmem_ld_wait();
+            tmem_ld_32x32(taddr + 96u, r1);
+            if (Q4) q4_chunk<2>(r0, tabq, pr, pi, Seq{}); else generic_chunk(r0, 2);
+            tmem_ld_wait();
+            if (Q4) q4_chunk<3>(r1, tabq, pr, pi, Seq{}); else generic_chunk(r1, 3);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
-            xr += (double)pr;
-            xi += (double)pi;
+            xr += (double)((pr[0] + pr[1]) + (pr[2] + pr[3]));
+            xi += (double)((pi[0] + pi[1]) + (pi[2] + pi[3]));
         }
-        if (m0 + row < N) out[m0 + row] = make_float2((float)xr, (float)xi);
+        // combine the two column halves of each row
+        if (half == 1) sRed[row] = make_double2(xr, xi);
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+        if (half == 0 && m0 + row < N) {
+            const double2 o = sRed[row];
+            out[m0 + row] = make_float2((float)(xr + o.x), (float)(xi + o.y));
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+}
+
+// q = 4 fast path: support digit rows scaled by 8 (see the epilogue)
+__global__ void scale8_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, long long words) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < words) out[i] = in[i] << 3;     // bytes are <= 3, no carry across byte lanes
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -325,14 +375,26 @@ int qsft_eval_synth_tc(const int8_t* qdig, int64_t N, const int8_t* loc, const f
                        int ld, float* out, void* stream) {
     (void)n;
     QSFT_CHECK_ARG(((uintptr_t)qdig & 15) == 0 && ((uintptr_t)loc & 15) == 0, "digit buffers must be 16-byte aligned");
-    CUtensorMap ma, mb;
-    if (int rc = make_map(&ma, qdig, N, ld, TC_BM)) return rc;
-    if (int rc = make_map(&mb, loc, S, ld, TC_BN)) return rc;
-    const float2* a = reinterpret_cast<const float2*>(strengths);
-    float2* o = reinterpret_cast<float2*>(out);
     cudaStream_t st = (cudaStream_t)stream;
     const bool q4 = (q == 4);
-    if (ld == 32) return q4 ? launch_tc<32, true>(ma, mb, a, N, S, q, o, st) : launch_tc<32, false>(ma, mb, a, N, S, q, o, st);
-    if (ld == 64) return q4 ? launch_tc<64, true>(ma, mb, a, N, S, q, o, st) : launch_tc<64, false>(ma, mb, a, N, S, q, o, st);
-    return q4 ? launch_tc<128, true>(ma, mb, a, N, S, q, o, st) : launch_tc<128, false>(ma, mb, a, N, S, q, o, st);
+    int8_t* loc8 = nullptr;
+    if (q4) {  // stream-ordered scratch copy of the support digits, scaled by 8
+        const long long words = S * (long long)ld / 4;
+        QSFT_CUDA(cudaMallocAsync(&loc8, (size_t)S * ld, st));
+        scale8_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(loc),
+                                                                       reinterpret_cast<uint32_t*>(loc8), words);
+        QSFT_LAUNCHED();
+    }
+    CUtensorMap ma, mb;
+    int rc = make_map(&ma, qdig, N, ld, TC_BM);
+    if (!rc) rc = make_map(&mb, q4 ? loc8 : loc, S, ld, TC_BN);
+    const float2* a = reinterpret_cast<const float2*>(strengths);
+    float2* o = reinterpret_cast<float2*>(out);
+    if (!rc) {
+        if (ld == 32) rc = q4 ? launch_tc<32, true>(ma, mb, a, N, S, q, o, st) : launch_tc<32, false>(ma, mb, a, N, S, q, o, st);
+        else if (ld == 64) rc = q4 ? launch_tc<64, true>(ma, mb, a, N, S, q, o, st) : launch_tc<64, false>(ma, mb, a, N, S, q, o, st);
+        else rc = q4 ? launch_tc<128, true>(ma, mb, a, N, S, q, o, st) : launch_tc<128, false>(ma, mb, a, N, S, q, o, st);
+    }
+    if (loc8) cudaFreeAsync(loc8, st);
+    return rc;
 }
