@@ -45,6 +45,12 @@ class DistContext:
             outs.append(torch.view_as_complex(cat) if t.is_complex() else cat)
         return outs, counts
 
+    def all_reduce_sum(self, value, device):
+        """Sum of one integer over ranks (stop rule of the peel loop)."""
+        t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+        td.all_reduce(t, group=self.group)
+        return int(t.item())
+
     def barrier(self):
         td.barrier(group=self.group)
 
@@ -77,10 +83,9 @@ def peel_sharded(prob, U, dist, max_rounds=15):
         if nf_local > cap:
             raise RuntimeError("find buffer overflow in sharded peel")
         (cj, k, rho), counts = dist.all_gather_var([prob.find_cj, prob.find_k, prob.find_rho], nf_local, cap)
-        tot = torch.tensor([multi_local], dtype=torch.int64, device=dev)
-        td.all_reduce(tot, group=dist.group)          # number of multitons this round (scalar; stop rule only)
+        n_multi = dist.all_reduce_sum(multi_local, dev)   # multitons this round (one scalar; stop rule only)
         nf = int(sum(counts))
-        if int(tot.item()) == 0 or nf == 0:
+        if n_multi == 0 or nf == 0:
             cont = False
         if nf > 0:
             all_cj.append(cj.cpu().numpy())

@@ -61,6 +61,9 @@ class QSFT:
         if dist is not None and dist.world_size > 1:
             from .dist import peel_sharded
             finds = peel_sharded(prob, U, dist)
+            if kwargs.get("device_result", False):
+                self.last_stats = {"rounds": int(finds[4]), "finds": int(len(finds[0])), "cutoff": float(cutoff)}
+                return {"find_cj": finds[0], "find_k": finds[1], "find_rho": finds[2], "find_round": finds[3]}
         else:
             prob.alloc(max_finds=min(15 * C * B, max(4096, 4 * C * B)))
             n_finds, n_rounds = prob.peel(U)
@@ -103,15 +106,35 @@ class QSFT:
         if len(cj) == 0:
             return {}, np.zeros((0, k.shape[1] if k.ndim == 2 else 0), dtype=np.int64)
         order = np.lexsort((cj, rnd))
-        k, rho = k[order].astype(np.int64), rho[order].astype(np.complex128)
-        uniq, first, inv = np.unique(k, axis=0, return_index=True, return_inverse=True)
-        inv = inv.reshape(-1)
-        sums = np.zeros(len(uniq), dtype=np.complex128)
+        k, rho = k[order], rho[order].astype(np.complex128)
+        # group equal k: pack the digits into two uint64 words (>= 64 bits each is plenty: n <= 128 digits of < 2^7
+        # would not fit, so hash-free exact packing uses as many words as needed)
+        n = k.shape[1]
+        per_word = max(1, 64 // max(1, int(np.ceil(np.log2(max(2, int(k.max()) + 1))))))
+        bits = 64 // per_word
+        words = []
+        for w0 in range(0, n, per_word):
+            blk = k[:, w0:min(n, w0 + per_word)].astype(np.uint64)
+            weights = (np.uint64(1) << (np.uint64(bits) * np.arange(blk.shape[1] - 1, -1, -1, dtype=np.uint64)))
+            words.append(blk @ weights)
+        srt = np.lexsort(tuple(words[::-1]))
+        same = np.ones(len(k), dtype=bool)
+        for w in words:
+            ws = w[srt]
+            same[1:] &= ws[1:] == ws[:-1]
+        same[0] = False
+        gid_sorted = np.cumsum(~same) - 1                  # group id along the sorted order
+        inv = np.empty(len(k), dtype=np.int64)
+        inv[srt] = gid_sorted
+        ngroups = int(gid_sorted[-1]) + 1
+        sums = np.zeros(ngroups, dtype=np.complex128)
         np.add.at(sums, inv, rho)
-        cnt = np.bincount(inv, minlength=len(uniq))
+        cnt = np.bincount(inv, minlength=ngroups)
         mean = sums / cnt
+        first = np.full(ngroups, len(k), dtype=np.int64)
+        np.minimum.at(first, inv, np.arange(len(k)))
         seen = np.argsort(first, kind="stable")
-        keys = uniq[seen]
+        keys = k[first[seen]].astype(np.int64)
         vals = mean[seen]
         gwht = dict(zip(map(tuple, keys.tolist()), vals.tolist()))
         return gwht, keys
