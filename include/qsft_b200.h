@@ -52,6 +52,20 @@ int qsft_qary_to_dec(const int8_t* dig, int ld, int64_t N, int q, int n, uint64_
 int qsft_eval_synth(const int8_t* qdig, int64_t N, const int8_t* loc, const float* strengths, int64_t S,
                     int q, int n, int ld, float* out, int impl, void* stream);
 
+/* K1+K2 fused for lattice queries, q = 4 ("lattice-factorised evaluation", SURVEY section 7 option b).  Computes the
+ * same samples as qsft_query_lattice + qsft_eval_synth for every delay row of one (M, D) block,
+ *     out[p][l] = sum_s a_s w^<k_s, (M l + d_p) mod q>,   l in Z_q^b in lattice order,
+ * as a complex matrix product with K = S on the tensor cores: with h_s = M^T k_s and l = (l_hi, l_lo),
+ *     out[p][l_hi, l_lo] = sum_s i^<h_hi(s), l_hi> * ( a_s i^(<d_p, k_s> + <h_lo(s), l_lo>) ),
+ * left operand exact in int8 (0, +-1), right operand = a_s quantised to 3 balanced base-128 int8 limbs (absolute error
+ * <= 2^-21 max|a| per coefficient), int32 accumulation (UTCIMMA kind::i8), limbs recombined in the epilogue.
+ *   M (n, b) int8, D (P, n) int8 (unpadded, as for qsft_query_lattice), loc (S, ld) int8, strengths (S) complex64,
+ *   out (P, q^b) complex64.  Allocates stream-ordered scratch (cudaMallocAsync): ~ 6 S P q^ceil(b/2) bytes.
+ * qsft_eval_lattice_supported returns 1 when the shape is handled (q == 4, 7 <= b <= 14). */
+int qsft_eval_lattice_supported(int q, int n, int b, int P, int64_t S);
+int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths, int64_t S,
+                            int q, int n, int b, int P, int ld, float* out, void* stream);
+
 /* K3 -- batched b-dimensional length-q DFT, forward sign, scaled by 1/q^b, in place.  Replaces
  * SubsampledSignal._compute_subtransform + gwht (qsft/input_signal_subsampled.py:264-266, qsft/utils.py:31-36).
  *   x (batch, q^b) complex64.  Index <-> digits MSB first on both sides (C-order reshape [q]*b).            */

@@ -1,0 +1,465 @@
+// K2L: lattice-factorised synthetic evaluation (fused K1 + K2) for q = 4 -- SURVEY section 7, option (b).
+//
+// For the query lattice m = M l + d_p the phase splits as  <k_s, M l + d_p> = <h_s, l> + <k_s, d_p>,  h_s = M^T k_s mod q.
+// With l = (l_hi, l_lo) (b1 + b2 digits) the samples of delay row p are a complex matrix product
+//     X_p[l_hi, l_lo] = sum_s  A[l_hi, s] * Y_p[s, l_lo],   A = i^<h_hi(s), l_hi>,   Y_p = a_s i^(e_ps + <h_lo(s), l_lo>)
+// with K = S on the tensor cores and NO per-(query, support) epilogue.  A is exact in int8 (entries 0, +-1 after the
+// real embedding [[Re, -Im], [Im, Re]]); Y_p is a rotation (sign / swap, exact) of a_s quantised to three balanced
+// base-128 int8 limbs (21 bits + sign relative to max|a|), accumulated error-free in int32 (UTCIMMA kind::i8) and
+// recombined in the epilogue.  Replaces synt_exp/synt_src/synthetic_signal.py:100-118 evaluated on the indices of
+// qsft/input_signal_subsampled.py:183-206, for every delay row of one (M, D) block at once.
+//
+// GEMM tile: 128 rows of A' (64 l_hi x {re, im}) x 128 columns (l_lo) x 3 limb accumulators (384 TMEM columns);
+// K' = 2S bytes streamed in 128-byte slabs through a 3-stage TMA/mbarrier ring (A slab 16 KB + 3 limb slabs 48 KB).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int LT_BM = 128, LT_BN = 128, LT_BK = 128, LT_STAGES = 3, LT_LIMBS = 3, LT_THREADS = 192;
+constexpr int LT_STAGE_BYTES = LT_BM * LT_BK + LT_LIMBS * LT_BN * LT_BK;   // 64 KB
+constexpr size_t LT_SMEM = 1024 + (size_t)LT_STAGES * LT_STAGE_BYTES + 256;
+constexpr int LT_SCALE_BITS = 20;
+
+__device__ __forceinline__ uint32_t lt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lt_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lt_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lt_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lt_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lt_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LT_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra LT_WAIT_DONE;\n\t"
+        "bra LT_WAIT_LOOP;\n\t"
+        "LT_WAIT_DONE:\n\t"
+        "}" ::"r"(lt_smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void lt_tma_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            lt_smem_u32(dst)),
+        "l"(map), "r"(lt_smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void lt_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(lt_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void lt_umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void lt_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// K-major tile, 128-byte rows, 128-byte swizzle: SBO = 1024 bytes, LBO unused, descriptor version 1
+__device__ __forceinline__ uint64_t lt_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// sum_i digit_i(a) * digit_i(b) mod 4 over nd base-4 digits packed two bits each
+__device__ __forceinline__ uint32_t dot4(uint32_t a, uint32_t b, int nd) {
+    uint32_t acc = 0;
+    for (int i = 0; i < nd; ++i) {
+        acc += ((a >> (2 * i)) & 3u) * ((b >> (2 * i)) & 3u);
+    }
+    return acc & 3u;
+}
+
+// ---- operand generation -----------------------------------------------------------------------------------
+// per support element: bin hash halves (h_hi, h_lo) and the delay phases e[p][s] = <d_p, k_s> mod 4
+__global__ void lt_prep_kernel(const int8_t* __restrict__ M, const int8_t* __restrict__ D, const int8_t* __restrict__ loc,
+                               long long S, int n, int b, int b1, int P, int ld, uint32_t* __restrict__ hhi,
+                               uint32_t* __restrict__ hlo, uint8_t* __restrict__ e) {
+    extern __shared__ int8_t lt_sm[];
+    int8_t* sM = lt_sm;             // (n, b)
+    int8_t* sD = lt_sm + n * b;     // (P, n)
+    for (int i = threadIdx.x; i < n * b; i += blockDim.x) sM[i] = M[i];
+    for (int i = threadIdx.x; i < P * n; i += blockDim.x) sD[i] = D[i];
+    __syncthreads();
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    int8_t k[QSFT_MAX_N];
+    const int8_t* row = loc + (size_t)s * ld;
+    for (int u = 0; u < n; ++u) k[u] = row[u];
+    uint32_t hi = 0, lo = 0;
+    for (int i = 0; i < b; ++i) {
+        int acc = 0;
+        for (int u = 0; u < n; ++u) acc += (int)sM[u * b + i] * (int)k[u];
+        if (i < b1) hi = (hi << 2) | (uint32_t)(acc & 3);
+        else lo = (lo << 2) | (uint32_t)(acc & 3);
+    }
+    hhi[s] = hi;
+    hlo[s] = lo;
+    for (int p = 0; p < P; ++p) {
+        int acc = 0;
+        for (int u = 0; u < n; ++u) acc += (int)sD[p * n + u] * (int)k[u];
+        e[(size_t)p * S + s] = (uint8_t)(acc & 3);
+    }
+}
+
+__global__ void lt_amax_kernel(const float2* __restrict__ a, long long S, unsigned int* __restrict__ amax_bits) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 0.f;
+    if (s < S) m = fmaxf(fabsf(a[s].x), fabsf(a[s].y));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));   // non-negative floats order like uints
+}
+
+// balanced base-128 limbs of round(x * scale): v = (l0 * 128 + l1) * 128 + l2, limbs in [-64, 64]
+__device__ __forceinline__ void limbs3(float x, float scale, int (&l)[3]) {
+    int v = __float2int_rn(x * scale);
+    int l2 = ((v + 64) & 127) - 64;
+    v = (v - l2) >> 7;
+    int l1 = ((v + 64) & 127) - 64;
+    v = (v - l1) >> 7;
+    l[0] = v; l[1] = l1; l[2] = l2;
+}
+
+// alimb[s] = {re limbs 0..2, im limbs 0..2, pad, pad} as int8x8
+__global__ void lt_quant_kernel(const float2* __restrict__ a, long long S, const unsigned int* __restrict__ amax_bits,
+                                float* __restrict__ inv_scale, int2* __restrict__ alimb) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float amax = __uint_as_float(*amax_bits);
+    const float scale = amax > 0.f ? (float)((1 << LT_SCALE_BITS) - 1) / amax : 0.f;
+    if (s == 0) *inv_scale = amax > 0.f ? amax / (float)((1 << LT_SCALE_BITS) - 1) : 0.f;
+    if (s >= S) return;
+    int lr[3], li[3];
+    limbs3(a[s].x, scale, lr);
+    limbs3(a[s].y, scale, li);
+    uint32_t w0 = (uint32_t)(lr[0] & 0xff) | ((uint32_t)(lr[1] & 0xff) << 8) | ((uint32_t)(lr[2] & 0xff) << 16);
+    uint32_t w1 = (uint32_t)(li[0] & 0xff) | ((uint32_t)(li[1] & 0xff) << 8) | ((uint32_t)(li[2] & 0xff) << 16);
+    alimb[s] = make_int2((int)w0, (int)w1);
+}
+
+// A'[2 l_hi + part][2 s + comp]:  part 0 (Re row): (er, -ei),  part 1 (Im row): (ei, er),  (er, ei) = i^<h_hi(s), l_hi>
+__global__ void lt_agen_kernel(const uint32_t* __restrict__ hhi, long long S, int b1, long long Kp,
+                               uint32_t* __restrict__ A) {
+    const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // two support elements = 4 K' bytes
+    const uint32_t lhi = blockIdx.y;
+    if (pair * 4 >= Kp) return;
+    uint32_t wre = 0, wim = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const long long s = 2 * pair + h;
+        if (s < S) {
+            const uint32_t t = dot4(hhi[s], lhi, b1);
+            const int er = (t == 0) - (t == 2), ei = (t == 1) - (t == 3);
+            wre |= ((uint32_t)(er & 0xff) | ((uint32_t)((-ei) & 0xff) << 8)) << (16 * h);
+            wim |= ((uint32_t)(ei & 0xff) | ((uint32_t)(er & 0xff) << 8)) << (16 * h);
+        }
+    }
+    A[((size_t)(2 * lhi) * Kp) / 4 + pair] = wre;
+    A[((size_t)(2 * lhi + 1) * Kp) / 4 + pair] = wim;
+}
+
+// B'_l[p * Nlo + l_lo][2 s + comp] = limb l of (Re, Im) of a_s * i^(e[p][s] + <h_lo(s), l_lo>)
+__global__ void lt_bgen_kernel(const uint32_t* __restrict__ hlo, const uint8_t* __restrict__ e, const int2* __restrict__ alimb,
+                               long long S, int b2, int P, long long Nlo, long long Kp, uint32_t* __restrict__ Bq) {
+    const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t llo = blockIdx.y;
+    if (pair * 4 >= Kp) return;
+    uint32_t tlo[2] = {0, 0};
+    int lr[2][3], li[2][3];
+    bool live[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const long long s = 2 * pair + h;
+        live[h] = s < S;
+        int2 w = live[h] ? alimb[s] : make_int2(0, 0);
+        if (live[h]) tlo[h] = dot4(hlo[s], llo, b2);
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            lr[h][l] = (int)(int8_t)((uint32_t)w.x >> (8 * l));
+            li[h][l] = (int)(int8_t)((uint32_t)w.y >> (8 * l));
+        }
+    }
+    const size_t Ntot = (size_t)P * Nlo;
+    for (int p = 0; p < P; ++p) {
+        uint32_t word[3] = {0, 0, 0};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long s = 2 * pair + h;
+            const uint32_t r = live[h] ? ((tlo[h] + e[(size_t)p * S + s]) & 3u) : 0u;
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                // (x, y) * i^r
+                const int x = lr[h][l], y = li[h][l];
+                const int yr = (r == 0) ? x : (r == 1) ? -y : (r == 2) ? -x : y;
+                const int yi = (r == 0) ? y : (r == 1) ? x : (r == 2) ? -y : -x;
+                word[l] |= ((uint32_t)(yr & 0xff) | ((uint32_t)(yi & 0xff) << 8)) << (16 * h);
+            }
+        }
+        const size_t rowi = (size_t)p * Nlo + llo;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) Bq[(((size_t)l * Ntot + rowi) * Kp) / 4 + pair] = word[l];
+    }
+}
+
+// ---- the GEMM ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LT_THREADS, 1)
+lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int nkb, int Ntot,
+               int Mhi, int Nlo, const float* __restrict__ inv_scale_ptr, float2* __restrict__ out) {
+    extern __shared__ uint8_t lt_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)lt_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)LT_STAGES * LT_STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + LT_STAGES;
+    uint64_t* tfull = bars + 2 * LT_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mtile = blockIdx.x, ntile = blockIdx.y;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < LT_STAGES; ++i) {
+            lt_mbar_init(&full[i], 1);
+            lt_mbar_init(&empty[i], 1);
+        }
+        lt_mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lt_smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int stage = kb % LT_STAGES;
+                const uint32_t ph = (uint32_t)(kb / LT_STAGES) & 1u;
+                lt_mbar_wait(&empty[stage], ph ^ 1u);
+                lt_mbar_expect_tx(&full[stage], LT_STAGE_BYTES);
+                uint8_t* st = base + (size_t)stage * LT_STAGE_BYTES;
+                lt_tma_2d(st, &tmA, kb * LT_BK, mtile * LT_BM, &full[stage]);
+#pragma unroll
+                for (int l = 0; l < LT_LIMBS; ++l)
+                    lt_tma_2d(st + LT_BM * LT_BK + l * (LT_BN * LT_BK), &tmB, kb * LT_BK, l * Ntot + ntile * LT_BN, &full[stage]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LT_BN >> 3) << 17) |
+                                       ((uint32_t)(LT_BM >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int stage = kb % LT_STAGES;
+                const uint32_t ph = (uint32_t)(kb / LT_STAGES) & 1u;
+                lt_mbar_wait(&full[stage], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = lt_smem_u32(base + (size_t)stage * LT_STAGE_BYTES);
+                const uint64_t adesc = lt_desc(sa);
+#pragma unroll
+                for (int l = 0; l < LT_LIMBS; ++l) {
+                    const uint64_t bdesc = lt_desc(sa + LT_BM * LT_BK + l * (LT_BN * LT_BK));
+#pragma unroll
+                    for (int k = 0; k < LT_BK / 32; ++k)
+                        lt_umma_i8(tmem_base + (uint32_t)(l * LT_BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                   (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                lt_commit(&empty[stage]);
+            }
+            lt_commit(tfull);
+        }
+    } else {
+        // epilogue: row r = 2 * l_hi_local + part lives in TMEM lane r; neighbouring lanes hold (Re, Im) of one l_hi
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int lhi = (mtile * LT_BM + row) >> 1;
+        const bool odd = lane & 1;
+        const int tiles_per_p = Nlo / LT_BN;
+        const int p = ntile / tiles_per_p;
+        const int llo0 = (ntile - p * tiles_per_p) * LT_BN;
+        const double inv_scale = (double)(*inv_scale_ptr);
+        lt_mbar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float2* orow = out + ((size_t)p * Mhi + lhi) * Nlo + llo0;
+#pragma unroll 1
+        for (int ch = 0; ch < LT_BN / 16; ++ch) {
+            uint32_t a0[16], a1[16], a2[16];
+            lt_ld16(taddr + (uint32_t)(0 * LT_BN + ch * 16), a0);
+            lt_ld16(taddr + (uint32_t)(1 * LT_BN + ch * 16), a1);
+            lt_ld16(taddr + (uint32_t)(2 * LT_BN + ch * 16), a2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float val[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const long long v = ((long long)(int)a0[j] * 128 + (long long)(int)a1[j]) * 128 + (long long)(int)a2[j];
+                val[j] = (float)((double)v * inv_scale);
+            }
+            // even lane (Re row) keeps columns 0..7, odd lane (Im row) keeps columns 8..15
+            float2 o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float send = odd ? val[j] : val[8 + j];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                o[j] = odd ? make_float2(recv, val[8 + j]) : make_float2(val[j], recv);
+            }
+            float4* dst = reinterpret_cast<float4*>(orow + ch * 16 + (odd ? 8 : 0));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[2 * j].x, o[2 * j].y, o[2 * j + 1].x, o[2 * j + 1].y);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int lt_make_map(CUtensorMap* map, const void* ptr, long long rows, long long kbytes) {
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    if (!enc) {
+        qsft_set_error("cuTensorMapEncodeTiled entry point not available");
+        return QSFT_ECUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kbytes};
+    cuuint32_t box[2] = {LT_BK, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        qsft_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld k=%lld)", (int)r, rows, kbytes);
+        return QSFT_ECUDA;
+    }
+    return QSFT_OK;
+}
+
+}  // namespace
+
+extern "C" int qsft_eval_lattice_supported(int q, int n, int b, int P, int64_t S) {
+    if (q != 4 || n < 1 || n > QSFT_MAX_N || P < 1 || S < 1) return 0;
+    const int b1 = b / 2, b2 = b - b1;
+    if (b1 < 3 || b2 < 4 || b > 14) return 0;                // 2 * 4^b1 >= 128 rows, 4^b2 >= 256 columns, grid.y limits
+    if ((long long)P * ipow64(4, b2) * 3 >= 0x7fffffffLL) return 0;
+    return 1;
+}
+
+extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths,
+                                       int64_t S, int q, int n, int b, int P, int ld, float* out, void* stream) {
+    QSFT_CHECK_ARG(qsft_eval_lattice_supported(q, n, b, P, S), "lattice evaluation supports q = 4, 7 <= b <= 14 only");
+    QSFT_CHECK_ARG(M && D && loc && strengths && out, "null pointer");
+    QSFT_CHECK_ARG(ld >= n && ld % 16 == 0, "bad ld");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int b1 = b / 2, b2 = b - b1;
+    const long long Mhi = ipow64(4, b1), Nlo = ipow64(4, b2);
+    const long long Kp = (2 * S + LT_BK - 1) / LT_BK * LT_BK;
+    const long long Ntot = (long long)P * Nlo;
+    // stream-ordered workspace
+    uint32_t *hhi = nullptr, *hlo = nullptr;
+    uint8_t* e = nullptr;
+    int2* alimb = nullptr;
+    unsigned int* amax = nullptr;
+    float* inv_scale = nullptr;
+    uint8_t *A = nullptr, *Bq = nullptr;
+    int rc = QSFT_OK;
+    static bool pool_tuned = false;
+    if (!pool_tuned) {  // keep the (large) operand workspace cached in the stream-ordered pool between calls
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_tuned = true;
+    }
+    auto alloc = [&](void** p, size_t bytes) {
+        if (rc == QSFT_OK && cudaMallocAsync(p, bytes, st) != cudaSuccess) {
+            qsft_set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+            rc = QSFT_ECUDA;
+        }
+    };
+    alloc((void**)&hhi, (size_t)S * 4);
+    alloc((void**)&hlo, (size_t)S * 4);
+    alloc((void**)&e, (size_t)P * S);
+    alloc((void**)&alimb, (size_t)S * 8);
+    alloc((void**)&amax, 8);
+    alloc((void**)&A, (size_t)2 * Mhi * Kp);
+    alloc((void**)&Bq, (size_t)LT_LIMBS * Ntot * Kp);
+    inv_scale = amax ? reinterpret_cast<float*>(amax + 1) : nullptr;
+    if (rc == QSFT_OK) {
+        const int T = 256;
+        const unsigned sb = (unsigned)((S + T - 1) / T);
+        cudaMemsetAsync(amax, 0, 8, st);
+        lt_prep_kernel<<<sb, T, (size_t)n * b + (size_t)P * n, st>>>(M, D, loc, S, n, b, b1, P, ld, hhi, hlo, e);
+        lt_amax_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax);
+        lt_quant_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax, inv_scale, alimb);
+        const unsigned pb = (unsigned)((Kp / 4 + T - 1) / T);
+        lt_agen_kernel<<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, S, b1, Kp, reinterpret_cast<uint32_t*>(A));
+        lt_bgen_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, e, alimb, S, b2, P, Nlo, Kp, reinterpret_cast<uint32_t*>(Bq));
+        g_qsft_launches.fetch_add(5, std::memory_order_relaxed);
+        CUtensorMap ma, mb;
+        rc = lt_make_map(&ma, A, 2 * Mhi, Kp);
+        if (!rc) rc = lt_make_map(&mb, Bq, LT_LIMBS * Ntot, Kp);
+        if (!rc) {
+            static bool attr = false;
+            if (!attr) {
+                if (cudaFuncSetAttribute(lt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess) {
+                    qsft_set_error("cudaFuncSetAttribute failed");
+                    rc = QSFT_ECUDA;
+                }
+                attr = true;
+            }
+        }
+        if (!rc) {
+            dim3 grid((unsigned)(2 * Mhi / LT_BM), (unsigned)(Ntot / LT_BN));
+            lt_gemm_kernel<<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Ntot, (int)Mhi, (int)Nlo, inv_scale,
+                                                              reinterpret_cast<float2*>(out));
+            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+            cudaError_t ce = cudaGetLastError();
+            if (ce != cudaSuccess) {
+                qsft_set_error("lattice GEMM launch failed: %s", cudaGetErrorString(ce));
+                rc = QSFT_ECUDA;
+            }
+        }
+    }
+    void* frees[] = {hhi, hlo, e, alimb, amax, A, Bq};
+    for (void* p : frees)
+        if (p) cudaFreeAsync(p, st);
+    return rc;
+}

@@ -141,6 +141,9 @@ class SubsampledSignal(Signal):
         B = self.q ** self.b
         rows = D_rows.shape[0]
         if self.device_subsample:
+            fused = self.subsample_lattice_device(M, D_rows)
+            if fused is not None:
+                return fused
             idx, dig = ops.query_lattice(M, D_rows, self.q, device=self.device, want_idx=False, want_digits=True,
                                          ld=self.ld)
             return self.subsample_device(dig.view(rows * B, self.ld)).view(rows, B)
@@ -154,6 +157,10 @@ class SubsampledSignal(Signal):
             flat = np.asarray(self.subsample(np.concatenate(query_indices)))
             out[:] = flat.reshape(rows, B)
         return torch.from_numpy(out.astype(np.complex64)).to(self.device)
+
+    def subsample_lattice_device(self, M, D_rows):
+        """Optional fused lattice sampler: samples (rows, B) of {M l + d_p}, or None to use K1 + subsample_device."""
+        return None
 
     def _compute_subtransform(self, samples, b):
         """gwht of every row restricted to the sub-lattice of the first b columns of M

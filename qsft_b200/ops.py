@@ -135,6 +135,29 @@ def eval_synth(qdig, loc, strengths, q, n, out=None, impl=0):
     return out
 
 
+def lattice_supported(q, n, b, P, S):
+    return bool(_lib.lib().qsft_eval_lattice_supported(q, n, b, P, S))
+
+
+def eval_synth_lattice(M, D, loc, strengths, q, out=None):
+    """Fused K1+K2 for the lattice {M l + d_p} (q = 4): M (n, b), D (P, n) integer arrays, loc (S, ld) int8 device,
+    strengths (S,) complex64 device -> samples (P, q^b) complex64."""
+    _need_cuda(loc, strengths)
+    M = np.ascontiguousarray(M, dtype=np.int8)
+    D = np.ascontiguousarray(D, dtype=np.int8)
+    n, b = M.shape
+    P = D.shape[0]
+    S, ld = loc.shape
+    dev = loc.device
+    Md, Dd = torch.from_numpy(M).to(dev), torch.from_numpy(D).to(dev)
+    if out is None:
+        out = torch.empty((P, q ** b), dtype=torch.complex64, device=dev)
+    with torch.cuda.device(dev), _timed("k2_eval_lattice", P * (q ** b) * S):
+        _lib.check(_lib.lib().qsft_eval_synth_lattice(_ptr(Md), _ptr(Dd), _ptr(loc), _ptr(strengths), S, q, n, b, P, ld,
+                                                      _ptr(out), _stream()))
+    return out
+
+
 def gwht_batch_(x, q, b):
     """K3, in place.  x (..., q^b) complex64 contiguous."""
     _need_cuda(x)

@@ -267,3 +267,58 @@ def test_peel_large_closed_form_exact_recovery():
     assert set(gw.keys()) == set(sw.keys())
     err = max(abs(gw[k] - v) for k, v in sw.items())
     assert err < 1e-5, err
+
+
+# ---- K2L: lattice-factorised evaluation (q = 4) -----------------------------------------------------------
+@pytest.mark.parametrize("n,b,S,P,seed", [(14, 7, 700, 5, 0), (40, 8, 3000, 3, 1), (40, 10, 257, 2, 2), (20, 9, 64, 4, 3),
+                                          (33, 7, 1, 1, 4)])
+def test_k2_lattice_matches_plain_path_and_oracle(n, b, S, P, seed):
+    q = 4
+    rng = np.random.default_rng(seed)
+    M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
+    loc = rng.integers(0, q, (n, S))
+    a = rng.uniform(0.2, 2, S) * np.exp(1j * rng.uniform(0, 2 * np.pi, S))
+    ld = utils.padded_ld(n)
+    loc_d = ops.pad_digits(loc.T, ld, DEV)
+    a_d = torch.from_numpy(a.astype(np.complex64)).to(DEV)
+    assert ops.lattice_supported(q, n, b, P, S)
+    got = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
+    _, dig = ops.query_lattice(M, D, q, device=DEV, want_idx=False, want_digits=True, ld=ld)
+    plain = ops.eval_synth(dig.view(-1, ld), loc_d, a_d, q, n, impl=1).view(P, q ** b)
+    scale = float(np.sqrt(np.sum(np.abs(a) ** 2)))
+    assert torch.max(torch.abs(got - plain)).item() <= 3e-6 * scale + 2e-6 * float(np.max(np.abs(a))) * np.sqrt(S)
+    # oracle on a sample of lattice points of delay row P-1
+    ls = rng.integers(0, q ** b, 200)
+    L = np.stack([(ls // q ** (b - 1 - i)) % q for i in range(b)])
+    qd = (((M @ L) % q + D[P - 1][:, None]) % q).T
+    want = orc.synth_eval_digits(qd, loc, a, q)
+    assert np.max(np.abs(got[P - 1].cpu().numpy()[ls] - want)) <= 3e-6 * scale + 2e-6 * float(np.max(np.abs(a))) * np.sqrt(S)
+
+
+def test_k2_lattice_unsupported_shapes():
+    assert not ops.lattice_supported(3, 10, 8, 3, 100)       # q != 4
+    assert not ops.lattice_supported(4, 10, 4, 3, 100)       # b too small
+    loc = torch.zeros((4, 32), dtype=torch.int8, device=DEV)
+    a = torch.ones(4, dtype=torch.complex64, device=DEV)
+    with pytest.raises(qsft_b200.QsftError):
+        ops.eval_synth_lattice(np.zeros((10, 4), int), np.zeros((2, 10), int), loc, a, 4)
+
+
+@pytest.mark.parametrize("impl", [2, 3, 0])
+def test_construct_and_transform_all_eval_impls_agree(impl):
+    """q = 4, b = 7 (lattice path eligible): the three evaluation kernels give the same bins and the same transform."""
+    n, q, S, b, C, R = 16, 4, 900, 7, 3, 2
+    qa = {"query_method": "complex", "num_subsample": C, "delays_method_source": "identity", "subsampling_method": "qsft",
+          "delays_method_channel": "nso", "num_repeat": R, "b": b}
+    np.random.seed(12)
+    sig = qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=0.5, a_max=1.5, noise_sd=0.0,
+                                                  query_args=dict(qa), eval_impl=impl)
+    for c in range(C):
+        for r in range(R):
+            want = orc.closed_form_bins(sig.Ms[c], sig.Ds[c][r], np.asarray(sig.locq), sig.strengths, q)
+            got = sig.Us[c][r][b].cpu().numpy()
+            assert np.max(np.abs(got - want)) <= 2e-6 * np.max(np.abs(want)) + 1e-7
+    res = qsft_b200.QSFT(num_subsample=C, num_repeat=R, b=b, reconstruct_method_source="identity",
+                         reconstruct_method_channel="nso").transform(sig)
+    assert set(res.keys()) == set(sig.signal_w.keys())
+    assert max(abs(res[k] - v) for k, v in sig.signal_w.items()) < 1e-5

@@ -50,14 +50,15 @@ def _run_sharded(world, make_problem, U0):
     def work(rank):
         try:
             torch.cuda.set_device(0)
-            with torch.cuda.stream(torch.cuda.Stream()):
-                prob = make_problem()
-                results[rank] = peel_sharded(prob, U0.clone(), ThreadDist(rank, world, shared))
-                torch.cuda.synchronize()
+            # all simulated ranks share the default stream: tensors handed between threads stay allocator-safe
+            prob = make_problem()
+            results[rank] = peel_sharded(prob, U0.clone(), ThreadDist(rank, world, shared))
+            torch.cuda.synchronize()
         except Exception as exc:  # pragma: no cover
             errors.append(exc)
             shared["bar"].abort()
 
+    torch.cuda.synchronize()
     threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
     [t.start() for t in threads]
     [t.join() for t in threads]
