@@ -5,6 +5,7 @@ same order), hands the bins to the on-device peeling loop (csrc/k4_peel.cu) and 
 the reference's result dict {tuple(k): complex}."""
 from __future__ import annotations
 
+import itertools
 import time
 
 import numpy as np
@@ -102,39 +103,42 @@ class QSFT:
     @staticmethod
     def _finds_to_dict(cj, k, rho, rnd):
         """Finds -> {tuple(k): mean of all rho found for k} in the reference's first-seen order
-        (result list order = round, then (i, j); averaging qsft.py:247-255)."""
-        if len(cj) == 0:
-            return {}, np.zeros((0, k.shape[1] if k.ndim == 2 else 0), dtype=np.int64)
+        (result list order = round, then (i, j); averaging qsft.py:247-255).  k (finds, n) small non-negative ints."""
+        nf = len(cj)
+        n = k.shape[1] if k.ndim == 2 else 0
+        if nf == 0:
+            return {}, np.zeros((0, n), dtype=np.int64)
         order = np.lexsort((cj, rnd))
-        k, rho = k[order], rho[order].astype(np.complex128)
-        # group equal k: pack the digits into two uint64 words (>= 64 bits each is plenty: n <= 128 digits of < 2^7
-        # would not fit, so hash-free exact packing uses as many words as needed)
-        n = k.shape[1]
-        per_word = max(1, 64 // max(1, int(np.ceil(np.log2(max(2, int(k.max()) + 1))))))
-        bits = 64 // per_word
-        words = []
-        for w0 in range(0, n, per_word):
-            blk = k[:, w0:min(n, w0 + per_word)].astype(np.uint64)
-            weights = (np.uint64(1) << (np.uint64(bits) * np.arange(blk.shape[1] - 1, -1, -1, dtype=np.uint64)))
-            words.append(blk @ weights)
-        srt = np.lexsort(tuple(words[::-1]))
-        same = np.ones(len(k), dtype=bool)
-        for w in words:
-            ws = w[srt]
-            same[1:] &= ws[1:] == ws[:-1]
-        same[0] = False
-        gid_sorted = np.cumsum(~same) - 1                  # group id along the sorted order
-        inv = np.empty(len(k), dtype=np.int64)
+        k8 = np.ascontiguousarray(k[order], dtype=np.uint8)
+        rho = rho[order].astype(np.complex128)
+        # group equal rows: 64-bit words of the zero-padded digit rows, mixed into one hash; ties verified exactly
+        nw = (n + 7) // 8
+        padded = np.zeros((nf, nw * 8), dtype=np.uint8)
+        padded[:, :n] = k8
+        words = padded.view(np.uint64)                              # (finds, nw)
+        mult = (np.arange(nw, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0xD6E8FEB86659FD93)) | np.uint64(1)
+        with np.errstate(over="ignore"):
+            h = np.bitwise_xor.reduce((words * mult) ^ ((words * mult) >> np.uint64(29)), axis=1)
+        srt = np.argsort(h, kind="stable")
+        ws = words[srt]
+        same = np.zeros(nf, dtype=bool)
+        same[1:] = np.all(ws[1:] == ws[:-1], axis=1)
+        if np.any((h[srt][1:] == h[srt][:-1]) & ~same[1:]):          # hash collision between different k: exact fallback
+            srt = np.lexsort(tuple(words[:, i] for i in range(nw - 1, -1, -1)))
+            ws = words[srt]
+            same[1:] = np.all(ws[1:] == ws[:-1], axis=1)
+        gid_sorted = np.cumsum(~same) - 1
+        inv = np.empty(nf, dtype=np.int64)
         inv[srt] = gid_sorted
         ngroups = int(gid_sorted[-1]) + 1
         sums = np.zeros(ngroups, dtype=np.complex128)
         np.add.at(sums, inv, rho)
         cnt = np.bincount(inv, minlength=ngroups)
         mean = sums / cnt
-        first = np.full(ngroups, len(k), dtype=np.int64)
-        np.minimum.at(first, inv, np.arange(len(k)))
+        first = np.full(ngroups, nf, dtype=np.int64)
+        np.minimum.at(first, inv, np.arange(nf))
         seen = np.argsort(first, kind="stable")
-        keys = k[first[seen]].astype(np.int64)
+        keys8 = k8[first[seen]]
         vals = mean[seen]
-        gwht = dict(zip(map(tuple, keys.tolist()), vals.tolist()))
-        return gwht, keys
+        gwht = dict(zip(itertools.batched(keys8.tobytes(), n), vals.tolist()))     # tuple(k) -> complex
+        return gwht, keys8.astype(np.int64)
