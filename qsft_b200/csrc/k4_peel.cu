@@ -197,15 +197,26 @@ __device__ bool rs_decode(const PeelDev& d, const uint8_t* sym, uint8_t* kout) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// classification: one thread per bin
+// classification.  Phase 1: one THREAD per bin computes the energy (lanes over consecutive bins -> coalesced row
+// reads; this is the HBM-bound part).  Phase 2: the WARP walks over its non-zeroton bins one at a time with lanes
+// over the delay rows (the rows were just read, so these loads hit L1/L2): all P_src-1 symbols are detected in
+// parallel, then rho / residual / bin hash are warp reductions.  No divergent per-thread detection.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 template <int NW>
 __global__ void __launch_bounds__(K4_THREADS)
 k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, long long j_end,
                    long long* __restrict__ find_cj, int8_t* __restrict__ find_k, float2* __restrict__ find_rho,
                    int32_t* __restrict__ find_round, int32_t* __restrict__ find_id, long long max_finds, int round,
                    unsigned long long* __restrict__ counters) {
-    __shared__ double2 s_tw[QSFT_MAX_Q + 1];   // w^t = (cos, sin)(2 pi t / q)
+    __shared__ double2 s_tw[QSFT_MAX_Q + 1];                       // w^t = (cos, sin)(2 pi t / q)
+    __shared__ __align__(16) uint8_t s_sym[K4_THREADS / 32][QSFT_MAX_N];   // detected symbols of the warp's current bin
+    __shared__ __align__(16) uint8_t s_k[K4_THREADS / 32][QSFT_MAX_N];     // decoded k digits (zero padded)
     if (threadIdx.x < d.q) {
         double sn, cs;
         sincospi(2.0 * (double)threadIdx.x / (double)d.q, &sn, &cs);
@@ -213,120 +224,138 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
     }
     __syncthreads();
     const int c = blockIdx.y;
-    const long long j = j_begin + (long long)blockIdx.x * K4_THREADS + threadIdx.x;
-    if (j >= j_end) return;
-    const float2* Uc = U + (size_t)c * d.P * d.B + j;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long jw = j_begin + (long long)blockIdx.x * K4_THREADS + warp * 32;   // first bin of this warp
+    const long long j = jw + lane;
     const long long B = d.B;
+    const float2* Uc = U + (size_t)c * d.P * B;
 
-    // energy test (qsft.py:164)
+    // phase 1: energy test (qsft.py:164)
     double energy = 0.0;
-    for (int p = 0; p < d.P; ++p) {
-        float2 v = Uc[(size_t)p * B];
-        energy += (double)v.x * v.x + (double)v.y * v.y;
+    if (j < j_end) {
+        const float2* col = Uc + j;
+        for (int p = 0; p < d.P; ++p) {
+            float2 v = col[(size_t)p * B];
+            energy += (double)v.x * v.x + (double)v.y * v.y;
+        }
+        if (!(energy > d.thresh)) find_id[(size_t)c * B + j] = -1;
     }
-    if (!(energy > d.thresh)) {
-        find_id[(size_t)c * B + j] = -1;
-        return;
-    }
+    unsigned mask = __ballot_sync(0xffffffffu, j < j_end && energy > d.thresh);
+    if (mask == 0) return;
 
-    // singleton detection -> symbols (reconstruct.py)
     const int nsym = d.P_src - 1;
-    uint8_t sym[QSFT_MAX_N];
     const double qd = (double)d.q;
-    if (d.channel == 0) {
-        float2 v0 = Uc[0];
-        const double a0 = atan2((double)v0.y, (double)v0.x);
-        for (int i = 1; i <= nsym; ++i) {
-            float2 v = Uc[(size_t)i * B];
-            const double a = atan2((double)v.y, (double)v.x);
-            const double val = qd * (a - a0) / kTwoPi;
-            long long r = (long long)rint(val);          // half-to-even like np.round
-            int m = (int)(r % d.q);
-            sym[i - 1] = (uint8_t)(m < 0 ? m + d.q : m);
-        }
-    } else {
-        const double step = kTwoPi / qd;
-        float2 zc[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) zc[r] = r < d.R ? Uc[(size_t)(r * d.P_src) * B] : make_float2(0.f, 0.f);
-        for (int i = 1; i <= nsym; ++i) {
-            double ar = 0.0, ai = 0.0;
-            for (int r = 0; r < d.R; ++r) {
-                float2 z = r < 8 ? zc[r] : Uc[(size_t)(r * d.P_src) * B];
-                float2 v = Uc[(size_t)(r * d.P_src + i) * B];
-                // z * conj(v)
-                ar += (double)z.x * v.x + (double)z.y * v.y;
-                ai += (double)z.y * v.x - (double)z.x * v.y;
-            }
-            ar /= d.R;
-            ai /= d.R;
-            double th = atan2(ai, ar);
-            if (th < 0.0) th += kTwoPi;                  // numpy: angle % (2 pi)
-            if (th >= kTwoPi) th -= kTwoPi;
-            int best = 0;
-            double bd = fabs(0.0 - th);
-            for (int m = 1; m <= d.q; ++m) {
-                double dist = fabs(step * (double)m - th);
-                if (dist < bd) {
-                    bd = dist;
-                    best = m;
-                }
-            }
-            sym[i - 1] = (uint8_t)(best % d.q);
-        }
-    }
-    uint8_t kd[QSFT_MAX_N];
-    if (d.source == 1) {
-        rs_decode(d, sym, kd);
-    } else {
-        for (int i = 0; i < d.n; ++i) kd[i] = sym[i];
-    }
-    uint32_t kw[NW];
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            int i = 4 * w + t;
-            if (i < d.n) word |= (uint32_t)kd[i] << (8 * t);
-        }
-        kw[w] = word;
-    }
-
-    // rho = <signature, col> / P with signature_p = w^(D_p . k)  (qsft.py:174-175)
-    double rr = 0.0, ri = 0.0;
     const int8_t* Dc = d.D + (size_t)c * d.P * d.ld;
-    for (int p = 0; p < d.P; ++p) {
-        const int t = dot_mod<NW>(Dc + (size_t)p * d.ld, d.ld, kw, d.q);
-        const double cs = s_tw[t].x, sn = s_tw[t].y;
-        float2 v = Uc[(size_t)p * B];
-        // conj(sig) * v
-        rr += cs * v.x + sn * v.y;
-        ri += cs * v.y - sn * v.x;
-    }
-    rr /= d.P;
-    ri /= d.P;
-    // ||col - rho sig||^2 = ||col||^2 - P |rho|^2 exactly (rho is the projection, |sig_p| = 1); fp64 keeps it accurate
-    const double res = energy - (double)d.P * (rr * rr + ri * ri);
-    const bool match = hash_bin<NW>(d, c, kw) == j;      // qsft.py:178-179
-    if (!match || res > d.thresh) {                      // qsft.py:183
-        find_id[(size_t)c * B + j] = -1;
-        atomicAdd(&counters[1], 1ull);
-        return;
-    }
-    const unsigned long long f = atomicAdd(&counters[0], 1ull);
-    if ((long long)f < max_finds) {
-        find_cj[f] = (long long)c * B + j;
-        uint32_t* ko = reinterpret_cast<uint32_t*>(find_k + (size_t)f * d.ld);
+    unsigned n_multi = 0;
+    while (mask) {
+        const int bi = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const long long jb = jw + bi;
+        const double e_b = __shfl_sync(0xffffffffu, energy, bi);
+        const float2* col = Uc + jb;
+
+        // singleton detection -> symbols, one delay row per lane (reconstruct.py)
+        for (int i0 = 1; i0 <= nsym; i0 += 32) {
+            const int i = i0 + lane;
+            if (i <= nsym) {
+                int symv;
+                if (d.channel == 0) {
+                    const float2 v0 = col[0];
+                    const float2 v = col[(size_t)i * B];
+                    const double a0 = atan2((double)v0.y, (double)v0.x);
+                    const double a = atan2((double)v.y, (double)v.x);
+                    const long long r = (long long)rint(qd * (a - a0) / kTwoPi);        // half-to-even like np.round
+                    const int m = (int)(r % d.q);
+                    symv = m < 0 ? m + d.q : m;
+                } else {
+                    double ar = 0.0, ai = 0.0;
+                    for (int r = 0; r < d.R; ++r) {
+                        const float2 z = col[(size_t)(r * d.P_src) * B];
+                        const float2 v = col[(size_t)(r * d.P_src + i) * B];
+                        ar += (double)z.x * v.x + (double)z.y * v.y;                     // z * conj(v)
+                        ai += (double)z.y * v.x - (double)z.x * v.y;
+                    }
+                    ar /= d.R;
+                    ai /= d.R;
+                    double th = atan2(ai, ar);
+                    if (th < 0.0) th += kTwoPi;                                          // numpy: angle % (2 pi)
+                    if (th >= kTwoPi) th -= kTwoPi;
+                    const double step = kTwoPi / qd;
+                    int best = 0;
+                    double bd = fabs(0.0 - th);
+                    for (int m = 1; m <= d.q; ++m) {                                     // argmin over q+1 roots, first minimum
+                        const double dist = fabs(step * (double)m - th);
+                        if (dist < bd) {
+                            bd = dist;
+                            best = m;
+                        }
+                    }
+                    symv = best % d.q;
+                }
+                s_sym[warp][i - 1] = (uint8_t)symv;
+            }
+        }
+        __syncwarp();
+        // k digits (zero padded to 4 * NW bytes)
+        if (d.source == 1) {
+            if (lane == 0) rs_decode(d, s_sym[warp], s_k[warp]);
+        } else {
+            for (int i = lane; i < d.n; i += 32) s_k[warp][i] = s_sym[warp][i];
+        }
+        for (int i = d.n + lane; i < 4 * NW && i < QSFT_MAX_N; i += 32) s_k[warp][i] = 0;
+        __syncwarp();
+        uint32_t kw[NW];
 #pragma unroll
-        for (int w = 0; w < NW; ++w) ko[w] = kw[w];
-        for (int w = NW; w < d.ld / 4; ++w) ko[w] = 0;
-        find_rho[f] = make_float2((float)rr, (float)ri);
-        if (find_round) find_round[f] = round;
-        find_id[(size_t)c * B + j] = (int32_t)f;
-    } else {
-        find_id[(size_t)c * B + j] = -1;
+        for (int w = 0; w < NW; ++w) kw[w] = reinterpret_cast<const uint32_t*>(s_k[warp])[w];
+
+        // rho = <signature, col> / P with signature_p = w^(D_p . k)  (qsft.py:174-175), lanes over delay rows
+        double rr = 0.0, ri = 0.0;
+        for (int p = lane; p < d.P; p += 32) {
+            const int t = dot_mod<NW>(Dc + (size_t)p * d.ld, d.ld, kw, d.q);
+            const double cs = s_tw[t].x, sn = s_tw[t].y;
+            const float2 v = col[(size_t)p * B];
+            rr += cs * v.x + sn * v.y;                                                   // conj(sig) * v
+            ri += cs * v.y - sn * v.x;
+        }
+        rr = warp_sum(rr) / d.P;
+        ri = warp_sum(ri) / d.P;
+        // ||col - rho sig||^2 = ||col||^2 - P |rho|^2 exactly (rho is the projection, |sig_p| = 1); fp64 keeps it accurate
+        const double res = e_b - (double)d.P * (rr * rr + ri * ri);
+        // bin hash j = dec(M_c^T k mod q) (qsft.py:178-179), one hash digit per lane
+        long long part = 0;
+        if (lane < d.b) {
+            long long wgt = 1;
+            for (int u = lane + 1; u < d.b; ++u) wgt *= d.q;
+            part = wgt * dot_mod<NW>(d.MT + ((size_t)c * d.b + lane) * d.ld, d.ld, kw, d.q);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        const bool single = (part == jb) && !(res > d.thresh);                          // qsft.py:183
+        if (!single) {
+            if (lane == 0) {
+                find_id[(size_t)c * B + jb] = -1;
+                ++n_multi;
+            }
+        } else {
+            unsigned long long f = 0;
+            if (lane == 0) f = atomicAdd(&counters[0], 1ull);
+            f = __shfl_sync(0xffffffffu, f, 0);
+            if ((long long)f < max_finds) {
+                uint32_t* ko = reinterpret_cast<uint32_t*>(find_k + (size_t)f * d.ld);
+                for (int w = lane; w < d.ld / 4; w += 32) ko[w] = (w < NW) ? reinterpret_cast<const uint32_t*>(s_k[warp])[w] : 0u;
+                if (lane == 0) {
+                    find_cj[f] = (long long)c * B + jb;
+                    find_rho[f] = make_float2((float)rr, (float)ri);
+                    if (find_round) find_round[f] = round;
+                    find_id[(size_t)c * B + jb] = (int32_t)f;
+                }
+            } else if (lane == 0) {
+                find_id[(size_t)c * B + jb] = -1;
+            }
+        }
+        __syncwarp();
     }
+    if (lane == 0 && n_multi) atomicAdd(&counters[1], (unsigned long long)n_multi);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -25,14 +25,17 @@ class DistContext:
         minef = torch.view_as_real(mine) if mine.is_complex() else mine
         td.all_gather_into_tensor(flat.reshape(-1), minef.reshape(-1), group=self.group)
 
-    def all_gather_var(self, tensors, count, cap):
+    def all_gather_var(self, tensors, count, cap, extra=0):
         """All-gather `count` leading rows of each tensor in `tensors` (fixed capacity `cap` per rank).
-        Returns (list of concatenated tensors, counts per rank)."""
+        Returns (list of concatenated tensors, counts per rank); the sum over ranks of the integer `extra` that
+        travelled with the counts is left in self.last_extra_sum (saves a separate all-reduce)."""
         dev = tensors[0].device
-        cnt = torch.tensor([count], dtype=torch.int64, device=dev)
-        counts = torch.empty(self.world_size, dtype=torch.int64, device=dev)
-        td.all_gather_into_tensor(counts, cnt, group=self.group)
-        counts = counts.cpu().tolist()
+        cnt = torch.tensor([count, int(extra)], dtype=torch.int64, device=dev)
+        allc = torch.empty(2 * self.world_size, dtype=torch.int64, device=dev)
+        td.all_gather_into_tensor(allc, cnt, group=self.group)
+        allc = allc.cpu().view(self.world_size, 2)
+        counts = allc[:, 0].tolist()
+        self.last_extra_sum = int(allc[:, 1].sum().item())
         m = max(counts)
         outs = []
         for t in tensors:
@@ -61,10 +64,10 @@ def bin_range(B, rank, world):
     return lo, min(B, lo + per)
 
 
-def peel_sharded(prob, U, dist, max_rounds=15):
+def peel_sharded(prob, U, dist, max_rounds=15, to_host=True):
     """Bin-sharded peeling loop (qsft.py:151-241 semantics).  Every rank holds the full U but only classifies and
     updates bins in its own j-range; finds are exchanged with one all-gather per round.
-    Returns (cj, k, rho, round, n_rounds) as NumPy arrays, identical on every rank."""
+    Returns (cj, k, rho, round, n_rounds), identical on every rank; NumPy arrays when to_host else CUDA tensors."""
     q, n, C, B = prob.q, prob.n, prob.C, prob.B
     dev = prob.device
     jb, je = bin_range(B, dist.rank, dist.world_size)
@@ -73,34 +76,41 @@ def peel_sharded(prob, U, dist, max_rounds=15):
     find_id_full = torch.empty((C, B), dtype=torch.int32, device=dev)
     all_cj, all_k, all_rho, all_round = [], [], [], []
     peeling_max = float(q) ** n
+    guard_can_bind = peeling_max <= 15.0 * C * B
     num_peeling, rnd, cont = 0, 0, True
     while cont and num_peeling < peeling_max and rnd < max_rounds:
         rnd += 1
         prob.counters.zero_()
         prob.classify(U, jb, je, rnd)
-        cnts = prob.counters.cpu().tolist()
+        cnts = prob.counters.cpu().tolist()               # the round's only host sync (find count + multiton count)
         nf_local, multi_local = int(cnts[0]), int(cnts[1])
         if nf_local > cap:
             raise RuntimeError("find buffer overflow in sharded peel")
-        (cj, k, rho), counts = dist.all_gather_var([prob.find_cj, prob.find_k, prob.find_rho], nf_local, cap)
-        n_multi = dist.all_reduce_sum(multi_local, dev)   # multitons this round (one scalar; stop rule only)
+        (cj, k, rho), counts = dist.all_gather_var([prob.find_cj, prob.find_k, prob.find_rho], nf_local, cap,
+                                                   extra=multi_local)
+        n_multi = dist.last_extra_sum
         nf = int(sum(counts))
         if n_multi == 0 or nf == 0:
             cont = False
         if nf > 0:
-            all_cj.append(cj.cpu().numpy())
-            all_k.append(k[:, :n].cpu().numpy())
-            all_rho.append(rho.cpu().numpy())
-            all_round.append(np.full(nf, rnd, dtype=np.int32))
-            if cont:
+            all_cj.append(cj)
+            all_k.append(k[:, :n])
+            all_rho.append(rho)
+            all_round.append(torch.full((nf,), rnd, dtype=torch.int32, device=dev))
+            if cont or guard_can_bind:
                 # rebuild the (C, B) find table for the whole round so "last (i, j) wins" can be checked locally
                 find_id_full.fill_(-1)
                 find_id_full.view(-1)[cj] = torch.arange(nf, dtype=torch.int32, device=dev)
-                owners = torch.zeros(1, dtype=torch.int64, device=dev)
+                owners = torch.zeros(1, dtype=torch.int64, device=dev) if guard_can_bind else None
                 prob.apply(U, jb, je, cj.contiguous(), k.contiguous(), rho.contiguous(), find_id_full, 0, nf,
                            dedupe=True, owner_count=owners)
-                if peeling_max <= 15.0 * C * B:
+                if guard_can_bind:
                     num_peeling += int(owners.item())
     if all_cj:
-        return (np.concatenate(all_cj), np.concatenate(all_k), np.concatenate(all_rho), np.concatenate(all_round), rnd)
-    return (np.zeros(0, np.int64), np.zeros((0, n), np.int8), np.zeros(0, np.complex64), np.zeros(0, np.int32), rnd)
+        out = (torch.cat(all_cj), torch.cat(all_k), torch.cat(all_rho), torch.cat(all_round))
+    else:
+        out = (torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros((0, n), dtype=torch.int8, device=dev),
+               torch.zeros(0, dtype=torch.complex64, device=dev), torch.zeros(0, dtype=torch.int32, device=dev))
+    if to_host:
+        out = tuple(t.cpu().numpy() for t in out)
+    return out + (rnd,)

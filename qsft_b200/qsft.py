@@ -61,7 +61,7 @@ class QSFT:
         dist = getattr(signal, "dist", None)
         if dist is not None and dist.world_size > 1:
             from .dist import peel_sharded
-            finds = peel_sharded(prob, U, dist)
+            finds = peel_sharded(prob, U, dist, to_host=not kwargs.get("device_result", False))
             if kwargs.get("device_result", False):
                 self.last_stats = {"rounds": int(finds[4]), "finds": int(len(finds[0])), "cutoff": float(cutoff)}
                 return {"find_cj": finds[0], "find_k": finds[1], "find_rho": finds[2], "find_round": finds[3]}

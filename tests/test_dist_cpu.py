@@ -39,8 +39,8 @@ def _worker(rank, world, port, out):
     a = torch.arange(cap, dtype=torch.int64) + 100 * rank
     k = (torch.arange(cap * 2, dtype=torch.int8).reshape(cap, 2) + rank)
     z = torch.arange(cap, dtype=torch.float32).to(torch.complex64) * (1j if rank else 1)
-    (ga, gk, gz), counts = ctx.all_gather_var([a, k, z], cnt, cap)
-    ok2 = counts == [3, 5] and ga.tolist() == [0, 1, 2, 100, 101, 102, 103, 104] and gk.shape == (8, 2) \
+    (ga, gk, gz), counts = ctx.all_gather_var([a, k, z], cnt, cap, extra=rank + 1)
+    ok2 = counts == [3, 5] and ctx.last_extra_sum == 3 and ga.tolist() == [0, 1, 2, 100, 101, 102, 103, 104] and gk.shape == (8, 2) \
         and gz[3:].tolist() == [complex(0, v) for v in range(5)]
     ok3 = bin_range(10, 0, 2) == (0, 5) and bin_range(10, 1, 2) == (5, 10) and bin_range(3, 1, 4) == (1, 2) \
         and bin_range(3, 3, 4) == (3, 3)

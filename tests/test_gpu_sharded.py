@@ -31,10 +31,11 @@ class ThreadDist:
         self.sh["bar"].wait()
         return out
 
-    def all_gather_var(self, tensors, count, cap):
+    def all_gather_var(self, tensors, count, cap, extra=0):
         torch.cuda.synchronize()
-        parts = self._exchange(([t[:count].clone() for t in tensors], count))
+        parts = self._exchange(([t[:count].clone() for t in tensors], count, int(extra)))
         counts = [p[1] for p in parts]
+        self.last_extra_sum = sum(p[2] for p in parts)
         outs = [torch.cat([p[0][i] for p in parts], dim=0) for i in range(len(tensors))]
         return outs, counts
 
