@@ -549,8 +549,9 @@ extern "C" int qsft_peel(const qsft_peel_desc* h, float* U, int64_t* find_cj, in
     // `num_peeling < q ** n` (qsft.py:151) can only bind when q^n is tiny: at most C*B balls are peeled per round
     const double peeling_max = pow((double)d.q, (double)d.n);
     const bool guard_can_bind = peeling_max <= 15.0 * (double)d.C * (double)d.B;
-    unsigned long long* host = nullptr;
-    QSFT_CUDA(cudaMallocHost(&host, 4 * sizeof(unsigned long long)));
+    // pinned read-back slot for the round counters: allocated once per host thread (cudaMallocHost costs milliseconds)
+    static thread_local unsigned long long* host = nullptr;
+    if (!host) QSFT_CUDA(cudaMallocHost(&host, 4 * sizeof(unsigned long long)));
     long long total = 0;
     double num_peeling = 0;
     int round = 0;
@@ -569,7 +570,6 @@ extern "C" int qsft_peel(const qsft_peel_desc* h, float* U, int64_t* find_cj, in
         const long long now = (long long)host[0];
         const long long multis = (long long)host[1];
         if (now > max_finds) {
-            cudaFreeHost(host);
             qsft_set_error("find buffer too small: %lld finds > max_finds=%lld", now, (long long)max_finds);
             return QSFT_EINVAL;
         }
@@ -587,7 +587,6 @@ extern "C" int qsft_peel(const qsft_peel_desc* h, float* U, int64_t* find_cj, in
         }
         total = now;
     }
-    cudaFreeHost(host);
     if (ce != cudaSuccess) {
         qsft_set_error("CUDA error in peel loop: %s", cudaGetErrorString(ce));
         return QSFT_ECUDA;
