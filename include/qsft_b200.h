@@ -107,14 +107,32 @@ int qsft_peel_apply(const qsft_peel_desc* d, float* U, int64_t j_begin, int64_t 
                     const int32_t* find_id, int64_t f_begin, int64_t n_finds, int dedupe,
                     unsigned long long* owner_count, void* stream);
 
+/* Distinct-k output of the peel (qsft.py:247-255 averages every rho recorded for the same k).  All device memory. */
+typedef struct {
+    int32_t* seen0;      /* (B) workspace: chain heads keyed by k's bin in group 0; must be ZERO before round 1        */
+    int8_t* uniq_k;      /* (max_uniq, ld) digits of each distinct k                                                   */
+    float* uniq_sum;     /* (max_uniq) complex64: sum of rho over all finds of that k (mean = sum / count)             */
+    int32_t* uniq_cnt;   /* (max_uniq) number of finds of that k                                                       */
+    int64_t* uniq_key;   /* (max_uniq) (round << 48) | (c * B + j) of the first find = the reference's first-seen order */
+    int32_t* uniq_next;  /* (max_uniq) workspace (chain links)                                                         */
+    int64_t max_uniq;
+} qsft_uniq;
+
+/* Collapse finds [f_begin, f_begin + n_finds) of round `round` (find_id must be the table of that round) into the
+ * distinct-k list; counters[4] is the running number of distinct k (atomic).                                     */
+int qsft_peel_reduce(const qsft_peel_desc* d, const int64_t* find_cj, const int8_t* find_k, const float* find_rho,
+                     const int32_t* find_id, int64_t f_begin, int64_t n_finds, int round, const qsft_uniq* uq,
+                     unsigned long long* counters, void* stream);
+
 /* Whole single-GPU peel loop (qsft.py:151-241): classify / apply rounds until the reference's stop rule
  * (no multitons or no singletons, or 15 rounds, or q^n peels).  SYNCHRONOUS (reads round counters back).
  *   Outputs: finds grouped by round (order inside a round is unspecified): find_cj / find_k / find_rho /
- *   find_round as above.  *n_finds_out = total finds, *n_rounds_out = rounds.  Workspaces: find_id (C, B) int32,
- *   counters (>= 4 x u64, device).                                                                              */
+ *   find_round as above.  *n_finds_out = total finds, *n_rounds_out = rounds; with uq != NULL also the distinct-k list
+ *   (*n_uniq_out entries).  Workspaces: find_id (C, B) int32, counters (>= 8 x u64, device).                                                                            */
 int qsft_peel(const qsft_peel_desc* d, float* U, int64_t* find_cj, int8_t* find_k, float* find_rho,
               int32_t* find_round, int32_t* find_id, int64_t max_finds, unsigned long long* counters,
-              int64_t* n_finds_out, int* n_rounds_out, void* stream);
+              const qsft_uniq* uq /* may be NULL */, int64_t* n_finds_out, int64_t* n_uniq_out, int* n_rounds_out,
+              void* stream);
 
 /* Closed-form bins (verification helper): U[p][j] = sum_{s: M^T k_s = j} a_s w^{<d_p,k_s>}.
  * Used by tests and by the peel benchmark to fill U without sampling.  U (P, B) must be zeroed by the caller. */

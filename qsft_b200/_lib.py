@@ -14,7 +14,7 @@ EXPORTS = [
     "qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count",
     "qsft_query_lattice", "qsft_dec_to_qary", "qsft_qary_to_dec", "qsft_eval_synth", "qsft_gwht_batch",
     "qsft_eval_lattice_supported", "qsft_eval_synth_lattice",
-    "qsft_peel_classify", "qsft_peel_apply", "qsft_peel", "qsft_closed_form_bins",
+    "qsft_peel_classify", "qsft_peel_apply", "qsft_peel_reduce", "qsft_peel", "qsft_closed_form_bins",
 ]
 
 
@@ -34,6 +34,12 @@ class PeelDesc(C.Structure):
         ("MT", C.c_void_p), ("D", C.c_void_p),
         ("rs_exp", C.c_void_p), ("rs_log", C.c_void_p),
     ]
+
+
+class Uniq(C.Structure):
+    """Mirror of qsft_uniq."""
+    _fields_ = [("seen0", C.c_void_p), ("uniq_k", C.c_void_p), ("uniq_sum", C.c_void_p), ("uniq_cnt", C.c_void_p),
+                ("uniq_key", C.c_void_p), ("uniq_next", C.c_void_p), ("max_uniq", C.c_int64)]
 
 
 _lib = None
@@ -77,7 +83,9 @@ def lib():
     pd = C.POINTER(PeelDesc)
     L.qsft_peel_classify.argtypes = [pd, vp, i64, i64, vp, vp, vp, vp, vp, i64, i32, vp, vp]
     L.qsft_peel_apply.argtypes = [pd, vp, i64, i64, vp, vp, vp, vp, i64, i64, i32, vp, vp]
-    L.qsft_peel.argtypes = [pd, vp, vp, vp, vp, vp, vp, i64, vp, C.POINTER(i64), C.POINTER(i32), vp]
+    pu = C.POINTER(Uniq)
+    L.qsft_peel_reduce.argtypes = [pd, vp, vp, vp, vp, i64, i64, i32, pu, vp, vp]
+    L.qsft_peel.argtypes = [pd, vp, vp, vp, vp, vp, vp, i64, vp, pu, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), vp]
     L.qsft_closed_form_bins.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp, i64, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)  # raises AttributeError if a declared symbol is missing

@@ -413,6 +413,87 @@ k4_apply_kernel(PeelDev d, float2* __restrict__ U, long long j_begin, long long 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// reduce: collapse the finds of one round into the list of distinct k (one thread per find).
+// The reference records every singleton (k, rho) and finally averages all rho recorded for the same k
+// (qsft.py:209-217, 247-255).  Duplicates of a k inside a round sit in the bins the other groups hash k to, so the
+// round's FIRST find of k (lowest group = first in (i, j) order) gathers them through find_id; re-finds of k in a
+// later round are merged through a chained hash table keyed by k's group-0 bin (seen0 = chain heads, unext = links).
+// ---------------------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(K4_THREADS)
+k4_reduce_kernel(PeelDev d, const long long* __restrict__ find_cj, const int8_t* __restrict__ find_k,
+                 const float2* __restrict__ find_rho, const int32_t* __restrict__ find_id, long long f_begin,
+                 long long n_finds, long long id_limit, int round, int32_t* __restrict__ seen0,
+                 int8_t* __restrict__ uk, float* __restrict__ usum, int32_t* __restrict__ ucnt,
+                 long long* __restrict__ ukey, int32_t* __restrict__ unext, long long max_uniq,
+                 unsigned long long* __restrict__ counters) {
+    const long long f = f_begin + (long long)blockIdx.x * K4_THREADS + threadIdx.x;
+    if (f >= f_begin + n_finds) return;
+    const long long cj = find_cj[f];
+    const int c = (int)(cj / d.B);
+    const int nw = d.ld / 4;
+    uint32_t kw[NW];
+    const uint32_t* kin = reinterpret_cast<const uint32_t*>(find_k + (size_t)f * d.ld);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) kw[w] = (w < nw) ? kin[w] : 0u;
+    float2 sum = find_rho[f];
+    int cnt = 1;
+    long long j0 = cj - (long long)c * d.B;
+    for (int c2 = 0; c2 < d.C; ++c2) {
+        if (c2 == c) continue;
+        const long long j2 = hash_bin<NW>(d, c2, kw);
+        if (c2 == 0) j0 = j2;
+        const int32_t f2 = find_id[(size_t)c2 * d.B + j2];
+        if (f2 >= 0 && (long long)f2 < id_limit) {
+            const uint32_t* k2 = reinterpret_cast<const uint32_t*>(find_k + (size_t)f2 * d.ld);
+            bool same = true;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) same &= ((w < nw) ? k2[w] : 0u) == kw[w];
+            if (same) {
+                if (c2 < c) return;              // an earlier group holds the round's first find of this k
+                const float2 r2 = find_rho[f2];
+                sum.x += r2.x;
+                sum.y += r2.y;
+                ++cnt;
+            }
+        }
+    }
+    // merge with an entry of an earlier round, if any
+    int32_t head = *reinterpret_cast<volatile int32_t*>(seen0 + j0);
+    // entries of this round may have been published by other SMs a moment ago: read the links through L2 (__ldcg)
+    for (int32_t e = head; e != 0; e = __ldcg(unext + (e - 1))) {
+        if ((int)(__ldcg(ukey + (e - 1)) >> 48) == round) continue;
+        const uint32_t* k2 = reinterpret_cast<const uint32_t*>(uk + (size_t)(e - 1) * d.ld);
+        bool same = true;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) same &= ((w < nw) ? k2[w] : 0u) == kw[w];
+        if (same) {
+            atomicAdd(usum + 2 * (size_t)(e - 1), sum.x);
+            atomicAdd(usum + 2 * (size_t)(e - 1) + 1, sum.y);
+            atomicAdd(ucnt + (e - 1), cnt);
+            return;
+        }
+    }
+    const unsigned long long u = atomicAdd(&counters[4], 1ull);
+    if ((long long)u >= max_uniq) return;
+    uint32_t* ko = reinterpret_cast<uint32_t*>(uk + (size_t)u * d.ld);
+    for (int w = 0; w < nw; ++w) ko[w] = (w < NW) ? kw[w] : 0u;
+    usum[2 * u] = sum.x;
+    usum[2 * u + 1] = sum.y;
+    ucnt[u] = cnt;
+    ukey[u] = ((long long)round << 48) | cj;
+    unext[u] = head;
+    __threadfence();
+    for (;;) {
+        const int32_t old = atomicCAS(seen0 + j0, head, (int32_t)(u + 1));
+        if (old == head) break;
+        head = old;                          // another k of this round was linked first: chain behind it
+        unext[u] = head;
+        __threadfence();
+    }
+}
+
 __global__ void k4_closed_form_kernel(const int8_t* __restrict__ MT, const int8_t* __restrict__ D, int q, int n, int b,
                                       int P, long long B, int ld, const int8_t* __restrict__ loc,
                                       const float2* __restrict__ a, long long S, float2* __restrict__ U) {
@@ -487,6 +568,26 @@ int apply_nw(const PeelDev& d, float2* U, long long jb, long long je, const long
     return QSFT_OK;
 }
 
+struct UniqOut {
+    int32_t* seen0;       // (B) chain heads, zero initialised by the caller / qsft_peel
+    int8_t* uk;           // (max_uniq, ld)
+    float* usum;          // (max_uniq) complex64: sum of rho over all finds of the k
+    int32_t* ucnt;        // (max_uniq) number of finds
+    long long* ukey;      // (max_uniq) (round << 48) | (c * B + j) of the first find: reference's first-seen order
+    int32_t* unext;       // (max_uniq) workspace
+    long long max_uniq;
+};
+
+template <int NW>
+int reduce_nw(const PeelDev& d, const long long* cj, const int8_t* fk, const float2* rho, const int32_t* fid,
+              long long f_begin, long long nf, long long id_limit, int round, const UniqOut& o,
+              unsigned long long* counters, cudaStream_t st) {
+    k4_reduce_kernel<NW><<<(unsigned)((nf + K4_THREADS - 1) / K4_THREADS), K4_THREADS, 0, st>>>(
+        d, cj, fk, rho, fid, f_begin, nf, id_limit, round, o.seen0, o.uk, o.usum, o.ucnt, o.ukey, o.unext, o.max_uniq, counters);
+    QSFT_LAUNCHED();
+    return QSFT_OK;
+}
+
 #define QSFT_NW_DISPATCH(fn, ...)                          \
     do {                                                   \
         const int nw__ = d.ld / 4;                         \
@@ -499,6 +600,12 @@ int apply_nw(const PeelDev& d, float2* U, long long jb, long long je, const long
 int do_classify(const PeelDev& d, const float2* U, long long jb, long long je, long long* cj, int8_t* fk, float2* rho,
                 int32_t* frd, int32_t* fid, long long maxf, int round, unsigned long long* counters, cudaStream_t st) {
     QSFT_NW_DISPATCH(classify_nw, d, U, jb, je, cj, fk, rho, frd, fid, maxf, round, counters, st);
+}
+
+int do_reduce(const PeelDev& d, const long long* cj, const int8_t* fk, const float2* rho, const int32_t* fid,
+              long long f_begin, long long nf, long long id_limit, int round, const UniqOut& o,
+              unsigned long long* counters, cudaStream_t st) {
+    QSFT_NW_DISPATCH(reduce_nw, d, cj, fk, rho, fid, f_begin, nf, id_limit, round, o, counters, st);
 }
 
 int do_apply(const PeelDev& d, float2* U, long long jb, long long je, const long long* cj, const int8_t* fk,
@@ -538,14 +645,35 @@ extern "C" int qsft_peel_apply(const qsft_peel_desc* h, float* U, int64_t j_begi
                     owner_count, (cudaStream_t)stream);
 }
 
+extern "C" int qsft_peel_reduce(const qsft_peel_desc* h, const int64_t* find_cj, const int8_t* find_k,
+                                const float* find_rho, const int32_t* find_id, int64_t f_begin, int64_t n_finds,
+                                int round, const qsft_uniq* uq, unsigned long long* counters, void* stream) {
+    PeelDev d;
+    if (int rc = make_dev(h, &d)) return rc;
+    QSFT_CHECK_ARG(find_cj && find_k && find_rho && find_id && uq && counters, "null pointer");
+    QSFT_CHECK_ARG(uq->seen0 && uq->uniq_k && uq->uniq_sum && uq->uniq_cnt && uq->uniq_key && uq->uniq_next && uq->max_uniq > 0,
+                   "incomplete qsft_uniq");
+    QSFT_CHECK_ARG(round >= 1 && round < 32768 && f_begin >= 0, "bad round / f_begin");
+    if (n_finds <= 0) return QSFT_OK;
+    UniqOut o{uq->seen0, uq->uniq_k, uq->uniq_sum, uq->uniq_cnt, (long long*)uq->uniq_key, uq->uniq_next, uq->max_uniq};
+    return do_reduce(d, (const long long*)find_cj, find_k, reinterpret_cast<const float2*>(find_rho), find_id, f_begin,
+                     n_finds, f_begin + n_finds, round, o, counters, (cudaStream_t)stream);
+}
+
 extern "C" int qsft_peel(const qsft_peel_desc* h, float* U, int64_t* find_cj, int8_t* find_k, float* find_rho,
                          int32_t* find_round, int32_t* find_id, int64_t max_finds, unsigned long long* counters,
-                         int64_t* n_finds_out, int* n_rounds_out, void* stream) {
+                         const qsft_uniq* uq, int64_t* n_finds_out, int64_t* n_uniq_out, int* n_rounds_out, void* stream) {
     PeelDev d;
     if (int rc = make_dev(h, &d)) return rc;
     QSFT_CHECK_ARG(U && find_cj && find_k && find_rho && find_round && find_id && counters && n_finds_out && n_rounds_out,
                    "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    UniqOut uo{};
+    if (uq) {
+        QSFT_CHECK_ARG(uq->seen0 && uq->uniq_k && uq->uniq_sum && uq->uniq_cnt && uq->uniq_key && uq->uniq_next && uq->max_uniq > 0,
+                       "incomplete qsft_uniq");
+        uo = UniqOut{uq->seen0, uq->uniq_k, uq->uniq_sum, uq->uniq_cnt, (long long*)uq->uniq_key, uq->uniq_next, uq->max_uniq};
+    }
     // `num_peeling < q ** n` (qsft.py:151) can only bind when q^n is tiny: at most C*B balls are peeled per round
     const double peeling_max = pow((double)d.q, (double)d.n);
     const bool guard_can_bind = peeling_max <= 15.0 * (double)d.C * (double)d.B;
@@ -558,8 +686,9 @@ extern "C" int qsft_peel(const qsft_peel_desc* h, float* U, int64_t* find_cj, in
     int rc = QSFT_OK;
     cudaError_t ce = cudaSuccess;
     bool cont = true;
-    // counters: [0] finds (running), [1] multitons of the round, [2] distinct balls peeled (running)
-    ce = cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st);
+    // counters: [0] finds (running), [1] multitons of the round, [2] distinct balls peeled (running), [4] distinct k
+    ce = cudaMemsetAsync(counters, 0, 6 * sizeof(unsigned long long), st);
+    if (ce == cudaSuccess && uq) ce = cudaMemsetAsync(uo.seen0, 0, (size_t)d.B * sizeof(int32_t), st);
     while (ce == cudaSuccess && rc == QSFT_OK && cont && num_peeling < peeling_max && round < 15) {
         ++round;
         if ((ce = cudaMemsetAsync(counters + 1, 0, sizeof(unsigned long long), st)) != cudaSuccess) break;
@@ -575,6 +704,10 @@ extern "C" int qsft_peel(const qsft_peel_desc* h, float* U, int64_t* find_cj, in
         }
         const long long nf = now - total;
         if (multis == 0 || nf == 0) cont = false;          // qsft.py:204-205
+        if (nf > 0 && uq) {
+            if ((rc = do_reduce(d, (const long long*)find_cj, find_k, reinterpret_cast<const float2*>(find_rho), find_id,
+                                total, nf, now, round, uo, counters, st)) != 0) break;
+        }
         // the reference also subtracts after its last round, but nothing reads U afterwards: skip unless the q^n guard needs the count
         if (nf > 0 && (cont || guard_can_bind)) {
             if ((rc = do_apply(d, reinterpret_cast<float2*>(U), 0, d.B, (const long long*)find_cj, find_k,
@@ -592,6 +725,19 @@ extern "C" int qsft_peel(const qsft_peel_desc* h, float* U, int64_t* find_cj, in
         return QSFT_ECUDA;
     }
     if (rc != QSFT_OK) return rc;
+    if (uq && n_uniq_out) {
+        if ((ce = cudaMemcpyAsync(host, counters + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st)) == cudaSuccess)
+            ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) {
+            qsft_set_error("CUDA error reading the unique count: %s", cudaGetErrorString(ce));
+            return QSFT_ECUDA;
+        }
+        if ((long long)host[0] > uo.max_uniq) {
+            qsft_set_error("unique buffer too small: %llu > %lld", host[0], uo.max_uniq);
+            return QSFT_EINVAL;
+        }
+        *n_uniq_out = (int64_t)host[0];
+    }
     *n_finds_out = total;
     *n_rounds_out = round;
     return QSFT_OK;

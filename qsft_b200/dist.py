@@ -64,23 +64,26 @@ def bin_range(B, rank, world):
     return lo, min(B, lo + per)
 
 
-def peel_sharded(prob, U, dist, max_rounds=15, to_host=True):
+def peel_sharded(prob, U, dist, max_rounds=15, to_host=False):
     """Bin-sharded peeling loop (qsft.py:151-241 semantics).  Every rank holds the full U but only classifies and
     updates bins in its own j-range; finds are exchanged with one all-gather per round.
-    Returns (cj, k, rho, round, n_rounds), identical on every rank; NumPy arrays when to_host else CUDA tensors."""
+    Returns (cj, k, rho, round, n_rounds), identical on every rank (NumPy arrays when to_host else CUDA tensors);
+    the distinct-k list is left in prob.uniq_* [0:prob.n_uniq] (see PeelProblem.distinct)."""
     q, n, C, B = prob.q, prob.n, prob.C, prob.B
     dev = prob.device
     jb, je = bin_range(B, dist.rank, dist.world_size)
     cap = max(1024, 2 * C * (je - jb))
-    prob.alloc(max_finds=cap)
+    prob.alloc(max_finds=cap, max_uniq=max(cap, min(C * B, 4 * cap * dist.world_size)))
     find_id_full = torch.empty((C, B), dtype=torch.int32, device=dev)
+    prob.counters.zero_()
+    prob.seen0.zero_()
     all_cj, all_k, all_rho, all_round = [], [], [], []
     peeling_max = float(q) ** n
     guard_can_bind = peeling_max <= 15.0 * C * B
     num_peeling, rnd, cont = 0, 0, True
     while cont and num_peeling < peeling_max and rnd < max_rounds:
         rnd += 1
-        prob.counters.zero_()
+        prob.counters[:4].zero_()
         prob.classify(U, jb, je, rnd)
         cnts = prob.counters.cpu().tolist()               # the round's only host sync (find count + multiton count)
         nf_local, multi_local = int(cnts[0]), int(cnts[1])
@@ -97,13 +100,15 @@ def peel_sharded(prob, U, dist, max_rounds=15, to_host=True):
             all_k.append(k[:, :n])
             all_rho.append(rho)
             all_round.append(torch.full((nf,), rnd, dtype=torch.int32, device=dev))
+            # rebuild the (C, B) find table of the whole round: duplicates of a k ("last (i, j) wins", averaging of
+            # repeated finds) are looked up through it, locally on every rank
+            find_id_full.fill_(-1)
+            find_id_full.view(-1)[cj] = torch.arange(nf, dtype=torch.int32, device=dev)
+            cjc, kc, rhoc = cj.contiguous(), k.contiguous(), rho.contiguous()
+            prob.reduce(cjc, kc, rhoc, find_id_full, 0, nf, rnd)
             if cont or guard_can_bind:
-                # rebuild the (C, B) find table for the whole round so "last (i, j) wins" can be checked locally
-                find_id_full.fill_(-1)
-                find_id_full.view(-1)[cj] = torch.arange(nf, dtype=torch.int32, device=dev)
                 owners = torch.zeros(1, dtype=torch.int64, device=dev) if guard_can_bind else None
-                prob.apply(U, jb, je, cj.contiguous(), k.contiguous(), rho.contiguous(), find_id_full, 0, nf,
-                           dedupe=True, owner_count=owners)
+                prob.apply(U, jb, je, cjc, kc, rhoc, find_id_full, 0, nf, dedupe=True, owner_count=owners)
                 if guard_can_bind:
                     num_peeling += int(owners.item())
     if all_cj:
@@ -111,6 +116,9 @@ def peel_sharded(prob, U, dist, max_rounds=15, to_host=True):
     else:
         out = (torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros((0, n), dtype=torch.int8, device=dev),
                torch.zeros(0, dtype=torch.complex64, device=dev), torch.zeros(0, dtype=torch.int32, device=dev))
+    prob.n_uniq = int(prob.counters[4].item())
+    if prob.n_uniq > prob.max_uniq:
+        raise RuntimeError("distinct-k buffer overflow in sharded peel")
     if to_host:
         out = tuple(t.cpu().numpy() for t in out)
     return out + (rnd,)

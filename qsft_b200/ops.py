@@ -209,7 +209,7 @@ class PeelProblem:
                                   rs_exp=0 if self.rs_exp is None else self.rs_exp.data_ptr(),
                                   rs_log=0 if self.rs_log is None else self.rs_log.data_ptr())
 
-    def alloc(self, max_finds):
+    def alloc(self, max_finds, max_uniq=None):
         dev = self.device
         self.max_finds = int(max_finds)
         self.find_cj = torch.empty(self.max_finds, dtype=torch.int64, device=dev)
@@ -217,20 +217,50 @@ class PeelProblem:
         self.find_rho = torch.empty(self.max_finds, dtype=torch.complex64, device=dev)
         self.find_round = torch.empty(self.max_finds, dtype=torch.int32, device=dev)
         self.find_id = torch.empty((self.C, self.B), dtype=torch.int32, device=dev)
-        self.counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        # distinct-k list (device-side averaging of duplicate finds, qsft.py:247-255)
+        self.max_uniq = int(max_uniq) if max_uniq else self.max_finds
+        self.seen0 = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self.uniq_k = torch.empty((self.max_uniq, self.ld), dtype=torch.int8, device=dev)
+        self.uniq_sum = torch.empty(self.max_uniq, dtype=torch.complex64, device=dev)
+        self.uniq_cnt = torch.empty(self.max_uniq, dtype=torch.int32, device=dev)
+        self.uniq_key = torch.empty(self.max_uniq, dtype=torch.int64, device=dev)
+        self.uniq_next = torch.empty(self.max_uniq, dtype=torch.int32, device=dev)
+        self.uniq = _lib.Uniq(seen0=self.seen0.data_ptr(), uniq_k=self.uniq_k.data_ptr(), uniq_sum=self.uniq_sum.data_ptr(),
+                              uniq_cnt=self.uniq_cnt.data_ptr(), uniq_key=self.uniq_key.data_ptr(),
+                              uniq_next=self.uniq_next.data_ptr(), max_uniq=self.max_uniq)
 
     # -- whole loop on one GPU -------------------------------------------------------------------------
     def peel(self, U):
         """Runs the full round loop in the library.  U (C, P, B) complex64 is modified in place.
-        Returns (n_finds, n_rounds); finds are in self.find_* [0:n_finds]."""
+        Returns (n_finds, n_rounds); finds are in self.find_* [0:n_finds], the distinct k in self.uniq_* [0:self.n_uniq]."""
         _need_cuda(U)
         assert U.shape == (self.C, self.P, self.B) and U.dtype == torch.complex64
-        nf, nr = C.c_int64(0), C.c_int(0)
+        nf, nu, nr = C.c_int64(0), C.c_int64(0), C.c_int(0)
         with torch.cuda.device(self.device), _timed("k4_peel", U.numel()):
             _lib.check(_lib.lib().qsft_peel(C.byref(self.desc), _ptr(U), _ptr(self.find_cj), _ptr(self.find_k),
                                             _ptr(self.find_rho), _ptr(self.find_round), _ptr(self.find_id),
-                                            self.max_finds, _ptr(self.counters), C.byref(nf), C.byref(nr), _stream()))
+                                            self.max_finds, _ptr(self.counters), C.byref(self.uniq), C.byref(nf),
+                                            C.byref(nu), C.byref(nr), _stream()))
+        self.n_uniq = nu.value
         return nf.value, nr.value
+
+    def distinct(self, n_uniq=None):
+        """Host copy of the distinct-k list in the reference's first-seen order:
+        (k (K, n) int8, mean rho (K,) complex128, count (K,) int32)."""
+        nu = self.n_uniq if n_uniq is None else n_uniq
+        key = self.uniq_key[:nu].cpu().numpy()
+        order = np.argsort(key, kind="stable")
+        k = self.uniq_k[:nu, :self.n].cpu().numpy()[order]
+        cnt = self.uniq_cnt[:nu].cpu().numpy()[order]
+        mean = self.uniq_sum[:nu].cpu().numpy().astype(np.complex128)[order] / cnt
+        return k, mean, cnt
+
+    def reduce(self, find_cj, find_k, find_rho, find_id, f_begin, n_finds, round_no):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().qsft_peel_reduce(C.byref(self.desc), _ptr(find_cj), _ptr(find_k), _ptr(find_rho),
+                                                   _ptr(find_id), f_begin, n_finds, round_no, C.byref(self.uniq),
+                                                   _ptr(self.counters), _stream()))
 
     # -- single steps (bin-sharded multi-GPU loop drives these) ----------------------------------------
     def classify(self, U, j_begin, j_end, round_no):

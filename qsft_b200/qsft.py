@@ -61,22 +61,24 @@ class QSFT:
         dist = getattr(signal, "dist", None)
         if dist is not None and dist.world_size > 1:
             from .dist import peel_sharded
-            finds = peel_sharded(prob, U, dist, to_host=not kwargs.get("device_result", False))
-            if kwargs.get("device_result", False):
-                self.last_stats = {"rounds": int(finds[4]), "finds": int(len(finds[0])), "cutoff": float(cutoff)}
-                return {"find_cj": finds[0], "find_k": finds[1], "find_rho": finds[2], "find_round": finds[3]}
+            n_rounds = peel_sharded(prob, U, dist)[4]
+            n_finds = -1
         else:
-            prob.alloc(max_finds=min(15 * C * B, max(4096, 4 * C * B)))
+            prob.alloc(max_finds=min(15 * C * B, max(4096, 4 * C * B)), max_uniq=max(4096, C * B))
             n_finds, n_rounds = prob.peel(U)
-            if kwargs.get("device_result", False):
-                # raw finds left in HBM (no host copy, no dict): used by the device-resident benchmark loop
-                self.last_stats = {"rounds": n_rounds, "finds": n_finds, "cutoff": float(cutoff)}
-                return {"find_cj": prob.find_cj[:n_finds], "find_k": prob.find_k[:n_finds, :n],
-                        "find_rho": prob.find_rho[:n_finds], "find_round": prob.find_round[:n_finds]}
-            finds = (prob.find_cj[:n_finds].cpu().numpy(), prob.find_k[:n_finds, :n].cpu().numpy(),
-                     prob.find_rho[:n_finds].cpu().numpy(), prob.find_round[:n_finds].cpu().numpy(), n_rounds)
-        gwht, loc_arr = self._finds_to_dict(*finds[:4])
-        self.last_stats = {"rounds": int(finds[4]), "finds": int(len(finds[0])), "cutoff": float(cutoff)}
+        self.last_stats = {"rounds": int(n_rounds), "finds": int(n_finds), "distinct": int(prob.n_uniq),
+                           "cutoff": float(cutoff)}
+        output = kwargs.get("output", "dict")
+        if output == "device":
+            # distinct k left in HBM (no host copy): k int8 (K, n), sum of rho complex64, find counts, first-seen keys
+            nu = prob.n_uniq
+            return {"k": prob.uniq_k[:nu, :n], "sum": prob.uniq_sum[:nu], "count": prob.uniq_cnt[:nu],
+                    "key": prob.uniq_key[:nu]}
+        loc_arr, values, counts = prob.distinct()          # first-seen order, mean over duplicate finds (qsft.py:247-255)
+        if output == "arrays":
+            gwht = {"locations": loc_arr, "values": values, "counts": counts}
+        else:
+            gwht = dict(zip(itertools.batched(loc_arr.astype(np.uint8).tobytes(), n), values.tolist()))
         peeling_time = time.time() - peeling_start
         if timing_verbose:
             print(f"Peeling Time:{peeling_time}", flush=True)
@@ -84,7 +86,7 @@ class QSFT:
             return gwht
         n_samples = C * P * B
         if len(loc_arr) > 0:
-            loc = [tuple(r) for r in loc_arr.tolist()]
+            loc = list(itertools.batched(loc_arr.astype(np.uint8).tobytes(), n))
             if kwargs.get("sort", False):
                 loc = sort_qary_vecs(loc)
             hw = calc_hamming_weight(loc_arr)

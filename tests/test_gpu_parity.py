@@ -191,6 +191,11 @@ def test_k4_peel_from_reference_bins(name):
     assert list(gw.keys()) == want_keys                   # same support, same first-seen order
     got = np.array([gw[k] for k in want_keys])
     assert np.max(np.abs(got - g["res_vals"])) <= 1e-5 * np.max(np.abs(g["res_vals"]))
+    # the device-side distinct-k list (averaging of duplicate finds on the GPU) agrees with the host grouping
+    dk, dv, dc = prob.distinct()
+    assert [tuple(int(v) for v in r) for r in dk] == want_keys
+    assert np.max(np.abs(dv - got)) <= 1e-6 * np.max(np.abs(got))
+    assert int(dc.sum()) == nf
 
 
 # ---- end to end with the same seed ----------------------------------------------------------------------
@@ -322,3 +327,7 @@ def test_construct_and_transform_all_eval_impls_agree(impl):
                          reconstruct_method_channel="nso").transform(sig)
     assert set(res.keys()) == set(sig.signal_w.keys())
     assert max(abs(res[k] - v) for k, v in sig.signal_w.items()) < 1e-5
+    arr = qsft_b200.QSFT(num_subsample=C, num_repeat=R, b=b, reconstruct_method_source="identity",
+                         reconstruct_method_channel="nso").transform(sig, output="arrays")
+    assert [tuple(int(v) for v in r) for r in arr["locations"]] == list(res.keys())
+    assert np.allclose(arr["values"], np.array(list(res.values())), rtol=0, atol=1e-6)

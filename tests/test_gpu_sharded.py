@@ -46,6 +46,7 @@ class ThreadDist:
 def _run_sharded(world, make_problem, U0):
     shared = {"slots": [None] * world, "bar": threading.Barrier(world)}
     results = [None] * world
+    distinct = [None] * world
     errors = []
 
     def work(rank):
@@ -54,6 +55,7 @@ def _run_sharded(world, make_problem, U0):
             # all simulated ranks share the default stream: tensors handed between threads stay allocator-safe
             prob = make_problem()
             results[rank] = peel_sharded(prob, U0.clone(), ThreadDist(rank, world, shared))
+            distinct[rank] = prob.distinct()
             torch.cuda.synchronize()
         except Exception as exc:  # pragma: no cover
             errors.append(exc)
@@ -64,7 +66,7 @@ def _run_sharded(world, make_problem, U0):
     [t.start() for t in threads]
     [t.join() for t in threads]
     assert not errors, errors
-    return results
+    return results, distinct
 
 
 @pytest.mark.parametrize("world", [2, 3])
@@ -86,9 +88,12 @@ def test_sharded_peel_equals_single_gpu(name, world):
     nf, nr = single.peel(U1)
     want, _ = qsft_b200.QSFT._finds_to_dict(single.find_cj[:nf].cpu().numpy(), single.find_k[:nf, :n].cpu().numpy(),
                                              single.find_rho[:nf].cpu().numpy(), single.find_round[:nf].cpu().numpy())
-    results = _run_sharded(world, make_problem, U0)
+    results, distinct = _run_sharded(world, make_problem, U0)
+    for dk, dv, dc in distinct:
+        assert [tuple(int(v) for v in r) for r in dk] == list(want.keys())
+        assert max(abs(v - want[key]) for v, key in zip(dv, want)) < 1e-5
     for cj, k, rho, rnd, rounds in results:
-        got, _ = qsft_b200.QSFT._finds_to_dict(cj, k, rho, rnd)
+        got, _ = qsft_b200.QSFT._finds_to_dict(cj.cpu().numpy(), k.cpu().numpy(), rho.cpu().numpy(), rnd.cpu().numpy())
         assert rounds == nr
         assert list(got.keys()) == list(want.keys())
         assert max(abs(got[key] - want[key]) for key in want) < 1e-5
