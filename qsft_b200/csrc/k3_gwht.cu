@@ -57,22 +57,25 @@ struct Dft<4> {
 
 // One pass over levels [a, a + r).  Tile = q^r rows (stride q^a) x W contiguous elements; for a == 0, W == 1 and
 // `outer` consecutive q^r blocks are processed per CTA.  Shared layout: e = (o * q^r + t) * W + w.
-template <int Q>
+// POW2 (q = 2, 4): every division / modulo below is a shift / mask (lgW = log2 W, lgq = log2 q) and global accesses
+// are 16-byte (two complex) vectors.
+template <int Q, bool POW2>
 __global__ void __launch_bounds__(K3_THREADS)
-k3_pass_kernel(float2* __restrict__ x, long long B, int q, int r, long long qa, int W, int outer, int rows /*q^r*/,
-               long long tiles_per_block, float scale) {
+k3_pass_kernel(float2* __restrict__ x, long long B, int q, int r, long long qa, int W, int lgW, int outer, int rows /*q^r*/,
+               long long tiles_per_block, long long tile0, float scale) {
     extern __shared__ float2 s[];
     __shared__ float2 s_tw[Q > 0 ? Q : QSFT_MAX_Q];
     const int tid = threadIdx.x;
     const int T = outer * rows * W;
     const int qq = Q > 0 ? Q : q;
+    constexpr int lgq = (Q == 2) ? 1 : 2;
     if (tid < qq) {
         float sn, cs;
         sincospif(-2.0f * (float)tid / (float)qq, &sn, &cs);
         s_tw[tid] = make_float2(cs, sn);
     }
     // locate the tile
-    const long long tile = blockIdx.x;
+    const long long tile = tile0 + blockIdx.x;
     const long long blk = tile / tiles_per_block;      // which length-B block of the batch
     const long long tin = tile - blk * tiles_per_block;
     float2* base = x + blk * B;
@@ -85,7 +88,18 @@ k3_pass_kernel(float2* __restrict__ x, long long B, int q, int r, long long qa, 
         g0 = high * qa * rows + mid * W;
     }
     // load
-    if (qa == 1) {
+    if (POW2) {
+        float4* s4 = reinterpret_cast<float4*>(s);
+        if (qa == 1) {
+            const float4* g4 = reinterpret_cast<const float4*>(base + g0);
+            for (int e = tid; e < T / 2; e += K3_THREADS) s4[e] = g4[e];
+        } else {
+            for (int e = tid; e < T / 2; e += K3_THREADS) {
+                const int t = (2 * e) >> lgW, w = (2 * e) & (W - 1);
+                s4[e] = *reinterpret_cast<const float4*>(base + g0 + (long long)t * qa + w);
+            }
+        }
+    } else if (qa == 1) {
         for (int e = tid; e < T; e += K3_THREADS) s[e] = base[g0 + e];
     } else {
         for (int e = tid; e < T; e += K3_THREADS) {
@@ -95,24 +109,30 @@ k3_pass_kernel(float2* __restrict__ x, long long B, int q, int r, long long qa, 
     }
     __syncthreads();
     float2 tw[Q > 0 ? Q : 1];
-    if (Q > 0) {
+    if constexpr (Q > 0) {
 #pragma unroll
-        for (int m = 0; m < (Q > 0 ? Q : 1); ++m) tw[m] = s_tw[m];
+        for (int m = 0; m < Q; ++m) tw[m] = s_tw[m];
     }
     // butterflies
-    int stride = W;
+    int stride = W, lgs = lgW;
     const int nbf = T / qq;
     for (int u = 0; u < r; ++u) {
         for (int i = tid; i < nbf; i += K3_THREADS) {
-            const int hi = i / stride, lo = i - hi * stride;
-            const int e0 = hi * stride * qq + lo;
-            if (Q > 0) {
-                float2 v[Q > 0 ? Q : 1];
+            int e0;
+            if (POW2) {
+                const int hi = i >> lgs, lo = i & (stride - 1);
+                e0 = (hi << (lgs + lgq)) + lo;
+            } else {
+                const int hi = i / stride, lo = i - hi * stride;
+                e0 = hi * stride * qq + lo;
+            }
+            if constexpr (Q > 0) {
+                float2 v[Q];
 #pragma unroll
-                for (int m = 0; m < (Q > 0 ? Q : 1); ++m) v[m] = s[e0 + m * stride];
-                Dft<(Q > 0 ? Q : 2)>::run(reinterpret_cast<float2(&)[Q > 0 ? Q : 2]>(v), tw);
+                for (int m = 0; m < Q; ++m) v[m] = s[e0 + m * stride];
+                Dft<Q>::run(v, tw);
 #pragma unroll
-                for (int m = 0; m < (Q > 0 ? Q : 1); ++m) s[e0 + m * stride] = v[m];
+                for (int m = 0; m < Q; ++m) s[e0 + m * stride] = v[m];
             } else {
                 float2 v[QSFT_MAX_Q];
                 for (int m = 0; m < q; ++m) v[m] = s[e0 + m * stride];
@@ -132,9 +152,22 @@ k3_pass_kernel(float2* __restrict__ x, long long B, int q, int r, long long qa, 
         }
         __syncthreads();
         stride *= qq;
+        lgs += lgq;
     }
     // store
-    if (qa == 1) {
+    if (POW2) {
+        const float4* s4 = reinterpret_cast<const float4*>(s);
+        for (int e = tid; e < T / 2; e += K3_THREADS) {
+            float4 v = s4[e];
+            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+            if (qa == 1) {
+                reinterpret_cast<float4*>(base + g0)[e] = v;
+            } else {
+                const int t = (2 * e) >> lgW, w = (2 * e) & (W - 1);
+                *reinterpret_cast<float4*>(base + g0 + (long long)t * qa + w) = v;
+            }
+        }
+    } else if (qa == 1) {
         for (int e = tid; e < T; e += K3_THREADS) {
             float2 v = s[e];
             base[g0 + e] = make_float2(v.x * scale, v.y * scale);
@@ -148,34 +181,64 @@ k3_pass_kernel(float2* __restrict__ x, long long B, int q, int r, long long qa, 
     }
 }
 
-template <int Q>
-int launch_pass(float2* x, long long batch, long long B, int q, int a, int r, int cap, float scale, cudaStream_t st) {
-    const long long qa = ipow64(q, a);
-    const int rows = (int)ipow64(q, r);
-    int W = 1, outer = 1;
+struct PassPlan {
+    int a, r, W, lgW, outer, rows, T;
+    long long qa, tiles_per_block;
+    float scale;
+};
+
+PassPlan plan_pass(long long B, int q, int a, int r, float scale) {
+    PassPlan p{};
+    p.a = a; p.r = r; p.scale = scale;
+    p.qa = ipow64(q, a);
+    p.rows = (int)ipow64(q, r);
+    p.W = 1; p.outer = 1; p.lgW = 0;
     if (a == 0) {
         // as many whole q^r blocks as fit (and exist) in one tile
-        long long fit = K3_TILE / rows;
-        long long have = B / rows;
-        long long o = 1;
+        long long fit = K3_TILE / p.rows, have = B / p.rows, o = 1;
         while (o * q <= fit && (have % (o * q)) == 0) o *= q;
-        outer = (int)o;
+        p.outer = (int)o;
     } else {
         int w = 0;
-        while (w < a && (long long)W * q * rows <= K3_TILE) {
-            W *= q;
+        while (w < a && (long long)p.W * q * p.rows <= K3_TILE) {
+            p.W *= q;
             ++w;
         }
+        while ((1 << p.lgW) < p.W) ++p.lgW;
     }
-    const int T = outer * rows * W;
-    const long long tiles_per_block = B / T;
-    const long long tiles = tiles_per_block * batch;
+    p.T = p.outer * p.rows * p.W;
+    p.tiles_per_block = B / p.T;
+    return p;
+}
+
+template <int Q>
+int launch_pass(float2* x, long long B, int q, const PassPlan& p, long long blk0, long long nblk, cudaStream_t st) {
+    const long long tiles = p.tiles_per_block * nblk;
     QSFT_CHECK_ARG(tiles <= 0x7fffffffLL, "too many tiles");
-    (void)cap;
-    k3_pass_kernel<Q><<<(unsigned)tiles, K3_THREADS, (size_t)T * sizeof(float2), st>>>(x, B, q, r, qa, W, outer, rows,
-                                                                                     tiles_per_block, scale);
+    // vector path: q = 2 / 4, tile and run lengths even (always true for W >= 2 or contiguous tiles of >= 2 elements)
+    const bool pow2 = (Q == 2 || Q == 4) && (p.T % 2 == 0) && (p.qa == 1 || p.W >= 2) && (B % 2 == 0);
+    const size_t smem = (size_t)p.T * sizeof(float2);
+    if (pow2) {
+        if constexpr (Q == 2 || Q == 4)
+            k3_pass_kernel<Q, true><<<(unsigned)tiles, K3_THREADS, smem, st>>>(x, B, q, p.r, p.qa, p.W, p.lgW, p.outer, p.rows,
+                                                                            p.tiles_per_block, blk0 * p.tiles_per_block, p.scale);
+    } else {
+        k3_pass_kernel<Q, false><<<(unsigned)tiles, K3_THREADS, smem, st>>>(x, B, q, p.r, p.qa, p.W, p.lgW, p.outer, p.rows,
+                                                                         p.tiles_per_block, blk0 * p.tiles_per_block, p.scale);
+    }
     QSFT_LAUNCHED();
     return QSFT_OK;
+}
+
+int launch_pass_q(float2* x, long long B, int q, const PassPlan& p, long long blk0, long long nblk, cudaStream_t st) {
+    switch (q) {
+        case 2: return launch_pass<2>(x, B, q, p, blk0, nblk, st);
+        case 3: return launch_pass<3>(x, B, q, p, blk0, nblk, st);
+        case 4: return launch_pass<4>(x, B, q, p, blk0, nblk, st);
+        case 5: return launch_pass<5>(x, B, q, p, blk0, nblk, st);
+        case 7: return launch_pass<7>(x, B, q, p, blk0, nblk, st);
+        default: return launch_pass<0>(x, B, q, p, blk0, nblk, st);
+    }
 }
 
 }  // namespace
@@ -201,24 +264,31 @@ extern "C" int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stre
     }
     QSFT_CHECK_ARG(cap >= 1, "q too large for the tile");
     const int passes = (b + cap - 1) / cap;
+    QSFT_CHECK_ARG(passes <= 8, "too many passes");
     const float inv = (float)(1.0 / (double)B);
     cudaStream_t st = (cudaStream_t)stream;
     float2* xx = reinterpret_cast<float2*>(x);
+    PassPlan plans[8];
     int a = 0;
     for (int p = 0; p < passes; ++p) {
-        int r = (b - a + (passes - p) - 1) / (passes - p);
-        const float scale = (p == passes - 1) ? inv : 1.0f;
-        int rc;
-        switch (q) {
-            case 2: rc = launch_pass<2>(xx, batch, B, q, a, r, cap, scale, st); break;
-            case 3: rc = launch_pass<3>(xx, batch, B, q, a, r, cap, scale, st); break;
-            case 4: rc = launch_pass<4>(xx, batch, B, q, a, r, cap, scale, st); break;
-            case 5: rc = launch_pass<5>(xx, batch, B, q, a, r, cap, scale, st); break;
-            case 7: rc = launch_pass<7>(xx, batch, B, q, a, r, cap, scale, st); break;
-            default: rc = launch_pass<0>(xx, batch, B, q, a, r, cap, scale, st); break;
-        }
-        if (rc) return rc;
+        const int r = (b - a + (passes - p) - 1) / (passes - p);
+        plans[p] = plan_pass(B, q, a, r, (p == passes - 1) ? inv : 1.0f);
         a += r;
+    }
+    // Multi-pass transforms are run chunk by chunk (a few length-B blocks at a time, all passes back to back) so that
+    // the intermediate of a chunk is still in the 126 MB L2 when the next pass reads it: DRAM sees ~1 read + 1 write.
+    long long chunk = batch;
+    if (passes > 1) {
+        const long long l2_budget = 40ll << 20;
+        chunk = l2_budget / (B * (long long)sizeof(float2));
+        if (chunk < 1) chunk = 1;
+        if (chunk > batch) chunk = batch;
+    }
+    for (long long blk0 = 0; blk0 < batch; blk0 += chunk) {
+        const long long nblk = (batch - blk0 < chunk) ? (batch - blk0) : chunk;
+        for (int p = 0; p < passes; ++p) {
+            if (int rc = launch_pass_q(xx, B, q, plans[p], blk0, nblk, st)) return rc;
+        }
     }
     return QSFT_OK;
 }
