@@ -181,6 +181,109 @@ k3_pass_kernel(float2* __restrict__ x, long long B, int q, int r, long long qa, 
     }
 }
 
+// ---- q = 4 fast pass: radix-16 steps in registers ---------------------------------------------------------
+// Tile = 4096 complex elements, 256 threads, 16 elements per thread and step.  The r <= 6 levels of the pass sit at
+// base-4 digit positions [p0, p0 + r) of the tile index e; they are processed two at a time (radix-16 butterfly in
+// registers), the first step reads global memory directly, the last one writes it directly, steps in between
+// exchange through shared memory with the XOR swizzle e ^ ((e >> 4) & 15), which makes every half-warp access
+// (16 lanes x 8 bytes) bank-conflict free for all digit positions.
+__device__ __forceinline__ int k3_swz(int e) { return e ^ ((e >> 4) & 15); }
+
+__device__ __forceinline__ void k3_r4(float2& a, float2& b, float2& c, float2& d) {
+    const float2 s02 = make_float2(a.x + c.x, a.y + c.y), d02 = make_float2(a.x - c.x, a.y - c.y);
+    const float2 s13 = make_float2(b.x + d.x, b.y + d.y), d13 = make_float2(b.x - d.x, b.y - d.y);
+    a = make_float2(s02.x + s13.x, s02.y + s13.y);
+    c = make_float2(s02.x - s13.x, s02.y - s13.y);
+    b = make_float2(d02.x + d13.y, d02.y - d13.x);   // d02 - i d13
+    d = make_float2(d02.x - d13.y, d02.y + d13.x);   // d02 + i d13
+}
+
+template <bool STRIDED>
+__global__ void __launch_bounds__(256)
+k3_q4_fast_kernel(float2* __restrict__ x, long long B, int r, int p0, long long qa, int lgW, long long tiles_per_block,
+                  long long tile0, float scale) {
+    __shared__ float2 s[4096];
+    const int tau = threadIdx.x;
+    const long long tile = tile0 + blockIdx.x;
+    const long long blk = tile / tiles_per_block;
+    const long long tin = tile - blk * tiles_per_block;
+    float2* base = x + blk * B;
+    const int W = 1 << lgW;
+    long long g0;
+    if (!STRIDED) {
+        g0 = tin * 4096ll;
+    } else {
+        const long long rows = 4096 >> lgW;
+        const long long mids = qa >> lgW;
+        const long long high = tin / mids, mid = tin - high * mids;
+        g0 = high * qa * rows + mid * W;
+    }
+    auto gptr = [&](int e) -> float2* {
+        return STRIDED ? base + g0 + (long long)(e >> lgW) * qa + (e & (W - 1)) : base + g0 + e;
+    };
+    const int nsteps = (r + 1) >> 1;
+    for (int st = 0; st < nsteps; ++st) {
+        const int p = p0 + 2 * st;
+        const bool pair = (2 * st + 1) < r;
+        const bool first = (st == 0), last = (st == nsteps - 1);
+        const int sh = 2 * p, lowmask = (1 << sh) - 1, step = 1 << sh;
+        float2 v[16];
+        int eb[4];
+        if (pair) {
+            eb[0] = ((tau >> sh) << (sh + 4)) | (tau & lowmask);
+            if (first) {
+                if (!STRIDED && p == 0) {
+                    const float4* g4 = reinterpret_cast<const float4*>(base + g0 + eb[0]);
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const float4 t4 = g4[m];
+                        v[2 * m] = make_float2(t4.x, t4.y);
+                        v[2 * m + 1] = make_float2(t4.z, t4.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) v[m] = *gptr(eb[0] + m * step);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) v[m] = s[k3_swz(eb[0] + m * step)];
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) k3_r4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);      // digit p
+#pragma unroll
+            for (int h = 0; h < 4; ++h) k3_r4(v[h], v[h + 4], v[h + 8], v[h + 12]);                      // digit p + 1
+            if (last) {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) *gptr(eb[0] + m * step) = make_float2(v[m].x * scale, v[m].y * scale);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) s[k3_swz(eb[0] + m * step)] = v[m];
+            }
+        } else {
+            // single level: four radix-4 butterflies per thread
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int beta = tau + 256 * k;
+                eb[k] = ((beta >> sh) << (sh + 2)) | (beta & lowmask);
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    v[4 * k + m] = first ? *gptr(eb[k] + m * step) : s[k3_swz(eb[k] + m * step)];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) k3_r4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    if (last) *gptr(eb[k] + m * step) = make_float2(v[4 * k + m].x * scale, v[4 * k + m].y * scale);
+                    else s[k3_swz(eb[k] + m * step)] = v[4 * k + m];
+                }
+            }
+        }
+        if (!last) __syncthreads();
+    }
+}
+
 struct PassPlan {
     int a, r, W, lgW, outer, rows, T;
     long long qa, tiles_per_block;
@@ -231,6 +334,18 @@ int launch_pass(float2* x, long long B, int q, const PassPlan& p, long long blk0
 }
 
 int launch_pass_q(float2* x, long long B, int q, const PassPlan& p, long long blk0, long long nblk, cudaStream_t st) {
+    if (q == 4 && p.T == 4096 && p.r <= 6) {
+        const long long tiles = p.tiles_per_block * nblk;
+        QSFT_CHECK_ARG(tiles <= 0x7fffffffLL, "too many tiles");
+        if (p.a == 0)
+            k3_q4_fast_kernel<false><<<(unsigned)tiles, 256, 0, st>>>(x, B, p.r, 0, 1, 0, p.tiles_per_block,
+                                                                      blk0 * p.tiles_per_block, p.scale);
+        else
+            k3_q4_fast_kernel<true><<<(unsigned)tiles, 256, 0, st>>>(x, B, p.r, p.lgW / 2, p.qa, p.lgW, p.tiles_per_block,
+                                                                     blk0 * p.tiles_per_block, p.scale);
+        QSFT_LAUNCHED();
+        return QSFT_OK;
+    }
     switch (q) {
         case 2: return launch_pass<2>(x, B, q, p, blk0, nblk, st);
         case 3: return launch_pass<3>(x, B, q, p, blk0, nblk, st);
@@ -271,7 +386,8 @@ extern "C" int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stre
     PassPlan plans[8];
     int a = 0;
     for (int p = 0; p < passes; ++p) {
-        const int r = (b - a + (passes - p) - 1) / (passes - p);
+        // first pass as large as the tile allows (contiguous, cheapest), the remaining levels spread evenly
+        const int r = (p == 0) ? ((b < cap) ? b : cap) : (b - a + (passes - p) - 1) / (passes - p);
         plans[p] = plan_pass(B, q, a, r, (p == passes - 1) ? inv : 1.0f);
         a += r;
     }
