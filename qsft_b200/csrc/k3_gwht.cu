@@ -199,15 +199,9 @@ __device__ __forceinline__ void k3_r4(float2& a, float2& b, float2& c, float2& d
 }
 
 template <bool STRIDED>
-__global__ void __launch_bounds__(256)
-k3_q4_fast_kernel(float2* __restrict__ x, long long B, int r, int p0, long long qa, int lgW, long long tiles_per_block,
-                  long long tile0, float scale) {
-    __shared__ float2 s[4096];
+__device__ __forceinline__ void k3_q4_tile(float2* __restrict__ s, float2* __restrict__ base, long long tin, int r, int p0,
+                                           long long qa, int lgW, float scale) {
     const int tau = threadIdx.x;
-    const long long tile = tile0 + blockIdx.x;
-    const long long blk = tile / tiles_per_block;
-    const long long tin = tile - blk * tiles_per_block;
-    float2* base = x + blk * B;
     const int W = 1 << lgW;
     long long g0;
     if (!STRIDED) {
@@ -236,13 +230,13 @@ k3_q4_fast_kernel(float2* __restrict__ x, long long B, int r, int p0, long long 
                     const float4* g4 = reinterpret_cast<const float4*>(base + g0 + eb[0]);
 #pragma unroll
                     for (int m = 0; m < 8; ++m) {
-                        const float4 t4 = g4[m];
+                        const float4 t4 = __ldcg(g4 + m);
                         v[2 * m] = make_float2(t4.x, t4.y);
                         v[2 * m + 1] = make_float2(t4.z, t4.w);
                     }
                 } else {
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) v[m] = *gptr(eb[0] + m * step);
+                    for (int m = 0; m < 16; ++m) v[m] = __ldcg(gptr(eb[0] + m * step));
                 }
             } else {
 #pragma unroll
@@ -267,7 +261,7 @@ k3_q4_fast_kernel(float2* __restrict__ x, long long B, int r, int p0, long long 
                 eb[k] = ((beta >> sh) << (sh + 2)) | (beta & lowmask);
 #pragma unroll
                 for (int m = 0; m < 4; ++m)
-                    v[4 * k + m] = first ? *gptr(eb[k] + m * step) : s[k3_swz(eb[k] + m * step)];
+                    v[4 * k + m] = first ? __ldcg(gptr(eb[k] + m * step)) : s[k3_swz(eb[k] + m * step)];
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) k3_r4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
@@ -281,6 +275,55 @@ k3_q4_fast_kernel(float2* __restrict__ x, long long B, int r, int p0, long long 
             }
         }
         if (!last) __syncthreads();
+    }
+}
+
+template <bool STRIDED>
+__global__ void __launch_bounds__(256)
+k3_q4_fast_kernel(float2* __restrict__ x, long long B, int r, int p0, long long qa, int lgW, long long tiles_per_block,
+                  long long tile0, float scale) {
+    __shared__ float2 s[4096];
+    const long long tile = tile0 + blockIdx.x;
+    const long long blk = tile / tiles_per_block;
+    k3_q4_tile<STRIDED>(s, x + blk * B, tile - blk * tiles_per_block, r, p0, qa, lgW, scale);
+}
+
+// Both passes of a two-pass transform (4^7 .. 4^12 points) in ONE launch: CTAs are enumerated block by block, first
+// the block's contiguous-pass tiles, then its strided-pass tiles; a strided tile waits on a per-block counter until
+// all contiguous tiles of its block have been written.  CTAs are dispatched in index order, so the tiles a waiter
+// depends on are always running or finished (no deadlock), and the intermediate of a block is consumed from L2
+// right after it was produced: DRAM sees one read and one write of the data.
+__global__ void __launch_bounds__(256)
+k3_q4_twopass_kernel(float2* __restrict__ x, long long B, int r1, int r2, long long qa2, int lgW2, int tiles1, int tiles2,
+                     unsigned int* __restrict__ done /* [nblocks] counters + [1] ticket */, long long nblocks, float scale) {
+    __shared__ float2 s[4096];
+    __shared__ unsigned int s_ticket;
+    // work items are handed out through an atomic ticket (not blockIdx): every lower ticket is then guaranteed to be
+    // held by a CTA that is already resident, which is what makes the wait below deadlock free
+    if (threadIdx.x == 0) s_ticket = atomicAdd(done + nblocks, 1u);
+    __syncthreads();
+    const unsigned int ticket = s_ticket;
+    const int per_block = tiles1 + tiles2;
+    const long long blk = ticket / per_block;
+    const int t = (int)(ticket - (unsigned int)(blk * per_block));
+    float2* base = x + blk * B;
+    if (t < tiles1) {
+        k3_q4_tile<false>(s, base, t, r1, 0, 1, 0, 1.0f);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(done + blk, 1u);
+        }
+    } else {
+        if (threadIdx.x == 0) {
+            unsigned int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + blk) : "memory");
+                if (seen < (unsigned)tiles1) __nanosleep(64);
+            } while (seen < (unsigned)tiles1);
+        }
+        __syncthreads();
+        k3_q4_tile<true>(s, base, t - tiles1, r2, lgW2 / 2, qa2, lgW2, scale);
     }
 }
 
@@ -390,6 +433,19 @@ extern "C" int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stre
         const int r = (p == 0) ? ((b < cap) ? b : cap) : (b - a + (passes - p) - 1) / (passes - p);
         plans[p] = plan_pass(B, q, a, r, (p == passes - 1) ? inv : 1.0f);
         a += r;
+    }
+    if (q == 4 && passes == 2 && plans[0].T == 4096 && plans[1].T == 4096 && plans[0].r <= 6 && plans[1].r <= 6 &&
+        plans[0].tiles_per_block + plans[1].tiles_per_block <= (1 << 20) &&
+        batch * (plans[0].tiles_per_block + plans[1].tiles_per_block) <= 0x7fffffffLL) {
+        unsigned int* done = nullptr;
+        QSFT_CUDA(cudaMallocAsync(&done, (size_t)(batch + 1) * sizeof(unsigned int), st));
+        QSFT_CUDA(cudaMemsetAsync(done, 0, (size_t)(batch + 1) * sizeof(unsigned int), st));
+        const int t1 = (int)plans[0].tiles_per_block, t2 = (int)plans[1].tiles_per_block;
+        k3_q4_twopass_kernel<<<(unsigned)(batch * (t1 + t2)), 256, 0, st>>>(xx, B, plans[0].r, plans[1].r, plans[1].qa,
+                                                                          plans[1].lgW, t1, t2, done, (long long)batch, inv);
+        QSFT_LAUNCHED();
+        QSFT_CUDA(cudaFreeAsync(done, st));
+        return QSFT_OK;
     }
     // Multi-pass transforms are run chunk by chunk (a few length-B blocks at a time, all passes back to back) so that
     // the intermediate of a chunk is still in the 126 MB L2 when the next pass reads it: DRAM sees ~1 read + 1 write.
