@@ -69,3 +69,4 @@ static inline bool index_fits(int q, int n, int limbs) {
 __host__ __device__ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 int qsft_num_sms();
+cudaError_t qsft_scratch_alloc(void** p, size_t bytes, cudaStream_t st);

@@ -398,18 +398,8 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     float* inv_scale = nullptr;
     uint8_t *A = nullptr, *Bq = nullptr;
     int rc = QSFT_OK;
-    static bool pool_tuned = false;
-    if (!pool_tuned) {  // keep the (large) operand workspace cached in the stream-ordered pool between calls
-        int dev = 0;
-        cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t thr = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-        pool_tuned = true;
-    }
     auto alloc = [&](void** p, size_t bytes) {
-        if (rc == QSFT_OK && cudaMallocAsync(p, bytes, st) != cudaSuccess) {
+        if (rc == QSFT_OK && qsft_scratch_alloc(p, bytes, st) != cudaSuccess) {
             qsft_set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
             rc = QSFT_ECUDA;
         }

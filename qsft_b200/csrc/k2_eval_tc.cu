@@ -380,7 +380,7 @@ int qsft_eval_synth_tc(const int8_t* qdig, int64_t N, const int8_t* loc, const f
     int8_t* loc8 = nullptr;
     if (q4) {  // stream-ordered scratch copy of the support digits, scaled by 8
         const long long words = S * (long long)ld / 4;
-        QSFT_CUDA(cudaMallocAsync(&loc8, (size_t)S * ld, st));
+        QSFT_CUDA(qsft_scratch_alloc((void**)&loc8, (size_t)S * ld, st));
         scale8_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(loc),
                                                                        reinterpret_cast<uint32_t*>(loc8), words);
         QSFT_LAUNCHED();

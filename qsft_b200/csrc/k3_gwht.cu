@@ -438,7 +438,7 @@ extern "C" int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stre
         plans[0].tiles_per_block + plans[1].tiles_per_block <= (1 << 20) &&
         batch * (plans[0].tiles_per_block + plans[1].tiles_per_block) <= 0x7fffffffLL) {
         unsigned int* done = nullptr;
-        QSFT_CUDA(cudaMallocAsync(&done, (size_t)(batch + 1) * sizeof(unsigned int), st));
+        QSFT_CUDA(qsft_scratch_alloc((void**)&done, (size_t)(batch + 1) * sizeof(unsigned int), st));
         QSFT_CUDA(cudaMemsetAsync(done, 0, (size_t)(batch + 1) * sizeof(unsigned int), st));
         const int t1 = (int)plans[0].tiles_per_block, t2 = (int)plans[1].tiles_per_block;
         k3_q4_twopass_kernel<<<(unsigned)(batch * (t1 + t2)), 256, 0, st>>>(xx, B, plans[0].r, plans[1].r, plans[1].qa,

@@ -24,6 +24,22 @@ int qsft_num_sms() {
     return sms;
 }
 
+// Stream-ordered scratch memory: keep freed blocks cached in the default pool (the default release threshold of 0
+// hands memory back to the driver at every synchronisation, which makes the next cudaMallocAsync cost milliseconds).
+cudaError_t qsft_scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+    static bool tuned = false;
+    if (!tuned) {
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        tuned = true;
+    }
+    return cudaMallocAsync(p, bytes, st);
+}
+
 extern "C" {
 const char* qsft_last_error(void) { return g_err; }
 int qsft_version(void) { return 100; }

@@ -331,3 +331,75 @@ def test_construct_and_transform_all_eval_impls_agree(impl):
                          reconstruct_method_channel="nso").transform(sig, output="arrays")
     assert [tuple(int(v) for v in r) for r in arr["locations"]] == list(res.keys())
     assert np.allclose(arr["values"], np.array(list(res.values())), rtol=0, atol=1e-6)
+
+
+# ---- BASELINE configs at full size ----------------------------------------------------------------------------
+def test_config2_full_size_noisy_nmse_matches_reference_run():
+    """BASELINE config 2 at full size (q=4 n=20 b=7 S=1000 C=3 nso R=3, 20 dB, seed 0).  The unmodified reference
+    recovered 1000/1000 coefficients with NMSE 3.3930553e-06 on this seed (BASELINE.md section 2, 523 s on 8 cores);
+    same seed => same Ms, Ds, support, get_MDU order and noise, so the NMSE must agree within 1 %."""
+    n, q, S, b, C, R = 20, 4, 1000, 7, 3, 3
+    noise_sd = float(np.sqrt(S / 10 ** (20 / 10)))
+    qa = {"query_method": "complex", "num_subsample": C, "delays_method_source": "identity", "subsampling_method": "qsft",
+          "delays_method_channel": "nso", "num_repeat": R, "b": b}
+    np.random.seed(0)
+    sig = qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=1, a_max=1, noise_sd=noise_sd,
+                                                  query_args=dict(qa))
+    res = qsft_b200.QSFT(num_subsample=C, num_repeat=R, b=b, reconstruct_method_source="identity",
+                         reconstruct_method_channel="nso").transform(sig, report=True)
+    assert res["n_samples"] == 3096576
+    assert set(res["gwht"].keys()) == set(sig.signal_w.keys())
+    nm = orc.nmse(res["gwht"], sig.signal_w)
+    assert abs(nm - 3.3930553e-06) <= 0.01 * 3.3930553e-06, nm
+
+
+def test_config3_shape_coded_q3_vs_oracle_closed_form():
+    """BASELINE config 3 (q=3 n=30 b=8 S=5000, coded delays t=4, C=3): construct on the GPU (plain tcgen05 path, q=3),
+    compare the bins with the closed form and the transform with the oracle fed the same bins."""
+    n, q, S, b, C, t = 30, 3, 5000, 8, 3, 4
+    qa = {"query_method": "complex", "num_subsample": C, "delays_method_source": "coded", "subsampling_method": "qsft",
+          "delays_method_channel": "identity", "num_repeat": 1, "b": b, "t": t}
+    np.random.seed(3)
+    sig = qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=1, a_max=1, noise_sd=0.0,
+                                                  query_args=dict(qa), max_weight=t)
+    assert sig.get_source_parity() == 33
+    np.random.seed(3)
+    sw, locq, strengths = orc.generate_signal_w(n, q, S, 1, 1, max_weight=t)
+    osig = orc.OracleSignal(n, q, dict(qa), locq, strengths, noise_sd=0.0, signal_w=sw, use_closed_form=True)
+    for c in range(C):
+        want = osig.Us[c][0][b]
+        got = sig.Us[c][0][b].cpu().numpy()
+        assert np.max(np.abs(got - want)) <= 1e-5 * np.max(np.abs(want))
+    st = np.random.get_state()
+    want = orc.transform(osig, C, 1, b, "coded", "identity", source_decoder=orc.get_reed_solomon_dec(n, t, q))
+    np.random.set_state(st)
+    got = qsft_b200.QSFT(num_subsample=C, num_repeat=1, b=b, reconstruct_method_source="coded",
+                         reconstruct_method_channel="identity",
+                         source_decoder=qsft_b200.get_reed_solomon_dec(n, t, q)).transform(sig)
+    assert list(got.keys()) == list(want.keys())
+    assert max(abs(got[k] - want[k]) for k in want) < 1e-5
+    assert len(got) >= 0.99 * len(sw) and set(got.keys()) <= set(sw.keys())
+
+
+def test_config4_shape_wide_index_low_degree():
+    """BASELINE config 4 shape with the reference-runnable delays (identity source + nso; 'coded' needs prime q):
+    q=4 n=50 (100-bit indices) b=8, weight <= 3 support, 30 dB.  Exact support recovery and NMSE below the noise."""
+    n, q, S, b, C, R = 50, 4, 1000, 8, 3, 3
+    noise_sd = float(np.sqrt(S / 10 ** (30 / 10)))
+    qa = {"query_method": "complex", "num_subsample": C, "delays_method_source": "identity", "subsampling_method": "qsft",
+          "delays_method_channel": "nso", "num_repeat": R, "b": b}
+    np.random.seed(4)
+    sig = qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=1, a_max=1, noise_sd=noise_sd,
+                                                  query_args=dict(qa), max_weight=3)
+    res = qsft_b200.QSFT(num_subsample=C, num_repeat=R, b=b, reconstruct_method_source="identity",
+                         reconstruct_method_channel="nso").transform(sig, report=True, sort=True)
+    assert set(res["gwht"].keys()) == set(sig.signal_w.keys())
+    assert res["max_hamming_weight"] <= 3
+    assert orc.nmse(res["gwht"], sig.signal_w) < 1e-4
+    # generic-signal route on the same object: K1 indices as Python ints (100 bits) -> subsample() -> same samples
+    idx = sig._get_qsft_query_indices(sig.Ms[0], sig.Ds[0][0][:2])
+    assert max(int(v).bit_length() for v in idx[1][:1000]) > 64
+    vals = sig.subsample(list(idx[1][:500]))
+    dig = orc.dec_to_qary_vec(list(idx[1][:500]), q, n).T
+    want = orc.synth_eval_digits(dig, np.asarray(sig.locq), sig.strengths, q)
+    assert np.max(np.abs(vals - want)) <= 1e-4

@@ -1,0 +1,89 @@
+"""Stand-alone timings of the HBM-bound kernels (K1, K3, K4) at config-5 sizes: GB/s against MEASURED_PEAKS.json."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import qsft_b200  # noqa: E402
+from qsft_b200 import ops, utils  # noqa: E402
+
+dev = torch.device("cuda", 0)
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+q, n, b, P = 4, 40, 10, 41
+B = q ** b
+
+
+def timeit(fn, iters=10, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.add_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)     # 256 MB > L2
+out = {}
+x = torch.randn((P, B, 2), device=dev).view(torch.float32)
+xc = torch.view_as_complex(x.view(P, B, 2))
+ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
+out["k3_gwht 41 x 4^10"] = {"ms": ms, "GBps_algorithmic(16B/elem)": 16 * P * B / ms / 1e6, "frac": 16 * P * B / ms / 1e6 / peak}
+for bb, rows in [(7, 1024), (8, 512), (6, 4096), (12, 4)]:
+    y = torch.view_as_complex(torch.randn((rows, q ** bb, 2), device=dev))
+    ms = timeit(lambda: ops.gwht_batch_(y, q, bb), flush=flush)
+    out[f"k3_gwht {rows} x 4^{bb}"] = {"ms": ms, "GBps": 16 * rows * q ** bb / ms / 1e6, "frac": 16 * rows * q ** bb / ms / 1e6 / peak}
+y = torch.view_as_complex(torch.randn((64, 3 ** 12, 2), device=dev))
+ms = timeit(lambda: ops.gwht_batch_(y, 3, 12), flush=flush)
+out["k3_gwht 64 x 3^12"] = {"ms": ms, "GBps": 16 * 64 * 3 ** 12 / ms / 1e6, "frac": 16 * 64 * 3 ** 12 / ms / 1e6 / peak}
+
+rng = np.random.default_rng(0)
+M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
+ms = timeit(lambda: ops.query_lattice(M, D, q, device=dev, want_idx=True, want_digits=False), flush=flush)
+out["k1_lattice idx only (16 B/index)"] = {"ms": ms, "GBps": 16 * P * B / ms / 1e6, "frac": 16 * P * B / ms / 1e6 / peak}
+ms = timeit(lambda: ops.query_lattice(M, D, q, device=dev, want_idx=False, want_digits=True), flush=flush)
+out["k1_lattice digits only (64 B/row)"] = {"ms": ms, "GBps": 64 * P * B / ms / 1e6, "frac": 64 * P * B / ms / 1e6 / peak}
+
+# K4: one classification round on config-5 bins (C=3, P=41), ~10 % singletons
+np.random.seed(1)
+S, C = 100_000, 3
+sw, locq, strengths = qsft_b200.generate_signal_w(n, q, S, 1, 1, 0, full=False)
+Ms, Ds = qsft_b200.get_Ms_and_Ds(n, q, query_method="complex", num_subsample=C, delays_method_source="identity",
+                                 delays_method_channel="nso", num_repeat=1, b=b)
+ld = utils.padded_ld(n)
+loc = ops.pad_digits(locq.T, ld, dev)
+a = torch.from_numpy(strengths.astype(np.complex64)).to(dev)
+U0 = torch.stack([ops.closed_form_bins(Ms[c], Ds[c][0], q, loc, a) for c in range(C)]).contiguous()
+Dall = np.stack([np.vstack(Ds[c]) for c in range(C)])
+prob = ops.PeelProblem(q, n, b, Ms, Dall, n + 1, "nso", "identity", 1e-9, dev)
+prob.alloc(4 * C * B, C * B)
+
+
+def classify_round1():
+    prob.counters.zero_()
+    prob.classify(U0, 0, B, 1)
+
+
+ms = timeit(classify_round1, flush=flush)
+out["k4_classify round 1 (C=3,P=41,B=4^10, 25% occupied)"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
+Uz = torch.zeros_like(U0)
+ms = timeit(lambda: (prob.counters.zero_(), prob.classify(Uz, 0, B, 1)), flush=flush)
+out["k4_classify all-zeroton round"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
+U = U0.clone()
+ms = timeit(lambda: (U.copy_(U0), prob.peel(U)), flush=flush)
+ms_copy = timeit(lambda: U.copy_(U0), flush=flush)
+out["k4 full peel loop (3 rounds incl. host syncs)"] = {"ms": ms - ms_copy, "rounds": prob.peel(U0.clone())[1]}
+out["copy U (torch) reference"] = {"ms": ms_copy, "GBps": 16 * C * P * B / ms_copy / 1e6}
+print(json.dumps(out, indent=1))
