@@ -106,19 +106,39 @@ class SubsampledSignal(Signal):
         self.transformTimes = [[{} for _ in range(R)] for _ in range(C)]
         events = []
         t_sample0 = time.time()
+        cache = bool(self.foldername) and world == 1
+        if cache:
+            Path(f"{self.foldername}/samples").mkdir(exist_ok=True)
+            Path(f"{self.foldername}/transforms").mkdir(exist_ok=True)
         for i in range(C):
             for j in range(R):
                 g0 = (i * R + j) * P_src
                 p0, p1 = max(lo, g0) - g0, min(hi, g0 + P_src) - g0
-                if p1 > p0:
-                    samples = self._sample_rows(self.Ms[i], np.asarray(self.Ds[i][j])[p0:p1])       # (p1-p0, B)
+                if p1 <= p0:
+                    continue
+                # on-disk cache in the reference's layout (input_signal_subsampled.py:122-155): transforms/U{i}_{j}.pickle
+                # = ({b: [row arrays]}, {b: seconds}), samples/M{i}_D{j}.pickle = complex array (P_src, B)
+                transform_file = Path(f"{self.foldername}/transforms/U{i}_{j}.pickle")
+                sample_file = Path(f"{self.foldername}/samples/M{i}_D{j}.pickle")
+                if cache and transform_file.is_file():
+                    Us_ij, Ts_ij = load_data(transform_file)
                     for bb in self.all_bs:
-                        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        ev0.record()
-                        self._Ubuf[bb][g0 + p0:g0 + p1] = self._compute_subtransform(samples, bb)
-                        ev1.record()
-                        events.append((i, j, bb, ev0, ev1))
-                    del samples
+                        self._Ubuf[bb][g0:g0 + P_src] = torch.from_numpy(np.asarray(Us_ij[bb]).astype(np.complex64)).to(dev)
+                        self.transformTimes[i][j][bb] = Ts_ij[bb]
+                    continue
+                if cache and sample_file.is_file():
+                    samples = torch.from_numpy(np.asarray(load_data(sample_file)).astype(np.complex64)).to(dev)
+                else:
+                    samples = self._sample_rows(self.Ms[i], np.asarray(self.Ds[i][j])[p0:p1])       # (p1-p0, B)
+                    if cache:
+                        save_data(samples.cpu().numpy().astype(complex), sample_file)
+                for bb in self.all_bs:
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                    self._Ubuf[bb][g0 + p0:g0 + p1] = self._compute_subtransform(samples, bb)
+                    ev1.record()
+                    events.append((i, j, bb, ev0, ev1))
+                del samples
         if world > 1:
             for bb in self.all_bs:
                 self.dist.all_gather_rows_(self._Ubuf[bb], per)
@@ -129,11 +149,17 @@ class SubsampledSignal(Signal):
                 g0 = (i * R + j) * P_src
                 for bb in self.all_bs:
                     self.Us[i][j][bb] = self._Ubuf[bb][g0:g0 + P_src]
-                    self.transformTimes[i][j][bb] = 0.0
+                    self.transformTimes[i][j].setdefault(bb, 0.0)
+        fresh = set()
         for (i, j, bb, ev0, ev1) in events:
             dt = ev0.elapsed_time(ev1) * 1e-3
             self.transformTimes[i][j][bb] += dt
             fft_total += dt
+            fresh.add((i, j))
+        if cache:
+            for (i, j) in fresh:
+                save_data(({bb: list(self.Us[i][j][bb].cpu().numpy().astype(complex)) for bb in self.all_bs},
+                           dict(self.transformTimes[i][j])), Path(f"{self.foldername}/transforms/U{i}_{j}.pickle"))
         self.sample_time = time.time() - t_sample0 - fft_total
 
     def _sample_rows(self, M, D_rows):

@@ -408,3 +408,73 @@ def test_config4_shape_wide_index_low_degree():
     dig = orc.dec_to_qary_vec(list(idx[1][:500]), q, n).T
     want = orc.synth_eval_digits(dig, np.asarray(sig.locq), sig.strengths, q)
     assert np.max(np.abs(vals - want)) <= 1e-4
+
+
+# ---- "next" rows of SURVEY 8f: generic black-box signals, on-disk cache, test-NMSE evaluator -----------------
+def test_generic_blackbox_signal_host_subsample_route():
+    """A user signal that only implements subsample(query_indices) like the reference's RNA signal: indices come from
+    K1 as Python ints, samples go back to the GPU for K3/K4."""
+    n, q, b, C = 12, 3, 4, 3
+    rng = np.random.default_rng(5)
+    locq = rng.integers(0, q, (n, 25))
+    a = np.exp(1j * rng.uniform(0, 2 * np.pi, 25))
+
+    class BlackBox(qsft_b200.SubsampledSignal):
+        calls = 0
+
+        def subsample(self, query_indices):
+            BlackBox.calls += 1
+            assert all(isinstance(v, int) for v in list(query_indices)[:3])
+            dig = orc.dec_to_qary_vec(list(query_indices), q, n).T
+            return orc.synth_eval_digits(dig, locq, a, q)
+
+    qa = {"query_method": "complex", "num_subsample": C, "delays_method_source": "identity", "subsampling_method": "qsft",
+          "delays_method_channel": "identity", "num_repeat": 1, "b": b}
+    np.random.seed(2)
+    sig = BlackBox(n=n, q=q, query_args=qa, noise_sd=0)
+    sig.noise_sd = 0
+    assert BlackBox.calls == C                       # q^b = 81 <= 10000 -> one call per (M, D) block like the reference
+    res = qsft_b200.QSFT(num_subsample=C, num_repeat=1, b=b, reconstruct_method_source="identity",
+                         reconstruct_method_channel="identity").transform(sig)
+    want = dict(zip(map(tuple, locq.T.tolist()), a))
+    assert set(res.keys()) == set(want.keys())
+    assert max(abs(res[k] - v) for k, v in want.items()) < 1e-5
+
+
+def test_folder_cache_reference_layout(tmp_path):
+    g = load_golden("q4_n10_allbs_subselect")
+    p = case_params(g)
+    folder = str(tmp_path / "sig")
+    sig = _build_signal(p, folder=folder)
+    import os
+    assert os.path.isfile(f"{folder}/Ms_and_Ds.pickle") and os.path.isfile(f"{folder}/samples/M0_D0.pickle")
+    Us_ij, Ts_ij = utils.load_data(f"{folder}/transforms/U2_1.pickle")
+    assert sorted(Us_ij.keys()) == [2, 3, 4] and np.asarray(Us_ij[4]).shape == (p["P_src"], 4 ** 4)
+    assert np.max(np.abs(np.asarray(Us_ij[3]) - g["Us_b3"][2, 1])) < 1e-6
+    # second construction loads everything from disk (RNG untouched, no kernels needed for sampling)
+    state = np.random.get_state()
+    sig2 = qsft_b200.SyntheticSubsampledSignal(signal_w=sig.signal_w, locq=sig.locq, strengths=sig.strengths,
+                                               noise_sd=sig.noise_sd, n=p["n"], q=p["q"], query_args=dict(p["query_args"]),
+                                               folder=folder)
+    assert np.array_equal(np.random.get_state()[1], state[1])
+    assert np.array_equal(np.array(sig2.Ms), np.array(sig.Ms))
+    for bb in sig.all_bs:
+        assert torch.allclose(sig2.Us[1][0][bb], sig.Us[1][0][bb], atol=1e-7)
+
+
+def test_test_nmse_evaluator():
+    from qsft_b200.test_helper import evaluate_model, test_nmse
+    q, n = 4, 40
+    rng = np.random.default_rng(8)
+    K = rng.integers(0, q, (300, n))
+    beta = {tuple(int(v) for v in k): complex(np.exp(1j * rng.uniform(0, 6.28))) for k in K}
+    idx = [int(rng.integers(0, 2 ** 62)) * (2 ** 18) + int(rng.integers(0, 2 ** 18)) for _ in range(2000)]   # 80-bit
+    dig = orc.dec_to_qary_vec(idx, q, n).T
+    y = orc.synth_eval_digits(dig, np.array(list(beta.keys())).T, np.array(list(beta.values())), q)
+    assert np.max(np.abs(evaluate_model(beta, idx, q, n) - y)) < 1e-4
+    assert test_nmse(beta, idx, y, q, n) < 1e-10
+    half = dict(list(beta.items())[:150])
+    y_half = orc.synth_eval_digits(dig, np.array(list(half.keys())).T, np.array(list(half.values())), q)
+    ref = np.linalg.norm(y_half - y) ** 2 / np.linalg.norm(y) ** 2
+    assert abs(test_nmse(half, idx, y, q, n) - ref) < 1e-6
+    assert test_nmse({}, idx, y, q, n) == 1
