@@ -94,8 +94,8 @@ __device__ __forceinline__ uint32_t dot4(uint32_t a, uint32_t b, int nd) {
 // ---- operand generation -----------------------------------------------------------------------------------
 // per support element: bin hash halves (h_hi, h_lo) and the delay phases e[p][s] = <d_p, k_s> mod 4
 __global__ void lt_prep_kernel(const int8_t* __restrict__ M, const int8_t* __restrict__ D, const int8_t* __restrict__ loc,
-                               long long S, int n, int b, int b1, int P, int ld, uint32_t* __restrict__ hhi,
-                               uint32_t* __restrict__ hlo, uint8_t* __restrict__ e) {
+                               long long S, long long Se, int n, int b, int b1, int P, int ld, uint32_t* __restrict__ hhi,
+                               uint32_t* __restrict__ hlo, uint8_t* __restrict__ e /* (P, Se), Se even */) {
     extern __shared__ int8_t lt_sm[];
     int8_t* sM = lt_sm;             // (n, b)
     int8_t* sD = lt_sm + n * b;     // (P, n)
@@ -119,7 +119,7 @@ __global__ void lt_prep_kernel(const int8_t* __restrict__ M, const int8_t* __res
     for (int p = 0; p < P; ++p) {
         int acc = 0;
         for (int u = 0; u < n; ++u) acc += (int)sD[p * n + u] * (int)k[u];
-        e[(size_t)p * S + s] = (uint8_t)(acc & 3);
+        e[(size_t)p * Se + s] = (uint8_t)(acc & 3);
     }
 }
 
@@ -179,45 +179,61 @@ __global__ void lt_agen_kernel(const uint32_t* __restrict__ hhi, long long S, in
 }
 
 // B'_l[p * Nlo + l_lo][2 s + comp] = limb l of (Re, Im) of a_s * i^(e[p][s] + <h_lo(s), l_lo>)
-__global__ void lt_bgen_kernel(const uint32_t* __restrict__ hlo, const uint8_t* __restrict__ e, const int2* __restrict__ alimb,
-                               long long S, int b2, int P, long long Nlo, long long Kp, uint32_t* __restrict__ Bq) {
+// One thread owns two consecutive support elements (4 K' bytes: x0 y0 x1 y1 per limb) of one l_lo and walks over the
+// delay rows.  A rotation by i^r is a byte swap of the (x, y) pair (PRMT) followed by a per-byte conditional negate
+// ((w ^ m) - m with SIMD-in-word subtract): ~2 instructions per generated byte, so the kernel is HBM-write bound.
+__global__ void __launch_bounds__(256)
+lt_bgen_kernel(const uint32_t* __restrict__ hlo, const uint8_t* __restrict__ e, const int2* __restrict__ alimb,
+               long long S, long long Se, int b2, int P, long long Nlo, long long Kp, uint32_t* __restrict__ Bq) {
     const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t llo = blockIdx.y;
     if (pair * 4 >= Kp) return;
-    uint32_t tlo[2] = {0, 0};
-    int lr[2][3], li[2][3];
-    bool live[2];
+    const long long s0 = 2 * pair;
+    const bool live0 = s0 < S, live1 = s0 + 1 < S;
+    // limb words [x0, y0, x1, y1] and the lattice part of the rotation
+    uint32_t base[3] = {0, 0, 0};
+    uint32_t t0 = 0, t1 = 0;
+    if (live0) {
+        const int2 w = alimb[s0];
+        t0 = dot4(hlo[s0], llo, b2);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const long long s = 2 * pair + h;
-        live[h] = s < S;
-        int2 w = live[h] ? alimb[s] : make_int2(0, 0);
-        if (live[h]) tlo[h] = dot4(hlo[s], llo, b2);
+        for (int l = 0; l < 3; ++l)
+            base[l] |= (((uint32_t)w.x >> (8 * l)) & 0xffu) | ((((uint32_t)w.y >> (8 * l)) & 0xffu) << 8);
+    }
+    if (live1) {
+        const int2 w = alimb[s0 + 1];
+        t1 = dot4(hlo[s0 + 1], llo, b2);
 #pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            lr[h][l] = (int)(int8_t)((uint32_t)w.x >> (8 * l));
-            li[h][l] = (int)(int8_t)((uint32_t)w.y >> (8 * l));
-        }
+        for (int l = 0; l < 3; ++l)
+            base[l] |= ((((uint32_t)w.x >> (8 * l)) & 0xffu) << 16) | ((((uint32_t)w.y >> (8 * l)) & 0xffu) << 24);
     }
     const size_t Ntot = (size_t)P * Nlo;
+    const size_t row_words = (size_t)Kp / 4;
+    uint32_t* out0 = Bq + ((size_t)llo) * row_words + pair;
+    const uint8_t* ep = e + s0;
     for (int p = 0; p < P; ++p) {
-        uint32_t word[3] = {0, 0, 0};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const long long s = 2 * pair + h;
-            const uint32_t r = live[h] ? ((tlo[h] + e[(size_t)p * S + s]) & 3u) : 0u;
-#pragma unroll
-            for (int l = 0; l < 3; ++l) {
-                // (x, y) * i^r
-                const int x = lr[h][l], y = li[h][l];
-                const int yr = (r == 0) ? x : (r == 1) ? -y : (r == 2) ? -x : y;
-                const int yi = (r == 0) ? y : (r == 1) ? x : (r == 2) ? -y : -x;
-                word[l] |= ((uint32_t)(yr & 0xff) | ((uint32_t)(yi & 0xff) << 8)) << (16 * h);
-            }
+        // e[p][s0], e[p][s0 + 1] (s0 is even: one aligned 16-bit load when both are live)
+        uint32_t r0 = t0, r1 = t1;
+        if (live1) {
+            const uint32_t ee = *reinterpret_cast<const uint16_t*>(ep + (size_t)p * Se);
+            r0 += ee & 0xffu;
+            r1 += ee >> 8;
+        } else if (live0) {
+            r0 += ep[(size_t)p * Se];
         }
-        const size_t rowi = (size_t)p * Nlo + llo;
+        r0 &= 3u;
+        r1 &= 3u;
+        // rotation r: swap (x, y) iff r & 1; negate byte 0 iff (r & 1) ^ (r >> 1); negate byte 1 iff r >> 1
+        const uint32_t b0 = r0 & 1u, h0 = r0 >> 1, b1 = r1 & 1u, h1 = r1 >> 1;
+        const uint32_t sel = (b0 ? 0x01u : 0x10u) | ((b1 ? 0x23u : 0x32u) << 8);
+        const uint32_t m = ((0u - (b0 ^ h0)) & 0x000000ffu) | ((0u - h0) & 0x0000ff00u) |
+                           ((0u - (b1 ^ h1)) & 0x00ff0000u) | ((0u - h1) & 0xff000000u);
+        uint32_t* o = out0 + (size_t)p * Nlo * row_words;
 #pragma unroll
-        for (int l = 0; l < 3; ++l) Bq[(((size_t)l * Ntot + rowi) * Kp) / 4 + pair] = word[l];
+        for (int l = 0; l < 3; ++l) {
+            const uint32_t sw = __byte_perm(base[l], 0u, sel);
+            o[(size_t)l * Ntot * row_words] = __vsub4(sw ^ m, m);
+        }
     }
 }
 
@@ -406,7 +422,8 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     };
     alloc((void**)&hhi, (size_t)S * 4);
     alloc((void**)&hlo, (size_t)S * 4);
-    alloc((void**)&e, (size_t)P * S);
+    const long long Se = (S + 3) & ~3ll;     // even row stride so that e[p][s0], e[p][s0+1] is one aligned 16-bit load
+    alloc((void**)&e, (size_t)P * Se);
     alloc((void**)&alimb, (size_t)S * 8);
     alloc((void**)&amax, 8);
     alloc((void**)&A, (size_t)2 * Mhi * Kp);
@@ -416,12 +433,12 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
         const int T = 256;
         const unsigned sb = (unsigned)((S + T - 1) / T);
         cudaMemsetAsync(amax, 0, 8, st);
-        lt_prep_kernel<<<sb, T, (size_t)n * b + (size_t)P * n, st>>>(M, D, loc, S, n, b, b1, P, ld, hhi, hlo, e);
+        lt_prep_kernel<<<sb, T, (size_t)n * b + (size_t)P * n, st>>>(M, D, loc, S, Se, n, b, b1, P, ld, hhi, hlo, e);
         lt_amax_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax);
         lt_quant_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax, inv_scale, alimb);
         const unsigned pb = (unsigned)((Kp / 4 + T - 1) / T);
         lt_agen_kernel<<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, S, b1, Kp, reinterpret_cast<uint32_t*>(A));
-        lt_bgen_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, e, alimb, S, b2, P, Nlo, Kp, reinterpret_cast<uint32_t*>(Bq));
+        lt_bgen_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, e, alimb, S, Se, b2, P, Nlo, Kp, reinterpret_cast<uint32_t*>(Bq));
         g_qsft_launches.fetch_add(5, std::memory_order_relaxed);
         CUtensorMap ma, mb;
         rc = lt_make_map(&ma, A, 2 * Mhi, Kp);

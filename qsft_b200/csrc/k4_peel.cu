@@ -262,11 +262,24 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
                 if (d.channel == 0) {
                     const float2 v0 = col[0];
                     const float2 v = col[(size_t)i * B];
-                    const double a0 = atan2((double)v0.y, (double)v0.x);
-                    const double a = atan2((double)v.y, (double)v.x);
-                    const long long r = (long long)rint(qd * (a - a0) / kTwoPi);        // half-to-even like np.round
-                    const int m = (int)(r % d.q);
-                    symv = m < 0 ? m + d.q : m;
+                    symv = -1;
+                    // fast path in fp32; anything within 0.01 of a rounding boundary is redone in fp64 so the decision
+                    // always equals the fp64 one (np.angle / np.round in the reference)
+                    if (fabsf(v0.x) + fabsf(v0.y) > 1e-30f && fabsf(v.x) + fabsf(v.y) > 1e-30f) {
+                        const float u = (float)d.q * (atan2f(v.y, v.x) - atan2f(v0.y, v0.x)) * 0.15915494309189535f;
+                        const float m = rintf(u);
+                        if (fabsf(u - m) < 0.49f) {
+                            const int mi = (int)m % d.q;
+                            symv = mi < 0 ? mi + d.q : mi;
+                        }
+                    }
+                    if (symv < 0) {
+                        const double a0 = atan2((double)v0.y, (double)v0.x);
+                        const double a = atan2((double)v.y, (double)v.x);
+                        const long long r = (long long)rint(qd * (a - a0) / kTwoPi);    // half-to-even like np.round
+                        const int m = (int)(r % d.q);
+                        symv = m < 0 ? m + d.q : m;
+                    }
                 } else {
                     double ar = 0.0, ai = 0.0;
                     for (int r = 0; r < d.R; ++r) {
@@ -277,20 +290,31 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
                     }
                     ar /= d.R;
                     ai /= d.R;
-                    double th = atan2(ai, ar);
-                    if (th < 0.0) th += kTwoPi;                                          // numpy: angle % (2 pi)
-                    if (th >= kTwoPi) th -= kTwoPi;
-                    const double step = kTwoPi / qd;
-                    int best = 0;
-                    double bd = fabs(0.0 - th);
-                    for (int m = 1; m <= d.q; ++m) {                                     // argmin over q+1 roots, first minimum
-                        const double dist = fabs(step * (double)m - th);
-                        if (dist < bd) {
-                            bd = dist;
-                            best = m;
-                        }
+                    symv = -1;
+                    const float arf = (float)ar, aif = (float)ai;
+                    if (fabsf(arf) + fabsf(aif) > 1e-30f) {
+                        float thf = atan2f(aif, arf);
+                        if (thf < 0.f) thf += 6.283185307179586f;
+                        const float u = thf * (float)d.q * 0.15915494309189535f;        // in [0, q]
+                        const float m = rintf(u);
+                        if (fabsf(u - m) < 0.49f) symv = (int)m % d.q;                   // nearest of the q+1 roots, mod q
                     }
-                    symv = best % d.q;
+                    if (symv < 0) {
+                        double th = atan2(ai, ar);
+                        if (th < 0.0) th += kTwoPi;                                      // numpy: angle % (2 pi)
+                        if (th >= kTwoPi) th -= kTwoPi;
+                        const double step = kTwoPi / qd;
+                        int best = 0;
+                        double bd = fabs(0.0 - th);
+                        for (int m = 1; m <= d.q; ++m) {                                 // argmin over q+1 roots, first minimum
+                            const double dist = fabs(step * (double)m - th);
+                            if (dist < bd) {
+                                bd = dist;
+                                best = m;
+                            }
+                        }
+                        symv = best % d.q;
+                    }
                 }
                 s_sym[warp][i - 1] = (uint8_t)symv;
             }
