@@ -38,7 +38,7 @@ def log(msg):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--repeat", type=int, default=DEFAULT_REPEAT, help="num_repeat R of the NSO delays")
@@ -315,9 +315,17 @@ def run_ours(a):
     k2_ms, k2_calls, k2_pairs = kt.get(k2_name, (0.0, 0, 0))
     ops_per_launch = ops_per_pair * (k2_pairs / max(1, k2_calls))      # algorithmic int8 ops of one launch
     achieved = ops_per_launch / (k2_ms / max(1, k2_calls) * 1e-3) / 1e12 if k2_ms > 0 else 0.0
+    # DRAM traffic of the GEMM launch from the committed ncu capture (same shape only), else null
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_k2l_traffic.json")))
+        if k2_name == "k2_eval_lattice" and a.gpus == 1 and (n, b, S) == (40, 10, 100_000):
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+    except Exception:
+        pass
     roofline = {"kernel": k2_desc, "bound": "tensor",
                 "achieved": achieved, "peak": 2 * bf16, "unit": "TFLOP/s", "frac": achieved / (2 * bf16),
-                "traffic": None, "peak_source": peak_src, "int8_ops_per_pair": ops_per_pair,
+                "traffic": traffic, "peak_source": peak_src, "int8_ops_per_pair": ops_per_pair,
                 "pairs_per_s": k2_pairs / (k2_ms * 1e-3) if k2_ms > 0 else None,
                 "share_of_step": (k2_ms / a.steps) / ms_per_step if ms_per_step else None,
                 "per_kernel_ms_per_step": {k: v[0] / a.steps for k, v in kt.items()}}
