@@ -12,6 +12,7 @@
 // GEMM tile: 128 rows of A' (64 l_hi x {re, im}) x 128 columns (l_lo) x 3 limb accumulators (384 TMEM columns);
 // K' = 2S bytes streamed in 128-byte slabs through a 3-stage TMA/mbarrier ring (A slab 16 KB + 3 limb slabs 48 KB).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -405,7 +406,17 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     const int b1 = b / 2, b2 = b - b1;
     const long long Mhi = ipow64(4, b1), Nlo = ipow64(4, b2);
     const long long Kp = (2 * S + LT_BK - 1) / LT_BK * LT_BK;
-    const long long Ntot = (long long)P * Nlo;
+    // The limb operand B' takes 3 * Nlo * Kp bytes per delay row: process the rows in chunks that keep it under a
+    // scratch budget (default 32 GB, QSFT_LATTICE_SCRATCH_GB overrides); A' is generated once and reused.
+    double budget_gb = 32.0;
+    if (const char* env = getenv("QSFT_LATTICE_SCRATCH_GB")) {
+        const double v = atof(env);
+        if (v > 0.0) budget_gb = v;
+    }
+    const double per_row = (double)LT_LIMBS * (double)Nlo * (double)Kp;
+    long long Pc = (long long)(budget_gb * 1e9 / per_row);
+    if (Pc < 1) Pc = 1;
+    if (Pc > P) Pc = P;
     // stream-ordered workspace
     uint32_t *hhi = nullptr, *hlo = nullptr;
     uint8_t* e = nullptr;
@@ -427,7 +438,7 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     alloc((void**)&alimb, (size_t)S * 8);
     alloc((void**)&amax, 8);
     alloc((void**)&A, (size_t)2 * Mhi * Kp);
-    alloc((void**)&Bq, (size_t)LT_LIMBS * Ntot * Kp);
+    alloc((void**)&Bq, (size_t)LT_LIMBS * Pc * Nlo * Kp);
     inv_scale = amax ? reinterpret_cast<float*>(amax + 1) : nullptr;
     if (rc == QSFT_OK) {
         const int T = 256;
@@ -438,11 +449,9 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
         lt_quant_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax, inv_scale, alimb);
         const unsigned pb = (unsigned)((Kp / 4 + T - 1) / T);
         lt_agen_kernel<<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, S, b1, Kp, reinterpret_cast<uint32_t*>(A));
-        lt_bgen_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, e, alimb, S, Se, b2, P, Nlo, Kp, reinterpret_cast<uint32_t*>(Bq));
-        g_qsft_launches.fetch_add(5, std::memory_order_relaxed);
+        g_qsft_launches.fetch_add(4, std::memory_order_relaxed);
         CUtensorMap ma, mb;
         rc = lt_make_map(&ma, A, 2 * Mhi, Kp);
-        if (!rc) rc = lt_make_map(&mb, Bq, LT_LIMBS * Ntot, Kp);
         if (!rc) {
             static bool attr = false;
             if (!attr) {
@@ -453,11 +462,17 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
                 attr = true;
             }
         }
-        if (!rc) {
+        for (long long p0 = 0; p0 < P && !rc; p0 += Pc) {
+            const long long pc = (P - p0 < Pc) ? (P - p0) : Pc;
+            const long long Ntot = pc * Nlo;
+            lt_bgen_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, e + (size_t)p0 * Se, alimb, S, Se, b2, (int)pc, Nlo, Kp,
+                                                                  reinterpret_cast<uint32_t*>(Bq));
+            rc = lt_make_map(&mb, Bq, LT_LIMBS * Ntot, Kp);
+            if (rc) break;
             dim3 grid((unsigned)(2 * Mhi / LT_BM), (unsigned)(Ntot / LT_BN));
             lt_gemm_kernel<<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Ntot, (int)Mhi, (int)Nlo, inv_scale,
-                                                              reinterpret_cast<float2*>(out));
-            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+                                                              reinterpret_cast<float2*>(out) + (size_t)p0 * Mhi * Nlo);
+            g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
             cudaError_t ce = cudaGetLastError();
             if (ce != cudaSuccess) {
                 qsft_set_error("lattice GEMM launch failed: %s", cudaGetErrorString(ce));

@@ -478,3 +478,17 @@ def test_test_nmse_evaluator():
     ref = np.linalg.norm(y_half - y) ** 2 / np.linalg.norm(y) ** 2
     assert abs(test_nmse(half, idx, y, q, n) - ref) < 1e-6
     assert test_nmse({}, idx, y, q, n) == 1
+
+
+def test_k2_lattice_row_chunking_gives_identical_samples(monkeypatch):
+    """The limb operand is generated per chunk of delay rows when it would exceed the scratch budget."""
+    q, n, b, S, P = 4, 24, 8, 500, 7
+    rng = np.random.default_rng(21)
+    M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
+    ld = utils.padded_ld(n)
+    loc_d = ops.pad_digits(rng.integers(0, q, (S, n)), ld, DEV)
+    a_d = torch.from_numpy(np.exp(1j * rng.uniform(0, 6.28, S)).astype(np.complex64)).to(DEV)
+    whole = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
+    monkeypatch.setenv("QSFT_LATTICE_SCRATCH_GB", "0.002")      # 3 * 256 * 1024 B per row -> 2 rows per chunk
+    chunked = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
+    assert torch.equal(whole, chunked)
