@@ -247,14 +247,26 @@ class PeelProblem:
 
     def distinct(self, n_uniq=None):
         """Host copy of the distinct-k list in the reference's first-seen order:
-        (k (K, n) int8, mean rho (K,) complex128, count (K,) int32)."""
+        (k (K, n) int8, mean rho (K,) complex128, count (K,) int32).  The entries are ordered on the device and come
+        back through pinned buffers with one synchronisation."""
         nu = self.n_uniq if n_uniq is None else n_uniq
-        key = self.uniq_key[:nu].cpu().numpy()
-        order = np.argsort(key, kind="stable")
-        k = self.uniq_k[:nu, :self.n].cpu().numpy()[order]
-        cnt = self.uniq_cnt[:nu].cpu().numpy()[order]
-        mean = self.uniq_sum[:nu].cpu().numpy().astype(np.complex128)[order] / cnt
-        return k, mean, cnt
+        if nu == 0:
+            return np.zeros((0, self.n), dtype=np.int8), np.zeros(0, dtype=np.complex128), np.zeros(0, dtype=np.int32)
+        order = torch.argsort(self.uniq_key[:nu])                       # keys are unique: (round << 48) | (c B + j)
+        k_d = self.uniq_k[:nu].index_select(0, order)[:, :self.n].contiguous()
+        s_d = torch.view_as_real(self.uniq_sum[:nu].index_select(0, order))
+        c_d = self.uniq_cnt[:nu].index_select(0, order)
+        k_h = torch.empty(k_d.shape, dtype=k_d.dtype, pin_memory=True)
+        s_h = torch.empty(s_d.shape, dtype=s_d.dtype, pin_memory=True)
+        c_h = torch.empty(c_d.shape, dtype=c_d.dtype, pin_memory=True)
+        k_h.copy_(k_d, non_blocking=True)
+        s_h.copy_(s_d, non_blocking=True)
+        c_h.copy_(c_d, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        cnt = c_h.numpy().copy()
+        sums = s_h.numpy().astype(np.float64)
+        mean = (sums[:, 0] + 1j * sums[:, 1]) / cnt
+        return k_h.numpy().copy(), mean, cnt
 
     def reduce(self, find_cj, find_k, find_rho, find_id, f_begin, n_finds, round_no):
         with torch.cuda.device(self.device):
