@@ -130,3 +130,21 @@ def test_finds_to_dict_matches_reference_averaging():
     assert keys.tolist() == [kA, kB]
     gw0, keys0 = QSFT._finds_to_dict(np.zeros(0, np.int64), np.zeros((0, 3), np.int8), np.zeros(0, np.complex64), np.zeros(0, np.int32))
     assert gw0 == {} and len(keys0) == 0
+
+
+def test_ctypes_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors (PeelDesc, Uniq) must have the C layout of include/qsft_b200.h (checked with gcc)."""
+    import ctypes
+    import subprocess
+    from qsft_b200 import _lib
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "qsft_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(qsft_peel_desc), offsetof(qsft_peel_desc, ld),'
+                   ' offsetof(qsft_peel_desc, cutoff), offsetof(qsft_peel_desc, MT), offsetof(qsft_peel_desc, rs_log),'
+                   ' sizeof(qsft_uniq), offsetof(qsft_uniq, max_uniq));return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    P, U = _lib.PeelDesc, _lib.Uniq
+    want = [ctypes.sizeof(P), P.ld.offset, P.cutoff.offset, P.MT.offset, P.rs_log.offset, ctypes.sizeof(U), U.max_uniq.offset]
+    assert got == want
