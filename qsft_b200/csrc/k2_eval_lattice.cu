@@ -2,7 +2,8 @@
 //
 // For the query lattice m = M l + d_p the phase splits as  <k_s, M l + d_p> = <h_s, l> + <k_s, d_p>,  h_s = M^T k_s mod q.
 // With l = (l_hi, l_lo) (b1 + b2 digits) the samples of delay row p are a complex matrix product
-//     X_p[l_hi, l_lo] = sum_s  A[l_hi, s] * Y_p[s, l_lo],   A = i^<h_hi(s), l_hi>,   Y_p = a_s i^(e_ps + <h_lo(s), l_lo>)
+//     X_p[l_hi, l_lo] = sum_s  A_p[l_hi, s] * Y[s, l_lo],   A_p = i^(<h_hi(s), l_hi> + e_ps),   Y = a_s i^<h_lo(s), l_lo>
+// (the delay phase e_ps = <k_s, d_p> rides on the exact operand, so the 3-limb operand Y is shared by all delay rows)
 // with K = S on the tensor cores and NO per-(query, support) epilogue.  A is exact in int8 (entries 0, +-1 after the
 // real embedding [[Re, -Im], [Im, Re]]); Y_p is a rotation (sign / swap, exact) of a_s quantised to three balanced
 // base-128 int8 limbs (21 bits + sign relative to max|a|), accumulated error-free in int32 (UTCIMMA kind::i8) and
@@ -158,90 +159,95 @@ __global__ void lt_quant_kernel(const float2* __restrict__ a, long long S, const
     alimb[s] = make_int2((int)w0, (int)w1);
 }
 
-// A'[2 l_hi + part][2 s + comp]:  part 0 (Re row): (er, -ei),  part 1 (Im row): (ei, er),  (er, ei) = i^<h_hi(s), l_hi>
-__global__ void lt_agen_kernel(const uint32_t* __restrict__ hhi, long long S, int b1, long long Kp,
-                               uint32_t* __restrict__ A) {
+// A'[(p * Mhi + l_hi) * 2 + part][2 s + comp]:  part 0 (Re row): (er, -ei),  part 1 (Im row): (ei, er),
+// (er, ei) = i^(<h_hi(s), l_hi> + e[p][s]).  One thread owns two support elements of one l_hi and walks over the
+// delay rows; the four possible byte pairs of a row are packed in a 64-bit constant and picked by a shift.
+__global__ void __launch_bounds__(256)
+lt_agen_kernel(const uint32_t* __restrict__ hhi, const uint8_t* __restrict__ e, long long S, long long Se, int b1, int P,
+               long long Mhi, long long Kp, uint32_t* __restrict__ A) {
     const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // two support elements = 4 K' bytes
     const uint32_t lhi = blockIdx.y;
     if (pair * 4 >= Kp) return;
-    uint32_t wre = 0, wim = 0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const long long s = 2 * pair + h;
-        if (s < S) {
-            const uint32_t t = dot4(hhi[s], lhi, b1);
-            const int er = (t == 0) - (t == 2), ei = (t == 1) - (t == 3);
-            wre |= ((uint32_t)(er & 0xff) | ((uint32_t)((-ei) & 0xff) << 8)) << (16 * h);
-            wim |= ((uint32_t)(ei & 0xff) | ((uint32_t)(er & 0xff) << 8)) << (16 * h);
+    const long long s0 = 2 * pair;
+    const bool live0 = s0 < S, live1 = s0 + 1 < S;
+    const uint32_t t0 = live0 ? dot4(hhi[s0], lhi, b1) : 0u;
+    const uint32_t t1 = live1 ? dot4(hhi[s0 + 1], lhi, b1) : 0u;
+    // byte pairs (lo byte first) for rotation r = 0..3:  Re row (er, -ei) = 01 00 | 00 FF | FF 00 | 00 01
+    //                                                    Im row (ei,  er) = 00 01 | 01 00 | 00 FF | FF 00
+    constexpr unsigned long long kRe = 0x010000FFFF000001ull, kIm = 0x00FFFF0000010100ull;
+    const size_t row_words = (size_t)Kp / 4;
+    uint32_t* out = A + ((size_t)(2 * lhi)) * row_words + pair;
+    const uint8_t* ep = e + s0;
+    for (int p = 0; p < P; ++p) {
+        uint32_t wre = 0, wim = 0;
+        if (live0) {
+            uint32_t r0 = t0, r1 = t1;
+            if (live1) {
+                const uint32_t ee = *reinterpret_cast<const uint16_t*>(ep + (size_t)p * Se);
+                r0 += ee & 0xffu;
+                r1 += ee >> 8;
+            } else {
+                r0 += ep[(size_t)p * Se];
+            }
+            r0 &= 3u;
+            r1 &= 3u;
+            wre = (uint32_t)(kRe >> (16 * r0)) & 0xffffu;
+            wim = (uint32_t)(kIm >> (16 * r0)) & 0xffffu;
+            if (live1) {
+                wre |= ((uint32_t)(kRe >> (16 * r1)) & 0xffffu) << 16;
+                wim |= ((uint32_t)(kIm >> (16 * r1)) & 0xffffu) << 16;
+            }
         }
+        uint32_t* o = out + (size_t)p * (size_t)(2 * Mhi) * row_words;
+        o[0] = wre;
+        o[row_words] = wim;
     }
-    A[((size_t)(2 * lhi) * Kp) / 4 + pair] = wre;
-    A[((size_t)(2 * lhi + 1) * Kp) / 4 + pair] = wim;
 }
 
-// B'_l[p * Nlo + l_lo][2 s + comp] = limb l of (Re, Im) of a_s * i^(e[p][s] + <h_lo(s), l_lo>)
-// One thread owns two consecutive support elements (4 K' bytes: x0 y0 x1 y1 per limb) of one l_lo and walks over the
-// delay rows.  A rotation by i^r is a byte swap of the (x, y) pair (PRMT) followed by a per-byte conditional negate
-// ((w ^ m) - m with SIMD-in-word subtract): ~2 instructions per generated byte, so the kernel is HBM-write bound.
+// B'_l[l_lo][2 s + comp] = limb l of (Re, Im) of a_s * i^<h_lo(s), l_lo>  (shared by all delay rows).
+// A rotation by i^r is a byte swap of the (x, y) pair (PRMT) followed by a per-byte conditional negate
+// ((w ^ m) - m with SIMD-in-word subtract).
 __global__ void __launch_bounds__(256)
-lt_bgen_kernel(const uint32_t* __restrict__ hlo, const uint8_t* __restrict__ e, const int2* __restrict__ alimb,
-               long long S, long long Se, int b2, int P, long long Nlo, long long Kp, uint32_t* __restrict__ Bq) {
+lt_bgen_kernel(const uint32_t* __restrict__ hlo, const int2* __restrict__ alimb, long long S, int b2, long long Nlo,
+               long long Kp, uint32_t* __restrict__ Bq) {
     const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t llo = blockIdx.y;
     if (pair * 4 >= Kp) return;
     const long long s0 = 2 * pair;
     const bool live0 = s0 < S, live1 = s0 + 1 < S;
-    // limb words [x0, y0, x1, y1] and the lattice part of the rotation
     uint32_t base[3] = {0, 0, 0};
-    uint32_t t0 = 0, t1 = 0;
+    uint32_t r0 = 0, r1 = 0;
     if (live0) {
         const int2 w = alimb[s0];
-        t0 = dot4(hlo[s0], llo, b2);
+        r0 = dot4(hlo[s0], llo, b2);
 #pragma unroll
         for (int l = 0; l < 3; ++l)
             base[l] |= (((uint32_t)w.x >> (8 * l)) & 0xffu) | ((((uint32_t)w.y >> (8 * l)) & 0xffu) << 8);
     }
     if (live1) {
         const int2 w = alimb[s0 + 1];
-        t1 = dot4(hlo[s0 + 1], llo, b2);
+        r1 = dot4(hlo[s0 + 1], llo, b2);
 #pragma unroll
         for (int l = 0; l < 3; ++l)
             base[l] |= ((((uint32_t)w.x >> (8 * l)) & 0xffu) << 16) | ((((uint32_t)w.y >> (8 * l)) & 0xffu) << 24);
     }
-    const size_t Ntot = (size_t)P * Nlo;
+    // rotation r: swap (x, y) iff r & 1; negate byte 0 iff (r & 1) ^ (r >> 1); negate byte 1 iff r >> 1
+    const uint32_t b0 = r0 & 1u, h0 = r0 >> 1, b1 = r1 & 1u, h1 = r1 >> 1;
+    const uint32_t sel = (b0 ? 0x01u : 0x10u) | ((b1 ? 0x23u : 0x32u) << 8);
+    const uint32_t m = ((0u - (b0 ^ h0)) & 0x000000ffu) | ((0u - h0) & 0x0000ff00u) |
+                       ((0u - (b1 ^ h1)) & 0x00ff0000u) | ((0u - h1) & 0xff000000u);
     const size_t row_words = (size_t)Kp / 4;
-    uint32_t* out0 = Bq + ((size_t)llo) * row_words + pair;
-    const uint8_t* ep = e + s0;
-    for (int p = 0; p < P; ++p) {
-        // e[p][s0], e[p][s0 + 1] (s0 is even: one aligned 16-bit load when both are live)
-        uint32_t r0 = t0, r1 = t1;
-        if (live1) {
-            const uint32_t ee = *reinterpret_cast<const uint16_t*>(ep + (size_t)p * Se);
-            r0 += ee & 0xffu;
-            r1 += ee >> 8;
-        } else if (live0) {
-            r0 += ep[(size_t)p * Se];
-        }
-        r0 &= 3u;
-        r1 &= 3u;
-        // rotation r: swap (x, y) iff r & 1; negate byte 0 iff (r & 1) ^ (r >> 1); negate byte 1 iff r >> 1
-        const uint32_t b0 = r0 & 1u, h0 = r0 >> 1, b1 = r1 & 1u, h1 = r1 >> 1;
-        const uint32_t sel = (b0 ? 0x01u : 0x10u) | ((b1 ? 0x23u : 0x32u) << 8);
-        const uint32_t m = ((0u - (b0 ^ h0)) & 0x000000ffu) | ((0u - h0) & 0x0000ff00u) |
-                           ((0u - (b1 ^ h1)) & 0x00ff0000u) | ((0u - h1) & 0xff000000u);
-        uint32_t* o = out0 + (size_t)p * Nlo * row_words;
 #pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            const uint32_t sw = __byte_perm(base[l], 0u, sel);
-            o[(size_t)l * Ntot * row_words] = __vsub4(sw ^ m, m);
-        }
+    for (int l = 0; l < 3; ++l) {
+        const uint32_t sw = __byte_perm(base[l], 0u, sel);
+        Bq[((size_t)l * Nlo + llo) * row_words + pair] = __vsub4(sw ^ m, m);
     }
 }
 
 // ---- the GEMM ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LT_THREADS, 1)
-lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int nkb, int Ntot,
-               int Mhi, int Nlo, const float* __restrict__ inv_scale_ptr, float2* __restrict__ out) {
+lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int nkb, int Mhi, int Nlo,
+               const float* __restrict__ inv_scale_ptr, float2* __restrict__ out) {
     extern __shared__ uint8_t lt_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)lt_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)LT_STAGES * LT_STAGE_BYTES);
@@ -251,7 +257,9 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mtile = blockIdx.x, ntile = blockIdx.y;
+    // n-tiles fastest: the CTAs sharing one A' m-tile (one delay row, 64 l_hi) are neighbours, so its slabs are fetched
+    // from DRAM once; the small limb operand B' (3 * Nlo rows) is shared by every CTA and lives in L2
+    const int ntile = blockIdx.x, mtile = blockIdx.y;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < LT_STAGES; ++i) {
@@ -283,7 +291,7 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 lt_tma_2d(st, &tmA, kb * LT_BK, mtile * LT_BM, &full[stage]);
 #pragma unroll
                 for (int l = 0; l < LT_LIMBS; ++l)
-                    lt_tma_2d(st + LT_BM * LT_BK + l * (LT_BN * LT_BK), &tmB, kb * LT_BK, l * Ntot + ntile * LT_BN, &full[stage]);
+                    lt_tma_2d(st + LT_BM * LT_BK + l * (LT_BN * LT_BK), &tmB, kb * LT_BK, l * Nlo + ntile * LT_BN, &full[stage]);
             }
         }
     } else if (warp == 1) {
@@ -313,11 +321,11 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // epilogue: row r = 2 * l_hi_local + part lives in TMEM lane r; neighbouring lanes hold (Re, Im) of one l_hi
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        const int lhi = (mtile * LT_BM + row) >> 1;
+        const long long grow = (long long)mtile * LT_BM + row;          // (p * Mhi + l_hi) * 2 + part
+        const int p = (int)(grow / (2 * Mhi));
+        const int lhi = (int)(grow - (long long)p * 2 * Mhi) >> 1;
         const bool odd = lane & 1;
-        const int tiles_per_p = Nlo / LT_BN;
-        const int p = ntile / tiles_per_p;
-        const int llo0 = (ntile - p * tiles_per_p) * LT_BN;
+        const int llo0 = ntile * LT_BN;
         const double inv_scale = (double)(*inv_scale_ptr);
         lt_mbar_wait(tfull, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -393,7 +401,7 @@ extern "C" int qsft_eval_lattice_supported(int q, int n, int b, int P, int64_t S
     if (q != 4 || n < 1 || n > QSFT_MAX_N || P < 1 || S < 1) return 0;
     const int b1 = b / 2, b2 = b - b1;
     if (b1 < 3 || b2 < 4 || b > 14) return 0;                // 2 * 4^b1 >= 128 rows, 4^b2 >= 256 columns, grid.y limits
-    if ((long long)P * ipow64(4, b2) * 3 >= 0x7fffffffLL) return 0;
+    if ((long long)P * ipow64(4, b1) * 2 >= 0x7fffffffLL) return 0;
     return 1;
 }
 
@@ -406,17 +414,18 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     const int b1 = b / 2, b2 = b - b1;
     const long long Mhi = ipow64(4, b1), Nlo = ipow64(4, b2);
     const long long Kp = (2 * S + LT_BK - 1) / LT_BK * LT_BK;
-    // The limb operand B' takes 3 * Nlo * Kp bytes per delay row: process the rows in chunks that keep it under a
-    // scratch budget (default 32 GB, QSFT_LATTICE_SCRATCH_GB overrides); A' is generated once and reused.
+    // The exact operand A' takes 2 * Mhi * Kp bytes per delay row: process the rows in chunks that keep it under a
+    // scratch budget (default 32 GB, QSFT_LATTICE_SCRATCH_GB overrides); the limb operand B' is generated once.
     double budget_gb = 32.0;
     if (const char* env = getenv("QSFT_LATTICE_SCRATCH_GB")) {
         const double v = atof(env);
         if (v > 0.0) budget_gb = v;
     }
-    const double per_row = (double)LT_LIMBS * (double)Nlo * (double)Kp;
+    const double per_row = 2.0 * (double)Mhi * (double)Kp;
     long long Pc = (long long)(budget_gb * 1e9 / per_row);
     if (Pc < 1) Pc = 1;
     if (Pc > P) Pc = P;
+    while (Pc * 2 * Mhi / LT_BM > 65535) --Pc;          // grid.y limit
     // stream-ordered workspace
     uint32_t *hhi = nullptr, *hlo = nullptr;
     uint8_t* e = nullptr;
@@ -437,8 +446,8 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     alloc((void**)&e, (size_t)P * Se);
     alloc((void**)&alimb, (size_t)S * 8);
     alloc((void**)&amax, 8);
-    alloc((void**)&A, (size_t)2 * Mhi * Kp);
-    alloc((void**)&Bq, (size_t)LT_LIMBS * Pc * Nlo * Kp);
+    alloc((void**)&A, (size_t)Pc * 2 * Mhi * Kp);
+    alloc((void**)&Bq, (size_t)LT_LIMBS * Nlo * Kp);
     inv_scale = amax ? reinterpret_cast<float*>(amax + 1) : nullptr;
     if (rc == QSFT_OK) {
         const int T = 256;
@@ -448,10 +457,10 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
         lt_amax_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax);
         lt_quant_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax, inv_scale, alimb);
         const unsigned pb = (unsigned)((Kp / 4 + T - 1) / T);
-        lt_agen_kernel<<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, S, b1, Kp, reinterpret_cast<uint32_t*>(A));
+        lt_bgen_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp, reinterpret_cast<uint32_t*>(Bq));
         g_qsft_launches.fetch_add(4, std::memory_order_relaxed);
         CUtensorMap ma, mb;
-        rc = lt_make_map(&ma, A, 2 * Mhi, Kp);
+        rc = lt_make_map(&mb, Bq, LT_LIMBS * Nlo, Kp);
         if (!rc) {
             static bool attr = false;
             if (!attr) {
@@ -464,13 +473,12 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
         }
         for (long long p0 = 0; p0 < P && !rc; p0 += Pc) {
             const long long pc = (P - p0 < Pc) ? (P - p0) : Pc;
-            const long long Ntot = pc * Nlo;
-            lt_bgen_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, e + (size_t)p0 * Se, alimb, S, Se, b2, (int)pc, Nlo, Kp,
-                                                                  reinterpret_cast<uint32_t*>(Bq));
-            rc = lt_make_map(&mb, Bq, LT_LIMBS * Ntot, Kp);
+            lt_agen_kernel<<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, e + (size_t)p0 * Se, S, Se, b1, (int)pc, Mhi, Kp,
+                                                                  reinterpret_cast<uint32_t*>(A));
+            rc = lt_make_map(&ma, A, pc * 2 * Mhi, Kp);
             if (rc) break;
-            dim3 grid((unsigned)(2 * Mhi / LT_BM), (unsigned)(Ntot / LT_BN));
-            lt_gemm_kernel<<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Ntot, (int)Mhi, (int)Nlo, inv_scale,
+            dim3 grid((unsigned)(Nlo / LT_BN), (unsigned)(pc * 2 * Mhi / LT_BM));
+            lt_gemm_kernel<<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo, inv_scale,
                                                               reinterpret_cast<float2*>(out) + (size_t)p0 * Mhi * Nlo);
             g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
             cudaError_t ce = cudaGetLastError();
