@@ -240,12 +240,17 @@ def run_ours(a):
     _lib.reset_launch_count()
     ops.TIMERS.reset(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_marks = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
     ev0.record()
+    step_marks[0].record()
     for s in range(a.warmup, total_steps):
         out, sft = transform(build_signal(inputs[s], resident[s]), "device")
+        step_marks[s - a.warmup + 1].record()
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+    per_step = [step_marks[i].elapsed_time(step_marks[i + 1]) for i in range(a.steps)]
+    log("per-step device ms: " + " ".join(f"{v:.1f}" for v in per_step))
     launches = _lib.launch_count()
     kt = ops.TIMERS.totals()
     ops.TIMERS.reset(False)

@@ -56,6 +56,22 @@ class _timed:
         return False
 
 
+_PINNED = {}
+
+
+def _pinned(tag, shape, dtype):
+    """Reusable page-locked staging buffer (cudaHostAlloc synchronises the device and costs milliseconds, so buffers are
+    kept for the life of the process and only grow)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    buf = _PINNED.get((tag, dtype))
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
+        _PINNED[(tag, dtype)] = buf
+    return buf[:n].view(shape)
+
+
 def _ptr(t):
     return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
 
@@ -256,9 +272,9 @@ class PeelProblem:
         k_d = self.uniq_k[:nu].index_select(0, order)[:, :self.n].contiguous()
         s_d = torch.view_as_real(self.uniq_sum[:nu].index_select(0, order))
         c_d = self.uniq_cnt[:nu].index_select(0, order)
-        k_h = torch.empty(k_d.shape, dtype=k_d.dtype, pin_memory=True)
-        s_h = torch.empty(s_d.shape, dtype=s_d.dtype, pin_memory=True)
-        c_h = torch.empty(c_d.shape, dtype=c_d.dtype, pin_memory=True)
+        k_h = _pinned("distinct_k", k_d.shape, k_d.dtype)
+        s_h = _pinned("distinct_sum", s_d.shape, s_d.dtype)
+        c_h = _pinned("distinct_cnt", c_d.shape, c_d.dtype)
         k_h.copy_(k_d, non_blocking=True)
         s_h.copy_(s_d, non_blocking=True)
         c_h.copy_(c_d, non_blocking=True)
