@@ -27,15 +27,21 @@ class DistContext:
 
     def all_gather_var(self, tensors, count, cap, extra=0):
         """All-gather `count` leading rows of each tensor in `tensors` (fixed capacity `cap` per rank).
-        Returns (list of concatenated tensors, counts per rank); the sum over ranks of the integer `extra` that
-        travelled with the counts is left in self.last_extra_sum (saves a separate all-reduce)."""
+        `count` / `extra` may be Python ints or a 2-element int64 CUDA tensor [count, extra] (then no host sync is needed
+        before the exchange).  Returns (list of concatenated tensors, counts per rank); the sum over ranks of `extra`
+        is left in self.last_extra_sum (saves a separate all-reduce)."""
         dev = tensors[0].device
-        cnt = torch.tensor([count, int(extra)], dtype=torch.int64, device=dev)
+        if isinstance(count, torch.Tensor):
+            cnt = count.to(torch.int64).contiguous()
+        else:
+            cnt = torch.tensor([int(count), int(extra)], dtype=torch.int64, device=dev)
         allc = torch.empty(2 * self.world_size, dtype=torch.int64, device=dev)
         td.all_gather_into_tensor(allc, cnt, group=self.group)
-        allc = allc.cpu().view(self.world_size, 2)
+        allc = allc.cpu().view(self.world_size, 2)          # the round's only host synchronisation
         counts = allc[:, 0].tolist()
         self.last_extra_sum = int(allc[:, 1].sum().item())
+        if max(counts) > cap:
+            raise RuntimeError("find buffer overflow in sharded peel")
         m = max(counts)
         outs = []
         for t in tensors:
@@ -85,12 +91,8 @@ def peel_sharded(prob, U, dist, max_rounds=15, to_host=False):
         rnd += 1
         prob.counters[:4].zero_()
         prob.classify(U, jb, je, rnd)
-        cnts = prob.counters.cpu().tolist()               # the round's only host sync (find count + multiton count)
-        nf_local, multi_local = int(cnts[0]), int(cnts[1])
-        if nf_local > cap:
-            raise RuntimeError("find buffer overflow in sharded peel")
-        (cj, k, rho), counts = dist.all_gather_var([prob.find_cj, prob.find_k, prob.find_rho], nf_local, cap,
-                                                   extra=multi_local)
+        # counters[0:2] = (finds, multitons) of this rank travel with the exchange: one host sync per round
+        (cj, k, rho), counts = dist.all_gather_var([prob.find_cj, prob.find_k, prob.find_rho], prob.counters[:2], cap)
         n_multi = dist.last_extra_sum
         nf = int(sum(counts))
         if n_multi == 0 or nf == 0:

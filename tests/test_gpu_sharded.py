@@ -33,6 +33,8 @@ class ThreadDist:
 
     def all_gather_var(self, tensors, count, cap, extra=0):
         torch.cuda.synchronize()
+        if isinstance(count, torch.Tensor):
+            count, extra = (int(v) for v in count.cpu().tolist())
         parts = self._exchange(([t[:count].clone() for t in tensors], count, int(extra)))
         counts = [p[1] for p in parts]
         self.last_extra_sum = sum(p[2] for p in parts)
