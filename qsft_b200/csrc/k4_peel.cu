@@ -15,8 +15,10 @@ constexpr double kTwoPi = 6.283185307179586476925286766559;
 
 struct PeelDev {
     int q, n, b, C, P, P_src, R, channel, source, rs_t, rs_s, ld;
+    unsigned int qmagic;      // ceil(2^32 / q): x mod q = x - mulhi(x, qmagic) * q for x < 2^32 / q
     long long B;
     double thresh;            // cutoff * P
+    double invP;              // 1 / P
     const int8_t* MT;         // (C, b, ld)   rows = columns of M, zero padded
     const int8_t* D;          // (C, P, ld)
     const int32_t* rs_exp;
@@ -30,9 +32,9 @@ __device__ __forceinline__ int dp4a_u(uint32_t a, uint32_t b, int c) {
     return d;
 }
 
-// <row, k> mod q; `row` has ld bytes (ld % 16 == 0), kw holds the digits of k four per word (zero padded)
+// <row, k> (not reduced; < 128 * 127^2 < 2^32 / q); `row` has ld bytes (ld % 16 == 0), kw holds the digits of k four per word (zero padded)
 template <int NW>
-__device__ __forceinline__ int dot_mod(const int8_t* row, int ld, const uint32_t (&kw)[NW], int q) {
+__device__ __forceinline__ int dot_raw(const int8_t* row, int ld, const uint32_t (&kw)[NW]) {
     const uint4* r4 = reinterpret_cast<const uint4*>(row);
     const int nv = ld >> 4;
     int acc = 0;
@@ -45,7 +47,11 @@ __device__ __forceinline__ int dot_mod(const int8_t* row, int ld, const uint32_t
         acc = dp4a_u(v.z, kw[4 * w + 2], acc);
         acc = dp4a_u(v.w, kw[4 * w + 3], acc);
     }
-    return acc % q;
+    return acc;
+}
+
+__device__ __forceinline__ int fast_mod(int x, int q, unsigned int qmagic) {   // 0 <= x < 2^32 / q
+    return x - (int)(__umulhi((unsigned int)x, qmagic) * (unsigned int)q);
 }
 
 // bin hash j = dec(M_c^T k mod q), b digits MSB first (qsft.py:178, :227)
@@ -53,7 +59,7 @@ template <int NW>
 __device__ __forceinline__ long long hash_bin(const PeelDev& d, int c, const uint32_t (&kw)[NW]) {
     long long j = 0;
     const int8_t* mt = d.MT + (size_t)c * d.b * d.ld;
-    for (int i = 0; i < d.b; ++i) j = j * d.q + dot_mod<NW>(mt + (size_t)i * d.ld, d.ld, kw, d.q);
+    for (int i = 0; i < d.b; ++i) j = j * d.q + fast_mod(dot_raw<NW>(mt + (size_t)i * d.ld, d.ld, kw), d.q, d.qmagic);
     return j;
 }
 
@@ -269,8 +275,9 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
                         const float u = (float)d.q * (atan2f(v.y, v.x) - atan2f(v0.y, v0.x)) * 0.15915494309189535f;
                         const float m = rintf(u);
                         if (fabsf(u - m) < 0.49f) {
-                            const int mi = (int)m % d.q;
-                            symv = mi < 0 ? mi + d.q : mi;
+                            int mi = (int)m;                    // |u| < q  =>  m in [-q, q]
+                            mi = mi < 0 ? mi + d.q : mi;
+                            symv = mi >= d.q ? mi - d.q : mi;
                         }
                     }
                     if (symv < 0) {
@@ -288,8 +295,7 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
                         ar += (double)z.x * v.x + (double)z.y * v.y;                     // z * conj(v)
                         ai += (double)z.y * v.x - (double)z.x * v.y;
                     }
-                    ar /= d.R;
-                    ai /= d.R;
+                    // np.mean divides by R > 0: the angle does not depend on it
                     symv = -1;
                     const float arf = (float)ar, aif = (float)ai;
                     if (fabsf(arf) + fabsf(aif) > 1e-30f) {
@@ -297,7 +303,7 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
                         if (thf < 0.f) thf += 6.283185307179586f;
                         const float u = thf * (float)d.q * 0.15915494309189535f;        // in [0, q]
                         const float m = rintf(u);
-                        if (fabsf(u - m) < 0.49f) symv = (int)m % d.q;                   // nearest of the q+1 roots, mod q
+                        if (fabsf(u - m) < 0.49f) symv = ((int)m >= d.q) ? (int)m - d.q : (int)m;   // nearest of the q+1 roots, mod q
                     }
                     if (symv < 0) {
                         double th = atan2(ai, ar);
@@ -335,14 +341,14 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
         // rho = <signature, col> / P with signature_p = w^(D_p . k)  (qsft.py:174-175), lanes over delay rows
         double rr = 0.0, ri = 0.0;
         for (int p = lane; p < d.P; p += 32) {
-            const int t = dot_mod<NW>(Dc + (size_t)p * d.ld, d.ld, kw, d.q);
+            const int t = fast_mod(dot_raw<NW>(Dc + (size_t)p * d.ld, d.ld, kw), d.q, d.qmagic);
             const double cs = s_tw[t].x, sn = s_tw[t].y;
             const float2 v = col[(size_t)p * B];
             rr += cs * v.x + sn * v.y;                                                   // conj(sig) * v
             ri += cs * v.y - sn * v.x;
         }
-        rr = warp_sum(rr) / d.P;
-        ri = warp_sum(ri) / d.P;
+        rr = warp_sum(rr) * d.invP;
+        ri = warp_sum(ri) * d.invP;
         // ||col - rho sig||^2 = ||col||^2 - P |rho|^2 exactly (rho is the projection, |sig_p| = 1); fp64 keeps it accurate
         const double res = e_b - (double)d.P * (rr * rr + ri * ri);
         // bin hash j = dec(M_c^T k mod q) (qsft.py:178-179), one hash digit per lane
@@ -350,7 +356,7 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
         if (lane < d.b) {
             long long wgt = 1;
             for (int u = lane + 1; u < d.b; ++u) wgt *= d.q;
-            part = wgt * dot_mod<NW>(d.MT + ((size_t)c * d.b + lane) * d.ld, d.ld, kw, d.q);
+            part = wgt * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + lane) * d.ld, d.ld, kw), d.q, d.qmagic);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -417,16 +423,16 @@ k4_apply_kernel(PeelDev d, float2* __restrict__ U, long long j_begin, long long 
     }
     if (owner_count && lane == 0) atomicAdd(owner_count, 1ull);   // distinct balls peeled (num_peeling, qsft.py:224)
     const float2 rho = find_rho[f];
-    const double qd = (double)d.q;
+    const float inv_q = 1.0f / (float)d.q;
     for (int l = 0; l < d.C; ++l) {
         const long long j = hash_bin<NW>(d, l, kw);
         if (j < j_begin || j >= j_end) continue;
         float2* Ul = U + (size_t)l * d.P * d.B + j;
         const int8_t* Dl = d.D + (size_t)l * d.P * d.ld;
         for (int p = lane; p < d.P; p += 32) {
-            const int t = dot_mod<NW>(Dl + (size_t)p * d.ld, d.ld, kw, d.q);
+            const int t = fast_mod(dot_raw<NW>(Dl + (size_t)p * d.ld, d.ld, kw), d.q, d.qmagic);
             float sn, cs;
-            sincospif(2.0f * (float)t / (float)qd, &sn, &cs);
+            sincospif(2.0f * (float)t * inv_q, &sn, &cs);
             // rho * w^t
             const float vr = rho.x * cs - rho.y * sn;
             const float vi = rho.x * sn + rho.y * cs;
@@ -567,6 +573,8 @@ int make_dev(const qsft_peel_desc* h, PeelDev* d) {
     d->channel = h->channel; d->source = h->source; d->rs_t = h->rs_t; d->rs_s = h->rs_s; d->ld = h->ld;
     d->B = ipow64(h->q, h->b);
     d->thresh = (double)h->cutoff * (double)h->P;
+    d->invP = 1.0 / (double)h->P;
+    d->qmagic = (unsigned int)(((1ull << 32) + h->q - 1) / h->q);
     d->MT = h->MT; d->D = h->D; d->rs_exp = h->rs_exp; d->rs_log = h->rs_log;
     d->rs_order = h->source ? (int)ipow64(h->q, h->rs_s) : 0;
     return QSFT_OK;
