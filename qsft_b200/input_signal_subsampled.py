@@ -101,7 +101,9 @@ class SubsampledSignal(Signal):
         rows_alloc = per * world
         dev = self.device
         # one HBM buffer per b: rows = flattened (c, r, p), padded to a multiple of the world size
-        self._Ubuf = {bb: torch.zeros((rows_alloc, self.q ** bb), dtype=torch.complex64, device=dev) for bb in self.all_bs}
+        self._Ubuf = {bb: torch.empty((rows_alloc, self.q ** bb), dtype=torch.complex64, device=dev) for bb in self.all_bs}
+        for bb in self.all_bs:
+            self._Ubuf[bb][G:].zero_()          # padding rows (multi-GPU row blocks of equal size)
         self.Us = [[{} for _ in range(R)] for _ in range(C)]
         self.transformTimes = [[{} for _ in range(R)] for _ in range(C)]
         events = []
@@ -126,16 +128,25 @@ class SubsampledSignal(Signal):
                         self._Ubuf[bb][g0:g0 + P_src] = torch.from_numpy(np.asarray(Us_ij[bb]).astype(np.complex64)).to(dev)
                         self.transformTimes[i][j][bb] = Ts_ij[bb]
                     continue
+                # with a single b the samples are produced straight into their rows of the U buffer and transformed
+                # in place (no staging copy)
+                inplace = (len(self.all_bs) == 1 and self.all_bs[0] == self.b and not cache)
+                target = self._Ubuf[self.b][g0 + p0:g0 + p1] if inplace else None
                 if cache and sample_file.is_file():
                     samples = torch.from_numpy(np.asarray(load_data(sample_file)).astype(np.complex64)).to(dev)
                 else:
-                    samples = self._sample_rows(self.Ms[i], np.asarray(self.Ds[i][j])[p0:p1])       # (p1-p0, B)
+                    samples = self._sample_rows(self.Ms[i], np.asarray(self.Ds[i][j])[p0:p1], out=target)   # (p1-p0, B)
                     if cache:
                         save_data(samples.cpu().numpy().astype(complex), sample_file)
                 for bb in self.all_bs:
                     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     ev0.record()
-                    self._Ubuf[bb][g0 + p0:g0 + p1] = self._compute_subtransform(samples, bb)
+                    if inplace:
+                        if samples.data_ptr() != target.data_ptr():
+                            target.copy_(samples)
+                        ops.gwht_batch_(target, self.q, bb)
+                    else:
+                        self._Ubuf[bb][g0 + p0:g0 + p1] = self._compute_subtransform(samples, bb)
                     ev1.record()
                     events.append((i, j, bb, ev0, ev1))
                 del samples
@@ -162,12 +173,13 @@ class SubsampledSignal(Signal):
                            dict(self.transformTimes[i][j])), Path(f"{self.foldername}/transforms/U{i}_{j}.pickle"))
         self.sample_time = time.time() - t_sample0 - fft_total
 
-    def _sample_rows(self, M, D_rows):
-        """Samples of the lattices {M l + d_p} for the given delay rows -> complex64 tensor (rows, B)."""
+    def _sample_rows(self, M, D_rows, out=None):
+        """Samples of the lattices {M l + d_p} for the given delay rows -> complex64 tensor (rows, B); `out`, when
+        given, is a contiguous (rows, B) complex64 CUDA tensor the device samplers may write into directly."""
         B = self.q ** self.b
         rows = D_rows.shape[0]
         if self.device_subsample:
-            fused = self.subsample_lattice_device(M, D_rows)
+            fused = self.subsample_lattice_device(M, D_rows, out=out)
             if fused is not None:
                 return fused
             idx, dig = ops.query_lattice(M, D_rows, self.q, device=self.device, want_idx=False, want_digits=True,
@@ -184,7 +196,7 @@ class SubsampledSignal(Signal):
             out[:] = flat.reshape(rows, B)
         return torch.from_numpy(out.astype(np.complex64)).to(self.device)
 
-    def subsample_lattice_device(self, M, D_rows):
+    def subsample_lattice_device(self, M, D_rows, out=None):
         """Optional fused lattice sampler: samples (rows, B) of {M l + d_p}, or None to use K1 + subsample_device."""
         return None
 

@@ -76,7 +76,7 @@ class SyntheticSubsampledSignal(SubsampledSignal):
         """digits (N, ld) int8 on the device -> complex64 samples (N,)."""
         return ops.eval_synth(digits, self._loc_dev, self._a_dev, self.q, self.n, impl=min(self.eval_impl, 2))
 
-    def subsample_lattice_device(self, M, D_rows):
+    def subsample_lattice_device(self, M, D_rows, out=None):
         """Lattice-factorised evaluation (K = S tensor-core GEMM) when the shape supports it; eval_impl: 0 = auto,
         1 = SIMT, 2 = plain tcgen05 (arbitrary queries), 3 = lattice (raises if unsupported)."""
         P, S = D_rows.shape[0], self._loc_dev.shape[0]
@@ -84,7 +84,7 @@ class SyntheticSubsampledSignal(SubsampledSignal):
         if self.eval_impl == 3 and not ok:
             raise ValueError("eval_impl=3 (lattice) supports q = 4 and 7 <= b <= 14 only")
         if ok and (self.eval_impl == 3 or (self.eval_impl == 0 and S >= 512)):
-            return ops.eval_synth_lattice(M, D_rows, self._loc_dev, self._a_dev, self.q)
+            return ops.eval_synth_lattice(M, D_rows, self._loc_dev, self._a_dev, self.q, out=out)
         return None
 
     def subsample(self, query_indices):
