@@ -69,4 +69,8 @@ static inline bool index_fits(int q, int n, int limbs) {
 __host__ __device__ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 int qsft_num_sms();
+// K2 variants (k2_eval_simt.cu / k2_eval_tc.cu), dispatched by qsft_eval_synth
+int qsft_eval_synth_tc(const int8_t* qdig, int64_t N, const int8_t* loc, const float* strengths, int64_t S, int q, int n,
+                       int ld, float* out, void* stream);
+bool qsft_eval_synth_tc_supported(int64_t N, int64_t S, int q, int n, int ld);
 cudaError_t qsft_scratch_alloc(void** p, size_t bytes, cudaStream_t st);

@@ -137,10 +137,6 @@ int qsft_eval_synth_simt(const int8_t* qdig, int64_t N, const int8_t* loc, const
     return QSFT_EINVAL;
 }
 
-int qsft_eval_synth_tc(const int8_t* qdig, int64_t N, const int8_t* loc, const float* strengths, int64_t S, int q,
-                       int n, int ld, float* out, void* stream);
-bool qsft_eval_synth_tc_supported(int64_t N, int64_t S, int q, int n, int ld);
-
 extern "C" int qsft_eval_synth(const int8_t* qdig, int64_t N, const int8_t* loc, const float* strengths, int64_t S,
                                int q, int n, int ld, float* out, int impl, void* stream) {
     QSFT_CHECK_ARG(q >= 2 && q <= QSFT_MAX_Q, "q=%d out of range", q);

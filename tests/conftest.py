@@ -14,6 +14,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the shared library is a build artefact (git-ignored): build it once if a fresh checkout lacks it
+    lib = os.path.join(ROOT, "qsft_b200", "libqsft_b200.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "qsft_b200", "csrc"), "-j8"], check=False,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def load_golden(name):
