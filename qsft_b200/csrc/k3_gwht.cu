@@ -189,16 +189,13 @@ k3_pass_kernel(float2* __restrict__ x, long long B, int q, int r, long long qa, 
 // (16 lanes x 8 bytes) bank-conflict free for all digit positions.
 __device__ __forceinline__ int k3_swz(int e) { return e ^ ((e >> 4) & 15); }
 
-// radix-4 butterfly (forward, w = -i) on packed fp32x2 (FADD2 / FFMA2): 8 instructions instead of 16
 __device__ __forceinline__ void k3_r4(float2& a, float2& b, float2& c, float2& d) {
-    const float2 m1 = make_float2(-1.f, -1.f);
-    const float2 s02 = __fadd2_rn(a, c), d02 = __ffma2_rn(c, m1, a);
-    const float2 s13 = __fadd2_rn(b, d), d13 = __ffma2_rn(d, m1, b);
-    const float2 sw = make_float2(d13.y, d13.x);                         // (Im, Re) of d13
-    a = __fadd2_rn(s02, s13);
-    c = __ffma2_rn(s13, m1, s02);
-    b = __ffma2_rn(sw, make_float2(1.f, -1.f), d02);                     // d02 - i d13
-    d = __ffma2_rn(sw, make_float2(-1.f, 1.f), d02);                     // d02 + i d13
+    const float2 s02 = make_float2(a.x + c.x, a.y + c.y), d02 = make_float2(a.x - c.x, a.y - c.y);
+    const float2 s13 = make_float2(b.x + d.x, b.y + d.y), d13 = make_float2(b.x - d.x, b.y - d.y);
+    a = make_float2(s02.x + s13.x, s02.y + s13.y);
+    c = make_float2(s02.x - s13.x, s02.y - s13.y);
+    b = make_float2(d02.x + d13.y, d02.y - d13.x);   // d02 - i d13
+    d = make_float2(d02.x - d13.y, d02.y + d13.x);   // d02 + i d13
 }
 
 template <bool STRIDED>
