@@ -244,9 +244,64 @@ lt_bgen_kernel(const uint32_t* __restrict__ hlo, const int2* __restrict__ alimb,
     }
 }
 
+// ---- packed phase tables for the in-kernel generation of A' (FUSED_A) -------------------------------------
+// T[l_hi][w]: 16 two-bit fields <h_hi(s), l_hi> mod 4 for s = 16 w .. 16 w + 15;  E2[p][w]: the delay phases e[p][s] packed
+// the same way.  A' is then a pure function of (T + E2) mod 4, generated slab by slab in shared memory by the GEMM CTAs.
+__global__ void __launch_bounds__(256)
+lt_ttab_kernel(const uint32_t* __restrict__ hhi, long long S, int b1, long long Tw, uint32_t* __restrict__ T) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lhi = blockIdx.y;
+    if (w >= Tw) return;
+    uint32_t word = 0;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const long long s = 16 * w + i;
+        if (s < S) word |= dot4(hhi[s], lhi, b1) << (2 * i);
+    }
+    T[(size_t)lhi * Tw + w] = word;
+}
+
+__global__ void __launch_bounds__(256)
+lt_etab_kernel(const uint8_t* __restrict__ e, long long S, long long Se, int P, long long Tw, uint32_t* __restrict__ E2) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.y;
+    if (w >= Tw) return;
+    uint32_t word = 0;
+    for (int i = 0; i < 16; ++i) {
+        const long long s = 16 * w + i;
+        if (s < S) word |= (uint32_t)(e[(size_t)p * Se + s] & 3u) << (2 * i);
+    }
+    E2[(size_t)p * Tw + w] = word;
+}
+
 // ---- the GEMM ---------------------------------------------------------------------------------------------
+// 16 bytes of an A' row pair: eight support elements, t = eight 2-bit phases (bits 0..15 of `t16`)
+//   re chunk = (er, -ei) x 8, im chunk = (ei, er) x 8, (er, ei) = i^t
+__device__ __forceinline__ void lt_a_chunks(uint32_t t16, uint4& re, uint4& im) {
+    uint32_t rw[4], iw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t t = (t16 >> (4 * j + 2 * h)) & 3u;
+            // selector bytes of i^t as (er, -ei, ei, er) picked from the byte table {0x00, 0x01, 0xFF}
+            const uint32_t sel = __byte_perm(0x10022001u, 0x02200110u, t * 0x11u + 0x40u);
+            v[h] = __byte_perm(0x00FF0100u, 0u, sel);
+        }
+        rw[j] = __byte_perm(v[0], v[1], 0x5410u);
+        iw[j] = __byte_perm(v[0], v[1], 0x7632u);
+    }
+    re = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+    im = make_uint4(iw[0], iw[1], iw[2], iw[3]);
+}
+
+// FUSED_A: the exact operand A' is not read from HBM; the four epilogue warps generate each 128 x 128-byte slab in
+// (128B-swizzled) shared memory from the packed phase tables while the tensor core works on the previous slabs.
+template <bool FUSED_A>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int nkb, int Mhi, int Nlo,
+               const uint32_t* __restrict__ Ttab, const uint32_t* __restrict__ Etab, int Tw,
                const float* __restrict__ inv_scale_ptr, float2* __restrict__ out) {
     extern __shared__ uint8_t lt_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)lt_raw + 1023) & ~(uintptr_t)1023);
@@ -263,7 +318,7 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < LT_STAGES; ++i) {
-            lt_mbar_init(&full[i], 1);
+            lt_mbar_init(&full[i], FUSED_A ? 5 : 1);     // TMA thread (+ one elected lane per A-producer warp)
             lt_mbar_init(&empty[i], 1);
         }
         lt_mbar_init(tfull, 1);
@@ -286,9 +341,9 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int stage = kb % LT_STAGES;
                 const uint32_t ph = (uint32_t)(kb / LT_STAGES) & 1u;
                 lt_mbar_wait(&empty[stage], ph ^ 1u);
-                lt_mbar_expect_tx(&full[stage], LT_STAGE_BYTES);
+                lt_mbar_expect_tx(&full[stage], FUSED_A ? (LT_STAGE_BYTES - LT_BM * LT_BK) : LT_STAGE_BYTES);
                 uint8_t* st = base + (size_t)stage * LT_STAGE_BYTES;
-                lt_tma_2d(st, &tmA, kb * LT_BK, mtile * LT_BM, &full[stage]);
+                if (!FUSED_A) lt_tma_2d(st, &tmA, kb * LT_BK, mtile * LT_BM, &full[stage]);
 #pragma unroll
                 for (int l = 0; l < LT_LIMBS; ++l)
                     lt_tma_2d(st + LT_BM * LT_BK + l * (LT_BN * LT_BK), &tmB, kb * LT_BK, l * Nlo + ntile * LT_BN, &full[stage]);
@@ -318,6 +373,47 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             lt_commit(tfull);
         }
     } else {
+        if (FUSED_A) {
+            // A' producer: thread (l = 0..63, half = 0..1) writes 32 support elements (4 x 16-byte chunks) of the row
+            // pair (2l, 2l + 1) of every slab.  t = (T + E2) mod 4 on sixteen 2-bit fields at once (no carries between
+            // fields: add without the top bits, xor them back).
+            const int pe = threadIdx.x - 64;
+            const int l = pe >> 1, half = pe & 1;
+            const long long grow0 = (long long)mtile * LT_BM;                 // first global A' row of this CTA
+            const int pp = (int)(grow0 / (2 * Mhi));
+            const int lhi0 = (int)(grow0 - (long long)pp * 2 * Mhi) >> 1;
+            const uint32_t* trow = Ttab + (size_t)(lhi0 + l) * Tw + 2 * half;
+            const uint32_t* erow = Etab + (size_t)pp * Tw + 2 * half;
+            uint2 tw = *reinterpret_cast<const uint2*>(trow), ew = *reinterpret_cast<const uint2*>(erow);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int stage = kb % LT_STAGES;
+                const uint32_t ph = (uint32_t)(kb / LT_STAGES) & 1u;
+                constexpr uint32_t H = 0xAAAAAAAAu;
+                const uint32_t t0 = ((tw.x & ~H) + (ew.x & ~H)) ^ ((tw.x ^ ew.x) & H);
+                const uint32_t t1 = ((tw.y & ~H) + (ew.y & ~H)) ^ ((tw.y ^ ew.y) & H);
+                if (kb + 1 < nkb) {                                            // prefetch the next slab's phases
+                    tw = *reinterpret_cast<const uint2*>(trow + 4 * (kb + 1));
+                    ew = *reinterpret_cast<const uint2*>(erow + 4 * (kb + 1));
+                }
+                lt_mbar_wait(&empty[stage], ph ^ 1u);
+                uint8_t* sa = base + (size_t)stage * LT_STAGE_BYTES;
+                const int r_re = 2 * l, r_im = 2 * l + 1;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t t16 = (c < 2 ? t0 : t1) >> (16 * (c & 1));
+                    uint4 re, im;
+                    lt_a_chunks(t16, re, im);
+                    const int chunk = half * 4 + c;
+                    *reinterpret_cast<uint4*>(sa + r_re * 128 + ((chunk ^ (r_re & 7)) << 4)) = re;
+                    *reinterpret_cast<uint4*>(sa + r_im * 128 + ((chunk ^ (r_im & 7)) << 4)) = im;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lt_smem_u32(&full[stage])) : "memory");
+                }
+            }
+        }
         // epilogue: row r = 2 * l_hi_local + part lives in TMEM lane r; neighbouring lanes hold (Re, Im) of one l_hi
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
@@ -414,20 +510,24 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     const int b1 = b / 2, b2 = b - b1;
     const long long Mhi = ipow64(4, b1), Nlo = ipow64(4, b2);
     const long long Kp = (2 * S + LT_BK - 1) / LT_BK * LT_BK;
-    // The exact operand A' takes 2 * Mhi * Kp bytes per delay row: process the rows in chunks that keep it under a
-    // scratch budget (default 32 GB, QSFT_LATTICE_SCRATCH_GB overrides); the limb operand B' is generated once.
+    // FUSED_A (default): A' is generated inside the GEMM from packed phase tables (no HBM round trip).  Otherwise it is
+    // materialised: 2 * Mhi * Kp bytes per delay row, rows processed in chunks that keep it under a scratch budget
+    // (default 32 GB, QSFT_LATTICE_SCRATCH_GB overrides).  The limb operand B' is generated once either way.
+    bool fused_a = true;
+    if (const char* env = getenv("QSFT_LATTICE_FUSED_A")) fused_a = atoi(env) != 0;
     double budget_gb = 32.0;
     if (const char* env = getenv("QSFT_LATTICE_SCRATCH_GB")) {
         const double v = atof(env);
         if (v > 0.0) budget_gb = v;
     }
     const double per_row = 2.0 * (double)Mhi * (double)Kp;
-    long long Pc = (long long)(budget_gb * 1e9 / per_row);
+    long long Pc = fused_a ? P : (long long)(budget_gb * 1e9 / per_row);
     if (Pc < 1) Pc = 1;
     if (Pc > P) Pc = P;
     while (Pc * 2 * Mhi / LT_BM > 65535) --Pc;          // grid.y limit
+    const long long Tw = Kp / 32;                       // packed phase words (16 support elements each) per row
     // stream-ordered workspace
-    uint32_t *hhi = nullptr, *hlo = nullptr;
+    uint32_t *hhi = nullptr, *hlo = nullptr, *Ttab = nullptr, *Etab = nullptr;
     uint8_t* e = nullptr;
     int2* alimb = nullptr;
     unsigned int* amax = nullptr;
@@ -446,7 +546,12 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     alloc((void**)&e, (size_t)P * Se);
     alloc((void**)&alimb, (size_t)S * 8);
     alloc((void**)&amax, 8);
-    alloc((void**)&A, (size_t)Pc * 2 * Mhi * Kp);
+    if (fused_a) {
+        alloc((void**)&Ttab, (size_t)Mhi * Tw * 4);
+        alloc((void**)&Etab, (size_t)P * Tw * 4);
+    } else {
+        alloc((void**)&A, (size_t)Pc * 2 * Mhi * Kp);
+    }
     alloc((void**)&Bq, (size_t)LT_LIMBS * Nlo * Kp);
     inv_scale = amax ? reinterpret_cast<float*>(amax + 1) : nullptr;
     if (rc == QSFT_OK) {
@@ -459,12 +564,20 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
         const unsigned pb = (unsigned)((Kp / 4 + T - 1) / T);
         lt_bgen_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp, reinterpret_cast<uint32_t*>(Bq));
         g_qsft_launches.fetch_add(4, std::memory_order_relaxed);
+        if (fused_a) {
+            const unsigned wb = (unsigned)((Tw + T - 1) / T);
+            lt_ttab_kernel<<<dim3(wb, (unsigned)Mhi), T, 0, st>>>(hhi, S, b1, Tw, Ttab);
+            lt_etab_kernel<<<dim3(wb, (unsigned)P), T, 0, st>>>(e, S, Se, P, Tw, Etab);
+            g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
+        }
         CUtensorMap ma, mb;
         rc = lt_make_map(&mb, Bq, LT_LIMBS * Nlo, Kp);
+        ma = mb;   // placeholder when A' is generated in the kernel
         if (!rc) {
             static bool attr = false;
             if (!attr) {
-                if (cudaFuncSetAttribute(lt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess) {
+                if (cudaFuncSetAttribute(lt_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
+                    cudaFuncSetAttribute(lt_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess) {
                     qsft_set_error("cudaFuncSetAttribute failed");
                     rc = QSFT_ECUDA;
                 }
@@ -473,14 +586,21 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
         }
         for (long long p0 = 0; p0 < P && !rc; p0 += Pc) {
             const long long pc = (P - p0 < Pc) ? (P - p0) : Pc;
-            lt_agen_kernel<<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, e + (size_t)p0 * Se, S, Se, b1, (int)pc, Mhi, Kp,
-                                                                  reinterpret_cast<uint32_t*>(A));
-            rc = lt_make_map(&ma, A, pc * 2 * Mhi, Kp);
-            if (rc) break;
             dim3 grid((unsigned)(Nlo / LT_BN), (unsigned)(pc * 2 * Mhi / LT_BM));
-            lt_gemm_kernel<<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo, inv_scale,
-                                                              reinterpret_cast<float2*>(out) + (size_t)p0 * Mhi * Nlo);
-            g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
+            float2* o = reinterpret_cast<float2*>(out) + (size_t)p0 * Mhi * Nlo;
+            if (fused_a) {
+                lt_gemm_kernel<true><<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo, Ttab,
+                                                                        Etab + (size_t)p0 * Tw, (int)Tw, inv_scale, o);
+                g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+            } else {
+                lt_agen_kernel<<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, e + (size_t)p0 * Se, S, Se, b1, (int)pc, Mhi, Kp,
+                                                                      reinterpret_cast<uint32_t*>(A));
+                rc = lt_make_map(&ma, A, pc * 2 * Mhi, Kp);
+                if (rc) break;
+                lt_gemm_kernel<false><<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo, nullptr,
+                                                                         nullptr, 0, inv_scale, o);
+                g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
+            }
             cudaError_t ce = cudaGetLastError();
             if (ce != cudaSuccess) {
                 qsft_set_error("lattice GEMM launch failed: %s", cudaGetErrorString(ce));
@@ -488,7 +608,7 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
             }
         }
     }
-    void* frees[] = {hhi, hlo, e, alimb, amax, A, Bq};
+    void* frees[] = {hhi, hlo, e, alimb, amax, A, Bq, Ttab, Etab};
     for (void* p : frees)
         if (p) cudaFreeAsync(p, st);
     return rc;
