@@ -510,10 +510,12 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     const int b1 = b / 2, b2 = b - b1;
     const long long Mhi = ipow64(4, b1), Nlo = ipow64(4, b2);
     const long long Kp = (2 * S + LT_BK - 1) / LT_BK * LT_BK;
-    // FUSED_A (default): A' is generated inside the GEMM from packed phase tables (no HBM round trip).  Otherwise it is
-    // materialised: 2 * Mhi * Kp bytes per delay row, rows processed in chunks that keep it under a scratch budget
-    // (default 32 GB, QSFT_LATTICE_SCRATCH_GB overrides).  The limb operand B' is generated once either way.
-    bool fused_a = true;
+    // Default: A' is materialised in HBM (2 * Mhi * Kp bytes per delay row), rows processed in chunks that keep it under a
+    // scratch budget (default 32 GB, QSFT_LATTICE_SCRATCH_GB overrides).  QSFT_LATTICE_FUSED_A=1 generates A' inside the
+    // GEMM from packed phase tables instead (no 17 GB scratch, no HBM round trip; measured: tensor pipe 63 % instead of
+    // 90 % busy because the four producer warps cannot keep up, 38.2 ms vs 31.6 + 3.2 ms per block of 41 rows; equal under
+    // the power cap).  The limb operand B' is generated once either way.
+    bool fused_a = false;
     if (const char* env = getenv("QSFT_LATTICE_FUSED_A")) fused_a = atoi(env) != 0;
     double budget_gb = 32.0;
     if (const char* env = getenv("QSFT_LATTICE_SCRATCH_GB")) {

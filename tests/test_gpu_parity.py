@@ -488,9 +488,10 @@ def test_k2_lattice_row_chunking_gives_identical_samples(monkeypatch):
     ld = utils.padded_ld(n)
     loc_d = ops.pad_digits(rng.integers(0, q, (S, n)), ld, DEV)
     a_d = torch.from_numpy(np.exp(1j * rng.uniform(0, 6.28, S)).astype(np.complex64)).to(DEV)
-    fused = ops.eval_synth_lattice(M, D, loc_d, a_d, q)          # default: A' generated inside the GEMM
-    monkeypatch.setenv("QSFT_LATTICE_FUSED_A", "0")              # A' materialised in HBM
-    whole = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
+    whole = ops.eval_synth_lattice(M, D, loc_d, a_d, q)          # default: A' materialised in HBM
+    monkeypatch.setenv("QSFT_LATTICE_FUSED_A", "1")              # A' generated inside the GEMM
+    fused = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
+    monkeypatch.setenv("QSFT_LATTICE_FUSED_A", "0")
     monkeypatch.setenv("QSFT_LATTICE_SCRATCH_GB", "0.0003")      # 2 * 256 * 1024 B per delay row -> rows in several chunks
     chunked = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
     assert torch.equal(whole, chunked)
