@@ -351,8 +351,12 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LT_BN >> 3) << 17) |
-                                       ((uint32_t)(LT_BM >> 4) << 24);
+            // instruction descriptors: D = S32, A = B = signed int8, K-major, M = 128; limbs 0 and 1 sit in adjacent
+            // shared-memory tiles and adjacent TMEM columns, so they are one N = 256 MMA (A is read twice, not three times)
+            constexpr uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LT_BM >> 4) << 24);
+            constexpr uint32_t idesc256 = idesc_base | ((uint32_t)((2 * LT_BN) >> 3) << 17);
+            constexpr uint32_t idesc128 = idesc_base | ((uint32_t)(LT_BN >> 3) << 17);
+            static_assert(LT_LIMBS == 3, "MMA issue below is written for three limbs");
             for (int kb = 0; kb < nkb; ++kb) {
                 const int stage = kb % LT_STAGES;
                 const uint32_t ph = (uint32_t)(kb / LT_STAGES) & 1u;
@@ -360,13 +364,13 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = lt_smem_u32(base + (size_t)stage * LT_STAGE_BYTES);
                 const uint64_t adesc = lt_desc(sa);
+                const uint64_t bdesc01 = lt_desc(sa + LT_BM * LT_BK);
+                const uint64_t bdesc2 = lt_desc(sa + LT_BM * LT_BK + 2 * (LT_BN * LT_BK));
 #pragma unroll
-                for (int l = 0; l < LT_LIMBS; ++l) {
-                    const uint64_t bdesc = lt_desc(sa + LT_BM * LT_BK + l * (LT_BN * LT_BK));
-#pragma unroll
-                    for (int k = 0; k < LT_BK / 32; ++k)
-                        lt_umma_i8(tmem_base + (uint32_t)(l * LT_BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                   (kb > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < LT_BK / 32; ++k) {
+                    const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                    lt_umma_i8(tmem_base, adesc + (uint64_t)(2 * k), bdesc01 + (uint64_t)(2 * k), idesc256, acc);
+                    lt_umma_i8(tmem_base + (uint32_t)(2 * LT_BN), adesc + (uint64_t)(2 * k), bdesc2 + (uint64_t)(2 * k), idesc128, acc);
                 }
                 lt_commit(&empty[stage]);
             }
