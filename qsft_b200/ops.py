@@ -82,12 +82,17 @@ def _need_cuda(*tensors):
             raise ValueError("expected contiguous CUDA tensors")
 
 
-def pad_digits(rows, ld, device):
-    """(N, n) integer digit rows (numpy / tensor) -> zero padded int8 device tensor (N, ld)."""
-    a = np.asarray(rows)
-    out = np.zeros((a.shape[0], ld), dtype=np.int8)
-    out[:, : a.shape[1]] = a
-    return torch.from_numpy(out).to(device)
+def pad_digits(rows, ld, device, transposed=False):
+    """Integer digit rows -> zero padded int8 device tensor (N, ld).  `rows` is (N, n), or (n, N) with transposed=True
+    (the reference keeps the support as columns: locq (n, S)); the narrow cast happens on the host on the contiguous
+    array, transposition and padding on the device."""
+    a = np.ascontiguousarray(np.asarray(rows), dtype=np.int8)
+    t = torch.from_numpy(a).to(device)
+    if transposed:
+        t = t.t()
+    out = torch.zeros((t.shape[0], ld), dtype=torch.int8, device=device)
+    out[:, : t.shape[1]] = t
+    return out
 
 
 def query_lattice(M, D, q, *, device, want_idx=True, want_digits=False, limbs=None, ld=None):

@@ -68,7 +68,7 @@ class SyntheticSubsampledSignal(SubsampledSignal):
         self._loc_dev = kwargs.get("loc_dev")
         self._a_dev = kwargs.get("a_dev")
         if self._loc_dev is None:
-            self._loc_dev = ops.pad_digits(np.asarray(self.locq).T, self.ld, self.device)
+            self._loc_dev = ops.pad_digits(self.locq, self.ld, self.device, transposed=True)
         if self._a_dev is None:
             self._a_dev = torch.from_numpy(self.strengths.astype(np.complex64)).to(self.device)
 
