@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import threading
 
 import numpy as np
 import torch
@@ -56,19 +57,20 @@ class _timed:
         return False
 
 
-_PINNED = {}
+_PINNED = threading.local()
 
 
 def _pinned(tag, shape, dtype):
     """Reusable page-locked staging buffer (cudaHostAlloc synchronises the device and costs milliseconds, so buffers are
-    kept for the life of the process and only grow)."""
+    kept for the life of the thread and only grow; one set per host thread)."""
     n = 1
     for d in shape:
         n *= int(d)
-    buf = _PINNED.get((tag, dtype))
+    cache = _PINNED.__dict__.setdefault("buffers", {})
+    buf = cache.get((tag, dtype))
     if buf is None or buf.numel() < n:
         buf = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
-        _PINNED[(tag, dtype)] = buf
+        cache[(tag, dtype)] = buf
     return buf[:n].view(shape)
 
 
