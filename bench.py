@@ -276,7 +276,7 @@ def run_ours(a):
         for s_ in range(a.warmup, total_steps):
             sig_ = build_signal(inputs[s_], None)
             res_, sft_ = transform(sig_, output)
-            last_ = (res_, inputs[s_][0], sft_.last_stats)
+            last_ = (res_, inputs[s_][0], sft_.last_stats, getattr(sig_, "_symm", None) is not None)
         e1.record()
         barrier()
         ms = max(e0.elapsed_time(e1), (time.time() - t_wall0) * 1e3)
@@ -290,7 +290,7 @@ def run_ours(a):
     log(f"end-to-end loop (arrays result): {e2e_ms_per_step:.1f} ms/step")
     e2e_dict_ms_per_step, last_d = e2e_loop("dict")
     log(f"end-to-end loop (dict result): {e2e_dict_ms_per_step:.1f} ms/step")
-    res, sw, stats = last
+    res, sw, stats, used_symm = last
     d2h = stats["distinct"] * (n + 8 + 4 + 8)
     got = dict(zip(map(tuple, res["locations"].tolist()), res["values"].tolist()))
     recovered = set(got.keys()) == set(sw.keys()) and set(last_d[0].keys()) == set(sw.keys())
@@ -348,7 +348,9 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "groups_G": G, "bins_B": B, "samples": G * B,
                    "l2": "inputs larger than L2 (per-step working set >= 1 GB)", "support_recovered_exactly": recovered,
                    "max_coeff_err": max_err, "eval_impl": a.eval_impl,
-                   "parallelism": f"delay rows sharded over {a.gpus} GPU(s), bin-sharded peel" if a.gpus > 1 else "single GPU"},
+                   "parallelism": (f"delay rows sharded over {a.gpus} GPU(s), U exchanged by "
+                                   + ("K3 peer stores into symmetric memory (fused all-gather)" if used_symm else "NCCL all-gather")
+                                   + ", bin-sharded peel with one all-gather of finds per round") if a.gpus > 1 else "single GPU"},
         "e2e": {"value": 1e3 / e2e_ms_per_step, "unit": "transforms/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "result": "host arrays (locations, values); output='arrays'",
                 "value_with_reference_dict_result": 1e3 / e2e_dict_ms_per_step},

@@ -70,6 +70,10 @@ int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const int8_t* loc,
  * SubsampledSignal._compute_subtransform + gwht (qsft/input_signal_subsampled.py:264-266, qsft/utils.py:31-36).
  *   x (batch, q^b) complex64.  Index <-> digits MSB first on both sides (C-order reshape [q]*b).            */
 int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stream);
+/* Same transform fused with the multi-GPU all-gather of its output: the final stores also go to the same offsets of
+ * n_peers (<= 7) peer buffers (peer_x[r] = device pointer, mapped in this process, to the corresponding rows of rank r's
+ * symmetric U buffer), i.e. P2P stores over NVLink instead of a separate collective.  peer_x is a HOST array.        */
+int qsft_gwht_batch_bcast(float* x, int64_t batch, int q, int b, float* const* peer_x, int n_peers, void* stream);
 
 /* K4 -- peeling decoder.  Replaces the loop of QSFT.transform (qsft/qsft.py:151-241) and the singleton detectors
  * (qsft/reconstruct.py:12-31, 100-113, 34-51 + qsft/ReedSolomon.py:26-48).

@@ -181,6 +181,23 @@ k3_pass_kernel(float2* __restrict__ x, long long B, int q, int r, long long qa, 
     }
 }
 
+// Peer copies of the output (fused transform + all-gather): the final store of the last pass also writes the element to
+// the same offset of up to 7 peer buffers (P2P stores over NVLink into the peers' symmetric U buffers).
+struct K3Peers {
+    float2* p[7];
+    int n;
+};
+
+__device__ __forceinline__ void k3_store(float2* dst, float2 v, const float2* xroot, const K3Peers& peers) {
+    *dst = v;
+    if (peers.n > 0) {
+        const long long off = dst - xroot;
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+            if (r < peers.n) peers.p[r][off] = v;
+    }
+}
+
 // ---- q = 4 fast pass: radix-16 steps in registers ---------------------------------------------------------
 // Tile = 4096 complex elements, 256 threads, 16 elements per thread and step.  The r <= 6 levels of the pass sit at
 // base-4 digit positions [p0, p0 + r) of the tile index e; they are processed two at a time (radix-16 butterfly in
@@ -200,7 +217,7 @@ __device__ __forceinline__ void k3_r4(float2& a, float2& b, float2& c, float2& d
 
 template <bool STRIDED>
 __device__ __forceinline__ void k3_q4_tile(float2* __restrict__ s, float2* __restrict__ base, long long tin, int r, int p0,
-                                           long long qa, int lgW, float scale) {
+                                           long long qa, int lgW, float scale, const float2* xroot, const K3Peers& peers) {
     const int tau = threadIdx.x;
     const int W = 1 << lgW;
     long long g0;
@@ -248,7 +265,8 @@ __device__ __forceinline__ void k3_q4_tile(float2* __restrict__ s, float2* __res
             for (int h = 0; h < 4; ++h) k3_r4(v[h], v[h + 4], v[h + 8], v[h + 12]);                      // digit p + 1
             if (last) {
 #pragma unroll
-                for (int m = 0; m < 16; ++m) *gptr(eb[0] + m * step) = make_float2(v[m].x * scale, v[m].y * scale);
+                for (int m = 0; m < 16; ++m)
+                    k3_store(gptr(eb[0] + m * step), make_float2(v[m].x * scale, v[m].y * scale), xroot, peers);
             } else {
 #pragma unroll
                 for (int m = 0; m < 16; ++m) s[k3_swz(eb[0] + m * step)] = v[m];
@@ -269,7 +287,7 @@ __device__ __forceinline__ void k3_q4_tile(float2* __restrict__ s, float2* __res
             for (int k = 0; k < 4; ++k) {
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
-                    if (last) *gptr(eb[k] + m * step) = make_float2(v[4 * k + m].x * scale, v[4 * k + m].y * scale);
+                    if (last) k3_store(gptr(eb[k] + m * step), make_float2(v[4 * k + m].x * scale, v[4 * k + m].y * scale), xroot, peers);
                     else s[k3_swz(eb[k] + m * step)] = v[4 * k + m];
                 }
             }
@@ -281,11 +299,11 @@ __device__ __forceinline__ void k3_q4_tile(float2* __restrict__ s, float2* __res
 template <bool STRIDED>
 __global__ void __launch_bounds__(256)
 k3_q4_fast_kernel(float2* __restrict__ x, long long B, int r, int p0, long long qa, int lgW, long long tiles_per_block,
-                  long long tile0, float scale) {
+                  long long tile0, float scale, K3Peers peers) {
     __shared__ float2 s[4096];
     const long long tile = tile0 + blockIdx.x;
     const long long blk = tile / tiles_per_block;
-    k3_q4_tile<STRIDED>(s, x + blk * B, tile - blk * tiles_per_block, r, p0, qa, lgW, scale);
+    k3_q4_tile<STRIDED>(s, x + blk * B, tile - blk * tiles_per_block, r, p0, qa, lgW, scale, x, peers);
 }
 
 // Both passes of a two-pass transform (4^7 .. 4^12 points) in ONE launch: CTAs are enumerated block by block, first
@@ -295,7 +313,8 @@ k3_q4_fast_kernel(float2* __restrict__ x, long long B, int r, int p0, long long 
 // right after it was produced: DRAM sees one read and one write of the data.
 __global__ void __launch_bounds__(256)
 k3_q4_twopass_kernel(float2* __restrict__ x, long long B, int r1, int r2, long long qa2, int lgW2, int tiles1, int tiles2,
-                     unsigned int* __restrict__ done /* [nblocks] counters + [1] ticket */, long long nblocks, float scale) {
+                     unsigned int* __restrict__ done /* [nblocks] counters + [1] ticket */, long long nblocks, float scale,
+                     K3Peers peers) {
     __shared__ float2 s[4096];
     __shared__ unsigned int s_ticket;
     // work items are handed out through an atomic ticket (not blockIdx): every lower ticket is then guaranteed to be
@@ -308,7 +327,9 @@ k3_q4_twopass_kernel(float2* __restrict__ x, long long B, int r1, int r2, long l
     const int t = (int)(ticket - (unsigned int)(blk * per_block));
     float2* base = x + blk * B;
     if (t < tiles1) {
-        k3_q4_tile<false>(s, base, t, r1, 0, 1, 0, 1.0f);
+        K3Peers none;
+        none.n = 0;
+        k3_q4_tile<false>(s, base, t, r1, 0, 1, 0, 1.0f, x, none);
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -323,7 +344,7 @@ k3_q4_twopass_kernel(float2* __restrict__ x, long long B, int r1, int r2, long l
             } while (seen < (unsigned)tiles1);
         }
         __syncthreads();
-        k3_q4_tile<true>(s, base, t - tiles1, r2, lgW2 / 2, qa2, lgW2, scale);
+        k3_q4_tile<true>(s, base, t - tiles1, r2, lgW2 / 2, qa2, lgW2, scale, x, peers);
     }
 }
 
@@ -376,16 +397,20 @@ int launch_pass(float2* x, long long B, int q, const PassPlan& p, long long blk0
     return QSFT_OK;
 }
 
-int launch_pass_q(float2* x, long long B, int q, const PassPlan& p, long long blk0, long long nblk, cudaStream_t st) {
+// peers.n > 0 only for the last pass of a transform and only honoured by the q = 4 kernels (returns 1 in *fused then)
+int launch_pass_q(float2* x, long long B, int q, const PassPlan& p, long long blk0, long long nblk, cudaStream_t st,
+                  const K3Peers& peers, bool* fused) {
+    if (fused) *fused = false;
     if (q == 4 && p.T == 4096 && p.r <= 6) {
+        if (fused) *fused = true;
         const long long tiles = p.tiles_per_block * nblk;
         QSFT_CHECK_ARG(tiles <= 0x7fffffffLL, "too many tiles");
         if (p.a == 0)
             k3_q4_fast_kernel<false><<<(unsigned)tiles, 256, 0, st>>>(x, B, p.r, 0, 1, 0, p.tiles_per_block,
-                                                                      blk0 * p.tiles_per_block, p.scale);
+                                                                      blk0 * p.tiles_per_block, p.scale, peers);
         else
             k3_q4_fast_kernel<true><<<(unsigned)tiles, 256, 0, st>>>(x, B, p.r, p.lgW / 2, p.qa, p.lgW, p.tiles_per_block,
-                                                                     blk0 * p.tiles_per_block, p.scale);
+                                                                     blk0 * p.tiles_per_block, p.scale, peers);
         QSFT_LAUNCHED();
         return QSFT_OK;
     }
@@ -401,7 +426,15 @@ int launch_pass_q(float2* x, long long B, int q, const PassPlan& p, long long bl
 
 }  // namespace
 
-extern "C" int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stream) {
+// plain copy of the finished transform to the peers, for the paths whose last pass cannot store remotely itself
+__global__ void k3_bcast_copy_kernel(const float4* __restrict__ x, long long n4, K3Peers peers) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        for (int r = 0; r < peers.n; ++r) reinterpret_cast<float4*>(peers.p[r])[i] = v;
+    }
+}
+
+static int gwht_impl(float* x, int64_t batch, int q, int b, const K3Peers& peers, void* stream) {
     QSFT_CHECK_ARG(q >= 2 && q <= QSFT_MAX_Q, "q=%d out of range", q);
     QSFT_CHECK_ARG(b >= 0 && b <= QSFT_MAX_B, "b=%d out of range", b);
     QSFT_CHECK_ARG(batch >= 0, "negative batch");
@@ -442,7 +475,7 @@ extern "C" int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stre
         QSFT_CUDA(cudaMemsetAsync(done, 0, (size_t)(batch + 1) * sizeof(unsigned int), st));
         const int t1 = (int)plans[0].tiles_per_block, t2 = (int)plans[1].tiles_per_block;
         k3_q4_twopass_kernel<<<(unsigned)(batch * (t1 + t2)), 256, 0, st>>>(xx, B, plans[0].r, plans[1].r, plans[1].qa,
-                                                                          plans[1].lgW, t1, t2, done, (long long)batch, inv);
+                                                                          plans[1].lgW, t1, t2, done, (long long)batch, inv, peers);
         QSFT_LAUNCHED();
         QSFT_CUDA(cudaFreeAsync(done, st));
         return QSFT_OK;
@@ -456,11 +489,39 @@ extern "C" int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stre
         if (chunk < 1) chunk = 1;
         if (chunk > batch) chunk = batch;
     }
+    K3Peers none;
+    none.n = 0;
+    bool all_fused = true;
     for (long long blk0 = 0; blk0 < batch; blk0 += chunk) {
         const long long nblk = (batch - blk0 < chunk) ? (batch - blk0) : chunk;
         for (int p = 0; p < passes; ++p) {
-            if (int rc = launch_pass_q(xx, B, q, plans[p], blk0, nblk, st)) return rc;
+            bool fused = false;
+            const bool lastp = (p == passes - 1);
+            if (int rc = launch_pass_q(xx, B, q, plans[p], blk0, nblk, st, lastp ? peers : none, lastp ? &fused : nullptr)) return rc;
+            if (lastp && !fused) all_fused = false;
         }
     }
+    if (peers.n > 0 && !all_fused) {
+        const long long n4 = batch * B / 2;   // float4 = two complex64 (B even or batch*B even required)
+        QSFT_CHECK_ARG((batch * B) % 2 == 0, "peer broadcast needs an even number of complex elements");
+        k3_bcast_copy_kernel<<<(unsigned)(4 * qsft_num_sms()), 256, 0, st>>>(reinterpret_cast<const float4*>(x), n4, peers);
+        QSFT_LAUNCHED();
+    }
     return QSFT_OK;
+}
+
+extern "C" int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stream) {
+    K3Peers none;
+    none.n = 0;
+    return gwht_impl(x, batch, q, b, none, stream);
+}
+
+extern "C" int qsft_gwht_batch_bcast(float* x, int64_t batch, int q, int b, float* const* peer_x, int n_peers, void* stream) {
+    QSFT_CHECK_ARG(n_peers >= 0 && n_peers <= 7, "n_peers must be in [0, 7]");
+    QSFT_CHECK_ARG(n_peers == 0 || peer_x != nullptr, "null peer list");
+    K3Peers peers;
+    peers.n = n_peers;
+    for (int r = 0; r < 7; ++r) peers.p[r] = r < n_peers ? reinterpret_cast<float2*>(peer_x[r]) : nullptr;
+    for (int r = 0; r < n_peers; ++r) QSFT_CHECK_ARG(peer_x[r] != nullptr, "null peer pointer");
+    return gwht_impl(x, batch, q, b, peers, stream);
 }

@@ -11,12 +11,41 @@ import torch.distributed as td
 
 
 class DistContext:
-    def __init__(self, group=None):
+    def __init__(self, group=None, symmetric=True):
         if not td.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.group = group
         self.rank = td.get_rank(group)
         self.world_size = td.get_world_size(group)
+        # symmetric (peer-mapped) U buffers let K3 store its output straight into every peer (fused all-gather);
+        # falls back to NCCL all_gather_into_tensor when symmetric memory is not available
+        self.symmetric = bool(symmetric) and td.get_backend(group) == "nccl" and self.world_size <= 8
+        self._symm_free = {}
+
+    # -- symmetric buffers ---------------------------------------------------------------------------------
+    def symm_acquire(self, nfloats, device):
+        """A float32 symmetric buffer of `nfloats` elements + its rendezvous handle, reused across signals (the
+        rendezvous costs milliseconds).  Returns None when symmetric memory cannot be set up."""
+        if not self.symmetric:
+            return None
+        pool = self._symm_free.setdefault(int(nfloats), [])
+        if pool:
+            return pool.pop()
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = self.group if self.group is not None else td.group.WORLD
+            buf = symm_mem.empty(int(nfloats), dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(buf, grp)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            return (buf, hdl, ptrs)
+        except Exception as exc:  # pragma: no cover - depends on the platform
+            self.symmetric = False
+            self.symmetric_error = repr(exc)
+            return None
+
+    def symm_release(self, item):
+        if item is not None:
+            self._symm_free.setdefault(int(item[0].numel()), []).append(item)
 
     def all_gather_rows_(self, buf, rows_per_rank):
         """buf (world*rows_per_rank, W): every rank has filled its own row block; gather all blocks in place."""

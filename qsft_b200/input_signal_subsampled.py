@@ -101,7 +101,17 @@ class SubsampledSignal(Signal):
         rows_alloc = per * world
         dev = self.device
         # one HBM buffer per b: rows = flattened (c, r, p), padded to a multiple of the world size
-        self._Ubuf = {bb: torch.empty((rows_alloc, self.q ** bb), dtype=torch.complex64, device=dev) for bb in self.all_bs}
+        # multi-GPU, single b: the U buffer is symmetric (peer mapped) memory and K3 stores its output straight into every
+        # peer's copy (fused transform + all-gather); otherwise plain buffers + one NCCL all-gather at the end
+        self._symm = None
+        if world > 1 and len(self.all_bs) == 1 and self.all_bs[0] == self.b:
+            self._symm = self.dist.symm_acquire(2 * rows_alloc * B, dev)
+        if self._symm is not None:
+            ubuf = torch.view_as_complex(self._symm[0].view(rows_alloc, B, 2))
+            self._symm[1].barrier()             # every rank is done with the previous contents of the (reused) buffer
+            self._Ubuf = {self.b: ubuf}
+        else:
+            self._Ubuf = {bb: torch.empty((rows_alloc, self.q ** bb), dtype=torch.complex64, device=dev) for bb in self.all_bs}
         for bb in self.all_bs:
             self._Ubuf[bb][G:].zero_()          # padding rows (multi-GPU row blocks of equal size)
         self.Us = [[{} for _ in range(R)] for _ in range(C)]
@@ -144,15 +154,23 @@ class SubsampledSignal(Signal):
                     if inplace:
                         if samples.data_ptr() != target.data_ptr():
                             target.copy_(samples)
-                        ops.gwht_batch_(target, self.q, bb)
+                        if self._symm is not None:
+                            row_off = (g0 + p0) * B * 8          # bytes from the start of the symmetric buffer
+                            peers = [ptr + row_off for r, ptr in enumerate(self._symm[2]) if r != self.dist.rank]
+                            ops.gwht_batch_bcast_(target, self.q, bb, peers)
+                        else:
+                            ops.gwht_batch_(target, self.q, bb)
                     else:
                         self._Ubuf[bb][g0 + p0:g0 + p1] = self._compute_subtransform(samples, bb)
                     ev1.record()
                     events.append((i, j, bb, ev0, ev1))
                 del samples
         if world > 1:
-            for bb in self.all_bs:
-                self.dist.all_gather_rows_(self._Ubuf[bb], per)
+            if self._symm is not None:
+                self._symm[1].barrier()         # all peers' stores into this rank's buffer have landed
+            else:
+                for bb in self.all_bs:
+                    self.dist.all_gather_rows_(self._Ubuf[bb], per)
         torch.cuda.synchronize(dev)
         fft_total = 0.0
         for i in range(C):
@@ -172,6 +190,12 @@ class SubsampledSignal(Signal):
                 save_data(({bb: list(self.Us[i][j][bb].cpu().numpy().astype(complex)) for bb in self.all_bs},
                            dict(self.transformTimes[i][j])), Path(f"{self.foldername}/transforms/U{i}_{j}.pickle"))
         self.sample_time = time.time() - t_sample0 - fft_total
+
+    def __del__(self):
+        symm = getattr(self, "_symm", None)
+        if symm is not None and getattr(self, "dist", None) is not None:
+            self.dist.symm_release(symm)
+            self._symm = None
 
     def _sample_rows(self, M, D_rows, out=None):
         """Samples of the lattices {M l + d_p} for the given delay rows -> complex64 tensor (rows, B); `out`, when

@@ -192,6 +192,19 @@ def gwht_batch_(x, q, b):
     return x
 
 
+def gwht_batch_bcast_(x, q, b, peer_ptrs):
+    """K3 fused with the all-gather of its output: in place on x (rows, q^b) and, in the same kernel, stored to the same
+    rows of the peers' symmetric buffers (`peer_ptrs`: device addresses of those rows, one per peer)."""
+    _need_cuda(x)
+    if x.dtype != torch.complex64 or x.shape[-1] != q ** b:
+        raise ValueError("x must be complex64 with last dimension q^b")
+    batch = x.numel() // (q ** b)
+    arr = (C.c_void_p * max(1, len(peer_ptrs)))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+    with torch.cuda.device(x.device), _timed("k3_gwht", x.numel()):
+        _lib.check(_lib.lib().qsft_gwht_batch_bcast(_ptr(x), batch, q, b, arr, len(peer_ptrs), _stream()))
+    return x
+
+
 class PeelProblem:
     """Device-side description of one peeling problem (qsft_peel_desc) + its workspaces."""
 
