@@ -157,6 +157,23 @@ def test_k3_linearity_and_delta_full_size():
     assert torch.max(torch.abs(yz[0] - (2.5 * y[0] - 1j * y[1]))) < 1e-8
 
 
+@pytest.mark.parametrize("q,b,batch", [(4, 10, 5), (4, 6, 41), (4, 4, 9), (4, 12, 2), (3, 7, 3), (2, 9, 4)])
+def test_k3_bcast_matches_plain(q, b, batch):
+    """The fused K3 + all-gather entry point writes the same bits to the local rows and to every peer buffer
+    (peers emulated by other allocations of this device) as the plain in-place transform."""
+    B = q ** b
+    x = torch.randn(batch, B, device=DEV) + 1j * torch.randn(batch, B, device=DEV)
+    x = x.to(torch.complex64)
+    want = ops.gwht_batch_(x.clone(), q, b)
+    peers = [torch.full((batch + 2, B), 7.0, dtype=torch.complex64, device=DEV) for _ in range(3)]
+    got = ops.gwht_batch_bcast_(x.clone(), q, b, [p[1:].data_ptr() for p in peers])
+    assert torch.equal(got, want)
+    for p in peers:
+        assert torch.equal(p[1:1 + batch], want)
+        assert bool((p[0] == 7.0).all()) and bool((p[-1] == 7.0).all())     # neighbours untouched
+    assert torch.equal(ops.gwht_batch_bcast_(x.clone(), q, b, []), want)
+
+
 # ---- construct (K1 + K2 + K3) against the reference's Us ----------------------------------------------------
 @pytest.mark.parametrize("name", FULL_CASES)
 def test_construct_matches_reference_Us(name):
