@@ -464,11 +464,260 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ---- 2:4 structured-sparse variant ------------------------------------------------------------------------
+// Every (Re, Im) byte pair of A' holds exactly one zero, so four consecutive K' bytes (two support elements) hold exactly two
+// non-zeros: A' is a valid 2:4 sparse operand for tcgen05.mma.sp.  Stored compressed (one +-1 byte per row and support
+// element) plus 4 bits of metadata per four logical bytes: half the tensor work and 0.625x the operand bytes, bit-exact.
+// The GEMM runs on CTA pairs (cta_group::2): 256 rows of A' x 128 columns x 3 limbs per pair; each CTA stages its own 128
+// compressed rows + metadata, ONE of limbs 0 / 1 and half of the limb-2 columns, so the limb operand is fetched once per pair.
+constexpr int SP_BK = 256;                                   // logical K' bytes per stage (128 support elements)
+constexpr int SP_STAGES = 3;
+constexpr int SP_A_BYTES = 128 * 128;                        // compressed A' slab: 128 rows x 128 bytes
+constexpr int SP_B01_BYTES = 2 * 128 * 128;                  // this CTA's limb (0 or 1), two 128-byte K halves
+constexpr int SP_B2_BYTES = 2 * 64 * 128;                    // this CTA's 64 columns of limb 2, two K halves
+constexpr int SP_E_BYTES = 2 * 2048;                         // metadata: two chunks of 128 rows x 16 bytes
+constexpr int SP_OFF_B01 = SP_A_BYTES, SP_OFF_B2 = SP_OFF_B01 + SP_B01_BYTES, SP_OFF_E = SP_OFF_B2 + SP_B2_BYTES;
+constexpr int SP_STAGE_BYTES = SP_OFF_E + SP_E_BYTES;        // 68 KB
+constexpr size_t SP_SMEM = 1024 + (size_t)SP_STAGES * SP_STAGE_BYTES + 256;
+constexpr uint32_t SP_TMEM_E = 384;                          // metadata columns behind the three limb accumulators
+static_assert(SP_STAGE_BYTES % 1024 == 0, "stage must keep the 1024-byte swizzle alignment");
+
+__device__ __forceinline__ uint32_t sp_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t sp_mapa(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void sp_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion is signalled on the pair leader's barrier (cluster address `bar_cluster`)
+__device__ __forceinline__ void sp_tma_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            lt_smem_u32(dst)),
+        "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void sp_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     lt_smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void sp_umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t e_tmem, uint32_t idesc,
+                                           uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.sp.cta_group::2.kind::i8 [%0], %1, %2, [%3], %4, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(e_tmem), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// un-swizzled K-major descriptor of one metadata chunk: 128 rows x 16 bytes, 8-row core matrices 128 bytes apart
+__device__ __forceinline__ uint64_t sp_edesc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(128 >> 4) << 16;
+    d |= (uint64_t)(128 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// Compressed A' and its metadata.  Ac[row][s] (row = (p * Mhi + l_hi) * 2 + part, one byte per support element):
+//   Re row (er, -ei): the non-zero sits at pair position r & 1 and is negative iff (r & 1) ^ (r >> 1)
+//   Im row (ei,  er): position 1 - (r & 1), negative iff r >> 1                          (r = rotation, i^r = er + i ei)
+// Metadata nibble of a 4-byte group (support elements 2c, 2c + 1) = idx0 | idx1 << 2 with idx0 = pos(2c), idx1 = 2 + pos(2c+1),
+// i.e. bits 0 and 2 are the two position bits and bit 3 is set; chunks of 128 rows x 16 bytes (128 logical K') in the
+// order (m-tile, k-chunk) so that one TMA box feeds one tcgen05.cp.  One thread = 16 support elements of one l_hi.
+__global__ void __launch_bounds__(256)
+lt_agen_sp_kernel(const uint32_t* __restrict__ hhi, const uint32_t* __restrict__ Etab, long long S, int b1, int P, long long Mhi,
+                  long long Sp /* padded support = bytes per Ac row */, long long Tw, uint8_t* __restrict__ Ac,
+                  uint8_t* __restrict__ Em) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lhi = blockIdx.y;
+    if (w * 16 >= Sp) return;
+    uint32_t t16 = 0;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const long long s = 16 * w + i;
+        if (s < S) t16 |= dot4(hhi[s], lhi, b1) << (2 * i);
+    }
+    const long long nk128 = Sp / 64;
+    const long long kc = w >> 2;
+    const int eoff = (int)(w & 3) * 4;
+    for (int p = 0; p < P; ++p) {
+        const uint32_t ew = Etab[(size_t)p * Tw + w];
+        constexpr uint32_t H = 0xAAAAAAAAu;
+        const uint32_t r16 = ((t16 & ~H) + (ew & ~H)) ^ ((t16 ^ ew) & H);      // sixteen 2-bit rotations
+        const uint32_t lo = r16 & 0x55555555u, hi = (r16 >> 1) & 0x55555555u;
+        const uint32_t nre = lo ^ hi, nim = hi;                                 // negative flags, one per 2-bit field
+        uint32_t wre[4], wim[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint32_t mr = (((nre >> (8 * g)) & 0x55u) * 0x00041041u) & 0x01010101u;
+            const uint32_t mi = (((nim >> (8 * g)) & 0x55u) * 0x00041041u) & 0x01010101u;
+            wre[g] = 0x01010101u ^ (mr * 0xFEu);
+            wim[g] = 0x01010101u ^ (mi * 0xFEu);
+        }
+        const long long row = ((long long)p * Mhi + lhi) * 2;
+        *reinterpret_cast<uint4*>(Ac + (size_t)row * Sp + 16 * w) = make_uint4(wre[0], wre[1], wre[2], wre[3]);
+        *reinterpret_cast<uint4*>(Ac + (size_t)(row + 1) * Sp + 16 * w) = make_uint4(wim[0], wim[1], wim[2], wim[3]);
+        const uint32_t mre = lo | 0x88888888u;
+        uint8_t* ebase = Em + (((size_t)(row >> 7) * nk128 + kc) * 128 + (size_t)(row & 127)) * 16 + eoff;
+        *reinterpret_cast<uint32_t*>(ebase) = mre;
+        *reinterpret_cast<uint32_t*>(ebase + 16) = mre ^ 0x55555555u;
+    }
+}
+
+__global__ void __launch_bounds__(LT_THREADS, 1)
+lt_gemm_sp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmE, int nkb, int Mhi, int Nlo,
+                  int n_mtiles, const float* __restrict__ inv_scale_ptr, float2* __restrict__ out) {
+    extern __shared__ uint8_t lt_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)lt_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)SP_STAGES * SP_STAGE_BYTES);
+    uint64_t* full = bars;                       // used in the leader CTA only: both CTAs' loads complete on it
+    uint64_t* empty = bars + SP_STAGES;          // one per CTA, released by the leader's multicast commit
+    uint64_t* tfull = bars + 2 * SP_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = sp_cluster_rank();
+    const int ntile = blockIdx.x >> 1;
+    const int mtile = 2 * blockIdx.y + (int)rank;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < SP_STAGES; ++i) {
+            lt_mbar_init(&full[i], 1);
+            lt_mbar_init(&empty[i], 1);
+        }
+        lt_mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lt_smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    sp_cluster_sync();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int nk128 = 2 * nkb;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int stage = kb % SP_STAGES;
+                const uint32_t ph = (uint32_t)(kb / SP_STAGES) & 1u;
+                lt_mbar_wait(&empty[stage], ph ^ 1u);
+                if (rank == 0) lt_mbar_expect_tx(&full[stage], 2 * SP_STAGE_BYTES);
+                const uint32_t fl = sp_mapa(lt_smem_u32(&full[stage]), 0);
+                uint8_t* st = base + (size_t)stage * SP_STAGE_BYTES;
+                sp_tma_2d(st, &tmA, kb * 128, mtile * LT_BM, fl);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    sp_tma_2d(st + SP_OFF_B01 + h * 16384, &tmB, kb * SP_BK + h * 128, (int)rank * Nlo + ntile * LT_BN, fl);
+                    sp_tma_2d(st + SP_OFF_B2 + h * 8192, &tmB2, kb * SP_BK + h * 128, 2 * Nlo + ntile * LT_BN + (int)rank * 64, fl);
+                }
+                sp_tma_2d(st + SP_OFF_E, &tmE, 0, (mtile * nk128 + 2 * kb) * 8, fl);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // D = S32, A = B = signed int8, sparse A, K-major, M = 256 over the CTA pair
+            constexpr uint32_t idesc_base = (1u << 2) | (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 4) << 24);
+            constexpr uint32_t idesc256 = idesc_base | ((256u >> 3) << 17);
+            constexpr uint32_t idesc128 = idesc_base | ((128u >> 3) << 17);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int stage = kb % SP_STAGES;
+                const uint32_t ph = (uint32_t)(kb / SP_STAGES) & 1u;
+                lt_mbar_wait(&full[stage], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = lt_smem_u32(base + (size_t)stage * SP_STAGE_BYTES);
+                const uint32_t te = tmem_base + SP_TMEM_E + (uint32_t)(kb & 1) * 8u;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    asm volatile("tcgen05.cp.cta_group::2.128x128b [%0], %1;" ::"r"(te + 4u * c), "l"(sp_edesc(sa + SP_OFF_E + c * 2048))
+                                 : "memory");
+                const uint64_t adesc = lt_desc(sa);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
+                    const uint64_t koff = (uint64_t)(4 * (j & 1));                      // 64 bytes of B per MMA
+                    const uint64_t b01 = lt_desc(sa + SP_OFF_B01 + (j >> 1) * 16384) + koff;
+                    const uint64_t b2 = lt_desc(sa + SP_OFF_B2 + (j >> 1) * 8192) + koff;
+                    sp_umma_i8(tmem_base, adesc + (uint64_t)(2 * j), b01, te + 2u * j, idesc256, acc);
+                    sp_umma_i8(tmem_base + 256u, adesc + (uint64_t)(2 * j), b2, te + 2u * j, idesc128, acc);
+                }
+                sp_commit_pair(&empty[stage]);
+            }
+            sp_commit_pair(tfull);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const long long grow = (long long)mtile * LT_BM + row;
+        const int p = (int)(grow / (2 * Mhi));
+        const int lhi = (int)(grow - (long long)p * 2 * Mhi) >> 1;
+        const bool odd = lane & 1;
+        const int llo0 = ntile * LT_BN;
+        const double inv_scale = (double)(*inv_scale_ptr);
+        lt_mbar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (mtile < n_mtiles) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            float2* orow = out + ((size_t)p * Mhi + lhi) * Nlo + llo0;
+#pragma unroll 1
+            for (int ch = 0; ch < LT_BN / 16; ++ch) {
+                uint32_t a0[16], a1[16], a2[16];
+                lt_ld16(taddr + (uint32_t)(0 * LT_BN + ch * 16), a0);
+                lt_ld16(taddr + (uint32_t)(1 * LT_BN + ch * 16), a1);
+                lt_ld16(taddr + (uint32_t)(2 * LT_BN + ch * 16), a2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float val[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const long long v = ((long long)(int)a0[j] * 128 + (long long)(int)a1[j]) * 128 + (long long)(int)a2[j];
+                    val[j] = (float)((double)v * inv_scale);
+                }
+                float2 o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float send = odd ? val[j] : val[8 + j];
+                    const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                    o[j] = odd ? make_float2(recv, val[8 + j]) : make_float2(val[j], recv);
+                }
+                float4* dst = reinterpret_cast<float4*>(orow + ch * 16 + (odd ? 8 : 0));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[2 * j].x, o[2 * j].y, o[2 * j + 1].x, o[2 * j + 1].y);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    sp_cluster_sync();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int lt_make_map(CUtensorMap* map, const void* ptr, long long rows, long long kbytes) {
+int lt_make_map(CUtensorMap* map, const void* ptr, long long rows, long long kbytes, int box_k = LT_BK, int box_rows = 128,
+                bool swizzle = true) {
     static EncodeTiledFn enc = nullptr;
     if (!enc) {
         void* p = nullptr;
@@ -483,10 +732,11 @@ int lt_make_map(CUtensorMap* map, const void* ptr, long long rows, long long kby
     }
     cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)kbytes};
-    cuuint32_t box[2] = {LT_BK, 128};
+    cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         qsft_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld k=%lld)", (int)r, rows, kbytes);
@@ -513,20 +763,25 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     cudaStream_t st = (cudaStream_t)stream;
     const int b1 = b / 2, b2 = b - b1;
     const long long Mhi = ipow64(4, b1), Nlo = ipow64(4, b2);
-    const long long Kp = (2 * S + LT_BK - 1) / LT_BK * LT_BK;
-    // Default: A' is materialised in HBM (2 * Mhi * Kp bytes per delay row), rows processed in chunks that keep it under a
-    // scratch budget (default 32 GB, QSFT_LATTICE_SCRATCH_GB overrides).  QSFT_LATTICE_FUSED_A=1 generates A' inside the
-    // GEMM from packed phase tables instead (no 17 GB scratch, no HBM round trip; measured: tensor pipe 63 % instead of
-    // 90 % busy because the four producer warps cannot keep up, 38.2 ms vs 31.6 + 3.2 ms per block of 41 rows; equal under
-    // the power cap).  The limb operand B' is generated once either way.
-    bool fused_a = false;
+    // Default: 2:4 structured-sparse A' (compressed + metadata, tcgen05.mma.sp on CTA pairs).  QSFT_LATTICE_SPARSE=0 selects
+    // the dense kernel: A' materialised in HBM (2 * Mhi * Kp bytes per delay row).  Either way the delay rows are processed in
+    // chunks that keep A' under a scratch budget (default 32 GB, QSFT_LATTICE_SCRATCH_GB overrides).
+    // QSFT_LATTICE_FUSED_A=1 (dense only) generates A' inside the GEMM from packed phase tables instead (no scratch, no HBM
+    // round trip; measured: tensor pipe 63 % instead of 90 % busy because the four producer warps cannot keep up, 38.2 ms vs
+    // 31.6 + 3.2 ms per block of 41 rows).  The limb operand B' is generated once in all variants.
+    bool fused_a = false, sparse = true;
     if (const char* env = getenv("QSFT_LATTICE_FUSED_A")) fused_a = atoi(env) != 0;
+    if (const char* env = getenv("QSFT_LATTICE_SPARSE")) sparse = atoi(env) != 0;
+    if (fused_a) sparse = false;
+    const long long kalign = sparse ? SP_BK : LT_BK;
+    const long long Kp = (2 * S + kalign - 1) / kalign * kalign;
+    const long long Sp = Kp / 2;                        // padded support = compressed bytes per A' row
     double budget_gb = 32.0;
     if (const char* env = getenv("QSFT_LATTICE_SCRATCH_GB")) {
         const double v = atof(env);
         if (v > 0.0) budget_gb = v;
     }
-    const double per_row = 2.0 * (double)Mhi * (double)Kp;
+    const double per_row = 2.0 * (double)Mhi * (sparse ? 0.625 * (double)Kp : (double)Kp);
     long long Pc = fused_a ? P : (long long)(budget_gb * 1e9 / per_row);
     if (Pc < 1) Pc = 1;
     if (Pc > P) Pc = P;
@@ -538,7 +793,7 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     int2* alimb = nullptr;
     unsigned int* amax = nullptr;
     float* inv_scale = nullptr;
-    uint8_t *A = nullptr, *Bq = nullptr;
+    uint8_t *A = nullptr, *Bq = nullptr, *Em = nullptr;
     int rc = QSFT_OK;
     auto alloc = [&](void** p, size_t bytes) {
         if (rc == QSFT_OK && qsft_scratch_alloc(p, bytes, st) != cudaSuccess) {
@@ -552,9 +807,15 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     alloc((void**)&e, (size_t)P * Se);
     alloc((void**)&alimb, (size_t)S * 8);
     alloc((void**)&amax, 8);
+    const long long mt_max = ((Pc * 2 * Mhi / LT_BM) + 1) & ~1ll;      // m-tiles per chunk, padded to whole CTA pairs
+    const long long nk128 = Kp / 128;
     if (fused_a) {
         alloc((void**)&Ttab, (size_t)Mhi * Tw * 4);
         alloc((void**)&Etab, (size_t)P * Tw * 4);
+    } else if (sparse) {
+        alloc((void**)&Etab, (size_t)P * Tw * 4);
+        alloc((void**)&A, (size_t)mt_max * LT_BM * Sp);
+        alloc((void**)&Em, (size_t)mt_max * nk128 * 2048);
     } else {
         alloc((void**)&A, (size_t)Pc * 2 * Mhi * Kp);
     }
@@ -570,20 +831,25 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
         const unsigned pb = (unsigned)((Kp / 4 + T - 1) / T);
         lt_bgen_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp, reinterpret_cast<uint32_t*>(Bq));
         g_qsft_launches.fetch_add(4, std::memory_order_relaxed);
+        const unsigned wb = (unsigned)((Tw + T - 1) / T);
         if (fused_a) {
-            const unsigned wb = (unsigned)((Tw + T - 1) / T);
             lt_ttab_kernel<<<dim3(wb, (unsigned)Mhi), T, 0, st>>>(hhi, S, b1, Tw, Ttab);
-            lt_etab_kernel<<<dim3(wb, (unsigned)P), T, 0, st>>>(e, S, Se, P, Tw, Etab);
-            g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
+            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
         }
-        CUtensorMap ma, mb;
+        if (fused_a || sparse) {
+            lt_etab_kernel<<<dim3(wb, (unsigned)P), T, 0, st>>>(e, S, Se, P, Tw, Etab);
+            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        CUtensorMap ma, mb, mb2, me;
         rc = lt_make_map(&mb, Bq, LT_LIMBS * Nlo, Kp);
+        if (!rc && sparse) rc = lt_make_map(&mb2, Bq, LT_LIMBS * Nlo, Kp, LT_BK, 64);
         ma = mb;   // placeholder when A' is generated in the kernel
         if (!rc) {
             static bool attr = false;
             if (!attr) {
                 if (cudaFuncSetAttribute(lt_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
-                    cudaFuncSetAttribute(lt_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess) {
+                    cudaFuncSetAttribute(lt_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
+                    cudaFuncSetAttribute(lt_gemm_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM) != cudaSuccess) {
                     qsft_set_error("cudaFuncSetAttribute failed");
                     rc = QSFT_ECUDA;
                 }
@@ -598,6 +864,32 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
                 lt_gemm_kernel<true><<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo, Ttab,
                                                                         Etab + (size_t)p0 * Tw, (int)Tw, inv_scale, o);
                 g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+            } else if (sparse) {
+                const long long n_mt = pc * 2 * Mhi / LT_BM, n_mt_pad = (n_mt + 1) & ~1ll;
+                if (n_mt_pad != n_mt) {         // odd tile count: give the idle half of the last CTA pair well-formed operands
+                    cudaMemsetAsync(A + (size_t)n_mt * LT_BM * Sp, 0, (size_t)LT_BM * Sp, st);
+                    cudaMemsetAsync(Em + (size_t)n_mt * nk128 * 2048, 0x88, (size_t)nk128 * 2048, st);
+                }
+                const unsigned ab = (unsigned)((Sp / 16 + T - 1) / T);
+                lt_agen_sp_kernel<<<dim3(ab, (unsigned)Mhi), T, 0, st>>>(hhi, Etab + (size_t)p0 * Tw, S, b1, (int)pc, Mhi, Sp, Tw, A, Em);
+                rc = lt_make_map(&ma, A, n_mt_pad * LT_BM, Sp);
+                if (!rc) rc = lt_make_map(&me, Em, n_mt_pad * nk128 * 8, 256, 256, 16, false);
+                if (rc) break;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(2 * (Nlo / LT_BN)), (unsigned)(n_mt_pad / 2));
+                cfg.blockDim = dim3(LT_THREADS);
+                cfg.dynamicSmemBytes = SP_SMEM;
+                cfg.stream = st;
+                cudaLaunchAttribute cattr[1];
+                cattr[0].id = cudaLaunchAttributeClusterDimension;
+                cattr[0].val.clusterDim.x = 2;
+                cattr[0].val.clusterDim.y = 1;
+                cattr[0].val.clusterDim.z = 1;
+                cfg.attrs = cattr;
+                cfg.numAttrs = 1;
+                cudaLaunchKernelEx(&cfg, lt_gemm_sp_kernel, ma, mb, mb2, me, (int)(Kp / SP_BK), (int)Mhi, (int)Nlo, (int)n_mt,
+                                   (const float*)inv_scale, o);
+                g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
             } else {
                 lt_agen_kernel<<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, e + (size_t)p0 * Se, S, Se, b1, (int)pc, Mhi, Kp,
                                                                       reinterpret_cast<uint32_t*>(A));
@@ -614,7 +906,7 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
             }
         }
     }
-    void* frees[] = {hhi, hlo, e, alimb, amax, A, Bq, Ttab, Etab};
+    void* frees[] = {hhi, hlo, e, alimb, amax, A, Bq, Ttab, Etab, Em};
     for (void* p : frees)
         if (p) cudaFreeAsync(p, st);
     return rc;
