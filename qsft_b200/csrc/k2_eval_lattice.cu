@@ -712,6 +712,231 @@ lt_gemm_sp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+// ---- sparse variant with A' generated straight into tensor memory --------------------------------------------
+// Measured (tools/sp_probe.cu): a sparse MMA pair (N = 256 + N = 128) costs 259 cycles when A' is read from shared memory but
+// 192 = 128 + 64 cycles (the issue floor) when A' sits in tensor memory; tcgen05.cp does not overlap with the MMAs (268).
+// So the four otherwise idle epilogue warps PRODUCE the compressed A' rows and their metadata from the packed phase tables
+// (2 bits per row and support element, L2 resident) and write them with tcgen05.st into a double-buffered TMEM region:
+// A' never exists in HBM or shared memory, the TMA ring carries only the limb operand (48 KB per CTA and stage).
+constexpr int TS_STAGES = 4;
+constexpr int TS_STAGE_BYTES = SP_B01_BYTES + SP_B2_BYTES;       // 48 KB
+constexpr int TS_OFF_B2 = SP_B01_BYTES;
+constexpr size_t TS_SMEM = 1024 + (size_t)TS_STAGES * TS_STAGE_BYTES + 256;
+constexpr uint32_t TS_TMEM_A = 384, TS_TMEM_BUF = 40;            // per buffer: 32 columns of A' (4 k-steps) + 8 of metadata
+
+__device__ __forceinline__ void ts_umma_i8(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t e_tmem, uint32_t idesc,
+                                           uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.sp.cta_group::2.kind::i8 [%0], [%1], %2, [%3], %4, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(e_tmem), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void ts_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void ts_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// sixteen support elements of one A' row: rotations r16 (2 bits each) -> 16 compressed bytes + 8 metadata nibbles
+// (same encoding as lt_agen_sp_kernel)
+__device__ __forceinline__ void ts_expand(uint32_t r16, bool im, uint32_t* a4, uint32_t& e1) {
+    const uint32_t lo = r16 & 0x55555555u, hi = (r16 >> 1) & 0x55555555u;
+    const uint32_t neg = im ? hi : (lo ^ hi);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t m = (((neg >> (8 * g)) & 0x55u) * 0x00041041u) & 0x01010101u;
+        a4[g] = 0x01010101u ^ (m * 0xFEu);
+    }
+    e1 = (lo | 0x88888888u) ^ (im ? 0x55555555u : 0u);
+}
+
+__global__ void __launch_bounds__(LT_THREADS, 1)
+lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2, int nkb, int Mhi, int Nlo,
+                    int n_mtiles, const uint32_t* __restrict__ Ttab, const uint32_t* __restrict__ Etab, int Tw,
+                    const float* __restrict__ inv_scale_ptr, float2* __restrict__ out) {
+    extern __shared__ uint8_t lt_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)lt_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)TS_STAGES * TS_STAGE_BYTES);
+    uint64_t* full = bars;                       // leader only: the limb slabs of both CTAs complete on it
+    uint64_t* empty = bars + TS_STAGES;          // per CTA, released by the leader's multicast commit
+    uint64_t* aready = bars + 2 * TS_STAGES;     // leader only: 2 CTAs x 4 producer warps have written TMEM buffer b
+    uint64_t* tfree = aready + 2;                // per CTA: the MMAs reading TMEM buffer b have completed
+    uint64_t* tfull = tfree + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = sp_cluster_rank();
+    const int ntile = blockIdx.x >> 1;
+    const int mtile = 2 * blockIdx.y + (int)rank;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < TS_STAGES; ++i) {
+            lt_mbar_init(&full[i], 1);
+            lt_mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            lt_mbar_init(&aready[i], 8);
+            lt_mbar_init(&tfree[i], 1);
+        }
+        lt_mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lt_smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    sp_cluster_sync();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int stage = kb % TS_STAGES;
+                const uint32_t ph = (uint32_t)(kb / TS_STAGES) & 1u;
+                lt_mbar_wait(&empty[stage], ph ^ 1u);
+                if (rank == 0) lt_mbar_expect_tx(&full[stage], 2 * TS_STAGE_BYTES);
+                const uint32_t fl = sp_mapa(lt_smem_u32(&full[stage]), 0);
+                uint8_t* st = base + (size_t)stage * TS_STAGE_BYTES;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    sp_tma_2d(st + h * 16384, &tmB, kb * SP_BK + h * 128, (int)rank * Nlo + ntile * LT_BN, fl);
+                    sp_tma_2d(st + TS_OFF_B2 + h * 8192, &tmB2, kb * SP_BK + h * 128, 2 * Nlo + ntile * LT_BN + (int)rank * 64, fl);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc_base = (1u << 2) | (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 4) << 24);
+            constexpr uint32_t idesc256 = idesc_base | ((256u >> 3) << 17);
+            constexpr uint32_t idesc128 = idesc_base | ((128u >> 3) << 17);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int stage = kb % TS_STAGES;
+                const uint32_t ph = (uint32_t)(kb / TS_STAGES) & 1u;
+                const int buf = kb & 1;
+                lt_mbar_wait(&aready[buf], (uint32_t)(kb >> 1) & 1u);
+                lt_mbar_wait(&full[stage], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = lt_smem_u32(base + (size_t)stage * TS_STAGE_BYTES);
+                const uint32_t ta = tmem_base + TS_TMEM_A + TS_TMEM_BUF * (uint32_t)buf, te = ta + 32u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
+                    const uint64_t koff = (uint64_t)(4 * (j & 1));
+                    const uint64_t b01 = lt_desc(sa + (j >> 1) * 16384) + koff;
+                    const uint64_t b2 = lt_desc(sa + TS_OFF_B2 + (j >> 1) * 8192) + koff;
+                    ts_umma_i8(tmem_base, ta + 8u * j, b01, te + 2u * j, idesc256, acc);
+                    ts_umma_i8(tmem_base + 256u, ta + 8u * j, b2, te + 2u * j, idesc128, acc);
+                }
+                sp_commit_pair(&empty[stage]);
+                sp_commit_pair(&tfree[buf]);
+            }
+            sp_commit_pair(tfull);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const bool odd = lane & 1;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        {
+            // A' producer: this thread owns TMEM lane `row` = A' row (p, l_hi, part); per stage 128 support elements =
+            // eight packed words of T[l_hi] and E2[p]; t = (T + E2) mod 4 on sixteen 2-bit fields at once
+            const int mt_eff = mtile < n_mtiles ? mtile : n_mtiles - 1;
+            const long long grow_g = (long long)mt_eff * LT_BM + row;
+            const int pg = (int)(grow_g / (2 * Mhi));
+            const int lhig = (int)(grow_g - (long long)pg * 2 * Mhi) >> 1;
+            const uint4* trow = reinterpret_cast<const uint4*>(Ttab + (size_t)lhig * Tw);
+            const uint4* erow = reinterpret_cast<const uint4*>(Etab + (size_t)pg * Tw);
+            const uint32_t ar0 = sp_mapa(lt_smem_u32(&aready[0]), 0), ar1 = sp_mapa(lt_smem_u32(&aready[1]), 0);
+            uint4 tw0 = trow[0], tw1 = trow[1], ew0 = erow[0], ew1 = erow[1];
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int buf = kb & 1;
+                const uint32_t tw[8] = {tw0.x, tw0.y, tw0.z, tw0.w, tw1.x, tw1.y, tw1.z, tw1.w};
+                const uint32_t ew[8] = {ew0.x, ew0.y, ew0.z, ew0.w, ew1.x, ew1.y, ew1.z, ew1.w};
+                if (kb + 1 < nkb) {
+                    tw0 = trow[2 * (kb + 1)]; tw1 = trow[2 * (kb + 1) + 1];
+                    ew0 = erow[2 * (kb + 1)]; ew1 = erow[2 * (kb + 1) + 1];
+                }
+                uint32_t av[32], ev[8];
+#pragma unroll
+                for (int wi = 0; wi < 8; ++wi) {
+                    constexpr uint32_t H = 0xAAAAAAAAu;
+                    const uint32_t r16 = ((tw[wi] & ~H) + (ew[wi] & ~H)) ^ ((tw[wi] ^ ew[wi]) & H);
+                    ts_expand(r16, odd, &av[4 * wi], ev[wi]);
+                }
+                lt_mbar_wait(&tfree[buf], ((uint32_t)(kb >> 1) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ta = lane_addr + TS_TMEM_A + TS_TMEM_BUF * (uint32_t)buf;
+                ts_st32(ta, av);
+                ts_st8(ta + 32u, ev);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(buf ? ar1 : ar0) : "memory");
+            }
+        }
+        // epilogue (as in the dense kernel)
+        const long long grow = (long long)mtile * LT_BM + row;
+        const int p = (int)(grow / (2 * Mhi));
+        const int lhi = (int)(grow - (long long)p * 2 * Mhi) >> 1;
+        const int llo0 = ntile * LT_BN;
+        const double inv_scale = (double)(*inv_scale_ptr);
+        lt_mbar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (mtile < n_mtiles) {
+            float2* orow = out + ((size_t)p * Mhi + lhi) * Nlo + llo0;
+#pragma unroll 1
+            for (int ch = 0; ch < LT_BN / 16; ++ch) {
+                uint32_t a0[16], a1[16], a2[16];
+                lt_ld16(lane_addr + (uint32_t)(0 * LT_BN + ch * 16), a0);
+                lt_ld16(lane_addr + (uint32_t)(1 * LT_BN + ch * 16), a1);
+                lt_ld16(lane_addr + (uint32_t)(2 * LT_BN + ch * 16), a2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float val[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const long long v = ((long long)(int)a0[j] * 128 + (long long)(int)a1[j]) * 128 + (long long)(int)a2[j];
+                    val[j] = (float)((double)v * inv_scale);
+                }
+                float2 o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float send = odd ? val[j] : val[8 + j];
+                    const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                    o[j] = odd ? make_float2(recv, val[8 + j]) : make_float2(val[j], recv);
+                }
+                float4* dst = reinterpret_cast<float4*>(orow + ch * 16 + (odd ? 8 : 0));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[2 * j].x, o[2 * j].y, o[2 * j + 1].x, o[2 * j + 1].y);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    sp_cluster_sync();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -769,11 +994,13 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     // QSFT_LATTICE_FUSED_A=1 (dense only) generates A' inside the GEMM from packed phase tables instead (no scratch, no HBM
     // round trip; measured: tensor pipe 63 % instead of 90 % busy because the four producer warps cannot keep up, 38.2 ms vs
     // 31.6 + 3.2 ms per block of 41 rows).  The limb operand B' is generated once in all variants.
-    bool fused_a = false, sparse = true;
+    bool fused_a = false;
+    int sparse_mode = 2;                                 // 2: A' generated into TMEM, 1: A' compressed in HBM, 0: dense
     if (const char* env = getenv("QSFT_LATTICE_FUSED_A")) fused_a = atoi(env) != 0;
-    if (const char* env = getenv("QSFT_LATTICE_SPARSE")) sparse = atoi(env) != 0;
-    if (fused_a) sparse = false;
-    const long long kalign = sparse ? SP_BK : LT_BK;
+    if (const char* env = getenv("QSFT_LATTICE_SPARSE")) sparse_mode = atoi(env);
+    if (fused_a || sparse_mode < 0 || sparse_mode > 2) sparse_mode = 0;
+    const bool sparse = sparse_mode == 1, sparse_ts = sparse_mode == 2;
+    const long long kalign = sparse_mode ? SP_BK : LT_BK;
     const long long Kp = (2 * S + kalign - 1) / kalign * kalign;
     const long long Sp = Kp / 2;                        // padded support = compressed bytes per A' row
     double budget_gb = 32.0;
@@ -782,7 +1009,7 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
         if (v > 0.0) budget_gb = v;
     }
     const double per_row = 2.0 * (double)Mhi * (sparse ? 0.625 * (double)Kp : (double)Kp);
-    long long Pc = fused_a ? P : (long long)(budget_gb * 1e9 / per_row);
+    long long Pc = (fused_a || sparse_ts) ? P : (long long)(budget_gb * 1e9 / per_row);
     if (Pc < 1) Pc = 1;
     if (Pc > P) Pc = P;
     while (Pc * 2 * Mhi / LT_BM > 65535) --Pc;          // grid.y limit
@@ -809,7 +1036,7 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     alloc((void**)&amax, 8);
     const long long mt_max = ((Pc * 2 * Mhi / LT_BM) + 1) & ~1ll;      // m-tiles per chunk, padded to whole CTA pairs
     const long long nk128 = Kp / 128;
-    if (fused_a) {
+    if (fused_a || sparse_ts) {
         alloc((void**)&Ttab, (size_t)Mhi * Tw * 4);
         alloc((void**)&Etab, (size_t)P * Tw * 4);
     } else if (sparse) {
@@ -832,24 +1059,25 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
         lt_bgen_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp, reinterpret_cast<uint32_t*>(Bq));
         g_qsft_launches.fetch_add(4, std::memory_order_relaxed);
         const unsigned wb = (unsigned)((Tw + T - 1) / T);
-        if (fused_a) {
+        if (fused_a || sparse_ts) {
             lt_ttab_kernel<<<dim3(wb, (unsigned)Mhi), T, 0, st>>>(hhi, S, b1, Tw, Ttab);
             g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
         }
-        if (fused_a || sparse) {
+        if (fused_a || sparse_mode) {
             lt_etab_kernel<<<dim3(wb, (unsigned)P), T, 0, st>>>(e, S, Se, P, Tw, Etab);
             g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
         }
         CUtensorMap ma, mb, mb2, me;
         rc = lt_make_map(&mb, Bq, LT_LIMBS * Nlo, Kp);
-        if (!rc && sparse) rc = lt_make_map(&mb2, Bq, LT_LIMBS * Nlo, Kp, LT_BK, 64);
+        if (!rc && sparse_mode) rc = lt_make_map(&mb2, Bq, LT_LIMBS * Nlo, Kp, LT_BK, 64);
         ma = mb;   // placeholder when A' is generated in the kernel
         if (!rc) {
             static bool attr = false;
             if (!attr) {
                 if (cudaFuncSetAttribute(lt_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
                     cudaFuncSetAttribute(lt_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
-                    cudaFuncSetAttribute(lt_gemm_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM) != cudaSuccess) {
+                    cudaFuncSetAttribute(lt_gemm_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM) != cudaSuccess ||
+                    cudaFuncSetAttribute(lt_gemm_spts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess) {
                     qsft_set_error("cudaFuncSetAttribute failed");
                     rc = QSFT_ECUDA;
                 }
@@ -863,6 +1091,24 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
             if (fused_a) {
                 lt_gemm_kernel<true><<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo, Ttab,
                                                                         Etab + (size_t)p0 * Tw, (int)Tw, inv_scale, o);
+                g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+            } else if (sparse_ts) {
+                const long long n_mt = pc * 2 * Mhi / LT_BM, n_mt_pad = (n_mt + 1) & ~1ll;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(2 * (Nlo / LT_BN)), (unsigned)(n_mt_pad / 2));
+                cfg.blockDim = dim3(LT_THREADS);
+                cfg.dynamicSmemBytes = TS_SMEM;
+                cfg.stream = st;
+                cudaLaunchAttribute cattr[1];
+                cattr[0].id = cudaLaunchAttributeClusterDimension;
+                cattr[0].val.clusterDim.x = 2;
+                cattr[0].val.clusterDim.y = 1;
+                cattr[0].val.clusterDim.z = 1;
+                cfg.attrs = cattr;
+                cfg.numAttrs = 1;
+                cudaLaunchKernelEx(&cfg, lt_gemm_spts_kernel, mb, mb2, (int)(Kp / SP_BK), (int)Mhi, (int)Nlo, (int)n_mt,
+                                   (const uint32_t*)Ttab, (const uint32_t*)(Etab + (size_t)p0 * Tw), (int)Tw,
+                                   (const float*)inv_scale, o);
                 g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
             } else if (sparse) {
                 const long long n_mt = pc * 2 * Mhi / LT_BM, n_mt_pad = (n_mt + 1) & ~1ll;

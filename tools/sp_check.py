@@ -1,4 +1,5 @@
-"""Debug helper: sparse (tcgen05.mma.sp, CTA pairs) vs dense lattice evaluation on small problems."""
+"""Debug helper: the sparse lattice-evaluation kernels (QSFT_LATTICE_SPARSE=1: compressed A' in HBM, =2: A' generated
+into tensor memory) against the dense kernel (=0) on small problems; all three are exact integer arithmetic."""
 import os
 import sys
 
@@ -10,6 +11,15 @@ from qsft_b200 import ops, utils  # noqa: E402
 
 DEV = torch.device("cuda:0")
 q = 4
+
+
+def run(mode, M, D, loc_d, a_d):
+    os.environ["QSFT_LATTICE_SPARSE"] = str(mode)
+    out = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
+    torch.cuda.synchronize()
+    return out
+
+
 for (n, b, S, P, seed) in [(14, 7, 700, 4, 0), (14, 7, 700, 5, 0), (40, 8, 3000, 3, 1), (40, 10, 257, 2, 2), (33, 7, 1, 1, 4)]:
     rng = np.random.default_rng(seed)
     M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
@@ -18,21 +28,20 @@ for (n, b, S, P, seed) in [(14, 7, 700, 4, 0), (14, 7, 700, 5, 0), (40, 8, 3000,
     ld = utils.padded_ld(n)
     loc_d = ops.pad_digits(loc.T, ld, DEV)
     a_d = torch.from_numpy(a.astype(np.complex64)).to(DEV)
-    os.environ["QSFT_LATTICE_SPARSE"] = "0"
-    dense = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
-    torch.cuda.synchronize()
-    os.environ["QSFT_LATTICE_SPARSE"] = "1"
-    sp = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
-    torch.cuda.synchronize()
-    diff = (sp - dense).abs()
-    B1 = 4 ** (b // 2)
-    d3 = diff.view(P, B1, -1)
-    print(f"n={n} b={b} S={S} P={P}: equal={torch.equal(sp, dense)} max|diff|={diff.max().item():.3e} max|dense|={dense.abs().max().item():.3e}",
-          flush=True)
-    if not torch.equal(sp, dense):
-        bad = (d3 > 0)
-        print("  bad fraction per delay row:", [round(float(bad[p].float().mean()), 3) for p in range(P)])
-        print("  bad fraction per l_lo 64-block:", [round(float(bad[:, :, i * 64:(i + 1) * 64].float().mean()), 3) for i in range(min(8, d3.shape[2] // 64))])
-        print("  bad fraction per l_hi 16-block:", [round(float(bad[:, i * 16:(i + 1) * 16].float().mean()), 3) for i in range(min(8, B1 // 16))])
-        print("  sample sp/dense:", sp[0, :4].tolist(), dense[0, :4].tolist())
+    dense = run(0, M, D, loc_d, a_d)
+    for mode in (1, 2):
+        sp = run(mode, M, D, loc_d, a_d)
+        diff = (sp - dense).abs()
+        B1 = 4 ** (b // 2)
+        d3 = diff.view(P, B1, -1)
+        print(f"mode={mode} n={n} b={b} S={S} P={P}: equal={torch.equal(sp, dense)} max|diff|={diff.max().item():.3e} "
+              f"max|dense|={dense.abs().max().item():.3e}", flush=True)
+        if not torch.equal(sp, dense):
+            bad = (d3 > 0)
+            print("  bad fraction per delay row:", [round(float(bad[p].float().mean()), 3) for p in range(P)])
+            print("  bad fraction per l_lo 64-block:",
+                  [round(float(bad[:, :, i * 64:(i + 1) * 64].float().mean()), 3) for i in range(min(8, d3.shape[2] // 64))])
+            print("  bad fraction per l_hi 16-block:",
+                  [round(float(bad[:, i * 16:(i + 1) * 16].float().mean()), 3) for i in range(min(8, B1 // 16))])
+            print("  sample sp/dense:", sp[0, 0, :3].tolist() if sp.dim() == 3 else sp[0, :3].tolist(), dense[0, :3].tolist())
 print("done")

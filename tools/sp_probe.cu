@@ -30,7 +30,7 @@ __device__ __forceinline__ uint64_t desc_plain(uint32_t saddr, uint32_t lbo, uin
 
 __global__ void __launch_bounds__(128, 1)
 probe_kernel(const uint8_t* __restrict__ Ac /* [128][128] */, const uint8_t* __restrict__ E /* [2][128][16] */,
-             const uint8_t* __restrict__ B /* [128][256] */, int* __restrict__ D /* [128][128] */, int e_lbo) {
+             const uint8_t* __restrict__ B /* [128][256] */, int* __restrict__ D /* [128][128] */, int e_lbo, int ts) {
     extern __shared__ uint8_t raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = base;                 // 16 KB
@@ -75,6 +75,15 @@ probe_kernel(const uint8_t* __restrict__ Ac /* [128][128] */, const uint8_t* __r
             const uint64_t bd = desc_sw128(su32(sB + (j >> 1) * 16384)) + (uint64_t)(4 * (j & 1));     // 64 bytes
             const uint32_t tej = te + 4 * (j >> 1) + 2 * (j & 1);
             const uint32_t acc = j > 0;
+            if (ts) {       // A slice (128 rows x 32 compressed bytes) staged in TMEM columns 144 + 8 j
+                const uint32_t ta = tm + 144 + 8 * j;
+                asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(ta), "l"(ad) : "memory");
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                    "tcgen05.mma.sp.cta_group::1.kind::i8 [%0], [%1], %2, [%3], %4, p;\n\t}" ::"r"(tm),
+                    "r"(ta), "l"(bd), "r"(tej), "r"(idesc), "r"(acc)
+                    : "memory");
+            } else
             asm volatile(
                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
                 "tcgen05.mma.sp.cta_group::1.kind::i8 [%0], %1, %2, [%3], %4, p;\n\t}" ::"r"(tm),
@@ -105,9 +114,10 @@ probe_kernel(const uint8_t* __restrict__ Ac /* [128][128] */, const uint8_t* __r
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256u) : "memory");
 }
 
-// Timing: `iters` back-to-back MMAs on resident operands (results meaningless), cycles per MMA by clock64.
-// mode 0: dense N = 256 (K = 32), 1: sparse N = 256 (K = 64), 2: sparse N = 128, 3: dense N = 128
-__global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int iters, long long* __restrict__ cycles) {
+// Timing: `iters` k-steps, each one N = 256 MMA into columns 0..255 and one N = 128 MMA into columns 256..383 (the
+// production pattern), on resident operands (results meaningless); cycles per k-step by clock64.
+//   sp: sparse (K = 64) or dense (K = 32);  ts: A read from TMEM;  cp: one tcgen05.cp 128x256b of the A slice per k-step
+__global__ void __launch_bounds__(128, 1) rate_kernel(int sp, int ts, int cp, int iters, long long* __restrict__ cycles) {
     extern __shared__ uint8_t raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bar = reinterpret_cast<uint64_t*>(base + 16384 + 65536 + 4096);
@@ -128,24 +138,39 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int iters, long 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm = *slot;
     if (tid == 0) {
-        const uint32_t te = tm + 384;
+        const uint32_t te = tm + 384, ta0 = tm + 400;
         const uint64_t ed = desc_plain(su32(base + 16384 + 65536), 128, 128);
         asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(te), "l"(ed) : "memory");
-        const uint32_t n = (mode == 0 || mode == 1) ? 256u : 128u;
-        const bool sp = (mode == 1 || mode == 2);
-        const uint32_t idesc = (sp ? (1u << 2) : 0u) | (2u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
-        const uint64_t ad = desc_sw128(su32(base)), bd = desc_sw128(su32(base + 16384));
+        const uint64_t ad = desc_sw128(su32(base)), bd = desc_sw128(su32(base + 16384)), bd2 = desc_sw128(su32(base + 16384 + 32768));
+        for (int j = 0; j < 4; ++j) asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(ta0 + 8 * j), "l"(ad + 2 * j) : "memory");
+        const uint32_t ib = (sp ? (1u << 2) : 0u) | (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+        const uint32_t i256 = ib | ((256u >> 3) << 17), i128 = ib | ((128u >> 3) << 17);
         const long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
-            const uint64_t a = ad + (uint64_t)(2 * (it & 3)), b = bd + (uint64_t)((sp ? 4 : 2) * (it & 1));
-            if (sp)
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-                             "tcgen05.mma.sp.cta_group::1.kind::i8 [%0], %1, %2, [%3], %4, p;\n\t}" ::"r"(tm), "l"(a), "l"(b),
-                             "r"(te + 2 * (it & 1)), "r"(idesc), "r"(1u) : "memory");
-            else
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                             "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tm), "l"(a), "l"(b), "r"(idesc), "r"(1u)
-                             : "memory");
+            const uint64_t a = ad + (uint64_t)(2 * (it & 3)), kb = (uint64_t)((sp ? 4 : 2) * (it & 1));
+            const uint32_t ta = ta0 + 8 * (it & 3), tej = te + 2 * (it & 1);
+            if (cp) asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(ta), "l"(a) : "memory");
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t d = tm + (h ? 256u : 0u), idesc = h ? i128 : i256;
+                const uint64_t b = (h ? bd2 : bd) + kb;
+                if (sp && ts)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                                 "tcgen05.mma.sp.cta_group::1.kind::i8 [%0], [%1], %2, [%3], %4, p;\n\t}" ::"r"(d), "r"(ta), "l"(b),
+                                 "r"(tej), "r"(idesc), "r"(1u) : "memory");
+                else if (sp)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                                 "tcgen05.mma.sp.cta_group::1.kind::i8 [%0], %1, %2, [%3], %4, p;\n\t}" ::"r"(d), "l"(a), "l"(b),
+                                 "r"(tej), "r"(idesc), "r"(1u) : "memory");
+                else if (ts)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(ta), "l"(b), "r"(idesc),
+                                 "r"(1u) : "memory");
+                else
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc),
+                                 "r"(1u) : "memory");
+            }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(bar)) : "memory");
         asm volatile(
@@ -194,7 +219,8 @@ int main() {
     cudaMemcpy(dA, Ac.data(), Ac.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 60000);
-    for (int variant = 0; variant < 4; ++variant) {
+    for (int variant = 0; variant < 6; ++variant) {
+        if (variant == 1 || variant == 3) continue;
         // variant bit 0: nibble = idx0 | idx1 << 2 (0) or idx1 | idx0 << 2 (1); bit 1: descriptor LBO 128 (0) or 16 (1)
         std::vector<uint8_t> E(4096, 0);
         for (int m = 0; m < M; ++m)
@@ -206,7 +232,7 @@ int main() {
             }
         cudaMemcpy(dE, E.data(), 4096, cudaMemcpyHostToDevice);
         cudaMemset(dD, 0xff, M * N * 4);
-        probe_kernel<<<1, 128, 60000>>>(dA, dE, dB, dD, (variant & 2) ? 16 : 128);
+        probe_kernel<<<1, 128, 60000>>>(dA, dE, dB, dD, (variant & 2) ? 16 : 128, variant >= 4);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("variant %d: CUDA error %s\n", variant, cudaGetErrorString(e)); return 1; }
         std::vector<int> got(M * N);
@@ -214,26 +240,27 @@ int main() {
         int bad = 0, first = -1;
         for (int i = 0; i < M * N; ++i)
             if (got[i] != ref[i]) { if (first < 0) first = i; ++bad; }
-        printf("variant %d: %d / %d mismatches", variant, bad, M * N);
+        printf("variant %d%s: %d / %d mismatches", variant, variant >= 4 ? " (A via tcgen05.cp in TMEM)" : "", bad, M * N);
         if (first >= 0) printf(" (first at row %d col %d: got %d want %d)", first / N, first % N, got[first], ref[first]);
         printf("\n");
     }
     long long* dc;
     cudaMalloc(&dc, 148 * 8);
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100000);
-    const char* names[4] = {"dense  N=256 K=32", "sparse N=256 K=64", "sparse N=128 K=64", "dense  N=128 K=32"};
     for (int grid : {1, 148})
-        for (int mode = 0; mode < 4; ++mode) {
+        for (int mode = 0; mode < 6; ++mode) {
+            const int sp = mode >= 3, ts = (mode % 3) >= 1, cp = (mode % 3) == 2;
             const int iters = 8192;
-            rate_kernel<<<grid, 128, 100000>>>(mode, iters, dc);
-            rate_kernel<<<grid, 128, 100000>>>(mode, iters, dc);
+            rate_kernel<<<grid, 128, 100000>>>(sp, ts, cp, iters, dc);
+            rate_kernel<<<grid, 128, 100000>>>(sp, ts, cp, iters, dc);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("rate mode %d: CUDA error %s\n", mode, cudaGetErrorString(e)); return 1; }
             long long hc[148];
             cudaMemcpy(hc, dc, grid * 8, cudaMemcpyDeviceToHost);
             long long mx = 0;
             for (int i = 0; i < grid; ++i) mx = hc[i] > mx ? hc[i] : mx;
-            printf("grid %3d %s: %.1f cycles / MMA\n", grid, names[mode], (double)mx / iters);
+            printf("grid %3d %s A from %s%s: %.1f cycles / k-step (N=256 + N=128)\n", grid, sp ? "sparse K=64" : "dense  K=32",
+                   ts ? "TMEM" : "smem", cp ? " + tcgen05.cp per k-step" : "", (double)mx / iters);
         }
     return 0;
 }
