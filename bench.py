@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--n", type=int, default=N_DIM)
     ap.add_argument("--eval-impl", type=int, default=0, help="K2 kernel: 0 auto, 1 SIMT, 2 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--peel-mode", default="auto", choices=["auto", "sharded", "replicated"],
+                    help="multi-GPU peeling: bin-sharded with one all-gather per round, or replicated on every rank")
     return ap.parse_args()
 
 
@@ -190,7 +192,7 @@ def run_ours(a):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         td.init_process_group("nccl", device_id=dev)
-        dist = DistContext()
+        dist = DistContext(peel_mode=a.peel_mode)
 
     def barrier():
         if dist is not None:
@@ -309,11 +311,24 @@ def run_ours(a):
         pass
     bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "2 x measured sustained bf16 (MEASURED_PEAKS.json), no int8 figure measured" if peaks else "2 x fallback 1.4 PF"
+    sparse_mode = int(os.environ.get("QSFT_LATTICE_SPARSE", "2") or 0)
+    if os.environ.get("QSFT_LATTICE_FUSED_A", "0") not in ("", "0") or sparse_mode not in (1, 2):
+        sparse_mode = 0
+    peak_mult = 2.0                                # dense int8 = 2 x bf16
     if "k2_eval_lattice" in kt:
-        # lattice-factorised evaluation: the tensor pipe executes 2 * (2*4^b1) * 4^b2 * (2S) * 3 limbs = 24 int8 ops per
-        # (query, support) pair; the launch also contains the operand-generation kernels
+        # lattice-factorised evaluation: the GEMM is 2 * (2*4^b1) * 4^b2 * (2S) * 3 limbs = 24 (dense-equivalent) int8 ops per
+        # (query, support) pair; the launch also contains the operand-generation kernels.  The default
+        # kernel runs it as a 2:4 structured-sparse MMA (A' has one zero per byte pair): half of those ops are executed and
+        # the matching peak is the sparse int8 rate = 2 x dense int8 = 4 x bf16.
         k2_name, ops_per_pair = "k2_eval_lattice", 24.0
-        k2_desc = "k2_eval_lattice (K=S tcgen05 int8 GEMM, exact +-1/+-i operand x 3-limb int8 operand; 24 int8 ops/pair)"
+        if sparse_mode:
+            peak_mult = 4.0
+            peak_src = peak_src.replace("2 x", "4 x (2:4 sparse int8 = 2 x dense int8 = 4 x bf16)")
+            k2_desc = ("k2_eval_lattice (K=S tcgen05.mma.sp int8 GEMM on CTA pairs, 2:4-sparse exact +-1/+-i operand "
+                       + ("generated in tensor memory" if sparse_mode == 2 else "compressed in HBM")
+                       + " x 3-limb int8 operand; 24 dense-equivalent int8 ops/pair, 12 executed)")
+        else:
+            k2_desc = "k2_eval_lattice (K=S tcgen05 int8 GEMM, exact +-1/+-i operand x 3-limb int8 operand; 24 int8 ops/pair)"
     else:
         k2_name, ops_per_pair = "k2_eval", 2.0 * n
         k2_desc = "k2_eval (tcgen05 int8 contraction K=n + root-of-unity epilogue; 2n int8 ops/pair)"
@@ -323,13 +338,14 @@ def run_ours(a):
     # DRAM traffic of the GEMM launch from the committed ncu capture (same shape only), else null
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_k2l_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", {0: "r1_k2l_traffic.json", 1: "r1_k2l_sparse_hbm_traffic.json",
+                                                            2: "r1_k2l_sparse_traffic.json"}[sparse_mode])))
         if k2_name == "k2_eval_lattice" and a.gpus == 1 and (n, b, S) == (40, 10, 100_000):
             traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
     except Exception:
         pass
     roofline = {"kernel": k2_desc, "bound": "tensor",
-                "achieved": achieved, "peak": 2 * bf16, "unit": "TFLOP/s", "frac": achieved / (2 * bf16),
+                "achieved": achieved, "peak": peak_mult * bf16, "unit": "TFLOP/s", "frac": achieved / (peak_mult * bf16),
                 "traffic": traffic, "peak_source": peak_src, "int8_ops_per_pair": ops_per_pair,
                 "pairs_per_s": k2_pairs / (k2_ms * 1e-3) if k2_ms > 0 else None,
                 "share_of_step": (k2_ms / a.steps) / ms_per_step if ms_per_step else None,
@@ -350,7 +366,9 @@ def run_ours(a):
                    "max_coeff_err": max_err, "eval_impl": a.eval_impl,
                    "parallelism": (f"delay rows sharded over {a.gpus} GPU(s), U exchanged by "
                                    + ("K3 peer stores into symmetric memory (fused all-gather)" if used_symm else "NCCL all-gather")
-                                   + ", bin-sharded peel with one all-gather of finds per round") if a.gpus > 1 else "single GPU"},
+                                   + (", bin-sharded peel with one all-gather of finds per round"
+                                      if dist.shard_peel(8 * G * B) else ", peel replicated on every rank (no collective)"))
+                   if a.gpus > 1 else "single GPU"},
         "e2e": {"value": 1e3 / e2e_ms_per_step, "unit": "transforms/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "result": "host arrays (locations, values); output='arrays'",
                 "value_with_reference_dict_result": 1e3 / e2e_dict_ms_per_step},

@@ -723,6 +723,7 @@ constexpr int TS_STAGE_BYTES = SP_B01_BYTES + SP_B2_BYTES;       // 48 KB
 constexpr int TS_OFF_B2 = SP_B01_BYTES;
 constexpr size_t TS_SMEM = 1024 + (size_t)TS_STAGES * TS_STAGE_BYTES + 256;
 constexpr uint32_t TS_TMEM_A = 384, TS_TMEM_BUF = 40;            // per buffer: 32 columns of A' (4 k-steps) + 8 of metadata
+constexpr int TS_NBUF = 3;                                       // TMEM operand buffers (384 + 3 * 40 = 504 columns)
 
 __device__ __forceinline__ void ts_umma_i8(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t e_tmem, uint32_t idesc,
                                            uint32_t acc) {
@@ -773,8 +774,8 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     uint64_t* full = bars;                       // leader only: the limb slabs of both CTAs complete on it
     uint64_t* empty = bars + TS_STAGES;          // per CTA, released by the leader's multicast commit
     uint64_t* aready = bars + 2 * TS_STAGES;     // leader only: 2 CTAs x 4 producer warps have written TMEM buffer b
-    uint64_t* tfree = aready + 2;                // per CTA: the MMAs reading TMEM buffer b have completed
-    uint64_t* tfull = tfree + 2;
+    uint64_t* tfree = aready + TS_NBUF;          // per CTA: the MMAs reading TMEM buffer b have completed
+    uint64_t* tfull = tfree + TS_NBUF;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -787,7 +788,7 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             lt_mbar_init(&full[i], 1);
             lt_mbar_init(&empty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < TS_NBUF; ++i) {
             lt_mbar_init(&aready[i], 8);
             lt_mbar_init(&tfree[i], 1);
         }
@@ -830,8 +831,8 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             for (int kb = 0; kb < nkb; ++kb) {
                 const int stage = kb % TS_STAGES;
                 const uint32_t ph = (uint32_t)(kb / TS_STAGES) & 1u;
-                const int buf = kb & 1;
-                lt_mbar_wait(&aready[buf], (uint32_t)(kb >> 1) & 1u);
+                const int buf = kb % TS_NBUF;
+                lt_mbar_wait(&aready[buf], (uint32_t)(kb / TS_NBUF) & 1u);
                 lt_mbar_wait(&full[stage], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = lt_smem_u32(base + (size_t)stage * TS_STAGE_BYTES);
@@ -864,10 +865,10 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             const int lhig = (int)(grow_g - (long long)pg * 2 * Mhi) >> 1;
             const uint4* trow = reinterpret_cast<const uint4*>(Ttab + (size_t)lhig * Tw);
             const uint4* erow = reinterpret_cast<const uint4*>(Etab + (size_t)pg * Tw);
-            const uint32_t ar0 = sp_mapa(lt_smem_u32(&aready[0]), 0), ar1 = sp_mapa(lt_smem_u32(&aready[1]), 0);
+            const uint32_t ar0 = sp_mapa(lt_smem_u32(&aready[0]), 0);
             uint4 tw0 = trow[0], tw1 = trow[1], ew0 = erow[0], ew1 = erow[1];
             for (int kb = 0; kb < nkb; ++kb) {
-                const int buf = kb & 1;
+                const int buf = kb % TS_NBUF;
                 const uint32_t tw[8] = {tw0.x, tw0.y, tw0.z, tw0.w, tw1.x, tw1.y, tw1.z, tw1.w};
                 const uint32_t ew[8] = {ew0.x, ew0.y, ew0.z, ew0.w, ew1.x, ew1.y, ew1.z, ew1.w};
                 if (kb + 1 < nkb) {
@@ -881,7 +882,7 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                     const uint32_t r16 = ((tw[wi] & ~H) + (ew[wi] & ~H)) ^ ((tw[wi] ^ ew[wi]) & H);
                     ts_expand(r16, odd, &av[4 * wi], ev[wi]);
                 }
-                lt_mbar_wait(&tfree[buf], ((uint32_t)(kb >> 1) & 1u) ^ 1u);
+                lt_mbar_wait(&tfree[buf], ((uint32_t)(kb / TS_NBUF) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ta = lane_addr + TS_TMEM_A + TS_TMEM_BUF * (uint32_t)buf;
                 ts_st32(ta, av);
@@ -889,8 +890,10 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
+                // relaxed: the TMEM writes are ordered by wait::st + fence::before_thread_sync; a releasing arrive would also
+                // drain the prefetched global loads (measured: MEMBAR.ALL.GPU + ERRBAR = 36 % of all stall samples)
                 if (lane == 0)
-                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(buf ? ar1 : ar0) : "memory");
+                    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ar0 + 8u * (uint32_t)buf) : "memory");
             }
         }
         // epilogue (as in the dense kernel)

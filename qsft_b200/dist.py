@@ -11,9 +11,17 @@ import torch.distributed as td
 
 
 class DistContext:
-    def __init__(self, group=None, symmetric=True):
+    def __init__(self, group=None, symmetric=True, peel_mode="auto", replicate_peel_max_bytes=8 << 30):
+        """peel_mode: "sharded" = bin-sharded peeling loop with one all-gather of the finds per round (peel_sharded);
+        "replicated" = every rank peels its full copy of U with the single-GPU loop (no collective at all; the whole
+        3-round peel of config 5 is 2.7 ms, less than the latency of the per-round exchanges); "auto" = replicated
+        while U is at most `replicate_peel_max_bytes`."""
         if not td.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
+        if peel_mode not in ("auto", "sharded", "replicated"):
+            raise ValueError("peel_mode must be 'auto', 'sharded' or 'replicated'")
+        self.peel_mode = peel_mode
+        self.replicate_peel_max_bytes = int(replicate_peel_max_bytes)
         self.group = group
         self.rank = td.get_rank(group)
         self.world_size = td.get_world_size(group)
@@ -21,6 +29,12 @@ class DistContext:
         # falls back to NCCL all_gather_into_tensor when symmetric memory is not available
         self.symmetric = bool(symmetric) and td.get_backend(group) == "nccl" and self.world_size <= 8
         self._symm_free = {}
+
+    def shard_peel(self, u_bytes):
+        """Whether the peeling loop of a transform whose bins take `u_bytes` is sharded over the ranks."""
+        if self.world_size == 1 or self.peel_mode == "replicated":
+            return False
+        return self.peel_mode == "sharded" or u_bytes > self.replicate_peel_max_bytes
 
     # -- symmetric buffers ---------------------------------------------------------------------------------
     def symm_acquire(self, nfloats, device):

@@ -59,7 +59,10 @@ class QSFT:
                 raise ValueError("reconstruct_method_source='coded' needs source_decoder=get_reed_solomon_dec(n, t, q)")
         prob = ops.PeelProblem(q, n, b, Ms, D, signal.get_source_parity(), channel, source, cutoff, dev, rs=rs)
         dist = getattr(signal, "dist", None)
-        if dist is not None and dist.world_size > 1:
+        shard = dist is not None and dist.world_size > 1
+        if shard and hasattr(dist, "shard_peel"):
+            shard = dist.shard_peel(U.numel() * 8)
+        if shard:
             from .dist import peel_sharded
             n_rounds = peel_sharded(prob, U, dist)[4]
             n_finds = -1

@@ -44,7 +44,10 @@ def _worker(rank, world, port, out):
         and gz[3:].tolist() == [complex(0, v) for v in range(5)]
     ok3 = bin_range(10, 0, 2) == (0, 5) and bin_range(10, 1, 2) == (5, 10) and bin_range(3, 1, 4) == (1, 2) \
         and bin_range(3, 3, 4) == (3, 3)
-    out[rank] = int(ok1 and ok2 and ok3)
+    # peel placement policy: replicated while U is small, sharded above the threshold or on request
+    ok4 = (not ctx.shard_peel(1 << 30)) and ctx.shard_peel(9 << 30) and DistContext(peel_mode="sharded").shard_peel(8) \
+        and not DistContext(peel_mode="replicated").shard_peel(1 << 40) and not ctx.symmetric
+    out[rank] = int(ok1 and ok2 and ok3 and ok4)
     td.destroy_process_group()
 
 

@@ -292,9 +292,13 @@ def test_peel_large_closed_form_exact_recovery():
 
 
 # ---- K2L: lattice-factorised evaluation (q = 4) -----------------------------------------------------------
+@pytest.mark.parametrize("mode", [2, 1, 0])
 @pytest.mark.parametrize("n,b,S,P,seed", [(14, 7, 700, 5, 0), (40, 8, 3000, 3, 1), (40, 10, 257, 2, 2), (20, 9, 64, 4, 3),
                                           (33, 7, 1, 1, 4)])
-def test_k2_lattice_matches_plain_path_and_oracle(n, b, S, P, seed):
+def test_k2_lattice_matches_plain_path_and_oracle(n, b, S, P, seed, mode, monkeypatch):
+    """mode = QSFT_LATTICE_SPARSE: 2 (default) 2:4-sparse A' generated in tensor memory, 1 sparse A' compressed in HBM,
+    0 dense A'."""
+    monkeypatch.setenv("QSFT_LATTICE_SPARSE", str(mode))
     q = 4
     rng = np.random.default_rng(seed)
     M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
@@ -505,11 +509,17 @@ def test_k2_lattice_row_chunking_gives_identical_samples(monkeypatch):
     ld = utils.padded_ld(n)
     loc_d = ops.pad_digits(rng.integers(0, q, (S, n)), ld, DEV)
     a_d = torch.from_numpy(np.exp(1j * rng.uniform(0, 6.28, S)).astype(np.complex64)).to(DEV)
-    whole = ops.eval_synth_lattice(M, D, loc_d, a_d, q)          # default: A' materialised in HBM
-    monkeypatch.setenv("QSFT_LATTICE_FUSED_A", "1")              # A' generated inside the GEMM
+    whole = ops.eval_synth_lattice(M, D, loc_d, a_d, q)          # default: sparse A' generated in tensor memory
+    monkeypatch.setenv("QSFT_LATTICE_FUSED_A", "1")              # dense A' generated inside the GEMM (shared memory)
     fused = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
     monkeypatch.setenv("QSFT_LATTICE_FUSED_A", "0")
-    monkeypatch.setenv("QSFT_LATTICE_SCRATCH_GB", "0.0003")      # 2 * 256 * 1024 B per delay row -> rows in several chunks
-    chunked = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
-    assert torch.equal(whole, chunked)
+    outs = {}
+    for mode in (0, 1):                                          # dense / compressed A' materialised in HBM ...
+        monkeypatch.setenv("QSFT_LATTICE_SPARSE", str(mode))
+        monkeypatch.delenv("QSFT_LATTICE_SCRATCH_GB", raising=False)
+        outs[mode, "whole"] = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
+        monkeypatch.setenv("QSFT_LATTICE_SCRATCH_GB", "0.0003")  # ... <= 2 * 256 * 1024 B per delay row -> rows in several chunks
+        outs[mode, "chunked"] = ops.eval_synth_lattice(M, D, loc_d, a_d, q)
     assert torch.equal(whole, fused)                             # same integer arithmetic -> bit identical
+    for key, val in outs.items():
+        assert torch.equal(whole, val), key
