@@ -427,10 +427,11 @@ int launch_pass_q(float2* x, long long B, int q, const PassPlan& p, long long bl
 }  // namespace
 
 // plain copy of the finished transform to the peers, for the paths whose last pass cannot store remotely itself
-__global__ void k3_bcast_copy_kernel(const float4* __restrict__ x, long long n4, K3Peers peers) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 v = x[i];
-        for (int r = 0; r < peers.n; ++r) reinterpret_cast<float4*>(peers.p[r])[i] = v;
+// (complex64 granularity: rows of odd length q^b are only 8-byte aligned)
+__global__ void k3_bcast_copy_kernel(const float2* __restrict__ x, long long n, K3Peers peers) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 v = x[i];
+        for (int r = 0; r < peers.n; ++r) peers.p[r][i] = v;
     }
 }
 
@@ -502,9 +503,7 @@ static int gwht_impl(float* x, int64_t batch, int q, int b, const K3Peers& peers
         }
     }
     if (peers.n > 0 && !all_fused) {
-        const long long n4 = batch * B / 2;   // float4 = two complex64 (B even or batch*B even required)
-        QSFT_CHECK_ARG((batch * B) % 2 == 0, "peer broadcast needs an even number of complex elements");
-        k3_bcast_copy_kernel<<<(unsigned)(4 * qsft_num_sms()), 256, 0, st>>>(reinterpret_cast<const float4*>(x), n4, peers);
+        k3_bcast_copy_kernel<<<(unsigned)(8 * qsft_num_sms()), 256, 0, st>>>(xx, batch * B, peers);
         QSFT_LAUNCHED();
     }
     return QSFT_OK;
