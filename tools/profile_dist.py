@@ -49,9 +49,16 @@ pr = cProfile.Profile()
 pr.enable()
 out = one(5, "device")
 pr.disable()
-arr = one(6, "arrays")          # collective: every rank takes part
+arrs = [one(6 + i, "arrays") for i in range(4)]          # collective: every rank takes part
+pr2 = cProfile.Profile()
+pr2.enable()
+arrs.append(one(11, "arrays"))
+pr2.disable()
+print(f"rank {rank}: arrays result construct/transform ms", arrs, flush=True)
+td.barrier()
 if rank == 0:
     print("timed (device result)", out)
-    print("arrays result", arr)
-    pstats.Stats(pr).sort_stats("cumtime").print_stats(32)
+    pstats.Stats(pr).sort_stats("cumtime").print_stats(25)
+    print("---- arrays result ----")
+    pstats.Stats(pr2).sort_stats("cumtime").print_stats(30)
 td.destroy_process_group()
