@@ -723,7 +723,8 @@ constexpr int TS_STAGE_BYTES = SP_B01_BYTES + SP_B2_BYTES;       // 48 KB
 constexpr int TS_OFF_B2 = SP_B01_BYTES;
 constexpr size_t TS_SMEM = 1024 + (size_t)TS_STAGES * TS_STAGE_BYTES + 256;
 constexpr uint32_t TS_TMEM_A = 384, TS_TMEM_BUF = 40;            // per buffer: 32 columns of A' (4 k-steps) + 8 of metadata
-constexpr int TS_NBUF = 3;                                       // TMEM operand buffers (384 + 3 * 40 = 504 columns)
+constexpr int TS_NBUF = 3;
+constexpr int TS_THREADS = 320;                                  // warps: 0 TMA, 1 MMA, 2..9 A' producers + epilogue                                       // TMEM operand buffers (384 + 3 * 40 = 504 columns)
 
 __device__ __forceinline__ void ts_umma_i8(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t e_tmem, uint32_t idesc,
                                            uint32_t acc) {
@@ -736,19 +737,17 @@ __device__ __forceinline__ void ts_umma_i8(uint32_t d_tmem, uint32_t a_tmem, uin
         "r"(a_tmem), "l"(bdesc), "r"(e_tmem), "r"(idesc), "r"(acc)
         : "memory");
 }
-__device__ __forceinline__ void ts_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void ts_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+            taddr),
         "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
-        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
-        "r"(r[31])
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
-__device__ __forceinline__ void ts_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+__device__ __forceinline__ void ts_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3])
                  : "memory");
 }
 // sixteen support elements of one A' row: rotations r16 (2 bits each) -> 16 compressed bytes + 8 metadata nibbles
@@ -764,7 +763,7 @@ __device__ __forceinline__ void ts_expand(uint32_t r16, bool im, uint32_t* a4, u
     e1 = (lo | 0x88888888u) ^ (im ? 0x55555555u : 0u);
 }
 
-__global__ void __launch_bounds__(LT_THREADS, 1)
+__global__ void __launch_bounds__(TS_THREADS, 1)
 lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2, int nkb, int Mhi, int Nlo,
                     int n_mtiles, const uint32_t* __restrict__ Ttab, const uint32_t* __restrict__ Etab, int Tw,
                     const float* __restrict__ inv_scale_ptr, float2* __restrict__ out) {
@@ -773,7 +772,7 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)TS_STAGES * TS_STAGE_BYTES);
     uint64_t* full = bars;                       // leader only: the limb slabs of both CTAs complete on it
     uint64_t* empty = bars + TS_STAGES;          // per CTA, released by the leader's multicast commit
-    uint64_t* aready = bars + 2 * TS_STAGES;     // leader only: 2 CTAs x 4 producer warps have written TMEM buffer b
+    uint64_t* aready = bars + 2 * TS_STAGES;     // leader only: 2 CTAs x 8 producer warps have written TMEM buffer b
     uint64_t* tfree = aready + TS_NBUF;          // per CTA: the MMAs reading TMEM buffer b have completed
     uint64_t* tfull = tfree + TS_NBUF;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
@@ -792,7 +791,7 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             lt_mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < TS_NBUF; ++i) {
-            lt_mbar_init(&aready[i], 8);
+            lt_mbar_init(&aready[i], 16);
             lt_mbar_init(&tfree[i], 1);
         }
         lt_mbar_init(tfull, 1);
@@ -855,32 +854,34 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             sp_commit_pair(tfull);
         }
     } else {
-        const int quarter = warp & 3;
+        // two warps per TMEM lane quarter: `half` 0 owns the first 64 support elements of a stage (k-steps 0, 1) and the
+        // first four column chunks of the epilogue, `half` 1 the rest
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const bool odd = lane & 1;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         {
-            // A' producer: this thread owns TMEM lane `row` = A' row (p, l_hi, part); per stage 128 support elements =
-            // eight packed words of T[l_hi] and E2[p]; t = (T + E2) mod 4 on sixteen 2-bit fields at once
+            // A' producer: this thread owns TMEM lane `row` = A' row (p, l_hi, part); per stage 64 support elements =
+            // four packed words of T[l_hi] and E2[p]; t = (T + E2) mod 4 on sixteen 2-bit fields at once
             const int mt_eff = mtile < n_mtiles ? mtile : n_mtiles - 1;
             const long long grow_g = (long long)mt_eff * LT_BM + row;
             const int pg = (int)(grow_g / (2 * Mhi));
             const int lhig = (int)(grow_g - (long long)pg * 2 * Mhi) >> 1;
-            const uint4* trow = reinterpret_cast<const uint4*>(Ttab + (size_t)lhig * Tw);
-            const uint4* erow = reinterpret_cast<const uint4*>(Etab + (size_t)pg * Tw);
+            const uint4* trow = reinterpret_cast<const uint4*>(Ttab + (size_t)lhig * Tw) + half;
+            const uint4* erow = reinterpret_cast<const uint4*>(Etab + (size_t)pg * Tw) + half;
             const uint32_t ar0 = sp_mapa(lt_smem_u32(&aready[0]), 0);
-            uint4 tw0 = trow[0], tw1 = trow[1], ew0 = erow[0], ew1 = erow[1];
+            uint4 tw0 = trow[0], ew0 = erow[0];
             for (int kb = 0; kb < nkb; ++kb) {
                 const int buf = kb % TS_NBUF;
-                const uint32_t tw[8] = {tw0.x, tw0.y, tw0.z, tw0.w, tw1.x, tw1.y, tw1.z, tw1.w};
-                const uint32_t ew[8] = {ew0.x, ew0.y, ew0.z, ew0.w, ew1.x, ew1.y, ew1.z, ew1.w};
+                const uint32_t tw[4] = {tw0.x, tw0.y, tw0.z, tw0.w};
+                const uint32_t ew[4] = {ew0.x, ew0.y, ew0.z, ew0.w};
                 if (kb + 1 < nkb) {
-                    tw0 = trow[2 * (kb + 1)]; tw1 = trow[2 * (kb + 1) + 1];
-                    ew0 = erow[2 * (kb + 1)]; ew1 = erow[2 * (kb + 1) + 1];
+                    tw0 = trow[2 * (kb + 1)];
+                    ew0 = erow[2 * (kb + 1)];
                 }
-                uint32_t av[32], ev[8];
+                uint32_t av[16], ev[4];
 #pragma unroll
-                for (int wi = 0; wi < 8; ++wi) {
+                for (int wi = 0; wi < 4; ++wi) {
                     constexpr uint32_t H = 0xAAAAAAAAu;
                     const uint32_t r16 = ((tw[wi] & ~H) + (ew[wi] & ~H)) ^ ((tw[wi] ^ ew[wi]) & H);
                     ts_expand(r16, odd, &av[4 * wi], ev[wi]);
@@ -888,8 +889,8 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 lt_mbar_wait(&tfree[buf], ((uint32_t)(kb / TS_NBUF) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ta = lane_addr + TS_TMEM_A + TS_TMEM_BUF * (uint32_t)buf;
-                ts_st32(ta, av);
-                ts_st8(ta + 32u, ev);
+                ts_st16(ta + 16u * (uint32_t)half, av);
+                ts_st4(ta + 32u + 4u * (uint32_t)half, ev);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
@@ -910,7 +911,7 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         if (mtile < n_mtiles) {
             float2* orow = out + ((size_t)p * Mhi + lhi) * Nlo + llo0;
 #pragma unroll 1
-            for (int ch = 0; ch < LT_BN / 16; ++ch) {
+            for (int ch = 4 * half; ch < 4 * half + 4; ++ch) {
                 uint32_t a0[16], a1[16], a2[16];
                 lt_ld16(lane_addr + (uint32_t)(0 * LT_BN + ch * 16), a0);
                 lt_ld16(lane_addr + (uint32_t)(1 * LT_BN + ch * 16), a1);
@@ -1102,7 +1103,7 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
                 const long long n_mt = pc * 2 * Mhi / LT_BM, n_mt_pad = (n_mt + 1) & ~1ll;
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3((unsigned)n_mt_pad, (unsigned)(Nlo / LT_BN));
-                cfg.blockDim = dim3(LT_THREADS);
+                cfg.blockDim = dim3(TS_THREADS);
                 cfg.dynamicSmemBytes = TS_SMEM;
                 cfg.stream = st;
                 cudaLaunchAttribute cattr[1];
