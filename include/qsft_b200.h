@@ -82,7 +82,9 @@ int qsft_gwht_batch_bcast(float* x, int64_t batch, int q, int b, float* const* p
 typedef struct {
     int q, n, b;          /* alphabet, signal dimension, subsampling dimension (B = q^b bins per group)            */
     int C, P, P_src;      /* groups, delay rows per group (P = R * P_src), rows of the source delay matrix         */
-    int channel;          /* 0 = identity (noiseless angles, reconstruct.py:12-31), 1 = nso1 (reconstruct.py:100-113) */
+    int channel;          /* 0 = identity (noiseless angles, reconstruct.py:12-31), 1 = nso1 (reconstruct.py:100-113),
+                             2 = nso2 (hard decision, reconstruct.py:116-129 + angle_q utils.py:104-105; the reference's
+                             QSFT.transform hard-codes nso1 at qsft.py:171, so this is only reachable by asking for it)  */
     int source;           /* 0 = identity, 1 = coded (Reed-Solomon syndrome decode, ReedSolomon.py:26-48)          */
     int rs_t, rs_s;       /* coded only: error capability t, extension degree s (P_src = 2*t*s + 1)                */
     int ld;               /* row stride (bytes) of MT, D and find_k digit rows: >= n, multiple of 16, zero padded  */
@@ -137,6 +139,24 @@ int qsft_peel(const qsft_peel_desc* d, float* U, int64_t* find_cj, int8_t* find_
               int32_t* find_round, int32_t* find_id, int64_t max_finds, unsigned long long* counters,
               const qsft_uniq* uq /* may be NULL */, int64_t* n_finds_out, int64_t* n_uniq_out, int* n_rounds_out,
               void* stream);
+
+/* The reference's public detector entry point for a batch of columns.  Replaces reconstruct.singleton_detection
+ * (qsft/reconstruct.py:132-168): channel stage noiseless (:12-31) / nso1 (:100-113) / nso2 (:116-129), then the
+ * optional coded source stage (:34-51 + qsft/ReedSolomon.py:26-48).
+ *   cols (N, P) complex64, one column of U per ROW (element p of column c at cols[c * P + p]), P = R * P_src.
+ *   k_out (N, ld_out) int8: source 0 -> the P_src - 1 detected symbols, source 1 -> the n decoded digits (all zero on
+ *   decoder failure, like galois' unchanged zero codeword); zero padded to ld_out.  n is only read for source 1.   */
+int qsft_singleton_detect(const float* cols, int64_t N, int q, int n, int P, int P_src, int channel, int source,
+                          int rs_t, int rs_s, const int32_t* rs_exp, const int32_t* rs_log, int8_t* k_out, int ld_out,
+                          void* stream);
+
+/* Replaces reconstruct.singleton_detection_mle (qsft/reconstruct.py:54-84) for N columns sharing one candidate set:
+ *   cols (N, P) complex64 as above, S (P, K) complex64 row-major = S_slice (signature of candidate k in column k).
+ *   k_sel[c] = argmin_k || col_c - (<S_k, col_c> / P) S_k ||_2 (first minimum), residual[c] = that norm (may be NULL).
+ * The caller maps k_sel through its `selection` list.  (QSFT.transform in the reference never reaches this detector:
+ * it does not pass selection / S_slice; it is a public function of reconstruct.py and is kept callable.)             */
+int qsft_detect_mle(const float* cols, int64_t N, int P, const float* S, int K, int32_t* k_sel, float* residual,
+                    void* stream);
 
 /* Closed-form bins (verification helper): U[p][j] = sum_{s: M^T k_s = j} a_s w^{<d_p,k_s>}.
  * Used by tests and by the peel benchmark to fill U without sampling.  U (P, B) must be zeroed by the caller. */

@@ -19,7 +19,8 @@ ref_shim.install()
 
 from qsft.qsft import QSFT  # noqa: E402
 from qsft.input_signal_subsampled import SubsampledSignal  # noqa: E402
-from qsft.reconstruct import singleton_detection  # noqa: E402
+from qsft.reconstruct import singleton_detection, singleton_detection_mle  # noqa: E402
+import qsft.qsft as ref_qsft_module  # noqa: E402
 from qsft.utils import qary_vec_to_dec, dec_to_qary_vec, gwht  # noqa: E402
 from synt_exp.synt_src.synthetic_signal import get_random_subsampled_signal, generate_signal_w  # noqa: E402
 
@@ -41,8 +42,11 @@ def pack_result(gw):
 
 
 def run_case(name, seed, n, q, S, b, C, R, src, chan, noise_sd, query_method="complex", max_weight=None,
-             all_bs=None, tr=None, store_samples=True):
-    """Full reference run: construct (sample + FFT) then QSFT.transform; stores every stage."""
+             all_bs=None, tr=None, store_samples=True, nso_subtype=None):
+    """Full reference run: construct (sample + FFT) then QSFT.transform; stores every stage.
+    nso_subtype="nso2": QSFT.transform hard-codes nso_subtype="nso1" (qsft.py:171); the reference's own
+    singleton_detection is wrapped so that this one keyword is replaced -- every line that runs is still the
+    reference's (reconstruct.py:116-129 instead of :100-113)."""
     # the signal object does not keep `strengths`: draw them once with the same seed (generate_signal_w is the
     # first RNG consumer inside get_random_subsampled_signal), then re-seed and build the real thing
     np.random.seed(seed)
@@ -62,7 +66,14 @@ def run_case(name, seed, n, q, S, b, C, R, src, chan, noise_sd, query_method="co
     np.random.set_state(state_before)
     sft = QSFT(num_subsample=tr["num_subsample"], num_repeat=tr["num_repeat"], b=tr["b"],
                reconstruct_method_source=src, reconstruct_method_channel=chan)
-    res = sft.transform(sig, report=True, sort=True)
+    if nso_subtype is not None:
+        orig = ref_qsft_module.singleton_detection
+        ref_qsft_module.singleton_detection = lambda U, **kw: orig(U, **{**kw, "nso_subtype": nso_subtype})
+    try:
+        res = sft.transform(sig, report=True, sort=True)
+    finally:
+        if nso_subtype is not None:
+            ref_qsft_module.singleton_detection = orig
     rng_probe = np.random.random()          # pins RNG consumption order
     keys, vals = pack_result(res["gwht"])
     P_src = sig.Ds[0][0].shape[0]
@@ -81,6 +92,8 @@ def run_case(name, seed, n, q, S, b, C, R, src, chan, noise_sd, query_method="co
         "avg_hw": np.float64(res["avg_hamming_weight"]), "max_hw": np.int64(res["max_hamming_weight"]),
         "rng_probe": np.float64(rng_probe),
     }
+    if nso_subtype is not None:
+        data["nso_subtype"] = nso_subtype
     for bb in sig.all_bs:
         data[f"Us_b{bb}"] = np.array([[sig.Us[i][j][bb] for j in range(R)] for i in range(C)])
     if store_samples:
@@ -139,6 +152,55 @@ def detect_case(name, seed):
     print(f"{name}: ok")
 
 
+def detect_case2(name, seed):
+    """Unit vectors for the two detectors QSFT.transform never selects: nso2 (hard decision, reconstruct.py:116-129)
+    and mle (reconstruct.py:54-84, called directly with selection / S_slice)."""
+    np.random.seed(seed)
+    out = {}
+    for tag, q, p1, R in [("nso2_q4", 4, 9, 3), ("nso2_q3", 3, 8, 5), ("nso2_q5", 5, 7, 2), ("nso2_q2", 2, 13, 4),
+                          ("nso2_q7", 7, 5, 1)]:
+        P = p1 * R
+        cols, ks = [], []
+        for t in range(96):
+            k = np.random.randint(q, size=p1 - 1)
+            base = np.concatenate([[0], k])
+            ph = np.concatenate([(np.random.randint(q) - base) % q for _ in range(R)])
+            amp = np.random.uniform(0.5, 2) * np.exp(1j * np.random.uniform(0, 2 * np.pi))
+            col = amp * np.exp(2j * np.pi * ph / q) + (t % 4) * 0.15 * (np.random.normal(size=P) + 1j * np.random.normal(size=P))
+            cols.append(col)
+            ks.append(singleton_detection(col, method_channel="nso", method_source="identity", q=q,
+                                          source_parity=p1, nso_subtype="nso2"))
+        out[tag + "_cols"] = np.array(cols)
+        out[tag + "_k"] = np.array(ks, dtype=np.int8)
+        out[tag + "_meta"] = np.array([q, p1, R], dtype=np.int64)
+    for tag, q, n, b, P in [("mle_q2", 2, 8, 3, 12), ("mle_q3", 3, 6, 2, 9), ("mle_q4", 4, 5, 2, 10)]:
+        M = np.random.randint(q, size=(n, b))
+        D = np.random.randint(q, size=(P, n))
+        allk = np.array(list(np.ndindex(*([q] * n))), dtype=np.int64).T          # (n, q^n), MSB first
+        hashes = (M.T @ allk) % q
+        j = hashes[:, np.random.randint(allk.shape[1])]                           # a non-empty bin
+        pre = allk[:, np.all(hashes == j[:, None], axis=0)]                       # candidates k with M^T k = j
+        selection = np.array([int(v) for v in qary_vec_to_dec(pre, q)], dtype=np.int64)
+        S_slice = np.exp(2j * np.pi * ((D @ pre) % q) / q)                        # (P, K) signatures under D
+        cols, sel_out, sig_out = [], [], []
+        for t in range(48):
+            true = np.random.randint(pre.shape[1])
+            amp = np.random.uniform(0.5, 2) * np.exp(1j * np.random.uniform(0, 2 * np.pi))
+            col = amp * S_slice[:, true] + (t % 4) * 0.2 * (np.random.normal(size=P) + 1j * np.random.normal(size=P))
+            ksel, sig = singleton_detection_mle(col, selection=selection, S_slice=S_slice, q=q, source_parity=P)
+            cols.append(col)
+            sel_out.append(int(ksel))
+            sig_out.append(sig)
+        out[tag + "_cols"] = np.array(cols)
+        out[tag + "_selection"] = selection
+        out[tag + "_S"] = S_slice
+        out[tag + "_ksel"] = np.array(sel_out, dtype=np.int64)
+        out[tag + "_sig"] = np.array(sig_out)
+        out[tag + "_meta"] = np.array([q, n, b, P], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: ok")
+
+
 def gwht_case(name, seed):
     np.random.seed(seed)
     out = {}
@@ -152,6 +214,13 @@ def gwht_case(name, seed):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--detectors" in sys.argv:      # only the fixtures added for nso2 / mle (the others stay byte-identical)
+        detect_case2("detect_units2", 12)
+        run_case("q4_n10_b4_nso2_noisy", 13, n=10, q=4, S=40, b=4, C=3, R=3, src="identity", chan="nso", noise_sd=0.3,
+                 nso_subtype="nso2", store_samples=False)
+        run_case("q3_n9_b3_nso2", 14, n=9, q=3, S=20, b=3, C=3, R=2, src="identity", chan="nso", noise_sd=0.0,
+                 nso_subtype="nso2", store_samples=False)
+        sys.exit(0)
     # BASELINE config 1 (seed 20 = quick_example convention)
     run_case("cfg1_q4_n10_b4_identity", 20, n=10, q=4, S=100, b=4, C=3, R=1, src="identity", chan="identity", noise_sd=0.0)
     # config-2 shaped, reduced: nso R=3, 20 dB  (noise_sd = sqrt(S / 10^(SNR/10)))

@@ -297,14 +297,44 @@ def detect_nso1(cols, q, p1):
     return out
 
 
-def singleton_detection(cols, q, method_channel, method_source, source_parity, source_decoder=None):
-    """reconstruct.py:132-168 for a batch of columns.  Returns k (n, nb)."""
+def angle_q(x, q):
+    """Quantised angle: index of the q-th root of unity nearest to x.  qsft/utils.py:104-105 (float floor divisions)."""
+    return (((np.angle(x) % TWO_PI // (np.pi / q)) + 1) // 2) % q
+
+
+def detect_nso2(cols, q, p1):
+    """Hard-decision NSO: cols (R*p1, nb) -> symbols (p1-1, nb).  reconstruct.py:116-129: every repeat votes with its
+    quantised phase difference, the votes are averaged AS NUMBERS (not circularly), np.round is half-to-even, and the
+    float result is truncated into the int array."""
+    a0 = angle_q(cols[0::p1], q)
+    out = np.zeros((p1 - 1, cols.shape[1]), dtype=int)
+    for i in range(1, p1):
+        a = angle_q(cols[i::p1], q)
+        out[i - 1] = (np.round(np.mean((a0 - a) % q, axis=0)) % q).astype(int)
+    return out
+
+
+def detect_mle(col, selection, S_slice):
+    """reconstruct.py:54-84 for ONE column (P,): least-squares amplitude for every candidate signature (columns of
+    S_slice, (P, K)), residual 2-norms, first minimum.  Returns (selection[k_sel], S_slice[:, k_sel], k_sel).
+    The reference can only be called directly (QSFT.transform never passes selection / S_slice)."""
+    P = S_slice.shape[0]
+    alphas = 1 / P * np.dot(np.conjugate(S_slice).T, col)
+    residuals = np.linalg.norm(col - (alphas * S_slice).T, ord=2, axis=1)
+    k_sel = int(np.argmin(residuals))
+    return selection[k_sel], S_slice[:, k_sel], k_sel
+
+
+def singleton_detection(cols, q, method_channel, method_source, source_parity, source_decoder=None,
+                        nso_subtype="nso1"):
+    """reconstruct.py:132-168 for a batch of columns.  Returns k (n, nb).  `mle` needs per-column candidate lists and
+    is exposed separately (detect_mle)."""
     if method_channel == "identity":
         sym = detect_noiseless(cols, q)
     elif method_channel == "nso":
-        sym = detect_nso1(cols, q, source_parity)
+        sym = detect_nso1(cols, q, source_parity) if nso_subtype == "nso1" else detect_nso2(cols, q, source_parity)
     else:
-        raise NotImplementedError("mle is unreachable from QSFT.transform in the reference (SURVEY a15)")
+        raise NotImplementedError("mle is unreachable from QSFT.transform in the reference (SURVEY a15): use detect_mle")
     if method_source == "identity":
         return sym
     if method_source == "coded":
@@ -318,8 +348,9 @@ def singleton_detection(cols, q, method_channel, method_source, source_parity, s
 # ----------------------------------------------------------------------------------------------------------
 def transform(signal, num_subsample, num_repeat, b, reconstruct_method_source="identity",
               reconstruct_method_channel="identity", source_decoder=None, report=False, sort=False,
-              cutoff=None, trace=None):
-    """QSFT.transform.  `trace`, if a list, receives per-round dicts (singletons / multitons / peeled) for tests."""
+              cutoff=None, trace=None, nso_subtype="nso1"):
+    """QSFT.transform.  `trace`, if a list, receives per-round dicts (singletons / multitons / peeled) for tests.
+    `nso_subtype` is hard-coded to "nso1" in the reference (qsft.py:171); "nso2" selects reconstruct.py:116-129."""
     q, n = signal.q, signal.n
     omega = np.exp(2j * np.pi / q)
     Ms, Ds, Us, _ = signal.get_MDU(num_subsample, num_repeat, b, trans_times=True)   # qsft.py:111
@@ -345,7 +376,7 @@ def transform(signal, num_subsample, num_repeat, b, reconstruct_method_source="i
                 continue
             cols = U[:, js]
             K = singleton_detection(cols, q, reconstruct_method_channel, reconstruct_method_source, p1,
-                                    source_decoder)                                   # :165-173
+                                    source_decoder, nso_subtype)                                   # :165-173
             sig = omega ** (D @ K)                                                     # :174
             rho = np.sum(np.conjugate(sig) * cols, axis=0) / P                         # :175
             res = np.sum(np.abs(cols - rho * sig) ** 2, axis=0)                        # :176

@@ -203,6 +203,95 @@ __device__ bool rs_decode(const PeelDev& d, const uint8_t* sym, uint8_t* kout) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// singleton detection: symbol i (1 <= i < P_src) of one column; element p of the column is col[p * stride].
+//   channel 0: noiseless angles (reconstruct.py:12-31), channel 1: nso1 soft decision (reconstruct.py:100-113),
+//   channel 2: nso2 hard decision (reconstruct.py:116-129 + angle_q, utils.py:104-105).
+// ---------------------------------------------------------------------------------------------------------
+// angle_q: (((angle mod 2 pi) // (pi / q)) + 1) // 2 mod q in fp64 like NumPy (np.angle of a complex128 holding the
+// fp32 value; the float floor divisions are exact small integers)
+__device__ __forceinline__ int angle_q_dev(float2 v, int q) {
+    double a = atan2((double)v.y, (double)v.x);
+    if (a < 0.0) a += kTwoPi;                      // numpy: angle % (2 pi)
+    if (a >= kTwoPi) a -= kTwoPi;
+    const long long sector = (long long)floor(a / (3.14159265358979323846 / (double)q));
+    return (int)(((sector + 1) >> 1) % q);
+}
+
+__device__ __forceinline__ int detect_symbol(const PeelDev& d, const float2* __restrict__ col, size_t stride, int i) {
+    const double qd = (double)d.q;
+    int symv;
+    if (d.channel == 0) {
+        const float2 v0 = col[0];
+        const float2 v = col[(size_t)i * stride];
+        symv = -1;
+        // fast path in fp32; anything within 0.01 of a rounding boundary is redone in fp64 so the decision
+        // always equals the fp64 one (np.angle / np.round in the reference)
+        if (fabsf(v0.x) + fabsf(v0.y) > 1e-30f && fabsf(v.x) + fabsf(v.y) > 1e-30f) {
+            const float u = (float)d.q * (atan2f(v.y, v.x) - atan2f(v0.y, v0.x)) * 0.15915494309189535f;
+            const float m = rintf(u);
+            if (fabsf(u - m) < 0.49f) {
+                int mi = (int)m;                    // |u| < q  =>  m in [-q, q]
+                mi = mi < 0 ? mi + d.q : mi;
+                symv = mi >= d.q ? mi - d.q : mi;
+            }
+        }
+        if (symv < 0) {
+            const double a0 = atan2((double)v0.y, (double)v0.x);
+            const double a = atan2((double)v.y, (double)v.x);
+            const long long r = (long long)rint(qd * (a - a0) / kTwoPi);    // half-to-even like np.round
+            const int m = (int)(r % d.q);
+            symv = m < 0 ? m + d.q : m;
+        }
+    } else if (d.channel == 1) {
+        double ar = 0.0, ai = 0.0;
+        for (int r = 0; r < d.R; ++r) {
+            const float2 z = col[(size_t)(r * d.P_src) * stride];
+            const float2 v = col[(size_t)(r * d.P_src + i) * stride];
+            ar += (double)z.x * v.x + (double)z.y * v.y;                     // z * conj(v)
+            ai += (double)z.y * v.x - (double)z.x * v.y;
+        }
+        // np.mean divides by R > 0: the angle does not depend on it
+        symv = -1;
+        const float arf = (float)ar, aif = (float)ai;
+        if (fabsf(arf) + fabsf(aif) > 1e-30f) {
+            float thf = atan2f(aif, arf);
+            if (thf < 0.f) thf += 6.283185307179586f;
+            const float u = thf * (float)d.q * 0.15915494309189535f;        // in [0, q]
+            const float m = rintf(u);
+            if (fabsf(u - m) < 0.49f) symv = ((int)m >= d.q) ? (int)m - d.q : (int)m;   // nearest of the q+1 roots, mod q
+        }
+        if (symv < 0) {
+            double th = atan2(ai, ar);
+            if (th < 0.0) th += kTwoPi;                                      // numpy: angle % (2 pi)
+            if (th >= kTwoPi) th -= kTwoPi;
+            const double step = kTwoPi / qd;
+            int best = 0;
+            double bd = fabs(0.0 - th);
+            for (int m = 1; m <= d.q; ++m) {                                 // argmin over q+1 roots, first minimum
+                const double dist = fabs(step * (double)m - th);
+                if (dist < bd) {
+                    bd = dist;
+                    best = m;
+                }
+            }
+            symv = best % d.q;
+        }
+    } else {
+        // nso2: every repeat votes with its quantised phase difference; the votes are averaged as numbers, np.round is
+        // half-to-even; the sum of R small integers and the division by R are exact / correctly rounded like np.mean
+        long long votes = 0;
+        for (int r = 0; r < d.R; ++r) {
+            const int a0 = angle_q_dev(col[(size_t)(r * d.P_src) * stride], d.q);
+            const int a = angle_q_dev(col[(size_t)(r * d.P_src + i) * stride], d.q);
+            int df = a0 - a;
+            votes += df < 0 ? df + d.q : df;
+        }
+        symv = (int)((long long)rint((double)votes / (double)d.R) % d.q);
+    }
+    return symv;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // classification.  Phase 1: one THREAD per bin computes the energy (lanes over consecutive bins -> coalesced row
 // reads; this is the HBM-bound part).  Phase 2: the WARP walks over its non-zeroton bins one at a time with lanes
 // over the delay rows (the rows were just read, so these loads hit L1/L2): all P_src-1 symbols are detected in
@@ -250,7 +339,6 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
     if (mask == 0) return;
 
     const int nsym = d.P_src - 1;
-    const double qd = (double)d.q;
     const int8_t* Dc = d.D + (size_t)c * d.P * d.ld;
     unsigned n_multi = 0;
     while (mask) {
@@ -264,64 +352,7 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
         for (int i0 = 1; i0 <= nsym; i0 += 32) {
             const int i = i0 + lane;
             if (i <= nsym) {
-                int symv;
-                if (d.channel == 0) {
-                    const float2 v0 = col[0];
-                    const float2 v = col[(size_t)i * B];
-                    symv = -1;
-                    // fast path in fp32; anything within 0.01 of a rounding boundary is redone in fp64 so the decision
-                    // always equals the fp64 one (np.angle / np.round in the reference)
-                    if (fabsf(v0.x) + fabsf(v0.y) > 1e-30f && fabsf(v.x) + fabsf(v.y) > 1e-30f) {
-                        const float u = (float)d.q * (atan2f(v.y, v.x) - atan2f(v0.y, v0.x)) * 0.15915494309189535f;
-                        const float m = rintf(u);
-                        if (fabsf(u - m) < 0.49f) {
-                            int mi = (int)m;                    // |u| < q  =>  m in [-q, q]
-                            mi = mi < 0 ? mi + d.q : mi;
-                            symv = mi >= d.q ? mi - d.q : mi;
-                        }
-                    }
-                    if (symv < 0) {
-                        const double a0 = atan2((double)v0.y, (double)v0.x);
-                        const double a = atan2((double)v.y, (double)v.x);
-                        const long long r = (long long)rint(qd * (a - a0) / kTwoPi);    // half-to-even like np.round
-                        const int m = (int)(r % d.q);
-                        symv = m < 0 ? m + d.q : m;
-                    }
-                } else {
-                    double ar = 0.0, ai = 0.0;
-                    for (int r = 0; r < d.R; ++r) {
-                        const float2 z = col[(size_t)(r * d.P_src) * B];
-                        const float2 v = col[(size_t)(r * d.P_src + i) * B];
-                        ar += (double)z.x * v.x + (double)z.y * v.y;                     // z * conj(v)
-                        ai += (double)z.y * v.x - (double)z.x * v.y;
-                    }
-                    // np.mean divides by R > 0: the angle does not depend on it
-                    symv = -1;
-                    const float arf = (float)ar, aif = (float)ai;
-                    if (fabsf(arf) + fabsf(aif) > 1e-30f) {
-                        float thf = atan2f(aif, arf);
-                        if (thf < 0.f) thf += 6.283185307179586f;
-                        const float u = thf * (float)d.q * 0.15915494309189535f;        // in [0, q]
-                        const float m = rintf(u);
-                        if (fabsf(u - m) < 0.49f) symv = ((int)m >= d.q) ? (int)m - d.q : (int)m;   // nearest of the q+1 roots, mod q
-                    }
-                    if (symv < 0) {
-                        double th = atan2(ai, ar);
-                        if (th < 0.0) th += kTwoPi;                                      // numpy: angle % (2 pi)
-                        if (th >= kTwoPi) th -= kTwoPi;
-                        const double step = kTwoPi / qd;
-                        int best = 0;
-                        double bd = fabs(0.0 - th);
-                        for (int m = 1; m <= d.q; ++m) {                                 // argmin over q+1 roots, first minimum
-                            const double dist = fabs(step * (double)m - th);
-                            if (dist < bd) {
-                                bd = dist;
-                                best = m;
-                            }
-                        }
-                        symv = best % d.q;
-                    }
-                }
+                const int symv = detect_symbol(d, col, (size_t)B, i);
                 s_sym[warp][i - 1] = (uint8_t)symv;
             }
         }
@@ -524,6 +555,84 @@ k4_reduce_kernel(PeelDev d, const long long* __restrict__ find_cj, const int8_t*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// stand-alone detectors (the reference's public reconstruct.singleton_detection for a batch of columns): one warp
+// per column, lanes over the symbols exactly as in phase 2 of the classification.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K4_THREADS)
+k4_detect_kernel(PeelDev d, const float2* __restrict__ cols, long long N, int8_t* __restrict__ k_out, int ld_out) {
+    __shared__ __align__(16) uint8_t s_sym[K4_THREADS / 32][QSFT_MAX_N];
+    __shared__ __align__(16) uint8_t s_k[K4_THREADS / 32][QSFT_MAX_N];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long c = (long long)blockIdx.x * (K4_THREADS / 32) + warp;
+    if (c >= N) return;                                     // whole warps leave together
+    const float2* col = cols + (size_t)c * d.P;             // element p of the column = col[p]
+    const int nsym = d.P_src - 1;
+    for (int i = 1 + lane; i <= nsym; i += 32) s_sym[warp][i - 1] = (uint8_t)detect_symbol(d, col, 1, i);
+    __syncwarp();
+    int nout = nsym;
+    const uint8_t* src = s_sym[warp];
+    if (d.source == 1) {
+        if (lane == 0) rs_decode(d, s_sym[warp], s_k[warp]);
+        __syncwarp();
+        nout = d.n;
+        src = s_k[warp];
+    }
+    int8_t* ko = k_out + (size_t)c * ld_out;
+    for (int i = lane; i < ld_out; i += 32) ko[i] = i < nout ? (int8_t)src[i] : (int8_t)0;
+}
+
+// singleton_detection_mle (reconstruct.py:54-84): one warp per column, lanes over the K candidate signatures.
+//   alpha_k = <S_k, col> / P,  residual_k = || col - alpha_k S_k ||_2,  k_sel = first minimum.  fp64 accumulation.
+__global__ void __launch_bounds__(K4_THREADS)
+k4_mle_kernel(const float2* __restrict__ cols, long long N, int P, const float2* __restrict__ S, int K,
+              int32_t* __restrict__ k_sel, float* __restrict__ residual) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long c = (long long)blockIdx.x * (K4_THREADS / 32) + warp;
+    if (c >= N) return;
+    const float2* col = cols + (size_t)c * P;
+    double best = 1.0e300;                                   // > any residual of finite fp32 data
+    int best_k = 0x7fffffff;
+    const double invP = 1.0 / (double)P;
+    for (int k = lane; k < K; k += 32) {
+        double ar = 0.0, ai = 0.0;
+        for (int p = 0; p < P; ++p) {
+            const float2 sg = S[(size_t)p * K + k];
+            const float2 v = col[p];
+            ar += (double)sg.x * v.x + (double)sg.y * v.y;  // conj(sg) * v
+            ai += (double)sg.x * v.y - (double)sg.y * v.x;
+        }
+        ar *= invP;
+        ai *= invP;
+        double r2 = 0.0;
+        for (int p = 0; p < P; ++p) {
+            const float2 sg = S[(size_t)p * K + k];
+            const float2 v = col[p];
+            const double er = (double)v.x - (ar * sg.x - ai * sg.y);
+            const double ei = (double)v.y - (ar * sg.y + ai * sg.x);
+            r2 += er * er + ei * ei;
+        }
+        const double r = sqrt(r2);
+        if (r < best) {                                      // ascending k per lane: strict < keeps the first minimum
+            best = r;
+            best_k = k;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+        if (ob < best || (ob == best && ok < best_k)) {
+            best = ob;
+            best_k = ok;
+        }
+    }
+    if (lane == 0) {
+        k_sel[c] = best_k;
+        if (residual) residual[c] = (float)best;
+    }
+}
+
 __global__ void k4_closed_form_kernel(const int8_t* __restrict__ MT, const int8_t* __restrict__ D, int q, int n, int b,
                                       int P, long long B, int ld, const int8_t* __restrict__ loc,
                                       const float2* __restrict__ a, long long S, float2* __restrict__ U) {
@@ -556,7 +665,7 @@ int make_dev(const qsft_peel_desc* h, PeelDev* d) {
     QSFT_CHECK_ARG(h->b >= 1 && h->b <= QSFT_MAX_B, "b=%d out of range", h->b);
     QSFT_CHECK_ARG(h->C >= 1 && h->C <= 65535, "C=%d out of range", h->C);
     QSFT_CHECK_ARG(h->P_src >= 2 && h->P >= h->P_src && h->P % h->P_src == 0, "P=%d must be a positive multiple of P_src=%d", h->P, h->P_src);
-    QSFT_CHECK_ARG(h->channel == 0 || h->channel == 1, "channel must be 0 (identity) or 1 (nso)");
+    QSFT_CHECK_ARG(h->channel >= 0 && h->channel <= 2, "channel must be 0 (identity), 1 (nso1) or 2 (nso2)");
     QSFT_CHECK_ARG(h->source == 0 || h->source == 1, "source must be 0 (identity) or 1 (coded)");
     QSFT_CHECK_ARG(h->ld >= h->n && h->ld % 16 == 0 && h->ld <= 128, "ld=%d must be >= n, a multiple of 16 and <= 128", h->ld);
     QSFT_CHECK_ARG(h->MT && h->D, "null M/D");
@@ -772,6 +881,47 @@ extern "C" int qsft_peel(const qsft_peel_desc* h, float* U, int64_t* find_cj, in
     }
     *n_finds_out = total;
     *n_rounds_out = round;
+    return QSFT_OK;
+}
+
+extern "C" int qsft_singleton_detect(const float* cols, int64_t N, int q, int n, int P, int P_src, int channel, int source,
+                                     int rs_t, int rs_s, const int32_t* rs_exp, const int32_t* rs_log, int8_t* k_out,
+                                     int ld_out, void* stream) {
+    QSFT_CHECK_ARG(N >= 0 && N <= 0x7fffffffll * (K4_THREADS / 32), "N=%lld out of range", (long long)N);
+    QSFT_CHECK_ARG(N == 0 || (cols && k_out), "null pointer");
+    QSFT_CHECK_ARG(q >= 2 && q <= QSFT_MAX_Q, "q=%d out of range", q);
+    QSFT_CHECK_ARG(P_src >= 2 && P_src - 1 <= QSFT_MAX_N && P >= P_src && P % P_src == 0,
+                   "P=%d must be a positive multiple of P_src=%d (2 <= P_src <= %d)", P, P_src, QSFT_MAX_N + 1);
+    QSFT_CHECK_ARG(channel >= 0 && channel <= 2, "channel must be 0 (identity), 1 (nso1) or 2 (nso2)");
+    QSFT_CHECK_ARG(source == 0 || source == 1, "source must be 0 (identity) or 1 (coded)");
+    if (channel == 0) QSFT_CHECK_ARG(P == P_src, "identity channel decoding needs num_repeat == 1");
+    PeelDev d{};
+    d.q = q; d.n = source ? n : P_src - 1; d.P = P; d.P_src = P_src; d.R = P / P_src; d.channel = channel; d.source = source;
+    if (source == 1) {
+        QSFT_CHECK_ARG(n >= 1 && n <= QSFT_MAX_N, "n=%d out of range", n);
+        QSFT_CHECK_ARG(rs_t >= 1 && 2 * rs_t <= RS_MAX_2T && rs_s >= 1 && P_src - 1 == 2 * rs_t * rs_s, "coded source needs P_src = 2ts + 1");
+        QSFT_CHECK_ARG(rs_exp && rs_log, "null GF tables");
+        d.rs_t = rs_t; d.rs_s = rs_s; d.rs_exp = rs_exp; d.rs_log = rs_log; d.rs_order = (int)ipow64(q, rs_s);
+    }
+    QSFT_CHECK_ARG(ld_out >= d.n, "ld_out=%d smaller than the %d output digits", ld_out, d.n);
+    if (N == 0) return QSFT_OK;
+    const int wpb = K4_THREADS / 32;
+    k4_detect_kernel<<<(unsigned)((N + wpb - 1) / wpb), K4_THREADS, 0, (cudaStream_t)stream>>>(
+        d, reinterpret_cast<const float2*>(cols), N, k_out, ld_out);
+    QSFT_LAUNCHED();
+    return QSFT_OK;
+}
+
+extern "C" int qsft_detect_mle(const float* cols, int64_t N, int P, const float* S, int K, int32_t* k_sel, float* residual,
+                               void* stream) {
+    QSFT_CHECK_ARG(N >= 0 && N <= 0x7fffffffll * (K4_THREADS / 32), "N=%lld out of range", (long long)N);
+    QSFT_CHECK_ARG(N == 0 || (cols && S && k_sel), "null pointer");
+    QSFT_CHECK_ARG(P >= 1 && K >= 1, "P=%d and K=%d must be positive", P, K);
+    if (N == 0) return QSFT_OK;
+    const int wpb = K4_THREADS / 32;
+    k4_mle_kernel<<<(unsigned)((N + wpb - 1) / wpb), K4_THREADS, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(cols), N, P, reinterpret_cast<const float2*>(S), K, k_sel, residual);
+    QSFT_LAUNCHED();
     return QSFT_OK;
 }
 

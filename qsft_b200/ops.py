@@ -205,11 +205,72 @@ def gwht_batch_bcast_(x, q, b, peer_ptrs):
     return x
 
 
+def channel_code(channel, nso_subtype="nso1"):
+    """reconstruct_method_channel (+ nso_subtype) -> the C ABI's channel code (qsft_peel_desc.channel)."""
+    if channel == "identity":
+        return 0
+    if channel == "nso":
+        if nso_subtype not in ("nso1", "nso2"):
+            raise ValueError(f"nso_subtype={nso_subtype!r} (nso1 | nso2)")
+        return 1 if nso_subtype == "nso1" else 2
+    if channel == "mle":
+        raise NotImplementedError("reconstruct_method_channel='mle' cannot run inside QSFT.transform (the reference never "
+                                  "passes selection / S_slice, qsft.py:165-173); call reconstruct.singleton_detection_mle")
+    raise NotImplementedError(f"reconstruct_method_channel={channel!r} is not supported (identity | nso)")
+
+
+def singleton_detect(cols, q, P_src, channel, source="identity", n=None, rs=None, nso_subtype="nso1"):
+    """Batch form of reconstruct.singleton_detection: cols (N, P) complex64 CUDA tensor, one column of U per row ->
+    int8 (N, n_out) digits (n_out = P_src - 1 symbols for source "identity", n decoded digits for "coded")."""
+    _need_cuda(cols)
+    if cols.dtype != torch.complex64 or cols.dim() != 2:
+        raise ValueError("cols must be a (N, P) complex64 tensor")
+    N, P = cols.shape
+    chan = channel_code(channel, nso_subtype)
+    dev = cols.device
+    rs_exp = rs_log = None
+    rs_t = rs_s = 0
+    if source == "coded":
+        if rs is None or n is None:
+            raise ValueError("coded source decoding needs the ReedSolomon object and n")
+        e, l = rs.device_tables()
+        rs_exp, rs_log = torch.from_numpy(e).to(dev), torch.from_numpy(l).to(dev)
+        rs_t, rs_s = rs.t, rs.s
+        n_out = int(n)
+    elif source == "identity":
+        n_out = P_src - 1
+    else:
+        raise NotImplementedError(f"reconstruct_method_source={source!r} is not supported (identity | coded)")
+    out = torch.empty((N, n_out), dtype=torch.int8, device=dev)
+    with torch.cuda.device(dev), _timed("k4_detect", N * P):
+        _lib.check(_lib.lib().qsft_singleton_detect(_ptr(cols), N, q, n_out, P, P_src, chan, 1 if source == "coded" else 0,
+                                                    rs_t, rs_s, _ptr(rs_exp), _ptr(rs_log), _ptr(out), n_out, _stream()))
+    return out
+
+
+def detect_mle(cols, S_slice):
+    """reconstruct.singleton_detection_mle for N columns sharing one candidate set: cols (N, P), S_slice (P, K) complex64
+    CUDA tensors -> (k_sel int32 (N,), residual float32 (N,))."""
+    _need_cuda(cols, S_slice)
+    if cols.dtype != torch.complex64 or S_slice.dtype != torch.complex64 or cols.dim() != 2 or S_slice.dim() != 2:
+        raise ValueError("cols (N, P) and S_slice (P, K) must be complex64 tensors")
+    N, P = cols.shape
+    if S_slice.shape[0] != P or S_slice.shape[1] < 1:
+        raise ValueError("S_slice must have one row per delay and at least one candidate")
+    k_sel = torch.empty(N, dtype=torch.int32, device=cols.device)
+    res = torch.empty(N, dtype=torch.float32, device=cols.device)
+    with torch.cuda.device(cols.device), _timed("k4_mle", N * P * S_slice.shape[1]):
+        _lib.check(_lib.lib().qsft_detect_mle(_ptr(cols), N, P, _ptr(S_slice), S_slice.shape[1], _ptr(k_sel), _ptr(res),
+                                              _stream()))
+    return k_sel, res
+
+
 class PeelProblem:
     """Device-side description of one peeling problem (qsft_peel_desc) + its workspaces."""
 
-    def __init__(self, q, n, b, Ms, Ds, P_src, channel, source, cutoff, device, rs=None):
-        """Ms: list of C (n, b) arrays; Ds: array (C, P, n)."""
+    def __init__(self, q, n, b, Ms, Ds, P_src, channel, source, cutoff, device, rs=None, nso_subtype="nso1"):
+        """Ms: list of C (n, b) arrays; Ds: array (C, P, n).  channel "nso" runs nso1 (what the reference's
+        QSFT.transform hard-codes, qsft.py:171) unless nso_subtype="nso2" asks for the hard-decision detector."""
         self.q, self.n, self.b = q, n, b
         self.C = len(Ms)
         Ds = np.asarray(Ds)
@@ -233,9 +294,7 @@ class PeelProblem:
             e, l = rs.device_tables()
             self.rs_exp, self.rs_log = torch.from_numpy(e).to(device), torch.from_numpy(l).to(device)
             rs_t, rs_s = rs.t, rs.s
-        chan = {"identity": 0, "nso": 1}.get(channel)
-        if chan is None:
-            raise NotImplementedError(f"reconstruct_method_channel={channel!r} is not supported (identity | nso)")
+        chan = channel_code(channel, nso_subtype)
         src = {"identity": 0, "coded": 1}.get(source)
         if src is None:
             raise NotImplementedError(f"reconstruct_method_source={source!r} is not supported (identity | coded)")

@@ -19,7 +19,9 @@ from .utils import calc_hamming_weight, sort_qary_vecs
 class QSFT:
     """kwargs: num_subsample, num_repeat, b, reconstruct_method_source ("identity" | "coded"),
     reconstruct_method_channel ("identity" | "nso"), source_decoder (from get_reed_solomon_dec; needed for
-    "coded"), noise_sd (accepted and ignored like the reference: the signal's noise_sd sets the threshold)."""
+    "coded"), noise_sd (accepted and ignored like the reference: the signal's noise_sd sets the threshold).
+    Extension: nso_subtype ("nso1" default = what the reference hard-codes at qsft.py:171; "nso2" = the hard-decision
+    detector reconstruct.py:116-129)."""
 
     def __init__(self, **kwargs):
         self.reconstruct_method_source = kwargs.get("reconstruct_method_source")
@@ -28,6 +30,7 @@ class QSFT:
         self.num_repeat = kwargs.get("num_repeat")
         self.b = kwargs.get("b")
         self.source_decoder = kwargs.get("source_decoder", None)
+        self.nso_subtype = kwargs.get("nso_subtype", "nso1")
         self.last_stats = {}
 
     def transform(self, signal, verbosity=0, report=False, timing_verbose=False, **kwargs):
@@ -57,7 +60,8 @@ class QSFT:
             rs = getattr(self.source_decoder, "__self__", None)
             if rs is None or not hasattr(rs, "device_tables"):
                 raise ValueError("reconstruct_method_source='coded' needs source_decoder=get_reed_solomon_dec(n, t, q)")
-        prob = ops.PeelProblem(q, n, b, Ms, D, signal.get_source_parity(), channel, source, cutoff, dev, rs=rs)
+        prob = ops.PeelProblem(q, n, b, Ms, D, signal.get_source_parity(), channel, source, cutoff, dev, rs=rs,
+                               nso_subtype=self.nso_subtype)
         dist = getattr(signal, "dist", None)
         shard = dist is not None and dist.world_size > 1
         if shard and hasattr(dist, "shard_peel"):

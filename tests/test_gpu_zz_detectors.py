@@ -1,0 +1,154 @@
+"""GPU parity for the stand-alone detector entry points (qsft_singleton_detect / qsft_detect_mle) and the nso2 channel
+of the peel: against fixtures produced by the reference's own reconstruct.py functions (oracle/gen_golden.py
+--detectors) and against the oracle.  Symbols are integers: bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import qsft_oracle as orc
+from conftest import NSO2_CASES, case_params, load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import qsft_b200
+    from qsft_b200 import ops, reconstruct
+    DEV = torch.device("cuda", 0)
+
+
+def test_detect_units_identity_and_nso1_standalone():
+    """reconstruct.singleton_detection for a batch of columns == the reference's per-column results."""
+    g = load_golden("detect_units")
+    for tag in ["nl_q4", "nl_q3", "nso_q4", "nso_q5", "nso_q2"]:
+        q, p1, R = (int(v) for v in g[tag + "_meta"])
+        chan = "identity" if tag.startswith("nl") else "nso"
+        cols = g[tag + "_cols"]                                   # (N, P) complex128
+        got = reconstruct.singleton_detection(cols.T, method_channel=chan, method_source="identity", q=q,
+                                              source_parity=p1, nso_subtype="nso1")
+        assert np.array_equal(got.T, g[tag + "_k"]), tag
+        one = reconstruct.singleton_detection(cols[3], method_channel=chan, method_source="identity", q=q,
+                                              source_parity=p1)
+        assert one.shape == (p1 - 1,) and np.array_equal(one, g[tag + "_k"][3])
+
+
+def test_detect_units_nso2():
+    g = load_golden("detect_units2")
+    for tag in ["nso2_q4", "nso2_q3", "nso2_q5", "nso2_q2", "nso2_q7"]:
+        q, p1, R = (int(v) for v in g[tag + "_meta"])
+        got = reconstruct.singleton_detection(g[tag + "_cols"].T, method_channel="nso", method_source="identity", q=q,
+                                              source_parity=p1, nso_subtype="nso2")
+        assert np.array_equal(got.T, g[tag + "_k"]), tag
+
+
+def test_detect_units_mle():
+    g = load_golden("detect_units2")
+    for tag in ["mle_q2", "mle_q3", "mle_q4"]:
+        sel, S = g[tag + "_selection"], g[tag + "_S"]
+        ksel, sig = reconstruct.singleton_detection_mle(g[tag + "_cols"].T, selection=sel, S_slice=S)
+        assert np.array_equal(ksel, g[tag + "_ksel"]), tag
+        assert np.array_equal(sig.T, g[tag + "_sig"])
+        k1, s1 = reconstruct.singleton_detection(g[tag + "_cols"][5], method_channel="mle", selection=sel, S_slice=S)
+        assert int(k1) == int(g[tag + "_ksel"][5]) and np.array_equal(s1, g[tag + "_sig"][5])
+        # residual = the oracle's minimum residual norm
+        cols = torch.from_numpy(g[tag + "_cols"].astype(np.complex64)).to(DEV)
+        idx, res = ops.detect_mle(cols, torch.from_numpy(S.astype(np.complex64)).to(DEV))
+        for c in range(0, len(cols), 7):
+            P = S.shape[0]
+            alphas = np.conjugate(S).T @ g[tag + "_cols"][c] / P
+            want = np.linalg.norm(g[tag + "_cols"][c] - (alphas * S).T, axis=1)
+            assert int(idx[c]) == int(np.argmin(want))
+            assert abs(float(res[c]) - want.min()) <= 1e-5 * max(1.0, want.min())
+
+
+def test_detect_mle_large_random_vs_oracle():
+    """More candidates than lanes, several warps per block, ties impossible (random data)."""
+    rng = np.random.default_rng(5)
+    P, K, N = 23, 1000, 77
+    S = np.exp(2j * np.pi * rng.integers(0, 5, (P, K)) / 5)
+    true = rng.integers(0, K, N)
+    cols = (S[:, true] * rng.uniform(0.5, 2, N) + 0.3 * (rng.normal(size=(P, N)) + 1j * rng.normal(size=(P, N)))).T
+    idx, _ = ops.detect_mle(torch.from_numpy(cols.astype(np.complex64)).to(DEV).contiguous(),
+                            torch.from_numpy(S.astype(np.complex64)).to(DEV))
+    want = [orc.detect_mle(c, np.arange(K), S)[2] for c in cols]
+    assert idx.cpu().tolist() == want
+
+
+def test_detect_coded_standalone_vs_oracle():
+    """Channel stage + Reed-Solomon source stage in one call == oracle decode of the same symbols."""
+    n, t, q, R = 20, 3, 3, 2
+    dec = qsft_b200.get_reed_solomon_dec(n, t, q)
+    rs = dec.__self__
+    D = rs.get_delay_matrix()
+    odec = orc.get_reed_solomon_dec(n, t, q)
+    p1 = D.shape[0]
+    rng = np.random.default_rng(3)
+    cols, want = [], []
+    for i in range(60):
+        k = np.zeros(n, dtype=int)
+        w = int(rng.integers(0, t + 2))                       # includes weight t + 1: decoder failure -> zeros
+        pos = rng.choice(n, w, replace=False)
+        k[pos] = rng.integers(1, q, w)
+        off = rng.integers(0, q, (R, n))
+        ph = np.concatenate([((off[r] - D) % q) @ k % q for r in range(R)])
+        col = (1.3 - 0.4j) * np.exp(2j * np.pi * ph / q)
+        cols.append(col)
+        sym = orc.detect_nso1(col[:, None], q, p1)[:, 0]
+        want.append(np.array(odec(list(sym))[0][0, :], dtype=int))
+    got = reconstruct.singleton_detection(np.array(cols).T, method_channel="nso", method_source="coded", q=q,
+                                          source_parity=p1, source_decoder=dec)
+    assert np.array_equal(got.T, np.array(want))
+
+
+def test_detect_argument_errors():
+    cols = torch.zeros((4, 10), dtype=torch.complex64, device=DEV)
+    with pytest.raises(qsft_b200.QsftError):
+        ops.singleton_detect(cols, 4, 3, "nso")                # P not a multiple of P_src
+    with pytest.raises(qsft_b200.QsftError):
+        ops.singleton_detect(cols, 4, 5, "identity")           # identity channel needs num_repeat == 1
+    with pytest.raises(ValueError):
+        ops.singleton_detect(cols, 4, 5, "nso", nso_subtype="nso3")
+    with pytest.raises(NotImplementedError):
+        ops.channel_code("mle")
+    assert ops.singleton_detect(cols[:0], 4, 5, "nso").shape == (0, 4)
+
+
+@pytest.mark.parametrize("name", NSO2_CASES)
+def test_k4_peel_nso2_from_reference_bins(name):
+    """Peel the reference's own (noisy) bins with channel = nso2: same finds in the same order as the reference run
+    whose singleton_detection was switched to nso_subtype="nso2"."""
+    g = load_golden(name)
+    p = case_params(g)
+    q, n = p["q"], p["n"]
+    U = torch.from_numpy(np.ascontiguousarray(g["mdu_Us"].reshape(p["trC"], -1, q ** p["trb"])).astype(np.complex64)).to(DEV)
+    D = g["mdu_Ds"].reshape(p["trC"], -1, n)
+    cutoff = 1e-9 + 1.5 * p["noise_sd"] ** 2 / q ** p["trb"]
+    prob = ops.PeelProblem(q, n, p["trb"], list(g["mdu_Ms"]), D, p["P_src"], p["chan"], p["src"], cutoff, DEV,
+                           nso_subtype="nso2")
+    prob.alloc(4 * U.shape[0] * U.shape[2])
+    prob.peel(U)
+    dk, dv, _ = prob.distinct()
+    want_keys = [tuple(int(v) for v in k) for k in g["res_keys"]]
+    assert [tuple(int(v) for v in r) for r in dk] == want_keys
+    assert np.max(np.abs(dv - g["res_vals"])) <= 1e-5 * np.max(np.abs(g["res_vals"]))
+
+
+@pytest.mark.parametrize("name", NSO2_CASES)
+def test_end_to_end_nso2_same_seed(name):
+    g = load_golden(name)
+    p = case_params(g)
+    np.random.seed(p["seed"])
+    sig = qsft_b200.get_random_subsampled_signal(n=p["n"], q=p["q"], sparsity=p["S"], a_min=1, a_max=1,
+                                                  noise_sd=p["noise_sd"], query_args=dict(p["query_args"]),
+                                                  max_weight=p["max_weight"])
+    sft = qsft_b200.QSFT(num_subsample=p["trC"], num_repeat=p["trR"], b=p["trb"], reconstruct_method_source=p["src"],
+                         reconstruct_method_channel=p["chan"], nso_subtype="nso2")
+    res = sft.transform(sig, report=True, sort=True)
+    assert np.random.random() == float(g["rng_probe"])
+    want_keys = [tuple(int(v) for v in k) for k in g["res_keys"]]
+    if p["noise_sd"] == 0:
+        assert list(res["gwht"].keys()) == want_keys
+        assert np.array_equal(np.array(res["locations"]), g["locations"])
+    else:
+        assert set(res["gwht"].keys()) == set(want_keys)
+    got = np.array([res["gwht"][k] for k in want_keys])
+    assert np.max(np.abs(got - g["res_vals"])) <= 1e-4

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import qsft_oracle as orc
-from conftest import FULL_CASES, INDEX_CASES, case_params, load_golden, u128_to_ints
+from conftest import FULL_CASES, INDEX_CASES, NSO2_CASES, case_params, load_golden, u128_to_ints
 
 
 def build(g):
@@ -86,6 +86,36 @@ def test_detection_units():
         else:
             k = orc.detect_nso1(cols, q, p1)
         assert np.array_equal(k.T, g[tag + "_k"]), tag
+
+
+def test_detection_units_nso2_mle():
+    """The detectors QSFT.transform never selects, pinned at function level."""
+    g = load_golden("detect_units2")
+    for tag in ["nso2_q4", "nso2_q3", "nso2_q5", "nso2_q2", "nso2_q7"]:
+        q, p1, R = (int(v) for v in g[tag + "_meta"])
+        k = orc.detect_nso2(g[tag + "_cols"].T, q, p1)
+        assert np.array_equal(k.T, g[tag + "_k"]), tag
+    for tag in ["mle_q2", "mle_q3", "mle_q4"]:
+        sel, S = g[tag + "_selection"], g[tag + "_S"]
+        for col, want_k, want_sig in zip(g[tag + "_cols"], g[tag + "_ksel"], g[tag + "_sig"]):
+            k, sig, idx = orc.detect_mle(col, sel, S)
+            assert int(k) == int(want_k) and np.array_equal(sig, want_sig) and sel[idx] == k, tag
+
+
+@pytest.mark.parametrize("name", NSO2_CASES)
+def test_nso2_pipeline_matches_reference(name):
+    g = load_golden(name)
+    assert str(g["nso_subtype"]) == "nso2"
+    p, sig = build(g)
+    assert np.array_equal(np.array(sig.Ms), g["Ms"]) and np.array_equal(np.array(sig.Ds[0]), g["Ds"])
+    mine = np.array([[sig.Us[i][j][p["b"]] for j in range(p["R"])] for i in range(p["C"])])
+    assert np.allclose(mine, g[f"Us_b{p['b']}"], rtol=1e-12, atol=1e-13)
+    res = orc.transform(sig, p["trC"], p["trR"], p["trb"], reconstruct_method_source=p["src"],
+                        reconstruct_method_channel=p["chan"], report=True, sort=True, nso_subtype="nso2")
+    assert np.random.random() == float(g["rng_probe"])
+    assert list(res["gwht"].keys()) == [tuple(int(v) for v in k) for k in g["res_keys"]]
+    assert np.allclose(np.array(list(res["gwht"].values())), g["res_vals"], rtol=1e-10, atol=1e-12)
+    assert np.array_equal(np.array(res["locations"]), g["locations"])
 
 
 def test_gwht_units():
