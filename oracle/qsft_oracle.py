@@ -447,7 +447,10 @@ class GFext:
         if not _is_prime(p):
             raise NotImplementedError("q is not a prime number")
         self.p, self.s, self.order = p, s, p ** s
-        for low in range(self.order):  # monic x^s + low
+        # galois 0.1.x RS default = matlab_primitive_poly(p, s): the lexicographically-minimal primitive polynomial,
+        # except GF(2^7) -> x^7 + x^3 + 1 (also GF(2^14), GF(2^16): beyond n <= 128).  [galois docs, from memory]
+        first = [9] if (p, s) == (2, 7) else []
+        for low in first + list(range(self.order)):  # monic x^s + low
             tab = self._try_poly(low)
             if tab is not None:
                 self.poly_low = low

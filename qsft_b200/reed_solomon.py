@@ -5,8 +5,9 @@ dependency here, the field arithmetic is implemented below).  The host class pro
 GF log/antilog tables; singleton decoding during peeling runs on the GPU (csrc/k4_peel.cu: rs_decode), the
 `syndrome_decode` method here is the API-compatible host entry (get_reed_solomon_dec) for callers that want it.
 
-Field construction: smallest primitive polynomial x^s + ... in integer order, primitive element x (what galois
-0.1.x is believed to use; decoded supports do not depend on this choice, the D matrix does -- see DESIGN.md).
+Field construction: lexicographically-minimal primitive polynomial x^s + ... (MATLAB's default; GF(2^7) uses
+x^7 + x^3 + 1), primitive element x (what galois 0.1.x is believed to use through matlab_primitive_poly; decoded
+supports do not depend on this choice, the D matrix does -- see DESIGN.md).
 """
 from __future__ import annotations
 
@@ -27,7 +28,10 @@ class GaloisField:
             raise NotImplementedError("q is not a prime number under 30!")
         self.p, self.s, self.order = p, s, p ** s
         self.exp = None
-        for low in range(1, self.order):
+        # galois 0.1.x builds RS fields from matlab_primitive_poly(p, s) = the lexicographically-minimal primitive
+        # polynomial, with the exception GF(2^7) -> x^7 + x^3 + 1 (the other exceptions, 2^14 and 2^16, exceed n <= 128)
+        first = [0b0001001] if (p, s) == (2, 7) else []
+        for low in first + list(range(1, self.order)):
             tab = self._powers_of_x(low)
             if tab is not None:
                 self.poly_low, self.exp = low, tab

@@ -98,7 +98,7 @@ def test_query_errors_like_reference():
 def test_reed_solomon_host_matches_oracle():
     import qsft_oracle as orc
     from qsft_b200.reed_solomon import ReedSolomon
-    for (n, t, q) in [(30, 4, 3), (20, 3, 5), (12, 2, 2)]:
+    for (n, t, q) in [(30, 4, 3), (20, 3, 5), (12, 2, 2), (100, 2, 2)]:       # (100, 2, 2): GF(2^7)
         a, o = ReedSolomon(n, t, q), orc.RSCode(n, t, q)
         D = a.get_delay_matrix()
         assert np.array_equal(D, o.get_delay_matrix())
@@ -113,6 +113,27 @@ def test_reed_solomon_host_matches_oracle():
                 syn = (D[1:] @ k) % q
             r1, r2 = a.syndrome_decode(list(syn)), o.syndrome_decode(list(syn))
             assert np.array_equal(r1[0], r2[0]) and r1[1] == r2[1]
+
+
+def test_field_polynomials_are_matlab_defaults():
+    """galois 0.1.x builds its RS fields from matlab_primitive_poly(p, m).  For p = 2 these are MATLAB's published
+    gf() defaults (decimal): the lexicographically-minimal primitive polynomial except m = 7.  Irreducibility of every
+    polynomial used is cross-checked with sympy."""
+    import qsft_oracle as orc
+    from qsft_b200.reed_solomon import GaloisField
+    from sympy.polys.domains import ZZ
+    from sympy.polys.galoistools import gf_irreducible_p
+    matlab = {2: 7, 3: 11, 4: 19, 5: 37, 6: 67, 7: 137, 8: 285, 9: 529, 10: 1033}
+    for m, dec in matlab.items():
+        assert (1 << m) + GaloisField(2, m).poly_low == dec
+        assert (1 << m) + orc.GFext(2, m).poly_low == dec
+    for p, m in [(3, 2), (3, 3), (3, 4), (5, 2), (5, 3), (7, 2), (11, 2), (13, 2)]:
+        h, o = GaloisField(p, m), orc.GFext(p, m)
+        assert h.poly_low == o.poly_low
+        coeffs = [1] + [(h.poly_low // p ** i) % p for i in range(m - 1, -1, -1)]       # monic, high degree first
+        assert gf_irreducible_p([ZZ(c) for c in coeffs], p, ZZ)
+        # primitive: x generates all p^m - 1 non-zero elements
+        assert len(set(int(v) for v in h.exp[: p ** m - 1])) == p ** m - 1
 
 
 def test_finds_to_dict_matches_reference_averaging():
