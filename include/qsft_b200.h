@@ -75,6 +75,13 @@ int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stream);
  * symmetric U buffer), i.e. P2P stores over NVLink instead of a separate collective.  peer_x is a HOST array.        */
 int qsft_gwht_batch_bcast(float* x, int64_t batch, int q, int b, float* const* peer_x, int n_peers, void* stream);
 
+/* Verification helper (host only, no device work): work item of ticket number `ticket` in the single-launch two-pass
+ * q = 4 transform (k3_q4_twopass_kernel): block, tile inside its pass, and whether it belongs to the strided (second)
+ * pass.  A strided tile of block k waits for all tiles1 contiguous tiles of block k; tests check that those always
+ * carry lower tickets and that the order is a bijection, for every lag.                                          */
+int qsft_k3_ticket_decode(uint32_t ticket, int64_t nblocks, int tiles1, int tiles2, int lag, int64_t* blk, int* tile,
+                          int* strided);
+
 /* K4 -- peeling decoder.  Replaces the loop of QSFT.transform (qsft/qsft.py:151-241) and the singleton detectors
  * (qsft/reconstruct.py:12-31, 100-113, 34-51 + qsft/ReedSolomon.py:26-48).
  *

@@ -15,7 +15,7 @@ EXPORTS = [
     "qsft_query_lattice", "qsft_dec_to_qary", "qsft_qary_to_dec", "qsft_eval_synth", "qsft_gwht_batch", "qsft_gwht_batch_bcast",
     "qsft_eval_lattice_supported", "qsft_eval_synth_lattice",
     "qsft_peel_classify", "qsft_peel_apply", "qsft_peel_reduce", "qsft_peel", "qsft_closed_form_bins",
-    "qsft_singleton_detect", "qsft_detect_mle",
+    "qsft_singleton_detect", "qsft_detect_mle", "qsft_k3_ticket_decode",
 ]
 
 
@@ -91,6 +91,7 @@ def lib():
     L.qsft_closed_form_bins.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp, i64, vp, vp]
     L.qsft_singleton_detect.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     L.qsft_detect_mle.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
+    L.qsft_k3_ticket_decode.argtypes = [C.c_uint32, i64, i32, i32, i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
     for name in EXPORTS:
         fn = getattr(L, name)  # raises AttributeError if a declared symbol is missing
         if name not in ("qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count"):

@@ -7,6 +7,8 @@
 // significant = first axis of the C-order reshape [q]*b).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int K3_THREADS = 256;
@@ -306,25 +308,67 @@ k3_q4_fast_kernel(float2* __restrict__ x, long long B, int r, int p0, long long 
     k3_q4_tile<STRIDED>(s, x + blk * B, tile - blk * tiles_per_block, r, p0, qa, lgW, scale, x, peers);
 }
 
-// Both passes of a two-pass transform (4^7 .. 4^12 points) in ONE launch: CTAs are enumerated block by block, first
-// the block's contiguous-pass tiles, then its strided-pass tiles; a strided tile waits on a per-block counter until
-// all contiguous tiles of its block have been written.  CTAs are dispatched in index order, so the tiles a waiter
-// depends on are always running or finished (no deadlock), and the intermediate of a block is consumed from L2
-// right after it was produced: DRAM sees one read and one write of the data.
-__global__ void __launch_bounds__(256)
+// Both passes of a two-pass transform (4^7 .. 4^12 points) in ONE launch.  Work items (tiles) are handed out through an
+// atomic ticket; a strided-pass tile of block k waits on a per-block counter until all contiguous-pass tiles of block k
+// have been written, so the intermediate of a block is consumed from L2: DRAM sees one read and one write of the data.
+//
+// Ticket order (k3_ticket_decode): contiguous tiles run `lag` blocks AHEAD of the strided tiles,
+//     C(0) .. C(lag-1) | C(lag) S(0) | C(lag+1) S(1) | ... | C(nb-1) S(nb-1-lag) | S(nb-lag) .. S(nb-1)
+// so (after the start-up blocks) lag * (tiles1 + tiles2) tickets lie between a block's last contiguous tile and its first
+// strided tile.  With
+// that distance >= the number of co-resident CTAs a strided tile never finds its block unfinished; with the plain order
+// (lag = 0: C(k) S(k) back to back) the strided tiles of a block become resident while its contiguous tiles still run and
+// about half of the resident CTAs only spin.  Every dependency of a ticket has a LOWER ticket, and lower tickets are
+// held by CTAs that are already resident or finished -> no deadlock for any lag.
+struct K3Ticket {
+    long long blk;
+    int t;          // tile inside its pass
+    bool strided;
+};
+
+__host__ __device__ inline K3Ticket k3_ticket_decode(unsigned int ticket, long long nblocks, int tiles1, int tiles2, int lag) {
+    K3Ticket o;
+    const long long L = lag < nblocks ? (lag < 0 ? 0 : lag) : nblocks;
+    const long long head = L * tiles1;                       // C(0) .. C(L-1)
+    if ((long long)ticket < head) {
+        o.blk = ticket / (unsigned int)tiles1;
+        o.t = (int)(ticket - (unsigned int)(o.blk * tiles1));
+        o.strided = false;
+        return o;
+    }
+    const long long u = (long long)ticket - head;
+    const long long per = (long long)tiles1 + tiles2;
+    const long long groups = nblocks - L;                    // group g: C(g + L) then S(g)
+    if (u < groups * per) {
+        const long long g = u / per;
+        const int v = (int)(u - g * per);
+        o.strided = v >= tiles1;
+        o.blk = o.strided ? g : g + L;
+        o.t = o.strided ? v - tiles1 : v;
+        return o;
+    }
+    const long long w = u - groups * per;                    // tail: S(nb - L) .. S(nb - 1)
+    const long long g = w / tiles2;
+    o.blk = groups + g;
+    o.t = (int)(w - g * tiles2);
+    o.strided = true;
+    return o;
+}
+
+// 64 registers (one 8-byte spill) -> 4 CTAs per SM instead of 3 at the 80 registers ptxas takes unconstrained
+__global__ void __launch_bounds__(256, 4)
 k3_q4_twopass_kernel(float2* __restrict__ x, long long B, int r1, int r2, long long qa2, int lgW2, int tiles1, int tiles2,
-                     unsigned int* __restrict__ done /* [nblocks] counters + [1] ticket */, long long nblocks, float scale,
-                     K3Peers peers) {
+                     unsigned int* __restrict__ done /* [nblocks] counters + [1] ticket */, long long nblocks, int lag,
+                     float scale, K3Peers peers) {
     __shared__ float2 s[4096];
     __shared__ unsigned int s_ticket;
-    // work items are handed out through an atomic ticket (not blockIdx): every lower ticket is then guaranteed to be
-    // held by a CTA that is already resident, which is what makes the wait below deadlock free
+    // tickets, not blockIdx: every lower ticket is then guaranteed to be held by a CTA that is already resident (or has
+    // finished), which is what makes the wait below deadlock free
     if (threadIdx.x == 0) s_ticket = atomicAdd(done + nblocks, 1u);
     __syncthreads();
-    const unsigned int ticket = s_ticket;
-    const int per_block = tiles1 + tiles2;
-    const long long blk = ticket / per_block;
-    const int t = (int)(ticket - (unsigned int)(blk * per_block));
+    const K3Ticket tk = k3_ticket_decode(s_ticket, nblocks, tiles1, tiles2, lag);
+    const long long blk = tk.blk;
+    const int t = tk.strided ? tk.t + tiles1 : tk.t;
     float2* base = x + blk * B;
     if (t < tiles1) {
         K3Peers none;
@@ -435,6 +479,31 @@ __global__ void k3_bcast_copy_kernel(const float2* __restrict__ x, long long n, 
     }
 }
 
+// How many blocks the contiguous pass runs ahead of the strided pass (see k3_q4_twopass_kernel): enough tickets between
+// a block's two passes to cover every co-resident CTA, but no more intermediate data than stays comfortably in L2.
+// QSFT_K3_LAG overrides (0 = the plain block-by-block order).
+static int k3_twopass_lag(long long B, int tiles1, int tiles2) {
+    if (const char* e = getenv("QSFT_K3_LAG")) {
+        const int v = atoi(e);
+        if (v >= 0 && v <= 4096) return v;
+    }
+    static int resident = 0;                                  // co-resident CTAs of the kernel on this device
+    if (resident == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_twopass_kernel, 256, 0) != cudaSuccess || per_sm < 1) {
+            (void)cudaGetLastError();
+            per_sm = 4;
+        }
+        resident = per_sm * qsft_num_sms();
+    }
+    const long long per = (long long)tiles1 + tiles2;
+    long long lag = (resident + per - 1) / per;
+    const long long l2_rows = (32ll << 20) / (B * (long long)sizeof(float2));    // intermediates kept live in L2
+    if (lag > l2_rows) lag = l2_rows;
+    if (lag < 1) lag = 1;
+    return (int)lag;
+}
+
 static int gwht_impl(float* x, int64_t batch, int q, int b, const K3Peers& peers, void* stream) {
     QSFT_CHECK_ARG(q >= 2 && q <= QSFT_MAX_Q, "q=%d out of range", q);
     QSFT_CHECK_ARG(b >= 0 && b <= QSFT_MAX_B, "b=%d out of range", b);
@@ -475,8 +544,9 @@ static int gwht_impl(float* x, int64_t batch, int q, int b, const K3Peers& peers
         QSFT_CUDA(qsft_scratch_alloc((void**)&done, (size_t)(batch + 1) * sizeof(unsigned int), st));
         QSFT_CUDA(cudaMemsetAsync(done, 0, (size_t)(batch + 1) * sizeof(unsigned int), st));
         const int t1 = (int)plans[0].tiles_per_block, t2 = (int)plans[1].tiles_per_block;
+        const int lag = k3_twopass_lag(B, t1, t2);
         k3_q4_twopass_kernel<<<(unsigned)(batch * (t1 + t2)), 256, 0, st>>>(xx, B, plans[0].r, plans[1].r, plans[1].qa,
-                                                                          plans[1].lgW, t1, t2, done, (long long)batch, inv, peers);
+                                                                          plans[1].lgW, t1, t2, done, (long long)batch, lag, inv, peers);
         QSFT_LAUNCHED();
         QSFT_CUDA(cudaFreeAsync(done, st));
         return QSFT_OK;
@@ -523,4 +593,18 @@ extern "C" int qsft_gwht_batch_bcast(float* x, int64_t batch, int q, int b, floa
     for (int r = 0; r < 7; ++r) peers.p[r] = r < n_peers ? reinterpret_cast<float2*>(peer_x[r]) : nullptr;
     for (int r = 0; r < n_peers; ++r) QSFT_CHECK_ARG(peer_x[r] != nullptr, "null peer pointer");
     return gwht_impl(x, batch, q, b, peers, stream);
+}
+
+// Host-side view of the two-pass kernel's ticket order (verification helper: tests prove on the CPU that the order is a
+// bijection onto the tiles and that every strided tile's dependencies have lower tickets, i.e. the kernel cannot deadlock).
+extern "C" int qsft_k3_ticket_decode(uint32_t ticket, int64_t nblocks, int tiles1, int tiles2, int lag, int64_t* blk,
+                                     int* tile, int* strided) {
+    QSFT_CHECK_ARG(nblocks >= 1 && tiles1 >= 1 && tiles2 >= 1 && lag >= 0, "bad shape");
+    QSFT_CHECK_ARG((long long)ticket < nblocks * ((long long)tiles1 + tiles2), "ticket out of range");
+    QSFT_CHECK_ARG(blk && tile && strided, "null pointer");
+    const K3Ticket t = k3_ticket_decode(ticket, nblocks, tiles1, tiles2, lag);
+    *blk = t.blk;
+    *tile = t.t;
+    *strided = t.strided ? 1 : 0;
+    return QSFT_OK;
 }

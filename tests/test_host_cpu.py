@@ -169,3 +169,35 @@ def test_ctypes_struct_layout_matches_header(tmp_path):
     P, U = _lib.PeelDesc, _lib.Uniq
     want = [ctypes.sizeof(P), P.ld.offset, P.cutoff.offset, P.MT.offset, P.rs_log.offset, ctypes.sizeof(U), U.max_uniq.offset]
     assert got == want
+
+
+def test_k3_twopass_ticket_order_is_deadlock_free():
+    """The single-launch two-pass DFT hands tiles out by ticket; a strided tile spins until every contiguous tile of its
+    block is written.  For every lag the order must be a bijection onto the tiles and every dependency must carry a
+    LOWER ticket (lower tickets are resident or finished => the spin always ends).  Runs the library's own decode."""
+    import ctypes as C
+    from qsft_b200 import _lib
+    L = _lib.lib()
+    blk, tile, strided = C.c_int64(), C.c_int(), C.c_int()
+    for nb, t1, t2 in [(1, 4, 4), (5, 4, 4), (7, 3, 5), (41, 16, 16), (3, 256, 256), (2, 1, 1)]:
+        for lag in [0, 1, 2, 3, nb - 1, nb, nb + 5]:
+            if lag < 0:
+                continue
+            seen = {}
+            c_last = {}                                      # block -> highest ticket among its contiguous tiles
+            s_first = {}                                     # block -> lowest ticket among its strided tiles
+            for tk in range(nb * (t1 + t2)):
+                _lib.check(L.qsft_k3_ticket_decode(tk, nb, t1, t2, lag, C.byref(blk), C.byref(tile), C.byref(strided)))
+                key = (blk.value, tile.value, strided.value)
+                assert key not in seen and 0 <= blk.value < nb and 0 <= tile.value < (t2 if strided.value else t1)
+                seen[key] = tk
+                if strided.value:
+                    s_first.setdefault(blk.value, tk)
+                else:
+                    c_last[blk.value] = tk
+            assert len(seen) == nb * (t1 + t2)
+            for k in range(nb):
+                assert c_last[k] < s_first[k], (nb, t1, t2, lag, k)
+                if 0 < lag < nb and k + lag < nb:            # tickets between a block's two passes (full distance once k >= lag)
+                    assert s_first[k] - c_last[k] - 1 == lag * t1 + min(k, lag) * t2
+    assert L.qsft_k3_ticket_decode(8, 1, 4, 4, 0, C.byref(blk), C.byref(tile), C.byref(strided)) != 0   # out of range
