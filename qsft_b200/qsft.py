@@ -44,11 +44,18 @@ class QSFT:
         peeling_start = time.time()
         dev = signal.device
         # (C, P, B) bins; a private copy because peeling subtracts in place (the reference vstacks copies too)
-        U = torch.stack([torch.cat([torch.as_tensor(u, device=dev) for u in us], dim=0) for us in Us]).contiguous()
-        if U.dtype != torch.complex64:
-            U = U.to(torch.complex64)
+        # (one copy straight into place: the bins are 1-3 GB at the large configurations)
+        C, P, B = len(Us), sum(int(u.shape[0]) for u in Us[0]), int(Us[0][0].shape[-1])
+        U = torch.empty((C, P, B), dtype=torch.complex64, device=dev)
+        for i, us in enumerate(Us):
+            row = 0
+            for u in us:
+                u = torch.as_tensor(u, device=dev)
+                U[i, row:row + u.shape[0]].copy_(u)
+                row += u.shape[0]
+            if row != P:
+                raise ValueError("every subsampling group must carry the same number of delay rows")
         D = np.stack([np.vstack(d) for d in Ds])
-        C, P, B = U.shape
         cutoff = 1e-9 + (1 + 0.5) * (signal.noise_sd ** 2) / (q ** b)   # noise threshold, qsft.py:124-125
         cutoff = kwargs.get("cutoff", cutoff)
         if verbosity >= 2:

@@ -201,3 +201,20 @@ def test_k3_twopass_ticket_order_is_deadlock_free():
                 if 0 < lag < nb and k + lag < nb:            # tickets between a block's two passes (full distance once k >= lag)
                     assert s_first[k] - c_last[k] - 1 == lag * t1 + min(k, lag) * t2
     assert L.qsft_k3_ticket_decode(8, 1, 4, 4, 0, C.byref(blk), C.byref(tile), C.byref(strided)) != 0   # out of range
+
+
+def test_narrow_int8_matches_numpy_cast():
+    """Host-side digit narrowing (ops.narrow_int8, the torch fast path of pad_digits) == ndarray.astype(int8)."""
+    import torch  # noqa: F401
+    from qsft_b200.ops import narrow_int8
+    rng = np.random.default_rng(0)
+    for dt in [np.int64, np.int32, np.int16, np.int8, np.uint8, np.uint16, np.uint32, np.uint64, np.float64]:
+        a = rng.integers(0, 100, (7, 13)).astype(dt)
+        for arr in [a, a.T, a[:, ::2], np.asfortranarray(a)]:
+            got = narrow_int8(arr).numpy()
+            assert got.dtype == np.int8 and got.flags.c_contiguous and np.array_equal(got, arr.astype(np.int8)), dt
+    ro = rng.integers(0, 4, (5, 5))
+    ro.setflags(write=False)
+    assert np.array_equal(narrow_int8(ro).numpy(), ro)
+    assert np.array_equal(narrow_int8([[1, 2], [3, 0]]).numpy(), [[1, 2], [3, 0]])
+    assert narrow_int8(np.zeros((0, 4), dtype=np.int64)).shape == (0, 4)
