@@ -355,6 +355,15 @@ def run_ours(a):
                 "pairs_per_s": k2_pairs / (k2_ms * 1e-3) if k2_ms > 0 else None,
                 "share_of_step": (k2_ms / a.steps) / ms_per_step if ms_per_step else None,
                 "per_kernel_ms_per_step": {k: v[0] / a.steps for k, v in kt.items()}}
+    if k2_name == "k2_eval_lattice" and sparse_mode and clocks and clocks.get("sm_mhz"):
+        # second denominator: the tensor pipe's measured ISSUE rate (tools/sp_probe.cu on this pool: one N=256 + one N=128
+        # sparse kind::i8 MMA with M=128, K=64 logical = 2*128*384*64 dense-equivalent ops every 192.1 cycles per SM)
+        # at the SM clock actually sampled during the timed region (the board power cap holds it below the 1965 MHz maximum)
+        per_clk = 2.0 * 128 * 384 * 64 / 192.1
+        issue_peak = per_clk * 148 * clocks["sm_mhz"] * 1e6 / 1e12
+        roofline["tensor_issue_rate"] = {"ops_per_clk_per_sm": per_clk, "sm_mhz": clocks["sm_mhz"], "peak": issue_peak,
+                                         "unit": "TFLOP/s", "frac": achieved / issue_peak if issue_peak else None,
+                                         "source": "tools/sp_probe.cu (profiles/README.md), clock = median nvidia-smi sample under load"}
     k3_ms, k3_calls, k3_elems = kt.get("k3_gwht", (0.0, 0, 0))
     if k3_ms > 0:
         gbs = 16.0 * k3_elems / (k3_ms * 1e-3) / 1e9
