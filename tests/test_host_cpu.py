@@ -218,3 +218,58 @@ def test_narrow_int8_matches_numpy_cast():
     assert np.array_equal(narrow_int8(ro).numpy(), ro)
     assert np.array_equal(narrow_int8([[1, 2], [3, 0]]).numpy(), [[1, 2], [3, 0]])
     assert narrow_int8(np.zeros((0, 4), dtype=np.int64)).shape == (0, 4)
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
+    """Every entry point validates its arguments before the first CUDA call: QSFT_EINVAL (-1) + a message, on any host."""
+    import ctypes as C
+    from qsft_b200 import _lib
+    L = _lib.lib()
+    null = C.c_void_p(0)
+    one = C.c_void_p(16)                                  # never dereferenced: validation fails first
+    EINVAL = -1
+
+    def bad(rc, needle):
+        assert rc == EINVAL
+        assert needle in L.qsft_last_error().decode(), L.qsft_last_error()
+
+    bad(L.qsft_query_lattice(one, one, 1, 10, 4, 3, one, 1, null, 0, null), "q=1")
+    bad(L.qsft_query_lattice(one, one, 4, 200, 4, 3, one, 2, null, 0, null), "n=200")
+    bad(L.qsft_query_lattice(one, one, 4, 40, 4, 3, one, 1, null, 0, null), "does not fit")      # 80 bits in one limb
+    bad(L.qsft_query_lattice(one, one, 4, 10, 4, 3, null, 1, null, 0, null), "null")
+    bad(L.qsft_query_lattice(one, one, 4, 10, 4, 3, null, 1, one, 24, null), "ld=24")
+    bad(L.qsft_eval_synth(one, 5, one, one, 5, 4, 10, 20, one, 0, null), "ld=20")
+    bad(L.qsft_eval_synth(one, 5, one, one, 5, 4, 10, 32, one, 7, null), "impl")
+    bad(L.qsft_eval_synth(one, 5, null, one, 5, 4, 10, 32, one, 0, null), "null")
+    bad(L.qsft_gwht_batch(one, 3, 1, 4, null), "q=1")
+    bad(L.qsft_gwht_batch(one, -1, 4, 4, null), "negative")
+    bad(L.qsft_gwht_batch(null, 3, 4, 4, null), "null")
+    assert L.qsft_gwht_batch(null, 0, 4, 4, null) == 0    # empty batch: nothing to do, nothing touched
+    assert L.qsft_eval_lattice_supported(4, 40, 10, 41, 100000) == 1
+    assert L.qsft_eval_lattice_supported(3, 40, 10, 41, 100000) == 0
+    assert L.qsft_eval_lattice_supported(4, 40, 6, 41, 100000) == 0
+    bad(L.qsft_eval_synth_lattice(one, one, one, one, 100, 3, 10, 8, 3, 32, one, null), "q = 4")
+    desc = _lib.PeelDesc(q=4, n=10, b=4, C=3, P=11, P_src=11, channel=0, source=0, rs_t=0, rs_s=0, ld=32, cutoff=1e-9,
+                         MT=16, D=16, rs_exp=0, rs_log=0)
+    cnt = C.c_int64(0)
+
+    def peel(d):
+        return L.qsft_peel(C.byref(d), one, one, one, one, one, one, 10, one, None, C.byref(cnt), C.byref(cnt),
+                           C.byref(C.c_int(0)), null)
+
+    for field, value, needle in [("channel", 3, "channel"), ("source", 2, "source"), ("ld", 24, "ld=24"), ("P", 12, "multiple"),
+                                 ("P_src", 10, "multiple"), ("b", 0, "b=0"), ("q", 1, "q=1"), ("MT", 0, "null")]:
+        d = _lib.PeelDesc.from_buffer_copy(desc)
+        setattr(d, field, value)
+        bad(peel(d), needle)
+    d = _lib.PeelDesc.from_buffer_copy(desc)
+    d.P, d.P_src, d.channel = 22, 11, 0                   # identity channel cannot use repeats
+    bad(peel(d), "num_repeat")
+    d = _lib.PeelDesc.from_buffer_copy(desc)
+    d.source, d.rs_t, d.rs_s = 1, 2, 2                    # coded: P_src must be 2ts + 1 = 9
+    bad(peel(d), "2ts + 1")
+    bad(L.qsft_singleton_detect(one, 4, 4, 10, 10, 3, 1, 0, 0, 0, null, null, one, 16, null), "multiple")
+    bad(L.qsft_singleton_detect(one, 4, 4, 10, 10, 5, 0, 0, 0, 0, null, null, one, 16, null), "num_repeat")
+    bad(L.qsft_singleton_detect(one, 4, 4, 10, 10, 5, 1, 0, 0, 0, null, null, one, 3, null), "ld_out")
+    bad(L.qsft_detect_mle(one, 4, 0, one, 5, one, null, null), "positive")
+    assert L.qsft_detect_mle(null, 0, 3, null, 5, null, null, null) == 0
