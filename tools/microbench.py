@@ -41,6 +41,12 @@ x = torch.randn((P, B, 2), device=dev).view(torch.float32)
 xc = torch.view_as_complex(x.view(P, B, 2))
 ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
 out["k3_gwht 41 x 4^10"] = {"ms": ms, "GBps_algorithmic(16B/elem)": 16 * P * B / ms / 1e6, "frac": 16 * P * B / ms / 1e6 / peak}
+# ticket order of the two-pass kernel: 0 = plain block-by-block order, k = contiguous pass k blocks ahead (default: auto)
+for lag in ("0", "1", "2", "3", "4"):
+    os.environ["QSFT_K3_LAG"] = lag
+    ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
+    out[f"k3_gwht 41 x 4^10, QSFT_K3_LAG={lag}"] = {"ms": ms, "frac": 16 * P * B / ms / 1e6 / peak}
+del os.environ["QSFT_K3_LAG"]
 for bb, rows in [(7, 1024), (8, 512), (6, 4096), (12, 4)]:
     y = torch.view_as_complex(torch.randn((rows, q ** bb, 2), device=dev))
     ms = timeit(lambda: ops.gwht_batch_(y, q, bb), flush=flush)
