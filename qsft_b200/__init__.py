@@ -9,8 +9,10 @@ from .synthetic_signal import (SyntheticSubsampledSignal, generate_signal_w,  # 
 from .query import get_Ms, get_D, get_Ms_and_Ds, get_reed_solomon_dec  # noqa: F401
 from .reed_solomon import ReedSolomon  # noqa: F401
 from . import reconstruct  # noqa: F401
+from .test_helper import TestHelper  # noqa: F401
+from .synthetic_helper import SyntheticHelper  # noqa: F401
 from .reconstruct import singleton_detection  # noqa: F401
 
 __all__ = ["QSFT", "SubsampledSignal", "SyntheticSubsampledSignal", "generate_signal_w",
            "get_random_subsampled_signal", "get_Ms", "get_D", "get_Ms_and_Ds", "get_reed_solomon_dec",
-           "ReedSolomon", "reconstruct", "singleton_detection", "QsftError", "lib", "build"]
+           "ReedSolomon", "reconstruct", "singleton_detection", "TestHelper", "SyntheticHelper", "QsftError", "lib", "build"]

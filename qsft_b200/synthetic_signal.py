@@ -53,6 +53,9 @@ class SyntheticSubsampledSignal(SubsampledSignal):
         self.q = kwargs["q"]
         self.n = kwargs["n"]
         self.locq = kwargs["locq"]
+        # the reference reads kwargs["noise_sd"] (KeyError when absent, synthetic_signal.py:94) although its own experiment
+        # drivers build the training signal without it and set the attribute later (test_helper.py:170): default to 0
+        kwargs.setdefault("noise_sd", 0.0)
         self.noise_sd = kwargs["noise_sd"]
         self.strengths = np.asarray(kwargs["strengths"])
         # "numpy": host normals in the reference's RNG order (seed parity); "device": torch.randn on the GPU

@@ -3,6 +3,7 @@ so callers can switch imports).  All arithmetic that matters for throughput runs
 these functions exist for Python-int interop and for tiny host-side bookkeeping."""
 from __future__ import annotations
 
+import json
 import pickle
 import zlib
 
@@ -99,3 +100,16 @@ def save_data(data, filename):
 def load_data(filename):
     with open(filename, "rb") as f:
         return pickle.loads(zlib.decompress(f.read()))
+
+
+class NpEncoder(json.JSONEncoder):
+    """JSON encoder accepting NumPy scalars / arrays (config.json of the experiment harness, qsft/utils.py:199-207)."""
+
+    def default(self, obj):
+        if isinstance(obj, np.integer):
+            return int(obj)
+        if isinstance(obj, np.floating):
+            return float(obj)
+        if isinstance(obj, np.ndarray):
+            return obj.tolist()
+        return super().default(obj)

@@ -152,3 +152,42 @@ def test_end_to_end_nso2_same_seed(name):
         assert set(res["gwht"].keys()) == set(want_keys)
     got = np.array([res["gwht"][k] for k in want_keys])
     assert np.max(np.abs(got - g["res_vals"])) <= 1e-4
+
+
+def test_synthetic_helper_sweep_end_to_end(tmp_path):
+    """The reference's experiment harness on top of the CUDA path: SyntheticHelper builds train (qsft lattice, cached in
+    the reference's folder layout) and test (uniform) signals, run_tests sweeps decoder settings, the test NMSE equals
+    the reference's dense formula (qsft/test_helper.py:235-260) evaluated in NumPy."""
+    from qsft_b200.parallel_tests import run_tests
+    n, q, S = 8, 4, 20
+    np.random.seed(31)
+    sw, locq, strengths = qsft_b200.generate_signal_w(n, q, S, 1, 1, full=False)
+    helper = qsft_b200.SyntheticHelper(signal_args={"n": n, "q": q, "locq": locq, "strengths": strengths},
+                                       methods=["qsft"], subsampling=True, exp_dir=tmp_path,
+                                       subsampling_args={"num_subsample": 3, "num_repeat": 2, "b": 4, "all_bs": [3, 4]},
+                                       test_args={"n_samples": 500})
+    for rel in ["config.json", "train/Ms_and_Ds.pickle", "train/samples/M0_D0.pickle", "train/transforms/U2_1.pickle",
+                "test/signal_t.pickle"]:
+        assert (tmp_path / rel).is_file(), rel
+    df = run_tests("qsft", helper, 1, [2, 3], [1, 2], [3, 4], [0.0], parallel=False)
+    assert len(df) == 8 and (df["n_samples"] == df["num_subsample"] * q ** df["b"] * df["num_repeat"] * (n + 1)).all()
+    best = df[(df["num_subsample"] == 3) & (df["b"] == 4)]
+    assert (best["found_sparsity"] == len(sw)).all() and (best["nmse"] < 1e-9).all()
+    # NMSE of a deliberately wrong model against the reference's formula
+    beta = {k: v * (1.1 if i % 2 else 1.0) for i, (k, v) in enumerate(sw.items())}
+    got = helper.test_model("qsft", beta=beta)
+    idx = list(helper.test_signal.signal_t.keys())
+    y = np.array(list(helper.test_signal.signal_t.values()))
+    dig = orc.dec_to_qary_vec(idx, q, n)
+    y_hat = np.exp(2j * np.pi * (dig.T @ np.array(list(beta.keys())).T) / q) @ np.array(list(beta.values()))
+    want = np.linalg.norm(y_hat - y) ** 2 / np.linalg.norm(y) ** 2
+    assert abs(got - want) <= 1e-4 * want
+    # a second helper on the same directory reuses the cached samples / transforms and gives the same model
+    helper2 = qsft_b200.SyntheticHelper(signal_args={"n": n, "q": q, "locq": locq, "strengths": strengths},
+                                        methods=["qsft"], subsampling=True, exp_dir=tmp_path,
+                                        subsampling_args={"num_subsample": 3, "num_repeat": 2, "b": 4, "all_bs": [3, 4]},
+                                        test_args={"n_samples": 500})
+    assert helper2.test_signal.signal_t.keys() == helper.test_signal.signal_t.keys()
+    m1 = helper.compute_model("qsft", {"num_subsample": 3, "num_repeat": 2, "b": 4, "noise_sd": 0.0})
+    m2 = helper2.compute_model("qsft", {"num_subsample": 3, "num_repeat": 2, "b": 4, "noise_sd": 0.0})
+    assert set(m1.keys()) == set(m2.keys()) == set(sw.keys())

@@ -273,3 +273,53 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     bad(L.qsft_singleton_detect(one, 4, 4, 10, 10, 5, 1, 0, 0, 0, null, null, one, 3, null), "ld_out")
     bad(L.qsft_detect_mle(one, 4, 0, one, 5, one, null, null), "positive")
     assert L.qsft_detect_mle(null, 0, 3, null, 5, null, null, null) == 0
+
+
+def test_experiment_harness_host_logic(tmp_path):
+    """TestHelper / run_tests plumbing with a stand-in signal factory (no GPU): folders, query_args per method,
+    config.json, the sweep table's columns and order (qsft/test_helper.py, qsft/parallel_tests.py)."""
+    import json
+    from qsft_b200.parallel_tests import run_tests
+    from qsft_b200.test_helper import TestHelper
+
+    made = []
+
+    class FakeSignal:
+        def __init__(self, **kw):
+            self.kw, self.noise_sd, self.signal_t = kw, kw.get("noise_sd"), {3: 1.0 + 0j, 5: 2.0 + 0j}
+            made.append(self)
+
+    class Helper(TestHelper):
+        def generate_signal(self, signal_args):
+            return FakeSignal(**signal_args)
+
+        def compute_model(self, method, model_kwargs, report=False, verbosity=0):
+            sig = self.train_signal if method == "qsft" else self.train_signal_coded
+            sig.noise_sd = model_kwargs["noise_sd"]
+            return {"gwht": {(0, 1): 1.0, (1, 1): 2.0}, "runtime": 0.5, "n_samples": model_kwargs["n_samples"],
+                    "locations": [], "max_hamming_weight": 2, "avg_hamming_weight": 1.5}
+
+        def test_model(self, method, **kwargs):
+            return 0.25 * len(kwargs["beta"])
+
+    sub = {"num_subsample": 3, "num_repeat": 2, "b": 4, "all_bs": [3, 4]}
+    h = Helper(signal_args={"n": 6, "q": 3, "t": 2, "locq": None, "strengths": None}, methods=["qsft", "qsft_coded"],
+               subsampling_args=sub, test_args={"n_samples": 100}, exp_dir=tmp_path)
+    assert json.load(open(tmp_path / "config.json")) == {"query_args": sub}
+    train, coded, test = made
+    assert train.kw["folder"] == tmp_path / "train" and coded.kw["folder"] == tmp_path / "train_coded"
+    assert train.kw["query_args"] == {**sub, "subsampling_method": "qsft", "query_method": "complex",
+                                      "delays_method_source": "identity", "delays_method_channel": "nso"}
+    assert coded.kw["query_args"]["delays_method_source"] == "coded" and coded.kw["query_args"]["t"] == 2
+    assert test.kw["query_args"] == {"subsampling_method": "uniform", "n_samples": 100} and test.kw["noise_sd"] == 0
+    assert (tmp_path / "test").is_dir() and sub == {"num_subsample": 3, "num_repeat": 2, "b": 4, "all_bs": [3, 4]}
+    df = run_tests("qsft", h, 2, [2, 3], [1], [3, 4], [0.1], parallel=False)
+    assert list(df.columns) == ["num_subsample", "num_repeat", "b", "noise_sd", "iter", "n", "q", "runtime",
+                                "found_sparsity", "n_samples", "ratio_samples", "max_hamming_weight", "nmse", "method"]
+    assert len(df) == 8 and list(df["b"][:4]) == [3, 3, 4, 4] and list(df["iter"][:2]) == [0, 1]
+    assert df["n_samples"][0] == 2 * 3 ** 3 * 1 * 7 and df["nmse"][0] == 0.5 and df["found_sparsity"][0] == 2
+    assert abs(df["ratio_samples"][0] - 2 * 27 * 7 / 3 ** 6) < 1e-12 and train.noise_sd == 0.1
+    with pytest.raises(NotImplementedError):
+        Helper(signal_args={"n": 6, "q": 3}, methods=["lasso"], subsampling_args=sub, test_args={}, exp_dir=tmp_path)
+    with pytest.raises(NotImplementedError):
+        TestHelper.compute_model(h, "gwht", {})
