@@ -221,6 +221,10 @@ if __name__ == "__main__":
         run_case("q3_n9_b3_nso2", 14, n=9, q=3, S=20, b=3, C=3, R=2, src="identity", chan="nso", noise_sd=0.0,
                  nso_subtype="nso2", store_samples=False)
         sys.exit(0)
+    if "--wide" in sys.argv:           # BASELINE config 4 shape, reduced: 100-bit indices through the whole reference pipeline
+        run_case("cfg4r_q4_n50_b4_lowweight_nso_noisy", 21, n=50, q=4, S=30, b=4, C=3, R=3, src="identity", chan="nso",
+                 noise_sd=float(np.sqrt(30 / 1000.0)), max_weight=3)
+        sys.exit(0)
     # BASELINE config 1 (seed 20 = quick_example convention)
     run_case("cfg1_q4_n10_b4_identity", 20, n=10, q=4, S=100, b=4, C=3, R=1, src="identity", chan="identity", noise_sd=0.0)
     # config-2 shaped, reduced: nso R=3, 20 dB  (noise_sd = sqrt(S / 10^(SNR/10)))

@@ -6,13 +6,13 @@ import pytest
 import torch
 
 import qsft_oracle as orc
-from conftest import NSO2_CASES, case_params, load_golden
+from conftest import NSO2_CASES, WIDE_FULL_CASES, case_params, load_golden, u128_to_ints
 
 pytestmark = pytest.mark.gpu
 
 if torch.cuda.is_available():
     import qsft_b200
-    from qsft_b200 import ops, reconstruct
+    from qsft_b200 import ops, reconstruct, utils
     DEV = torch.device("cuda", 0)
 
 
@@ -191,3 +191,50 @@ def test_synthetic_helper_sweep_end_to_end(tmp_path):
     m1 = helper.compute_model("qsft", {"num_subsample": 3, "num_repeat": 2, "b": 4, "noise_sd": 0.0})
     m2 = helper2.compute_model("qsft", {"num_subsample": 3, "num_repeat": 2, "b": 4, "noise_sd": 0.0})
     assert set(m1.keys()) == set(m2.keys()) == set(sw.keys())
+
+
+@pytest.mark.parametrize("name", WIDE_FULL_CASES)
+def test_wide_index_pipeline_matches_reference(name):
+    """BASELINE config 4 shape (q=4, n=50: 100-bit indices, weight <= 3 support, nso R=3, 30 dB), reduced to b=4, against
+    a full run of the unmodified reference: lattice indices (hi, lo limbs), samples, bins, peel from the reference's
+    bins, and the same-seed end-to-end transform."""
+    g = load_golden(name)
+    p = case_params(g)
+    q, n, b = p["q"], p["n"], p["b"]
+    assert utils.index_limbs(q, n) == 2
+    # K1: indices of group (0, 0)
+    idx, _ = ops.query_lattice(g["Ms"][0], g["Ds"][0], q, device=DEV)
+    host = idx.cpu().numpy().view(np.uint64)
+    assert np.array_equal(host[..., 0], g["idx00_hi"]) and np.array_equal(host[..., 1], g["idx00_lo"])
+    # construct (K1 + K2 + K3) with the reference's seed
+    np.random.seed(p["seed"])
+    sig = qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=p["S"], a_min=1, a_max=1, noise_sd=p["noise_sd"],
+                                                  query_args=dict(p["query_args"]), max_weight=p["max_weight"])
+    assert np.array_equal(np.array(sig.Ms), g["Ms"]) and np.array_equal(np.array(sig.Ds[0]), g["Ds"])
+    got = sig.subsample(u128_to_ints(g["idx00_hi"][1], g["idx00_lo"][1]))
+    assert np.max(np.abs(got - g["samples00_row1"])) <= 1e-5 * max(1.0, np.max(np.abs(g["samples00_row1"])))
+    mine = np.array([[sig.Us[i][j][b].cpu().numpy() for j in range(p["R"])] for i in range(p["C"])])
+    assert np.max(np.abs(mine - g[f"Us_b{b}"])) <= 1e-5 * np.max(np.abs(g[f"Us_b{b}"]))
+    # end to end, same seed: same support, NMSE within 1 % of the reference's
+    sft = qsft_b200.QSFT(num_subsample=p["trC"], num_repeat=p["trR"], b=p["trb"], reconstruct_method_source=p["src"],
+                         reconstruct_method_channel=p["chan"])
+    res = sft.transform(sig, report=True, sort=True)
+    assert np.random.random() == float(g["rng_probe"])
+    want_keys = [tuple(int(v) for v in k) for k in g["res_keys"]]
+    assert set(res["gwht"].keys()) == set(want_keys)
+    vals = np.array([res["gwht"][k] for k in want_keys])
+    assert np.max(np.abs(vals - g["res_vals"])) <= 1e-4
+    true_w = dict(zip(map(tuple, g["locq"].T.tolist()), g["strengths"]))
+    nm_ref, nm_got = orc.nmse(dict(zip(want_keys, g["res_vals"])), true_w), orc.nmse(res["gwht"], true_w)
+    assert abs(nm_got - nm_ref) <= 0.01 * nm_ref + 1e-12
+    assert res["n_samples"] == int(g["n_samples"]) and res["max_hamming_weight"] == int(g["max_hw"])
+    # K4 alone on the reference's own noisy bins: same finds in the same first-seen order
+    U = torch.from_numpy(np.ascontiguousarray(g["mdu_Us"].reshape(p["trC"], -1, q ** p["trb"])).astype(np.complex64)).to(DEV)
+    D = g["mdu_Ds"].reshape(p["trC"], -1, n)
+    prob = ops.PeelProblem(q, n, p["trb"], list(g["mdu_Ms"]), D, p["P_src"], p["chan"], p["src"],
+                           1e-9 + 1.5 * p["noise_sd"] ** 2 / q ** p["trb"], DEV)
+    prob.alloc(4 * U.shape[0] * U.shape[2])
+    prob.peel(U)
+    dk, dv, _ = prob.distinct()
+    assert [tuple(int(v) for v in r) for r in dk] == want_keys
+    assert np.max(np.abs(dv - g["res_vals"])) <= 1e-5 * np.max(np.abs(g["res_vals"]))

@@ -5,7 +5,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import FULL_CASES, INDEX_CASES, ROOT, case_params, load_golden, u128_to_ints
+from conftest import FULL_CASES, WIDE_FULL_CASES, INDEX_CASES, ROOT, case_params, load_golden, u128_to_ints
 
 
 def test_library_loads_and_exports_every_declared_symbol():
@@ -42,7 +42,7 @@ def test_product_does_not_import_oracle():
                 assert "qsft_oracle" not in src and "import oracle" not in src and "/root/reference" not in src, f
 
 
-@pytest.mark.parametrize("name", FULL_CASES)
+@pytest.mark.parametrize("name", FULL_CASES + WIDE_FULL_CASES)
 def test_host_rng_order_matches_reference(name):
     """generate_signal_w -> get_Ms_and_Ds consume np.random like the reference (same seed, same arrays)."""
     from qsft_b200.synthetic_signal import generate_signal_w

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import qsft_oracle as orc
-from conftest import FULL_CASES, INDEX_CASES, NSO2_CASES, case_params, load_golden, u128_to_ints
+from conftest import FULL_CASES, WIDE_FULL_CASES, INDEX_CASES, NSO2_CASES, case_params, load_golden, u128_to_ints
 
 
 def build(g):
@@ -16,7 +16,7 @@ def build(g):
     return p, sig
 
 
-@pytest.mark.parametrize("name", FULL_CASES)
+@pytest.mark.parametrize("name", FULL_CASES + WIDE_FULL_CASES)
 def test_full_pipeline_matches_reference(name):
     g = load_golden(name)
     p, sig = build(g)
@@ -53,7 +53,7 @@ def test_full_pipeline_matches_reference(name):
     assert abs(res["avg_hamming_weight"] - float(g["avg_hw"])) < 1e-12
 
 
-@pytest.mark.parametrize("name", FULL_CASES)
+@pytest.mark.parametrize("name", FULL_CASES + WIDE_FULL_CASES)
 def test_closed_form_bins_identity(name):
     g = load_golden(name)
     p = case_params(g)
