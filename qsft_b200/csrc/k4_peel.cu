@@ -7,6 +7,8 @@
 // U per round).  Rounds are synchronous like the reference: classify on a frozen U, then subtract.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int K4_THREADS = 128;
@@ -420,6 +422,192 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// classification, version 2 (opt-in: QSFT_K4_IMPL=2; written at the end of round 1 without GPU time -- NOT YET
+// MEASURED, the default stays version 1 above).  Same decisions and outputs as k4_classify_kernel.
+//   CTA = 256 consecutive bins of one group.  Phase 1 (thread = bin) streams the tile's columns through the energy sum
+//   AND into shared memory (every global byte is read once, coalesced); the CTA compacts its candidate bins; phase 2
+//   gives every candidate a group of 8 lanes (lanes over delay rows / symbols / hash digits: P = 41 -> 6 iterations at
+//   85 % lane utilisation instead of 2 at 64 %, 3-step group reductions, columns / D / M^T rows from shared memory).
+//   Shared layout: columns [P][257] float2 (odd stride: the 8 lanes of a group hit 8 different banks), D rows and M^T rows
+//   with stride ld + 16 bytes (conflict-free 16-byte loads), symbols [32 groups][4 NW].
+// Identity source decoding only (coded delays fall back to version 1).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int K4V2_THREADS = 256;
+constexpr int K4V2_COLS = K4V2_THREADS + 1;     // padded column stride (float2 elements)
+constexpr int K4V2_G = 8;                       // lanes per candidate bin
+
+template <int NW>
+__device__ __forceinline__ int dot_raw_s(const int8_t* row, int ld, const uint32_t (&kw)[NW]) {   // row in shared memory
+    const uint4* r4 = reinterpret_cast<const uint4*>(row);
+    const int nv = ld >> 4;
+    int acc = 0;
+#pragma unroll
+    for (int w = 0; w < NW / 4; ++w) {
+        if (w >= nv) break;
+        const uint4 v = r4[w];
+        acc = dp4a_u(v.x, kw[4 * w + 0], acc);
+        acc = dp4a_u(v.y, kw[4 * w + 1], acc);
+        acc = dp4a_u(v.z, kw[4 * w + 2], acc);
+        acc = dp4a_u(v.w, kw[4 * w + 3], acc);
+    }
+    return acc;
+}
+
+static size_t k4v2_smem_bytes(const PeelDev& d, int nw) {
+    return (size_t)d.P * K4V2_COLS * sizeof(float2) + 16 +             // columns (+ alignment slack)
+           (size_t)(d.P + d.b) * (d.ld + 16) +                           // D rows, M^T rows
+           (size_t)(K4V2_THREADS / K4V2_G) * 4 * nw;                     // symbols
+}
+
+template <int NW>
+__global__ void __launch_bounds__(K4V2_THREADS, 2)
+k4_classify_v2_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, long long j_end,
+                      long long* __restrict__ find_cj, int8_t* __restrict__ find_k, float2* __restrict__ find_rho,
+                      int32_t* __restrict__ find_round, int32_t* __restrict__ find_id, long long max_finds, int round,
+                      unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char k4v2_smem[];
+    __shared__ double2 s_tw[QSFT_MAX_Q + 1];
+    __shared__ double s_energy[K4V2_THREADS];
+    __shared__ int s_cand[K4V2_THREADS];
+    __shared__ int s_wcnt[K4V2_THREADS / 32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = blockIdx.y;
+    const long long B = d.B;
+    const int rs = d.ld + 16;                                            // padded row stride of the D / M^T copies
+    float2* s_col = reinterpret_cast<float2*>(k4v2_smem);
+    size_t off = ((size_t)d.P * K4V2_COLS * sizeof(float2) + 15) & ~(size_t)15;
+    int8_t* s_D = reinterpret_cast<int8_t*>(k4v2_smem + off);
+    int8_t* s_MT = s_D + (size_t)d.P * rs;
+    uint8_t* s_sym = reinterpret_cast<uint8_t*>(s_MT + (size_t)d.b * rs);
+
+    // phase 0: tables
+    if (tid < d.q) {
+        double sn, cs;
+        sincospi(2.0 * (double)tid / (double)d.q, &sn, &cs);
+        s_tw[tid] = make_double2(cs, sn);
+    }
+    {
+        const int vpr = d.ld >> 4;                                       // 16-byte vectors per row
+        const uint4* gD = reinterpret_cast<const uint4*>(d.D + (size_t)c * d.P * d.ld);
+        for (int e = tid; e < d.P * vpr; e += K4V2_THREADS) {
+            const int r = e / vpr, v = e - r * vpr;
+            *reinterpret_cast<uint4*>(s_D + (size_t)r * rs + 16 * v) = __ldg(gD + e);
+        }
+        const uint4* gM = reinterpret_cast<const uint4*>(d.MT + (size_t)c * d.b * d.ld);
+        for (int e = tid; e < d.b * vpr; e += K4V2_THREADS) {
+            const int r = e / vpr, v = e - r * vpr;
+            *reinterpret_cast<uint4*>(s_MT + (size_t)r * rs + 16 * v) = __ldg(gM + e);
+        }
+    }
+
+    // phase 1: energy (same summation order as version 1) + stash of the columns
+    const long long j0 = j_begin + (long long)blockIdx.x * K4V2_THREADS;
+    const long long j = j0 + tid;
+    const float2* Uc = U + (size_t)c * d.P * B;
+    double energy = 0.0;
+    if (j < j_end) {
+        const float2* gcol = Uc + j;
+#pragma unroll 8
+        for (int p = 0; p < d.P; ++p) {
+            const float2 v = gcol[(size_t)p * B];
+            s_col[(size_t)p * K4V2_COLS + tid] = v;
+            energy += (double)v.x * v.x + (double)v.y * v.y;
+        }
+        if (!(energy > d.thresh)) find_id[(size_t)c * B + j] = -1;
+    }
+    s_energy[tid] = energy;
+    const bool cand = (j < j_end) && (energy > d.thresh);
+    const unsigned cbal = __ballot_sync(0xffffffffu, cand);
+    if (lane == 0) s_wcnt[warp] = __popc(cbal);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < K4V2_THREADS / 32; ++w) {
+        const int n = s_wcnt[w];
+        base += (w < warp) ? n : 0;
+        total += n;
+    }
+    if (cand) s_cand[base + __popc(cbal & ((1u << lane) - 1u))] = tid;
+    __syncthreads();
+    if (total == 0) return;
+
+    // phase 2: one 8-lane group per candidate bin
+    const int grp = tid / K4V2_G, gl = tid % K4V2_G;
+    const int nsym = d.P_src - 1;
+    uint8_t* sym = s_sym + (size_t)grp * (4 * NW);
+    const int iters = (total + K4V2_THREADS / K4V2_G - 1) / (K4V2_THREADS / K4V2_G);
+    unsigned n_multi = 0;
+    for (int it = 0; it < iters; ++it) {                                 // uniform trip count: the shuffles below use full masks
+        const int ci = it * (K4V2_THREADS / K4V2_G) + grp;
+        const bool valid = ci < total;
+        const int my = s_cand[valid ? ci : 0];
+        const long long jb = j0 + my;
+        const float2* col = s_col + my;                                  // element p of the column = col[p * K4V2_COLS]
+
+        for (int i = 1 + gl; i <= nsym; i += K4V2_G) sym[i - 1] = (uint8_t)detect_symbol(d, col, (size_t)K4V2_COLS, i);
+        for (int i = nsym + gl; i < 4 * NW; i += K4V2_G) sym[i] = 0;     // identity source: k = the n = P_src - 1 symbols
+        __syncwarp();
+        uint32_t kw[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) kw[w] = reinterpret_cast<const uint32_t*>(sym)[w];
+
+        double rr = 0.0, ri = 0.0;
+        for (int p = gl; p < d.P; p += K4V2_G) {
+            const int t = fast_mod(dot_raw_s<NW>(s_D + (size_t)p * rs, d.ld, kw), d.q, d.qmagic);
+            const double cs = s_tw[t].x, sn = s_tw[t].y;
+            const float2 v = col[(size_t)p * K4V2_COLS];
+            rr += cs * v.x + sn * v.y;
+            ri += cs * v.y - sn * v.x;
+        }
+        long long part = 0;
+        for (int i = gl; i < d.b; i += K4V2_G) {
+            long long wgt = 1;
+            for (int u = i + 1; u < d.b; ++u) wgt *= d.q;
+            part += wgt * fast_mod(dot_raw_s<NW>(s_MT + (size_t)i * rs, d.ld, kw), d.q, d.qmagic);
+        }
+#pragma unroll
+        for (int o = K4V2_G / 2; o > 0; o >>= 1) {                       // xor partners stay inside the aligned 8-lane group
+            rr += __shfl_xor_sync(0xffffffffu, rr, o);
+            ri += __shfl_xor_sync(0xffffffffu, ri, o);
+            part += __shfl_xor_sync(0xffffffffu, part, o);
+        }
+        rr *= d.invP;
+        ri *= d.invP;
+        const double res = s_energy[my] - (double)d.P * (rr * rr + ri * ri);
+        const bool single = valid && (part == jb) && !(res > d.thresh);
+        const bool lead = gl == 0;
+
+        const unsigned sb = __ballot_sync(0xffffffffu, lead && single);
+        unsigned long long fbase = 0;
+        if (lane == 0 && sb) fbase = atomicAdd(&counters[0], (unsigned long long)__popc(sb));
+        fbase = __shfl_sync(0xffffffffu, fbase, 0);
+        unsigned long long f = fbase + (unsigned long long)__popc(sb & ((1u << lane) - 1u));
+        f = __shfl_sync(0xffffffffu, f, lane & ~(K4V2_G - 1));           // the leader's slot for its whole group
+        if (single) {
+            if ((long long)f < max_finds) {
+                uint32_t* ko = reinterpret_cast<uint32_t*>(find_k + (size_t)f * d.ld);
+                for (int w = gl; w < d.ld / 4; w += K4V2_G) ko[w] = (w < NW) ? reinterpret_cast<const uint32_t*>(sym)[w] : 0u;
+                if (lead) {
+                    find_cj[f] = (long long)c * B + jb;
+                    find_rho[f] = make_float2((float)rr, (float)ri);
+                    if (find_round) find_round[f] = round;
+                    find_id[(size_t)c * B + jb] = (int32_t)f;
+                }
+            } else if (lead) {
+                find_id[(size_t)c * B + jb] = -1;
+            }
+        } else if (valid && lead) {
+            find_id[(size_t)c * B + jb] = -1;
+            ++n_multi;
+        }
+        __syncwarp();                                                    // sym is rewritten in the next iteration
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_multi += __shfl_xor_sync(0xffffffffu, n_multi, o);
+    if (lane == 0 && n_multi) atomicAdd(&counters[1], (unsigned long long)n_multi);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // apply: one warp per find
 // ---------------------------------------------------------------------------------------------------------
 template <int NW>
@@ -738,8 +926,33 @@ int reduce_nw(const PeelDev& d, const long long* cj, const int8_t* fk, const flo
         return fn<32>(__VA_ARGS__);                        \
     } while (0)
 
+template <int NW>
+int classify_v2_nw(const PeelDev& d, const float2* U, long long jb, long long je, long long* cj, int8_t* fk, float2* rho,
+                   int32_t* frd, int32_t* fid, long long maxf, int round, unsigned long long* counters, cudaStream_t st) {
+    const size_t smem = k4v2_smem_bytes(d, NW);
+    static size_t configured = 0;                            // per template instance
+    if (smem > configured) {
+        QSFT_CUDA(cudaFuncSetAttribute(k4_classify_v2_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)((je - jb + K4V2_THREADS - 1) / K4V2_THREADS), (unsigned)d.C);
+    k4_classify_v2_kernel<NW><<<grid, K4V2_THREADS, smem, st>>>(d, U, jb, je, cj, fk, rho, frd, fid, maxf, round, counters);
+    QSFT_LAUNCHED();
+    return QSFT_OK;
+}
+
+// QSFT_K4_IMPL=2 selects the shared-memory / 8-lane-group classification when the problem fits it (identity source
+// decoding, tile <= 100 KB of shared memory so that two CTAs stay resident); read on every call.
+static bool k4_use_v2(const PeelDev& d) {
+    const char* e = getenv("QSFT_K4_IMPL");
+    if (!e || atoi(e) != 2 || d.source != 0) return false;
+    const int nw = d.ld / 4 <= 4 ? 4 : d.ld / 4 <= 8 ? 8 : d.ld / 4 <= 16 ? 16 : 32;
+    return k4v2_smem_bytes(d, nw) <= 100 * 1024;
+}
+
 int do_classify(const PeelDev& d, const float2* U, long long jb, long long je, long long* cj, int8_t* fk, float2* rho,
                 int32_t* frd, int32_t* fid, long long maxf, int round, unsigned long long* counters, cudaStream_t st) {
+    if (k4_use_v2(d)) QSFT_NW_DISPATCH(classify_v2_nw, d, U, jb, je, cj, fk, rho, frd, fid, maxf, round, counters, st);
     QSFT_NW_DISPATCH(classify_nw, d, U, jb, je, cj, fk, rho, frd, fid, maxf, round, counters, st);
 }
 

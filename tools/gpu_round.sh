@@ -13,6 +13,9 @@ set -x
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $out/${tag}_gpu.csv 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log
 timeout 300 python tools/microbench.py > $out/${tag}_microbench.json 2> $out/${tag}_microbench.err
+# opt-in kernels written without GPU time (K4 classification v2): parity against the default kernel, then its timings
+QSFT_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_detectors.py -k experimental -q > $out/${tag}_pytest_experimental.log 2>&1
+QSFT_K4_IMPL=2 timeout 300 python tools/microbench.py > $out/${tag}_microbench_k4v2.json 2> $out/${tag}_microbench_k4v2.err
 timeout 600 python bench.py > $out/${tag}_bench_N1.json 2> $out/${tag}_bench_N1.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 0 > $out/${tag}_bench_reference.json 2> /dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
