@@ -225,6 +225,10 @@ if __name__ == "__main__":
         run_case("cfg4r_q4_n50_b4_lowweight_nso_noisy", 21, n=50, q=4, S=30, b=4, C=3, R=3, src="identity", chan="nso",
                  noise_sd=float(np.sqrt(30 / 1000.0)), max_weight=3)
         sys.exit(0)
+    if "--wide2" in sys.argv:          # q = 2 with 100-bit indices, noiseless identity delays (P_src = 101), loaded bins
+        run_case("q2_n100_b5_identity_wide", 22, n=100, q=2, S=14, b=5, C=3, R=1, src="identity", chan="identity",
+                 noise_sd=0.0)
+        sys.exit(0)
     # BASELINE config 1 (seed 20 = quick_example convention)
     run_case("cfg1_q4_n10_b4_identity", 20, n=10, q=4, S=100, b=4, C=3, R=1, src="identity", chan="identity", noise_sd=0.0)
     # config-2 shaped, reduced: nso R=3, 20 dB  (noise_sd = sqrt(S / 10^(SNR/10)))

@@ -32,7 +32,8 @@ def u128_to_ints(hi, lo):
 
 FULL_CASES = ["cfg1_q4_n10_b4_identity", "cfg2r_q4_n14_b5_nso_noisy", "q3_n12_b4_lowweight_nso",
               "q2_n12_b4_simple", "q4_n10_allbs_subselect", "q5_n6_b3_identity_noisy"]
-WIDE_FULL_CASES = ["cfg4r_q4_n50_b4_lowweight_nso_noisy"]   # BASELINE config 4 shape (100-bit indices), reduced
+WIDE_FULL_CASES = ["cfg4r_q4_n50_b4_lowweight_nso_noisy",    # BASELINE config 4 shape (100-bit indices), reduced
+                   "q2_n100_b5_identity_wide"]               # q = 2, 100-bit indices, P_src = 101
 NSO2_CASES = ["q4_n10_b4_nso2_noisy", "q3_n9_b3_nso2"]      # reference run with nso_subtype="nso2" (see gen_golden.py)
 INDEX_CASES = ["idx_q4_n40_b3", "idx_q4_n50_b2", "idx_q3_n45_b3", "idx_q7_n22_b2", "idx_q2_n100_b5"]
 

@@ -8,7 +8,14 @@ import torch
 import qsft_oracle as orc
 from conftest import NSO2_CASES, WIDE_FULL_CASES, case_params, load_golden, u128_to_ints
 
-pytestmark = pytest.mark.gpu
+import os
+
+# Everything in this file exercises code written at the end of round 1, after the round's GPU budget was spent: none of it
+# has run on a GPU yet.  It is skipped by default so that the default `-m gpu` suite only contains validated tests;
+# `QSFT_TEST_UNVALIDATED=1 pytest tests/test_gpu_zz_detectors.py` (first step of tools/gpu_round.sh) runs it.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("QSFT_TEST_UNVALIDATED") != "1" and os.environ.get("QSFT_TEST_EXPERIMENTAL") != "1",
+                                 reason="first GPU run pending (set QSFT_TEST_UNVALIDATED=1)")]
 
 if torch.cuda.is_available():
     import qsft_b200
@@ -241,8 +248,6 @@ def test_wide_index_pipeline_matches_reference(name):
 
 
 # ---- experimental kernels (opt-in, written without GPU time; run with QSFT_TEST_EXPERIMENTAL=1) ---------------------
-import os  # noqa: E402
-
 experimental = pytest.mark.skipif(os.environ.get("QSFT_TEST_EXPERIMENTAL") != "1",
                                   reason="opt-in kernels not yet validated on a GPU (set QSFT_TEST_EXPERIMENTAL=1)")
 

@@ -12,6 +12,8 @@ mkdir -p $out
 set -x
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $out/${tag}_gpu.csv 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log
+# tests of the code written without GPU time (detectors, nso2, harness, 100-bit pipelines): no -x, every failure is wanted
+QSFT_TEST_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_zz_detectors.py -m gpu -q -k "not experimental" > $out/${tag}_pytest_unvalidated.log 2>&1
 timeout 300 python tools/microbench.py > $out/${tag}_microbench.json 2> $out/${tag}_microbench.err
 # opt-in kernels written without GPU time (K4 classification v2): parity against the default kernel, then its timings
 QSFT_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_detectors.py -k experimental -q > $out/${tag}_pytest_experimental.log 2>&1
