@@ -134,6 +134,15 @@ def test_field_polynomials_are_matlab_defaults():
         assert gf_irreducible_p([ZZ(c) for c in coeffs], p, ZZ)
         # primitive: x generates all p^m - 1 non-zero elements
         assert len(set(int(v) for v in h.exp[: p ** m - 1])) == p ** m - 1
+        # antilog table == x^e mod f computed independently by sympy's GF(p)[x] arithmetic
+        from sympy.polys.galoistools import gf_pow_mod
+        f = [ZZ(c) for c in coeffs]
+        for e in list(range(0, min(p ** m - 1, 40))) + [p ** m - 2]:
+            r = gf_pow_mod([ZZ(1), ZZ(0)], e, f, p, ZZ) or [ZZ(0)]
+            val = 0
+            for cdig in r:                                  # high degree first -> base-p integer
+                val = val * p + int(cdig) % p
+            assert int(h.exp[e]) == val == int(o.exp[e]), (p, m, e)
 
 
 def test_finds_to_dict_matches_reference_averaging():
