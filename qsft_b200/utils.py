@@ -113,3 +113,40 @@ class NpEncoder(json.JSONEncoder):
         if isinstance(obj, np.ndarray):
             return obj.tolist()
         return super().default(obj)
+
+
+def _gwht_device(x, q, n, inverse):
+    """K3 on one dense vector: numpy / tensor of q^n complex values -> NumPy complex128 (same shape)."""
+    import torch
+    from . import ops
+    if not torch.cuda.is_available():
+        raise RuntimeError("qsft_b200 needs a CUDA device (there is no CPU fallback)")
+    a = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+    shape = a.shape
+    if a.size != q ** n:
+        raise ValueError(f"expected q^n = {q ** n} values, got {a.size}")
+    v = np.ascontiguousarray(a.reshape(1, -1), dtype=np.complex64)
+    if inverse:
+        v = np.conj(v)
+    t = ops.gwht_batch_(torch.from_numpy(v).cuda(), q, n)
+    out = t.cpu().numpy().astype(np.complex128).reshape(shape)
+    return np.conj(out) * float(q ** n) if inverse else out
+
+
+def gwht(x, q, n):
+    """Dense q-ary Fourier transform with forward scaling 1/q^n (qsft/utils.py:31-36), computed by the K3 kernel."""
+    return _gwht_device(x, q, n, False)
+
+
+def igwht(x, q, n):
+    """Inverse of gwht (qsft/utils.py:44-49): ifftn * q^n = conj(gwht(conj(x))) * q^n."""
+    return _gwht_device(x, q, n, True)
+
+
+def gwht_tensored(x, q, n):
+    """gwht of an array already shaped [q] * n (qsft/utils.py:38-41)."""
+    return _gwht_device(x, q, n, False)
+
+
+def igwht_tensored(x, q, n):
+    return _gwht_device(x, q, n, True)

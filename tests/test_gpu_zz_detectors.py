@@ -323,3 +323,18 @@ def test_experimental_k4_v2_full_peel_config2_shape(monkeypatch):
                                    reconstruct_method_channel="nso").transform(sig)
     assert list(out[1].keys()) == list(out[2].keys())
     assert max(abs(out[1][k] - out[2][k]) for k in out[1]) < 1e-5
+
+
+def test_dense_gwht_igwht_utils():
+    """utils.gwht / igwht (the reference's dense helpers, qsft/utils.py:31-49) on the K3 kernel."""
+    g = load_golden("gwht_units")
+    for key in g.files:
+        if key.startswith("x_"):
+            _, qs, bs = key.split("_")
+            q, b = int(qs[1:]), int(bs[1:])
+            y = utils.gwht(g[key], q, b)
+            assert np.max(np.abs(y - g["y" + key[1:]])) <= 1e-6 * np.max(np.abs(g[key]))
+            back = utils.igwht(g["y" + key[1:]], q, b)
+            assert np.max(np.abs(back - g[key])) <= 1e-5 * np.max(np.abs(g[key]))
+            shaped = utils.gwht_tensored(g[key].reshape([q] * b), q, b)
+            assert shaped.shape == tuple([q] * b) and np.max(np.abs(shaped.ravel() - y)) == 0
