@@ -332,3 +332,19 @@ def test_experiment_harness_host_logic(tmp_path):
         Helper(signal_args={"n": 6, "q": 3}, methods=["lasso"], subsampling_args=sub, test_args={}, exp_dir=tmp_path)
     with pytest.raises(NotImplementedError):
         TestHelper.compute_model(h, "gwht", {})
+
+
+def test_rs_parity_check_matrix_known_answer():
+    """Known answer for the Reed-Solomon conventions (field polynomial, H[j, i] = (alpha^(1+j))^(nt-1-i), degree-descending
+    vectors): the first rows of galois.ReedSolomon(15, 9).H over GF(2^4) as printed in the galois documentation (quoted
+    from memory -- galois itself is not installed here), recovered from the delay matrix of ReedSolomon(n=15, t=3, q=2)."""
+    import qsft_oracle as orc
+    from qsft_b200.reed_solomon import ReedSolomon
+    want = [[9, 13, 15, 14, 7, 10, 5, 11, 12, 6, 3, 8, 4, 2, 1],
+            [13, 14, 10, 11, 6, 8, 2, 9, 15, 7, 5, 12, 3, 4, 1]]
+    for cls in (ReedSolomon, orc.RSCode):
+        rs = cls(15, 3, 2)
+        D = np.array(rs.get_delay_matrix())
+        assert D.shape == (2 * 3 * 4 + 1, 15) and not D[0].any()
+        H = [[int("".join(str(int(v)) for v in D[4 * j + 1:4 * j + 5, i]), 2) for i in range(15)] for j in range(2)]
+        assert H == want
