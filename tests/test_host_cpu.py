@@ -348,3 +348,27 @@ def test_rs_parity_check_matrix_known_answer():
         assert D.shape == (2 * 3 * 4 + 1, 15) and not D[0].any()
         H = [[int("".join(str(int(v)) for v in D[4 * j + 1:4 * j + 5, i]), 2) for i in range(15)] for j in range(2)]
         assert H == want
+
+
+def test_reconstruct_host_stage_and_dispatch_errors():
+    """reconstruct.singleton_detection_coded is the host-side source stage (reconstruct.py:34-51); dispatch errors are
+    raised before any device work."""
+    import qsft_oracle as orc
+    from qsft_b200 import get_reed_solomon_dec, reconstruct
+    n, t, q = 12, 2, 3
+    dec, odec = get_reed_solomon_dec(n, t, q), orc.get_reed_solomon_dec(n, t, q)
+    D = dec.__self__.get_delay_matrix()
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        k = np.zeros(n, dtype=int)
+        k[rng.choice(n, 2, replace=False)] = rng.integers(1, q, 2)
+        sym = (D[1:] @ k) % q
+        got = reconstruct.singleton_detection_coded(sym, source_decoder=dec)
+        assert got.dtype == np.int32 and np.array_equal(got, k)
+        assert np.array_equal(got, np.array(odec(list(sym))[0][0, :], dtype=np.int32))
+    with pytest.raises(TypeError):
+        reconstruct.singleton_detection(np.ones(5, dtype=complex), method_channel="bogus", q=3)
+    with pytest.raises(TypeError):
+        reconstruct.singleton_detection(np.ones(5, dtype=complex), method_source="bogus", method_channel="nso", q=3)
+    with pytest.raises(ValueError):
+        reconstruct.singleton_detection(np.ones(5, dtype=complex), method_source="coded", method_channel="nso", q=3)
