@@ -383,8 +383,17 @@ k3_q4_twopass_kernel(float2* __restrict__ x, long long B, int r1, int r2, long l
         if (threadIdx.x == 0) {
             unsigned int seen;
             do {
+#ifdef QSFT_EMU   // CPU execution by tests/emu runs the CTAs one after the other in ticket order: an unfinished dependency
+                  // could never complete, so it is reported instead of awaited (test infrastructure; never in the product build)
+                seen = *reinterpret_cast<volatile unsigned int*>(done + blk);
+                if (seen < (unsigned)tiles1) {
+                    emu_fail("k3 two-pass: a strided tile was scheduled before its block's contiguous tiles finished");
+                    seen = (unsigned)tiles1;
+                }
+#else
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + blk) : "memory");
                 if (seen < (unsigned)tiles1) __nanosleep(64);
+#endif
             } while (seen < (unsigned)tiles1);
         }
         __syncthreads();

@@ -1,0 +1,54 @@
+"""Builds tests/emu/_gen/libk4emu.so and libk3emu.so: the DEVICE source of qsft_b200/csrc/k4_peel.cu / k3_gwht.cu compiled
+by g++ against the CPU execution shim (cuda_emu.h) plus small host drivers (k4_emu.cpp, k3_emu.cpp).  Test infrastructure
+only."""
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+GEN = os.path.join(HERE, "_gen")
+LIB = os.path.join(GEN, "libk4emu.so")
+
+
+def _rewrite(body):
+    body = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+(?: \w+)*?) (\w+)\[\];",
+                  r"\1* \2 = reinterpret_cast<\1*>(emu_dyn_smem());", body)
+    return re.sub(r"\b__shared__\b", "static", body)
+
+
+def device_part(which="k4"):
+    if which == "k4":
+        src = open(os.path.join(ROOT, "qsft_b200", "csrc", "k4_peel.cu")).read()
+        start = src.index('#include "common.cuh"') + len('#include "common.cuh"')
+        end = src.index("int make_dev(")                  # host code (with <<< >>> launches) starts here
+        return _rewrite(src[start:end]) + "\n}  // namespace (closed by build_emu.py)\n"
+    src = open(os.path.join(ROOT, "qsft_b200", "csrc", "k3_gwht.cu")).read()
+    start = src.index('#include "common.cuh"') + len('#include "common.cuh"')
+    end = src.index("template <int Q>\nint launch_pass(")  # kernels + PassPlan / plan_pass (plain host code); launches follow
+    return _rewrite(src[start:end]) + "\n}  // namespace (closed by build_emu.py)\n"
+
+
+def build(force=False, which="k4"):
+    os.makedirs(GEN, exist_ok=True)
+    lib = os.path.join(GEN, f"lib{which}emu.so")
+    inc = os.path.join(GEN, f"{which}_device.inc")
+    cu = {"k4": "k4_peel.cu", "k3": "k3_gwht.cu"}[which]
+    text = device_part(which)
+    srcs = [os.path.join(HERE, f"{which}_emu.cpp"), os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "qsft_b200", "csrc", cu)]
+    fresh = os.path.exists(lib) and os.path.exists(inc) and open(inc).read() == text and \
+        all(os.path.getmtime(lib) >= os.path.getmtime(p) for p in srcs)
+    if fresh and not force:
+        return lib
+    open(inc, "w").write(text)
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-w", "-I/usr/local/cuda/include",
+           os.path.join(HERE, f"{which}_emu.cpp"), "-o", lib]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building the kernel emulation failed:\n" + res.stderr[-4000:])
+    return lib
+
+
+if __name__ == "__main__":
+    print(build(force=True, which="k4"))
+    print(build(force=True, which="k3"))

@@ -1,0 +1,186 @@
+"""CPU: the DEVICE source of the K4 kernels (qsft_b200/csrc/k4_peel.cu: classification v1 and the opt-in v2, reduce,
+apply, the stand-alone detectors) executed by the SIMT emulation in tests/emu (g++, one OS thread per CUDA thread) and
+compared with the fixtures of the unmodified reference.  This checks the kernels' LOGIC without a GPU -- indexing,
+reductions, decisions, the round loop; it says nothing about the memory model or speed, and it is test infrastructure:
+the product has no CPU path."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import FULL_CASES, NSO2_CASES, WIDE_FULL_CASES, case_params, load_golden
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import build_emu  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu():
+    L = C.CDLL(build_emu.build())
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+    desc = [i32] * 11 + [f32, vp, vp, vp, vp]
+    L.emu_classify.argtypes = desc + [vp, vp, vp, vp, vp, vp, i64, i32, vp, i32]
+    L.emu_peel.argtypes = desc + [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, i32,
+                                  C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    L.emu_detect.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32]
+    L.emu_mle.argtypes = [vp, i64, i32, vp, i32, vp, vp]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def padded_ld(n):
+    return max(32, (n + 31) // 32 * 32)
+
+
+class Problem:
+    """Host mirror of ops.PeelProblem for the emulated kernels."""
+
+    def __init__(self, q, n, b, Ms, Ds, P_src, channel, cutoff):
+        self.q, self.n, self.b, self.C = q, n, b, len(Ms)
+        Ds = np.asarray(Ds)
+        self.P, self.P_src, self.B, self.ld = Ds.shape[1], P_src, q ** b, padded_ld(n)
+        self.MT = np.zeros((self.C, b, self.ld), dtype=np.int8)
+        for c, M in enumerate(Ms):
+            self.MT[c, :, :n] = np.asarray(M).T
+        self.D = np.zeros((self.C, self.P, self.ld), dtype=np.int8)
+        self.D[:, :, :n] = Ds
+        self.channel, self.cutoff = channel, cutoff
+        mf = 4 * self.C * self.B
+        self.max_finds = mf
+        self.find_cj = np.zeros(mf, dtype=np.int64)
+        self.find_k = np.zeros((mf, self.ld), dtype=np.int8)
+        self.find_rho = np.zeros(mf, dtype=np.complex64)
+        self.find_round = np.zeros(mf, dtype=np.int32)
+        self.find_id = np.full((self.C, self.B), -7, dtype=np.int32)
+        self.counters = np.zeros(8, dtype=np.uint64)
+        self.seen0 = np.zeros(self.B, dtype=np.int32)
+        self.uk = np.zeros((mf, self.ld), dtype=np.int8)
+        self.usum = np.zeros(mf, dtype=np.complex64)
+        self.ucnt = np.zeros(mf, dtype=np.int32)
+        self.ukey = np.zeros(mf, dtype=np.int64)
+        self.unext = np.zeros(mf, dtype=np.int32)
+
+    def desc(self):
+        return [self.q, self.n, self.b, self.C, self.P, self.P_src, self.channel, 0, 0, 0, self.ld, C.c_float(self.cutoff),
+                _p(self.MT), _p(self.D), None, None]
+
+    def classify(self, L, U, impl):
+        self.counters[:] = 0
+        self.find_id[:] = -7
+        assert L.emu_classify(*self.desc(), _p(U), _p(self.find_cj), _p(self.find_k), _p(self.find_rho), _p(self.find_round),
+                              _p(self.find_id), self.max_finds, 1, _p(self.counters), impl) == 0
+        nf, nm = int(self.counters[0]), int(self.counters[1])
+        order = np.argsort(self.find_cj[:nf])
+        return {"nf": nf, "nm": nm, "cj": self.find_cj[:nf][order].copy(), "k": self.find_k[:nf][order].copy(),
+                "rho": self.find_rho[:nf][order].copy(), "fid": self.find_id.copy()}
+
+    def peel(self, L, U, impl):
+        nf, nu, nr = C.c_longlong(0), C.c_longlong(0), C.c_int(0)
+        rc = L.emu_peel(*self.desc(), _p(U), _p(self.find_cj), _p(self.find_k), _p(self.find_rho), _p(self.find_round),
+                        _p(self.find_id), self.max_finds, _p(self.seen0), _p(self.uk), _p(self.usum), _p(self.ucnt),
+                        _p(self.ukey), _p(self.unext), self.max_finds, impl, C.byref(nf), C.byref(nu), C.byref(nr))
+        assert rc == 0
+        nu = nu.value
+        order = np.argsort(self.ukey[:nu])
+        keys = [tuple(int(v) for v in r[:self.n]) for r in self.uk[:nu][order]]
+        vals = self.usum[:nu][order].astype(np.complex128) / self.ucnt[:nu][order]
+        return keys, vals, nf.value, nr.value
+
+
+def _problem_from_golden(g, p, nso_subtype="nso1"):
+    q, n = p["q"], p["n"]
+    U = np.ascontiguousarray(g["mdu_Us"].reshape(p["trC"], -1, q ** p["trb"])).astype(np.complex64)
+    D = g["mdu_Ds"].reshape(p["trC"], -1, n)
+    channel = 0 if p["chan"] == "identity" else (1 if nso_subtype == "nso1" else 2)
+    cutoff = 1e-9 + 1.5 * p["noise_sd"] ** 2 / q ** p["trb"]
+    return Problem(q, n, p["trb"], list(g["mdu_Ms"]), D, p["P_src"], channel, cutoff), U
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("name", FULL_CASES + WIDE_FULL_CASES)
+def test_emulated_peel_from_reference_bins(emu, name, impl):
+    """The kernels' round loop on the reference's own bins: same distinct coefficients in the same first-seen order."""
+    g = load_golden(name)
+    p = case_params(g)
+    prob, U = _problem_from_golden(g, p)
+    keys, vals, nf, nr = prob.peel(emu, U, impl)
+    want = [tuple(int(v) for v in k) for k in g["res_keys"]]
+    assert keys == want
+    assert np.max(np.abs(vals - g["res_vals"])) <= 1e-5 * np.max(np.abs(g["res_vals"]))
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("name", NSO2_CASES)
+def test_emulated_peel_nso2(emu, name, impl):
+    g = load_golden(name)
+    p = case_params(g)
+    prob, U = _problem_from_golden(g, p, "nso2")
+    keys, vals, _, _ = prob.peel(emu, U, impl)
+    assert keys == [tuple(int(v) for v in k) for k in g["res_keys"]]
+    assert np.max(np.abs(vals - g["res_vals"])) <= 1e-5 * np.max(np.abs(g["res_vals"]))
+
+
+@pytest.mark.parametrize("name", ["cfg2r_q4_n14_b5_nso_noisy", "q5_n6_b3_identity_noisy", "q2_n100_b5_identity_wide",
+                                  "q3_n12_b4_lowweight_nso"])
+def test_emulated_classify_v2_equals_v1(emu, name):
+    g = load_golden(name)
+    p = case_params(g)
+    prob, U = _problem_from_golden(g, p)
+    v1, v2 = prob.classify(emu, U, 1), prob.classify(emu, U, 2)
+    assert v1["nf"] == v2["nf"] > 0 and v1["nm"] == v2["nm"]
+    assert np.array_equal(v1["cj"], v2["cj"]) and np.array_equal(v1["k"], v2["k"])
+    assert np.max(np.abs(v1["rho"] - v2["rho"])) <= 2e-6 * max(1.0, np.max(np.abs(v1["rho"])))
+    assert np.array_equal(v1["fid"] >= 0, v2["fid"] >= 0) and not (v2["fid"] == -7).any() and not (v1["fid"] == -7).any()
+
+
+def test_emulated_detectors(emu):
+    g = load_golden("detect_units")
+    g2 = load_golden("detect_units2")
+    for gg, tag, channel in [(g, "nl_q4", 0), (g, "nl_q3", 0), (g, "nso_q4", 1), (g, "nso_q5", 1), (g, "nso_q2", 1),
+                             (g2, "nso2_q4", 2), (g2, "nso2_q3", 2), (g2, "nso2_q5", 2), (g2, "nso2_q2", 2), (g2, "nso2_q7", 2)]:
+        q, p1, R = (int(v) for v in gg[tag + "_meta"])
+        cols = np.ascontiguousarray(gg[tag + "_cols"].astype(np.complex64))
+        out = np.full((len(cols), 16), 99, dtype=np.int8)
+        assert emu.emu_detect(_p(cols), len(cols), q, 0, p1 * R, p1, channel, 0, 0, 0, None, None, _p(out), 16) == 0
+        assert np.array_equal(out[:, :p1 - 1], gg[tag + "_k"]) and not out[:, p1 - 1:].any(), tag
+    for tag in ["mle_q2", "mle_q3", "mle_q4"]:
+        cols = np.ascontiguousarray(g2[tag + "_cols"].astype(np.complex64))
+        S = np.ascontiguousarray(g2[tag + "_S"].astype(np.complex64))
+        ksel = np.zeros(len(cols), dtype=np.int32)
+        res = np.zeros(len(cols), dtype=np.float32)
+        assert emu.emu_mle(_p(cols), len(cols), S.shape[0], _p(S), S.shape[1], _p(ksel), _p(res)) == 0
+        assert np.array_equal(g2[tag + "_selection"][ksel], g2[tag + "_ksel"]), tag
+
+
+def test_emulated_detect_coded(emu):
+    """Channel stage + Reed-Solomon decode inside the detection kernel == oracle decode (incl. decoder failures)."""
+    import qsft_oracle as orc
+    from qsft_b200.reed_solomon import ReedSolomon
+    n, t, q, R = 12, 2, 3, 2
+    rs = ReedSolomon(n, t, q)
+    D = rs.get_delay_matrix()
+    odec = orc.get_reed_solomon_dec(n, t, q)
+    p1 = D.shape[0]
+    e, l = rs.device_tables()
+    e, l = np.ascontiguousarray(e, dtype=np.int32), np.ascontiguousarray(l, dtype=np.int32)
+    rng = np.random.default_rng(3)
+    cols, want = [], []
+    for i in range(40):
+        k = np.zeros(n, dtype=int)
+        w = int(rng.integers(0, t + 2))
+        k[rng.choice(n, w, replace=False)] = rng.integers(1, q, w)
+        off = rng.integers(0, q, (R, n))
+        ph = np.concatenate([((off[r] - D) % q) @ k % q for r in range(R)])
+        col = (1.3 - 0.4j) * np.exp(2j * np.pi * ph / q)
+        cols.append(col)
+        sym = orc.detect_nso1(col[:, None], q, p1)[:, 0]
+        want.append(np.array(odec(list(sym))[0][0, :], dtype=int))
+    cols = np.ascontiguousarray(np.array(cols).astype(np.complex64))
+    out = np.full((len(cols), 16), 99, dtype=np.int8)
+    assert emu.emu_detect(_p(cols), len(cols), q, n, p1 * R, p1, 1, 1, t, rs.s, _p(e), _p(l), _p(out), 16) == 0
+    assert np.array_equal(out[:, :n], np.array(want)) and not out[:, n:].any()
