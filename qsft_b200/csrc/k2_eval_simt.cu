@@ -11,9 +11,14 @@ constexpr int K2_QPT = 2;       // queries per thread (register tile)
 constexpr int K2_TS = 256;      // support rows staged per shared-memory tile
 
 __device__ __forceinline__ int dp4a_s32(uint32_t a, uint32_t b, int c) {
+#ifdef QSFT_EMU   // CPU execution of this kernel source by tests/emu (test infrastructure; never defined in the product build)
+    for (int i = 0; i < 4; ++i) c += (int)((a >> (8 * i)) & 255u) * (int)((b >> (8 * i)) & 255u);
+    return c;
+#else
     int d;
     asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
+#endif
 }
 
 // Q == 4: rotation table a_s * i^t staged per tile (exact: sign / swap).  Q == 0: generic q, twiddle LUT + complex FMA.

@@ -23,6 +23,16 @@ def device_part(which="k4"):
         start = src.index('#include "common.cuh"') + len('#include "common.cuh"')
         end = src.index("int make_dev(")                  # host code (with <<< >>> launches) starts here
         return _rewrite(src[start:end]) + "\n}  // namespace (closed by build_emu.py)\n"
+    if which == "k1":
+        src = open(os.path.join(ROOT, "qsft_b200", "csrc", "k1_lattice.cu")).read()
+        start = src.index('#include "common.cuh"') + len('#include "common.cuh"')
+        end = src.index('extern "C" int qsft_query_lattice(')   # the anonymous namespace is already closed here
+        return _rewrite(src[start:end])
+    if which == "k2":
+        src = open(os.path.join(ROOT, "qsft_b200", "csrc", "k2_eval_simt.cu")).read()
+        start = src.index('#include "common.cuh"') + len('#include "common.cuh"')
+        end = src.index("template <int NW>\nint launch_nw(")
+        return _rewrite(src[start:end]) + "\n}  // namespace (closed by build_emu.py)\n"
     src = open(os.path.join(ROOT, "qsft_b200", "csrc", "k3_gwht.cu")).read()
     start = src.index('#include "common.cuh"') + len('#include "common.cuh"')
     end = src.index("template <int Q>\nint launch_pass(")  # kernels + PassPlan / plan_pass (plain host code); launches follow
@@ -33,7 +43,7 @@ def build(force=False, which="k4"):
     os.makedirs(GEN, exist_ok=True)
     lib = os.path.join(GEN, f"lib{which}emu.so")
     inc = os.path.join(GEN, f"{which}_device.inc")
-    cu = {"k4": "k4_peel.cu", "k3": "k3_gwht.cu"}[which]
+    cu = {"k4": "k4_peel.cu", "k3": "k3_gwht.cu", "k1": "k1_lattice.cu", "k2": "k2_eval_simt.cu"}[which]
     text = device_part(which)
     srcs = [os.path.join(HERE, f"{which}_emu.cpp"), os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "qsft_b200", "csrc", cu)]
     fresh = os.path.exists(lib) and os.path.exists(inc) and open(inc).read() == text and \
@@ -52,3 +62,5 @@ def build(force=False, which="k4"):
 if __name__ == "__main__":
     print(build(force=True, which="k4"))
     print(build(force=True, which="k3"))
+    print(build(force=True, which="k1"))
+    print(build(force=True, which="k2"))

@@ -189,3 +189,7 @@ inline const char*& emu_failure() {
     return msg;
 }
 inline void emu_fail(const char* msg) { emu_failure() = msg; }
+
+inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
+    return (unsigned long long)(((unsigned __int128)a * b) >> 64);
+}
