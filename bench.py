@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--n", type=int, default=N_DIM)
     ap.add_argument("--eval-impl", type=int, default=0, help="K2 kernel: 0 auto, 1 SIMT, 2 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the untimed side checks run in subprocesses after the measurement (N = 1 only)")
     ap.add_argument("--peel-mode", default="auto", choices=["auto", "sharded", "replicated"],
                     help="multi-GPU peeling: bin-sharded with one all-gather per round, or replicated on every rank")
     return ap.parse_args()
@@ -397,9 +399,54 @@ def run_ours(a):
         secs, detail, sample, cores = cpu_reference_transform_seconds(a)
         line["cpu_baseline"] = {"value": 1.0 / secs, "unit": "transforms/s", "cores": cores, "kind": "port",
                                 "sample": sample, "detail": detail}
+    if a.gpus == 1 and not a.no_extras:
+        try:
+            torch.cuda.empty_cache()
+            line["extras"] = run_extras()
+        except Exception as exc:            # the side checks must never cost the measurement
+            line["extras"] = {"error": repr(exc)}
     print(json.dumps(line), flush=True)
     if dist is not None:
         td.destroy_process_group()
+
+
+def run_extras():
+    """Untimed side checks AFTER the measurement, each in its own subprocess (a failure or a crash there cannot touch the
+    numbers above): the GPU tests of code that was written after the round's interactive GPU budget was spent and are
+    therefore skipped in the default suite, and A/B timings of the opt-in kernel variants.  Nothing here feeds `value`."""
+    deadline = time.time() + 330.0          # all side checks together: at most ~5.5 minutes
+
+    def sub(cmd, env=None, timeout=240):
+        t0 = time.time()
+        timeout = min(timeout, deadline - t0)
+        if timeout < 20:
+            return -8, "", "skipped: side-check time budget used up", 0.0
+        try:
+            r = subprocess.run(cmd, cwd=ROOT, env={**os.environ, **(env or {})}, capture_output=True, text=True, timeout=timeout)
+            return r.returncode, r.stdout, r.stderr, time.time() - t0
+        except subprocess.TimeoutExpired:
+            return -9, "", "timeout", time.time() - t0
+
+    out = {"note": "untimed side checks run after the measurement in subprocesses; not part of value / e2e"}
+    py = sys.executable
+    rc, so, se, dt = sub([py, "-m", "pytest", "tests/test_gpu_zz_detectors.py", "-q", "-m", "gpu", "-k", "not experimental",
+                          "-p", "no:cacheprovider"], {"QSFT_TEST_UNVALIDATED": "1"})
+    tail = [ln for ln in so.strip().splitlines() if ln.strip()]
+    out["unvalidated_gpu_tests"] = {"rc": rc, "summary": tail[-1] if tail else se[-300:], "seconds": round(dt, 1),
+                                    "failed": [ln for ln in tail if ln.startswith("FAILED")][:20]}
+    rc, so, se, dt = sub([py, "-m", "pytest", "tests/test_gpu_zz_detectors.py", "-q", "-m", "gpu", "-k", "experimental",
+                          "-p", "no:cacheprovider"], {"QSFT_TEST_EXPERIMENTAL": "1"})
+    tail = [ln for ln in so.strip().splitlines() if ln.strip()]
+    out["k4_v2_parity_tests"] = {"rc": rc, "summary": tail[-1] if tail else se[-300:], "seconds": round(dt, 1),
+                                 "failed": [ln for ln in tail if ln.startswith("FAILED")][:20]}
+    for key, env in (("microbench_default", {}), ("microbench_k4_v2", {"QSFT_K4_IMPL": "2"})):
+        only = "k3lag,k4" if not env else "k4"
+        rc, so, se, dt = sub([py, "tools/microbench.py", "--only", only], env, timeout=150)
+        try:
+            out[key] = json.loads(so)
+        except Exception:
+            out[key] = {"rc": rc, "stderr": se[-300:]}
+    return out
 
 
 def run_reference(a):

@@ -21,8 +21,8 @@ QSFT_K4_IMPL=2 timeout 300 python tools/microbench.py > $out/${tag}_microbench_k
 timeout 600 python bench.py > $out/${tag}_bench_N1.json 2> $out/${tag}_bench_N1.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 0 > $out/${tag}_bench_reference.json 2> /dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k3_q4_twopass|k4_classify|k4_apply|k4_reduce' -c 8 \
-    -o $out/${tag}_k3k4 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > /dev/null 2>&1
+    -o $out/${tag}_k3k4 python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras > /dev/null 2>&1
 tail -3 $out/${tag}_pytest.log
 cat $out/${tag}_bench_N1.json | head -c 3000

@@ -11,6 +11,7 @@ sys.path.insert(0, ROOT)
 import qsft_b200  # noqa: E402
 from qsft_b200 import ops, utils  # noqa: E402
 
+ONLY = set(sys.argv[sys.argv.index("--only") + 1].split(",")) if "--only" in sys.argv else {"k1", "k3", "k3lag", "k4"}
 dev = torch.device("cuda", 0)
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -42,25 +43,30 @@ xc = torch.view_as_complex(x.view(P, B, 2))
 ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
 out["k3_gwht 41 x 4^10"] = {"ms": ms, "GBps_algorithmic(16B/elem)": 16 * P * B / ms / 1e6, "frac": 16 * P * B / ms / 1e6 / peak}
 # ticket order of the two-pass kernel: 0 = plain block-by-block order, k = contiguous pass k blocks ahead (default: auto)
-for lag in ("0", "1", "2", "3", "4"):
+for lag in (("0", "1", "2", "3", "4") if "k3lag" in ONLY else ()):
     os.environ["QSFT_K3_LAG"] = lag
     ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
     out[f"k3_gwht 41 x 4^10, QSFT_K3_LAG={lag}"] = {"ms": ms, "frac": 16 * P * B / ms / 1e6 / peak}
-del os.environ["QSFT_K3_LAG"]
-for bb, rows in [(7, 1024), (8, 512), (6, 4096), (12, 4)]:
+os.environ.pop("QSFT_K3_LAG", None)
+for bb, rows in ([(7, 1024), (8, 512), (6, 4096), (12, 4)] if "k3" in ONLY else []):
     y = torch.view_as_complex(torch.randn((rows, q ** bb, 2), device=dev))
     ms = timeit(lambda: ops.gwht_batch_(y, q, bb), flush=flush)
     out[f"k3_gwht {rows} x 4^{bb}"] = {"ms": ms, "GBps": 16 * rows * q ** bb / ms / 1e6, "frac": 16 * rows * q ** bb / ms / 1e6 / peak}
-y = torch.view_as_complex(torch.randn((64, 3 ** 12, 2), device=dev))
-ms = timeit(lambda: ops.gwht_batch_(y, 3, 12), flush=flush)
-out["k3_gwht 64 x 3^12"] = {"ms": ms, "GBps": 16 * 64 * 3 ** 12 / ms / 1e6, "frac": 16 * 64 * 3 ** 12 / ms / 1e6 / peak}
+if "k3" in ONLY:
+    y = torch.view_as_complex(torch.randn((64, 3 ** 12, 2), device=dev))
+    ms = timeit(lambda: ops.gwht_batch_(y, 3, 12), flush=flush)
+    out["k3_gwht 64 x 3^12"] = {"ms": ms, "GBps": 16 * 64 * 3 ** 12 / ms / 1e6, "frac": 16 * 64 * 3 ** 12 / ms / 1e6 / peak}
 
 rng = np.random.default_rng(0)
 M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
-ms = timeit(lambda: ops.query_lattice(M, D, q, device=dev, want_idx=True, want_digits=False), flush=flush)
-out["k1_lattice idx only (16 B/index)"] = {"ms": ms, "GBps": 16 * P * B / ms / 1e6, "frac": 16 * P * B / ms / 1e6 / peak}
-ms = timeit(lambda: ops.query_lattice(M, D, q, device=dev, want_idx=False, want_digits=True), flush=flush)
-out["k1_lattice digits only (64 B/row)"] = {"ms": ms, "GBps": 64 * P * B / ms / 1e6, "frac": 64 * P * B / ms / 1e6 / peak}
+if "k1" in ONLY:
+    ms = timeit(lambda: ops.query_lattice(M, D, q, device=dev, want_idx=True, want_digits=False), flush=flush)
+    out["k1_lattice idx only (16 B/index)"] = {"ms": ms, "GBps": 16 * P * B / ms / 1e6, "frac": 16 * P * B / ms / 1e6 / peak}
+    ms = timeit(lambda: ops.query_lattice(M, D, q, device=dev, want_idx=False, want_digits=True), flush=flush)
+    out["k1_lattice digits only (64 B/row)"] = {"ms": ms, "GBps": 64 * P * B / ms / 1e6, "frac": 64 * P * B / ms / 1e6 / peak}
+if "k4" not in ONLY:
+    print(json.dumps(out, indent=1))
+    sys.exit(0)
 
 # K4: one classification round on config-5 bins (C=3, P=41), ~10 % singletons
 np.random.seed(1)
@@ -83,7 +89,7 @@ def classify_round1():
 
 
 ms = timeit(classify_round1, flush=flush)
-out["k4_classify round 1 (C=3,P=41,B=4^10, 25% occupied)"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
+out[f"k4_classify round 1 (C=3,P=41,B=4^10), QSFT_K4_IMPL={os.environ.get('QSFT_K4_IMPL', '1')}"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
 Uz = torch.zeros_like(U0)
 ms = timeit(lambda: (prob.counters.zero_(), prob.classify(Uz, 0, B, 1)), flush=flush)
 out["k4_classify all-zeroton round"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
