@@ -10,6 +10,9 @@ num_repeat=R (default in DEFAULT_REPEAT), noiseless; one *step* = one full trans
 query lattice (K1) -> synthetic evaluation (K2) -> batched q-ary DFT (K3) -> peeling (K4), exact support recovery
 checked on the last step.  Prints ONE JSON line (see README / DESIGN.md for the keys).
 
+At N = 1 the line also carries "extras": untimed side checks run AFTER the measurement in subprocesses (pending GPU tests,
+A/B timings of opt-in kernel variants); `--no-extras` skips them.
+
 `--impl reference` times the CPU oracle port of the reference NumPy path (oracle/qsft_oracle.py; the reference is
 pure Python and cannot travel to the GPU box) on bounded samples of the same workload and extrapolates.
 """
