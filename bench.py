@@ -417,7 +417,7 @@ def run_extras():
     """Untimed side checks AFTER the measurement, each in its own subprocess (a failure or a crash there cannot touch the
     numbers above): the GPU tests of code that was written after the round's interactive GPU budget was spent and are
     therefore skipped in the default suite, and A/B timings of the opt-in kernel variants.  Nothing here feeds `value`."""
-    deadline = time.time() + 330.0          # all side checks together: at most ~5.5 minutes
+    deadline = time.time() + 420.0          # all side checks together: at most 7 minutes
 
     def sub(cmd, env=None, timeout=240):
         t0 = time.time()
@@ -442,7 +442,9 @@ def run_extras():
     tail = [ln for ln in so.strip().splitlines() if ln.strip()]
     out["k4_v2_parity_tests"] = {"rc": rc, "summary": tail[-1] if tail else se[-300:], "seconds": round(dt, 1),
                                  "failed": [ln for ln in tail if ln.startswith("FAILED")][:20]}
-    for key, env in (("microbench_default", {}), ("microbench_k4_v2", {"QSFT_K4_IMPL": "2"})):
+    for key, env in (("microbench_default", {}), ("microbench_k4_v2", {"QSFT_K4_IMPL": "2"}),
+                     ("microbench_k4_v2_fastdet", {"QSFT_K4_IMPL": "2", "QSFT_K4_FASTDET": "1"}),
+                     ("microbench_k4_fastdet", {"QSFT_K4_FASTDET": "1"})):
         only = "k3lag,k4" if not env else "k4"
         rc, so, se, dt = sub([py, "tools/microbench.py", "--only", only], env, timeout=150)
         try:

@@ -26,6 +26,7 @@ struct PeelDev {
     const int32_t* rs_exp;
     const int32_t* rs_log;
     int rs_order;             // q^s
+    int fastdet;              // opt-in (QSFT_K4_FASTDET=1): q = 2 / 4 symbols by quadrant comparison instead of atan2f
 };
 
 __device__ __forceinline__ int dp4a_u(uint32_t a, uint32_t b, int c) {
@@ -224,16 +225,33 @@ __device__ __forceinline__ int angle_q_dev(float2 v, int q) {
     return (int)(((sector + 1) >> 1) % q);
 }
 
+// Index of the q-th root of unity nearest to the direction of (re, im) for q = 2 / 4 by comparisons (opt-in fast path):
+// the quadrant boundaries are the diagonals (q = 4) / the imaginary axis (q = 2); a value within ~0.03 rad of a boundary
+// (or a vanishing one) returns -1 and takes the exact path, so the decision always equals the exact one.
+__device__ __forceinline__ int quadrant_symbol(int q, float re, float im) {
+    const float ax = fabsf(re), ay = fabsf(im);
+    if (!(ax + ay > 1e-30f)) return -1;
+    if (q == 4) {
+        if (!(fabsf(ax - ay) > 0.03f * (ax + ay))) return -1;
+        return ax > ay ? (re > 0.f ? 0 : 2) : (im > 0.f ? 1 : 3);
+    }
+    if (!(ax > 0.03f * (ax + ay))) return -1;
+    return re > 0.f ? 0 : 1;
+}
+
 __device__ __forceinline__ int detect_symbol(const PeelDev& d, const float2* __restrict__ col, size_t stride, int i) {
     const double qd = (double)d.q;
+    const bool quad = d.fastdet && (d.q == 4 || d.q == 2);
     int symv;
     if (d.channel == 0) {
         const float2 v0 = col[0];
         const float2 v = col[(size_t)i * stride];
         symv = -1;
+        // round(q (angle v - angle v0) / 2 pi) mod q = root nearest to the direction of v conj(v0)
+        if (quad) symv = quadrant_symbol(d.q, fmaf(v.x, v0.x, v.y * v0.y), fmaf(v.y, v0.x, -(v.x * v0.y)));
         // fast path in fp32; anything within 0.01 of a rounding boundary is redone in fp64 so the decision
         // always equals the fp64 one (np.angle / np.round in the reference)
-        if (fabsf(v0.x) + fabsf(v0.y) > 1e-30f && fabsf(v.x) + fabsf(v.y) > 1e-30f) {
+        if (symv < 0 && fabsf(v0.x) + fabsf(v0.y) > 1e-30f && fabsf(v.x) + fabsf(v.y) > 1e-30f) {
             const float u = (float)d.q * (atan2f(v.y, v.x) - atan2f(v0.y, v0.x)) * 0.15915494309189535f;
             const float m = rintf(u);
             if (fabsf(u - m) < 0.49f) {
@@ -260,7 +278,8 @@ __device__ __forceinline__ int detect_symbol(const PeelDev& d, const float2* __r
         // np.mean divides by R > 0: the angle does not depend on it
         symv = -1;
         const float arf = (float)ar, aif = (float)ai;
-        if (fabsf(arf) + fabsf(aif) > 1e-30f) {
+        if (quad) symv = quadrant_symbol(d.q, arf, aif);
+        if (symv < 0 && fabsf(arf) + fabsf(aif) > 1e-30f) {
             float thf = atan2f(aif, arf);
             if (thf < 0.f) thf += 6.283185307179586f;
             const float u = thf * (float)d.q * 0.15915494309189535f;        // in [0, q]
@@ -879,6 +898,8 @@ int make_dev(const qsft_peel_desc* h, PeelDev* d) {
     d->qmagic = (unsigned int)(((1ull << 32) + h->q - 1) / h->q);
     d->MT = h->MT; d->D = h->D; d->rs_exp = h->rs_exp; d->rs_log = h->rs_log;
     d->rs_order = h->source ? (int)ipow64(h->q, h->rs_s) : 0;
+    const char* fd = getenv("QSFT_K4_FASTDET");          // opt-in, unmeasured: see quadrant_symbol
+    d->fastdet = (fd && atoi(fd) != 0) ? 1 : 0;
     return QSFT_OK;
 }
 
@@ -1115,6 +1136,7 @@ extern "C" int qsft_singleton_detect(const float* cols, int64_t N, int q, int n,
     if (channel == 0) QSFT_CHECK_ARG(P == P_src, "identity channel decoding needs num_repeat == 1");
     PeelDev d{};
     d.q = q; d.n = source ? n : P_src - 1; d.P = P; d.P_src = P_src; d.R = P / P_src; d.channel = channel; d.source = source;
+    if (const char* fd = getenv("QSFT_K4_FASTDET")) d.fastdet = atoi(fd) != 0 ? 1 : 0;
     if (source == 1) {
         QSFT_CHECK_ARG(n >= 1 && n <= QSFT_MAX_N, "n=%d out of range", n);
         QSFT_CHECK_ARG(rs_t >= 1 && 2 * rs_t <= RS_MAX_2T && rs_s >= 1 && P_src - 1 == 2 * rs_t * rs_s, "coded source needs P_src = 2ts + 1");

@@ -52,41 +52,47 @@ inline Ctx*& cur() {
     return c;
 }
 
-// Runs kernel body `fn` (a lambda calling the __global__ function with its arguments) over the grid.
+// Runs kernel body `fn` (a lambda calling the __global__ function with its arguments) over the grid: one OS thread per
+// CUDA thread of a block, created once per launch; the threads walk through the blocks together, one block at a time
+// (shared memory is a set of statics), separated by a barrier.
 inline void launch(dim3 grid, dim3 block, const std::function<void()>& fn) {
     const int nthreads = (int)(block.x * block.y * block.z);
     const int nwarps = (nthreads + 31) / 32;
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
-                Block blk;
-                pthread_barrier_init(&blk.bar, nullptr, nthreads);
-                std::vector<Warp> warps(nwarps);
-                for (int w = 0; w < nwarps; ++w) {
-                    const int lanes = (w == nwarps - 1 && nthreads % 32) ? nthreads % 32 : 32;
-                    pthread_barrier_init(&warps[w].bar, nullptr, lanes);
-                }
-                std::vector<std::thread> ths;
-                ths.reserve(nthreads);
-                for (int t = 0; t < nthreads; ++t) {
-                    ths.emplace_back([&, t]() {
-                        Ctx c;
-                        c.tid = make_uint3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+    Block blk;
+    pthread_barrier_init(&blk.bar, nullptr, nthreads);
+    pthread_barrier_t step;
+    pthread_barrier_init(&step, nullptr, nthreads);
+    std::vector<Warp> warps(nwarps);
+    for (int w = 0; w < nwarps; ++w) {
+        const int lanes = (w == nwarps - 1 && nthreads % 32) ? nthreads % 32 : 32;
+        pthread_barrier_init(&warps[w].bar, nullptr, lanes);
+    }
+    std::vector<std::thread> ths;
+    ths.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        ths.emplace_back([&, t]() {
+            Ctx c;
+            c.tid = make_uint3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+            c.bdim = block;
+            c.gdim = grid;
+            c.warp = &warps[t / 32];
+            c.block = &blk;
+            c.lane = t % 32;
+            cur() = &c;
+            for (unsigned bz = 0; bz < grid.z; ++bz)
+                for (unsigned by = 0; by < grid.y; ++by)
+                    for (unsigned bx = 0; bx < grid.x; ++bx) {
                         c.bid = make_uint3(bx, by, bz);
-                        c.bdim = block;
-                        c.gdim = grid;
-                        c.warp = &warps[t / 32];
-                        c.block = &blk;
-                        c.lane = t % 32;
-                        cur() = &c;
                         fn();
-                        cur() = nullptr;
-                    });
-                }
-                for (auto& th : ths) th.join();
-                for (int w = 0; w < nwarps; ++w) pthread_barrier_destroy(&warps[w].bar);
-                pthread_barrier_destroy(&blk.bar);
-            }
+                        pthread_barrier_wait(&step);          // next block only when every thread has left this one
+                    }
+            cur() = nullptr;
+        });
+    }
+    for (auto& th : ths) th.join();
+    for (int w = 0; w < nwarps; ++w) pthread_barrier_destroy(&warps[w].bar);
+    pthread_barrier_destroy(&step);
+    pthread_barrier_destroy(&blk.bar);
 }
 
 template <typename T>

@@ -19,6 +19,8 @@ int fill_dev(PeelDev* d, int q, int n, int b, int C, int P, int P_src, int chann
     d->qmagic = (unsigned int)(((1ull << 32) + q - 1) / q);
     d->MT = MT; d->D = D; d->rs_exp = rs_exp; d->rs_log = rs_log;
     d->rs_order = source ? (int)ipow64(q, rs_s) : 0;
+    const char* fd = getenv("QSFT_K4_FASTDET");
+    d->fastdet = (fd && atoi(fd) != 0) ? 1 : 0;
     return 0;
 }
 
@@ -117,6 +119,8 @@ int emu_detect(const float* cols, long long N, int q, int n, int P, int P_src, i
     memset(&d, 0, sizeof(d));
     d.q = q; d.n = source ? n : P_src - 1; d.P = P; d.P_src = P_src; d.R = P / P_src; d.channel = channel; d.source = source;
     if (source) { d.rs_t = rs_t; d.rs_s = rs_s; d.rs_exp = rs_exp; d.rs_log = rs_log; d.rs_order = (int)ipow64(q, rs_s); }
+    const char* fd = getenv("QSFT_K4_FASTDET");
+    d.fastdet = (fd && atoi(fd) != 0) ? 1 : 0;
     const int wpb = K4_THREADS / 32;
     emu::launch(dim3((unsigned)((N + wpb - 1) / wpb)), dim3(K4_THREADS),
                 [&]() { k4_detect_kernel(d, reinterpret_cast<const float2*>(cols), N, k_out, ld_out); });

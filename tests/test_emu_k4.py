@@ -184,3 +184,38 @@ def test_emulated_detect_coded(emu):
     out = np.full((len(cols), 16), 99, dtype=np.int8)
     assert emu.emu_detect(_p(cols), len(cols), q, n, p1 * R, p1, 1, 1, t, rs.s, _p(e), _p(l), _p(out), 16) == 0
     assert np.array_equal(out[:, :n], np.array(want)) and not out[:, n:].any()
+
+
+def test_emulated_quadrant_detection_equals_exact(emu, monkeypatch):
+    """Opt-in QSFT_K4_FASTDET=1 (q = 2 / 4 symbols by quadrant comparison) decides exactly like the default path, also on
+    columns placed on and next to the decision boundaries."""
+    rng = np.random.default_rng(17)
+    for q, channel, p1, R in [(4, 0, 9, 1), (4, 1, 9, 1), (4, 1, 7, 3), (2, 0, 11, 1), (2, 1, 11, 2), (4, 2, 9, 2)]:
+        P, N = p1 * R, 4000
+        ph = rng.integers(0, q, (N, P)) + rng.choice([0.0, 0.0, 0.5, 0.49, 0.51, 0.499999, 0.25], (N, P)) \
+            + rng.normal(0, 0.02, (N, P)) * rng.integers(0, 2, (N, 1))
+        amp = rng.uniform(0.2, 3, (N, 1)) * np.exp(1j * rng.uniform(0, 2 * np.pi, (N, 1)))
+        cols = amp * np.exp(2j * np.pi * ph / q)
+        cols[::97] = 0                                       # vanishing columns
+        cols[5::131, 0] = 0                                  # vanishing reference delay
+        cols = np.ascontiguousarray(cols.astype(np.complex64))
+        outs = []
+        for fast in ("0", "1"):
+            monkeypatch.setenv("QSFT_K4_FASTDET", fast)
+            out = np.full((N, 16), 99, dtype=np.int8)
+            assert emu.emu_detect(_p(cols), N, q, 0, P, p1, channel, 0, 0, 0, None, None, _p(out), 16) == 0
+            outs.append(out)
+        assert np.array_equal(outs[0], outs[1]), (q, channel)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("name", ["cfg1_q4_n10_b4_identity", "cfg2r_q4_n14_b5_nso_noisy", "q2_n12_b4_simple",
+                                  "q4_n10_allbs_subselect"])
+def test_emulated_peel_with_quadrant_detection(emu, name, impl, monkeypatch):
+    monkeypatch.setenv("QSFT_K4_FASTDET", "1")
+    g = load_golden(name)
+    p = case_params(g)
+    prob, U = _problem_from_golden(g, p)
+    keys, vals, _, _ = prob.peel(emu, U, impl)
+    assert keys == [tuple(int(v) for v in k) for k in g["res_keys"]]
+    assert np.max(np.abs(vals - g["res_vals"])) <= 1e-5 * np.max(np.abs(g["res_vals"]))

@@ -89,7 +89,7 @@ def classify_round1():
 
 
 ms = timeit(classify_round1, flush=flush)
-out[f"k4_classify round 1 (C=3,P=41,B=4^10), QSFT_K4_IMPL={os.environ.get('QSFT_K4_IMPL', '1')}"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
+out[f"k4_classify round 1 (C=3,P=41,B=4^10), QSFT_K4_IMPL={os.environ.get('QSFT_K4_IMPL', '1')} FASTDET={os.environ.get('QSFT_K4_FASTDET', '0')}"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
 Uz = torch.zeros_like(U0)
 ms = timeit(lambda: (prob.counters.zero_(), prob.classify(Uz, 0, B, 1)), flush=flush)
 out["k4_classify all-zeroton round"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
