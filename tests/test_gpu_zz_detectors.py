@@ -295,6 +295,13 @@ def test_experimental_k4_classify_v2_equals_v1(q, n, b, S, R, chan, noise, monke
     prob.alloc(4 * C * q ** b)
     v1 = _classify_once(prob, U, 1, monkeypatch)
     v2 = _classify_once(prob, U, 2, monkeypatch)
+    monkeypatch.setenv("QSFT_K4_FASTDET", "1")               # quadrant detection (q = 2 / 4), both kernels
+    f1 = _classify_once(prob, U, 1, monkeypatch)
+    f2 = _classify_once(prob, U, 2, monkeypatch)
+    monkeypatch.delenv("QSFT_K4_FASTDET")
+    for alt in (f1, f2):
+        assert alt["nf"] == v1["nf"] and alt["nm"] == v1["nm"]
+        assert np.array_equal(alt["cj"], v1["cj"]) and np.array_equal(alt["k"], v1["k"])
     assert v1["nf"] == v2["nf"] and v1["nm"] == v2["nm"] and v1["nf"] > 0
     assert np.array_equal(v1["cj"], v2["cj"]) and np.array_equal(v1["k"], v2["k"]) and np.array_equal(v1["round"], v2["round"])
     assert np.max(np.abs(v1["rho"] - v2["rho"])) <= 2e-6 * max(1.0, np.max(np.abs(v1["rho"])))
