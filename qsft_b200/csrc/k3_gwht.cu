@@ -355,8 +355,10 @@ __host__ __device__ inline K3Ticket k3_ticket_decode(unsigned int ticket, long l
     return o;
 }
 
-// 64 registers (one 8-byte spill) -> 4 CTAs per SM instead of 3 at the 80 registers ptxas takes unconstrained
-__global__ void __launch_bounds__(256, 4)
+// MINB = 4: 64 registers (one 8-byte spill) -> 4 CTAs per SM (default); MINB = 3: the 80 registers ptxas takes
+// unconstrained -> 3 CTAs per SM (QSFT_K3_CTAS=3, kept for the A/B measurement)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k3_q4_twopass_kernel(float2* __restrict__ x, long long B, int r1, int r2, long long qa2, int lgW2, int tiles1, int tiles2,
                      unsigned int* __restrict__ done /* [nblocks] counters + [1] ticket */, long long nblocks, int lag,
                      float scale, K3Peers peers) {
@@ -491,17 +493,27 @@ __global__ void k3_bcast_copy_kernel(const float2* __restrict__ x, long long n, 
 // How many blocks the contiguous pass runs ahead of the strided pass (see k3_q4_twopass_kernel): enough tickets between
 // a block's two passes to cover every co-resident CTA, but no more intermediate data than stays comfortably in L2.
 // QSFT_K3_LAG overrides (0 = the plain block-by-block order).
+static int k3_twopass_ctas() {                                // CTAs per SM the two-pass kernel is compiled for
+    const char* e = getenv("QSFT_K3_CTAS");
+    return (e && atoi(e) == 3) ? 3 : 4;
+}
+
 static int k3_twopass_lag(long long B, int tiles1, int tiles2) {
     if (const char* e = getenv("QSFT_K3_LAG")) {
         const int v = atoi(e);
         if (v >= 0 && v <= 4096) return v;
     }
-    static int resident = 0;                                  // co-resident CTAs of the kernel on this device
+    const int minb = k3_twopass_ctas();
+    static int resident_by_minb[5] = {0, 0, 0, 0, 0};         // co-resident CTAs of the kernel on this device
+    int& resident = resident_by_minb[minb];
     if (resident == 0) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_twopass_kernel, 256, 0) != cudaSuccess || per_sm < 1) {
+        const cudaError_t e = (minb == 3)
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_twopass_kernel<3>, 256, 0)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_twopass_kernel<4>, 256, 0);
+        if (e != cudaSuccess || per_sm < 1) {
             (void)cudaGetLastError();
-            per_sm = 4;
+            per_sm = minb;
         }
         resident = per_sm * qsft_num_sms();
     }
@@ -554,8 +566,12 @@ static int gwht_impl(float* x, int64_t batch, int q, int b, const K3Peers& peers
         QSFT_CUDA(cudaMemsetAsync(done, 0, (size_t)(batch + 1) * sizeof(unsigned int), st));
         const int t1 = (int)plans[0].tiles_per_block, t2 = (int)plans[1].tiles_per_block;
         const int lag = k3_twopass_lag(B, t1, t2);
-        k3_q4_twopass_kernel<<<(unsigned)(batch * (t1 + t2)), 256, 0, st>>>(xx, B, plans[0].r, plans[1].r, plans[1].qa,
-                                                                          plans[1].lgW, t1, t2, done, (long long)batch, lag, inv, peers);
+        if (k3_twopass_ctas() == 3)
+            k3_q4_twopass_kernel<3><<<(unsigned)(batch * (t1 + t2)), 256, 0, st>>>(xx, B, plans[0].r, plans[1].r, plans[1].qa,
+                                                                                 plans[1].lgW, t1, t2, done, (long long)batch, lag, inv, peers);
+        else
+            k3_q4_twopass_kernel<4><<<(unsigned)(batch * (t1 + t2)), 256, 0, st>>>(xx, B, plans[0].r, plans[1].r, plans[1].qa,
+                                                                                 plans[1].lgW, t1, t2, done, (long long)batch, lag, inv, peers);
         QSFT_LAUNCHED();
         QSFT_CUDA(cudaFreeAsync(done, st));
         return QSFT_OK;

@@ -83,7 +83,7 @@ extern "C" int emu_gwht(float* xf, long long batch, int q, int b, int lag, float
         const int t1 = (int)plans[0].tiles_per_block, t2 = (int)plans[1].tiles_per_block;
         *used_twopass = 1;
         emu::launch(dim3((unsigned)(batch * (t1 + t2))), dim3(256), [&]() {
-            k3_q4_twopass_kernel(x, B, plans[0].r, plans[1].r, plans[1].qa, plans[1].lgW, t1, t2, done.data(), batch, lag, inv, peers);
+            k3_q4_twopass_kernel<4>(x, B, plans[0].r, plans[1].r, plans[1].qa, plans[1].lgW, t1, t2, done.data(), batch, lag, inv, peers);
         });
         return emu_failure() ? 1 : 0;
     }

@@ -48,6 +48,14 @@ for lag in (("0", "1", "2", "3", "4") if "k3lag" in ONLY else ()):
     ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
     out[f"k3_gwht 41 x 4^10, QSFT_K3_LAG={lag}"] = {"ms": ms, "frac": 16 * P * B / ms / 1e6 / peak}
 os.environ.pop("QSFT_K3_LAG", None)
+if "k3lag" in ONLY:                                          # 3 CTAs per SM (80 registers) instead of 4 (64 registers)
+    os.environ["QSFT_K3_CTAS"] = "3"
+    for lag in ("0", "2", "3"):
+        os.environ["QSFT_K3_LAG"] = lag
+        ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
+        out[f"k3_gwht 41 x 4^10, QSFT_K3_CTAS=3 QSFT_K3_LAG={lag}"] = {"ms": ms, "frac": 16 * P * B / ms / 1e6 / peak}
+    os.environ.pop("QSFT_K3_LAG", None)
+    os.environ.pop("QSFT_K3_CTAS", None)
 for bb, rows in ([(7, 1024), (8, 512), (6, 4096), (12, 4)] if "k3" in ONLY else []):
     y = torch.view_as_complex(torch.randn((rows, q ** bb, 2), device=dev))
     ms = timeit(lambda: ops.gwht_batch_(y, q, bb), flush=flush)
