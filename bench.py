@@ -417,9 +417,9 @@ def run_extras():
     """Untimed side checks AFTER the measurement, each in its own subprocess (a failure or a crash there cannot touch the
     numbers above): the GPU tests of code that was written after the round's interactive GPU budget was spent and are
     therefore skipped in the default suite, and A/B timings of the opt-in kernel variants.  Nothing here feeds `value`."""
-    deadline = time.time() + 420.0          # all side checks together: at most 7 minutes
+    deadline = time.time() + 180.0          # all side checks together: at most 3 minutes
 
-    def sub(cmd, env=None, timeout=240):
+    def sub(cmd, env=None, timeout=120):
         t0 = time.time()
         timeout = min(timeout, deadline - t0)
         if timeout < 20:
@@ -430,27 +430,27 @@ def run_extras():
         except subprocess.TimeoutExpired:
             return -9, "", "timeout", time.time() - t0
 
+    def pytest_summary(rc, so, se, dt):
+        tail = [ln for ln in so.strip().splitlines() if ln.strip()]
+        return {"rc": rc, "summary": tail[-1] if tail else se[-300:], "seconds": round(dt, 1),
+                "failed": [ln for ln in tail if ln.startswith("FAILED")][:20]}
+
     out = {"note": "untimed side checks run after the measurement in subprocesses; not part of value / e2e"}
     py = sys.executable
-    rc, so, se, dt = sub([py, "-m", "pytest", "tests/test_gpu_zz_detectors.py", "-q", "-m", "gpu", "-k", "not experimental",
-                          "-p", "no:cacheprovider"], {"QSFT_TEST_UNVALIDATED": "1"})
-    tail = [ln for ln in so.strip().splitlines() if ln.strip()]
-    out["unvalidated_gpu_tests"] = {"rc": rc, "summary": tail[-1] if tail else se[-300:], "seconds": round(dt, 1),
-                                    "failed": [ln for ln in tail if ln.startswith("FAILED")][:20]}
-    rc, so, se, dt = sub([py, "-m", "pytest", "tests/test_gpu_zz_detectors.py", "-q", "-m", "gpu", "-k", "experimental",
-                          "-p", "no:cacheprovider"], {"QSFT_TEST_EXPERIMENTAL": "1"})
-    tail = [ln for ln in so.strip().splitlines() if ln.strip()]
-    out["k4_v2_parity_tests"] = {"rc": rc, "summary": tail[-1] if tail else se[-300:], "seconds": round(dt, 1),
-                                 "failed": [ln for ln in tail if ln.startswith("FAILED")][:20]}
-    for key, env in (("microbench_default", {}), ("microbench_k4_v2", {"QSFT_K4_IMPL": "2"}),
-                     ("microbench_k4_v2_fastdet", {"QSFT_K4_IMPL": "2", "QSFT_K4_FASTDET": "1"}),
-                     ("microbench_k4_fastdet", {"QSFT_K4_FASTDET": "1"})):
-        only = "k3lag,k4" if not env else "k4"
-        rc, so, se, dt = sub([py, "tools/microbench.py", "--only", only], env, timeout=150)
-        try:
-            out[key] = json.loads(so)
-        except Exception:
-            out[key] = {"rc": rc, "stderr": se[-300:]}
+    # 1. stand-alone timings: K3 ticket-lag / CTAs-per-SM sweep, K4 classification variants (with a parity checksum)
+    rc, so, se, dt = sub([py, "tools/microbench.py", "--only", "k3lag,k4", "--k4-variants"], timeout=90)
+    try:
+        out["microbench"] = json.loads(so)
+    except Exception:
+        out["microbench"] = {"rc": rc, "stderr": se[-300:]}
+    # 2. the GPU tests that are skipped by default until their first GPU run
+    out["unvalidated_gpu_tests"] = pytest_summary(*sub(
+        [py, "-m", "pytest", "tests/test_gpu_zz_detectors.py", "-q", "-m", "gpu", "-k", "not experimental", "-p", "no:cacheprovider"],
+        {"QSFT_TEST_UNVALIDATED": "1"}))
+    # 3. parity of the opt-in K4 variants against the default kernel (if time is left)
+    out["k4_variant_parity_tests"] = pytest_summary(*sub(
+        [py, "-m", "pytest", "tests/test_gpu_zz_detectors.py", "-q", "-m", "gpu", "-k", "experimental", "-p", "no:cacheprovider"],
+        {"QSFT_TEST_EXPERIMENTAL": "1"}))
     return out
 
 

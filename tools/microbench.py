@@ -98,6 +98,31 @@ def classify_round1():
 
 ms = timeit(classify_round1, flush=flush)
 out[f"k4_classify round 1 (C=3,P=41,B=4^10), QSFT_K4_IMPL={os.environ.get('QSFT_K4_IMPL', '1')} FASTDET={os.environ.get('QSFT_K4_FASTDET', '0')}"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
+if "--k4-variants" in sys.argv:
+    # the opt-in classification variants in the same process (the knobs are read on every call): time of round 1 and a
+    # cheap parity signal -- number of singletons / multitons and an order-independent checksum of the finds
+    def signature():
+        classify_round1()
+        torch.cuda.synchronize()
+        nf, nm = int(prob.counters[0]), int(prob.counters[1])
+        cj = prob.find_cj[:nf]
+        k = prob.find_k[:nf].to(torch.int64)
+        w = torch.arange(1, k.shape[1] + 1, device=dev, dtype=torch.int64)
+        return nf, nm, int(cj.sum()), int(((k * w).sum(dim=1) * (cj % 1000003 + 1)).sum())
+
+    base_sig = signature()
+    for impl, fast in (("1", "1"), ("2", "0"), ("2", "1")):
+        os.environ["QSFT_K4_IMPL"], os.environ["QSFT_K4_FASTDET"] = impl, fast
+        try:
+            sig = signature()
+            ms = timeit(classify_round1, flush=flush)
+            out[f"k4_classify round 1, QSFT_K4_IMPL={impl} FASTDET={fast}"] = {
+                "ms": ms, "frac": 8 * C * P * B / ms / 1e6 / peak, "same_finds_as_default": sig == base_sig,
+                "finds": sig[0], "multitons": sig[1]}
+        except Exception as exc:
+            out[f"k4_classify round 1, QSFT_K4_IMPL={impl} FASTDET={fast}"] = {"error": repr(exc)}
+    os.environ.pop("QSFT_K4_IMPL", None)
+    os.environ.pop("QSFT_K4_FASTDET", None)
 Uz = torch.zeros_like(U0)
 ms = timeit(lambda: (prob.counters.zero_(), prob.classify(Uz, 0, B, 1)), flush=flush)
 out["k4_classify all-zeroton round"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
