@@ -40,8 +40,12 @@ def padded_ld(n):
 class Problem:
     """Host mirror of ops.PeelProblem for the emulated kernels."""
 
-    def __init__(self, q, n, b, Ms, Ds, P_src, channel, cutoff):
+    def __init__(self, q, n, b, Ms, Ds, P_src, channel, cutoff, rs=None):
         self.q, self.n, self.b, self.C = q, n, b, len(Ms)
+        self.rs = rs
+        if rs is not None:
+            e, l = rs.device_tables()
+            self.rs_exp, self.rs_log = np.ascontiguousarray(e, dtype=np.int32), np.ascontiguousarray(l, dtype=np.int32)
         Ds = np.asarray(Ds)
         self.P, self.P_src, self.B, self.ld = Ds.shape[1], P_src, q ** b, padded_ld(n)
         self.MT = np.zeros((self.C, b, self.ld), dtype=np.int8)
@@ -66,6 +70,9 @@ class Problem:
         self.unext = np.zeros(mf, dtype=np.int32)
 
     def desc(self):
+        if self.rs is not None:
+            return [self.q, self.n, self.b, self.C, self.P, self.P_src, self.channel, 1, self.rs.t, self.rs.s, self.ld,
+                    C.c_float(self.cutoff), _p(self.MT), _p(self.D), _p(self.rs_exp), _p(self.rs_log)]
         return [self.q, self.n, self.b, self.C, self.P, self.P_src, self.channel, 0, 0, 0, self.ld, C.c_float(self.cutoff),
                 _p(self.MT), _p(self.D), None, None]
 
@@ -219,3 +226,34 @@ def test_emulated_peel_with_quadrant_detection(emu, name, impl, monkeypatch):
     keys, vals, _, _ = prob.peel(emu, U, impl)
     assert keys == [tuple(int(v) for v in k) for k in g["res_keys"]]
     assert np.max(np.abs(vals - g["res_vals"])) <= 1e-5 * np.max(np.abs(g["res_vals"]))
+
+
+def test_emulated_peel_coded_source_vs_oracle(emu):
+    """Reed-Solomon source decoding inside the classification kernel (config-3 shape, reduced): the emulated peel loop
+    on the oracle's bins == the oracle's transform with its own decoder, same order."""
+    import qsft_oracle as orc
+    from qsft_b200.reed_solomon import ReedSolomon
+    np.random.seed(4)
+    n, q, S, b, Cn, t, R = 14, 3, 30, 3, 3, 3, 2
+    qa = {"query_method": "complex", "num_subsample": Cn, "delays_method_source": "coded", "subsampling_method": "qsft",
+          "delays_method_channel": "nso", "num_repeat": R, "b": b, "t": t}
+    signal_w, locq, strengths = orc.generate_signal_w(n, q, S, 1, 1, max_weight=t)
+    sig = orc.OracleSignal(n, q, qa, locq, strengths, noise_sd=0.0, signal_w=signal_w)
+    Ms, Ds, Us = sig.get_MDU(Cn, R, b)
+
+    class Fixed:
+        q, n, noise_sd = sig.q, sig.n, 0.0
+
+        def get_source_parity(self):
+            return sig.get_source_parity()
+
+        def get_MDU(self, *a, **k):
+            return Ms, Ds, [[np.array(u) for u in us] for us in Us], None
+
+    want = orc.transform(Fixed(), Cn, R, b, "coded", "nso", source_decoder=orc.get_reed_solomon_dec(n, t, q))
+    U = np.ascontiguousarray(np.array([np.vstack(us) for us in Us]).astype(np.complex64))
+    D = np.array([np.vstack(d) for d in Ds])
+    prob = Problem(q, n, b, Ms, D, sig.get_source_parity(), 1, 1e-9, rs=ReedSolomon(n, t, q))
+    keys, vals, _, _ = prob.peel(emu, U, 1)
+    assert keys == list(want.keys()) and len(keys) >= 0.8 * len(signal_w)
+    assert np.max(np.abs(vals - np.array(list(want.values())))) <= 1e-5
