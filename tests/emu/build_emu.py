@@ -28,6 +28,13 @@ def device_part(which="k4"):
         start = src.index('#include "common.cuh"') + len('#include "common.cuh"')
         end = src.index('extern "C" int qsft_query_lattice(')   # the anonymous namespace is already closed here
         return _rewrite(src[start:end])
+    if which == "k2l":
+        # operand generation of the lattice-factorised evaluation (pure integer SIMT code); the GEMM kernels are tcgen05 / TMA
+        src = open(os.path.join(ROOT, "qsft_b200", "csrc", "k2_eval_lattice.cu")).read()
+        start = src.index("// sum_i digit_i(a) * digit_i(b) mod 4")
+        end = src.index("// ---- the GEMM ----")
+        head = "namespace {\nconstexpr int LT_SCALE_BITS = %s;\n" % re.search(r"constexpr int LT_SCALE_BITS = (\d+);", src).group(1)
+        return head + _rewrite(src[start:end]) + "\n}  // namespace (closed by build_emu.py)\n"
     if which == "k2":
         src = open(os.path.join(ROOT, "qsft_b200", "csrc", "k2_eval_simt.cu")).read()
         start = src.index('#include "common.cuh"') + len('#include "common.cuh"')
@@ -43,7 +50,7 @@ def build(force=False, which="k4"):
     os.makedirs(GEN, exist_ok=True)
     lib = os.path.join(GEN, f"lib{which}emu.so")
     inc = os.path.join(GEN, f"{which}_device.inc")
-    cu = {"k4": "k4_peel.cu", "k3": "k3_gwht.cu", "k1": "k1_lattice.cu", "k2": "k2_eval_simt.cu"}[which]
+    cu = {"k4": "k4_peel.cu", "k3": "k3_gwht.cu", "k1": "k1_lattice.cu", "k2": "k2_eval_simt.cu", "k2l": "k2_eval_lattice.cu"}[which]
     text = device_part(which)
     srcs = [os.path.join(HERE, f"{which}_emu.cpp"), os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "qsft_b200", "csrc", cu)]
     fresh = os.path.exists(lib) and os.path.exists(inc) and open(inc).read() == text and \
@@ -64,3 +71,4 @@ if __name__ == "__main__":
     print(build(force=True, which="k3"))
     print(build(force=True, which="k1"))
     print(build(force=True, which="k2"))
+    print(build(force=True, which="k2l"))

@@ -199,3 +199,29 @@ inline void emu_fail(const char* msg) { emu_failure() = msg; }
 inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
     return (unsigned long long)(((unsigned __int128)a * b) >> 64);
 }
+
+// integer / conversion intrinsics used by the operand-generation kernels
+inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
+    const unsigned long long pool = ((unsigned long long)b << 32) | a;
+    unsigned out = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned n = (sel >> (4 * i)) & 0xfu;
+        unsigned byte = (unsigned)(pool >> (8 * (n & 7u))) & 0xffu;
+        if (n & 8u) byte = (byte & 0x80u) ? 0xffu : 0x00u;          // sign replication mode
+        out |= byte << (8 * i);
+    }
+    return out;
+}
+inline unsigned __vsub4(unsigned a, unsigned b) {
+    unsigned out = 0;
+    for (int i = 0; i < 4; ++i) out |= (((a >> (8 * i)) - (b >> (8 * i))) & 0xffu) << (8 * i);
+    return out;
+}
+inline unsigned atomicMax(unsigned* p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline int __float2int_rn(float x) { return (int)nearbyintf(x); }

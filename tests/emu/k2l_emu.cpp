@@ -1,0 +1,55 @@
+// Host driver of the operand-generation kernels of the lattice-factorised evaluation (lt_prep / lt_amax / lt_quant /
+// lt_bgen / lt_ttab / lt_etab in qsft_b200/csrc/k2_eval_lattice.cu) under the CPU execution shim -- TEST INFRASTRUCTURE
+// ONLY.  The GEMM kernels themselves (tcgen05 / TMA) cannot be emulated; these kernels produce everything they consume.
+#include "cuda_emu.h"
+#define QSFT_EMU 1
+#include "../../qsft_b200/csrc/common.cuh"
+#include "_gen/k2l_device.inc"
+
+extern "C" {
+
+int emu_lt_prep(const int8_t* M, const int8_t* D, const int8_t* loc, long long S, long long Se, int n, int b, int b1, int P,
+                int ld, uint32_t* hhi, uint32_t* hlo, uint8_t* e) {
+    const int T = 256;
+    emu::launch(dim3((unsigned)((S + T - 1) / T)), dim3(T), [&]() { lt_prep_kernel(M, D, loc, S, Se, n, b, b1, P, ld, hhi, hlo, e); });
+    return 0;
+}
+
+int emu_lt_quant(const float* a, long long S, float* inv_scale, int32_t* alimb /* (S, 2) */) {
+    const int T = 256;
+    unsigned int amax = 0;
+    const unsigned sb = (unsigned)((S + T - 1) / T);
+    emu::launch(dim3(sb), dim3(T), [&]() { lt_amax_kernel(reinterpret_cast<const float2*>(a), S, &amax); });
+    emu::launch(dim3(sb), dim3(T), [&]() {
+        lt_quant_kernel(reinterpret_cast<const float2*>(a), S, &amax, inv_scale, reinterpret_cast<int2*>(alimb));
+    });
+    return 0;
+}
+
+int emu_lt_bgen(const uint32_t* hlo, const int32_t* alimb, long long S, int b2, long long Nlo, long long Kp, uint32_t* Bq) {
+    const int T = 256;
+    emu::launch(dim3((unsigned)((Kp / 4 + T - 1) / T), (unsigned)Nlo), dim3(T),
+                [&]() { lt_bgen_kernel(hlo, reinterpret_cast<const int2*>(alimb), S, b2, Nlo, Kp, Bq); });
+    return 0;
+}
+
+int emu_lt_ttab(const uint32_t* hhi, long long S, int b1, long long Tw, long long Mhi, uint32_t* T_) {
+    const int T = 256;
+    emu::launch(dim3((unsigned)((Tw + T - 1) / T), (unsigned)Mhi), dim3(T), [&]() { lt_ttab_kernel(hhi, S, b1, Tw, T_); });
+    return 0;
+}
+
+int emu_lt_etab(const uint8_t* e, long long S, long long Se, int P, long long Tw, uint32_t* E2) {
+    const int T = 256;
+    emu::launch(dim3((unsigned)((Tw + T - 1) / T), (unsigned)P), dim3(T), [&]() { lt_etab_kernel(e, S, Se, P, Tw, E2); });
+    return 0;
+}
+
+int emu_lt_agen(const uint32_t* hhi, const uint8_t* e, long long S, long long Se, int b1, int P, long long Mhi, long long Kp,
+                uint32_t* A) {
+    const int T = 256;
+    emu::launch(dim3((unsigned)((Kp / 4 + T - 1) / T), (unsigned)Mhi), dim3(T),
+                [&]() { lt_agen_kernel(hhi, e, S, Se, b1, P, Mhi, Kp, A); });
+    return 0;
+}
+}

@@ -1,0 +1,102 @@
+"""CPU: the operand-generation kernels of the lattice-factorised evaluation (lt_prep / lt_amax / lt_quant / lt_agen /
+lt_bgen / lt_ttab / lt_etab in k2_eval_lattice.cu) executed by the SIMT emulation (tests/emu).  With the tensor-core GEMM
+replaced by an exact integer matrix product in NumPy, the operands they produce must reproduce the samples of the lattice
+{M l + d_p}: the whole factorisation  x_p[l_hi, l_lo] = sum_s i^(<h_hi, l_hi> + e_ps) * (a_s i^<h_lo, l_lo>)  is checked
+against the oracle's direct evaluation, and the packed phase tables against the materialised operand."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import qsft_oracle as orc
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import build_emu  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu():
+    L = C.CDLL(build_emu.build(which="k2l"))
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_longlong
+    L.emu_lt_prep.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.emu_lt_quant.argtypes = [vp, i64, vp, vp]
+    L.emu_lt_bgen.argtypes = [vp, vp, i64, i32, i64, i64, vp]
+    L.emu_lt_ttab.argtypes = [vp, i64, i32, i64, i64, vp]
+    L.emu_lt_etab.argtypes = [vp, i64, i64, i32, i64, vp]
+    L.emu_lt_agen.argtypes = [vp, vp, i64, i64, i32, i32, i64, i64, vp]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("n,b,S,P,seed", [(12, 7, 37, 5, 0), (40, 8, 90, 3, 1), (9, 7, 64, 2, 2)])
+def test_emulated_lattice_operands_reproduce_the_samples(emu, n, b, S, P, seed):
+    q = 4
+    rng = np.random.default_rng(seed)
+    M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
+    locq = rng.integers(0, q, (n, S))
+    a = rng.uniform(0.3, 2, S) * np.exp(1j * rng.uniform(0, 2 * np.pi, S))
+    b1, b2 = b // 2, b - b // 2
+    Mhi, Nlo = q ** b1, q ** b2
+    ld = max(32, (n + 31) // 32 * 32)
+    Kp = (2 * S + 127) // 128 * 128
+    Tw = Kp // 32
+    Se = (S + 3) & ~3
+    M8, D8 = np.ascontiguousarray(M, dtype=np.int8), np.ascontiguousarray(D, dtype=np.int8)
+    loc = np.zeros((S, ld), dtype=np.int8)
+    loc[:, :n] = locq.T
+    hhi, hlo = np.zeros(S, dtype=np.uint32), np.zeros(S, dtype=np.uint32)
+    e = np.zeros((P, Se), dtype=np.uint8)
+    assert emu.emu_lt_prep(_p(M8), _p(D8), _p(loc), S, Se, n, b, b1, P, ld, _p(hhi), _p(hlo), _p(e)) == 0
+    # bin-hash halves and delay phases against their definitions
+    H = (M.T @ locq) % q                                                   # (b, S) digits of M^T k, MSB first
+    want_hi = sum(H[i].astype(np.int64) << (2 * (b1 - 1 - i)) for i in range(b1))
+    want_lo = sum(H[b1 + i].astype(np.int64) << (2 * (b2 - 1 - i)) for i in range(b2))
+    assert np.array_equal(hhi, want_hi) and np.array_equal(hlo, want_lo)
+    assert np.array_equal(e[:, :S], (D @ locq) % q)
+    # quantisation: three balanced base-128 limbs
+    a32 = np.ascontiguousarray(a.astype(np.complex64))
+    inv_scale = np.zeros(1, dtype=np.float32)
+    alimb = np.zeros((S, 2), dtype=np.int32)
+    assert emu.emu_lt_quant(_p(a32), S, _p(inv_scale), _p(alimb)) == 0
+    limbs = alimb.view(np.int8).reshape(S, 2, 4)[:, :, :3].astype(np.int64)     # (S, re/im, limb)
+    assert np.abs(limbs[:, :, 1:]).max() <= 64
+    vq = (limbs[:, :, 0] * 128 + limbs[:, :, 1]) * 128 + limbs[:, :, 2]
+    aq = (vq[:, 0] + 1j * vq[:, 1]) * float(inv_scale[0])
+    assert np.max(np.abs(aq - a32)) <= 0.75 * float(inv_scale[0]) * np.sqrt(2)
+    # materialised operands
+    A = np.zeros((P, Mhi, 2, Kp), dtype=np.int8)
+    assert emu.emu_lt_agen(_p(hhi), _p(e), S, Se, b1, P, Mhi, Kp, _p(A)) == 0
+    Bq = np.zeros((3, Nlo, Kp), dtype=np.int8)
+    assert emu.emu_lt_bgen(_p(hlo), _p(alimb), S, b2, Nlo, Kp, _p(Bq)) == 0
+    assert not A[..., 2 * S:].any() and not Bq[..., 2 * S:].any()          # K padding is zero
+    assert set(np.unique(A)) <= {-1, 0, 1}
+    pairs = A[..., :2 * S].reshape(P, Mhi, 2, S, 2)
+    assert (np.count_nonzero(pairs, axis=-1) == 1).all()                   # exactly one zero per (Re, Im) byte pair: 2:4 sparse
+    # exact integer GEMM + limb recombination == the samples of the lattice, straight from the definition
+    acc = np.einsum("pmrk,lnk->lpmrn", A.astype(np.int64), Bq.astype(np.int64))
+    val = ((acc[0] * 128 + acc[1]) * 128 + acc[2]) * float(inv_scale[0])   # (P, Mhi, 2, Nlo)
+    got = (val[:, :, 0, :] + 1j * val[:, :, 1, :]).reshape(P, Mhi * Nlo)
+    dig = orc.query_digits(M, D, q)                                        # (P, n, B)
+    want = np.stack([orc.synth_eval_digits(dig[p].T, locq, aq, q) for p in range(P)])
+    assert np.max(np.abs(got - want)) <= 1e-9 * S
+    exact = np.stack([orc.synth_eval_digits(dig[p].T, locq, a, q) for p in range(P)])
+    assert np.max(np.abs(got - exact)) <= 2 * S * float(inv_scale[0])     # quantisation of the strengths only
+    # packed phase tables == the rotations the materialised operand was built from
+    Ttab = np.zeros((Mhi, Tw), dtype=np.uint32)
+    Etab = np.zeros((P, Tw), dtype=np.uint32)
+    assert emu.emu_lt_ttab(_p(hhi), S, b1, Tw, Mhi, _p(Ttab)) == 0
+    assert emu.emu_lt_etab(_p(e), S, Se, P, Tw, _p(Etab)) == 0
+    f = np.arange(16)
+    Tf = ((Ttab[:, :, None] >> (2 * f)) & 3).reshape(Mhi, -1)[:, :S]       # (Mhi, S)
+    Ef = ((Etab[:, :, None] >> (2 * f)) & 3).reshape(P, -1)[:, :S]
+    rot = (Tf[None, :, :] + Ef[:, None, :]) % 4                            # (P, Mhi, S)
+    er, ei = np.array([1, 0, -1, 0])[rot], np.array([0, 1, 0, -1])[rot]
+    assert np.array_equal(pairs[:, :, 0, :, 0], er) and np.array_equal(pairs[:, :, 0, :, 1], -ei)
+    assert np.array_equal(pairs[:, :, 1, :, 0], ei) and np.array_equal(pairs[:, :, 1, :, 1], er)
+    lhi_d = np.stack([(np.arange(Mhi) >> (2 * (b1 - 1 - i))) & 3 for i in range(b1)])     # (b1, Mhi) MSB first
+    assert np.array_equal(Tf, (lhi_d.T @ H[:b1]) % 4)
