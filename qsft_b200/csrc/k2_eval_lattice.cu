@@ -207,41 +207,50 @@ lt_agen_kernel(const uint32_t* __restrict__ hhi, const uint8_t* __restrict__ e, 
 
 // B'_l[l_lo][2 s + comp] = limb l of (Re, Im) of a_s * i^<h_lo(s), l_lo>  (shared by all delay rows).
 // A rotation by i^r is a byte swap of the (x, y) pair (PRMT) followed by a per-byte conditional negate
-// ((w ^ m) - m with SIMD-in-word subtract).
+// ((w ^ m) - m with SIMD-in-word subtract).  One thread owns two support elements and walks over LT_BGEN_LL consecutive
+// l_lo: the limb bytes are loaded and packed once, only the two rotations change per l_lo.
+constexpr int LT_BGEN_LL = 8;
 __global__ void __launch_bounds__(256)
 lt_bgen_kernel(const uint32_t* __restrict__ hlo, const int2* __restrict__ alimb, long long S, int b2, long long Nlo,
                long long Kp, uint32_t* __restrict__ Bq) {
     const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t llo = blockIdx.y;
     if (pair * 4 >= Kp) return;
     const long long s0 = 2 * pair;
     const bool live0 = s0 < S, live1 = s0 + 1 < S;
     uint32_t base[3] = {0, 0, 0};
-    uint32_t r0 = 0, r1 = 0;
+    uint32_t h0w = 0, h1w = 0;
     if (live0) {
         const int2 w = alimb[s0];
-        r0 = dot4(hlo[s0], llo, b2);
+        h0w = hlo[s0];
 #pragma unroll
         for (int l = 0; l < 3; ++l)
             base[l] |= (((uint32_t)w.x >> (8 * l)) & 0xffu) | ((((uint32_t)w.y >> (8 * l)) & 0xffu) << 8);
     }
     if (live1) {
         const int2 w = alimb[s0 + 1];
-        r1 = dot4(hlo[s0 + 1], llo, b2);
+        h1w = hlo[s0 + 1];
 #pragma unroll
         for (int l = 0; l < 3; ++l)
             base[l] |= ((((uint32_t)w.x >> (8 * l)) & 0xffu) << 16) | ((((uint32_t)w.y >> (8 * l)) & 0xffu) << 24);
     }
-    // rotation r: swap (x, y) iff r & 1; negate byte 0 iff (r & 1) ^ (r >> 1); negate byte 1 iff r >> 1
-    const uint32_t b0 = r0 & 1u, h0 = r0 >> 1, b1 = r1 & 1u, h1 = r1 >> 1;
-    const uint32_t sel = (b0 ? 0x01u : 0x10u) | ((b1 ? 0x23u : 0x32u) << 8);
-    const uint32_t m = ((0u - (b0 ^ h0)) & 0x000000ffu) | ((0u - h0) & 0x0000ff00u) |
-                       ((0u - (b1 ^ h1)) & 0x00ff0000u) | ((0u - h1) & 0xff000000u);
     const size_t row_words = (size_t)Kp / 4;
+    const long long llo_begin = (long long)blockIdx.y * LT_BGEN_LL;
+#pragma unroll 4
+    for (int j = 0; j < LT_BGEN_LL; ++j) {
+        const long long llo = llo_begin + j;
+        if (llo >= Nlo) break;
+        // dead elements have zero limbs: their rotation does not matter
+        const uint32_t r0 = dot4(h0w, (uint32_t)llo, b2), r1 = dot4(h1w, (uint32_t)llo, b2);
+        // rotation r: swap (x, y) iff r & 1; negate byte 0 iff (r & 1) ^ (r >> 1); negate byte 1 iff r >> 1
+        const uint32_t b0 = r0 & 1u, h0 = r0 >> 1, b1 = r1 & 1u, h1 = r1 >> 1;
+        const uint32_t sel = (b0 ? 0x01u : 0x10u) | ((b1 ? 0x23u : 0x32u) << 8);
+        const uint32_t m = ((0u - (b0 ^ h0)) & 0x000000ffu) | ((0u - h0) & 0x0000ff00u) |
+                           ((0u - (b1 ^ h1)) & 0x00ff0000u) | ((0u - h1) & 0xff000000u);
 #pragma unroll
-    for (int l = 0; l < 3; ++l) {
-        const uint32_t sw = __byte_perm(base[l], 0u, sel);
-        Bq[((size_t)l * Nlo + llo) * row_words + pair] = __vsub4(sw ^ m, m);
+        for (int l = 0; l < 3; ++l) {
+            const uint32_t sw = __byte_perm(base[l], 0u, sel);
+            Bq[((size_t)l * Nlo + (size_t)llo) * row_words + pair] = __vsub4(sw ^ m, m);
+        }
     }
 }
 
@@ -1064,7 +1073,8 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
         lt_amax_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax);
         lt_quant_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax, inv_scale, alimb);
         const unsigned pb = (unsigned)((Kp / 4 + T - 1) / T);
-        lt_bgen_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp, reinterpret_cast<uint32_t*>(Bq));
+        lt_bgen_kernel<<<dim3(pb, (unsigned)((Nlo + LT_BGEN_LL - 1) / LT_BGEN_LL)), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp,
+                                                                                                 reinterpret_cast<uint32_t*>(Bq));
         g_qsft_launches.fetch_add(4, std::memory_order_relaxed);
         const unsigned wb = (unsigned)((Tw + T - 1) / T);
         if (fused_a || sparse_ts) {

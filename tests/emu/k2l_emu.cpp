@@ -28,7 +28,7 @@ int emu_lt_quant(const float* a, long long S, float* inv_scale, int32_t* alimb /
 
 int emu_lt_bgen(const uint32_t* hlo, const int32_t* alimb, long long S, int b2, long long Nlo, long long Kp, uint32_t* Bq) {
     const int T = 256;
-    emu::launch(dim3((unsigned)((Kp / 4 + T - 1) / T), (unsigned)Nlo), dim3(T),
+    emu::launch(dim3((unsigned)((Kp / 4 + T - 1) / T), (unsigned)((Nlo + LT_BGEN_LL - 1) / LT_BGEN_LL)), dim3(T),
                 [&]() { lt_bgen_kernel(hlo, reinterpret_cast<const int2*>(alimb), S, b2, Nlo, Kp, Bq); });
     return 0;
 }
