@@ -60,10 +60,11 @@ extern "C" {
 int emu_classify(int q, int n, int b, int C, int P, int P_src, int channel, int source, int rs_t, int rs_s, int ld,
                  float cutoff, const int8_t* MT, const int8_t* D, const int32_t* rs_exp, const int32_t* rs_log,
                  const float* U, long long* find_cj, int8_t* find_k, float* find_rho, int32_t* find_round, int32_t* find_id,
-                 long long max_finds, int round, unsigned long long* counters, int impl) {
+                 long long max_finds, int round, unsigned long long* counters, int impl, long long j_begin, long long j_end) {
     PeelDev d;
     fill_dev(&d, q, n, b, C, P, P_src, channel, source, rs_t, rs_s, ld, cutoff, MT, D, rs_exp, rs_log);
-    classify(d, reinterpret_cast<const float2*>(U), 0, d.B, find_cj, find_k, reinterpret_cast<float2*>(find_rho), find_round,
+    if (j_end < 0) j_end = d.B;
+    classify(d, reinterpret_cast<const float2*>(U), j_begin, j_end, find_cj, find_k, reinterpret_cast<float2*>(find_rho), find_round,
              find_id, max_finds, round, counters, impl);
     return 0;
 }

@@ -21,7 +21,7 @@ def emu():
     L = C.CDLL(build_emu.build())
     vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float
     desc = [i32] * 11 + [f32, vp, vp, vp, vp]
-    L.emu_classify.argtypes = desc + [vp, vp, vp, vp, vp, vp, i64, i32, vp, i32]
+    L.emu_classify.argtypes = desc + [vp, vp, vp, vp, vp, vp, i64, i32, vp, i32, i64, i64]
     L.emu_peel.argtypes = desc + [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, i32,
                                   C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.emu_detect.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32]
@@ -76,11 +76,12 @@ class Problem:
         return [self.q, self.n, self.b, self.C, self.P, self.P_src, self.channel, 0, 0, 0, self.ld, C.c_float(self.cutoff),
                 _p(self.MT), _p(self.D), None, None]
 
-    def classify(self, L, U, impl):
+    def classify(self, L, U, impl, ranges=None):
         self.counters[:] = 0
         self.find_id[:] = -7
-        assert L.emu_classify(*self.desc(), _p(U), _p(self.find_cj), _p(self.find_k), _p(self.find_rho), _p(self.find_round),
-                              _p(self.find_id), self.max_finds, 1, _p(self.counters), impl) == 0
+        for (jb, je) in (ranges or [(0, -1)]):               # bin ranges append to the same find list (sharded peel)
+            assert L.emu_classify(*self.desc(), _p(U), _p(self.find_cj), _p(self.find_k), _p(self.find_rho),
+                                  _p(self.find_round), _p(self.find_id), self.max_finds, 1, _p(self.counters), impl, jb, je) == 0
         nf, nm = int(self.counters[0]), int(self.counters[1])
         order = np.argsort(self.find_cj[:nf])
         return {"nf": nf, "nm": nm, "cj": self.find_cj[:nf][order].copy(), "k": self.find_k[:nf][order].copy(),
@@ -257,3 +258,18 @@ def test_emulated_peel_coded_source_vs_oracle(emu):
     keys, vals, _, _ = prob.peel(emu, U, 1)
     assert keys == list(want.keys()) and len(keys) >= 0.8 * len(signal_w)
     assert np.max(np.abs(vals - np.array(list(want.values())))) <= 1e-5
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+def test_emulated_classify_bin_ranges(emu, impl):
+    """Bin-sharded classification (multi-GPU peel): ragged ranges that do not align with the CTA tiles give the same finds
+    and the same find table as one pass over all bins."""
+    g = load_golden("cfg2r_q4_n14_b5_nso_noisy")
+    p = case_params(g)
+    prob, U = _problem_from_golden(g, p)
+    full = prob.classify(emu, U, impl)
+    B = prob.B
+    parts = prob.classify(emu, U, impl, ranges=[(0, 37), (37, 37), (37, 700), (700, B)])
+    assert parts["nf"] == full["nf"] and parts["nm"] == full["nm"]
+    assert np.array_equal(parts["cj"], full["cj"]) and np.array_equal(parts["k"], full["k"])
+    assert np.array_equal(parts["fid"] >= 0, full["fid"] >= 0) and not (parts["fid"] == -7).any()
