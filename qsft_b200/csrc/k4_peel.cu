@@ -71,6 +71,20 @@ __device__ __forceinline__ long long hash_bin(const PeelDev& d, int c, const uin
     return j;
 }
 
+// the same hash computed by a whole warp: one hash digit per lane (b <= 32), all lanes get the result
+template <int NW>
+__device__ __forceinline__ long long hash_bin_warp(const PeelDev& d, int c, const uint32_t (&kw)[NW], int lane) {
+    long long part = 0;
+    if (lane < d.b) {
+        long long wgt = 1;
+        for (int u = lane + 1; u < d.b; ++u) wgt *= d.q;
+        part = wgt * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + lane) * d.ld, d.ld, kw), d.q, d.qmagic);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    return part;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // GF(p^s) helpers for the coded path; elements are ints whose base-p digits are polynomial coefficients.
 // ---------------------------------------------------------------------------------------------------------
@@ -653,7 +667,7 @@ k4_apply_kernel(PeelDev d, float2* __restrict__ U, long long j_begin, long long 
     if (dedupe) {
         // ball_values "last (i, j) wins" (qsft.py:215): skip when a higher group found the same k this round
         for (int c2 = c + 1; c2 < d.C; ++c2) {
-            const long long j2 = hash_bin<NW>(d, c2, kw);
+            const long long j2 = hash_bin_warp<NW>(d, c2, kw, lane);
             const int32_t f2 = find_id[(size_t)c2 * d.B + j2];
             if (f2 >= 0 && (long long)f2 < id_limit) {
                 const uint32_t* k2 = reinterpret_cast<const uint32_t*>(find_k + (size_t)f2 * d.ld);
@@ -668,7 +682,7 @@ k4_apply_kernel(PeelDev d, float2* __restrict__ U, long long j_begin, long long 
     const float2 rho = find_rho[f];
     const float inv_q = 1.0f / (float)d.q;
     for (int l = 0; l < d.C; ++l) {
-        const long long j = hash_bin<NW>(d, l, kw);
+        const long long j = hash_bin_warp<NW>(d, l, kw, lane);
         if (j < j_begin || j >= j_end) continue;
         float2* Ul = U + (size_t)l * d.P * d.B + j;
         const int8_t* Dl = d.D + (size_t)l * d.P * d.ld;
