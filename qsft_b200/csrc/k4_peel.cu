@@ -71,15 +71,20 @@ __device__ __forceinline__ long long hash_bin(const PeelDev& d, int c, const uin
     return j;
 }
 
-// the same hash computed by a whole warp: one hash digit per lane (b <= 32), all lanes get the result
+// weight q^(b-1-i) of hash digit i (0 for i >= b): loop invariant of the per-bin / per-find work, computed once per thread
+__device__ __forceinline__ long long hash_weight(const PeelDev& d, int i) {
+    if (i >= d.b) return 0;
+    long long wgt = 1;
+    for (int u = i + 1; u < d.b; ++u) wgt *= d.q;
+    return wgt;
+}
+
+// the same hash computed by a whole warp: one hash digit per lane (b <= 32), all lanes get the result;
+// wgt = hash_weight(d, lane)
 template <int NW>
-__device__ __forceinline__ long long hash_bin_warp(const PeelDev& d, int c, const uint32_t (&kw)[NW], int lane) {
+__device__ __forceinline__ long long hash_bin_warp(const PeelDev& d, int c, const uint32_t (&kw)[NW], int lane, long long wgt) {
     long long part = 0;
-    if (lane < d.b) {
-        long long wgt = 1;
-        for (int u = lane + 1; u < d.b; ++u) wgt *= d.q;
-        part = wgt * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + lane) * d.ld, d.ld, kw), d.q, d.qmagic);
-    }
+    if (lane < d.b) part = wgt * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + lane) * d.ld, d.ld, kw), d.q, d.qmagic);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     return part;
@@ -380,6 +385,8 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
 
     const int nsym = d.P_src - 1;
     const int8_t* Dc = d.D + (size_t)c * d.P * d.ld;
+    const long long wgt = hash_weight(d, lane);                   // loop invariants of the per-bin work
+    for (int i = d.n + lane; i < 4 * NW && i < QSFT_MAX_N; i += 32) s_k[warp][i] = 0;   // zero padding of k: written once
     unsigned n_multi = 0;
     while (mask) {
         const int bi = __ffs(mask) - 1;
@@ -403,7 +410,6 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
         } else {
             for (int i = lane; i < d.n; i += 32) s_k[warp][i] = s_sym[warp][i];
         }
-        for (int i = d.n + lane; i < 4 * NW && i < QSFT_MAX_N; i += 32) s_k[warp][i] = 0;
         __syncwarp();
         uint32_t kw[NW];
 #pragma unroll
@@ -424,11 +430,7 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
         const double res = e_b - (double)d.P * (rr * rr + ri * ri);
         // bin hash j = dec(M_c^T k mod q) (qsft.py:178-179), one hash digit per lane
         long long part = 0;
-        if (lane < d.b) {
-            long long wgt = 1;
-            for (int u = lane + 1; u < d.b; ++u) wgt *= d.q;
-            part = wgt * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + lane) * d.ld, d.ld, kw), d.q, d.qmagic);
-        }
+        if (lane < d.b) part = wgt * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + lane) * d.ld, d.ld, kw), d.q, d.qmagic);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         const bool single = (part == jb) && !(res > d.thresh);                          // qsft.py:183
@@ -575,6 +577,9 @@ k4_classify_v2_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin
     uint8_t* sym = s_sym + (size_t)grp * (4 * NW);
     const int iters = (total + K4V2_THREADS / K4V2_G - 1) / (K4V2_THREADS / K4V2_G);
     unsigned n_multi = 0;
+    long long wgt[32 / K4V2_G];                                          // hash digit weights of this lane (b <= 32)
+#pragma unroll
+    for (int u = 0; u < 32 / K4V2_G; ++u) wgt[u] = hash_weight(d, gl + u * K4V2_G);
     for (int it = 0; it < iters; ++it) {                                 // uniform trip count: the shuffles below use full masks
         const int ci = it * (K4V2_THREADS / K4V2_G) + grp;
         const bool valid = ci < total;
@@ -598,10 +603,10 @@ k4_classify_v2_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin
             ri += cs * v.y - sn * v.x;
         }
         long long part = 0;
-        for (int i = gl; i < d.b; i += K4V2_G) {
-            long long wgt = 1;
-            for (int u = i + 1; u < d.b; ++u) wgt *= d.q;
-            part += wgt * fast_mod(dot_raw_s<NW>(s_MT + (size_t)i * rs, d.ld, kw), d.q, d.qmagic);
+#pragma unroll
+        for (int u = 0; u < 32 / K4V2_G; ++u) {
+            const int i = gl + u * K4V2_G;
+            if (i < d.b) part += wgt[u] * fast_mod(dot_raw_s<NW>(s_MT + (size_t)i * rs, d.ld, kw), d.q, d.qmagic);
         }
 #pragma unroll
         for (int o = K4V2_G / 2; o > 0; o >>= 1) {                       // xor partners stay inside the aligned 8-lane group
@@ -659,6 +664,7 @@ k4_apply_kernel(PeelDev d, float2* __restrict__ U, long long j_begin, long long 
     if (f >= f_begin + n_finds) return;
     const long long cj = find_cj[f];
     const int c = (int)(cj / d.B);
+    const long long wgt = hash_weight(d, lane);
     uint32_t kw[NW];
     const uint32_t* kin = reinterpret_cast<const uint32_t*>(find_k + (size_t)f * d.ld);
 #pragma unroll
@@ -667,7 +673,7 @@ k4_apply_kernel(PeelDev d, float2* __restrict__ U, long long j_begin, long long 
     if (dedupe) {
         // ball_values "last (i, j) wins" (qsft.py:215): skip when a higher group found the same k this round
         for (int c2 = c + 1; c2 < d.C; ++c2) {
-            const long long j2 = hash_bin_warp<NW>(d, c2, kw, lane);
+            const long long j2 = hash_bin_warp<NW>(d, c2, kw, lane, wgt);
             const int32_t f2 = find_id[(size_t)c2 * d.B + j2];
             if (f2 >= 0 && (long long)f2 < id_limit) {
                 const uint32_t* k2 = reinterpret_cast<const uint32_t*>(find_k + (size_t)f2 * d.ld);
@@ -682,7 +688,7 @@ k4_apply_kernel(PeelDev d, float2* __restrict__ U, long long j_begin, long long 
     const float2 rho = find_rho[f];
     const float inv_q = 1.0f / (float)d.q;
     for (int l = 0; l < d.C; ++l) {
-        const long long j = hash_bin_warp<NW>(d, l, kw, lane);
+        const long long j = hash_bin_warp<NW>(d, l, kw, lane, wgt);
         if (j < j_begin || j >= j_end) continue;
         float2* Ul = U + (size_t)l * d.P * d.B + j;
         const int8_t* Dl = d.D + (size_t)l * d.P * d.ld;
