@@ -257,18 +257,28 @@ lt_bgen_kernel(const uint32_t* __restrict__ hlo, const int2* __restrict__ alimb,
 // ---- packed phase tables for the in-kernel generation of A' (FUSED_A) -------------------------------------
 // T[l_hi][w]: 16 two-bit fields <h_hi(s), l_hi> mod 4 for s = 16 w .. 16 w + 15;  E2[p][w]: the delay phases e[p][s] packed
 // the same way.  A' is then a pure function of (T + E2) mod 4, generated slab by slab in shared memory by the GEMM CTAs.
+// One thread owns the sixteen support elements of word w and walks over LT_TTAB_LL consecutive l_hi (the bin-hash words
+// are loaded once); blockIdx.y enumerates groups of LT_TTAB_LL rows.
+constexpr int LT_TTAB_LL = 8;
 __global__ void __launch_bounds__(256)
-lt_ttab_kernel(const uint32_t* __restrict__ hhi, long long S, int b1, long long Tw, uint32_t* __restrict__ T) {
+lt_ttab_kernel(const uint32_t* __restrict__ hhi, long long S, int b1, long long Tw, long long Mhi, uint32_t* __restrict__ T) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lhi = blockIdx.y;
     if (w >= Tw) return;
-    uint32_t word = 0;
-#pragma unroll 4
+    uint32_t h[16];
+#pragma unroll
     for (int i = 0; i < 16; ++i) {
         const long long s = 16 * w + i;
-        if (s < S) word |= dot4(hhi[s], lhi, b1) << (2 * i);
+        h[i] = s < S ? hhi[s] : 0u;                     // dead elements: rotation 0, like the per-element guard before
     }
-    T[(size_t)lhi * Tw + w] = word;
+    const long long l0 = (long long)blockIdx.y * LT_TTAB_LL;
+    for (int j = 0; j < LT_TTAB_LL; ++j) {
+        const long long lhi = l0 + j;
+        if (lhi >= Mhi) break;
+        uint32_t word = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) word |= dot4(h[i], (uint32_t)lhi, b1) << (2 * i);
+        T[(size_t)lhi * Tw + w] = word;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1078,7 +1088,7 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
         g_qsft_launches.fetch_add(4, std::memory_order_relaxed);
         const unsigned wb = (unsigned)((Tw + T - 1) / T);
         if (fused_a || sparse_ts) {
-            lt_ttab_kernel<<<dim3(wb, (unsigned)Mhi), T, 0, st>>>(hhi, S, b1, Tw, Ttab);
+            lt_ttab_kernel<<<dim3(wb, (unsigned)((Mhi + LT_TTAB_LL - 1) / LT_TTAB_LL)), T, 0, st>>>(hhi, S, b1, Tw, Mhi, Ttab);
             g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
         }
         if (fused_a || sparse_mode) {

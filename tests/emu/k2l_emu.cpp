@@ -35,7 +35,8 @@ int emu_lt_bgen(const uint32_t* hlo, const int32_t* alimb, long long S, int b2, 
 
 int emu_lt_ttab(const uint32_t* hhi, long long S, int b1, long long Tw, long long Mhi, uint32_t* T_) {
     const int T = 256;
-    emu::launch(dim3((unsigned)((Tw + T - 1) / T), (unsigned)Mhi), dim3(T), [&]() { lt_ttab_kernel(hhi, S, b1, Tw, T_); });
+    emu::launch(dim3((unsigned)((Tw + T - 1) / T), (unsigned)((Mhi + LT_TTAB_LL - 1) / LT_TTAB_LL)), dim3(T),
+                [&]() { lt_ttab_kernel(hhi, S, b1, Tw, Mhi, T_); });
     return 0;
 }
 
