@@ -417,7 +417,7 @@ def run_extras():
     """Untimed side checks AFTER the measurement, each in its own subprocess (a failure or a crash there cannot touch the
     numbers above): the GPU tests of code that was written after the round's interactive GPU budget was spent and are
     therefore skipped in the default suite, and A/B timings of the opt-in kernel variants.  Nothing here feeds `value`."""
-    deadline = time.time() + 180.0          # all side checks together: at most 3 minutes
+    deadline = time.time() + 240.0          # all side checks together: at most 4 minutes
 
     def sub(cmd, env=None, timeout=120):
         t0 = time.time()
@@ -437,6 +437,17 @@ def run_extras():
 
     out = {"note": "untimed side checks run after the measurement in subprocesses; not part of value / e2e"}
     py = sys.executable
+    # 0. the same bench (short) with the opt-in A' expansion of the GEMM kernel: whole-step A/B against the line above
+    rc, so, se, dt = sub([py, os.path.abspath(__file__), "--steps", "6", "--warmup", "3", "--no-cpu-baseline", "--no-extras"],
+                         {"QSFT_LATTICE_EXPAND": "1"}, timeout=90)
+    try:
+        ab = json.loads(so.strip().splitlines()[-1])
+        out["bench_QSFT_LATTICE_EXPAND=1"] = {"ms_per_step": ab["ms_per_step"], "e2e": ab["e2e"]["value"],
+                                              "support_recovered_exactly": ab["config"]["support_recovered_exactly"],
+                                              "max_coeff_err": ab["config"]["max_coeff_err"], "clocks": ab.get("clocks"),
+                                              "k2_ms_per_step": ab["roofline"]["per_kernel_ms_per_step"].get("k2_eval_lattice")}
+    except Exception:
+        out["bench_QSFT_LATTICE_EXPAND=1"] = {"rc": rc, "stderr": se[-300:]}
     # 1. stand-alone timings: K3 ticket-lag / CTAs-per-SM sweep, K4 classification variants (with a parity checksum)
     rc, so, se, dt = sub([py, "tools/microbench.py", "--only", "k3lag,k4", "--k4-variants"], timeout=90)
     try:

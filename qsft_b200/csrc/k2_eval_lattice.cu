@@ -294,6 +294,28 @@ lt_etab_kernel(const uint8_t* __restrict__ e, long long S, long long Se, int P, 
     E2[(size_t)p * Tw + w] = word;
 }
 
+// sixteen support elements of one A' row: rotations r16 (2 bits each) -> 16 compressed bytes (+-1) + 8 metadata nibbles
+// (same encoding as lt_agen_sp_kernel).  PX = false: sign bits spread by a multiply, masked, scaled by 0xFE and xor-ed
+// (six instructions per four elements).  PX = true (opt-in QSFT_LATTICE_EXPAND=1, unmeasured): the multiply moves sign bit
+// 2j of the group straight to the top bit of byte j (shifts 7 + 6i: bit 2j + 7 + 6i = 8b + 7 only for i = j = b, and nothing
+// else ever lands on or carries into 8b + 6 / 8b + 7), PRMT in sign-replication mode turns the bytes into 0x00 / 0xFF and an
+// OR sets the low bit: five instructions, no mask of the product.  Both are checked exhaustively per group on the CPU.
+template <bool PX>
+__device__ __forceinline__ void ts_expand(uint32_t r16, bool im, uint32_t* a4, uint32_t& e1) {
+    const uint32_t lo = r16 & 0x55555555u, hi = (r16 >> 1) & 0x55555555u;
+    const uint32_t neg = im ? hi : (lo ^ hi);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (PX) {
+            a4[g] = __byte_perm(((neg >> (8 * g)) & 0x55u) * 0x02082080u, 0u, 0xBA98u) | 0x01010101u;
+        } else {
+            const uint32_t m = (((neg >> (8 * g)) & 0x55u) * 0x00041041u) & 0x01010101u;
+            a4[g] = 0x01010101u ^ (m * 0xFEu);
+        }
+    }
+    e1 = (lo | 0x88888888u) ^ (im ? 0x55555555u : 0u);
+}
+
 // ---- the GEMM ---------------------------------------------------------------------------------------------
 // 16 bytes of an A' row pair: eight support elements, t = eight 2-bit phases (bits 0..15 of `t16`)
 //   re chunk = (er, -ei) x 8, im chunk = (ei, er) x 8, (er, ei) = i^t
@@ -770,19 +792,8 @@ __device__ __forceinline__ void ts_st4(uint32_t taddr, const uint32_t (&r)[4]) {
                  "r"(r[3])
                  : "memory");
 }
-// sixteen support elements of one A' row: rotations r16 (2 bits each) -> 16 compressed bytes + 8 metadata nibbles
-// (same encoding as lt_agen_sp_kernel)
-__device__ __forceinline__ void ts_expand(uint32_t r16, bool im, uint32_t* a4, uint32_t& e1) {
-    const uint32_t lo = r16 & 0x55555555u, hi = (r16 >> 1) & 0x55555555u;
-    const uint32_t neg = im ? hi : (lo ^ hi);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const uint32_t m = (((neg >> (8 * g)) & 0x55u) * 0x00041041u) & 0x01010101u;
-        a4[g] = 0x01010101u ^ (m * 0xFEu);
-    }
-    e1 = (lo | 0x88888888u) ^ (im ? 0x55555555u : 0u);
-}
 
+template <bool PX>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2, int nkb, int Mhi, int Nlo,
                     int n_mtiles, const uint32_t* __restrict__ Ttab, const uint32_t* __restrict__ Etab, int Tw,
@@ -904,7 +915,7 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 for (int wi = 0; wi < 4; ++wi) {
                     constexpr uint32_t H = 0xAAAAAAAAu;
                     const uint32_t r16 = ((tw[wi] & ~H) + (ew[wi] & ~H)) ^ ((tw[wi] ^ ew[wi]) & H);
-                    ts_expand(r16, odd, &av[4 * wi], ev[wi]);
+                    ts_expand<PX>(r16, odd, &av[4 * wi], ev[wi]);
                 }
                 lt_mbar_wait(&tfree[buf], ((uint32_t)(kb / TS_NBUF) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1105,7 +1116,8 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
                 if (cudaFuncSetAttribute(lt_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
                     cudaFuncSetAttribute(lt_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
                     cudaFuncSetAttribute(lt_gemm_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM) != cudaSuccess ||
-                    cudaFuncSetAttribute(lt_gemm_spts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess) {
+                    cudaFuncSetAttribute(lt_gemm_spts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess ||
+                    cudaFuncSetAttribute(lt_gemm_spts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess) {
                     qsft_set_error("cudaFuncSetAttribute failed");
                     rc = QSFT_ECUDA;
                 }
@@ -1134,7 +1146,9 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
                 cattr[0].val.clusterDim.z = 1;
                 cfg.attrs = cattr;
                 cfg.numAttrs = 1;
-                cudaLaunchKernelEx(&cfg, lt_gemm_spts_kernel, mb, mb2, (int)(Kp / SP_BK), (int)Mhi, (int)Nlo, (int)n_mt,
+                const char* px = getenv("QSFT_LATTICE_EXPAND");                  // opt-in A' expansion variant (see ts_expand)
+                cudaLaunchKernelEx(&cfg, (px && atoi(px) == 1) ? lt_gemm_spts_kernel<true> : lt_gemm_spts_kernel<false>, mb, mb2,
+                                   (int)(Kp / SP_BK), (int)Mhi, (int)Nlo, (int)n_mt,
                                    (const uint32_t*)Ttab, (const uint32_t*)(Etab + (size_t)p0 * Tw), (int)Tw,
                                    (const float*)inv_scale, o);
                 g_qsft_launches.fetch_add(1, std::memory_order_relaxed);

@@ -53,4 +53,13 @@ int emu_lt_agen(const uint32_t* hhi, const uint8_t* e, long long S, long long Se
                 [&]() { lt_agen_kernel(hhi, e, S, Se, b1, P, Mhi, Kp, A); });
     return 0;
 }
+
+// the A' expansion of the tensor-memory GEMM kernel (ts_expand<PX>) for n words: a4 (n, 4), e1 (n)
+int emu_ts_expand(const uint32_t* r16, long long n, int im, int px, uint32_t* a4, uint32_t* e1) {
+    for (long long i = 0; i < n; ++i) {
+        if (px) ts_expand<true>(r16[i], im != 0, a4 + 4 * i, e1[i]);
+        else ts_expand<false>(r16[i], im != 0, a4 + 4 * i, e1[i]);
+    }
+    return 0;
+}
 }

@@ -100,3 +100,34 @@ def test_emulated_lattice_operands_reproduce_the_samples(emu, n, b, S, P, seed):
     assert np.array_equal(pairs[:, :, 1, :, 0], ei) and np.array_equal(pairs[:, :, 1, :, 1], er)
     lhi_d = np.stack([(np.arange(Mhi) >> (2 * (b1 - 1 - i))) & 3 for i in range(b1)])     # (b1, Mhi) MSB first
     assert np.array_equal(Tf, (lhi_d.T @ H[:b1]) % 4)
+
+
+def test_ts_expand_variants_match_the_definition(emu):
+    """The A' expansion inside the tensor-memory GEMM kernel (16 two-bit rotations -> 16 bytes of +-1 and 8 metadata
+    nibbles): the default and the opt-in PRMT variant (QSFT_LATTICE_EXPAND=1) agree with each other and with the
+    definition -- Re row (er, -ei), Im row (ei, er), (er, ei) = i^r, 2:4 metadata nibble = idx0 | idx1 << 2 -- for every
+    16-bit pattern in both halves of the word and for random words."""
+    emu.emu_ts_expand.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(0)
+    low = np.arange(1 << 16, dtype=np.uint32)
+    words = np.ascontiguousarray(np.concatenate([low, low << 16, low | (low << 16), rng.integers(0, 1 << 32, 200_000, dtype=np.uint64)
+                                                 .astype(np.uint32)]))
+    f = np.arange(16)
+    rot = (words[:, None] >> (2 * f)) & 3                                  # (N, 16)
+    er, ei = np.array([1, 0, -1, 0])[rot], np.array([0, 1, 0, -1])[rot]
+    for im in (0, 1):
+        dense = np.stack([ei, er], axis=-1) if im else np.stack([er, -ei], axis=-1)      # (N, 16, 2) logical byte pairs
+        outs = []
+        for px in (0, 1):
+            a4 = np.zeros((len(words), 4), dtype=np.uint32)
+            e1 = np.zeros(len(words), dtype=np.uint32)
+            assert emu.emu_ts_expand(_p(words), len(words), im, px, _p(a4), _p(e1)) == 0
+            outs.append((a4, e1))
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+        comp = outs[0][0].view(np.int8).reshape(len(words), 16)            # one compressed byte per support element
+        nib = (outs[0][1][:, None] >> (4 * np.arange(8))) & 15             # one nibble per element pair
+        assert (nib & 8).all() and not (nib & 2).any()
+        pos = np.stack([nib & 1, (nib >> 2) & 1], axis=-1).reshape(len(words), 16)       # index of the non-zero in each pair
+        rebuilt = np.zeros_like(dense)
+        np.put_along_axis(rebuilt, pos[..., None], comp[..., None].astype(dense.dtype), axis=-1)
+        assert np.array_equal(rebuilt, dense)
