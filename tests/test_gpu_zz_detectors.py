@@ -345,3 +345,22 @@ def test_dense_gwht_igwht_utils():
             assert np.max(np.abs(back - g[key])) <= 1e-5 * np.max(np.abs(g[key]))
             shaped = utils.gwht_tensored(g[key].reshape([q] * b), q, b)
             assert shaped.shape == tuple([q] * b) and np.max(np.abs(shaped.ravel() - y)) == 0
+
+
+@experimental
+@pytest.mark.parametrize("n,b,S,P,seed", [(14, 7, 700, 5, 0), (40, 10, 3000, 3, 1), (20, 9, 257, 4, 3)])
+def test_experimental_lattice_expand_variant_bit_identical(n, b, S, P, seed, monkeypatch):
+    """QSFT_LATTICE_EXPAND=1 (PRMT sign-replication A' expansion in the tensor-memory GEMM) produces the same bits."""
+    q = 4
+    rng = np.random.default_rng(seed)
+    M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
+    locq = rng.integers(0, q, (n, S))
+    a = rng.uniform(0.5, 2, S) * np.exp(1j * rng.uniform(0, 2 * np.pi, S))
+    ld = utils.padded_ld(n)
+    loc = ops.pad_digits(locq.T, ld, DEV)
+    ad = torch.from_numpy(a.astype(np.complex64)).to(DEV)
+    monkeypatch.delenv("QSFT_LATTICE_EXPAND", raising=False)
+    ref = ops.eval_synth_lattice(M, D, loc, ad, q).clone()
+    monkeypatch.setenv("QSFT_LATTICE_EXPAND", "1")
+    got = ops.eval_synth_lattice(M, D, loc, ad, q)
+    assert torch.equal(got, ref)
