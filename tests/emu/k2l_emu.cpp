@@ -62,4 +62,13 @@ int emu_ts_expand(const uint32_t* r16, long long n, int im, int px, uint32_t* a4
     }
     return 0;
 }
+
+// the producers' whole per-word step: table words (t, e) -> expansion of (t + e) mod 4
+int emu_ts_phase_expand(const uint32_t* tw, const uint32_t* ew, long long n, int im, int px, uint32_t* a4, uint32_t* e1) {
+    for (long long i = 0; i < n; ++i) {
+        if (px) ts_phase_expand<true>(tw[i], ew[i], im != 0, a4 + 4 * i, e1[i]);
+        else ts_phase_expand<false>(tw[i], ew[i], im != 0, a4 + 4 * i, e1[i]);
+    }
+    return 0;
+}
 }

@@ -131,3 +131,26 @@ def test_ts_expand_variants_match_the_definition(emu):
         rebuilt = np.zeros_like(dense)
         np.put_along_axis(rebuilt, pos[..., None], comp[..., None].astype(dense.dtype), axis=-1)
         assert np.array_equal(rebuilt, dense)
+
+
+def test_ts_phase_expand_variants(emu):
+    """Table words (t, e) -> expansion of (t + e) mod 4: the opt-in variant (bit planes computed directly) == the default
+    (SWAR add + expansion) == expansion of the field-wise sum, for all pairs of 8-bit patterns in every byte and random words."""
+    emu.emu_ts_expand.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    emu.emu_ts_phase_expand.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(1)
+    a8, b8 = np.meshgrid(np.arange(256, dtype=np.uint32), np.arange(256, dtype=np.uint32), indexing="ij")
+    a8, b8 = a8.ravel(), b8.ravel()
+    tw = np.concatenate([a8 * 0x01010101, a8 << 24, rng.integers(0, 1 << 32, 300_000, dtype=np.uint64).astype(np.uint32)])
+    ew = np.concatenate([b8 * 0x01010101, b8 << 24, rng.integers(0, 1 << 32, 300_000, dtype=np.uint64).astype(np.uint32)])
+    tw, ew = np.ascontiguousarray(tw.astype(np.uint32)), np.ascontiguousarray(ew.astype(np.uint32))
+    f = np.arange(16, dtype=np.uint32)
+    summed = ((((tw[:, None] >> (2 * f)) & 3) + ((ew[:, None] >> (2 * f)) & 3)) & 3)
+    r16 = np.ascontiguousarray(np.bitwise_or.reduce(summed.astype(np.uint32) << (2 * f), axis=1).astype(np.uint32))
+    for im in (0, 1):
+        want_a, want_e = np.zeros((len(tw), 4), dtype=np.uint32), np.zeros(len(tw), dtype=np.uint32)
+        assert emu.emu_ts_expand(_p(r16), len(r16), im, 0, _p(want_a), _p(want_e)) == 0
+        for px in (0, 1):
+            a4, e1 = np.zeros((len(tw), 4), dtype=np.uint32), np.zeros(len(tw), dtype=np.uint32)
+            assert emu.emu_ts_phase_expand(_p(tw), _p(ew), len(tw), im, px, _p(a4), _p(e1)) == 0
+            assert np.array_equal(a4, want_a) and np.array_equal(e1, want_e), (im, px)
