@@ -300,6 +300,22 @@ lt_etab_kernel(const uint8_t* __restrict__ e, long long S, long long Se, int P, 
 // 2j of the group straight to the top bit of byte j (shifts 7 + 6i: bit 2j + 7 + 6i = 8b + 7 only for i = j = b, and nothing
 // else ever lands on or carries into 8b + 6 / 8b + 7), PRMT in sign-replication mode turns the bytes into 0x00 / 0xFF and an
 // OR sets the low bit: five instructions, no mask of the product.  Both are checked exhaustively per group on the CPU.
+// every byte -> 0x00 / 0xFF according to its top bit: PTX prmt in its generic form replicates the sign of the selected byte
+// when bit 3 of the selector nibble is set.  (CUDA's __byte_perm only honours three selector bits per nibble -- the compiler
+// masks 0xBA98 to 0x3210, an identity permutation -- so this has to be the PTX instruction.)
+__device__ __forceinline__ uint32_t lt_sign_bytes(uint32_t x) {
+#ifdef QSFT_EMU   // CPU execution by tests/emu (test infrastructure; never defined in the product build)
+    uint32_t o = 0;
+    for (int i = 0; i < 4; ++i)
+        if ((x >> (8 * i + 7)) & 1u) o |= 0xFFu << (8 * i);
+    return o;
+#else
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xBA98u));
+    return d;
+#endif
+}
+
 template <bool PX>
 __device__ __forceinline__ void ts_expand(uint32_t r16, bool im, uint32_t* a4, uint32_t& e1) {
     const uint32_t lo = r16 & 0x55555555u, hi = (r16 >> 1) & 0x55555555u;
@@ -307,7 +323,7 @@ __device__ __forceinline__ void ts_expand(uint32_t r16, bool im, uint32_t* a4, u
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         if (PX) {
-            a4[g] = __byte_perm(((neg >> (8 * g)) & 0x55u) * 0x02082080u, 0u, 0xBA98u) | 0x01010101u;
+            a4[g] = lt_sign_bytes(((neg >> (8 * g)) & 0x55u) * 0x02082080u) | 0x01010101u;
         } else {
             const uint32_t m = (((neg >> (8 * g)) & 0x55u) * 0x00041041u) & 0x01010101u;
             a4[g] = 0x01010101u ^ (m * 0xFEu);
@@ -332,7 +348,7 @@ __device__ __forceinline__ void ts_phase_expand(uint32_t tw, uint32_t ew, bool i
         const uint32_t neg = im ? hi : (lo ^ hi);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-            a4[g] = __byte_perm(((neg >> (8 * g)) & 0x55u) * 0x02082080u, 0u, 0xBA98u) | 0x01010101u;
+            a4[g] = lt_sign_bytes(((neg >> (8 * g)) & 0x55u) * 0x02082080u) | 0x01010101u;
         e1 = (lo | 0x88888888u) ^ (im ? 0x55555555u : 0u);
     }
 }

@@ -205,9 +205,8 @@ inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
     const unsigned long long pool = ((unsigned long long)b << 32) | a;
     unsigned out = 0;
     for (int i = 0; i < 4; ++i) {
-        const unsigned n = (sel >> (4 * i)) & 0xfu;
-        unsigned byte = (unsigned)(pool >> (8 * (n & 7u))) & 0xffu;
-        if (n & 8u) byte = (byte & 0x80u) ? 0xffu : 0x00u;          // sign replication mode
+        const unsigned n = (sel >> (4 * i)) & 0x7u;                 // CUDA's __byte_perm honours THREE selector bits per nibble
+        const unsigned byte = (unsigned)(pool >> (8 * n)) & 0xffu;  // (no sign-replication mode, unlike PTX prmt)
         out |= byte << (8 * i);
     }
     return out;
