@@ -20,6 +20,10 @@ QSFT_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_detector
 QSFT_K4_IMPL=2 timeout 300 python tools/microbench.py > $out/${tag}_microbench_k4v2.json 2> $out/${tag}_microbench_k4v2.err
 timeout 600 python bench.py > $out/${tag}_bench_N1.json 2> $out/${tag}_bench_N1.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 0 > $out/${tag}_bench_reference.json 2> /dev/null
+# whole-step A/B of the opt-in variants (same box, back to back)
+QSFT_LATTICE_EXPAND=1 timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-extras > $out/${tag}_bench_N1_expand.json 2> /dev/null
+QSFT_K4_IMPL=2 QSFT_K4_FASTDET=1 timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-extras > $out/${tag}_bench_N1_k4v2.json 2> /dev/null
+timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-extras > $out/${tag}_bench_N1_default_again.json 2> /dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k3_q4_twopass|k4_classify|k4_apply|k4_reduce' -c 8 \
