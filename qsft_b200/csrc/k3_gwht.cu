@@ -9,6 +9,8 @@
 
 #include <stdlib.h>
 
+#include "k3_shared.cuh"
+
 namespace {
 
 constexpr int K3_THREADS = 256;
@@ -183,23 +185,6 @@ k3_pass_kernel(float2* __restrict__ x, long long B, int q, int r, long long qa, 
     }
 }
 
-// Peer copies of the output (fused transform + all-gather): the final store of the last pass also writes the element to
-// the same offset of up to 7 peer buffers (P2P stores over NVLink into the peers' symmetric U buffers).
-struct K3Peers {
-    float2* p[7];
-    int n;
-};
-
-__device__ __forceinline__ void k3_store(float2* dst, float2 v, const float2* xroot, const K3Peers& peers) {
-    *dst = v;
-    if (peers.n > 0) {
-        const long long off = dst - xroot;
-#pragma unroll
-        for (int r = 0; r < 7; ++r)
-            if (r < peers.n) peers.p[r][off] = v;
-    }
-}
-
 // ---- q = 4 fast pass: radix-16 steps in registers ---------------------------------------------------------
 // Tile = 4096 complex elements, 256 threads, 16 elements per thread and step.  The r <= 6 levels of the pass sit at
 // base-4 digit positions [p0, p0 + r) of the tile index e; they are processed two at a time (radix-16 butterfly in
@@ -320,41 +305,6 @@ k3_q4_fast_kernel(float2* __restrict__ x, long long B, int r, int p0, long long 
 // (lag = 0: C(k) S(k) back to back) the strided tiles of a block become resident while its contiguous tiles still run and
 // about half of the resident CTAs only spin.  Every dependency of a ticket has a LOWER ticket, and lower tickets are
 // held by CTAs that are already resident or finished -> no deadlock for any lag.
-struct K3Ticket {
-    long long blk;
-    int t;          // tile inside its pass
-    bool strided;
-};
-
-__host__ __device__ inline K3Ticket k3_ticket_decode(unsigned int ticket, long long nblocks, int tiles1, int tiles2, int lag) {
-    K3Ticket o;
-    const long long L = lag < nblocks ? (lag < 0 ? 0 : lag) : nblocks;
-    const long long head = L * tiles1;                       // C(0) .. C(L-1)
-    if ((long long)ticket < head) {
-        o.blk = ticket / (unsigned int)tiles1;
-        o.t = (int)(ticket - (unsigned int)(o.blk * tiles1));
-        o.strided = false;
-        return o;
-    }
-    const long long u = (long long)ticket - head;
-    const long long per = (long long)tiles1 + tiles2;
-    const long long groups = nblocks - L;                    // group g: C(g + L) then S(g)
-    if (u < groups * per) {
-        const long long g = u / per;
-        const int v = (int)(u - g * per);
-        o.strided = v >= tiles1;
-        o.blk = o.strided ? g : g + L;
-        o.t = o.strided ? v - tiles1 : v;
-        return o;
-    }
-    const long long w = u - groups * per;                    // tail: S(nb - L) .. S(nb - 1)
-    const long long g = w / tiles2;
-    o.blk = groups + g;
-    o.t = (int)(w - g * tiles2);
-    o.strided = true;
-    return o;
-}
-
 // MINB = 4: 64 registers (one 8-byte spill) -> 4 CTAs per SM (default); MINB = 3: the 80 registers ptxas takes
 // unconstrained -> 3 CTAs per SM (QSFT_K3_CTAS=3, kept for the A/B measurement)
 template <int MINB>
@@ -493,10 +443,7 @@ __global__ void k3_bcast_copy_kernel(const float2* __restrict__ x, long long n, 
 // How many blocks the contiguous pass runs ahead of the strided pass (see k3_q4_twopass_kernel): enough tickets between
 // a block's two passes to cover every co-resident CTA, but no more intermediate data than stays comfortably in L2.
 // QSFT_K3_LAG overrides (0 = the plain block-by-block order).
-static int k3_twopass_ctas() {                                // CTAs per SM the two-pass kernel is compiled for
-    const char* e = getenv("QSFT_K3_CTAS");
-    return (e && atoi(e) == 3) ? 3 : 4;
-}
+static int k3_twopass_ctas() { return 4; }                    // CTAs per SM the two-pass kernel is compiled for
 
 static int k3_twopass_lag(long long B, int tiles1, int tiles2) {
     if (const char* e = getenv("QSFT_K3_LAG")) {
@@ -508,9 +455,7 @@ static int k3_twopass_lag(long long B, int tiles1, int tiles2) {
     int& resident = resident_by_minb[minb];
     if (resident == 0) {
         int per_sm = 0;
-        const cudaError_t e = (minb == 3)
-            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_twopass_kernel<3>, 256, 0)
-            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_twopass_kernel<4>, 256, 0);
+        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_twopass_kernel<4>, 256, 0);
         if (e != cudaSuccess || per_sm < 1) {
             (void)cudaGetLastError();
             per_sm = minb;
@@ -535,6 +480,17 @@ static int gwht_impl(float* x, int64_t batch, int q, int b, const K3Peers& peers
     for (int i = 0; i < b; ++i) Bd *= q;
     QSFT_CHECK_ARG(Bd <= 4e12, "q^b too large");
     const long long B = ipow64(q, b);
+    // q = 4, 4^6 .. 4^10 points: the TMA pipeline of k3_gwht_tma.cu (QSFT_K3_IMPL=1 keeps the register-staged kernels below
+    // as a cross-check)
+    if (q == 4 && b >= 6 && b <= 10) {
+        const char* impl = getenv("QSFT_K3_IMPL");
+        if (!(impl && atoi(impl) == 1)) {
+            float* pp[7];
+            for (int r = 0; r < 7; ++r) pp[r] = r < peers.n ? reinterpret_cast<float*>(peers.p[r]) : nullptr;
+            const int rc = qsft_k3_q4_tma(x, batch, b, pp, peers.n, (cudaStream_t)stream);
+            if (rc != QSFT_EUNSUPPORTED) return rc;
+        }
+    }
     // levels per pass: as many as fit in a tile, spread evenly over the passes
     int cap = 0;
     {
@@ -566,11 +522,7 @@ static int gwht_impl(float* x, int64_t batch, int q, int b, const K3Peers& peers
         QSFT_CUDA(cudaMemsetAsync(done, 0, (size_t)(batch + 1) * sizeof(unsigned int), st));
         const int t1 = (int)plans[0].tiles_per_block, t2 = (int)plans[1].tiles_per_block;
         const int lag = k3_twopass_lag(B, t1, t2);
-        if (k3_twopass_ctas() == 3)
-            k3_q4_twopass_kernel<3><<<(unsigned)(batch * (t1 + t2)), 256, 0, st>>>(xx, B, plans[0].r, plans[1].r, plans[1].qa,
-                                                                                 plans[1].lgW, t1, t2, done, (long long)batch, lag, inv, peers);
-        else
-            k3_q4_twopass_kernel<4><<<(unsigned)(batch * (t1 + t2)), 256, 0, st>>>(xx, B, plans[0].r, plans[1].r, plans[1].qa,
+        k3_q4_twopass_kernel<4><<<(unsigned)(batch * (t1 + t2)), 256, 0, st>>>(xx, B, plans[0].r, plans[1].r, plans[1].qa,
                                                                                  plans[1].lgW, t1, t2, done, (long long)batch, lag, inv, peers);
         QSFT_LAUNCHED();
         QSFT_CUDA(cudaFreeAsync(done, st));

@@ -9,332 +9,9 @@
 
 #include <stdlib.h>
 
+#include "k4_shared.cuh"
+
 namespace {
-
-constexpr int K4_THREADS = 128;
-constexpr int RS_MAX_2T = 32;
-constexpr double kTwoPi = 6.283185307179586476925286766559;
-
-struct PeelDev {
-    int q, n, b, C, P, P_src, R, channel, source, rs_t, rs_s, ld;
-    unsigned int qmagic;      // ceil(2^32 / q): x mod q = x - mulhi(x, qmagic) * q for x < 2^32 / q
-    long long B;
-    double thresh;            // cutoff * P
-    double invP;              // 1 / P
-    const int8_t* MT;         // (C, b, ld)   rows = columns of M, zero padded
-    const int8_t* D;          // (C, P, ld)
-    const int32_t* rs_exp;
-    const int32_t* rs_log;
-    int rs_order;             // q^s
-    int fastdet;              // opt-in (QSFT_K4_FASTDET=1): q = 2 / 4 symbols by quadrant comparison instead of atan2f
-};
-
-__device__ __forceinline__ int dp4a_u(uint32_t a, uint32_t b, int c) {
-#ifdef QSFT_EMU   // CPU execution of this kernel source by tests/emu (test infrastructure; never defined in the product build)
-    for (int i = 0; i < 4; ++i) c += (int)((a >> (8 * i)) & 255u) * (int)((b >> (8 * i)) & 255u);
-    return c;
-#else
-    int d;
-    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-#endif
-}
-
-// <row, k> (not reduced; < 128 * 127^2 < 2^32 / q); `row` has ld bytes (ld % 16 == 0), kw holds the digits of k four per word (zero padded)
-template <int NW>
-__device__ __forceinline__ int dot_raw(const int8_t* row, int ld, const uint32_t (&kw)[NW]) {
-    const uint4* r4 = reinterpret_cast<const uint4*>(row);
-    const int nv = ld >> 4;
-    int acc = 0;
-#pragma unroll
-    for (int w = 0; w < NW / 4; ++w) {
-        if (w >= nv) break;
-        uint4 v = __ldg(r4 + w);
-        acc = dp4a_u(v.x, kw[4 * w + 0], acc);
-        acc = dp4a_u(v.y, kw[4 * w + 1], acc);
-        acc = dp4a_u(v.z, kw[4 * w + 2], acc);
-        acc = dp4a_u(v.w, kw[4 * w + 3], acc);
-    }
-    return acc;
-}
-
-__device__ __forceinline__ int fast_mod(int x, int q, unsigned int qmagic) {   // 0 <= x < 2^32 / q
-    return x - (int)(__umulhi((unsigned int)x, qmagic) * (unsigned int)q);
-}
-
-// bin hash j = dec(M_c^T k mod q), b digits MSB first (qsft.py:178, :227)
-template <int NW>
-__device__ __forceinline__ long long hash_bin(const PeelDev& d, int c, const uint32_t (&kw)[NW]) {
-    long long j = 0;
-    const int8_t* mt = d.MT + (size_t)c * d.b * d.ld;
-    for (int i = 0; i < d.b; ++i) j = j * d.q + fast_mod(dot_raw<NW>(mt + (size_t)i * d.ld, d.ld, kw), d.q, d.qmagic);
-    return j;
-}
-
-// weight q^(b-1-i) of hash digit i (0 for i >= b): loop invariant of the per-bin / per-find work, computed once per thread
-__device__ __forceinline__ long long hash_weight(const PeelDev& d, int i) {
-    if (i >= d.b) return 0;
-    long long wgt = 1;
-    for (int u = i + 1; u < d.b; ++u) wgt *= d.q;
-    return wgt;
-}
-
-// the same hash computed by a whole warp: one hash digit per lane (b <= 32), all lanes get the result;
-// wgt = hash_weight(d, lane)
-template <int NW>
-__device__ __forceinline__ long long hash_bin_warp(const PeelDev& d, int c, const uint32_t (&kw)[NW], int lane, long long wgt) {
-    long long part = 0;
-    if (lane < d.b) part = wgt * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + lane) * d.ld, d.ld, kw), d.q, d.qmagic);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    return part;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// GF(p^s) helpers for the coded path; elements are ints whose base-p digits are polynomial coefficients.
-// ---------------------------------------------------------------------------------------------------------
-struct GF {
-    int p, s, order;
-    const int32_t* ex;
-    const int32_t* lg;
-    __device__ __forceinline__ int add(int a, int b) const {
-        int out = 0, w = 1;
-        for (int i = 0; i < s; ++i) {
-            int da = a % p, db = b % p;
-            a /= p; b /= p;
-            int v = da + db;
-            v = v >= p ? v - p : v;
-            out += v * w;
-            w *= p;
-        }
-        return out;
-    }
-    __device__ __forceinline__ int neg(int a) const {
-        int out = 0, w = 1;
-        for (int i = 0; i < s; ++i) {
-            int da = a % p;
-            a /= p;
-            out += (da ? p - da : 0) * w;
-            w *= p;
-        }
-        return out;
-    }
-    __device__ __forceinline__ int sub(int a, int b) const { return add(a, neg(b)); }
-    __device__ __forceinline__ int mul(int a, int b) const {
-        if (a == 0 || b == 0) return 0;
-        return __ldg(ex + __ldg(lg + a) + __ldg(lg + b));
-    }
-    __device__ __forceinline__ int inv(int a) const { return __ldg(ex + (order - 1 - __ldg(lg + a)) % (order - 1)); }
-    __device__ __forceinline__ int alpha_pow(int e) const {
-        e %= (order - 1);
-        if (e < 0) e += order - 1;
-        return __ldg(ex + e);
-    }
-};
-
-// Syndrome decode: sym (2ts symbols of Z_q) -> k digits (n), returns false on decoder failure (k left all zero,
-// like galois returning the unchanged zero codeword with n_errors = -1).
-__device__ bool rs_decode(const PeelDev& d, const uint8_t* sym, uint8_t* kout) {
-    GF F{d.q, d.rs_s, d.rs_order, d.rs_exp, d.rs_log};
-    const int t = d.rs_t, s = d.rs_s, n = d.n, nt = d.rs_order - 1;
-    const int T2 = 2 * t;
-    int S[RS_MAX_2T];
-    bool any = false;
-    for (int i = 0; i < T2; ++i) {
-        int v = 0;
-        for (int u = 0; u < s; ++u) v = v * d.q + sym[s * i + u];
-        S[i] = v;
-        any |= (v != 0);
-    }
-    for (int i = 0; i < n; ++i) kout[i] = 0;
-    if (!any) return true;
-    int Lam[RS_MAX_2T + 2], Bp[RS_MAX_2T + 2], Nw[RS_MAX_2T + 2];
-    for (int i = 0; i < T2 + 2; ++i) Lam[i] = Bp[i] = 0;
-    Lam[0] = Bp[0] = 1;
-    int L = 0, m = 1, bb = 1, lenL = 1, lenB = 1;
-    for (int r = 0; r < T2; ++r) {
-        int dd = S[r];
-        for (int i = 1; i <= L; ++i)
-            if (i < lenL) dd = F.add(dd, F.mul(Lam[i], S[r - i]));
-        if (dd == 0) {
-            ++m;
-            continue;
-        }
-        int coef = F.mul(dd, F.inv(bb));
-        int lenN = max(lenL, lenB + m);
-        if (lenN > T2 + 2) return false;
-        for (int i = 0; i < lenN; ++i) Nw[i] = i < lenL ? Lam[i] : 0;
-        for (int i = 0; i < lenB; ++i) Nw[i + m] = F.sub(Nw[i + m], F.mul(coef, Bp[i]));
-        if (2 * L <= r) {
-            for (int i = 0; i < lenL; ++i) Bp[i] = Lam[i];
-            lenB = lenL;
-            bb = dd;
-            L = r + 1 - L;
-            m = 1;
-        } else {
-            ++m;
-        }
-        for (int i = 0; i < lenN; ++i) Lam[i] = Nw[i];
-        lenL = lenN;
-    }
-    while (lenL > 1 && Lam[lenL - 1] == 0) --lenL;
-    const int deg = lenL - 1;
-    if (deg != L || deg > t || deg == 0) return false;
-    // Omega = S(x) Lambda(x) mod x^2t
-    int Om[RS_MAX_2T];
-    for (int a = 0; a < T2; ++a) {
-        int v = 0;
-        for (int i = 0; i <= deg && i <= a; ++i) v = F.add(v, F.mul(Lam[i], S[a - i]));
-        Om[a] = v;
-    }
-    int found = 0;
-    bool ok = true;
-    for (int i = 0; i < n && ok; ++i) {
-        const int e = n - 1 - i;              // locator X = alpha^e for retained coordinate i
-        const int xinv = F.alpha_pow(-e);
-        int acc = 0, pw = 1;
-        for (int c = 0; c <= deg; ++c) {
-            acc = F.add(acc, F.mul(Lam[c], pw));
-            pw = F.mul(pw, xinv);
-        }
-        if (acc != 0) continue;
-        ++found;
-        int num = 0;
-        pw = 1;
-        for (int c = 0; c < T2; ++c) {
-            num = F.add(num, F.mul(Om[c], pw));
-            pw = F.mul(pw, xinv);
-        }
-        int den = 0;
-        pw = 1;
-        for (int c = 1; c <= deg; ++c) {
-            int term = 0;
-            for (int u = 0; u < c % d.q; ++u) term = F.add(term, Lam[c]);
-            den = F.add(den, F.mul(term, pw));
-            pw = F.mul(pw, xinv);
-        }
-        if (den == 0) {
-            ok = false;
-            break;
-        }
-        const int val = F.neg(F.mul(num, F.inv(den)));
-        if (val >= d.q) ok = false;            // error value must be in the prime subfield
-        kout[i] = (uint8_t)val;
-    }
-    (void)nt;
-    if (!ok || found != deg) {
-        for (int i = 0; i < n; ++i) kout[i] = 0;
-        return false;
-    }
-    return true;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// singleton detection: symbol i (1 <= i < P_src) of one column; element p of the column is col[p * stride].
-//   channel 0: noiseless angles (reconstruct.py:12-31), channel 1: nso1 soft decision (reconstruct.py:100-113),
-//   channel 2: nso2 hard decision (reconstruct.py:116-129 + angle_q, utils.py:104-105).
-// ---------------------------------------------------------------------------------------------------------
-// angle_q: (((angle mod 2 pi) // (pi / q)) + 1) // 2 mod q in fp64 like NumPy (np.angle of a complex128 holding the
-// fp32 value; the float floor divisions are exact small integers)
-__device__ __forceinline__ int angle_q_dev(float2 v, int q) {
-    double a = atan2((double)v.y, (double)v.x);
-    if (a < 0.0) a += kTwoPi;                      // numpy: angle % (2 pi)
-    if (a >= kTwoPi) a -= kTwoPi;
-    const long long sector = (long long)floor(a / (3.14159265358979323846 / (double)q));
-    return (int)(((sector + 1) >> 1) % q);
-}
-
-// Index of the q-th root of unity nearest to the direction of (re, im) for q = 2 / 4 by comparisons (opt-in fast path):
-// the quadrant boundaries are the diagonals (q = 4) / the imaginary axis (q = 2); a value within ~0.03 rad of a boundary
-// (or a vanishing one) returns -1 and takes the exact path, so the decision always equals the exact one.
-__device__ __forceinline__ int quadrant_symbol(int q, float re, float im) {
-    const float ax = fabsf(re), ay = fabsf(im);
-    if (!(ax + ay > 1e-30f)) return -1;
-    if (q == 4) {
-        if (!(fabsf(ax - ay) > 0.03f * (ax + ay))) return -1;
-        return ax > ay ? (re > 0.f ? 0 : 2) : (im > 0.f ? 1 : 3);
-    }
-    if (!(ax > 0.03f * (ax + ay))) return -1;
-    return re > 0.f ? 0 : 1;
-}
-
-__device__ __forceinline__ int detect_symbol(const PeelDev& d, const float2* __restrict__ col, size_t stride, int i) {
-    const double qd = (double)d.q;
-    const bool quad = d.fastdet && (d.q == 4 || d.q == 2);
-    int symv;
-    if (d.channel == 0) {
-        const float2 v0 = col[0];
-        const float2 v = col[(size_t)i * stride];
-        symv = -1;
-        // round(q (angle v - angle v0) / 2 pi) mod q = root nearest to the direction of v conj(v0)
-        if (quad) symv = quadrant_symbol(d.q, fmaf(v.x, v0.x, v.y * v0.y), fmaf(v.y, v0.x, -(v.x * v0.y)));
-        // fast path in fp32; anything within 0.01 of a rounding boundary is redone in fp64 so the decision
-        // always equals the fp64 one (np.angle / np.round in the reference)
-        if (symv < 0 && fabsf(v0.x) + fabsf(v0.y) > 1e-30f && fabsf(v.x) + fabsf(v.y) > 1e-30f) {
-            const float u = (float)d.q * (atan2f(v.y, v.x) - atan2f(v0.y, v0.x)) * 0.15915494309189535f;
-            const float m = rintf(u);
-            if (fabsf(u - m) < 0.49f) {
-                int mi = (int)m;                    // |u| < q  =>  m in [-q, q]
-                mi = mi < 0 ? mi + d.q : mi;
-                symv = mi >= d.q ? mi - d.q : mi;
-            }
-        }
-        if (symv < 0) {
-            const double a0 = atan2((double)v0.y, (double)v0.x);
-            const double a = atan2((double)v.y, (double)v.x);
-            const long long r = (long long)rint(qd * (a - a0) / kTwoPi);    // half-to-even like np.round
-            const int m = (int)(r % d.q);
-            symv = m < 0 ? m + d.q : m;
-        }
-    } else if (d.channel == 1) {
-        double ar = 0.0, ai = 0.0;
-        for (int r = 0; r < d.R; ++r) {
-            const float2 z = col[(size_t)(r * d.P_src) * stride];
-            const float2 v = col[(size_t)(r * d.P_src + i) * stride];
-            ar += (double)z.x * v.x + (double)z.y * v.y;                     // z * conj(v)
-            ai += (double)z.y * v.x - (double)z.x * v.y;
-        }
-        // np.mean divides by R > 0: the angle does not depend on it
-        symv = -1;
-        const float arf = (float)ar, aif = (float)ai;
-        if (quad) symv = quadrant_symbol(d.q, arf, aif);
-        if (symv < 0 && fabsf(arf) + fabsf(aif) > 1e-30f) {
-            float thf = atan2f(aif, arf);
-            if (thf < 0.f) thf += 6.283185307179586f;
-            const float u = thf * (float)d.q * 0.15915494309189535f;        // in [0, q]
-            const float m = rintf(u);
-            if (fabsf(u - m) < 0.49f) symv = ((int)m >= d.q) ? (int)m - d.q : (int)m;   // nearest of the q+1 roots, mod q
-        }
-        if (symv < 0) {
-            double th = atan2(ai, ar);
-            if (th < 0.0) th += kTwoPi;                                      // numpy: angle % (2 pi)
-            if (th >= kTwoPi) th -= kTwoPi;
-            const double step = kTwoPi / qd;
-            int best = 0;
-            double bd = fabs(0.0 - th);
-            for (int m = 1; m <= d.q; ++m) {                                 // argmin over q+1 roots, first minimum
-                const double dist = fabs(step * (double)m - th);
-                if (dist < bd) {
-                    bd = dist;
-                    best = m;
-                }
-            }
-            symv = best % d.q;
-        }
-    } else {
-        // nso2: every repeat votes with its quantised phase difference; the votes are averaged as numbers, np.round is
-        // half-to-even; the sum of R small integers and the division by R are exact / correctly rounded like np.mean
-        long long votes = 0;
-        for (int r = 0; r < d.R; ++r) {
-            const int a0 = angle_q_dev(col[(size_t)(r * d.P_src) * stride], d.q);
-            const int a = angle_q_dev(col[(size_t)(r * d.P_src + i) * stride], d.q);
-            int df = a0 - a;
-            votes += df < 0 ? df + d.q : df;
-        }
-        symv = (int)((long long)rint((double)votes / (double)d.R) % d.q);
-    }
-    return symv;
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // classification.  Phase 1: one THREAD per bin computes the energy (lanes over consecutive bins -> coalesced row
@@ -399,7 +76,7 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
         for (int i0 = 1; i0 <= nsym; i0 += 32) {
             const int i = i0 + lane;
             if (i <= nsym) {
-                const int symv = detect_symbol(d, col, (size_t)B, i);
+                const int symv = detect_symbol(d, StridedCol{col, (size_t)B, d.P_src}, i);
                 s_sym[warp][i - 1] = (uint8_t)symv;
             }
         }
@@ -458,195 +135,6 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
         }
         __syncwarp();
     }
-    if (lane == 0 && n_multi) atomicAdd(&counters[1], (unsigned long long)n_multi);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// classification, version 2 (opt-in: QSFT_K4_IMPL=2; written at the end of round 1 without GPU time -- NOT YET
-// MEASURED, the default stays version 1 above).  Same decisions and outputs as k4_classify_kernel.
-//   CTA = 256 consecutive bins of one group.  Phase 1 (thread = bin) streams the tile's columns through the energy sum
-//   AND into shared memory (every global byte is read once, coalesced); the CTA compacts its candidate bins; phase 2
-//   gives every candidate a group of 8 lanes (lanes over delay rows / symbols / hash digits: P = 41 -> 6 iterations at
-//   85 % lane utilisation instead of 2 at 64 %, 3-step group reductions, columns / D / M^T rows from shared memory).
-//   Shared layout: columns [P][257] float2 (odd stride: the 8 lanes of a group hit 8 different banks), D rows and M^T rows
-//   with stride ld + 16 bytes (conflict-free 16-byte loads), symbols [32 groups][4 NW].
-// Identity source decoding only (coded delays fall back to version 1).
-// ---------------------------------------------------------------------------------------------------------
-constexpr int K4V2_THREADS = 256;
-constexpr int K4V2_COLS = K4V2_THREADS + 1;     // padded column stride (float2 elements)
-constexpr int K4V2_G = 8;                       // lanes per candidate bin
-
-template <int NW>
-__device__ __forceinline__ int dot_raw_s(const int8_t* row, int ld, const uint32_t (&kw)[NW]) {   // row in shared memory
-    const uint4* r4 = reinterpret_cast<const uint4*>(row);
-    const int nv = ld >> 4;
-    int acc = 0;
-#pragma unroll
-    for (int w = 0; w < NW / 4; ++w) {
-        if (w >= nv) break;
-        const uint4 v = r4[w];
-        acc = dp4a_u(v.x, kw[4 * w + 0], acc);
-        acc = dp4a_u(v.y, kw[4 * w + 1], acc);
-        acc = dp4a_u(v.z, kw[4 * w + 2], acc);
-        acc = dp4a_u(v.w, kw[4 * w + 3], acc);
-    }
-    return acc;
-}
-
-static size_t k4v2_smem_bytes(const PeelDev& d, int nw) {
-    return (size_t)d.P * K4V2_COLS * sizeof(float2) + 16 +             // columns (+ alignment slack)
-           (size_t)(d.P + d.b) * (d.ld + 16) +                           // D rows, M^T rows
-           (size_t)(K4V2_THREADS / K4V2_G) * 4 * nw;                     // symbols
-}
-
-template <int NW>
-__global__ void __launch_bounds__(K4V2_THREADS, 2)
-k4_classify_v2_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, long long j_end,
-                      long long* __restrict__ find_cj, int8_t* __restrict__ find_k, float2* __restrict__ find_rho,
-                      int32_t* __restrict__ find_round, int32_t* __restrict__ find_id, long long max_finds, int round,
-                      unsigned long long* __restrict__ counters) {
-    extern __shared__ __align__(16) unsigned char k4v2_smem[];
-    __shared__ double2 s_tw[QSFT_MAX_Q + 1];
-    __shared__ double s_energy[K4V2_THREADS];
-    __shared__ int s_cand[K4V2_THREADS];
-    __shared__ int s_wcnt[K4V2_THREADS / 32];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int c = blockIdx.y;
-    const long long B = d.B;
-    const int rs = d.ld + 16;                                            // padded row stride of the D / M^T copies
-    float2* s_col = reinterpret_cast<float2*>(k4v2_smem);
-    size_t off = ((size_t)d.P * K4V2_COLS * sizeof(float2) + 15) & ~(size_t)15;
-    int8_t* s_D = reinterpret_cast<int8_t*>(k4v2_smem + off);
-    int8_t* s_MT = s_D + (size_t)d.P * rs;
-    uint8_t* s_sym = reinterpret_cast<uint8_t*>(s_MT + (size_t)d.b * rs);
-
-    // phase 0: tables
-    if (tid < d.q) {
-        double sn, cs;
-        sincospi(2.0 * (double)tid / (double)d.q, &sn, &cs);
-        s_tw[tid] = make_double2(cs, sn);
-    }
-    {
-        const int vpr = d.ld >> 4;                                       // 16-byte vectors per row
-        const uint4* gD = reinterpret_cast<const uint4*>(d.D + (size_t)c * d.P * d.ld);
-        for (int e = tid; e < d.P * vpr; e += K4V2_THREADS) {
-            const int r = e / vpr, v = e - r * vpr;
-            *reinterpret_cast<uint4*>(s_D + (size_t)r * rs + 16 * v) = __ldg(gD + e);
-        }
-        const uint4* gM = reinterpret_cast<const uint4*>(d.MT + (size_t)c * d.b * d.ld);
-        for (int e = tid; e < d.b * vpr; e += K4V2_THREADS) {
-            const int r = e / vpr, v = e - r * vpr;
-            *reinterpret_cast<uint4*>(s_MT + (size_t)r * rs + 16 * v) = __ldg(gM + e);
-        }
-    }
-
-    // phase 1: energy (same summation order as version 1) + stash of the columns
-    const long long j0 = j_begin + (long long)blockIdx.x * K4V2_THREADS;
-    const long long j = j0 + tid;
-    const float2* Uc = U + (size_t)c * d.P * B;
-    double energy = 0.0;
-    if (j < j_end) {
-        const float2* gcol = Uc + j;
-#pragma unroll 8
-        for (int p = 0; p < d.P; ++p) {
-            const float2 v = gcol[(size_t)p * B];
-            s_col[(size_t)p * K4V2_COLS + tid] = v;
-            energy += (double)v.x * v.x + (double)v.y * v.y;
-        }
-        if (!(energy > d.thresh)) find_id[(size_t)c * B + j] = -1;
-    }
-    s_energy[tid] = energy;
-    const bool cand = (j < j_end) && (energy > d.thresh);
-    const unsigned cbal = __ballot_sync(0xffffffffu, cand);
-    if (lane == 0) s_wcnt[warp] = __popc(cbal);
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < K4V2_THREADS / 32; ++w) {
-        const int n = s_wcnt[w];
-        base += (w < warp) ? n : 0;
-        total += n;
-    }
-    if (cand) s_cand[base + __popc(cbal & ((1u << lane) - 1u))] = tid;
-    __syncthreads();
-    if (total == 0) return;
-
-    // phase 2: one 8-lane group per candidate bin
-    const int grp = tid / K4V2_G, gl = tid % K4V2_G;
-    const int nsym = d.P_src - 1;
-    uint8_t* sym = s_sym + (size_t)grp * (4 * NW);
-    const int iters = (total + K4V2_THREADS / K4V2_G - 1) / (K4V2_THREADS / K4V2_G);
-    unsigned n_multi = 0;
-    long long wgt[32 / K4V2_G];                                          // hash digit weights of this lane (b <= 32)
-#pragma unroll
-    for (int u = 0; u < 32 / K4V2_G; ++u) wgt[u] = hash_weight(d, gl + u * K4V2_G);
-    for (int it = 0; it < iters; ++it) {                                 // uniform trip count: the shuffles below use full masks
-        const int ci = it * (K4V2_THREADS / K4V2_G) + grp;
-        const bool valid = ci < total;
-        const int my = s_cand[valid ? ci : 0];
-        const long long jb = j0 + my;
-        const float2* col = s_col + my;                                  // element p of the column = col[p * K4V2_COLS]
-
-        for (int i = 1 + gl; i <= nsym; i += K4V2_G) sym[i - 1] = (uint8_t)detect_symbol(d, col, (size_t)K4V2_COLS, i);
-        for (int i = nsym + gl; i < 4 * NW; i += K4V2_G) sym[i] = 0;     // identity source: k = the n = P_src - 1 symbols
-        __syncwarp();
-        uint32_t kw[NW];
-#pragma unroll
-        for (int w = 0; w < NW; ++w) kw[w] = reinterpret_cast<const uint32_t*>(sym)[w];
-
-        double rr = 0.0, ri = 0.0;
-        for (int p = gl; p < d.P; p += K4V2_G) {
-            const int t = fast_mod(dot_raw_s<NW>(s_D + (size_t)p * rs, d.ld, kw), d.q, d.qmagic);
-            const double cs = s_tw[t].x, sn = s_tw[t].y;
-            const float2 v = col[(size_t)p * K4V2_COLS];
-            rr += cs * v.x + sn * v.y;
-            ri += cs * v.y - sn * v.x;
-        }
-        long long part = 0;
-#pragma unroll
-        for (int u = 0; u < 32 / K4V2_G; ++u) {
-            const int i = gl + u * K4V2_G;
-            if (i < d.b) part += wgt[u] * fast_mod(dot_raw_s<NW>(s_MT + (size_t)i * rs, d.ld, kw), d.q, d.qmagic);
-        }
-#pragma unroll
-        for (int o = K4V2_G / 2; o > 0; o >>= 1) {                       // xor partners stay inside the aligned 8-lane group
-            rr += __shfl_xor_sync(0xffffffffu, rr, o);
-            ri += __shfl_xor_sync(0xffffffffu, ri, o);
-            part += __shfl_xor_sync(0xffffffffu, part, o);
-        }
-        rr *= d.invP;
-        ri *= d.invP;
-        const double res = s_energy[my] - (double)d.P * (rr * rr + ri * ri);
-        const bool single = valid && (part == jb) && !(res > d.thresh);
-        const bool lead = gl == 0;
-
-        const unsigned sb = __ballot_sync(0xffffffffu, lead && single);
-        unsigned long long fbase = 0;
-        if (lane == 0 && sb) fbase = atomicAdd(&counters[0], (unsigned long long)__popc(sb));
-        fbase = __shfl_sync(0xffffffffu, fbase, 0);
-        unsigned long long f = fbase + (unsigned long long)__popc(sb & ((1u << lane) - 1u));
-        f = __shfl_sync(0xffffffffu, f, lane & ~(K4V2_G - 1));           // the leader's slot for its whole group
-        if (single) {
-            if ((long long)f < max_finds) {
-                uint32_t* ko = reinterpret_cast<uint32_t*>(find_k + (size_t)f * d.ld);
-                for (int w = gl; w < d.ld / 4; w += K4V2_G) ko[w] = (w < NW) ? reinterpret_cast<const uint32_t*>(sym)[w] : 0u;
-                if (lead) {
-                    find_cj[f] = (long long)c * B + jb;
-                    find_rho[f] = make_float2((float)rr, (float)ri);
-                    if (find_round) find_round[f] = round;
-                    find_id[(size_t)c * B + jb] = (int32_t)f;
-                }
-            } else if (lead) {
-                find_id[(size_t)c * B + jb] = -1;
-            }
-        } else if (valid && lead) {
-            find_id[(size_t)c * B + jb] = -1;
-            ++n_multi;
-        }
-        __syncwarp();                                                    // sym is rewritten in the next iteration
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n_multi += __shfl_xor_sync(0xffffffffu, n_multi, o);
     if (lane == 0 && n_multi) atomicAdd(&counters[1], (unsigned long long)n_multi);
 }
 
@@ -752,39 +240,7 @@ k4_reduce_kernel(PeelDev d, const long long* __restrict__ find_cj, const int8_t*
             }
         }
     }
-    // merge with an entry of an earlier round, if any
-    int32_t head = *reinterpret_cast<volatile int32_t*>(seen0 + j0);
-    // entries of this round may have been published by other SMs a moment ago: read the links through L2 (__ldcg)
-    for (int32_t e = head; e != 0; e = __ldcg(unext + (e - 1))) {
-        if ((int)(__ldcg(ukey + (e - 1)) >> 48) == round) continue;
-        const uint32_t* k2 = reinterpret_cast<const uint32_t*>(uk + (size_t)(e - 1) * d.ld);
-        bool same = true;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) same &= ((w < nw) ? k2[w] : 0u) == kw[w];
-        if (same) {
-            atomicAdd(usum + 2 * (size_t)(e - 1), sum.x);
-            atomicAdd(usum + 2 * (size_t)(e - 1) + 1, sum.y);
-            atomicAdd(ucnt + (e - 1), cnt);
-            return;
-        }
-    }
-    const unsigned long long u = atomicAdd(&counters[4], 1ull);
-    if ((long long)u >= max_uniq) return;
-    uint32_t* ko = reinterpret_cast<uint32_t*>(uk + (size_t)u * d.ld);
-    for (int w = 0; w < nw; ++w) ko[w] = (w < NW) ? kw[w] : 0u;
-    usum[2 * u] = sum.x;
-    usum[2 * u + 1] = sum.y;
-    ucnt[u] = cnt;
-    ukey[u] = ((long long)round << 48) | cj;
-    unext[u] = head;
-    __threadfence();
-    for (;;) {
-        const int32_t old = atomicCAS(seen0 + j0, head, (int32_t)(u + 1));
-        if (old == head) break;
-        head = old;                          // another k of this round was linked first: chain behind it
-        unext[u] = head;
-        __threadfence();
-    }
+    k4_uniq_commit<NW>(d, kw, sum, cnt, cj, j0, round, seen0, uk, usum, ucnt, ukey, unext, max_uniq, counters);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -800,7 +256,7 @@ k4_detect_kernel(PeelDev d, const float2* __restrict__ cols, long long N, int8_t
     if (c >= N) return;                                     // whole warps leave together
     const float2* col = cols + (size_t)c * d.P;             // element p of the column = col[p]
     const int nsym = d.P_src - 1;
-    for (int i = 1 + lane; i <= nsym; i += 32) s_sym[warp][i - 1] = (uint8_t)detect_symbol(d, col, 1, i);
+    for (int i = 1 + lane; i <= nsym; i += 32) s_sym[warp][i - 1] = (uint8_t)detect_symbol(d, StridedCol{col, 1, d.P_src}, i);
     __syncwarp();
     int nout = nsym;
     const uint8_t* src = s_sym[warp];
@@ -918,8 +374,8 @@ int make_dev(const qsft_peel_desc* h, PeelDev* d) {
     d->qmagic = (unsigned int)(((1ull << 32) + h->q - 1) / h->q);
     d->MT = h->MT; d->D = h->D; d->rs_exp = h->rs_exp; d->rs_log = h->rs_log;
     d->rs_order = h->source ? (int)ipow64(h->q, h->rs_s) : 0;
-    const char* fd = getenv("QSFT_K4_FASTDET");          // opt-in, unmeasured: see quadrant_symbol
-    d->fastdet = (fd && atoi(fd) != 0) ? 1 : 0;
+    const char* fd = getenv("QSFT_K4_FASTDET");          // quadrant detection (see quadrant_symbol) unless disabled
+    d->fastdet = (fd && atoi(fd) == 0) ? 0 : 1;
     return QSFT_OK;
 }
 
@@ -943,16 +399,6 @@ int apply_nw(const PeelDev& d, float2* U, long long jb, long long je, const long
     return QSFT_OK;
 }
 
-struct UniqOut {
-    int32_t* seen0;       // (B) chain heads, zero initialised by the caller / qsft_peel
-    int8_t* uk;           // (max_uniq, ld)
-    float* usum;          // (max_uniq) complex64: sum of rho over all finds of the k
-    int32_t* ucnt;        // (max_uniq) number of finds
-    long long* ukey;      // (max_uniq) (round << 48) | (c * B + j) of the first find: reference's first-seen order
-    int32_t* unext;       // (max_uniq) workspace
-    long long max_uniq;
-};
-
 template <int NW>
 int reduce_nw(const PeelDev& d, const long long* cj, const int8_t* fk, const float2* rho, const int32_t* fid,
               long long f_begin, long long nf, long long id_limit, int round, const UniqOut& o,
@@ -972,33 +418,8 @@ int reduce_nw(const PeelDev& d, const long long* cj, const int8_t* fk, const flo
         return fn<32>(__VA_ARGS__);                        \
     } while (0)
 
-template <int NW>
-int classify_v2_nw(const PeelDev& d, const float2* U, long long jb, long long je, long long* cj, int8_t* fk, float2* rho,
-                   int32_t* frd, int32_t* fid, long long maxf, int round, unsigned long long* counters, cudaStream_t st) {
-    const size_t smem = k4v2_smem_bytes(d, NW);
-    static size_t configured = 0;                            // per template instance
-    if (smem > configured) {
-        QSFT_CUDA(cudaFuncSetAttribute(k4_classify_v2_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    dim3 grid((unsigned)((je - jb + K4V2_THREADS - 1) / K4V2_THREADS), (unsigned)d.C);
-    k4_classify_v2_kernel<NW><<<grid, K4V2_THREADS, smem, st>>>(d, U, jb, je, cj, fk, rho, frd, fid, maxf, round, counters);
-    QSFT_LAUNCHED();
-    return QSFT_OK;
-}
-
-// QSFT_K4_IMPL=2 selects the shared-memory / 8-lane-group classification when the problem fits it (identity source
-// decoding, tile <= 100 KB of shared memory so that two CTAs stay resident); read on every call.
-static bool k4_use_v2(const PeelDev& d) {
-    const char* e = getenv("QSFT_K4_IMPL");
-    if (!e || atoi(e) != 2 || d.source != 0) return false;
-    const int nw = d.ld / 4 <= 4 ? 4 : d.ld / 4 <= 8 ? 8 : d.ld / 4 <= 16 ? 16 : 32;
-    return k4v2_smem_bytes(d, nw) <= 100 * 1024;
-}
-
 int do_classify(const PeelDev& d, const float2* U, long long jb, long long je, long long* cj, int8_t* fk, float2* rho,
                 int32_t* frd, int32_t* fid, long long maxf, int round, unsigned long long* counters, cudaStream_t st) {
-    if (k4_use_v2(d)) QSFT_NW_DISPATCH(classify_v2_nw, d, U, jb, je, cj, fk, rho, frd, fid, maxf, round, counters, st);
     QSFT_NW_DISPATCH(classify_nw, d, U, jb, je, cj, fk, rho, frd, fid, maxf, round, counters, st);
 }
 
@@ -1073,6 +494,23 @@ extern "C" int qsft_peel(const qsft_peel_desc* h, float* U, int64_t* find_cj, in
         QSFT_CHECK_ARG(uq->seen0 && uq->uniq_k && uq->uniq_sum && uq->uniq_cnt && uq->uniq_key && uq->uniq_next && uq->max_uniq > 0,
                        "incomplete qsft_uniq");
         uo = UniqOut{uq->seen0, uq->uniq_k, uq->uniq_sum, uq->uniq_cnt, (long long*)uq->uniq_key, uq->uniq_next, uq->max_uniq};
+    }
+    // default: the whole loop on the device (k4_peel_loop.cu; U is left untouched).  QSFT_K4_IMPL=1 keeps the host-driven
+    // classify / reduce / apply rounds below as a cross-check (they modify U in place like the reference).
+    {
+        const char* impl = getenv("QSFT_K4_IMPL");
+        if (!(impl && atoi(impl) == 1) && d.C * d.R <= 16) {
+            const float* blocks[16];
+            for (int c = 0; c < d.C; ++c)
+                for (int r = 0; r < d.R; ++r) blocks[c * d.R + r] = U + 2 * ((size_t)c * d.P + (size_t)r * d.P_src) * (size_t)d.B;
+            int64_t nu = 0;
+            const int rc = qsft_peel_loop(d, blocks, d.B, find_cj, find_k, find_rho, find_round, find_id, max_finds, counters,
+                                          uq ? &uo : nullptr, n_finds_out, &nu, n_rounds_out, st);
+            if (rc != QSFT_EUNSUPPORTED) {
+                if (rc == QSFT_OK && n_uniq_out) *n_uniq_out = nu;
+                return rc;
+            }
+        }
     }
     // `num_peeling < q ** n` (qsft.py:151) can only bind when q^n is tiny: at most C*B balls are peeled per round
     const double peeling_max = pow((double)d.q, (double)d.n);
@@ -1156,6 +594,7 @@ extern "C" int qsft_singleton_detect(const float* cols, int64_t N, int q, int n,
     if (channel == 0) QSFT_CHECK_ARG(P == P_src, "identity channel decoding needs num_repeat == 1");
     PeelDev d{};
     d.q = q; d.n = source ? n : P_src - 1; d.P = P; d.P_src = P_src; d.R = P / P_src; d.channel = channel; d.source = source;
+    d.fastdet = 1;
     if (const char* fd = getenv("QSFT_K4_FASTDET")) d.fastdet = atoi(fd) != 0 ? 1 : 0;
     if (source == 1) {
         QSFT_CHECK_ARG(n >= 1 && n <= QSFT_MAX_N, "n=%d out of range", n);

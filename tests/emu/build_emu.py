@@ -22,7 +22,12 @@ def device_part(which="k4"):
         src = open(os.path.join(ROOT, "qsft_b200", "csrc", "k4_peel.cu")).read()
         start = src.index('#include "common.cuh"') + len('#include "common.cuh"')
         end = src.index("int make_dev(")                  # host code (with <<< >>> launches) starts here
-        return _rewrite(src[start:end]) + "\n}  // namespace (closed by build_emu.py)\n"
+        text = _rewrite(src[start:end]) + "\n}  // namespace (closed by build_emu.py)\n"
+        # the persistent on-device round loop (plain-copy variant; the TMA variant is sm_100a only)
+        src = open(os.path.join(ROOT, "qsft_b200", "csrc", "k4_peel_loop.cu")).read()
+        start = src.index('#include "common.cuh"') + len('#include "common.cuh"')
+        end = src.index("}  // namespace (device part; the CPU emulation cuts here)")
+        return text + _rewrite(src[start:end]) + "\n}  // namespace (closed by build_emu.py)\n"
     if which == "k1":
         src = open(os.path.join(ROOT, "qsft_b200", "csrc", "k1_lattice.cu")).read()
         start = src.index('#include "common.cuh"') + len('#include "common.cuh"')
@@ -53,12 +58,14 @@ def build(force=False, which="k4"):
     cu = {"k4": "k4_peel.cu", "k3": "k3_gwht.cu", "k1": "k1_lattice.cu", "k2": "k2_eval_simt.cu", "k2l": "k2_eval_lattice.cu"}[which]
     text = device_part(which)
     srcs = [os.path.join(HERE, f"{which}_emu.cpp"), os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "qsft_b200", "csrc", cu)]
+    if which == "k4":
+        srcs += [os.path.join(ROOT, "qsft_b200", "csrc", f) for f in ("k4_peel_loop.cu", "k4_shared.cuh")]
     fresh = os.path.exists(lib) and os.path.exists(inc) and open(inc).read() == text and \
         all(os.path.getmtime(lib) >= os.path.getmtime(p) for p in srcs)
     if fresh and not force:
         return lib
     open(inc, "w").write(text)
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-w", "-I/usr/local/cuda/include",
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-w", "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "qsft_b200", "csrc"),
            os.path.join(HERE, f"{which}_emu.cpp"), "-o", lib]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

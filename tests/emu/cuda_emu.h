@@ -174,6 +174,7 @@ inline float atomicAdd(float* p, float v) {
     memcpy(&f, &old, 4);
     return f;
 }
+inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicCAS(int* p, int cmp, int val) {
     __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
     return cmp;

@@ -35,21 +35,45 @@ int nw_of(int ld) { return ld / 4 <= 4 ? 4 : ld / 4 <= 8 ? 8 : ld / 4 <= 16 ? 16
     }
 
 void classify(const PeelDev& d, const float2* U, long long jb, long long je, long long* cj, int8_t* fk, float2* rho,
-              int32_t* frd, int32_t* fid, long long maxf, int round, unsigned long long* counters, int impl) {
+              int32_t* frd, int32_t* fid, long long maxf, int round, unsigned long long* counters) {
     const int nw = nw_of(d.ld);
-    // same eligibility rule as k4_use_v2 in the product: identity source decoding, tile <= 100 KB of shared memory
-    if (impl == 2 && (d.source != 0 || k4v2_smem_bytes(d, nw) > 100 * 1024)) impl = 1;
-    if (impl == 2) {
-        dim3 grid((unsigned)((je - jb + K4V2_THREADS - 1) / K4V2_THREADS), (unsigned)d.C);
-        NW_SWITCH(nw, emu::launch(grid, dim3(K4V2_THREADS), [&]() {
-                      k4_classify_v2_kernel<NW>(d, U, jb, je, cj, fk, rho, frd, fid, maxf, round, counters);
-                  }));
-    } else {
-        dim3 grid((unsigned)((je - jb + K4_THREADS - 1) / K4_THREADS), (unsigned)d.C);
-        NW_SWITCH(nw, emu::launch(grid, dim3(K4_THREADS), [&]() {
-                      k4_classify_kernel<NW>(d, U, jb, je, cj, fk, rho, frd, fid, maxf, round, counters);
-                  }));
-    }
+    dim3 grid((unsigned)((je - jb + K4_THREADS - 1) / K4_THREADS), (unsigned)d.C);
+    NW_SWITCH(nw, emu::launch(grid, dim3(K4_THREADS), [&]() {
+                  k4_classify_kernel<NW>(d, U, jb, je, cj, fk, rho, frd, fid, maxf, round, counters);
+              }));
+}
+
+// The persistent loop kernel (k4_peel_loop.cu, plain-copy variant) as ONE block: mirrors the host side of qsft_peel_loop.
+int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, float2* rho, int32_t* frd, int32_t* fid,
+              long long maxf, const UniqOut& uo, unsigned long long* counters, int bw) {
+    if (d.C * d.R > KL_MAX_BLOCKS || d.P_src > 256) return -3;
+    KlArgs a{};
+    a.d = d;
+    a.ldU = d.B;
+    a.sbox = (d.P_src * 128 + 1023) & ~1023;
+    a.bw = bw;
+    const int fixed = 4 * 2 * QSFT_MAX_N + 32 * 4;
+    const int per_warp = ((2 * (bw >> 4) * d.R * a.sbox + fixed) + 1023) & ~1023;
+    a.wpc = (232 * 1024 - 4096) / per_warp;
+    if (a.wpc > KL_THREADS / 32) a.wpc = KL_THREADS / 32;
+    if (a.wpc < 1) return -3;
+    KlBlocks blk{};
+    for (int c = 0; c < d.C; ++c)
+        for (int r = 0; r < d.R; ++r) blk.p[c * d.R + r] = U + ((size_t)c * d.P + (size_t)r * d.P_src) * d.B;
+    std::vector<int32_t> head((size_t)d.C * d.B, 0), next((size_t)maxf * d.C, 0);
+    std::vector<unsigned long long> multi(16, 0);
+    unsigned int gbar = 0;
+    int dflag = 0;
+    emu::launch(dim3(1), dim3(256), [&]() { kl_dstruct_kernel(d, &dflag); });
+    a.find_cj = cj; a.find_k = fk; a.find_rho = rho; a.find_round = frd; a.find_id = fid; a.max_finds = maxf;
+    a.head = head.data(); a.next = next.data(); a.uo = uo; a.has_uniq = 1; a.counters = counters; a.multi = multi.data();
+    a.gbar = &gbar; a.dstruct = &dflag; a.max_rounds = 15;
+    a.peeling_max = pow((double)d.q, (double)d.n);
+    a.guard_can_bind = a.peeling_max <= 15.0 * (double)d.C * (double)d.B ? 1 : 0;
+    a.rel_floor = 1e-10f;
+    const int nw = nw_of(d.ld);
+    NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_THREADS), [&]() { k4_peel_loop_kernel<NW, false>(a, blk); }));
+    return 0;
 }
 
 }  // namespace
@@ -64,8 +88,9 @@ int emu_classify(int q, int n, int b, int C, int P, int P_src, int channel, int 
     PeelDev d;
     fill_dev(&d, q, n, b, C, P, P_src, channel, source, rs_t, rs_s, ld, cutoff, MT, D, rs_exp, rs_log);
     if (j_end < 0) j_end = d.B;
+    (void)impl;
     classify(d, reinterpret_cast<const float2*>(U), j_begin, j_end, find_cj, find_k, reinterpret_cast<float2*>(find_rho), find_round,
-             find_id, max_finds, round, counters, impl);
+             find_id, max_finds, round, counters);
     return 0;
 }
 
@@ -80,14 +105,27 @@ int emu_peel(int q, int n, int b, int C, int P, int P_src, int channel, int sour
     unsigned long long counters[8] = {0};
     memset(seen0, 0, (size_t)d.B * sizeof(int32_t));
     const int nw = nw_of(d.ld);
+    if (impl >= 2) {            // 2: the on-device loop with 32-bin warp tiles, 3: 16-bin tiles
+        UniqOut uo{seen0, uk, usum, ucnt, ukey, unext, max_uniq};
+        if (int rc = peel_loop(d, reinterpret_cast<const float2*>(U), find_cj, find_k, reinterpret_cast<float2*>(find_rho), find_round,
+                               find_id, max_finds, uo, counters, impl == 2 ? 32 : 16))
+            return rc;
+        if (counters[6]) return -1;
+        if ((long long)counters[4] > max_uniq) return -2;
+        *n_finds_out = (long long)counters[7];
+        *n_uniq_out = (long long)counters[4];
+        *n_rounds_out = (int)counters[5];
+        return 0;
+    }
     long long total = 0;
     int round = 0;
     bool cont = true;
-    while (cont && round < 15) {
+    const double peeling_max = pow((double)d.q, (double)d.n);      // qsft.py:151
+    while (cont && (double)counters[2] < peeling_max && round < 15) {
         ++round;
         counters[1] = 0;
         classify(d, reinterpret_cast<const float2*>(U), 0, d.B, find_cj, find_k, reinterpret_cast<float2*>(find_rho),
-                 find_round, find_id, max_finds, round, counters, impl);
+                 find_round, find_id, max_finds, round, counters);
         const long long now = (long long)counters[0], multis = (long long)counters[1];
         if (now > max_finds) return -1;
         const long long nf = now - total;
@@ -98,7 +136,7 @@ int emu_peel(int q, int n, int b, int C, int P, int P_src, int channel, int sour
                                                now, round, seen0, uk, usum, ucnt, ukey, unext, max_uniq, counters);
                       }));
         }
-        if (nf > 0 && cont) {
+        if (nf > 0 && (cont || peeling_max <= 15.0 * (double)d.C * (double)d.B)) {
             const int wpb = K4_THREADS / 32;
             NW_SWITCH(nw, emu::launch(dim3((unsigned)((nf + wpb - 1) / wpb)), dim3(K4_THREADS), [&]() {
                           k4_apply_kernel<NW>(d, reinterpret_cast<float2*>(U), 0, d.B, find_cj, find_k,

@@ -1,5 +1,5 @@
-"""CPU: the DEVICE source of the K4 kernels (qsft_b200/csrc/k4_peel.cu: classification v1 and the opt-in v2, reduce,
-apply, the stand-alone detectors) executed by the SIMT emulation in tests/emu (g++, one OS thread per CUDA thread) and
+"""CPU: the DEVICE source of the K4 kernels (qsft_b200/csrc/k4_peel.cu: classification, reduce, apply, the stand-alone
+detectors; k4_peel_loop.cu: the persistent on-device round loop as impl 2 / 3 = 32- / 16-bin warp tiles, one block) executed by the SIMT emulation in tests/emu (g++, one OS thread per CUDA thread) and
 compared with the fixtures of the unmodified reference.  This checks the kernels' LOGIC without a GPU -- indexing,
 reductions, decisions, the round loop; it says nothing about the memory model or speed, and it is test infrastructure:
 the product has no CPU path."""
@@ -109,7 +109,7 @@ def _problem_from_golden(g, p, nso_subtype="nso1"):
     return Problem(q, n, p["trb"], list(g["mdu_Ms"]), D, p["P_src"], channel, cutoff), U
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 @pytest.mark.parametrize("name", FULL_CASES + WIDE_FULL_CASES)
 def test_emulated_peel_from_reference_bins(emu, name, impl):
     """The kernels' round loop on the reference's own bins: same distinct coefficients in the same first-seen order."""
@@ -131,19 +131,6 @@ def test_emulated_peel_nso2(emu, name, impl):
     keys, vals, _, _ = prob.peel(emu, U, impl)
     assert keys == [tuple(int(v) for v in k) for k in g["res_keys"]]
     assert np.max(np.abs(vals - g["res_vals"])) <= 1e-5 * np.max(np.abs(g["res_vals"]))
-
-
-@pytest.mark.parametrize("name", ["cfg2r_q4_n14_b5_nso_noisy", "q5_n6_b3_identity_noisy", "q2_n100_b5_identity_wide",
-                                  "q3_n12_b4_lowweight_nso"])
-def test_emulated_classify_v2_equals_v1(emu, name):
-    g = load_golden(name)
-    p = case_params(g)
-    prob, U = _problem_from_golden(g, p)
-    v1, v2 = prob.classify(emu, U, 1), prob.classify(emu, U, 2)
-    assert v1["nf"] == v2["nf"] > 0 and v1["nm"] == v2["nm"]
-    assert np.array_equal(v1["cj"], v2["cj"]) and np.array_equal(v1["k"], v2["k"])
-    assert np.max(np.abs(v1["rho"] - v2["rho"])) <= 2e-6 * max(1.0, np.max(np.abs(v1["rho"])))
-    assert np.array_equal(v1["fid"] >= 0, v2["fid"] >= 0) and not (v2["fid"] == -7).any() and not (v1["fid"] == -7).any()
 
 
 def test_emulated_detectors(emu):
@@ -255,12 +242,13 @@ def test_emulated_peel_coded_source_vs_oracle(emu):
     U = np.ascontiguousarray(np.array([np.vstack(us) for us in Us]).astype(np.complex64))
     D = np.array([np.vstack(d) for d in Ds])
     prob = Problem(q, n, b, Ms, D, sig.get_source_parity(), 1, 1e-9, rs=ReedSolomon(n, t, q))
-    keys, vals, _, _ = prob.peel(emu, U, 1)
-    assert keys == list(want.keys()) and len(keys) >= 0.8 * len(signal_w)
+    for impl in (1, 2):
+        keys, vals, _, _ = prob.peel(emu, U.copy(), impl)
+        assert keys == list(want.keys()) and len(keys) >= 0.8 * len(signal_w)
     assert np.max(np.abs(vals - np.array(list(want.values())))) <= 1e-5
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1])
 def test_emulated_classify_bin_ranges(emu, impl):
     """Bin-sharded classification (multi-GPU peel): ragged ranges that do not align with the CTA tiles give the same finds
     and the same find table as one pass over all bins."""

@@ -134,6 +134,25 @@ def test_k3_gwht_multi_pass_vs_oracle(q, b, batch):
     assert np.max(np.abs(got - want)) <= 2e-6 * np.max(np.abs(x)) / np.sqrt(q ** b) * np.sqrt(b) + 1e-7
 
 
+@pytest.mark.parametrize("b,batch", [(6, 1), (6, 37), (7, 1), (7, 9), (8, 5), (9, 3), (10, 1), (10, 7)])
+def test_k3_tma_pipeline_bit_identical_to_register_staged_kernels(b, batch, monkeypatch):
+    """The TMA pipeline (k3_gwht_tma.cu, default for q = 4, 6 <= b <= 10) performs the same butterflies in the same order
+    as the register-staged kernels (QSFT_K3_IMPL=1): bit-identical output, also through the peer-store entry point."""
+    q = 4
+    B = q ** b
+    x = (torch.randn(batch, B, device=DEV) + 1j * torch.randn(batch, B, device=DEV)).to(torch.complex64)
+    got = ops.gwht_batch_(x.clone(), q, b)
+    peers = [torch.full((batch + 2, B), 7.0, dtype=torch.complex64, device=DEV) for _ in range(2)]
+    got_b = ops.gwht_batch_bcast_(x.clone(), q, b, [p[1:].data_ptr() for p in peers])
+    monkeypatch.setenv("QSFT_K3_IMPL", "1")
+    want = ops.gwht_batch_(x.clone(), q, b)
+    assert torch.equal(got, want)
+    assert torch.equal(got_b, want)
+    for p in peers:
+        assert torch.equal(p[1:1 + batch], want)
+        assert bool((p[0] == 7.0).all()) and bool((p[-1] == 7.0).all())
+
+
 def test_k3_linearity_and_delta_full_size():
     """Size-independent properties at BASELINE size 4^10: transform of a delta is a pure character / q^b;
     linearity."""

@@ -10,12 +10,7 @@ from conftest import NSO2_CASES, WIDE_FULL_CASES, case_params, load_golden, u128
 
 import os
 
-# Everything in this file exercises code written at the end of round 1, after the round's GPU budget was spent: none of it
-# has run on a GPU yet.  It is skipped by default so that the default `-m gpu` suite only contains validated tests;
-# `QSFT_TEST_UNVALIDATED=1 pytest tests/test_gpu_zz_detectors.py` (first step of tools/gpu_round.sh) runs it.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("QSFT_TEST_UNVALIDATED") != "1" and os.environ.get("QSFT_TEST_EXPERIMENTAL") != "1",
-                                 reason="first GPU run pending (set QSFT_TEST_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 if torch.cuda.is_available():
     import qsft_b200
@@ -252,31 +247,15 @@ experimental = pytest.mark.skipif(os.environ.get("QSFT_TEST_EXPERIMENTAL") != "1
                                   reason="opt-in kernels not yet validated on a GPU (set QSFT_TEST_EXPERIMENTAL=1)")
 
 
-def _classify_once(prob, U, impl, monkeypatch):
-    if impl == 2:
-        monkeypatch.setenv("QSFT_K4_IMPL", "2")
-    else:
-        monkeypatch.delenv("QSFT_K4_IMPL", raising=False)
-    prob.counters.zero_()
-    prob.find_id.fill_(-7)
-    prob.classify(U, 0, prob.B, 1)
-    torch.cuda.synchronize()
-    nf, nm = int(prob.counters[0]), int(prob.counters[1])
-    cj = prob.find_cj[:nf].cpu().numpy()
-    order = np.argsort(cj)
-    return {"nf": nf, "nm": nm, "cj": cj[order], "k": prob.find_k[:nf].cpu().numpy()[order],
-            "rho": prob.find_rho[:nf].cpu().numpy()[order], "fid": prob.find_id.cpu().numpy().copy(),
-            "round": prob.find_round[:nf].cpu().numpy()[order]}
-
-
-@experimental
 @pytest.mark.parametrize("q,n,b,S,R,chan,noise", [(4, 40, 10, 100_000, 1, "nso", 0.0), (4, 20, 7, 1000, 3, "nso", 3.16),
                                                   (4, 10, 4, 100, 1, "identity", 0.0), (3, 12, 5, 60, 2, "nso", 0.0),
                                                   (5, 6, 3, 25, 1, "identity", 0.02), (2, 100, 6, 30, 1, "nso", 0.0),
-                                                  (4, 40, 9, 30_000, 1, "nso2", 0.0)])
-def test_experimental_k4_classify_v2_equals_v1(q, n, b, S, R, chan, noise, monkeypatch):
-    """QSFT_K4_IMPL=2 (shared-memory tile, 8 lanes per candidate) makes the same decisions as the default kernel: same
-    singletons (bin, k), same multiton count, same find_id pattern, rho equal to fp32 rounding."""
+                                                  (4, 40, 9, 30_000, 1, "nso2", 0.0), (3, 7, 2, 12, 1, "identity", 0.0)])
+def test_k4_device_loop_equals_host_driven_rounds(q, n, b, S, R, chan, noise, monkeypatch):
+    """The persistent on-device round loop (k4_peel_loop.cu, default) against the host-driven classify / reduce / apply
+    rounds (QSFT_K4_IMPL=1, the round-1 path the reference fixtures pinned): same distinct k in the same first-seen
+    order, same number of rounds and finds, values equal to fp32 rounding; the device loop leaves U untouched.
+    Odd q^b exercises the plain-copy tile variant (no TMA), the others the TMA variant."""
     np.random.seed(q * 100 + n)
     C = 3
     sw, locq, strengths = qsft_b200.generate_signal_w(n, q, S, 1, 1, full=False)
@@ -293,43 +272,19 @@ def test_experimental_k4_classify_v2_equals_v1(q, n, b, S, R, chan, noise, monke
     prob = ops.PeelProblem(q, n, b, Ms, Dall, n + 1, channel, "identity", 1e-9 + 1.5 * noise ** 2 / q ** b, DEV,
                            nso_subtype="nso2" if chan == "nso2" else "nso1")
     prob.alloc(4 * C * q ** b)
-    v1 = _classify_once(prob, U, 1, monkeypatch)
-    v2 = _classify_once(prob, U, 2, monkeypatch)
-    monkeypatch.setenv("QSFT_K4_FASTDET", "1")               # quadrant detection (q = 2 / 4), both kernels
-    f1 = _classify_once(prob, U, 1, monkeypatch)
-    f2 = _classify_once(prob, U, 2, monkeypatch)
-    monkeypatch.delenv("QSFT_K4_FASTDET")
-    for alt in (f1, f2):
-        assert alt["nf"] == v1["nf"] and alt["nm"] == v1["nm"]
-        assert np.array_equal(alt["cj"], v1["cj"]) and np.array_equal(alt["k"], v1["k"])
-    assert v1["nf"] == v2["nf"] and v1["nm"] == v2["nm"] and v1["nf"] > 0
-    assert np.array_equal(v1["cj"], v2["cj"]) and np.array_equal(v1["k"], v2["k"]) and np.array_equal(v1["round"], v2["round"])
-    assert np.max(np.abs(v1["rho"] - v2["rho"])) <= 2e-6 * max(1.0, np.max(np.abs(v1["rho"])))
-    assert np.array_equal(v1["fid"] >= 0, v2["fid"] >= 0) and not (v2["fid"] == -7).any()
-    # find_id points at the find of its own bin
-    fid2 = prob.find_id.cpu().numpy().ravel()
-    cj2 = prob.find_cj[:v2["nf"]].cpu().numpy()
-    hit = np.nonzero(fid2 >= 0)[0]
-    assert np.array_equal(cj2[fid2[hit]], hit)
-
-
-@experimental
-def test_experimental_k4_v2_full_peel_config2_shape(monkeypatch):
-    """Whole peel loop with the v2 classification on a noisy config-2-shaped problem == default kernel's result."""
-    p = dict(n=20, q=4, S=1000, b=7, C=3, R=3)
-    qa = {"query_method": "complex", "num_subsample": 3, "delays_method_source": "identity", "subsampling_method": "qsft",
-          "delays_method_channel": "nso", "num_repeat": 3, "b": 7}
-    out = {}
-    for impl in (1, 2):
-        if impl == 2:
-            monkeypatch.setenv("QSFT_K4_IMPL", "2")
-        np.random.seed(0)
-        sig = qsft_b200.get_random_subsampled_signal(n=p["n"], q=p["q"], sparsity=p["S"], a_min=1, a_max=1,
-                                                      noise_sd=3.1623, query_args=dict(qa))
-        out[impl] = qsft_b200.QSFT(num_subsample=3, num_repeat=3, b=7, reconstruct_method_source="identity",
-                                   reconstruct_method_channel="nso").transform(sig)
-    assert list(out[1].keys()) == list(out[2].keys())
-    assert max(abs(out[1][k] - out[2][k]) for k in out[1]) < 1e-5
+    monkeypatch.delenv("QSFT_K4_IMPL", raising=False)
+    U0 = U.clone()
+    nf_d, nr_d = prob.peel(U)
+    assert torch.equal(U, U0)
+    k_d, v_d, c_d = prob.distinct()
+    monkeypatch.setenv("QSFT_K4_IMPL", "1")
+    nf_h, nr_h = prob.peel(U0)
+    k_h, v_h, c_h = prob.distinct()
+    assert (nf_d, nr_d) == (nf_h, nr_h) and nf_d > 0
+    assert np.array_equal(k_d, k_h) and np.array_equal(c_d, c_h)
+    assert np.max(np.abs(v_d - v_h)) <= 1e-5 * np.max(np.abs(v_h))
+    if noise == 0.0 and chan != "nso2":
+        assert len(k_d) >= 0.9 * len(sw)
 
 
 def test_dense_gwht_igwht_utils():

@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 import qsft_b200  # noqa: E402
 from qsft_b200 import ops, utils  # noqa: E402
 
-ONLY = set(sys.argv[sys.argv.index("--only") + 1].split(",")) if "--only" in sys.argv else {"k1", "k3", "k3lag", "k4"}
+ONLY = set(sys.argv[sys.argv.index("--only") + 1].split(",")) if "--only" in sys.argv else {"k1", "k3", "k4"}
 dev = torch.device("cuda", 0)
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -42,21 +42,7 @@ x = torch.randn((P, B, 2), device=dev).view(torch.float32)
 xc = torch.view_as_complex(x.view(P, B, 2))
 ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
 out["k3_gwht 41 x 4^10"] = {"ms": ms, "GBps_algorithmic(16B/elem)": 16 * P * B / ms / 1e6, "frac": 16 * P * B / ms / 1e6 / peak}
-# ticket order of the two-pass kernel: 0 = plain block-by-block order, k = contiguous pass k blocks ahead (default: auto)
-for lag in (("0", "1", "2", "3", "4") if "k3lag" in ONLY else ()):
-    os.environ["QSFT_K3_LAG"] = lag
-    ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
-    out[f"k3_gwht 41 x 4^10, QSFT_K3_LAG={lag}"] = {"ms": ms, "frac": 16 * P * B / ms / 1e6 / peak}
-os.environ.pop("QSFT_K3_LAG", None)
-if "k3lag" in ONLY:                                          # 3 CTAs per SM (80 registers) instead of 4 (64 registers)
-    os.environ["QSFT_K3_CTAS"] = "3"
-    for lag in ("0", "2", "3"):
-        os.environ["QSFT_K3_LAG"] = lag
-        ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
-        out[f"k3_gwht 41 x 4^10, QSFT_K3_CTAS=3 QSFT_K3_LAG={lag}"] = {"ms": ms, "frac": 16 * P * B / ms / 1e6 / peak}
-    os.environ.pop("QSFT_K3_LAG", None)
-    os.environ.pop("QSFT_K3_CTAS", None)
-for bb, rows in ([(7, 1024), (8, 512), (6, 4096), (12, 4)] if "k3" in ONLY else []):
+for bb, rows in ([(7, 1024), (8, 512), (9, 128), (6, 4096), (12, 4)] if "k3" in ONLY else []):
     y = torch.view_as_complex(torch.randn((rows, q ** bb, 2), device=dev))
     ms = timeit(lambda: ops.gwht_batch_(y, q, bb), flush=flush)
     out[f"k3_gwht {rows} x 4^{bb}"] = {"ms": ms, "GBps": 16 * rows * q ** bb / ms / 1e6, "frac": 16 * rows * q ** bb / ms / 1e6 / peak}
@@ -97,41 +83,49 @@ def classify_round1():
 
 
 ms = timeit(classify_round1, flush=flush)
-out[f"k4_classify round 1 (C=3,P=41,B=4^10), QSFT_K4_IMPL={os.environ.get('QSFT_K4_IMPL', '1')} FASTDET={os.environ.get('QSFT_K4_FASTDET', '0')}"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
-if "--k4-variants" in sys.argv:
-    # the opt-in classification variants in the same process (the knobs are read on every call): time of round 1 and a
-    # cheap parity signal -- number of singletons / multitons and an order-independent checksum of the finds
-    def signature():
-        classify_round1()
-        torch.cuda.synchronize()
-        nf, nm = int(prob.counters[0]), int(prob.counters[1])
-        cj = prob.find_cj[:nf]
-        k = prob.find_k[:nf].to(torch.int64)
-        w = torch.arange(1, k.shape[1] + 1, device=dev, dtype=torch.int64)
-        return nf, nm, int(cj.sum()), int(((k * w).sum(dim=1) * (cj % 1000003 + 1)).sum())
+out["k4_classify_kernel round 1 (stand-alone classification, C=3,P=41,B=4^10)"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
 
-    base_sig = signature()
-    for impl, fast in (("1", "1"), ("2", "0"), ("2", "1")):
-        os.environ["QSFT_K4_IMPL"], os.environ["QSFT_K4_FASTDET"] = impl, fast
-        try:
-            sig = signature()
-            ms = timeit(classify_round1, flush=flush)
-            out[f"k4_classify round 1, QSFT_K4_IMPL={impl} FASTDET={fast}"] = {
-                "ms": ms, "frac": 8 * C * P * B / ms / 1e6 / peak, "same_finds_as_default": sig == base_sig,
-                "finds": sig[0], "multitons": sig[1]}
-        except Exception as exc:
-            out[f"k4_classify round 1, QSFT_K4_IMPL={impl} FASTDET={fast}"] = {"error": repr(exc)}
-    os.environ.pop("QSFT_K4_IMPL", None)
-    os.environ.pop("QSFT_K4_FASTDET", None)
-try:                                     # (a faulting opt-in variant above would have poisoned the context: keep what we have)
+
+def peel_sig(Uin):
+    nf, nr = prob.peel(Uin)
+    torch.cuda.synchronize()
+    nu = prob.n_uniq
+    k = prob.uniq_k[:nu].to(torch.int64)
+    w = torch.arange(1, k.shape[1] + 1, device=dev, dtype=torch.int64)
+    return nf, nr, nu, int(((k * w).sum(dim=1) * (prob.uniq_key[:nu] % 1000003 + 1)).sum()), float(prob.uniq_sum[:nu].abs().sum())
+
+
+try:
+    round_bytes = 8 * C * P * B
+    # the whole loop in one persistent kernel (default); U is not modified
+    sig_dev = peel_sig(U0)
+    ms = timeit(lambda: prob.peel(U0), flush=flush)
+    out["k4 peel, device loop (default)"] = {"ms": ms, "rounds": sig_dev[1], "finds": sig_dev[0], "distinct": sig_dev[2],
+                                             "GBps(8 B x rounds)": round_bytes * sig_dev[1] / ms / 1e6,
+                                             "frac": round_bytes * sig_dev[1] / ms / 1e6 / peak}
+    os.environ["QSFT_K4_MAX_ROUNDS"] = "1"
+    ms = timeit(lambda: prob.peel(U0), flush=flush)
+    out["k4 peel, device loop, round 1 only (QSFT_K4_MAX_ROUNDS=1)"] = {"ms": ms, "GBps": round_bytes / ms / 1e6, "frac": round_bytes / ms / 1e6 / peak}
+    os.environ.pop("QSFT_K4_MAX_ROUNDS")
     Uz = torch.zeros_like(U0)
-    ms = timeit(lambda: (prob.counters.zero_(), prob.classify(Uz, 0, B, 1)), flush=flush)
-    out["k4_classify all-zeroton round"] = {"ms": ms, "GBps": 8 * C * P * B / ms / 1e6, "frac": 8 * C * P * B / ms / 1e6 / peak}
+    ms = timeit(lambda: prob.peel(Uz), flush=flush)
+    out["k4 peel, device loop, all-zeroton bins (1 round)"] = {"ms": ms, "GBps": round_bytes / ms / 1e6, "frac": round_bytes / ms / 1e6 / peak}
+    os.environ["QSFT_K4_NO_TMA"] = "1"
+    sig_nt = peel_sig(U0)
+    ms = timeit(lambda: prob.peel(U0), flush=flush)
+    out["k4 peel, device loop without TMA (QSFT_K4_NO_TMA=1)"] = {"ms": ms, "same_result": sig_nt[:4] == sig_dev[:4]}
+    os.environ.pop("QSFT_K4_NO_TMA")
+    # host-driven rounds (cross-check path): modifies U in place, so every run starts from a copy
+    os.environ["QSFT_K4_IMPL"] = "1"
     U = U0.clone()
+    sig_host = peel_sig(U)
     ms = timeit(lambda: (U.copy_(U0), prob.peel(U)), flush=flush)
     ms_copy = timeit(lambda: U.copy_(U0), flush=flush)
-    out["k4 full peel loop (3 rounds incl. host syncs)"] = {"ms": ms - ms_copy, "rounds": prob.peel(U0.clone())[1]}
+    out["k4 peel, host-driven rounds (QSFT_K4_IMPL=1)"] = {"ms": ms - ms_copy, "rounds": sig_host[1], "finds": sig_host[0],
+                                                          "same_result_as_device_loop": sig_host[:4] == sig_dev[:4],
+                                                          "sum_abs_rel_diff": abs(sig_host[4] - sig_dev[4]) / max(sig_host[4], 1e-30)}
+    os.environ.pop("QSFT_K4_IMPL")
     out["copy U (torch) reference"] = {"ms": ms_copy, "GBps": 16 * C * P * B / ms_copy / 1e6}
 except Exception as exc:
-    out["error after the variants"] = repr(exc)
+    out["error in the peel timings"] = repr(exc)
 print(json.dumps(out, indent=1))
