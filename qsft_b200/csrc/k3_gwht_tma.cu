@@ -41,13 +41,18 @@ struct KtInfo {
 // element index -> position in the 128-byte-swizzled tile (16-byte chunk index ^= row & 7)
 __device__ __forceinline__ int kt_swz(int e) { return e ^ (((e >> 4) & 7) << 1); }
 
+// radix-4 butterfly on packed fp32 pairs (FADD2 / FFMA2: one instruction per complex add; a - b = fma(b, -1, a) and the
+// +-i rotations = fma(swap(b), (+-1, -+1), a) are exactly the scalar adds / subtracts, so results are bit-identical to the
+// register-staged kernels of k3_gwht.cu)
 __device__ __forceinline__ void kt_r4(float2& a, float2& b, float2& c, float2& d) {
-    const float2 s02 = make_float2(a.x + c.x, a.y + c.y), d02 = make_float2(a.x - c.x, a.y - c.y);
-    const float2 s13 = make_float2(b.x + d.x, b.y + d.y), d13 = make_float2(b.x - d.x, b.y - d.y);
-    a = make_float2(s02.x + s13.x, s02.y + s13.y);
-    c = make_float2(s02.x - s13.x, s02.y - s13.y);
-    b = make_float2(d02.x + d13.y, d02.y - d13.x);   // d02 - i d13
-    d = make_float2(d02.x - d13.y, d02.y + d13.x);   // d02 + i d13
+    const float2 m1 = make_float2(-1.f, -1.f);
+    const float2 s02 = __fadd2_rn(a, c), d02 = __ffma2_rn(c, m1, a);
+    const float2 s13 = __fadd2_rn(b, d), d13 = __ffma2_rn(d, m1, b);
+    const float2 sw = make_float2(d13.y, d13.x);
+    a = __fadd2_rn(s02, s13);
+    c = __ffma2_rn(s13, m1, s02);
+    b = __ffma2_rn(sw, make_float2(1.f, -1.f), d02);   // d02 - i d13
+    d = __ffma2_rn(sw, make_float2(-1.f, 1.f), d02);   // d02 + i d13
 }
 
 __device__ __forceinline__ void kt_r16(float2 (&v)[16]) {
@@ -57,13 +62,37 @@ __device__ __forceinline__ void kt_r16(float2 (&v)[16]) {
     for (int h = 0; h < 4; ++h) kt_r4(v[h], v[h + 4], v[h + 8], v[h + 12]);
 }
 
+// A contiguous-pass tile is "published" (its block's counter of finished tiles bumped, release) by every consumer warp once
+// the warp's stores are visible.  The fence would wait for the stores just issued, so the publish is DEFERRED: it runs right
+// before the stores of the warp's next tile (a whole tile of butterflies later the fence returns at once), or as soon as the
+// warp would otherwise block (the next tile may depend on this very publish), or at the end.
+struct KtPending {
+    unsigned int* ctr;                               // nullptr: nothing pending
+    __device__ __forceinline__ void flush() {
+        if (ctr != nullptr) {
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) {
+                __threadfence();
+                atomicAdd(ctr, 1u);
+            }
+            ctr = nullptr;
+        }
+    }
+};
+
+template <bool PEERS>
+__device__ __forceinline__ void kt_store(float2* dst, float2 v, const float2* xroot, const K3Peers& peers) {
+    if (PEERS) k3_store(dst, v, xroot, peers);
+    else *dst = v;
+}
+
 __device__ __forceinline__ void kt_bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(KT_CONSUMERS) : "memory"); }
 
 // One tile: levels at base-4 digit positions [P0, P0 + R) of the tile index e.  STRIDED: the tile is 4^R rows (stride 4096
 // elements) x W = 4^P0 contiguous elements, e = t * W + w; otherwise 4096 contiguous elements.
-template <bool STRIDED, int R, int P0>
+template <bool STRIDED, int R, int P0, bool PEERS>
 __device__ __forceinline__ void kt_tile(float2* __restrict__ s, float2* __restrict__ gbase, float scale, const float2* xroot,
-                                        const K3Peers& peers, uint64_t* empty_bar) {
+                                        const K3Peers& peers, uint64_t* empty_bar, KtPending& pend) {
     const int tau = threadIdx.x;                     // consumer threads are 0 .. 255
     constexpr int lgW = STRIDED ? 2 * P0 : 0;
     constexpr int W = 1 << lgW;
@@ -95,9 +124,10 @@ __device__ __forceinline__ void kt_tile(float2* __restrict__ s, float2* __restri
             if (last) {
                 __syncwarp();
                 if ((tau & 31) == 0) tma::mbar_arrive(empty_bar);     // this warp no longer reads the stage
+                pend.flush();
                 float2* g = STRIDED ? gbase + (long long)(eb >> lgW) * KT_TILE + (eb & (W - 1)) : gbase + eb;
 #pragma unroll
-                for (int m = 0; m < 16; ++m) k3_store(g + m * gstep, make_float2(v[m].x * scale, v[m].y * scale), xroot, peers);
+                for (int m = 0; m < 16; ++m) kt_store<PEERS>(g + m * gstep, make_float2(v[m].x * scale, v[m].y * scale), xroot, peers);
             } else if (p == 0) {
                 float4* s4 = reinterpret_cast<float4*>(s) + tau * 8;
 #pragma unroll
@@ -121,13 +151,14 @@ __device__ __forceinline__ void kt_tile(float2* __restrict__ s, float2* __restri
             if (last) {
                 __syncwarp();
                 if ((tau & 31) == 0) tma::mbar_arrive(empty_bar);
+                pend.flush();
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float2* g = STRIDED ? gbase + (long long)(eb[k] >> lgW) * KT_TILE + (eb[k] & (W - 1)) : gbase + eb[k];
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
-                    if (last) k3_store(g + m * gstep, make_float2(v[4 * k + m].x * scale, v[4 * k + m].y * scale), xroot, peers);
+                    if (last) kt_store<PEERS>(g + m * gstep, make_float2(v[4 * k + m].x * scale, v[4 * k + m].y * scale), xroot, peers);
                     else s[kt_swz(eb[k] + m * step)] = v[4 * k + m];
                 }
             }
@@ -136,6 +167,7 @@ __device__ __forceinline__ void kt_tile(float2* __restrict__ s, float2* __restri
     }
 }
 
+template <bool PEERS>
 __global__ void __launch_bounds__(KT_THREADS, 2)
 k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2, float2* __restrict__ x,
                  long long B, int r1, int r2, int tiles1, int tiles2, unsigned int* __restrict__ done /* [nblocks] + ticket */,
@@ -164,13 +196,16 @@ k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant_
         if ((threadIdx.x & 31) == 0) {
             tma::prefetch_map(&tm1);
             tma::prefetch_map(&tm2);
+            // tickets, not blockIdx: every lower ticket is held by a CTA that is already resident (or finished), which is
+            // what makes the dependency wait below deadlock free.  The ticket of the NEXT tile is drawn before this one's
+            // stage is waited for, so the round trip of the atomic overlaps the wait.
+            unsigned int ticket_next = atomicAdd(done + nblocks, 1u);
             for (unsigned it = 0;; ++it) {
                 const int stage = (int)(it % KT_STAGES);
                 const uint32_t ph = (it / KT_STAGES) & 1u;
+                const unsigned int ticket = ticket_next;
+                if ((long long)ticket < total) ticket_next = atomicAdd(done + nblocks, 1u);
                 tma::mbar_wait(&empty[stage], ph ^ 1u);
-                // tickets, not blockIdx: every lower ticket is held by a CTA that is already resident (or finished), which is
-                // what makes the dependency wait below deadlock free
-                const unsigned int ticket = atomicAdd(done + nblocks, 1u);
                 if ((long long)ticket >= total) {
                     info[stage].blk = -1;
                     tma::mbar_arrive(&full[stage]);
@@ -207,10 +242,14 @@ k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant_
         }
     } else {
         // ---- consumers -------------------------------------------------------------------------------------------
+        KtPending pend{nullptr};
         for (unsigned it = 0;; ++it) {
             const int stage = (int)(it % KT_STAGES);
             const uint32_t ph = (it / KT_STAGES) & 1u;
-            tma::mbar_wait(&full[stage], ph);
+            if (!tma::mbar_try_wait(&full[stage], ph)) {
+                pend.flush();                        // about to block: the producer may be waiting for this publish
+                tma::mbar_wait(&full[stage], ph);
+            }
             const long long blk = info[stage].blk;
             if (blk < 0) break;
             const int t = info[stage].t;
@@ -218,29 +257,23 @@ k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant_
             float2* s = reinterpret_cast<float2*>(base + (size_t)stage * KT_TILE_BYTES);
             float2* xb = x + blk * B;
             if (!strided) {
-                K3Peers none;
-                none.n = 0;
                 if (tiles2 == 0) {
-                    kt_tile<false, 6, 0>(s, xb + (long long)t * KT_TILE, scale1, x, peers, &empty[stage]);
+                    kt_tile<false, 6, 0, PEERS>(s, xb + (long long)t * KT_TILE, scale1, x, peers, &empty[stage], pend);
                 } else {
-                    kt_tile<false, 6, 0>(s, xb + (long long)t * KT_TILE, scale1, x, none, &empty[stage]);
-                    // publish: this warp's part of the tile is written
-                    __syncwarp();
-                    if ((threadIdx.x & 31) == 0) {
-                        __threadfence();
-                        atomicAdd(done + blk, 1u);
-                    }
+                    kt_tile<false, 6, 0, false>(s, xb + (long long)t * KT_TILE, scale1, x, peers, &empty[stage], pend);
+                    pend.ctr = done + blk;           // publish later: this warp's part of the tile is written
                 }
             } else {
                 float2* gb = xb + ((long long)t << lgW);
                 switch (r2) {
-                    case 4: kt_tile<true, 4, 2>(s, gb, scale2, x, peers, &empty[stage]); break;
-                    case 3: kt_tile<true, 3, 3>(s, gb, scale2, x, peers, &empty[stage]); break;
-                    case 2: kt_tile<true, 2, 4>(s, gb, scale2, x, peers, &empty[stage]); break;
-                    default: kt_tile<true, 1, 5>(s, gb, scale2, x, peers, &empty[stage]); break;
+                    case 4: kt_tile<true, 4, 2, PEERS>(s, gb, scale2, x, peers, &empty[stage], pend); break;
+                    case 3: kt_tile<true, 3, 3, PEERS>(s, gb, scale2, x, peers, &empty[stage], pend); break;
+                    case 2: kt_tile<true, 2, 4, PEERS>(s, gb, scale2, x, peers, &empty[stage], pend); break;
+                    default: kt_tile<true, 1, 5, PEERS>(s, gb, scale2, x, peers, &empty[stage], pend); break;
                 }
             }
         }
+        pend.flush();
     }
 }
 
@@ -269,9 +302,10 @@ int qsft_k3_q4_tma(float* xf, int64_t batch, int b, float* const* peer_x, int n_
         return rc;
     static int ctas = 0;
     if (ctas == 0) {
-        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT_SMEM));
+        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT_SMEM));
+        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT_SMEM));
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_tma_kernel, KT_THREADS, KT_SMEM) != cudaSuccess || per_sm < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_tma_kernel<true>, KT_THREADS, KT_SMEM) != cudaSuccess || per_sm < 1) {
             (void)cudaGetLastError();
             per_sm = 1;
         }
@@ -297,8 +331,12 @@ int qsft_k3_q4_tma(float* xf, int64_t batch, int b, float* const* peer_x, int n_
     peers.n = n_peers;
     for (int r = 0; r < 7; ++r) peers.p[r] = r < n_peers ? reinterpret_cast<float2*>(peer_x[r]) : nullptr;
     const float inv = (float)(1.0 / (double)B);
-    k3_q4_tma_kernel<<<grid, KT_THREADS, KT_SMEM, st>>>(tm1, tm2, reinterpret_cast<float2*>(xf), B, r1, r2, tiles1, tiles2, done,
-                                                        (long long)batch, lag, r2 ? 1.0f : inv, inv, peers);
+    if (n_peers > 0)
+        k3_q4_tma_kernel<true><<<grid, KT_THREADS, KT_SMEM, st>>>(tm1, tm2, reinterpret_cast<float2*>(xf), B, r1, r2, tiles1, tiles2,
+                                                                  done, (long long)batch, lag, r2 ? 1.0f : inv, inv, peers);
+    else
+        k3_q4_tma_kernel<false><<<grid, KT_THREADS, KT_SMEM, st>>>(tm1, tm2, reinterpret_cast<float2*>(xf), B, r1, r2, tiles1, tiles2,
+                                                                   done, (long long)batch, lag, r2 ? 1.0f : inv, inv, peers);
     QSFT_LAUNCHED();
     QSFT_CUDA(cudaFreeAsync(done, st));
     return QSFT_OK;

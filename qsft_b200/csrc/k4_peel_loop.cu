@@ -8,14 +8,18 @@
 // 2 * C * P float atomics per ball on DRAM-resident data by C pointer swaps, needs no private copy of U, and every round
 // starts from the original samples (no accumulated rounding).
 //
-// Classification of one round: every warp owns 16- or 32-bin tiles (all P delay rows of those bins), double buffered:
-//   * TMA variant (row stride a multiple of 16 bytes): the tile is fetched with cp.async.bulk.tensor boxes of
-//     {16 bins = 128 B, P_src rows} per (c, r) block with the 128-byte swizzle, so that both access patterns are free of
-//     bank conflicts: lanes over bins (energy scan) and lanes over delay rows (detection, rho, residual);
-//   * plain variant (odd q^b): the warp copies the tile with coalesced loads into the same layout.
-//   Phase 1: energies (one lane per bin) and the bins' ball lists; bins with listed balls are updated in place by 8-lane
-//   groups.  Phase 2: non-zeroton bins are handled four at a time by 8-lane groups: symbols (reconstruct.py:12-31,100-129),
-//   optional Reed-Solomon decode, rho and residual (qsft.py:174-183), bin hash check (qsft.py:178-179).
+// Classification of one round: the CTA walks over tiles of W bins (W = 128 .. 16) x all P delay rows of one group:
+//   * TMA variant (q^b a multiple of 16): 1 producer warp + 16 consumer warps, ring of 2 .. 6 stages.  A tile is ONE
+//     cp.async.bulk.tensor box {16 bins = 128 B, P_src rows, W / 16 chunks} per repeat block (every delay row contributes
+//     W * 8 contiguous bytes) and lands as [chunk][row][128 B] with the 128-byte swizzle, so that both access patterns are
+//     free of bank conflicts: lanes over bins (energy scan) and lanes over delay rows (detection, rho, residual).  The
+//     bins' ball-list heads travel with the tile (cp.async.bulk).
+//   * plain variant (odd q^b, tiny q^b; also what the CPU emulation of tests/emu runs): the 16 consumer warps copy the tile
+//     with coalesced loads into the same layout, single stage.
+//   Step 0 (rounds > 1): bins with listed balls are updated in place by 8-lane groups.  Step 1: energies, 512 threads over
+//   W bins x row slices.  One CTA barrier.  Step 2: every warp rebuilds the tile's candidate mask and takes its share of the
+//   non-zeroton bins, four at a time by 8-lane groups: symbols (reconstruct.py:12-31,100-129), optional Reed-Solomon decode,
+//   rho and residual in ONE pass over the rows (qsft.py:174-183), bin hash check (qsft.py:178-179).
 // Link phase of a round: one thread per find: duplicate gathering / averaging exactly like k4_reduce_kernel, and the
 // "last (i, j) wins" find of every k (qsft.py:215) links the ball into its C bins.
 #include "common.cuh"
@@ -30,16 +34,21 @@
 
 namespace {
 
-constexpr int KL_THREADS = 256;
+constexpr int KL_CW = 16;                    // consumer warps
+constexpr int KL_CT = KL_CW * 32;            // consumer threads
 constexpr int KL_MAX_BLOCKS = 16;            // (c, r) blocks of U addressed separately (C * R <= 16)
 constexpr int KL_G = 8;                      // lanes per bin in the group phases
+constexpr int KL_MAXW = 128;                 // bins per tile, at most
+constexpr int KL_MAX_STAGES = 6;
+constexpr int KL_SYM = 2 * QSFT_MAX_N;       // per group: detected symbols + decoded k
+constexpr int KL_CTRL_BYTES = 256 + 2 * KL_CT * 4 + 2 * KL_MAXW * 4 + KL_CW * 4 * KL_SYM;
 
 struct KlBlocks {
     const float2* p[KL_MAX_BLOCKS];          // block c * R + r: (P_src, ldU) complex64, bin index contiguous
 };
 #ifndef QSFT_EMU
 struct KlMaps {
-    CUtensorMap m[KL_MAX_BLOCKS];            // the same blocks as 2-D tensors {2 B floats, P_src rows}, box {32, P_src}
+    CUtensorMap m[KL_MAX_BLOCKS];            // the same blocks as 3-D tensors {32 floats, P_src rows, B / 16 chunks}
 };
 #endif
 
@@ -61,9 +70,10 @@ struct KlArgs {
     unsigned long long* multi;               // [r] multitons of round r (1 <= r <= 15; workspace, zeroed by the host)
     unsigned int* gbar;                      // grid barrier counter (zeroed by the host)
     const int* dstruct;                      // device flag: D[c][r][i] = D[c][r][0] - e_{i-1} (identity / nso delays)
-    int wpc;                                 // warps per CTA that classify (shared-memory budget)
-    int bw;                                  // bins per warp tile: 16 or 32
-    int sbox;                                // bytes per (half, repeat) sub-box of a tile: P_src * 128 rounded up to 1024
+    int W, lgW;                              // bins per tile (power of two, 16 .. 128)
+    int box;                                 // bytes per repeat block of a tile: (W / 16) * P_src * 128 rounded up to 1024
+    int stage_bytes;                         // R * box + list heads, rounded up to 1024
+    int nstages;
     int max_rounds;
     int guard_can_bind;
     double peeling_max;
@@ -71,22 +81,63 @@ struct KlArgs {
 };
 
 // ---- tile access -------------------------------------------------------------------------------------------------
-// tile = [half h (16 bins)][repeat r][row i (128 B: 16 bins, 16-byte chunks xor-swizzled with i & 7)]
+// stage = [repeat r][chunk ch (16 bins)][row i][128 B: 16 bins, 16-byte chunks xor-swizzled with the line index & 7]
 struct TileCol {
-    float2* t;
-    int R, sbox8;                            // sbox in float2 units
+    uint8_t* t;
+    int P_src, box;
     int lb;                                  // local bin
     __device__ __forceinline__ int off(int r, int i) const {
-        return ((lb >> 4) * R + r) * sbox8 + (i << 4) + (((((lb & 15) >> 1) ^ (i & 7)) << 1) | (lb & 1));
+        const int line = (lb >> 4) * P_src + i;
+        return r * box + line * 128 + (((((lb & 15) >> 1) ^ (line & 7)) << 4) | ((lb & 1) << 3));
     }
-    __device__ __forceinline__ float2 ri(int r, int i) const { return t[off(r, i)]; }
-    __device__ __forceinline__ float2& ref(int r, int i) const { return t[off(r, i)]; }
+    __device__ __forceinline__ float2 ri(int r, int i) const { return *reinterpret_cast<const float2*>(t + off(r, i)); }
+    __device__ __forceinline__ float2& ref(int r, int i) const { return *reinterpret_cast<float2*>(t + off(r, i)); }
 };
 
 __device__ __forceinline__ float kl_group_sum(float v) {
 #pragma unroll
     for (int o = KL_G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// position of the n-th (0-based) set bit of m; n < popc(m)
+__device__ __forceinline__ int kl_nth_bit(unsigned m, int n) {
+    int pos = 0;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const unsigned low = m & ((1u << s) - 1u);
+        const int c = __popc(low);
+        if (n >= c) {
+            n -= c;
+            m >>= s;
+            pos += s;
+        } else {
+            m = low;
+        }
+    }
+    return pos;
+}
+
+// local bin of rank `rank` in the tile's masks (4 words of 32 bins), -1 when rank >= total
+__device__ __forceinline__ int kl_pick(const unsigned (&mask)[4], int rank) {
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const int c = __popc(mask[w]);
+        if (rank >= 0 && rank < c) return w * 32 + kl_nth_bit(mask[w], rank);
+        rank -= c;
+    }
+    return -1;
+}
+
+template <bool TMA>
+__device__ __forceinline__ void kl_consumer_barrier() {
+#ifndef QSFT_EMU
+    if (TMA) {
+        asm volatile("bar.sync 1, %0;" ::"n"(KL_CT) : "memory");
+        return;
+    }
+#endif
+    __syncthreads();
 }
 
 __device__ __forceinline__ void kl_grid_barrier(unsigned int* gbar, unsigned int& epoch) {
@@ -134,266 +185,304 @@ struct KlPhase {
     }
 };
 
+// ---- one tile: steps 0 .. 2 (consumer threads only, tid < KL_CT) ------------------------------------------------------
+template <int NW, bool TMA>
+__device__ __forceinline__ void kl_tile(const KlArgs& a, uint8_t* stage, int c, long long j0, int round, int par, float* s_part,
+                                        float* s_efix, uint8_t* s_symw, const float2* s_tw, bool structured,
+                                        const long long (&wgt)[32 / KL_G], unsigned& n_multi) {
+    const PeelDev& d = a.d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = lane / KL_G, gl = lane % KL_G;
+    const int W = a.W, R = d.R, P_src = d.P_src;
+    const long long B = d.B;
+    const int32_t* s_head = reinterpret_cast<const int32_t*>(stage + (size_t)R * a.box);
+    float* part = s_part + par * KL_CT;
+    float* efix = s_efix + par * KL_MAXW;
+    const float thresh = (float)d.thresh;
+    const int nsym = P_src - 1;
+    uint8_t* sym = s_symw + grp * KL_SYM;
+
+    // ---- step 0: bins with peeled balls (qsft.py:223-241 applied to the shared-memory copy) ------------------------------
+    unsigned tmask[4] = {0u, 0u, 0u, 0u};
+    if (round > 1) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int lb = w * 32 + lane;
+            const bool on = lb < W && j0 + lb < B && s_head[lb] != 0;
+            tmask[w] = __ballot_sync(0xffffffffu, on);
+        }
+        const int total = __popc(tmask[0]) + __popc(tmask[1]) + __popc(tmask[2]) + __popc(tmask[3]);
+        for (int base = 4 * warp; base < total; base += 4 * KL_CW) {
+            const int rank = base + grp;
+            const int my = rank < total ? kl_pick(tmask, rank) : -1;
+            int f = my >= 0 ? s_head[my] - 1 : -1;
+            TileCol tc{stage, P_src, a.box, my >= 0 ? my : 0};
+            while (__ballot_sync(0xffffffffu, f >= 0)) {
+                if (f >= 0) {
+                    const uint4* src = reinterpret_cast<const uint4*>(a.find_k + (size_t)f * d.ld);
+                    for (int w = gl; w < d.ld / 16; w += KL_G) reinterpret_cast<uint4*>(sym)[w] = __ldcg(src + w);
+                }
+                __syncwarp();
+                if (f >= 0) {
+                    uint32_t kw[NW];
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) kw[w] = (4 * w < d.ld) ? reinterpret_cast<const uint32_t*>(sym)[w] : 0u;
+                    const float2 rho = __ldcg(a.find_rho + f);
+                    const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, sym, kw, structured};
+                    for (int r = 0; r < R; ++r) {
+                        const int tb = ph.base(r);
+                        for (int i = gl; i < P_src; i += KL_G) {
+                            const float2 w = s_tw[ph.row(r, i, tb)];
+                            float2& v = tc.ref(r, i);
+                            v.x -= rho.x * w.x - rho.y * w.y;
+                            v.y -= rho.x * w.y + rho.y * w.x;
+                        }
+                    }
+                    f = __ldcg(a.next + (size_t)f * d.C + c) - 1;
+                }
+                __syncwarp();
+            }
+            // energy of the updated bin
+            float e2 = 0.f;
+            if (my >= 0)
+                for (int r = 0; r < R; ++r)
+                    for (int i = gl; i < P_src; i += KL_G) {
+                        const float2 v = tc.ri(r, i);
+                        e2 = fmaf(v.x, v.x, fmaf(v.y, v.y, e2));
+                    }
+            e2 = kl_group_sum(e2);
+            if (my >= 0 && gl == 0) efix[my] = e2;
+        }
+    }
+
+    // ---- step 1: energy partials, thread = (row slice, bin) -------------------------------------------------------------
+    {
+        const int lb = tid & (W - 1), prt = tid >> a.lgW, nparts = KL_CT >> a.lgW;
+        TileCol tc{stage, P_src, a.box, lb};
+        float e = 0.f;
+        for (int r = 0; r < R; ++r)
+            for (int i = prt; i < P_src; i += nparts) {
+                const float2 v = tc.ri(r, i);
+                e = fmaf(v.x, v.x, fmaf(v.y, v.y, e));
+            }
+        part[tid] = e;
+    }
+    kl_consumer_barrier<TMA>();
+
+    // ---- step 2: candidate masks (every warp), then this warp's share of the non-zeroton bins ----------------------------
+    unsigned cmask[4] = {0u, 0u, 0u, 0u};
+    float ew[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+        const int nparts = KL_CT >> a.lgW;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int lb = w * 32 + lane;
+            const bool valid = lb < W && j0 + lb < B;
+            float e = 0.f;
+            if (valid) {
+                if ((tmask[w] >> lane) & 1u) {
+                    e = efix[lb];
+                } else {
+                    for (int p = 0; p < nparts; ++p) e += part[p * W + lb];
+                }
+            }
+            ew[w] = e;
+            cmask[w] = __ballot_sync(0xffffffffu, valid && e > thresh);
+        }
+    }
+    const int total = __popc(cmask[0]) + __popc(cmask[1]) + __popc(cmask[2]) + __popc(cmask[3]);
+    for (int base = 4 * warp; base < total; base += 4 * KL_CW) {
+        const int rank = base + grp;
+        const int my = rank < total ? kl_pick(cmask, rank) : -1;
+        const bool act = my >= 0;
+        const int lbm = act ? my : 0;
+        const long long jb = j0 + lbm;
+        float e_b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float v = __shfl_sync(0xffffffffu, ew[w], lbm & 31);
+            if ((lbm >> 5) == w) e_b = v;
+        }
+        TileCol tc{stage, P_src, a.box, lbm};
+        uint8_t* kb = sym;
+        if (act) {
+            for (int i = 1 + gl; i <= nsym; i += KL_G) sym[i - 1] = (uint8_t)detect_symbol(d, tc, i);
+            for (int i = nsym + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) sym[i] = 0;
+        }
+        __syncwarp();
+        if (d.source == 1) {
+            kb = sym + QSFT_MAX_N;
+            if (act) {
+                for (int i = d.n + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) kb[i] = 0;
+                if (gl == 0) rs_decode(d, sym, kb);
+            }
+            __syncwarp();
+        }
+        uint32_t kw[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) kw[w] = reinterpret_cast<const uint32_t*>(kb)[w];
+        const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, kb, kw, structured};
+        // rho = <signature, col> / P (qsft.py:174-175) and the residual ||col - rho sig||^2 (qsft.py:176,183) in one pass:
+        // with z_i = conj(sig_i) col_i and the shift z0 = z of row (0, 0),  rho = z0 + mean(z_i - z0)  and
+        // residual = sum |z_i - z0|^2 - |sum (z_i - z0)|^2 / P.  For a singleton every z_i - z0 is at rounding level, so the
+        // subtraction cancels nothing that matters; for a multiton the residual is large either way.
+        float sx = 0.f, sy = 0.f, s2 = 0.f;
+        float2 z0 = make_float2(0.f, 0.f);
+        if (act) {
+            const int tb0 = ph.base(0);
+            {
+                const float2 w = s_tw[tb0];
+                const float2 v = tc.ri(0, 0);
+                z0 = make_float2(w.x * v.x + w.y * v.y, w.x * v.y - w.y * v.x);
+            }
+            for (int r = 0; r < R; ++r) {
+                const int tb = r == 0 ? tb0 : ph.base(r);
+                for (int i = gl; i < P_src; i += KL_G) {
+                    const float2 w = s_tw[ph.row(r, i, tb)];
+                    const float2 v = tc.ri(r, i);
+                    const float dx = (w.x * v.x + w.y * v.y) - z0.x;            // conj(sig) * v - z0
+                    const float dy = (w.x * v.y - w.y * v.x) - z0.y;
+                    sx += dx;
+                    sy += dy;
+                    s2 = fmaf(dx, dx, fmaf(dy, dy, s2));
+                }
+            }
+        }
+        sx = kl_group_sum(sx);
+        sy = kl_group_sum(sy);
+        s2 = kl_group_sum(s2);
+        const float invP = (float)d.invP;
+        const float rr = z0.x + sx * invP, ri = z0.y + sy * invP;
+        const float res = s2 - (sx * sx + sy * sy) * invP;
+        // bin hash j = dec(M_c^T k mod q) (qsft.py:178-179)
+        long long hsum = 0;
+        if (act) {
+#pragma unroll
+            for (int u = 0; u < 32 / KL_G; ++u) {
+                const int i = gl + u * KL_G;
+                if (i < d.b)
+                    hsum += wgt[u] * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + i) * d.ld, d.ld, kw), d.q, d.qmagic);
+            }
+        }
+#pragma unroll
+        for (int o = KL_G / 2; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
+        const float lim = fmaxf(thresh, a.rel_floor * e_b);
+        const bool single = act && (hsum == jb) && !(res > lim);
+        const bool lead = (gl == 0);
+        const unsigned sb = __ballot_sync(0xffffffffu, lead && single);
+        unsigned long long fbase = 0;
+        if (lane == 0 && sb) fbase = atomicAdd(&a.counters[0], (unsigned long long)__popc(sb));
+        fbase = __shfl_sync(0xffffffffu, fbase, 0);
+        unsigned long long f = fbase + (unsigned long long)__popc(sb & ((1u << lane) - 1u));
+        f = __shfl_sync(0xffffffffu, f, lane & ~(KL_G - 1));
+        if (single) {
+            if ((long long)f < a.max_finds) {
+                uint32_t* ko = reinterpret_cast<uint32_t*>(a.find_k + (size_t)f * d.ld);
+                for (int w = gl; w < d.ld / 4; w += KL_G) ko[w] = (w < NW) ? kw[w] : 0u;
+                if (lead) {
+                    a.find_cj[f] = (long long)c * B + jb;
+                    a.find_rho[f] = make_float2(rr, ri);
+                    a.find_round[f] = round;
+                    a.find_id[(size_t)c * B + jb] = (int32_t)f;
+                }
+            }
+        } else if (act && lead) {
+            ++n_multi;
+        }
+        __syncwarp();
+    }
+}
+
 // ---- one classification round ---------------------------------------------------------------------------------------
 template <int NW, bool TMA>
 __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk,
 #ifndef QSFT_EMU
                                             const CUtensorMap* maps,
 #endif
-                                            int round, uint8_t* wsm, uint64_t* bars, unsigned int& tiles_done,
-                                            const float2* s_tw) {
+                                            int round, uint8_t* stages, uint64_t* bars, unsigned int& tiles_done, float* s_part,
+                                            float* s_efix, uint8_t* s_sym, const float2* s_tw) {
     const PeelDev& d = a.d;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = lane / KL_G, gl = lane % KL_G;
-    const int R = d.R, P_src = d.P_src, bw = a.bw, nh = bw >> 4;
-    const int sbox8 = a.sbox >> 3;
-    const int tile_bytes = nh * R * a.sbox;
-    float2* tiles[2] = {reinterpret_cast<float2*>(wsm), reinterpret_cast<float2*>(wsm + tile_bytes)};
-    uint8_t* s_sym = wsm + 2 * tile_bytes;                         // [4 groups][2][QSFT_MAX_N]: symbols, decoded k
-    float* s_e = reinterpret_cast<float*>(s_sym + 4 * 2 * QSFT_MAX_N);
+    const int W = a.W, R = d.R, P_src = d.P_src;
     const long long B = d.B;
-    const long long tpg = (B + bw - 1) / bw;                       // tiles per group
+    const long long tpg = (B + W - 1) >> a.lgW;                    // tiles per group
     const long long n_tiles = tpg * d.C;
-    const long long gw = (long long)warp * gridDim.x + blockIdx.x, GW = (long long)a.wpc * gridDim.x;
-    const float thresh = (float)d.thresh;
-    const int nsym = P_src - 1;
-    const bool structured = (*a.dstruct != 0);
+    const bool consumer = threadIdx.x < KL_CT;
     unsigned n_multi = 0;
-    long long wgt[32 / KL_G];
-#pragma unroll
-    for (int u = 0; u < 32 / KL_G; ++u) wgt[u] = hash_weight(d, gl + u * KL_G);
-
-    auto issue = [&](long long tt, int stage) {
 #ifndef QSFT_EMU
-        if constexpr (TMA) {
-            if (lane == 0) {
+    if (TMA && !consumer) {
+        // ---- producer warp ------------------------------------------------------------------------------------------
+        if (threadIdx.x == KL_CT) {
+            uint64_t* full = bars;
+            uint64_t* empty = bars + KL_MAX_STAGES;
+            unsigned int it = tiles_done;
+            const uint32_t box_bytes = (uint32_t)((W >> 4) * P_src * 128);
+            for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++it) {
+                const int st = (int)(it % (unsigned)a.nstages);
+                const uint32_t ph = (it / (unsigned)a.nstages) & 1u;
+                tma::mbar_wait(&empty[st], ph ^ 1u);
                 const int c = (int)(tt / tpg);
-                const long long j0 = (tt - (long long)c * tpg) * bw;
-                int halves = 0;
-                for (int h = 0; h < nh; ++h) halves += (j0 + 16 * h < B) ? 1 : 0;
-                tma::mbar_expect_tx(&bars[stage], (uint32_t)(halves * R * P_src * 128));
-                for (int h = 0; h < nh; ++h) {
-                    if (j0 + 16 * h >= B) continue;
-                    for (int r = 0; r < R; ++r)
-                        tma::load_2d(reinterpret_cast<uint8_t*>(tiles[stage]) + (size_t)(h * R + r) * a.sbox, &maps[c * R + r],
-                                     (int)(2 * (j0 + 16 * h)), 0, &bars[stage]);
-                }
+                const long long j0 = (tt - (long long)c * tpg) << a.lgW;
+                uint8_t* dst = stages + (size_t)st * a.stage_bytes;
+                const long long left = B - j0;
+                const uint32_t head_bytes = round > 1 ? (uint32_t)((left < W ? left : W) * 4) : 0u;
+                tma::mbar_expect_tx(&full[st], (uint32_t)R * box_bytes + head_bytes);
+                for (int r = 0; r < R; ++r) tma::load_3d(dst + (size_t)r * a.box, &maps[c * R + r], 0, 0, (int)(j0 >> 4), &full[st]);
+                if (head_bytes) tma::bulk_g2s(dst + (size_t)R * a.box, a.head + (size_t)c * B + j0, head_bytes, &full[st]);
             }
         }
+        // every producer and consumer advances by the same number of tiles
+        const long long mine = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        tiles_done += (unsigned int)mine;
+        return;
+    }
 #endif
-    };
-
-    if (warp < a.wpc) {
-#ifndef QSFT_EMU
-        if constexpr (TMA) {
-            // U is written by other kernels / never by this one, the lists by generic stores: nothing to order for the TMA
-            // reads of U beyond the kernel boundary.  First tile of this round:
-            if (gw < n_tiles) issue(gw, (int)(tiles_done & 1u));
-        }
-#endif
-        for (long long tt = gw; tt < n_tiles; tt += GW) {
-            const int stage = (int)(tiles_done & 1u);
-            const uint32_t parity = (tiles_done >> 1) & 1u;
+    if (consumer) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int gl = lane % KL_G;
+        const bool structured = (*a.dstruct != 0);
+        long long wgt[32 / KL_G];
+#pragma unroll
+        for (int u = 0; u < 32 / KL_G; ++u) wgt[u] = hash_weight(d, gl + u * KL_G);
+        uint8_t* s_symw = s_sym + (size_t)warp * 4 * KL_SYM;
+        for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++tiles_done) {
             const int c = (int)(tt / tpg);
-            const long long j0 = (tt - (long long)c * tpg) * bw;
-            float2* tile = tiles[stage];
-            if constexpr (TMA) {
+            const long long j0 = (tt - (long long)c * tpg) << a.lgW;
+            uint8_t* stage = stages;
+            if (TMA) {
 #ifndef QSFT_EMU
-                // the other stage was consumed (and partly rewritten in place) one iteration ago: order those generic-proxy
-                // accesses before the bulk copy that overwrites it
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (tt + GW < n_tiles) issue(tt + GW, stage ^ 1);
-                tma::mbar_wait(&bars[stage], parity);
+                const int st = (int)(tiles_done % (unsigned)a.nstages);
+                stage = stages + (size_t)st * a.stage_bytes;
+                tma::mbar_wait(&bars[st], (tiles_done / (unsigned)a.nstages) & 1u);
 #endif
             } else {
-                // coalesced copy into the tile layout: lanes over bins (bw = 32) or over bins x two rows (bw = 16)
-                const int lbf = lane & (bw - 1), sub = lane / bw, nsub = 32 / bw;
-                const long long jf = j0 + lbf;
-                TileCol tc{tile, R, sbox8, lbf};
+                // coalesced copy into the tile layout (single stage): the previous tile's readers are done first
+                kl_consumer_barrier<TMA>();
+                const int lb = threadIdx.x & (W - 1), prt = threadIdx.x >> a.lgW, nparts = KL_CT >> a.lgW;
+                const long long jf = j0 + lb;
+                TileCol tc{stage, P_src, a.box, lb};
                 for (int r = 0; r < R; ++r) {
                     const float2* src = blk.p[c * R + r] + jf;
-                    for (int i = sub; i < P_src; i += nsub)
-                        tc.ref(r, i) = (jf < B) ? src[(size_t)i * a.ldU] : make_float2(0.f, 0.f);
+                    for (int i = prt; i < P_src; i += nparts) tc.ref(r, i) = (jf < B) ? src[(size_t)i * a.ldU] : make_float2(0.f, 0.f);
                 }
-                __syncwarp();
+                if (round > 1 && threadIdx.x < W)
+                    reinterpret_cast<int32_t*>(stage + (size_t)R * a.box)[threadIdx.x] =
+                        (j0 + threadIdx.x < B) ? __ldcg(a.head + (size_t)c * B + j0 + threadIdx.x) : 0;
+                kl_consumer_barrier<TMA>();
             }
-            ++tiles_done;
-
-            // ---- phase 1: energy per bin, ball lists ------------------------------------------------------------------
-            const int lb = lane & (bw - 1), sub = lane / bw, nsub = 32 / bw;
-            const long long j = j0 + lb;
-            const bool valid = (j < B);
-            float e = 0.f;
-            {
-                TileCol tc{tile, R, sbox8, lb};
-                for (int r = 0; r < R; ++r)
-                    for (int i = sub; i < P_src; i += nsub) {
-                        const float2 v = tc.ri(r, i);
-                        e = fmaf(v.x, v.x, fmaf(v.y, v.y, e));
-                    }
-                if (nsub == 2) e += __shfl_xor_sync(0xffffffffu, e, 16);
-            }
-            int hd = 0;
-            if (round > 1 && valid && sub == 0) hd = __ldcg(a.head + (size_t)c * B + j);
-            unsigned touched = __ballot_sync(0xffffffffu, hd != 0);
-            if (touched) {
-                // subtract the balls peeled off these bins in earlier rounds (qsft.py:223-241), 4 bins at a time
-                while (touched) {
-                    int my = -1;
-#pragma unroll
-                    for (int g = 0; g < 32 / KL_G; ++g) {
-                        const int bit = touched ? __ffs(touched) - 1 : -1;
-                        if (touched) touched &= touched - 1;
-                        if (g == grp) my = bit;
-                    }
-                    int f = __shfl_sync(0xffffffffu, hd, my >= 0 ? my : 0) - 1;
-                    if (my < 0) f = -1;
-                    TileCol tc{tile, R, sbox8, my >= 0 ? my : 0};
-                    uint8_t* kb = s_sym + grp * (2 * QSFT_MAX_N);
-                    while (__ballot_sync(0xffffffffu, f >= 0)) {
-                        if (f >= 0) {
-                            const uint4* src = reinterpret_cast<const uint4*>(a.find_k + (size_t)f * d.ld);
-                            for (int w = gl; w < d.ld / 16; w += KL_G) reinterpret_cast<uint4*>(kb)[w] = __ldcg(src + w);
-                        }
-                        __syncwarp();
-                        if (f >= 0) {
-                            uint32_t kw[NW];
-#pragma unroll
-                            for (int w = 0; w < NW; ++w) kw[w] = (4 * w < d.ld) ? reinterpret_cast<const uint32_t*>(kb)[w] : 0u;
-                            const float2 rho = __ldcg(a.find_rho + f);
-                            const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, kb, kw, structured};
-                            for (int r = 0; r < R; ++r) {
-                                const int tb = ph.base(r);
-                                for (int i = gl; i < P_src; i += KL_G) {
-                                    const float2 w = s_tw[ph.row(r, i, tb)];
-                                    float2& v = tc.ref(r, i);
-                                    v.x -= rho.x * w.x - rho.y * w.y;
-                                    v.y -= rho.x * w.y + rho.y * w.x;
-                                }
-                            }
-                            f = __ldcg(a.next + (size_t)f * d.C + c) - 1;
-                        }
-                        __syncwarp();
-                    }
-                    // energy of the updated bin
-                    float e2 = 0.f;
-                    if (my >= 0)
-                        for (int r = 0; r < R; ++r)
-                            for (int i = gl; i < P_src; i += KL_G) {
-                                const float2 v = tc.ri(r, i);
-                                e2 = fmaf(v.x, v.x, fmaf(v.y, v.y, e2));
-                            }
-                    e2 = kl_group_sum(e2);
-                    if (my >= 0 && gl == 0) s_e[my] = e2;
-                }
+            kl_tile<NW, TMA>(a, stage, c, j0, round, (int)(tiles_done & 1u), s_part, s_efix, s_symw, s_tw, structured, wgt, n_multi);
+#ifndef QSFT_EMU
+            if (TMA) {
+                // this warp is done with the stage; its in-place updates (generic proxy) are ordered before the next bulk copy
+                if (round > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (hd != 0) e = s_e[lb];
+                if (lane == 0) tma::mbar_arrive(&bars[KL_MAX_STAGES + (int)(tiles_done % (unsigned)a.nstages)]);
             }
-
-            // ---- phase 2: non-zeroton bins, four at a time ----------------------------------------------------------
-            unsigned cand = __ballot_sync(0xffffffffu, valid && sub == 0 && e > thresh);
-            while (cand) {
-                int my = -1;
-#pragma unroll
-                for (int g = 0; g < 32 / KL_G; ++g) {
-                    const int bit = cand ? __ffs(cand) - 1 : -1;
-                    if (cand) cand &= cand - 1;
-                    if (g == grp) my = bit;
-                }
-                const bool act = my >= 0;
-                const int lbm = act ? my : 0;
-                const long long jb = j0 + lbm;
-                const float e_b = __shfl_sync(0xffffffffu, e, lbm);
-                TileCol tc{tile, R, sbox8, lbm};
-                uint8_t* sym = s_sym + grp * (2 * QSFT_MAX_N);
-                uint8_t* kb = sym;
-                if (act) {
-                    for (int i = 1 + gl; i <= nsym; i += KL_G) sym[i - 1] = (uint8_t)detect_symbol(d, tc, i);
-                    for (int i = nsym + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) sym[i] = 0;
-                }
-                __syncwarp();
-                if (d.source == 1) {
-                    kb = sym + QSFT_MAX_N;
-                    if (act) {
-                        for (int i = d.n + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) kb[i] = 0;
-                        if (gl == 0) rs_decode(d, sym, kb);
-                    }
-                    __syncwarp();
-                }
-                uint32_t kw[NW];
-#pragma unroll
-                for (int w = 0; w < NW; ++w) kw[w] = reinterpret_cast<const uint32_t*>(kb)[w];
-                const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, kb, kw, structured};
-                // rho = <signature, col> / P (qsft.py:174-175)
-                float rr = 0.f, ri = 0.f;
-                if (act)
-                    for (int r = 0; r < R; ++r) {
-                        const int tb = ph.base(r);
-                        for (int i = gl; i < P_src; i += KL_G) {
-                            const float2 w = s_tw[ph.row(r, i, tb)];
-                            const float2 v = tc.ri(r, i);
-                            rr += w.x * v.x + w.y * v.y;                       // conj(sig) * v
-                            ri += w.x * v.y - w.y * v.x;
-                        }
-                    }
-                rr = kl_group_sum(rr) * (float)d.invP;
-                ri = kl_group_sum(ri) * (float)d.invP;
-                // residual ||col - rho sig||^2 (qsft.py:176,183), summed directly: every term is small for a singleton
-                float res = 0.f;
-                if (act)
-                    for (int r = 0; r < R; ++r) {
-                        const int tb = ph.base(r);
-                        for (int i = gl; i < P_src; i += KL_G) {
-                            const float2 w = s_tw[ph.row(r, i, tb)];
-                            const float2 v = tc.ri(r, i);
-                            const float dx = v.x - (rr * w.x - ri * w.y), dy = v.y - (rr * w.y + ri * w.x);
-                            res = fmaf(dx, dx, fmaf(dy, dy, res));
-                        }
-                    }
-                res = kl_group_sum(res);
-                // bin hash j = dec(M_c^T k mod q) (qsft.py:178-179)
-                long long part = 0;
-                if (act) {
-#pragma unroll
-                    for (int u = 0; u < 32 / KL_G; ++u) {
-                        const int i = gl + u * KL_G;
-                        if (i < d.b)
-                            part += wgt[u] * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + i) * d.ld, d.ld, kw), d.q, d.qmagic);
-                    }
-                }
-#pragma unroll
-                for (int o = KL_G / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                const float lim = fmaxf(thresh, a.rel_floor * e_b);
-                const bool single = act && (part == jb) && !(res > lim);
-                const bool lead = (gl == 0);
-                const unsigned sb = __ballot_sync(0xffffffffu, lead && single);
-                unsigned long long fbase = 0;
-                if (lane == 0 && sb) fbase = atomicAdd(&a.counters[0], (unsigned long long)__popc(sb));
-                fbase = __shfl_sync(0xffffffffu, fbase, 0);
-                unsigned long long f = fbase + (unsigned long long)__popc(sb & ((1u << lane) - 1u));
-                f = __shfl_sync(0xffffffffu, f, lane & ~(KL_G - 1));
-                if (single) {
-                    if ((long long)f < a.max_finds) {
-                        uint32_t* ko = reinterpret_cast<uint32_t*>(a.find_k + (size_t)f * d.ld);
-                        for (int w = gl; w < d.ld / 4; w += KL_G) ko[w] = (w < NW) ? kw[w] : 0u;
-                        if (lead) {
-                            a.find_cj[f] = (long long)c * B + jb;
-                            a.find_rho[f] = make_float2(rr, ri);
-                            a.find_round[f] = round;
-                            a.find_id[(size_t)c * B + jb] = (int32_t)f;
-                        }
-                    }
-                } else if (act && lead) {
-                    ++n_multi;
-                }
-                __syncwarp();
-            }
+#endif
         }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n_multi += __shfl_xor_sync(0xffffffffu, n_multi, o);
-    if (lane == 0 && n_multi) atomicAdd(&a.multi[round], (unsigned long long)n_multi);
+        for (int o = 16; o > 0; o >>= 1) n_multi += __shfl_xor_sync(0xffffffffu, n_multi, o);
+        if (lane == 0 && n_multi) atomicAdd(&a.multi[round], (unsigned long long)n_multi);
+    }
 }
 
 // ---- link phase: one thread per find of the round ---------------------------------------------------------------------
@@ -402,7 +491,7 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, long long f0, long long
     const PeelDev& d = a.d;
     const int nw = d.ld / 4;
     const long long B = d.B;
-    for (long long f = f0 + (long long)blockIdx.x * KL_THREADS + threadIdx.x; f < f1; f += (long long)gridDim.x * KL_THREADS) {
+    for (long long f = f0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; f < f1; f += (long long)gridDim.x * blockDim.x) {
         const long long cj = a.find_cj[f];
         const int c = (int)(cj / B);
         uint32_t kw[NW];
@@ -456,7 +545,7 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, long long f0, long long
 }
 
 template <int NW, bool TMA>
-__global__ void __launch_bounds__(KL_THREADS, 1)
+__global__ void __launch_bounds__(TMA ? KL_CT + 32 : KL_CT, 1)
 k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
 #ifndef QSFT_EMU
                     , const __grid_constant__ KlMaps maps
@@ -464,9 +553,7 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
 ) {
     extern __shared__ __align__(1024) uint8_t kl_smem[];
     __shared__ float2 s_tw[QSFT_MAX_Q + 1];
-    __shared__ __align__(8) uint64_t s_bars[2 * (KL_THREADS / 32)];
     const PeelDev& d = a.d;
-    const int warp = threadIdx.x >> 5;
     if (threadIdx.x < d.q) {
         float sn, cs;
         sincospif(2.0f * (float)threadIdx.x / (float)d.q, &sn, &cs);
@@ -481,16 +568,24 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
     }
 #ifndef QSFT_EMU
     uint8_t* base = kl_smem + ((1024u - (tma::smem_u32(kl_smem) & 1023u)) & 1023u);
-    if (TMA && threadIdx.x == 0) {
-        for (int i = 0; i < 2 * (KL_THREADS / 32); ++i) tma::mbar_init(&s_bars[i], 1);
-        tma::mbar_fence_init();
-    }
 #else
     uint8_t* base = kl_smem;
 #endif
+    uint8_t* ctrl = base + (size_t)a.nstages * a.stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);                           // full[6], empty[6]
+    float* s_part = reinterpret_cast<float*>(ctrl + 256);                         // [2][KL_CT]
+    float* s_efix = s_part + 2 * KL_CT;                                           // [2][KL_MAXW]
+    uint8_t* s_sym = reinterpret_cast<uint8_t*>(s_efix + 2 * KL_MAXW);            // [KL_CW][4][KL_SYM]
+#ifndef QSFT_EMU
+    if (TMA && threadIdx.x == 0) {
+        for (int i = 0; i < KL_MAX_STAGES; ++i) {
+            tma::mbar_init(&bars[i], 1);
+            tma::mbar_init(&bars[KL_MAX_STAGES + i], KL_CW);
+        }
+        tma::mbar_fence_init();
+    }
+#endif
     __syncthreads();
-    const int per_warp = 2 * (a.bw >> 4) * d.R * a.sbox + 4 * 2 * QSFT_MAX_N + 32 * 4;
-    uint8_t* wsm = base + (size_t)warp * ((per_warp + 1023) & ~1023);
     unsigned int epoch = 0, tiles_done = 0;
     long long total = 0;
     double num_peeling = 0;
@@ -502,7 +597,7 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
 #ifndef QSFT_EMU
                              maps.m,
 #endif
-                             round, wsm, &s_bars[2 * warp], tiles_done, s_tw);
+                             round, base, bars, tiles_done, s_part, s_efix, s_sym, s_tw);
         kl_grid_barrier(a.gbar, epoch);
         const long long now = (long long)__ldcg(a.counters + 0);
         const long long multis = (long long)__ldcg(a.multi + round);
@@ -550,6 +645,26 @@ __global__ void kl_dstruct_kernel(PeelDev d, int* flag) {
     if (threadIdx.x == 0) *flag = bad ? 0 : 1;
 }
 
+// tile geometry for a shared-memory budget: the widest tile (<= 128 bins, no wider than the group needs) that leaves at
+// least `min_stages` stages.  Returns false when even 16-bin tiles do not fit.
+inline bool kl_geometry(const PeelDev& d, int budget, int min_stages, KlArgs* a) {
+    for (int W = KL_MAXW; W >= 16; W >>= 1) {
+        if (W > 16 && (long long)(W >> 1) >= d.B) continue;
+        const int box = ((W >> 4) * d.P_src * 128 + 1023) & ~1023;
+        const long long stage = ((long long)d.R * box + W * 4 + 1023) & ~1023ll;
+        const long long n = ((long long)budget - KL_CTRL_BYTES) / stage;
+        if (n >= min_stages) {
+            a->W = W;
+            a->lgW = W == 128 ? 7 : W == 64 ? 6 : W == 32 ? 5 : 4;
+            a->box = box;
+            a->stage_bytes = (int)stage;
+            a->nstages = n > KL_MAX_STAGES ? KL_MAX_STAGES : (int)n;
+            return true;
+        }
+    }
+    return false;
+}
+
 }  // namespace (device part; the CPU emulation cuts here)
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -560,7 +675,7 @@ int kl_launch(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use
     void* params[] = {(void*)&a, (void*)&blk, (void*)&maps};
     const void* fn = use_tma ? (const void*)k4_peel_loop_kernel<NW, true> : (const void*)k4_peel_loop_kernel<NW, false>;
     QSFT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    QSFT_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(KL_THREADS), params, smem, st));
+    QSFT_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(use_tma ? KL_CT + 32 : KL_CT), params, smem, st));
     g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
     return QSFT_OK;
 }
@@ -588,48 +703,37 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
     KlArgs a{};
     a.d = d;
     a.ldU = ldU;
-    a.sbox = (d.P_src * 128 + 1023) & ~1023;
-    // tile width: 32 bins unless that leaves fewer than 4 warps per SM
-    const int fixed = 4 * 2 * QSFT_MAX_N + 32 * 4;
-    const int budget = smem_max - 2048 - 1024;
-    a.bw = 32;
-    auto per_warp = [&](int bw) { return ((2 * (bw >> 4) * d.R * a.sbox + fixed) + 1023) & ~1023; };
-    if (budget / per_warp(32) < 4) a.bw = 16;
-    a.wpc = budget / per_warp(a.bw);
-    if (a.wpc > KL_THREADS / 32) a.wpc = KL_THREADS / 32;
-    if (a.wpc < 1) return QSFT_EUNSUPPORTED;
-    const size_t smem = (size_t)a.wpc * per_warp(a.bw) + 1024;
-    const bool use_tma = (ldU % 2 == 0) && (getenv("QSFT_K4_NO_TMA") == nullptr);
+    bool use_tma = (d.B % 16 == 0) && (ldU % 2 == 0) && (getenv("QSFT_K4_NO_TMA") == nullptr);
+    for (int i = 0; i < nblk; ++i)
+        if ((uintptr_t)blocks[i] & 15) use_tma = false;
+    const int budget = smem_max - 1024 - 2048;             // alignment slack + the kernel's static shared memory
+    if (!kl_geometry(d, budget, use_tma ? 2 : 1, &a)) return QSFT_EUNSUPPORTED;
     KlBlocks blk{};
-    for (int i = 0; i < nblk; ++i) {
-        blk.p[i] = reinterpret_cast<const float2*>(blocks[i]);
-        if (use_tma && ((uintptr_t)blocks[i] & 15)) return QSFT_EUNSUPPORTED;
+    for (int i = 0; i < nblk; ++i) blk.p[i] = reinterpret_cast<const float2*>(blocks[i]);
+    KlMaps hm;
+    memset(&hm, 0, sizeof(hm));
+    for (int i = 0; i < nblk && use_tma; ++i) {
+        const cuuint64_t dims[3] = {32, (cuuint64_t)d.P_src, (cuuint64_t)(d.B / 16)};
+        const cuuint64_t strides[2] = {(cuuint64_t)ldU * 8, 128};
+        const cuuint32_t box[3] = {32, (cuuint32_t)d.P_src, (cuuint32_t)(a.W >> 4)};
+        if (tma::make_map(&hm.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, blocks[i], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) !=
+            QSFT_OK)
+            use_tma = false;                                // a shape the tensor map cannot express: plain copies instead
     }
+    if (!use_tma) a.nstages = 1;
+    const size_t smem = (size_t)a.nstages * a.stage_bytes + KL_CTRL_BYTES + 1024;
     // workspace: ball lists, grid barrier, delay-structure flag
     const size_t head_b = (size_t)d.C * d.B * 4, next_b = (size_t)max_finds * d.C * 4;
     uint8_t* ws = nullptr;
     const size_t head_off = 256, next_off = head_off + ((head_b + 255) & ~(size_t)255);
     QSFT_CUDA(qsft_scratch_alloc((void**)&ws, next_off + next_b, st));
-    QSFT_CUDA(cudaMemsetAsync(ws, 0, head_off + head_b, st));                  // barrier, flag, list heads
+    QSFT_CUDA(cudaMemsetAsync(ws, 0, head_off + head_b, st));                  // barrier, flag, round counters, list heads
     a.gbar = reinterpret_cast<unsigned int*>(ws);
     int* dflag = reinterpret_cast<int*>(ws + 64);
     a.multi = reinterpret_cast<unsigned long long*>(ws + 128);                 // 16 slots
     a.dstruct = dflag;
     a.head = reinterpret_cast<int32_t*>(ws + head_off);
     a.next = reinterpret_cast<int32_t*>(ws + next_off);
-    KlMaps hm;
-    memset(&hm, 0, sizeof(hm));
-    if (use_tma) {
-        for (int i = 0; i < nblk; ++i) {
-            const cuuint64_t dims[2] = {(cuuint64_t)(2 * d.B), (cuuint64_t)d.P_src};
-            const cuuint64_t strides[1] = {(cuuint64_t)ldU * 8};
-            const cuuint32_t box[2] = {32, (cuuint32_t)d.P_src};
-            if (int rc = tma::make_map(&hm.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, blocks[i], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) {
-                cudaFreeAsync(ws, st);
-                return rc;
-            }
-        }
-    }
     a.find_cj = (long long*)find_cj;
     a.find_k = find_k;
     a.find_rho = reinterpret_cast<float2*>(find_rho);

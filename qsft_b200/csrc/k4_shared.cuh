@@ -304,16 +304,16 @@ __device__ __forceinline__ int detect_symbol(const PeelDev& d, const Col& col, i
             symv = m < 0 ? m + d.q : m;
         }
     } else if (d.channel == 1) {
-        double ar = 0.0, ai = 0.0;
+        // fp32 first: both fast decisions below keep a safety margin far above the fp32 rounding of these sums; only a
+        // value near a decision boundary is redone in fp64 (np.mean divides by R > 0: the angle does not depend on it)
+        float arf = 0.f, aif = 0.f;
         for (int r = 0; r < d.R; ++r) {
             const float2 z = col.ri(r, 0);
             const float2 v = col.ri(r, i);
-            ar += (double)z.x * v.x + (double)z.y * v.y;                     // z * conj(v)
-            ai += (double)z.y * v.x - (double)z.x * v.y;
+            arf = fmaf(z.x, v.x, fmaf(z.y, v.y, arf));                       // z * conj(v)
+            aif = fmaf(z.y, v.x, fmaf(-z.x, v.y, aif));
         }
-        // np.mean divides by R > 0: the angle does not depend on it
         symv = -1;
-        const float arf = (float)ar, aif = (float)ai;
         if (quad) symv = quadrant_symbol(d.q, arf, aif);
         if (symv < 0 && fabsf(arf) + fabsf(aif) > 1e-30f) {
             float thf = atan2f(aif, arf);
@@ -322,6 +322,14 @@ __device__ __forceinline__ int detect_symbol(const PeelDev& d, const Col& col, i
             const float m = rintf(u);
             if (fabsf(u - m) < 0.49f) symv = ((int)m >= d.q) ? (int)m - d.q : (int)m;   // nearest of the q+1 roots, mod q
         }
+        double ar = 0.0, ai = 0.0;
+        if (symv < 0)
+            for (int r = 0; r < d.R; ++r) {
+                const float2 z = col.ri(r, 0);
+                const float2 v = col.ri(r, i);
+                ar += (double)z.x * v.x + (double)z.y * v.y;
+                ai += (double)z.y * v.x - (double)z.x * v.y;
+            }
         if (symv < 0) {
             double th = atan2(ai, ar);
             if (th < 0.0) th += kTwoPi;                                      // numpy: angle % (2 pi)

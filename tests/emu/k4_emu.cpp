@@ -44,19 +44,21 @@ void classify(const PeelDev& d, const float2* U, long long jb, long long je, lon
 }
 
 // The persistent loop kernel (k4_peel_loop.cu, plain-copy variant) as ONE block: mirrors the host side of qsft_peel_loop.
+// maxW caps the tile width (128 = the product's choice) so that the narrower tile shapes are exercised too.
 int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, float2* rho, int32_t* frd, int32_t* fid,
-              long long maxf, const UniqOut& uo, unsigned long long* counters, int bw) {
+              long long maxf, const UniqOut& uo, unsigned long long* counters, int maxW) {
     if (d.C * d.R > KL_MAX_BLOCKS || d.P_src > 256) return -3;
     KlArgs a{};
     a.d = d;
     a.ldU = d.B;
-    a.sbox = (d.P_src * 128 + 1023) & ~1023;
-    a.bw = bw;
-    const int fixed = 4 * 2 * QSFT_MAX_N + 32 * 4;
-    const int per_warp = ((2 * (bw >> 4) * d.R * a.sbox + fixed) + 1023) & ~1023;
-    a.wpc = (232 * 1024 - 4096) / per_warp;
-    if (a.wpc > KL_THREADS / 32) a.wpc = KL_THREADS / 32;
-    if (a.wpc < 1) return -3;
+    if (!kl_geometry(d, 228 * 1024, 1, &a)) return -3;
+    while (a.W > maxW) {                                       // narrower tiles on request
+        a.W >>= 1;
+        a.lgW -= 1;
+        a.box = ((a.W >> 4) * d.P_src * 128 + 1023) & ~1023;
+        a.stage_bytes = (d.R * a.box + a.W * 4 + 1023) & ~1023;
+    }
+    a.nstages = 1;
     KlBlocks blk{};
     for (int c = 0; c < d.C; ++c)
         for (int r = 0; r < d.R; ++r) blk.p[c * d.R + r] = U + ((size_t)c * d.P + (size_t)r * d.P_src) * d.B;
@@ -72,7 +74,7 @@ int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, floa
     a.guard_can_bind = a.peeling_max <= 15.0 * (double)d.C * (double)d.B ? 1 : 0;
     a.rel_floor = 1e-10f;
     const int nw = nw_of(d.ld);
-    NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_THREADS), [&]() { k4_peel_loop_kernel<NW, false>(a, blk); }));
+    NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_CT), [&]() { k4_peel_loop_kernel<NW, false>(a, blk); }));
     return 0;
 }
 
@@ -105,10 +107,10 @@ int emu_peel(int q, int n, int b, int C, int P, int P_src, int channel, int sour
     unsigned long long counters[8] = {0};
     memset(seen0, 0, (size_t)d.B * sizeof(int32_t));
     const int nw = nw_of(d.ld);
-    if (impl >= 2) {            // 2: the on-device loop with 32-bin warp tiles, 3: 16-bin tiles
+    if (impl >= 2) {            // 2: the on-device loop with the product's tile width (<= 128 bins), 3: 32-bin tiles
         UniqOut uo{seen0, uk, usum, ucnt, ukey, unext, max_uniq};
         if (int rc = peel_loop(d, reinterpret_cast<const float2*>(U), find_cj, find_k, reinterpret_cast<float2*>(find_rho), find_round,
-                               find_id, max_finds, uo, counters, impl == 2 ? 32 : 16))
+                               find_id, max_finds, uo, counters, impl == 2 ? 128 : 32))
             return rc;
         if (counters[6]) return -1;
         if ((long long)counters[4] > max_uniq) return -2;
