@@ -25,12 +25,12 @@
 
 namespace {
 
-constexpr int KT_STAGES = 3;
+constexpr int KT_MAX_STAGES = 6;                    // ring depth is a launch parameter (2 .. 6 tiles of 32 KB per CTA)
 constexpr int KT_TILE = 4096;                       // complex elements per tile
 constexpr int KT_TILE_BYTES = KT_TILE * 8;
 constexpr int KT_CONSUMERS = 256;
 constexpr int KT_THREADS = KT_CONSUMERS + 32;
-constexpr size_t KT_SMEM = 1024 + (size_t)KT_STAGES * KT_TILE_BYTES + 128;
+__host__ __device__ constexpr size_t kt_smem(int stages) { return 1024 + (size_t)stages * KT_TILE_BYTES + 256; }
 
 struct KtInfo {
     long long blk;                                   // -1: no more work
@@ -68,11 +68,12 @@ __device__ __forceinline__ void kt_r16(float2 (&v)[16]) {
 // warp would otherwise block (the next tile may depend on this very publish), or at the end.
 struct KtPending {
     unsigned int* ctr;                               // nullptr: nothing pending
+    int nofence;                                     // measurement aid only (QSFT_K3_NOFENCE=1): publish without the fence
     __device__ __forceinline__ void flush() {
         if (ctr != nullptr) {
             __syncwarp();
             if ((threadIdx.x & 31) == 0) {
-                __threadfence();
+                if (!nofence) __threadfence();
                 atomicAdd(ctr, 1u);
             }
             ctr = nullptr;
@@ -171,19 +172,19 @@ template <bool PEERS>
 __global__ void __launch_bounds__(KT_THREADS, 2)
 k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2, float2* __restrict__ x,
                  long long B, int r1, int r2, int tiles1, int tiles2, unsigned int* __restrict__ done /* [nblocks] + ticket */,
-                 long long nblocks, int lag, float scale1, float scale2, K3Peers peers) {
+                 long long nblocks, int lag, int nstages, int nofence, float scale1, float scale2, K3Peers peers) {
     extern __shared__ __align__(1024) uint8_t kt_raw[];
     uint8_t* base = kt_raw + ((1024u - (tma::smem_u32(kt_raw) & 1023u)) & 1023u);      // 1024-byte aligned (TMA swizzle atom)
-    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)KT_STAGES * KT_TILE_BYTES);
-    uint64_t* empty = full + KT_STAGES;
-    KtInfo* info = reinterpret_cast<KtInfo*>(empty + KT_STAGES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)nstages * KT_TILE_BYTES);
+    uint64_t* empty = full + KT_MAX_STAGES;
+    KtInfo* info = reinterpret_cast<KtInfo*>(empty + KT_MAX_STAGES);
     const int warp = threadIdx.x >> 5;
     const int rows = (int)(B / KT_TILE);                                     // 4096-element runs per block = 4^r2
     const int lgW = 2 * (6 - r2);
     const long long total = nblocks * ((long long)tiles1 + tiles2);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < KT_STAGES; ++i) {
+        for (int i = 0; i < nstages; ++i) {
             tma::mbar_init(&full[i], 1);
             tma::mbar_init(&empty[i], KT_CONSUMERS / 32);
         }
@@ -201,8 +202,8 @@ k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant_
             // stage is waited for, so the round trip of the atomic overlaps the wait.
             unsigned int ticket_next = atomicAdd(done + nblocks, 1u);
             for (unsigned it = 0;; ++it) {
-                const int stage = (int)(it % KT_STAGES);
-                const uint32_t ph = (it / KT_STAGES) & 1u;
+                const int stage = (int)(it % (unsigned)nstages);
+                const uint32_t ph = (it / (unsigned)nstages) & 1u;
                 const unsigned int ticket = ticket_next;
                 if ((long long)ticket < total) ticket_next = atomicAdd(done + nblocks, 1u);
                 tma::mbar_wait(&empty[stage], ph ^ 1u);
@@ -242,10 +243,10 @@ k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant_
         }
     } else {
         // ---- consumers -------------------------------------------------------------------------------------------
-        KtPending pend{nullptr};
+        KtPending pend{nullptr, nofence};
         for (unsigned it = 0;; ++it) {
-            const int stage = (int)(it % KT_STAGES);
-            const uint32_t ph = (it / KT_STAGES) & 1u;
+            const int stage = (int)(it % (unsigned)nstages);
+            const uint32_t ph = (it / (unsigned)nstages) & 1u;
             if (!tma::mbar_try_wait(&full[stage], ph)) {
                 pend.flush();                        // about to block: the producer may be waiting for this publish
                 tma::mbar_wait(&full[stage], ph);
@@ -300,12 +301,19 @@ int qsft_k3_q4_tma(float* xf, int64_t batch, int b, float* const* peer_x, int n_
     const cuuint32_t box2[3] = {32, (cuuint32_t)W16, (cuuint32_t)(r2 ? (256 / W16) : 1)};
     if (int rc = tma::make_map(&tm2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, xf, dims, strides, r2 ? box2 : box1, CU_TENSOR_MAP_SWIZZLE_128B))
         return rc;
-    static int ctas = 0;
+    // ring depth: 3 tiles per CTA, two CTAs per SM (QSFT_K3_STAGES = 2 .. 6 for measurements)
+    int nstages = 3, nofence = 0;
+    if (const char* e = getenv("QSFT_K3_STAGES"))
+        if (atoi(e) >= 2 && atoi(e) <= KT_MAX_STAGES) nstages = atoi(e);
+    if (const char* e = getenv("QSFT_K3_NOFENCE")) nofence = atoi(e) != 0;
+    static int ctas_by_stages[KT_MAX_STAGES + 1] = {0};
+    int& ctas = ctas_by_stages[nstages];
+    const size_t smem = kt_smem(nstages);
     if (ctas == 0) {
-        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT_SMEM));
-        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT_SMEM));
+        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kt_smem(KT_MAX_STAGES)));
+        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kt_smem(KT_MAX_STAGES)));
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_tma_kernel<true>, KT_THREADS, KT_SMEM) != cudaSuccess || per_sm < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_tma_kernel<true>, KT_THREADS, smem) != cudaSuccess || per_sm < 1) {
             (void)cudaGetLastError();
             per_sm = 1;
         }
@@ -318,7 +326,7 @@ int qsft_k3_q4_tma(float* xf, int64_t batch, int b, float* const* peer_x, int n_
     int lag = 1;
     if (tiles2) {
         const long long per = (long long)tiles1 + tiles2;
-        long long l = ((long long)ctas * KT_STAGES + per - 1) / per;
+        long long l = ((long long)ctas * nstages + per - 1) / per;
         const long long l2_rows = (48ll << 20) / (B * 8);
         if (l > l2_rows) l = l2_rows;
         if (l < 1) l = 1;
@@ -332,11 +340,11 @@ int qsft_k3_q4_tma(float* xf, int64_t batch, int b, float* const* peer_x, int n_
     for (int r = 0; r < 7; ++r) peers.p[r] = r < n_peers ? reinterpret_cast<float2*>(peer_x[r]) : nullptr;
     const float inv = (float)(1.0 / (double)B);
     if (n_peers > 0)
-        k3_q4_tma_kernel<true><<<grid, KT_THREADS, KT_SMEM, st>>>(tm1, tm2, reinterpret_cast<float2*>(xf), B, r1, r2, tiles1, tiles2,
-                                                                  done, (long long)batch, lag, r2 ? 1.0f : inv, inv, peers);
+        k3_q4_tma_kernel<true><<<grid, KT_THREADS, smem, st>>>(tm1, tm2, reinterpret_cast<float2*>(xf), B, r1, r2, tiles1, tiles2, done,
+                                                               (long long)batch, lag, nstages, nofence, r2 ? 1.0f : inv, inv, peers);
     else
-        k3_q4_tma_kernel<false><<<grid, KT_THREADS, KT_SMEM, st>>>(tm1, tm2, reinterpret_cast<float2*>(xf), B, r1, r2, tiles1, tiles2,
-                                                                   done, (long long)batch, lag, r2 ? 1.0f : inv, inv, peers);
+        k3_q4_tma_kernel<false><<<grid, KT_THREADS, smem, st>>>(tm1, tm2, reinterpret_cast<float2*>(xf), B, r1, r2, tiles1, tiles2, done,
+                                                                (long long)batch, lag, nstages, nofence, r2 ? 1.0f : inv, inv, peers);
     QSFT_LAUNCHED();
     QSFT_CUDA(cudaFreeAsync(done, st));
     return QSFT_OK;

@@ -34,14 +34,15 @@
 
 namespace {
 
-constexpr int KL_CW = 16;                    // consumer warps
-constexpr int KL_CT = KL_CW * 32;            // consumer threads
+constexpr int KL_NS = 4;                     // scanner warps (one bin per thread, tiles of at most 128 bins)
+constexpr int KL_NC = 12;                    // candidate warps
+constexpr int KL_CT = (KL_NS + KL_NC) * 32;  // threads without the TMA producer warp
 constexpr int KL_MAX_BLOCKS = 16;            // (c, r) blocks of U addressed separately (C * R <= 16)
 constexpr int KL_G = 8;                      // lanes per bin in the group phases
 constexpr int KL_MAXW = 128;                 // bins per tile, at most
 constexpr int KL_MAX_STAGES = 6;
 constexpr int KL_SYM = 2 * QSFT_MAX_N;       // per group: detected symbols + decoded k
-constexpr int KL_CTRL_BYTES = 256 + 2 * KL_CT * 4 + 2 * KL_MAXW * 4 + KL_CW * 4 * KL_SYM;
+constexpr int KL_CTRL_BYTES = 256 + KL_MAX_STAGES * 576 + KL_NC * 4 * KL_SYM;
 
 struct KlBlocks {
     const float2* p[KL_MAX_BLOCKS];          // block c * R + r: (P_src, ldU) complex64, bin index contiguous
@@ -129,17 +130,6 @@ __device__ __forceinline__ int kl_pick(const unsigned (&mask)[4], int rank) {
     return -1;
 }
 
-template <bool TMA>
-__device__ __forceinline__ void kl_consumer_barrier() {
-#ifndef QSFT_EMU
-    if (TMA) {
-        asm volatile("bar.sync 1, %0;" ::"n"(KL_CT) : "memory");
-        return;
-    }
-#endif
-    __syncthreads();
-}
-
 __device__ __forceinline__ void kl_grid_barrier(unsigned int* gbar, unsigned int& epoch) {
     __syncthreads();
     if (gridDim.x > 1) {
@@ -185,38 +175,75 @@ struct KlPhase {
     }
 };
 
-// ---- one tile: steps 0 .. 2 (consumer threads only, tid < KL_CT) ------------------------------------------------------
-template <int NW, bool TMA>
-__device__ __forceinline__ void kl_tile(const KlArgs& a, uint8_t* stage, int c, long long j0, int round, int par, float* s_part,
-                                        float* s_efix, uint8_t* s_symw, const float2* s_tw, bool structured,
+// Per-stage hand-over from the scanner warps to the candidate warps.
+struct KlTileInfo {
+    unsigned mask[4];                        // work items of the tile: bins that are not zerotons or carry peeled balls
+    unsigned tmask[4];                       // ... of which: bins with peeled balls (their energy is not known yet)
+    float e[KL_MAXW];                        // bin energies (bins without peeled balls)
+};
+
+// ---- scanner warps (threads 0 .. 127, one bin each): energies and the tile's work list --------------------------------
+__device__ __forceinline__ void kl_scan(const KlArgs& a, uint8_t* stage, long long j0, int round, KlTileInfo* info) {
+    const PeelDev& d = a.d;
+    const int lb = threadIdx.x, warp = lb >> 5;
+    const int R = d.R, P_src = d.P_src;
+    const bool valid = lb < a.W && j0 + lb < d.B;
+    int hd = 0;
+    if (round > 1 && valid) hd = reinterpret_cast<const int32_t*>(stage + (size_t)R * a.box)[lb];
+    float e0 = 0.f, e1 = 0.f;
+    if (valid && hd == 0) {
+        TileCol tc{stage, P_src, a.box, lb};
+        for (int r = 0; r < R; ++r) {
+            int i = 0;
+            for (; i + 1 < P_src; i += 2) {
+                const float2 v = tc.ri(r, i), w = tc.ri(r, i + 1);
+                e0 = fmaf(v.x, v.x, fmaf(v.y, v.y, e0));
+                e1 = fmaf(w.x, w.x, fmaf(w.y, w.y, e1));
+            }
+            if (i < P_src) {
+                const float2 v = tc.ri(r, i);
+                e0 = fmaf(v.x, v.x, fmaf(v.y, v.y, e0));
+            }
+        }
+    }
+    const float e = e0 + e1;
+    if (lb < KL_MAXW) info->e[lb] = e;
+    const unsigned m = __ballot_sync(0xffffffffu, valid && (hd != 0 || e > (float)d.thresh));
+    const unsigned t = __ballot_sync(0xffffffffu, hd != 0);
+    if ((lb & 31) == 0) {
+        info->mask[warp] = m;
+        info->tmask[warp] = t;
+    }
+}
+
+// ---- candidate warps (cw = 0 .. KL_NC - 1): this warp's share of the tile's work items, four at a time ------------------
+template <int NW>
+__device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const KlTileInfo* info, int c, long long j0, int round,
+                                        int slot, uint8_t* s_symw, const float2* s_tw, bool structured,
                                         const long long (&wgt)[32 / KL_G], unsigned& n_multi) {
     const PeelDev& d = a.d;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lane = threadIdx.x & 31;
     const int grp = lane / KL_G, gl = lane % KL_G;
-    const int W = a.W, R = d.R, P_src = d.P_src;
+    const int R = d.R, P_src = d.P_src;
     const long long B = d.B;
     const int32_t* s_head = reinterpret_cast<const int32_t*>(stage + (size_t)R * a.box);
-    float* part = s_part + par * KL_CT;
-    float* efix = s_efix + par * KL_MAXW;
     const float thresh = (float)d.thresh;
     const int nsym = P_src - 1;
     uint8_t* sym = s_symw + grp * KL_SYM;
-
-    // ---- step 0: bins with peeled balls (qsft.py:223-241 applied to the shared-memory copy) ------------------------------
-    unsigned tmask[4] = {0u, 0u, 0u, 0u};
-    if (round > 1) {
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const int lb = w * 32 + lane;
-            const bool on = lb < W && j0 + lb < B && s_head[lb] != 0;
-            tmask[w] = __ballot_sync(0xffffffffu, on);
-        }
-        const int total = __popc(tmask[0]) + __popc(tmask[1]) + __popc(tmask[2]) + __popc(tmask[3]);
-        for (int base = 4 * warp; base < total; base += 4 * KL_CW) {
-            const int rank = base + grp;
-            const int my = rank < total ? kl_pick(tmask, rank) : -1;
-            int f = my >= 0 ? s_head[my] - 1 : -1;
-            TileCol tc{stage, P_src, a.box, my >= 0 ? my : 0};
+    const unsigned mask[4] = {info->mask[0], info->mask[1], info->mask[2], info->mask[3]};
+    const int total = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
+    for (int base = 4 * slot; base < total; base += 4 * KL_NC) {
+        const int rank = base + grp;
+        const int my = rank < total ? kl_pick(mask, rank) : -1;
+        bool act = my >= 0;
+        const int lbm = act ? my : 0;
+        const long long jb = j0 + lbm;
+        TileCol tc{stage, P_src, a.box, lbm};
+        float e_b = info->e[lbm];
+        // bins with peeled balls (qsft.py:223-241 applied to the shared-memory copy), then their energy
+        const bool touched = act && round > 1 && ((info->tmask[lbm >> 5] >> (lbm & 31)) & 1u);
+        if (round > 1 && __ballot_sync(0xffffffffu, touched)) {
+            int f = touched ? s_head[lbm] - 1 : -1;
             while (__ballot_sync(0xffffffffu, f >= 0)) {
                 if (f >= 0) {
                     const uint4* src = reinterpret_cast<const uint4*>(a.find_k + (size_t)f * d.ld);
@@ -242,68 +269,19 @@ __device__ __forceinline__ void kl_tile(const KlArgs& a, uint8_t* stage, int c, 
                 }
                 __syncwarp();
             }
-            // energy of the updated bin
             float e2 = 0.f;
-            if (my >= 0)
+            if (touched)
                 for (int r = 0; r < R; ++r)
                     for (int i = gl; i < P_src; i += KL_G) {
                         const float2 v = tc.ri(r, i);
                         e2 = fmaf(v.x, v.x, fmaf(v.y, v.y, e2));
                     }
             e2 = kl_group_sum(e2);
-            if (my >= 0 && gl == 0) efix[my] = e2;
-        }
-    }
-
-    // ---- step 1: energy partials, thread = (row slice, bin) -------------------------------------------------------------
-    {
-        const int lb = tid & (W - 1), prt = tid >> a.lgW, nparts = KL_CT >> a.lgW;
-        TileCol tc{stage, P_src, a.box, lb};
-        float e = 0.f;
-        for (int r = 0; r < R; ++r)
-            for (int i = prt; i < P_src; i += nparts) {
-                const float2 v = tc.ri(r, i);
-                e = fmaf(v.x, v.x, fmaf(v.y, v.y, e));
+            if (touched) {
+                e_b = e2;
+                act = e2 > thresh;                                  // energy test (qsft.py:164)
             }
-        part[tid] = e;
-    }
-    kl_consumer_barrier<TMA>();
-
-    // ---- step 2: candidate masks (every warp), then this warp's share of the non-zeroton bins ----------------------------
-    unsigned cmask[4] = {0u, 0u, 0u, 0u};
-    float ew[4] = {0.f, 0.f, 0.f, 0.f};
-    {
-        const int nparts = KL_CT >> a.lgW;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const int lb = w * 32 + lane;
-            const bool valid = lb < W && j0 + lb < B;
-            float e = 0.f;
-            if (valid) {
-                if ((tmask[w] >> lane) & 1u) {
-                    e = efix[lb];
-                } else {
-                    for (int p = 0; p < nparts; ++p) e += part[p * W + lb];
-                }
-            }
-            ew[w] = e;
-            cmask[w] = __ballot_sync(0xffffffffu, valid && e > thresh);
         }
-    }
-    const int total = __popc(cmask[0]) + __popc(cmask[1]) + __popc(cmask[2]) + __popc(cmask[3]);
-    for (int base = 4 * warp; base < total; base += 4 * KL_CW) {
-        const int rank = base + grp;
-        const int my = rank < total ? kl_pick(cmask, rank) : -1;
-        const bool act = my >= 0;
-        const int lbm = act ? my : 0;
-        const long long jb = j0 + lbm;
-        float e_b = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const float v = __shfl_sync(0xffffffffu, ew[w], lbm & 31);
-            if ((lbm >> 5) == w) e_b = v;
-        }
-        TileCol tc{stage, P_src, a.box, lbm};
         uint8_t* kb = sym;
         if (act) {
             for (int i = 1 + gl; i <= nsym; i += KL_G) sym[i - 1] = (uint8_t)detect_symbol(d, tc, i);
@@ -394,95 +372,123 @@ __device__ __forceinline__ void kl_tile(const KlArgs& a, uint8_t* stage, int c, 
 }
 
 // ---- one classification round ---------------------------------------------------------------------------------------
+// TMA variant: warp roles -- KL_NS scanner warps (threads 0 .. 127), KL_NC candidate warps, 1 producer warp -- coupled only
+// through the stages' mbarriers (full: tile landed; scanned: work list ready; empty: every candidate warp is done), so the
+// streaming scan of the next tiles overlaps the latency-bound candidate work of the previous ones.
+// Plain variant: the same two functions separated by CTA barriers, single stage.
 template <int NW, bool TMA>
 __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk,
 #ifndef QSFT_EMU
                                             const CUtensorMap* maps,
 #endif
-                                            int round, uint8_t* stages, uint64_t* bars, unsigned int& tiles_done, float* s_part,
-                                            float* s_efix, uint8_t* s_sym, const float2* s_tw) {
+                                            int round, uint8_t* stages, uint64_t* bars, unsigned int& tiles_done, KlTileInfo* infos,
+                                            uint8_t* s_sym, const float2* s_tw) {
     const PeelDev& d = a.d;
     const int W = a.W, R = d.R, P_src = d.P_src;
     const long long B = d.B;
     const long long tpg = (B + W - 1) >> a.lgW;                    // tiles per group
     const long long n_tiles = tpg * d.C;
-    const bool consumer = threadIdx.x < KL_CT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long mine = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     unsigned n_multi = 0;
+    const bool is_cand = warp >= KL_NS && warp < KL_NS + KL_NC;
+    bool structured = false;
+    long long wgt[32 / KL_G] = {0, 0, 0, 0};
+    if (is_cand) {
+        structured = (*a.dstruct != 0);
+#pragma unroll
+        for (int u = 0; u < 32 / KL_G; ++u) wgt[u] = hash_weight(d, (lane % KL_G) + u * KL_G);
+    }
+    uint8_t* s_symw = s_sym + (size_t)(is_cand ? warp - KL_NS : 0) * 4 * KL_SYM;
 #ifndef QSFT_EMU
-    if (TMA && !consumer) {
-        // ---- producer warp ------------------------------------------------------------------------------------------
-        if (threadIdx.x == KL_CT) {
-            uint64_t* full = bars;
-            uint64_t* empty = bars + KL_MAX_STAGES;
-            unsigned int it = tiles_done;
-            const uint32_t box_bytes = (uint32_t)((W >> 4) * P_src * 128);
+    if (TMA) {
+        uint64_t* full = bars;
+        uint64_t* empty = bars + KL_MAX_STAGES;
+        uint64_t* scanned = bars + 2 * KL_MAX_STAGES;
+        unsigned int it = tiles_done;
+        if (warp == KL_NS + KL_NC) {
+            // ---- producer warp --------------------------------------------------------------------------------------
+            if (lane == 0) {
+                const uint32_t box_bytes = (uint32_t)((W >> 4) * P_src * 128);
+                for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++it) {
+                    const int st = (int)(it % (unsigned)a.nstages);
+                    const uint32_t ph = (it / (unsigned)a.nstages) & 1u;
+                    tma::mbar_wait(&empty[st], ph ^ 1u);
+                    const int c = (int)(tt / tpg);
+                    const long long j0 = (tt - (long long)c * tpg) << a.lgW;
+                    uint8_t* dst = stages + (size_t)st * a.stage_bytes;
+                    const long long left = B - j0;
+                    const uint32_t head_bytes = round > 1 ? (uint32_t)((left < W ? left : W) * 4) : 0u;
+                    tma::mbar_expect_tx(&full[st], (uint32_t)R * box_bytes + head_bytes);
+                    for (int r = 0; r < R; ++r)
+                        tma::load_3d(dst + (size_t)r * a.box, &maps[c * R + r], 0, 0, (int)(j0 >> 4), &full[st]);
+                    if (head_bytes) tma::bulk_g2s(dst + (size_t)R * a.box, a.head + (size_t)c * B + j0, head_bytes, &full[st]);
+                }
+            }
+        } else if (warp < KL_NS) {
+            // ---- scanner warps --------------------------------------------------------------------------------------
             for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++it) {
                 const int st = (int)(it % (unsigned)a.nstages);
                 const uint32_t ph = (it / (unsigned)a.nstages) & 1u;
-                tma::mbar_wait(&empty[st], ph ^ 1u);
                 const int c = (int)(tt / tpg);
                 const long long j0 = (tt - (long long)c * tpg) << a.lgW;
-                uint8_t* dst = stages + (size_t)st * a.stage_bytes;
-                const long long left = B - j0;
-                const uint32_t head_bytes = round > 1 ? (uint32_t)((left < W ? left : W) * 4) : 0u;
-                tma::mbar_expect_tx(&full[st], (uint32_t)R * box_bytes + head_bytes);
-                for (int r = 0; r < R; ++r) tma::load_3d(dst + (size_t)r * a.box, &maps[c * R + r], 0, 0, (int)(j0 >> 4), &full[st]);
-                if (head_bytes) tma::bulk_g2s(dst + (size_t)R * a.box, a.head + (size_t)c * B + j0, head_bytes, &full[st]);
+                tma::mbar_wait(&full[st], ph);
+                kl_scan(a, stages + (size_t)st * a.stage_bytes, j0, round, &infos[st]);
+                __syncwarp();
+                if (lane == 0) tma::mbar_arrive(&scanned[st]);
+            }
+        } else {
+            // ---- candidate warps ------------------------------------------------------------------------------------
+            const int cw = warp - KL_NS;
+            for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++it) {
+                const int st = (int)(it % (unsigned)a.nstages);
+                const uint32_t ph = (it / (unsigned)a.nstages) & 1u;
+                const int c = (int)(tt / tpg);
+                const long long j0 = (tt - (long long)c * tpg) << a.lgW;
+                tma::mbar_wait(&scanned[st], ph);
+                tma::mbar_wait(&full[st], ph);                     // already complete: makes the bulk copies visible here too
+                kl_cand<NW>(a, stages + (size_t)st * a.stage_bytes, &infos[st], c, j0, round, (int)((cw + 5u * it) % (unsigned)KL_NC),
+                            s_symw, s_tw, structured, wgt, n_multi);
+                // this warp is done with the stage; its in-place updates (generic proxy) are ordered before the next bulk copy
+                if (round > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tma::mbar_arrive(&empty[st]);
             }
         }
-        // every producer and consumer advances by the same number of tiles
-        const long long mine = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         tiles_done += (unsigned int)mine;
-        return;
     }
 #endif
-    if (consumer) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int gl = lane % KL_G;
-        const bool structured = (*a.dstruct != 0);
-        long long wgt[32 / KL_G];
-#pragma unroll
-        for (int u = 0; u < 32 / KL_G; ++u) wgt[u] = hash_weight(d, gl + u * KL_G);
-        uint8_t* s_symw = s_sym + (size_t)warp * 4 * KL_SYM;
-        for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++tiles_done) {
+    if (!TMA) {
+        unsigned int it = tiles_done;
+        for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++it) {
             const int c = (int)(tt / tpg);
             const long long j0 = (tt - (long long)c * tpg) << a.lgW;
-            uint8_t* stage = stages;
-            if (TMA) {
-#ifndef QSFT_EMU
-                const int st = (int)(tiles_done % (unsigned)a.nstages);
-                stage = stages + (size_t)st * a.stage_bytes;
-                tma::mbar_wait(&bars[st], (tiles_done / (unsigned)a.nstages) & 1u);
-#endif
-            } else {
-                // coalesced copy into the tile layout (single stage): the previous tile's readers are done first
-                kl_consumer_barrier<TMA>();
-                const int lb = threadIdx.x & (W - 1), prt = threadIdx.x >> a.lgW, nparts = KL_CT >> a.lgW;
+            // coalesced copy into the tile layout (single stage): the previous tile's readers are done first
+            __syncthreads();
+            {
+                const int lb = threadIdx.x & (W - 1), prt = threadIdx.x >> a.lgW, nparts = (int)blockDim.x >> a.lgW;
                 const long long jf = j0 + lb;
-                TileCol tc{stage, P_src, a.box, lb};
+                TileCol tc{stages, P_src, a.box, lb};
                 for (int r = 0; r < R; ++r) {
                     const float2* src = blk.p[c * R + r] + jf;
                     for (int i = prt; i < P_src; i += nparts) tc.ref(r, i) = (jf < B) ? src[(size_t)i * a.ldU] : make_float2(0.f, 0.f);
                 }
                 if (round > 1 && threadIdx.x < W)
-                    reinterpret_cast<int32_t*>(stage + (size_t)R * a.box)[threadIdx.x] =
+                    reinterpret_cast<int32_t*>(stages + (size_t)R * a.box)[threadIdx.x] =
                         (j0 + threadIdx.x < B) ? __ldcg(a.head + (size_t)c * B + j0 + threadIdx.x) : 0;
-                kl_consumer_barrier<TMA>();
             }
-            kl_tile<NW, TMA>(a, stage, c, j0, round, (int)(tiles_done & 1u), s_part, s_efix, s_symw, s_tw, structured, wgt, n_multi);
-#ifndef QSFT_EMU
-            if (TMA) {
-                // this warp is done with the stage; its in-place updates (generic proxy) are ordered before the next bulk copy
-                if (round > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) tma::mbar_arrive(&bars[KL_MAX_STAGES + (int)(tiles_done % (unsigned)a.nstages)]);
-            }
-#endif
+            __syncthreads();
+            if (warp < KL_NS) kl_scan(a, stages, j0, round, &infos[0]);
+            __syncthreads();
+            if (is_cand)
+                kl_cand<NW>(a, stages, &infos[0], c, j0, round, (int)((warp - KL_NS + 5u * it) % (unsigned)KL_NC), s_symw, s_tw,
+                            structured, wgt, n_multi);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n_multi += __shfl_xor_sync(0xffffffffu, n_multi, o);
-        if (lane == 0 && n_multi) atomicAdd(&a.multi[round], (unsigned long long)n_multi);
+        tiles_done += (unsigned int)mine;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_multi += __shfl_xor_sync(0xffffffffu, n_multi, o);
+    if (lane == 0 && n_multi) atomicAdd(&a.multi[round], (unsigned long long)n_multi);
 }
 
 // ---- link phase: one thread per find of the round ---------------------------------------------------------------------
@@ -572,15 +578,15 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
     uint8_t* base = kl_smem;
 #endif
     uint8_t* ctrl = base + (size_t)a.nstages * a.stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);                           // full[6], empty[6]
-    float* s_part = reinterpret_cast<float*>(ctrl + 256);                         // [2][KL_CT]
-    float* s_efix = s_part + 2 * KL_CT;                                           // [2][KL_MAXW]
-    uint8_t* s_sym = reinterpret_cast<uint8_t*>(s_efix + 2 * KL_MAXW);            // [KL_CW][4][KL_SYM]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);                           // full[6], empty[6], scanned[6]
+    KlTileInfo* infos = reinterpret_cast<KlTileInfo*>(ctrl + 256);                // [KL_MAX_STAGES], 576 bytes apart
+    uint8_t* s_sym = ctrl + 256 + KL_MAX_STAGES * 576;                            // [KL_NC][4][KL_SYM]
 #ifndef QSFT_EMU
     if (TMA && threadIdx.x == 0) {
         for (int i = 0; i < KL_MAX_STAGES; ++i) {
             tma::mbar_init(&bars[i], 1);
-            tma::mbar_init(&bars[KL_MAX_STAGES + i], KL_CW);
+            tma::mbar_init(&bars[KL_MAX_STAGES + i], KL_NC);
+            tma::mbar_init(&bars[2 * KL_MAX_STAGES + i], KL_NS);
         }
         tma::mbar_fence_init();
     }
@@ -597,7 +603,7 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
 #ifndef QSFT_EMU
                              maps.m,
 #endif
-                             round, base, bars, tiles_done, s_part, s_efix, s_sym, s_tw);
+                             round, base, bars, tiles_done, infos, s_sym, s_tw);
         kl_grid_barrier(a.gbar, epoch);
         const long long now = (long long)__ldcg(a.counters + 0);
         const long long multis = (long long)__ldcg(a.multi + round);

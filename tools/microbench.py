@@ -42,6 +42,18 @@ x = torch.randn((P, B, 2), device=dev).view(torch.float32)
 xc = torch.view_as_complex(x.view(P, B, 2))
 ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
 out["k3_gwht 41 x 4^10"] = {"ms": ms, "GBps_algorithmic(16B/elem)": 16 * P * B / ms / 1e6, "frac": 16 * P * B / ms / 1e6 / peak}
+if "k3sweep" in ONLY:                       # ring depth / fence cost of the TMA pipeline, and the register-staged kernels, same box
+    for st in ("2", "3", "4", "5", "6"):
+        for nf in ("0", "1"):
+            os.environ["QSFT_K3_STAGES"], os.environ["QSFT_K3_NOFENCE"] = st, nf
+            ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
+            out[f"k3_gwht 41 x 4^10, stages={st} nofence={nf}"] = {"ms": ms, "frac": 16 * P * B / ms / 1e6 / peak}
+    os.environ.pop("QSFT_K3_STAGES")
+    os.environ.pop("QSFT_K3_NOFENCE")
+    os.environ["QSFT_K3_IMPL"] = "1"
+    ms = timeit(lambda: ops.gwht_batch_(xc, q, b), flush=flush)
+    out["k3_gwht 41 x 4^10, register-staged kernels (QSFT_K3_IMPL=1)"] = {"ms": ms, "frac": 16 * P * B / ms / 1e6 / peak}
+    os.environ.pop("QSFT_K3_IMPL")
 for bb, rows in ([(7, 1024), (8, 512), (9, 128), (6, 4096), (12, 4)] if "k3" in ONLY else []):
     y = torch.view_as_complex(torch.randn((rows, q ** bb, 2), device=dev))
     ms = timeit(lambda: ops.gwht_batch_(y, q, bb), flush=flush)
