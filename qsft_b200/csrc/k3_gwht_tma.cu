@@ -7,7 +7,7 @@
 // `lag` blocks ahead of the strided pass (k3_ticket_decode, k3_shared.cuh), so the intermediate is consumed from L2 and
 // DRAM sees one read and one write of the data.
 //
-// CTA = 1 producer warp + 8 consumer warps, two CTAs per SM, ring of 3 x 32 KB tiles per CTA:
+// CTA = 1 producer warp + 8 consumer warps, two CTAs per SM, ring of 2 x 32 KB tiles per CTA:
 //   producer   fetches a ticket, waits for the tile's dependencies (strided tiles: the per-block counter of finished
 //              contiguous tiles), and issues ONE cp.async.bulk.tensor per tile.  Both tile shapes are boxes of the same 3-D
 //              view {16 elements = 128 B, 256 chunks, batch * B / 4096 runs} of the buffer and land in shared memory as
@@ -301,8 +301,9 @@ int qsft_k3_q4_tma(float* xf, int64_t batch, int b, float* const* peer_x, int n_
     const cuuint32_t box2[3] = {32, (cuuint32_t)W16, (cuuint32_t)(r2 ? (256 / W16) : 1)};
     if (int rc = tma::make_map(&tm2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, xf, dims, strides, r2 ? box2 : box1, CU_TENSOR_MAP_SWIZZLE_128B))
         return rc;
-    // ring depth: 3 tiles per CTA, two CTAs per SM (QSFT_K3_STAGES = 2 .. 6 for measurements)
-    int nstages = 3, nofence = 0;
+    // ring depth: 2 tiles per CTA, two CTAs per SM measured best (r2c sweep: 0.258 ms for 41 x 4^10 against 0.275 / 0.286 ms
+    // with 3 / 4 stages; QSFT_K3_STAGES = 2 .. 6 for measurements)
+    int nstages = 2, nofence = 0;
     if (const char* e = getenv("QSFT_K3_STAGES"))
         if (atoi(e) >= 2 && atoi(e) <= KT_MAX_STAGES) nstages = atoi(e);
     if (const char* e = getenv("QSFT_K3_NOFENCE")) nofence = atoi(e) != 0;

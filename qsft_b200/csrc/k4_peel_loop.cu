@@ -1,692 +1,13 @@
-// K4, default path: the whole peeling loop of QSFT.transform (qsft/qsft.py:151-255) in ONE persistent cooperative kernel --
-// classification rounds, the reference's stop rule, duplicate averaging and "peeling" all run on the device, with two grid
-// barriers per round and no host round trip.
-//
-// U is NEVER modified.  The reference subtracts every peeled ball from the bins it hashes to (qsft.py:223-241); here a peeled
-// ball is LINKED into the (short) list of each of those bins instead (one atomic exchange per group), and a classification
-// round subtracts the listed balls from its shared-memory copy of the bin before it looks at it.  That replaces
-// 2 * C * P float atomics per ball on DRAM-resident data by C pointer swaps, needs no private copy of U, and every round
-// starts from the original samples (no accumulated rounding).
-//
-// Classification of one round: the CTA walks over tiles of W bins (W = 128 .. 16) x all P delay rows of one group:
-//   * TMA variant (q^b a multiple of 16): 1 producer warp + 16 consumer warps, ring of 2 .. 6 stages.  A tile is ONE
-//     cp.async.bulk.tensor box {16 bins = 128 B, P_src rows, W / 16 chunks} per repeat block (every delay row contributes
-//     W * 8 contiguous bytes) and lands as [chunk][row][128 B] with the 128-byte swizzle, so that both access patterns are
-//     free of bank conflicts: lanes over bins (energy scan) and lanes over delay rows (detection, rho, residual).  The
-//     bins' ball-list heads travel with the tile (cp.async.bulk).
-//   * plain variant (odd q^b, tiny q^b; also what the CPU emulation of tests/emu runs): the 16 consumer warps copy the tile
-//     with coalesced loads into the same layout, single stage.
-//   Step 0 (rounds > 1): bins with listed balls are updated in place by 8-lane groups.  Step 1: energies, 512 threads over
-//   W bins x row slices.  One CTA barrier.  Step 2: every warp rebuilds the tile's candidate mask and takes its share of the
-//   non-zeroton bins, four at a time by 8-lane groups: symbols (reconstruct.py:12-31,100-129), optional Reed-Solomon decode,
-//   rho and residual in ONE pass over the rows (qsft.py:174-183), bin hash check (qsft.py:178-179).
-// Link phase of a round: one thread per find: duplicate gathering / averaging exactly like k4_reduce_kernel, and the
-// "last (i, j) wins" find of every k (qsft.py:215) links the ball into its C bins.
-#include "common.cuh"
+// K4, default path: host side of the persistent on-device peel loop (kernels: k4_peel_loop.cuh, instantiated per digit-word
+// count NW in k4_peel_loop_nw8.cu / _nw16.cu / _nw32.cu so that the translation units compile in parallel).
+#include "k4_peel_loop.cuh"
 
-#include <stdlib.h>
-#include <string.h>
-
-#include "k4_shared.cuh"
-#ifndef QSFT_EMU
-#include "tma.cuh"
-#endif
-
-namespace {
-
-constexpr int KL_NS = 4;                     // scanner warps (one bin per thread, tiles of at most 128 bins)
-constexpr int KL_NC = 12;                    // candidate warps
-constexpr int KL_CT = (KL_NS + KL_NC) * 32;  // threads without the TMA producer warp
-constexpr int KL_MAX_BLOCKS = 16;            // (c, r) blocks of U addressed separately (C * R <= 16)
-constexpr int KL_G = 8;                      // lanes per bin in the group phases
-constexpr int KL_MAXW = 128;                 // bins per tile, at most
-constexpr int KL_MAX_STAGES = 6;
-constexpr int KL_SYM = 2 * QSFT_MAX_N;       // per group: detected symbols + decoded k
-constexpr int KL_CTRL_BYTES = 256 + KL_MAX_STAGES * 576 + KL_NC * 4 * KL_SYM;
-
-struct KlBlocks {
-    const float2* p[KL_MAX_BLOCKS];          // block c * R + r: (P_src, ldU) complex64, bin index contiguous
-};
-#ifndef QSFT_EMU
-struct KlMaps {
-    CUtensorMap m[KL_MAX_BLOCKS];            // the same blocks as 3-D tensors {32 floats, P_src rows, B / 16 chunks}
-};
-#endif
-
-struct KlArgs {
-    PeelDev d;
-    long long ldU;                           // row stride of every block (elements)
-    long long* find_cj;
-    int8_t* find_k;
-    float2* find_rho;
-    int32_t* find_round;
-    int32_t* find_id;                        // (C, B): written for singletons only; validated through find_cj
-    long long max_finds;
-    int32_t* head;                           // (C, B): last ball linked into the bin + 1 (0 = none); zeroed by the host
-    int32_t* next;                           // (max_finds, C): previous ball of the same bin + 1
-    UniqOut uo;
-    int has_uniq;
-    unsigned long long* counters;            // [0] finds, [2] balls peeled, [4] distinct k, [5] rounds, [6] error flags,
-                                             // [7] finds kept
-    unsigned long long* multi;               // [r] multitons of round r (1 <= r <= 15; workspace, zeroed by the host)
-    unsigned int* gbar;                      // grid barrier counter (zeroed by the host)
-    const int* dstruct;                      // device flag: D[c][r][i] = D[c][r][0] - e_{i-1} (identity / nso delays)
-    int W, lgW;                              // bins per tile (power of two, 16 .. 128)
-    int box;                                 // bytes per repeat block of a tile: (W / 16) * P_src * 128 rounded up to 1024
-    int stage_bytes;                         // R * box + list heads, rounded up to 1024
-    int nstages;
-    int max_rounds;
-    int guard_can_bind;
-    double peeling_max;
-    float rel_floor;                         // residual floor relative to the bin energy (fp32 resolution of U)
-};
-
-// ---- tile access -------------------------------------------------------------------------------------------------
-// stage = [repeat r][chunk ch (16 bins)][row i][128 B: 16 bins, 16-byte chunks xor-swizzled with the line index & 7]
-struct TileCol {
-    uint8_t* t;
-    int P_src, box;
-    int lb;                                  // local bin
-    __device__ __forceinline__ int off(int r, int i) const {
-        const int line = (lb >> 4) * P_src + i;
-        return r * box + line * 128 + (((((lb & 15) >> 1) ^ (line & 7)) << 4) | ((lb & 1) << 3));
-    }
-    __device__ __forceinline__ float2 ri(int r, int i) const { return *reinterpret_cast<const float2*>(t + off(r, i)); }
-    __device__ __forceinline__ float2& ref(int r, int i) const { return *reinterpret_cast<float2*>(t + off(r, i)); }
-};
-
-__device__ __forceinline__ float kl_group_sum(float v) {
-#pragma unroll
-    for (int o = KL_G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// position of the n-th (0-based) set bit of m; n < popc(m)
-__device__ __forceinline__ int kl_nth_bit(unsigned m, int n) {
-    int pos = 0;
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-        const unsigned low = m & ((1u << s) - 1u);
-        const int c = __popc(low);
-        if (n >= c) {
-            n -= c;
-            m >>= s;
-            pos += s;
-        } else {
-            m = low;
-        }
-    }
-    return pos;
-}
-
-// local bin of rank `rank` in the tile's masks (4 words of 32 bins), -1 when rank >= total
-__device__ __forceinline__ int kl_pick(const unsigned (&mask)[4], int rank) {
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        const int c = __popc(mask[w]);
-        if (rank >= 0 && rank < c) return w * 32 + kl_nth_bit(mask[w], rank);
-        rank -= c;
-    }
-    return -1;
-}
-
-__device__ __forceinline__ void kl_grid_barrier(unsigned int* gbar, unsigned int& epoch) {
-    __syncthreads();
-    if (gridDim.x > 1) {
-        if (threadIdx.x == 0) {
-            ++epoch;
-            __threadfence();
-            atomicAdd(gbar, 1u);
-            const unsigned int target = epoch * gridDim.x;
-#ifndef QSFT_EMU
-            unsigned int seen;
-            for (;;) {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(gbar) : "memory");
-                if (seen >= target) break;
-                __nanosleep(32);
-            }
-#else
-            (void)target;
-#endif
-            __threadfence();
-        }
-        __syncthreads();
-    }
-}
-
-// phase t = <D[c][r * P_src + i], k> mod q for the k whose digits sit in kb (bytes) / kw (words)
-template <int NW>
-struct KlPhase {
-    const PeelDev& d;
-    const int8_t* Dc;                         // D rows of group c
-    const uint8_t* kb;
-    const uint32_t (&kw)[NW];
-    bool structured;
-    __device__ __forceinline__ int base(int r) const {            // phase of row (r, 0)
-        return fast_mod(dot_raw<NW>(Dc + (size_t)(r * d.P_src) * d.ld, d.ld, kw), d.q, d.qmagic);
-    }
-    __device__ __forceinline__ int row(int r, int i, int tbase) const {
-        if (i == 0) return tbase;
-        if (structured) {
-            const int t = tbase - (int)kb[i - 1];
-            return t < 0 ? t + d.q : t;
-        }
-        return fast_mod(dot_raw<NW>(Dc + (size_t)(r * d.P_src + i) * d.ld, d.ld, kw), d.q, d.qmagic);
-    }
-};
-
-// Per-stage hand-over from the scanner warps to the candidate warps.
-struct KlTileInfo {
-    unsigned mask[4];                        // work items of the tile: bins that are not zerotons or carry peeled balls
-    unsigned tmask[4];                       // ... of which: bins with peeled balls (their energy is not known yet)
-    float e[KL_MAXW];                        // bin energies (bins without peeled balls)
-};
-
-// ---- scanner warps (threads 0 .. 127, one bin each): energies and the tile's work list --------------------------------
-__device__ __forceinline__ void kl_scan(const KlArgs& a, uint8_t* stage, long long j0, int round, KlTileInfo* info) {
-    const PeelDev& d = a.d;
-    const int lb = threadIdx.x, warp = lb >> 5;
-    const int R = d.R, P_src = d.P_src;
-    const bool valid = lb < a.W && j0 + lb < d.B;
-    int hd = 0;
-    if (round > 1 && valid) hd = reinterpret_cast<const int32_t*>(stage + (size_t)R * a.box)[lb];
-    float e0 = 0.f, e1 = 0.f;
-    if (valid && hd == 0) {
-        TileCol tc{stage, P_src, a.box, lb};
-        for (int r = 0; r < R; ++r) {
-            int i = 0;
-            for (; i + 1 < P_src; i += 2) {
-                const float2 v = tc.ri(r, i), w = tc.ri(r, i + 1);
-                e0 = fmaf(v.x, v.x, fmaf(v.y, v.y, e0));
-                e1 = fmaf(w.x, w.x, fmaf(w.y, w.y, e1));
-            }
-            if (i < P_src) {
-                const float2 v = tc.ri(r, i);
-                e0 = fmaf(v.x, v.x, fmaf(v.y, v.y, e0));
-            }
-        }
-    }
-    const float e = e0 + e1;
-    if (lb < KL_MAXW) info->e[lb] = e;
-    const unsigned m = __ballot_sync(0xffffffffu, valid && (hd != 0 || e > (float)d.thresh));
-    const unsigned t = __ballot_sync(0xffffffffu, hd != 0);
-    if ((lb & 31) == 0) {
-        info->mask[warp] = m;
-        info->tmask[warp] = t;
-    }
-}
-
-// ---- candidate warps (cw = 0 .. KL_NC - 1): this warp's share of the tile's work items, four at a time ------------------
-template <int NW>
-__device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const KlTileInfo* info, int c, long long j0, int round,
-                                        int slot, uint8_t* s_symw, const float2* s_tw, bool structured,
-                                        const long long (&wgt)[32 / KL_G], unsigned& n_multi) {
-    const PeelDev& d = a.d;
-    const int lane = threadIdx.x & 31;
-    const int grp = lane / KL_G, gl = lane % KL_G;
-    const int R = d.R, P_src = d.P_src;
-    const long long B = d.B;
-    const int32_t* s_head = reinterpret_cast<const int32_t*>(stage + (size_t)R * a.box);
-    const float thresh = (float)d.thresh;
-    const int nsym = P_src - 1;
-    uint8_t* sym = s_symw + grp * KL_SYM;
-    const unsigned mask[4] = {info->mask[0], info->mask[1], info->mask[2], info->mask[3]};
-    const int total = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
-    for (int base = 4 * slot; base < total; base += 4 * KL_NC) {
-        const int rank = base + grp;
-        const int my = rank < total ? kl_pick(mask, rank) : -1;
-        bool act = my >= 0;
-        const int lbm = act ? my : 0;
-        const long long jb = j0 + lbm;
-        TileCol tc{stage, P_src, a.box, lbm};
-        float e_b = info->e[lbm];
-        // bins with peeled balls (qsft.py:223-241 applied to the shared-memory copy), then their energy
-        const bool touched = act && round > 1 && ((info->tmask[lbm >> 5] >> (lbm & 31)) & 1u);
-        if (round > 1 && __ballot_sync(0xffffffffu, touched)) {
-            int f = touched ? s_head[lbm] - 1 : -1;
-            while (__ballot_sync(0xffffffffu, f >= 0)) {
-                if (f >= 0) {
-                    const uint4* src = reinterpret_cast<const uint4*>(a.find_k + (size_t)f * d.ld);
-                    for (int w = gl; w < d.ld / 16; w += KL_G) reinterpret_cast<uint4*>(sym)[w] = __ldcg(src + w);
-                }
-                __syncwarp();
-                if (f >= 0) {
-                    uint32_t kw[NW];
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) kw[w] = (4 * w < d.ld) ? reinterpret_cast<const uint32_t*>(sym)[w] : 0u;
-                    const float2 rho = __ldcg(a.find_rho + f);
-                    const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, sym, kw, structured};
-                    for (int r = 0; r < R; ++r) {
-                        const int tb = ph.base(r);
-                        for (int i = gl; i < P_src; i += KL_G) {
-                            const float2 w = s_tw[ph.row(r, i, tb)];
-                            float2& v = tc.ref(r, i);
-                            v.x -= rho.x * w.x - rho.y * w.y;
-                            v.y -= rho.x * w.y + rho.y * w.x;
-                        }
-                    }
-                    f = __ldcg(a.next + (size_t)f * d.C + c) - 1;
-                }
-                __syncwarp();
-            }
-            float e2 = 0.f;
-            if (touched)
-                for (int r = 0; r < R; ++r)
-                    for (int i = gl; i < P_src; i += KL_G) {
-                        const float2 v = tc.ri(r, i);
-                        e2 = fmaf(v.x, v.x, fmaf(v.y, v.y, e2));
-                    }
-            e2 = kl_group_sum(e2);
-            if (touched) {
-                e_b = e2;
-                act = e2 > thresh;                                  // energy test (qsft.py:164)
-            }
-        }
-        uint8_t* kb = sym;
-        if (act) {
-            for (int i = 1 + gl; i <= nsym; i += KL_G) sym[i - 1] = (uint8_t)detect_symbol(d, tc, i);
-            for (int i = nsym + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) sym[i] = 0;
-        }
-        __syncwarp();
-        if (d.source == 1) {
-            kb = sym + QSFT_MAX_N;
-            if (act) {
-                for (int i = d.n + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) kb[i] = 0;
-                if (gl == 0) rs_decode(d, sym, kb);
-            }
-            __syncwarp();
-        }
-        uint32_t kw[NW];
-#pragma unroll
-        for (int w = 0; w < NW; ++w) kw[w] = reinterpret_cast<const uint32_t*>(kb)[w];
-        const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, kb, kw, structured};
-        // rho = <signature, col> / P (qsft.py:174-175) and the residual ||col - rho sig||^2 (qsft.py:176,183) in one pass:
-        // with z_i = conj(sig_i) col_i and the shift z0 = z of row (0, 0),  rho = z0 + mean(z_i - z0)  and
-        // residual = sum |z_i - z0|^2 - |sum (z_i - z0)|^2 / P.  For a singleton every z_i - z0 is at rounding level, so the
-        // subtraction cancels nothing that matters; for a multiton the residual is large either way.
-        float sx = 0.f, sy = 0.f, s2 = 0.f;
-        float2 z0 = make_float2(0.f, 0.f);
-        if (act) {
-            const int tb0 = ph.base(0);
-            {
-                const float2 w = s_tw[tb0];
-                const float2 v = tc.ri(0, 0);
-                z0 = make_float2(w.x * v.x + w.y * v.y, w.x * v.y - w.y * v.x);
-            }
-            for (int r = 0; r < R; ++r) {
-                const int tb = r == 0 ? tb0 : ph.base(r);
-                for (int i = gl; i < P_src; i += KL_G) {
-                    const float2 w = s_tw[ph.row(r, i, tb)];
-                    const float2 v = tc.ri(r, i);
-                    const float dx = (w.x * v.x + w.y * v.y) - z0.x;            // conj(sig) * v - z0
-                    const float dy = (w.x * v.y - w.y * v.x) - z0.y;
-                    sx += dx;
-                    sy += dy;
-                    s2 = fmaf(dx, dx, fmaf(dy, dy, s2));
-                }
-            }
-        }
-        sx = kl_group_sum(sx);
-        sy = kl_group_sum(sy);
-        s2 = kl_group_sum(s2);
-        const float invP = (float)d.invP;
-        const float rr = z0.x + sx * invP, ri = z0.y + sy * invP;
-        const float res = s2 - (sx * sx + sy * sy) * invP;
-        // bin hash j = dec(M_c^T k mod q) (qsft.py:178-179)
-        long long hsum = 0;
-        if (act) {
-#pragma unroll
-            for (int u = 0; u < 32 / KL_G; ++u) {
-                const int i = gl + u * KL_G;
-                if (i < d.b)
-                    hsum += wgt[u] * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + i) * d.ld, d.ld, kw), d.q, d.qmagic);
-            }
-        }
-#pragma unroll
-        for (int o = KL_G / 2; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
-        const float lim = fmaxf(thresh, a.rel_floor * e_b);
-        const bool single = act && (hsum == jb) && !(res > lim);
-        const bool lead = (gl == 0);
-        const unsigned sb = __ballot_sync(0xffffffffu, lead && single);
-        unsigned long long fbase = 0;
-        if (lane == 0 && sb) fbase = atomicAdd(&a.counters[0], (unsigned long long)__popc(sb));
-        fbase = __shfl_sync(0xffffffffu, fbase, 0);
-        unsigned long long f = fbase + (unsigned long long)__popc(sb & ((1u << lane) - 1u));
-        f = __shfl_sync(0xffffffffu, f, lane & ~(KL_G - 1));
-        if (single) {
-            if ((long long)f < a.max_finds) {
-                uint32_t* ko = reinterpret_cast<uint32_t*>(a.find_k + (size_t)f * d.ld);
-                for (int w = gl; w < d.ld / 4; w += KL_G) ko[w] = (w < NW) ? kw[w] : 0u;
-                if (lead) {
-                    a.find_cj[f] = (long long)c * B + jb;
-                    a.find_rho[f] = make_float2(rr, ri);
-                    a.find_round[f] = round;
-                    a.find_id[(size_t)c * B + jb] = (int32_t)f;
-                }
-            }
-        } else if (act && lead) {
-            ++n_multi;
-        }
-        __syncwarp();
-    }
-}
-
-// ---- one classification round ---------------------------------------------------------------------------------------
-// TMA variant: warp roles -- KL_NS scanner warps (threads 0 .. 127), KL_NC candidate warps, 1 producer warp -- coupled only
-// through the stages' mbarriers (full: tile landed; scanned: work list ready; empty: every candidate warp is done), so the
-// streaming scan of the next tiles overlaps the latency-bound candidate work of the previous ones.
-// Plain variant: the same two functions separated by CTA barriers, single stage.
-template <int NW, bool TMA>
-__device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk,
-#ifndef QSFT_EMU
-                                            const CUtensorMap* maps,
-#endif
-                                            int round, uint8_t* stages, uint64_t* bars, unsigned int& tiles_done, KlTileInfo* infos,
-                                            uint8_t* s_sym, const float2* s_tw) {
-    const PeelDev& d = a.d;
-    const int W = a.W, R = d.R, P_src = d.P_src;
-    const long long B = d.B;
-    const long long tpg = (B + W - 1) >> a.lgW;                    // tiles per group
-    const long long n_tiles = tpg * d.C;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long mine = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    unsigned n_multi = 0;
-    const bool is_cand = warp >= KL_NS && warp < KL_NS + KL_NC;
-    bool structured = false;
-    long long wgt[32 / KL_G] = {0, 0, 0, 0};
-    if (is_cand) {
-        structured = (*a.dstruct != 0);
-#pragma unroll
-        for (int u = 0; u < 32 / KL_G; ++u) wgt[u] = hash_weight(d, (lane % KL_G) + u * KL_G);
-    }
-    uint8_t* s_symw = s_sym + (size_t)(is_cand ? warp - KL_NS : 0) * 4 * KL_SYM;
-#ifndef QSFT_EMU
-    if (TMA) {
-        uint64_t* full = bars;
-        uint64_t* empty = bars + KL_MAX_STAGES;
-        uint64_t* scanned = bars + 2 * KL_MAX_STAGES;
-        unsigned int it = tiles_done;
-        if (warp == KL_NS + KL_NC) {
-            // ---- producer warp --------------------------------------------------------------------------------------
-            if (lane == 0) {
-                const uint32_t box_bytes = (uint32_t)((W >> 4) * P_src * 128);
-                for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++it) {
-                    const int st = (int)(it % (unsigned)a.nstages);
-                    const uint32_t ph = (it / (unsigned)a.nstages) & 1u;
-                    tma::mbar_wait(&empty[st], ph ^ 1u);
-                    const int c = (int)(tt / tpg);
-                    const long long j0 = (tt - (long long)c * tpg) << a.lgW;
-                    uint8_t* dst = stages + (size_t)st * a.stage_bytes;
-                    const long long left = B - j0;
-                    const uint32_t head_bytes = round > 1 ? (uint32_t)((left < W ? left : W) * 4) : 0u;
-                    tma::mbar_expect_tx(&full[st], (uint32_t)R * box_bytes + head_bytes);
-                    for (int r = 0; r < R; ++r)
-                        tma::load_3d(dst + (size_t)r * a.box, &maps[c * R + r], 0, 0, (int)(j0 >> 4), &full[st]);
-                    if (head_bytes) tma::bulk_g2s(dst + (size_t)R * a.box, a.head + (size_t)c * B + j0, head_bytes, &full[st]);
-                }
-            }
-        } else if (warp < KL_NS) {
-            // ---- scanner warps --------------------------------------------------------------------------------------
-            for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++it) {
-                const int st = (int)(it % (unsigned)a.nstages);
-                const uint32_t ph = (it / (unsigned)a.nstages) & 1u;
-                const int c = (int)(tt / tpg);
-                const long long j0 = (tt - (long long)c * tpg) << a.lgW;
-                tma::mbar_wait(&full[st], ph);
-                kl_scan(a, stages + (size_t)st * a.stage_bytes, j0, round, &infos[st]);
-                __syncwarp();
-                if (lane == 0) tma::mbar_arrive(&scanned[st]);
-            }
-        } else {
-            // ---- candidate warps ------------------------------------------------------------------------------------
-            const int cw = warp - KL_NS;
-            for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++it) {
-                const int st = (int)(it % (unsigned)a.nstages);
-                const uint32_t ph = (it / (unsigned)a.nstages) & 1u;
-                const int c = (int)(tt / tpg);
-                const long long j0 = (tt - (long long)c * tpg) << a.lgW;
-                tma::mbar_wait(&scanned[st], ph);
-                tma::mbar_wait(&full[st], ph);                     // already complete: makes the bulk copies visible here too
-                kl_cand<NW>(a, stages + (size_t)st * a.stage_bytes, &infos[st], c, j0, round, (int)((cw + 5u * it) % (unsigned)KL_NC),
-                            s_symw, s_tw, structured, wgt, n_multi);
-                // this warp is done with the stage; its in-place updates (generic proxy) are ordered before the next bulk copy
-                if (round > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) tma::mbar_arrive(&empty[st]);
-            }
-        }
-        tiles_done += (unsigned int)mine;
-    }
-#endif
-    if (!TMA) {
-        unsigned int it = tiles_done;
-        for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++it) {
-            const int c = (int)(tt / tpg);
-            const long long j0 = (tt - (long long)c * tpg) << a.lgW;
-            // coalesced copy into the tile layout (single stage): the previous tile's readers are done first
-            __syncthreads();
-            {
-                const int lb = threadIdx.x & (W - 1), prt = threadIdx.x >> a.lgW, nparts = (int)blockDim.x >> a.lgW;
-                const long long jf = j0 + lb;
-                TileCol tc{stages, P_src, a.box, lb};
-                for (int r = 0; r < R; ++r) {
-                    const float2* src = blk.p[c * R + r] + jf;
-                    for (int i = prt; i < P_src; i += nparts) tc.ref(r, i) = (jf < B) ? src[(size_t)i * a.ldU] : make_float2(0.f, 0.f);
-                }
-                if (round > 1 && threadIdx.x < W)
-                    reinterpret_cast<int32_t*>(stages + (size_t)R * a.box)[threadIdx.x] =
-                        (j0 + threadIdx.x < B) ? __ldcg(a.head + (size_t)c * B + j0 + threadIdx.x) : 0;
-            }
-            __syncthreads();
-            if (warp < KL_NS) kl_scan(a, stages, j0, round, &infos[0]);
-            __syncthreads();
-            if (is_cand)
-                kl_cand<NW>(a, stages, &infos[0], c, j0, round, (int)((warp - KL_NS + 5u * it) % (unsigned)KL_NC), s_symw, s_tw,
-                            structured, wgt, n_multi);
-        }
-        tiles_done += (unsigned int)mine;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n_multi += __shfl_xor_sync(0xffffffffu, n_multi, o);
-    if (lane == 0 && n_multi) atomicAdd(&a.multi[round], (unsigned long long)n_multi);
-}
-
-// ---- link phase: one thread per find of the round ---------------------------------------------------------------------
-template <int NW>
-__device__ __forceinline__ void kl_link(const KlArgs& a, long long f0, long long f1, int round, bool do_link) {
-    const PeelDev& d = a.d;
-    const int nw = d.ld / 4;
-    const long long B = d.B;
-    for (long long f = f0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; f < f1; f += (long long)gridDim.x * blockDim.x) {
-        const long long cj = a.find_cj[f];
-        const int c = (int)(cj / B);
-        uint32_t kw[NW];
-        const uint32_t* kin = reinterpret_cast<const uint32_t*>(a.find_k + (size_t)f * d.ld);
-#pragma unroll
-        for (int w = 0; w < NW; ++w) kw[w] = (w < nw) ? kin[w] : 0u;
-        float2 sum = a.find_rho[f];
-        int cnt = 1;
-        bool first = true, last = true;
-        long long jl[KL_MAX_BLOCKS];                       // C <= 16 on this path
-        for (int c2 = 0; c2 < d.C; ++c2) {
-            if (c2 == c) {
-                jl[c2] = cj - (long long)c * B;
-                continue;
-            }
-            const long long j2 = hash_bin<NW>(d, c2, kw);
-            jl[c2] = j2;
-            const int32_t f2 = a.find_id[(size_t)c2 * B + j2];
-            // find_id is only written for singletons: an entry is a find of THIS round iff it lies in the round's range and
-            // that find really sits in bin (c2, j2)
-            if ((long long)f2 >= f0 && (long long)f2 < f1 && a.find_cj[f2] == (long long)c2 * B + j2) {
-                const uint32_t* k2 = reinterpret_cast<const uint32_t*>(a.find_k + (size_t)f2 * d.ld);
-                bool same = true;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) same &= ((w < nw) ? k2[w] : 0u) == kw[w];
-                if (same) {
-                    if (c2 < c) {
-                        first = false;                      // an earlier group holds the round's first find of this k
-                    } else {
-                        last = false;                       // ball_values: a later (i, j) wins (qsft.py:215)
-                        const float2 r2 = a.find_rho[f2];
-                        sum.x += r2.x;
-                        sum.y += r2.y;
-                        ++cnt;
-                    }
-                }
-            }
-        }
-        if (first && a.has_uniq)
-            k4_uniq_commit<NW>(d, kw, sum, cnt, cj, jl[0], round, a.uo.seen0, a.uo.uk, a.uo.usum, a.uo.ucnt, a.uo.ukey, a.uo.unext,
-                               a.uo.max_uniq, a.counters);
-        if (last && do_link) {
-            // peel: the ball joins the list of every bin it hashes to (qsft.py:223-241)
-            for (int l = 0; l < d.C; ++l) {
-                const int32_t prev = atomicExch(a.head + (size_t)l * B + jl[l], (int32_t)(f + 1));
-                a.next[(size_t)f * d.C + l] = prev;
-            }
-            atomicAdd(&a.counters[2], 1ull);                // num_peeling (qsft.py:224)
-        }
-    }
-}
-
-template <int NW, bool TMA>
-__global__ void __launch_bounds__(TMA ? KL_CT + 32 : KL_CT, 1)
-k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
-#ifndef QSFT_EMU
-                    , const __grid_constant__ KlMaps maps
-#endif
-) {
-    extern __shared__ __align__(1024) uint8_t kl_smem[];
-    __shared__ float2 s_tw[QSFT_MAX_Q + 1];
-    const PeelDev& d = a.d;
-    if (threadIdx.x < d.q) {
-        float sn, cs;
-        sincospif(2.0f * (float)threadIdx.x / (float)d.q, &sn, &cs);
-        if (d.q == 4) {                                     // exact quarter turns
-            cs = (threadIdx.x == 0) ? 1.f : (threadIdx.x == 2) ? -1.f : 0.f;
-            sn = (threadIdx.x == 1) ? 1.f : (threadIdx.x == 3) ? -1.f : 0.f;
-        } else if (d.q == 2) {
-            cs = threadIdx.x == 0 ? 1.f : -1.f;
-            sn = 0.f;
-        }
-        s_tw[threadIdx.x] = make_float2(cs, sn);
-    }
-#ifndef QSFT_EMU
-    uint8_t* base = kl_smem + ((1024u - (tma::smem_u32(kl_smem) & 1023u)) & 1023u);
-#else
-    uint8_t* base = kl_smem;
-#endif
-    uint8_t* ctrl = base + (size_t)a.nstages * a.stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);                           // full[6], empty[6], scanned[6]
-    KlTileInfo* infos = reinterpret_cast<KlTileInfo*>(ctrl + 256);                // [KL_MAX_STAGES], 576 bytes apart
-    uint8_t* s_sym = ctrl + 256 + KL_MAX_STAGES * 576;                            // [KL_NC][4][KL_SYM]
-#ifndef QSFT_EMU
-    if (TMA && threadIdx.x == 0) {
-        for (int i = 0; i < KL_MAX_STAGES; ++i) {
-            tma::mbar_init(&bars[i], 1);
-            tma::mbar_init(&bars[KL_MAX_STAGES + i], KL_NC);
-            tma::mbar_init(&bars[2 * KL_MAX_STAGES + i], KL_NS);
-        }
-        tma::mbar_fence_init();
-    }
-#endif
-    __syncthreads();
-    unsigned int epoch = 0, tiles_done = 0;
-    long long total = 0;
-    double num_peeling = 0;
-    int round = 0;
-    bool cont = true;
-    while (cont && num_peeling < a.peeling_max && round < a.max_rounds) {
-        ++round;
-        kl_classify<NW, TMA>(a, blk,
-#ifndef QSFT_EMU
-                             maps.m,
-#endif
-                             round, base, bars, tiles_done, infos, s_sym, s_tw);
-        kl_grid_barrier(a.gbar, epoch);
-        const long long now = (long long)__ldcg(a.counters + 0);
-        const long long multis = (long long)__ldcg(a.multi + round);
-        if (now > a.max_finds) {                            // find buffer too small: report, stop (uniform over the grid)
-            if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[6] = 1ull;
-            total = a.max_finds;
-            break;
-        }
-        const long long nf = now - total;
-        if (multis == 0 || nf == 0) cont = false;           // qsft.py:204-205
-        // the reference also subtracts after its last round, but nothing reads the bins afterwards: skip unless the q^n
-        // guard needs the count
-        const bool do_link = cont || a.guard_can_bind;
-        if (nf > 0) kl_link<NW>(a, total, now, round, do_link);
-        total = now;
-        if (cont || a.guard_can_bind) {
-            kl_grid_barrier(a.gbar, epoch);
-            if (a.guard_can_bind) num_peeling = (double)__ldcg(a.counters + 2);
-        }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        a.counters[5] = (unsigned long long)round;
-        a.counters[7] = (unsigned long long)total;
-    }
-}
-
-// D[c][r * P_src + i] == (D[c][r * P_src] - e_{i-1}) mod q for all c, r, i >= 1 (and P_src == n + 1)?
-__global__ void kl_dstruct_kernel(PeelDev d, int* flag) {
-    __shared__ int bad;
-    if (threadIdx.x == 0) bad = (d.P_src != d.n + 1) ? 1 : 0;
-    __syncthreads();
-    const long long total = (long long)d.C * d.P * d.n;
-    for (long long e = threadIdx.x; e < total && !bad; e += blockDim.x) {
-        const int u = (int)(e % d.n);
-        const long long cp = e / d.n;
-        const int p = (int)(cp % d.P), c = (int)(cp / d.P);
-        const int r = p / d.P_src, i = p - r * d.P_src;
-        if (i == 0) continue;
-        const int d0 = d.D[((size_t)c * d.P + r * d.P_src) * d.ld + u];
-        int want = d0 - (u == i - 1 ? 1 : 0);
-        if (want < 0) want += d.q;
-        if ((int)d.D[((size_t)c * d.P + p) * d.ld + u] != want) bad = 1;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *flag = bad ? 0 : 1;
-}
-
-// tile geometry for a shared-memory budget: the widest tile (<= 128 bins, no wider than the group needs) that leaves at
-// least `min_stages` stages.  Returns false when even 16-bin tiles do not fit.
-inline bool kl_geometry(const PeelDev& d, int budget, int min_stages, KlArgs* a) {
-    for (int W = KL_MAXW; W >= 16; W >>= 1) {
-        if (W > 16 && (long long)(W >> 1) >= d.B) continue;
-        const int box = ((W >> 4) * d.P_src * 128 + 1023) & ~1023;
-        const long long stage = ((long long)d.R * box + W * 4 + 1023) & ~1023ll;
-        const long long n = ((long long)budget - KL_CTRL_BYTES) / stage;
-        if (n >= min_stages) {
-            a->W = W;
-            a->lgW = W == 128 ? 7 : W == 64 ? 6 : W == 32 ? 5 : 4;
-            a->box = box;
-            a->stage_bytes = (int)stage;
-            a->nstages = n > KL_MAX_STAGES ? KL_MAX_STAGES : (int)n;
-            return true;
-        }
-    }
-    return false;
-}
-
-}  // namespace (device part; the CPU emulation cuts here)
-
-// ---- host side ---------------------------------------------------------------------------------------------------------
-namespace {
-
-template <int NW>
-int kl_launch(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, size_t smem, int grid, cudaStream_t st) {
-    void* params[] = {(void*)&a, (void*)&blk, (void*)&maps};
-    const void* fn = use_tma ? (const void*)k4_peel_loop_kernel<NW, true> : (const void*)k4_peel_loop_kernel<NW, false>;
-    QSFT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    QSFT_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(use_tma ? KL_CT + 32 : KL_CT), params, smem, st));
-    g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
-    return QSFT_OK;
-}
-
-}  // namespace
+int qsft_kl_launch_nw8(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, int rc_form, size_t smem, int grid,
+                       cudaStream_t st);
+int qsft_kl_launch_nw16(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, int rc_form, size_t smem, int grid,
+                        cudaStream_t st);
+int qsft_kl_launch_nw32(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, int rc_form, size_t smem, int grid,
+                        cudaStream_t st);
 
 // Whole peel loop on the device.  blocks[c * R + r] -> (P_src, ldU) complex64 rows of group c, repeat r (device pointers,
 // host array).  Outputs as qsft_peel.  Returns QSFT_EUNSUPPORTED when the shape does not fit this kernel (C * R > 16,
@@ -761,10 +82,12 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
     QSFT_LAUNCHED();
     int rc;
     const int nw = d.ld / 4;
-    if (nw <= 4) rc = kl_launch<4>(a, blk, hm, use_tma, smem, sms, st);
-    else if (nw <= 8) rc = kl_launch<8>(a, blk, hm, use_tma, smem, sms, st);
-    else if (nw <= 16) rc = kl_launch<16>(a, blk, hm, use_tma, smem, sms, st);
-    else rc = kl_launch<32>(a, blk, hm, use_tma, smem, sms, st);
+    // candidate bins held in registers when they fit (the stage is released early), else worked on in shared memory
+    int rc_form = (d.R == 1 && d.P_src <= 56) ? 1 : (d.R <= 3 && d.P_src <= 48) ? 3 : 0;
+    if (getenv("QSFT_K4_NO_REGS") != nullptr) rc_form = 0;     // cross-check of the shared-memory form (tests)
+    if (nw <= 8) rc = qsft_kl_launch_nw8(a, blk, hm, use_tma, rc_form, smem, sms, st);
+    else if (nw <= 16) rc = qsft_kl_launch_nw16(a, blk, hm, use_tma, rc_form, smem, sms, st);
+    else rc = qsft_kl_launch_nw32(a, blk, hm, use_tma, rc_form, smem, sms, st);
     if (rc != QSFT_OK) {
         cudaFreeAsync(ws, st);
         return rc;

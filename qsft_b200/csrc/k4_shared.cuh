@@ -141,7 +141,7 @@ struct GF {
 
 // Syndrome decode: sym (2ts symbols of Z_q) -> k digits (n), returns false on decoder failure (k left all zero,
 // like galois returning the unchanged zero codeword with n_errors = -1).
-__device__ bool rs_decode(const PeelDev& d, const uint8_t* sym, uint8_t* kout) {
+__device__ __noinline__ bool rs_decode(const PeelDev& d, const uint8_t* sym, uint8_t* kout) {
     GF F{d.q, d.rs_s, d.rs_order, d.rs_exp, d.rs_log};
     const int t = d.rs_t, s = d.rs_s, n = d.n, nt = d.rs_order - 1;
     const int T2 = 2 * t;
@@ -243,7 +243,7 @@ __device__ bool rs_decode(const PeelDev& d, const uint8_t* sym, uint8_t* kout) {
 // ---------------------------------------------------------------------------------------------------------
 // angle_q: (((angle mod 2 pi) // (pi / q)) + 1) // 2 mod q in fp64 like NumPy (np.angle of a complex128 holding the
 // fp32 value; the float floor divisions are exact small integers)
-__device__ __forceinline__ int angle_q_dev(float2 v, int q) {
+__device__ __noinline__ int angle_q_dev(float2 v, int q) {
     double a = atan2((double)v.y, (double)v.x);
     if (a < 0.0) a += kTwoPi;                      // numpy: angle % (2 pi)
     if (a >= kTwoPi) a -= kTwoPi;
@@ -274,38 +274,83 @@ struct StridedCol {
     __device__ __forceinline__ float2 ri(int r, int i) const { return col[(size_t)(r * P_src + i) * stride]; }
 };
 
+__device__ __noinline__ int symbol_noiseless_exact(int q, float2 v0, float2 v) {
+    const double a0 = atan2((double)v0.y, (double)v0.x);
+    const double a = atan2((double)v.y, (double)v.x);
+    const long long r = (long long)rint((double)q * (a - a0) / kTwoPi);          // half-to-even like np.round
+    const int m = (int)(r % q);
+    return m < 0 ? m + q : m;
+}
+
+// ---- decisions on values (shared by the column-accessor form below and the register-resident form of k4_peel_loop.cu) ----
+// noiseless (reconstruct.py:12-31): round(q (angle v - angle v0) / 2 pi) mod q = root nearest to the direction of v conj(v0)
+__device__ __forceinline__ int symbol_noiseless(const PeelDev& d, float2 v0, float2 v) {
+    int symv = -1;
+    if (d.fastdet && (d.q == 4 || d.q == 2))
+        symv = quadrant_symbol(d.q, fmaf(v.x, v0.x, v.y * v0.y), fmaf(v.y, v0.x, -(v.x * v0.y)));
+    // fast path in fp32; anything within 0.01 of a rounding boundary is redone in fp64 so the decision
+    // always equals the fp64 one (np.angle / np.round in the reference)
+    if (symv < 0 && fabsf(v0.x) + fabsf(v0.y) > 1e-30f && fabsf(v.x) + fabsf(v.y) > 1e-30f) {
+        const float u = (float)d.q * (atan2f(v.y, v.x) - atan2f(v0.y, v0.x)) * 0.15915494309189535f;
+        const float m = rintf(u);
+        if (fabsf(u - m) < 0.49f) {
+            int mi = (int)m;                    // |u| < q  =>  m in [-q, q]
+            mi = mi < 0 ? mi + d.q : mi;
+            symv = mi >= d.q ? mi - d.q : mi;
+        }
+    }
+    if (symv < 0) symv = symbol_noiseless_exact(d.q, v0, v);
+    return symv;
+}
+
+// nso1 (reconstruct.py:100-113) from the fp32 sum over the repeats of z conj(v): -1 when the value sits too close to a
+// decision boundary for fp32 (both fast decisions keep a margin far above the rounding of the sum)
+__device__ __forceinline__ int symbol_nso1_fast(const PeelDev& d, float arf, float aif) {
+    int symv = -1;
+    if (d.fastdet && (d.q == 4 || d.q == 2)) symv = quadrant_symbol(d.q, arf, aif);
+    if (symv < 0 && fabsf(arf) + fabsf(aif) > 1e-30f) {
+        float thf = atan2f(aif, arf);
+        if (thf < 0.f) thf += 6.283185307179586f;
+        const float u = thf * (float)d.q * 0.15915494309189535f;        // in [0, q]
+        const float m = rintf(u);
+        if (fabsf(u - m) < 0.49f) symv = ((int)m >= d.q) ? (int)m - d.q : (int)m;   // nearest of the q+1 roots, mod q
+    }
+    return symv;
+}
+
+// ... and from the fp64 sum, exactly like NumPy: argmin over the q + 1 roots, first minimum (np.mean divides by R > 0: the
+// angle does not depend on it)
+__device__ __noinline__ int symbol_nso1_exact(const PeelDev& d, double ar, double ai) {
+    double th = atan2(ai, ar);
+    if (th < 0.0) th += kTwoPi;                                          // numpy: angle % (2 pi)
+    if (th >= kTwoPi) th -= kTwoPi;
+    const double step = kTwoPi / (double)d.q;
+    int best = 0;
+    double bd = fabs(0.0 - th);
+    for (int m = 1; m <= d.q; ++m) {
+        const double dist = fabs(step * (double)m - th);
+        if (dist < bd) {
+            bd = dist;
+            best = m;
+        }
+    }
+    return best % d.q;
+}
+
+// nso2 (reconstruct.py:116-129): every repeat votes with its quantised phase difference; the votes are averaged as numbers,
+// np.round is half-to-even; the sum of R small integers and the division by R are exact / correctly rounded like np.mean
+__device__ __forceinline__ int nso2_vote(const PeelDev& d, float2 z, float2 v) {
+    const int df = angle_q_dev(z, d.q) - angle_q_dev(v, d.q);
+    return df < 0 ? df + d.q : df;
+}
+__device__ __forceinline__ int symbol_nso2(const PeelDev& d, long long votes) {
+    return (int)((long long)rint((double)votes / (double)d.R) % d.q);
+}
+
 template <class Col>
 __device__ __forceinline__ int detect_symbol(const PeelDev& d, const Col& col, int i) {
-    const double qd = (double)d.q;
-    const bool quad = d.fastdet && (d.q == 4 || d.q == 2);
-    int symv;
-    if (d.channel == 0) {
-        const float2 v0 = col.ri(0, 0);
-        const float2 v = col.ri(0, i);
-        symv = -1;
-        // round(q (angle v - angle v0) / 2 pi) mod q = root nearest to the direction of v conj(v0)
-        if (quad) symv = quadrant_symbol(d.q, fmaf(v.x, v0.x, v.y * v0.y), fmaf(v.y, v0.x, -(v.x * v0.y)));
-        // fast path in fp32; anything within 0.01 of a rounding boundary is redone in fp64 so the decision
-        // always equals the fp64 one (np.angle / np.round in the reference)
-        if (symv < 0 && fabsf(v0.x) + fabsf(v0.y) > 1e-30f && fabsf(v.x) + fabsf(v.y) > 1e-30f) {
-            const float u = (float)d.q * (atan2f(v.y, v.x) - atan2f(v0.y, v0.x)) * 0.15915494309189535f;
-            const float m = rintf(u);
-            if (fabsf(u - m) < 0.49f) {
-                int mi = (int)m;                    // |u| < q  =>  m in [-q, q]
-                mi = mi < 0 ? mi + d.q : mi;
-                symv = mi >= d.q ? mi - d.q : mi;
-            }
-        }
-        if (symv < 0) {
-            const double a0 = atan2((double)v0.y, (double)v0.x);
-            const double a = atan2((double)v.y, (double)v.x);
-            const long long r = (long long)rint(qd * (a - a0) / kTwoPi);    // half-to-even like np.round
-            const int m = (int)(r % d.q);
-            symv = m < 0 ? m + d.q : m;
-        }
-    } else if (d.channel == 1) {
-        // fp32 first: both fast decisions below keep a safety margin far above the fp32 rounding of these sums; only a
-        // value near a decision boundary is redone in fp64 (np.mean divides by R > 0: the angle does not depend on it)
+    if (d.channel == 0) return symbol_noiseless(d, col.ri(0, 0), col.ri(0, i));
+    if (d.channel == 1) {
         float arf = 0.f, aif = 0.f;
         for (int r = 0; r < d.R; ++r) {
             const float2 z = col.ri(r, 0);
@@ -313,52 +358,20 @@ __device__ __forceinline__ int detect_symbol(const PeelDev& d, const Col& col, i
             arf = fmaf(z.x, v.x, fmaf(z.y, v.y, arf));                       // z * conj(v)
             aif = fmaf(z.y, v.x, fmaf(-z.x, v.y, aif));
         }
-        symv = -1;
-        if (quad) symv = quadrant_symbol(d.q, arf, aif);
-        if (symv < 0 && fabsf(arf) + fabsf(aif) > 1e-30f) {
-            float thf = atan2f(aif, arf);
-            if (thf < 0.f) thf += 6.283185307179586f;
-            const float u = thf * (float)d.q * 0.15915494309189535f;        // in [0, q]
-            const float m = rintf(u);
-            if (fabsf(u - m) < 0.49f) symv = ((int)m >= d.q) ? (int)m - d.q : (int)m;   // nearest of the q+1 roots, mod q
-        }
+        const int symv = symbol_nso1_fast(d, arf, aif);
+        if (symv >= 0) return symv;
         double ar = 0.0, ai = 0.0;
-        if (symv < 0)
-            for (int r = 0; r < d.R; ++r) {
-                const float2 z = col.ri(r, 0);
-                const float2 v = col.ri(r, i);
-                ar += (double)z.x * v.x + (double)z.y * v.y;
-                ai += (double)z.y * v.x - (double)z.x * v.y;
-            }
-        if (symv < 0) {
-            double th = atan2(ai, ar);
-            if (th < 0.0) th += kTwoPi;                                      // numpy: angle % (2 pi)
-            if (th >= kTwoPi) th -= kTwoPi;
-            const double step = kTwoPi / qd;
-            int best = 0;
-            double bd = fabs(0.0 - th);
-            for (int m = 1; m <= d.q; ++m) {                                 // argmin over q+1 roots, first minimum
-                const double dist = fabs(step * (double)m - th);
-                if (dist < bd) {
-                    bd = dist;
-                    best = m;
-                }
-            }
-            symv = best % d.q;
-        }
-    } else {
-        // nso2: every repeat votes with its quantised phase difference; the votes are averaged as numbers, np.round is
-        // half-to-even; the sum of R small integers and the division by R are exact / correctly rounded like np.mean
-        long long votes = 0;
         for (int r = 0; r < d.R; ++r) {
-            const int a0 = angle_q_dev(col.ri(r, 0), d.q);
-            const int a = angle_q_dev(col.ri(r, i), d.q);
-            int df = a0 - a;
-            votes += df < 0 ? df + d.q : df;
+            const float2 z = col.ri(r, 0);
+            const float2 v = col.ri(r, i);
+            ar += (double)z.x * v.x + (double)z.y * v.y;
+            ai += (double)z.y * v.x - (double)z.x * v.y;
         }
-        symv = (int)((long long)rint((double)votes / (double)d.R) % d.q);
+        return symbol_nso1_exact(d, ar, ai);
     }
-    return symv;
+    long long votes = 0;
+    for (int r = 0; r < d.R; ++r) votes += nso2_vote(d, col.ri(r, 0), col.ri(r, i));
+    return symbol_nso2(d, votes);
 }
 
 

@@ -13,6 +13,7 @@ import torch
 
 from . import ops
 from .input_signal_subsampled import SubsampledSignal
+from .result import SparseSpectrum
 from .utils import calc_hamming_weight, sort_qary_vecs
 
 
@@ -92,7 +93,8 @@ class QSFT:
         if output == "arrays":
             gwht = {"locations": loc_arr, "values": values, "counts": counts}
         else:
-            gwht = dict(zip(itertools.batched(loc_arr.astype(np.uint8).tobytes(), n), values.tolist()))
+            # the reference's {tuple(k): complex}; the tuples are created on first use (result.py)
+            gwht = SparseSpectrum(loc_arr, values)
         peeling_time = time.time() - peeling_start
         if timing_verbose:
             print(f"Peeling Time:{peeling_time}", flush=True)

@@ -24,7 +24,7 @@ def device_part(which="k4"):
         end = src.index("int make_dev(")                  # host code (with <<< >>> launches) starts here
         text = _rewrite(src[start:end]) + "\n}  // namespace (closed by build_emu.py)\n"
         # the persistent on-device round loop (plain-copy variant; the TMA variant is sm_100a only)
-        src = open(os.path.join(ROOT, "qsft_b200", "csrc", "k4_peel_loop.cu")).read()
+        src = open(os.path.join(ROOT, "qsft_b200", "csrc", "k4_peel_loop.cuh")).read()
         start = src.index('#include "common.cuh"') + len('#include "common.cuh"')
         end = src.index("}  // namespace (device part; the CPU emulation cuts here)")
         return text + _rewrite(src[start:end]) + "\n}  // namespace (closed by build_emu.py)\n"
@@ -59,7 +59,7 @@ def build(force=False, which="k4"):
     text = device_part(which)
     srcs = [os.path.join(HERE, f"{which}_emu.cpp"), os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "qsft_b200", "csrc", cu)]
     if which == "k4":
-        srcs += [os.path.join(ROOT, "qsft_b200", "csrc", f) for f in ("k4_peel_loop.cu", "k4_shared.cuh")]
+        srcs += [os.path.join(ROOT, "qsft_b200", "csrc", f) for f in ("k4_peel_loop.cuh", "k4_shared.cuh")]
     fresh = os.path.exists(lib) and os.path.exists(inc) and open(inc).read() == text and \
         all(os.path.getmtime(lib) >= os.path.getmtime(p) for p in srcs)
     if fresh and not force:

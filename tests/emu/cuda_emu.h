@@ -29,6 +29,9 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#ifndef __noinline__
+#define __noinline__
+#endif
 
 namespace emu {
 

@@ -46,7 +46,7 @@ void classify(const PeelDev& d, const float2* U, long long jb, long long je, lon
 // The persistent loop kernel (k4_peel_loop.cu, plain-copy variant) as ONE block: mirrors the host side of qsft_peel_loop.
 // maxW caps the tile width (128 = the product's choice) so that the narrower tile shapes are exercised too.
 int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, float2* rho, int32_t* frd, int32_t* fid,
-              long long maxf, const UniqOut& uo, unsigned long long* counters, int maxW) {
+              long long maxf, const UniqOut& uo, unsigned long long* counters, int maxW, bool regs) {
     if (d.C * d.R > KL_MAX_BLOCKS || d.P_src > 256) return -3;
     KlArgs a{};
     a.d = d;
@@ -74,7 +74,14 @@ int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, floa
     a.guard_can_bind = a.peeling_max <= 15.0 * (double)d.C * (double)d.B ? 1 : 0;
     a.rel_floor = 1e-10f;
     const int nw = nw_of(d.ld);
-    NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_CT), [&]() { k4_peel_loop_kernel<NW, false>(a, blk); }));
+    const int rc_form = !regs ? 0 : (d.R == 1 && d.P_src <= 56) ? 1 : (d.R <= 3 && d.P_src <= 48) ? 3 : 0;
+    if (rc_form == 1) {
+        NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_CT), [&]() { k4_peel_loop_kernel<NW, false, 1>(a, blk); }));
+    } else if (rc_form == 3) {
+        NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_CT), [&]() { k4_peel_loop_kernel<NW, false, 3>(a, blk); }));
+    } else {
+        NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_CT), [&]() { k4_peel_loop_kernel<NW, false, 0>(a, blk); }));
+    }
     return 0;
 }
 
@@ -107,10 +114,11 @@ int emu_peel(int q, int n, int b, int C, int P, int P_src, int channel, int sour
     unsigned long long counters[8] = {0};
     memset(seen0, 0, (size_t)d.B * sizeof(int32_t));
     const int nw = nw_of(d.ld);
-    if (impl >= 2) {            // 2: the on-device loop with the product's tile width (<= 128 bins), 3: 32-bin tiles
+    if (impl >= 2) {            // on-device loop: 2 = product's tile width, bins in shared memory; 3 = 32-bin tiles;
+                                // 4 = product's tile width, candidate bins in registers when the shape allows
         UniqOut uo{seen0, uk, usum, ucnt, ukey, unext, max_uniq};
         if (int rc = peel_loop(d, reinterpret_cast<const float2*>(U), find_cj, find_k, reinterpret_cast<float2*>(find_rho), find_round,
-                               find_id, max_finds, uo, counters, impl == 2 ? 128 : 32))
+                               find_id, max_finds, uo, counters, impl == 3 ? 32 : 128, impl == 4))
             return rc;
         if (counters[6]) return -1;
         if ((long long)counters[4] > max_uniq) return -2;

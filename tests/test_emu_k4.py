@@ -1,5 +1,5 @@
 """CPU: the DEVICE source of the K4 kernels (qsft_b200/csrc/k4_peel.cu: classification, reduce, apply, the stand-alone
-detectors; k4_peel_loop.cu: the persistent on-device round loop as impl 2 / 3 = 128- / 32-bin tiles, one block) executed by the SIMT emulation in tests/emu (g++, one OS thread per CUDA thread) and
+detectors; k4_peel_loop.cu: the persistent on-device round loop as impl 2 / 3 = 128- / 32-bin tiles, 4 = candidate bins in registers; one block) executed by the SIMT emulation in tests/emu (g++, one OS thread per CUDA thread) and
 compared with the fixtures of the unmodified reference.  This checks the kernels' LOGIC without a GPU -- indexing,
 reductions, decisions, the round loop; it says nothing about the memory model or speed, and it is test infrastructure:
 the product has no CPU path."""
@@ -109,7 +109,7 @@ def _problem_from_golden(g, p, nso_subtype="nso1"):
     return Problem(q, n, p["trb"], list(g["mdu_Ms"]), D, p["P_src"], channel, cutoff), U
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4])
 @pytest.mark.parametrize("name", FULL_CASES + WIDE_FULL_CASES)
 def test_emulated_peel_from_reference_bins(emu, name, impl):
     """The kernels' round loop on the reference's own bins: same distinct coefficients in the same first-seen order."""
@@ -122,7 +122,7 @@ def test_emulated_peel_from_reference_bins(emu, name, impl):
     assert np.max(np.abs(vals - g["res_vals"])) <= 1e-5 * np.max(np.abs(g["res_vals"]))
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 4])
 @pytest.mark.parametrize("name", NSO2_CASES)
 def test_emulated_peel_nso2(emu, name, impl):
     g = load_golden(name)
@@ -242,7 +242,7 @@ def test_emulated_peel_coded_source_vs_oracle(emu):
     U = np.ascontiguousarray(np.array([np.vstack(us) for us in Us]).astype(np.complex64))
     D = np.array([np.vstack(d) for d in Ds])
     prob = Problem(q, n, b, Ms, D, sig.get_source_parity(), 1, 1e-9, rs=ReedSolomon(n, t, q))
-    for impl in (1, 2):
+    for impl in (1, 2, 4):
         keys, vals, _, _ = prob.peel(emu, U.copy(), impl)
         assert keys == list(want.keys()) and len(keys) >= 0.8 * len(signal_w)
     assert np.max(np.abs(vals - np.array(list(want.values())))) <= 1e-5

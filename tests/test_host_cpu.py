@@ -372,3 +372,37 @@ def test_reconstruct_host_stage_and_dispatch_errors():
         reconstruct.singleton_detection(np.ones(5, dtype=complex), method_source="bogus", method_channel="nso", q=3)
     with pytest.raises(ValueError):
         reconstruct.singleton_detection(np.ones(5, dtype=complex), method_source="coded", method_channel="nso", q=3)
+
+
+def test_sparse_spectrum_behaves_like_the_reference_dict():
+    """QSFT.transform's result container (qsft_b200/result.py): a dict {tuple(k): complex} filled on first use."""
+    import copy
+    import pickle
+    from qsft_b200.result import SparseSpectrum
+    rng = np.random.default_rng(5)
+    loc = rng.integers(0, 4, (50, 7)).astype(np.int8)
+    loc = np.unique(loc, axis=0)[::-1].copy()                # distinct keys, some fixed order
+    val = rng.normal(size=len(loc)) + 1j * rng.normal(size=len(loc))
+    want = {tuple(int(v) for v in k): complex(c) for k, c in zip(loc, val)}
+
+    def fresh():
+        return SparseSpectrum(loc, val)
+
+    assert isinstance(fresh(), dict) and len(fresh()) == len(want) and bool(fresh())
+    assert fresh() == want and want == fresh() and not (fresh() != want)
+    assert list(fresh()) == list(want) and list(fresh().keys()) == list(want.keys())
+    assert list(fresh().items()) == list(want.items()) and list(fresh().values()) == list(want.values())
+    k0 = next(iter(want))
+    assert fresh()[k0] == want[k0] and k0 in fresh() and (9,) * 7 not in fresh() and fresh().get((9,) * 7, 1.5) == 1.5
+    assert dict(fresh()) == want and {**fresh()} == want and fresh().copy() == want
+    assert pickle.loads(pickle.dumps(fresh())) == want and copy.deepcopy(fresh()) == want
+    assert repr(fresh()) == repr(want)
+    d = fresh()
+    d[(9,) * 7] = 2j
+    assert len(d) == len(want) + 1 and d.pop((9,) * 7) == 2j and d == want
+    d = fresh()
+    del d[k0]
+    assert len(d) == len(want) - 1 and k0 not in d
+    assert np.array_equal(fresh().locations, loc) and np.array_equal(fresh().coefficients, val)
+    empty = SparseSpectrum(np.zeros((0, 7), dtype=np.int8), np.zeros(0, dtype=complex))
+    assert len(empty) == 0 and not empty and empty == {} and list(empty.items()) == []
