@@ -81,7 +81,8 @@ constexpr int KL_G = 8;                      // lanes per bin in the group phase
 constexpr int KL_MAXW = 128;                 // bins per tile, at most
 constexpr int KL_MAX_STAGES = 6;
 constexpr int KL_SYM = 2 * QSFT_MAX_N;       // per group: detected symbols + decoded k
-constexpr int KL_CTRL_BYTES = 256 + KL_MAX_STAGES * 576 + KL_NC * 4 * KL_SYM;
+constexpr int KL_MB = 32;                    // mailbox entries per candidate warp (at most 6 stages x 3 groups pending)
+constexpr int KL_CTRL_BYTES = 256 + KL_MAX_STAGES * 576 + KL_NC * KL_MB * 4 + 128 + KL_NC * 4 * KL_SYM;
 
 // ---- tile access -------------------------------------------------------------------------------------------------
 // stage = [repeat r][chunk ch (16 bins)][row i][128 B: 16 bins, 16-byte chunks xor-swizzled with the line index & 7]
@@ -182,6 +183,9 @@ struct KlTileInfo {
     unsigned mask[4];                        // work items of the tile: bins that are not zerotons or carry peeled balls
     unsigned tmask[4];                       // ... of which: bins with peeled balls (their energy is not known yet)
     float e[KL_MAXW];                        // bin energies (bins without peeled balls)
+    long long j0;                            // first bin of the tile
+    int c;                                   // group
+    int left;                                // item groups (of four bins) not yet copied out of the stage
 };
 
 // ---- scanner warps: energies and the tile's work list ----------------------------------------------------------------------
@@ -250,7 +254,7 @@ __device__ __forceinline__ void kl_scan(const KlArgs& a, uint8_t* stage, long lo
 // ---- candidate warps (cw = 0 .. KL_NC - 1): this warp's share of the tile's work items, four at a time ------------------
 template <int NW>
 __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const KlTileInfo* info, int c, long long j0, int round,
-                                        int slot, uint8_t* s_symw, const float2* s_tw, bool structured,
+                                        int g, uint8_t* s_symw, const float2* s_tw, bool structured,
                                         const long long (&wgt)[32 / KL_G], unsigned& n_multi) {
     const PeelDev& d = a.d;
     const int lane = threadIdx.x & 31;
@@ -263,8 +267,8 @@ __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const K
     uint8_t* sym = s_symw + grp * KL_SYM;
     const unsigned mask[4] = {info->mask[0], info->mask[1], info->mask[2], info->mask[3]};
     const int total = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
-    for (int base = 4 * slot; base < total; base += 4 * KL_NC) {
-        const int rank = base + grp;
+    {
+        const int rank = 4 * g + grp;
         const int my = rank < total ? kl_pick(mask, rank) : -1;
         bool act = my >= 0;
         const int lbm = act ? my : 0;
@@ -409,8 +413,9 @@ __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const K
 // Same decisions and the same arithmetic as kl_cand.
 template <int NW, int RMAX, int MIMAX>
 __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, const KlTileInfo* info, int c, long long j0, int round,
-                                             int slot, uint8_t* s_symw, const float2* s_tw, bool structured,
-                                             const long long (&wgt)[32 / KL_G], unsigned& n_multi, uint64_t* empty_bar) {
+                                             int g, uint8_t* s_symw, const float2* s_tw, bool structured,
+                                             const long long (&wgt)[32 / KL_G], unsigned& n_multi, uint64_t* empty_bar,
+                                             KlTileInfo* info_rw) {
     const PeelDev& d = a.d;
     const int lane = threadIdx.x & 31;
     const int grp = lane / KL_G, gl = lane % KL_G;
@@ -422,18 +427,8 @@ __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, co
     uint8_t* sym = s_symw + grp * KL_SYM;
     const unsigned mask[4] = {info->mask[0], info->mask[1], info->mask[2], info->mask[3]};
     const int total = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
-    bool released = false;
-    auto release = [&]() {
-        released = true;
-#ifndef QSFT_EMU
-        if (empty_bar != nullptr) {
-            __syncwarp();
-            if (lane == 0) tma::mbar_arrive(empty_bar);
-        }
-#endif
-    };
-    for (int base = 4 * slot; base < total; base += 4 * KL_NC) {
-        const int rank = base + grp;
+    {
+        const int rank = 4 * g + grp;
         const int my = rank < total ? kl_pick(mask, rank) : -1;
         bool act = my >= 0;
         const int lbm = act ? my : 0;
@@ -452,7 +447,13 @@ __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, co
         float e_b = info->e[lbm];
         const bool touched = act && round > 1 && ((info->tmask[lbm >> 5] >> (lbm & 31)) & 1u);
         int f = touched ? s_head[lbm] - 1 : -1;
-        if (base + 4 * KL_NC >= total) release();              // last item of this warp in the tile: the stage is free
+#ifndef QSFT_EMU
+        if (empty_bar != nullptr) {
+            // the group is out of the stage; whoever takes the tile's last group hands the stage back to the producer
+            __syncwarp();
+            if (lane == 0 && atomicSub(&info_rw->left, 1) == 1) tma::mbar_arrive(empty_bar);
+        }
+#endif
         // bins with peeled balls (qsft.py:223-241 applied to the register copy), then their energy
         if (round > 1 && __ballot_sync(0xffffffffu, touched)) {
             while (__ballot_sync(0xffffffffu, f >= 0)) {
@@ -639,43 +640,48 @@ __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, co
         }
         __syncwarp();
     }
-    if (!released) release();
 }
 
 // dispatch on the register-resident form: RC = 1: R = 1, P_src <= 56; RC = 3: R <= 3, P_src <= 48; RC = 0: shared memory
 template <int NW, int RC>
-__device__ __forceinline__ void kl_cand_any(const KlArgs& a, uint8_t* stage, const KlTileInfo* info, int c, long long j0, int round,
-                                            int slot, uint8_t* s_symw, const float2* s_tw, bool structured,
-                                            const long long (&wgt)[32 / KL_G], unsigned& n_multi, uint64_t* empty_bar) {
+__device__ __forceinline__ void kl_cand_any(const KlArgs& a, uint8_t* stage, KlTileInfo* info, int c, long long j0, int round, int g,
+                                            uint8_t* s_symw, const float2* s_tw, bool structured, const long long (&wgt)[32 / KL_G],
+                                            unsigned& n_multi, uint64_t* empty_bar) {
     if (RC == 1) {
-        kl_cand_regs<NW, 1, 7>(a, stage, info, c, j0, round, slot, s_symw, s_tw, structured, wgt, n_multi, empty_bar);
+        kl_cand_regs<NW, 1, 7>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, empty_bar, info);
     } else if (RC == 3) {
-        kl_cand_regs<NW, 3, 6>(a, stage, info, c, j0, round, slot, s_symw, s_tw, structured, wgt, n_multi, empty_bar);
+        kl_cand_regs<NW, 3, 6>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, empty_bar, info);
     } else {
-        kl_cand<NW>(a, stage, info, c, j0, round, slot, s_symw, s_tw, structured, wgt, n_multi);
+        kl_cand<NW>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi);
 #ifndef QSFT_EMU
         if (empty_bar != nullptr) {
-            // this warp is done with the stage; its in-place updates (generic proxy) are ordered before the next bulk copy
+            // done with the stage; in-place updates (generic proxy) are ordered before the next bulk copy
             if (round > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if ((threadIdx.x & 31) == 0) tma::mbar_arrive(empty_bar);
+            if ((threadIdx.x & 31) == 0 && atomicSub(&info->left, 1) == 1) tma::mbar_arrive(empty_bar);
         }
 #endif
     }
 }
 
 // ---- one classification round ---------------------------------------------------------------------------------------
-// TMA variant: warp roles -- KL_NS scanner warps (threads 0 .. 127), KL_NC candidate warps, 1 producer warp -- coupled only
-// through the stages' mbarriers (full: tile landed; scanned: work list ready; empty: every candidate warp is done), so the
-// streaming scan of the next tiles overlaps the latency-bound candidate work of the previous ones.
-// Plain variant: the same two functions separated by CTA barriers, single stage.
+// TMA variant, warp roles: 1 producer warp; 2 scanner teams of 2 warps (alternate tiles); KL_NC candidate warps.
+//   producer -> scanners : the stage's `full` mbarrier (bulk copies landed)
+//   scanners -> candidates: per-warp MAILBOXES in shared memory.  After its scan the team's leader hands the tile's groups of
+//                          four work items round-robin to the candidate warps, in tile order (the two teams take turns
+//                          through `s_pub`), and after the CTA's last tile of the round a sentinel.  A candidate warp only
+//                          ever touches tiles it has work in, so a warp busy with one tile's candidates (microseconds of
+//                          latency-bound work) never holds up the stages of other tiles.
+//   candidates -> producer: the tile's `left` counter; whoever copies the last group out of the stage (or the scanner, when
+//                          the tile has no work) arrives on the stage's `empty` mbarrier.
+// Plain variant: scan and candidate work separated by CTA barriers, groups assigned statically, single stage.
 template <int NW, bool TMA, int RC>
 __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk,
 #ifndef QSFT_EMU
                                             const CUtensorMap* maps,
 #endif
-                                            int round, uint8_t* stages, uint64_t* bars, unsigned int& tiles_done, KlTileInfo* infos,
-                                            uint8_t* s_sym, const float2* s_tw) {
+                                            int round, uint8_t* stages, uint64_t* bars, unsigned int& tiles_done, unsigned int& mb_head,
+                                            KlTileInfo* infos, unsigned int* mbox, uint8_t* s_sym, const float2* s_tw) {
     const PeelDev& d = a.d;
     const int W = a.W, R = d.R, P_src = d.P_src;
     const long long B = d.B;
@@ -697,7 +703,8 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
     if (TMA) {
         uint64_t* full = bars;
         uint64_t* empty = bars + KL_MAX_STAGES;
-        uint64_t* scanned = bars + 2 * KL_MAX_STAGES;
+        unsigned int* mb_tail = mbox + KL_NC * KL_MB;              // [KL_NC] entries handed to each warp so far
+        volatile unsigned int* s_pub = mbox + KL_NC * KL_MB + KL_NC;   // tiles published so far (CTA-wide sequence number)
         unsigned int it = tiles_done;
         if (warp == KL_NS + KL_NC) {
             // ---- producer warp --------------------------------------------------------------------------------------
@@ -727,23 +734,53 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
                 const uint32_t ph = (it / (unsigned)a.nstages) & 1u;
                 const int c = (int)(tt / tpg);
                 const long long j0 = (tt - (long long)c * tpg) << a.lgW;
+                KlTileInfo* info = &infos[st];
                 tma::mbar_wait(&full[st], ph);
-                kl_scan(a, stages + (size_t)st * a.stage_bytes, j0, round, &infos[st], t);
-                __syncwarp();
-                if (lane == 0) tma::mbar_arrive(&scanned[st]);
+                kl_scan(a, stages + (size_t)st * a.stage_bytes, j0, round, info, t);
+                if (team == 0) asm volatile("bar.sync 2, 64;" ::: "memory");
+                else asm volatile("bar.sync 3, 64;" ::: "memory");
+                if (t == 0) {
+                    while (*s_pub != it) __nanosleep(20);           // tiles are published in order
+                    __threadfence_block();
+                    const int total = __popc(info->mask[0]) + __popc(info->mask[1]) + __popc(info->mask[2]) + __popc(info->mask[3]);
+                    const int ng = (total + 3) >> 2;
+                    info->j0 = j0;
+                    info->c = c;
+                    info->left = ng;
+                    __threadfence_block();
+                    if (ng == 0) tma::mbar_arrive(&empty[st]);
+                    unsigned int w = (5u * it) % (unsigned)KL_NC;
+                    for (int g = 0; g < ng; ++g) {
+                        const unsigned int slot = mb_tail[w]++;
+                        *reinterpret_cast<volatile unsigned int*>(&mbox[w * KL_MB + (slot & (KL_MB - 1))]) =
+                            0x80000000u | ((unsigned)st << 8) | (unsigned)g;
+                        w = w + 1 == (unsigned)KL_NC ? 0u : w + 1;
+                    }
+                    if (tt + gridDim.x >= n_tiles)                   // the CTA's last tile of the round: everybody goes home
+                        for (int cw = 0; cw < KL_NC; ++cw) {
+                            const unsigned int slot = mb_tail[cw]++;
+                            *reinterpret_cast<volatile unsigned int*>(&mbox[cw * KL_MB + (slot & (KL_MB - 1))]) = 0x800000ffu;
+                        }
+                    __threadfence_block();
+                    *s_pub = it + 1;
+                }
             }
-        } else {
+        } else if (mine > 0) {
             // ---- candidate warps ------------------------------------------------------------------------------------
             const int cw = warp - KL_NS;
-            for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++it) {
-                const int st = (int)(it % (unsigned)a.nstages);
-                const uint32_t ph = (it / (unsigned)a.nstages) & 1u;
-                const int c = (int)(tt / tpg);
-                const long long j0 = (tt - (long long)c * tpg) << a.lgW;
-                tma::mbar_wait(&scanned[st], ph);
-                tma::mbar_wait(&full[st], ph);                     // already complete: makes the bulk copies visible here too
-                kl_cand_any<NW, RC>(a, stages + (size_t)st * a.stage_bytes, &infos[st], c, j0, round,
-                                    (int)((cw + 5u * it) % (unsigned)KL_NC), s_symw, s_tw, structured, wgt, n_multi, &empty[st]);
+            for (;;) {
+                volatile unsigned int* slot = &mbox[cw * KL_MB + (mb_head & (KL_MB - 1))];
+                unsigned int e;
+                while ((e = *slot) == 0u) __nanosleep(20);
+                __syncwarp();
+                if (lane == 0) *slot = 0u;
+                ++mb_head;
+                __threadfence_block();
+                if ((e & 0xffu) == 0xffu) break;
+                const int st = (int)((e >> 8) & 7u), g = (int)(e & 0xffu);
+                KlTileInfo* info = &infos[st];
+                kl_cand_any<NW, RC>(a, stages + (size_t)st * a.stage_bytes, info, info->c, info->j0, round, g, s_symw, s_tw, structured,
+                                    wgt, n_multi, &empty[st]);
             }
         }
         tiles_done += (unsigned int)mine;
@@ -771,9 +808,11 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
             __syncthreads();
             if (warp < 2) kl_scan(a, stages, j0, round, &infos[0], (int)threadIdx.x);
             __syncthreads();
-            if (is_cand)
-                kl_cand_any<NW, RC>(a, stages, &infos[0], c, j0, round, (int)((warp - KL_NS + 5u * it) % (unsigned)KL_NC), s_symw, s_tw,
-                                    structured, wgt, n_multi, nullptr);
+            if (is_cand) {
+                const int total = __popc(infos[0].mask[0]) + __popc(infos[0].mask[1]) + __popc(infos[0].mask[2]) + __popc(infos[0].mask[3]);
+                for (int g = (int)((warp - KL_NS + 5u * it) % (unsigned)KL_NC); 4 * g < total; g += KL_NC)
+                    kl_cand_any<NW, RC>(a, stages, &infos[0], c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, nullptr);
+            }
         }
         tiles_done += (unsigned int)mine;
     }
@@ -869,21 +908,25 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
     uint8_t* base = kl_smem;
 #endif
     uint8_t* ctrl = base + (size_t)a.nstages * a.stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);                           // full[6], empty[6], scanned[6]
-    KlTileInfo* infos = reinterpret_cast<KlTileInfo*>(ctrl + 256);                // [KL_MAX_STAGES], 576 bytes apart
-    uint8_t* s_sym = ctrl + 256 + KL_MAX_STAGES * 576;                            // [KL_NC][4][KL_SYM]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);                           // full[6], empty[6]
+    KlTileInfo* infos = reinterpret_cast<KlTileInfo*>(ctrl + 256);                // [KL_MAX_STAGES], at most 576 bytes each
+    unsigned int* mbox = reinterpret_cast<unsigned int*>(ctrl + 256 + KL_MAX_STAGES * 576);   // mailboxes, tails, s_pub
+    uint8_t* s_sym = ctrl + 256 + KL_MAX_STAGES * 576 + KL_NC * KL_MB * 4 + 128;  // [KL_NC][4][KL_SYM]
+    static_assert(sizeof(KlTileInfo) <= 576 && KL_NC * 4 + 4 <= 128, "control block layout");
 #ifndef QSFT_EMU
-    if (TMA && threadIdx.x == 0) {
-        for (int i = 0; i < KL_MAX_STAGES; ++i) {
-            tma::mbar_init(&bars[i], 1);
-            tma::mbar_init(&bars[KL_MAX_STAGES + i], KL_NC);
-            tma::mbar_init(&bars[2 * KL_MAX_STAGES + i], KL_NS / 2);
+    if (TMA) {
+        for (int i = threadIdx.x; i < KL_NC * KL_MB + 32; i += blockDim.x) mbox[i] = 0u;
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < KL_MAX_STAGES; ++i) {
+                tma::mbar_init(&bars[i], 1);
+                tma::mbar_init(&bars[KL_MAX_STAGES + i], 1);
+            }
+            tma::mbar_fence_init();
         }
-        tma::mbar_fence_init();
     }
 #endif
     __syncthreads();
-    unsigned int epoch = 0, tiles_done = 0;
+    unsigned int epoch = 0, tiles_done = 0, mb_head = 0;
     long long total = 0;
     double num_peeling = 0;
     int round = 0;
@@ -894,7 +937,7 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
 #ifndef QSFT_EMU
                              maps.m,
 #endif
-                             round, base, bars, tiles_done, infos, s_sym, s_tw);
+                             round, base, bars, tiles_done, mb_head, infos, mbox, s_sym, s_tw);
         kl_grid_barrier(a.gbar, epoch);
         const long long now = (long long)__ldcg(a.counters + 0);
         const long long multis = (long long)__ldcg(a.multi + round);

@@ -243,7 +243,7 @@ __device__ __noinline__ bool rs_decode(const PeelDev& d, const uint8_t* sym, uin
 // ---------------------------------------------------------------------------------------------------------
 // angle_q: (((angle mod 2 pi) // (pi / q)) + 1) // 2 mod q in fp64 like NumPy (np.angle of a complex128 holding the
 // fp32 value; the float floor divisions are exact small integers)
-__device__ __noinline__ int angle_q_dev(float2 v, int q) {
+__device__ __forceinline__ int angle_q_dev(float2 v, int q) {
     double a = atan2((double)v.y, (double)v.x);
     if (a < 0.0) a += kTwoPi;                      // numpy: angle % (2 pi)
     if (a >= kTwoPi) a -= kTwoPi;

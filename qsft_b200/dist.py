@@ -106,6 +106,35 @@ class DistContext:
     def barrier(self):
         td.barrier(group=self.group)
 
+    # -- agreement of host-side randomness --------------------------------------------------------------------------
+    # Ms / Ds, the group / repeat selection of get_MDU and the noise seed are drawn from the host NumPy RNG on every rank
+    # (the reference's RNG order).  Ranks that were seeded differently would transform with different matrices and the
+    # gathered bins would silently mix them, so: the matrices are compared (hash all-gather, error on mismatch) and small
+    # index arrays are taken from rank 0.
+    def _device(self):
+        return torch.device("cuda", torch.cuda.current_device()) if td.get_backend(self.group) == "nccl" else torch.device("cpu")
+
+    def assert_same(self, what, *arrays):
+        """Raises on every rank when the byte contents of `arrays` differ between ranks."""
+        import hashlib
+        h = hashlib.blake2b(digest_size=8)
+        for a in arrays:
+            a = np.ascontiguousarray(a)
+            h.update(str(a.shape).encode())
+            h.update(a.tobytes())
+        mine = torch.tensor([int.from_bytes(h.digest(), "little", signed=True)], dtype=torch.int64, device=self._device())
+        everyone = torch.empty(self.world_size, dtype=torch.int64, device=mine.device)
+        td.all_gather_into_tensor(everyone, mine, group=self.group)
+        if not bool((everyone == everyone[0]).all()):
+            raise RuntimeError(f"{what} differ between ranks: seed the NumPy RNG identically on every rank (or pass the same "
+                               f"Ms= / Ds=), the delay rows of ONE transform are sharded over the ranks")
+
+    def from_rank0(self, arr):
+        """The int64 array `arr` of rank 0, on every rank (same shape everywhere)."""
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to(self._device())
+        td.broadcast(t, src=td.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        return t.cpu().numpy()
+
 
 def bin_range(B, rank, world):
     per = -(-B // world)

@@ -81,6 +81,9 @@ class SubsampledSignal(Signal):
                 save_data((self.Ms, self.Ds), path)
         else:
             self.Ms, self.Ds = get_Ms_and_Ds(self.n, self.q, **self.query_args)
+        if self.dist is not None and self.dist.world_size > 1:
+            self.dist.assert_same("the subsampling / delay matrices (Ms, Ds)", *[np.asarray(M) for M in self.Ms],
+                                  *[np.asarray(D) for Dc in self.Ds for D in Dc])
 
     def _row_shard(self, total_rows):
         """Contiguous slice of the flattened (c, r, p) delay rows owned by this rank."""
@@ -275,6 +278,10 @@ class SubsampledSignal(Signal):
         if ret_num_subsample <= self.num_subsample and ret_num_repeat <= self.num_repeat and b <= self.b:
             subsample_idx = np.random.choice(self.num_subsample, ret_num_subsample, replace=False)
             delay_idx = np.random.choice(self.num_repeat, ret_num_repeat, replace=False)
+            if self.dist is not None and self.dist.world_size > 1:
+                # every rank consumed the RNG like the reference; the selection itself is rank 0's on all ranks
+                both = self.dist.from_rank0(np.concatenate([subsample_idx, delay_idx]))
+                subsample_idx, delay_idx = both[:len(subsample_idx)], both[len(subsample_idx):]
             for i in subsample_idx:
                 Ms_ret.append(self.Ms[i][:, :b])
                 Ds_ret.append([])

@@ -47,7 +47,15 @@ def _worker(rank, world, port, out):
     # peel placement policy: replicated while U is small, sharded above the threshold or on request
     ok4 = (not ctx.shard_peel(1 << 30)) and ctx.shard_peel(9 << 30) and DistContext(peel_mode="sharded").shard_peel(8) \
         and not DistContext(peel_mode="replicated").shard_peel(1 << 40) and not ctx.symmetric
-    out[rank] = int(ok1 and ok2 and ok3 and ok4)
+    # agreement of host-side randomness: equal arrays pass, rank-dependent ones raise on every rank; rank 0's indices win
+    ctx.assert_same("test arrays", np.arange(6).reshape(2, 3), np.ones(4, dtype=np.int8))
+    try:
+        ctx.assert_same("test arrays", np.arange(6) + rank)
+        ok5 = False
+    except RuntimeError as exc:
+        ok5 = "differ between ranks" in str(exc)
+    ok5 = ok5 and ctx.from_rank0(np.array([3 + rank, 1, 2 * rank])).tolist() == [3, 1, 0]
+    out[rank] = int(ok1 and ok2 and ok3 and ok4 and ok5)
     td.destroy_process_group()
 
 
