@@ -83,7 +83,7 @@ k4_classify_kernel(PeelDev d, const float2* __restrict__ U, long long j_begin, l
         __syncwarp();
         // k digits (zero padded to 4 * NW bytes)
         if (d.source == 1) {
-            if (lane == 0) rs_decode(d, s_sym[warp], s_k[warp]);
+            if (lane == 0) rs_decode(rs_params(d), s_sym[warp], s_k[warp]);
         } else {
             for (int i = lane; i < d.n; i += 32) s_k[warp][i] = s_sym[warp][i];
         }
@@ -261,7 +261,7 @@ k4_detect_kernel(PeelDev d, const float2* __restrict__ cols, long long N, int8_t
     int nout = nsym;
     const uint8_t* src = s_sym[warp];
     if (d.source == 1) {
-        if (lane == 0) rs_decode(d, s_sym[warp], s_k[warp]);
+        if (lane == 0) rs_decode(rs_params(d), s_sym[warp], s_k[warp]);
         __syncwarp();
         nout = d.n;
         src = s_k[warp];

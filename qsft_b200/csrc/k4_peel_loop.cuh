@@ -327,7 +327,7 @@ __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const K
             kb = sym + QSFT_MAX_N;
             if (act) {
                 for (int i = d.n + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) kb[i] = 0;
-                if (gl == 0) rs_decode(d, sym, kb);
+                if (gl == 0) rs_decode(rs_params(d), sym, kb);
             }
             __syncwarp();
         }
@@ -410,7 +410,9 @@ __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const K
 // For R <= RMAX repeats and P_src <= 8 * MIMAX delay rows: every lane of the 8-lane group copies its rows (r, i = gl + 8 m) of
 // the bin into registers and the warp releases the stage right away, so the producer refills it while the latency-bound rest
 // (symbols, rho, hash, the find's atomics) runs; peeled balls are subtracted from the registers instead of shared memory.
-// Same decisions and the same arithmetic as kl_cand.
+// Same decisions and the same arithmetic as kl_cand.  Only for identity source decoding with structured delays, D[r][i] =
+// D[r][0] - e_(i-1) (identity / nso delay matrices; the host checks it): the phase of row (r, i) is then base(r) - digit(i-1),
+// no dot product per row.
 template <int NW, int RMAX, int MIMAX>
 __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, const KlTileInfo* info, int c, long long j0, int round,
                                              int g, uint8_t* s_symw, const float2* s_tw, bool structured,
@@ -476,7 +478,9 @@ __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, co
                             for (int m = 0; m < MIMAX; ++m) {
                                 const int i = gl + KL_G * m;
                                 if (i < P_src) {
-                                    const float2 w = s_tw[ph.row(r, i, tb)];
+                                    int t = i == 0 ? tb : tb - (int)sym[i - 1];         // structured delays: base - digit
+                                    t = t < 0 ? t + d.q : t;
+                                    const float2 w = s_tw[t];
                                     v[r][m].x -= rho.x * w.x - rho.y * w.y;
                                     v[r][m].y -= rho.x * w.y + rho.y * w.x;
                                 }
@@ -530,7 +534,7 @@ __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, co
                                 ar += (double)z[r].x * v[r][m].x + (double)z[r].y * v[r][m].y;
                                 ai += (double)z[r].y * v[r][m].x - (double)z[r].x * v[r][m].y;
                             }
-                        sv = symbol_nso1_exact(d, ar, ai);
+                        sv = symbol_nso1_exact(d.q, ar, ai);
                     }
                 } else {
                     long long votes = 0;
@@ -551,7 +555,7 @@ __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, co
             kb = sym + QSFT_MAX_N;
             if (act) {
                 for (int i = d.n + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) kb[i] = 0;
-                if (gl == 0) rs_decode(d, sym, kb);
+                if (gl == 0) rs_decode(rs_params(d), sym, kb);
             }
             __syncwarp();
         }
@@ -559,7 +563,6 @@ __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, co
 #pragma unroll
         for (int w = 0; w < NW; ++w) kw[w] = reinterpret_cast<const uint32_t*>(kb)[w];
         const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, kb, kw, structured};
-        const bool symphase = structured && d.source == 0;         // phase of row (r, i) = base(r) - symbol i
         // rho and the residual in one pass (see kl_cand)
         float sx = 0.f, sy = 0.f, s2 = 0.f;
         float2 z0 = make_float2(0.f, 0.f);
@@ -577,15 +580,8 @@ __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, co
                     for (int m = 0; m < MIMAX; ++m) {
                         const int i = gl + KL_G * m;
                         if (i < P_src) {
-                            int t;
-                            if (i == 0) {
-                                t = tb;
-                            } else if (symphase) {
-                                t = tb - symreg[m];
-                                t = t < 0 ? t + d.q : t;
-                            } else {
-                                t = ph.row(r, i, tb);
-                            }
+                            int t = i == 0 ? tb : tb - symreg[m];                       // structured delays: base - symbol
+                            t = t < 0 ? t + d.q : t;
                             const float2 w = s_tw[t];
                             const float dx = (w.x * v[r][m].x + w.y * v[r][m].y) - z0.x;     // conj(sig) * v - z0
                             const float dy = (w.x * v[r][m].y - w.y * v[r][m].x) - z0.y;

@@ -141,7 +141,16 @@ struct GF {
 
 // Syndrome decode: sym (2ts symbols of Z_q) -> k digits (n), returns false on decoder failure (k left all zero,
 // like galois returning the unchanged zero codeword with n_errors = -1).
-__device__ __noinline__ bool rs_decode(const PeelDev& d, const uint8_t* sym, uint8_t* kout) {
+// Out of line, with its parameters BY VALUE: a reference to the kernel's PeelDev parameter would force a local-memory copy of
+// the whole struct (and every d.field access through it); the decoder is long and rare, so it is one shared copy of code.
+struct RsParams {
+    int q, n, rs_t, rs_s, rs_order;
+    const int32_t* rs_exp;
+    const int32_t* rs_log;
+};
+__device__ __forceinline__ RsParams rs_params(const PeelDev& d) { return RsParams{d.q, d.n, d.rs_t, d.rs_s, d.rs_order, d.rs_exp, d.rs_log}; }
+
+__device__ __noinline__ bool rs_decode(RsParams d, const uint8_t* sym, uint8_t* kout) {
     GF F{d.q, d.rs_s, d.rs_order, d.rs_exp, d.rs_log};
     const int t = d.rs_t, s = d.rs_s, n = d.n, nt = d.rs_order - 1;
     const int T2 = 2 * t;
@@ -243,7 +252,7 @@ __device__ __noinline__ bool rs_decode(const PeelDev& d, const uint8_t* sym, uin
 // ---------------------------------------------------------------------------------------------------------
 // angle_q: (((angle mod 2 pi) // (pi / q)) + 1) // 2 mod q in fp64 like NumPy (np.angle of a complex128 holding the
 // fp32 value; the float floor divisions are exact small integers)
-__device__ __forceinline__ int angle_q_dev(float2 v, int q) {
+__device__ __noinline__ int angle_q_dev(float2 v, int q) {
     double a = atan2((double)v.y, (double)v.x);
     if (a < 0.0) a += kTwoPi;                      // numpy: angle % (2 pi)
     if (a >= kTwoPi) a -= kTwoPi;
@@ -284,21 +293,34 @@ __device__ __noinline__ int symbol_noiseless_exact(int q, float2 v0, float2 v) {
 
 // ---- decisions on values (shared by the column-accessor form below and the register-resident form of k4_peel_loop.cu) ----
 // noiseless (reconstruct.py:12-31): round(q (angle v - angle v0) / 2 pi) mod q = root nearest to the direction of v conj(v0)
+// fp32 paths for general q (one shared copy of the atan2f code; scalar parameters, see rs_decode); -1: too close to a
+// decision boundary for fp32, redo in fp64
+__device__ __noinline__ int symbol_noiseless_angle(int q, float2 v0, float2 v) {
+    if (!(fabsf(v0.x) + fabsf(v0.y) > 1e-30f && fabsf(v.x) + fabsf(v.y) > 1e-30f)) return -1;
+    const float u = (float)q * (atan2f(v.y, v.x) - atan2f(v0.y, v0.x)) * 0.15915494309189535f;
+    const float m = rintf(u);
+    if (!(fabsf(u - m) < 0.49f)) return -1;
+    int mi = (int)m;                            // |u| < q  =>  m in [-q, q]
+    mi = mi < 0 ? mi + q : mi;
+    return mi >= q ? mi - q : mi;
+}
+__device__ __noinline__ int symbol_nso1_angle(int q, float arf, float aif) {
+    if (!(fabsf(arf) + fabsf(aif) > 1e-30f)) return -1;
+    float thf = atan2f(aif, arf);
+    if (thf < 0.f) thf += 6.283185307179586f;
+    const float u = thf * (float)q * 0.15915494309189535f;              // in [0, q]
+    const float m = rintf(u);
+    if (!(fabsf(u - m) < 0.49f)) return -1;
+    return ((int)m >= q) ? (int)m - q : (int)m;                         // nearest of the q+1 roots, mod q
+}
+
 __device__ __forceinline__ int symbol_noiseless(const PeelDev& d, float2 v0, float2 v) {
     int symv = -1;
     if (d.fastdet && (d.q == 4 || d.q == 2))
         symv = quadrant_symbol(d.q, fmaf(v.x, v0.x, v.y * v0.y), fmaf(v.y, v0.x, -(v.x * v0.y)));
     // fast path in fp32; anything within 0.01 of a rounding boundary is redone in fp64 so the decision
     // always equals the fp64 one (np.angle / np.round in the reference)
-    if (symv < 0 && fabsf(v0.x) + fabsf(v0.y) > 1e-30f && fabsf(v.x) + fabsf(v.y) > 1e-30f) {
-        const float u = (float)d.q * (atan2f(v.y, v.x) - atan2f(v0.y, v0.x)) * 0.15915494309189535f;
-        const float m = rintf(u);
-        if (fabsf(u - m) < 0.49f) {
-            int mi = (int)m;                    // |u| < q  =>  m in [-q, q]
-            mi = mi < 0 ? mi + d.q : mi;
-            symv = mi >= d.q ? mi - d.q : mi;
-        }
-    }
+    if (symv < 0) symv = symbol_noiseless_angle(d.q, v0, v);
     if (symv < 0) symv = symbol_noiseless_exact(d.q, v0, v);
     return symv;
 }
@@ -308,33 +330,27 @@ __device__ __forceinline__ int symbol_noiseless(const PeelDev& d, float2 v0, flo
 __device__ __forceinline__ int symbol_nso1_fast(const PeelDev& d, float arf, float aif) {
     int symv = -1;
     if (d.fastdet && (d.q == 4 || d.q == 2)) symv = quadrant_symbol(d.q, arf, aif);
-    if (symv < 0 && fabsf(arf) + fabsf(aif) > 1e-30f) {
-        float thf = atan2f(aif, arf);
-        if (thf < 0.f) thf += 6.283185307179586f;
-        const float u = thf * (float)d.q * 0.15915494309189535f;        // in [0, q]
-        const float m = rintf(u);
-        if (fabsf(u - m) < 0.49f) symv = ((int)m >= d.q) ? (int)m - d.q : (int)m;   // nearest of the q+1 roots, mod q
-    }
+    if (symv < 0) symv = symbol_nso1_angle(d.q, arf, aif);
     return symv;
 }
 
 // ... and from the fp64 sum, exactly like NumPy: argmin over the q + 1 roots, first minimum (np.mean divides by R > 0: the
 // angle does not depend on it)
-__device__ __noinline__ int symbol_nso1_exact(const PeelDev& d, double ar, double ai) {
+__device__ __noinline__ int symbol_nso1_exact(int q, double ar, double ai) {
     double th = atan2(ai, ar);
     if (th < 0.0) th += kTwoPi;                                          // numpy: angle % (2 pi)
     if (th >= kTwoPi) th -= kTwoPi;
-    const double step = kTwoPi / (double)d.q;
+    const double step = kTwoPi / (double)q;
     int best = 0;
     double bd = fabs(0.0 - th);
-    for (int m = 1; m <= d.q; ++m) {
+    for (int m = 1; m <= q; ++m) {
         const double dist = fabs(step * (double)m - th);
         if (dist < bd) {
             bd = dist;
             best = m;
         }
     }
-    return best % d.q;
+    return best % q;
 }
 
 // nso2 (reconstruct.py:116-129): every repeat votes with its quantised phase difference; the votes are averaged as numbers,
@@ -367,7 +383,7 @@ __device__ __forceinline__ int detect_symbol(const PeelDev& d, const Col& col, i
             ar += (double)z.x * v.x + (double)z.y * v.y;
             ai += (double)z.y * v.x - (double)z.x * v.y;
         }
-        return symbol_nso1_exact(d, ar, ai);
+        return symbol_nso1_exact(d.q, ar, ai);
     }
     long long votes = 0;
     for (int r = 0; r < d.R; ++r) votes += nso2_vote(d, col.ri(r, 0), col.ri(r, i));

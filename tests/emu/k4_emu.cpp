@@ -74,7 +74,7 @@ int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, floa
     a.guard_can_bind = a.peeling_max <= 15.0 * (double)d.C * (double)d.B ? 1 : 0;
     a.rel_floor = 1e-10f;
     const int nw = nw_of(d.ld);
-    const int rc_form = !regs ? 0 : (d.R == 1 && d.P_src <= 56) ? 1 : (d.R <= 3 && d.P_src <= 48) ? 3 : 0;
+    const int rc_form = (!regs || !dflag || d.source != 0) ? 0 : (d.R == 1 && d.P_src <= 56) ? 1 : (d.R <= 3 && d.P_src <= 48) ? 3 : 0;
     if (rc_form == 1) {
         NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_CT), [&]() { k4_peel_loop_kernel<NW, false, 1>(a, blk); }));
     } else if (rc_form == 3) {
