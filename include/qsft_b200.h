@@ -141,11 +141,25 @@ int qsft_peel_reduce(const qsft_peel_desc* d, const int64_t* find_cj, const int8
  * (no multitons or no singletons, or 15 rounds, or q^n peels).  SYNCHRONOUS (reads round counters back).
  *   Outputs: finds grouped by round (order inside a round is unspecified): find_cj / find_k / find_rho /
  *   find_round as above.  *n_finds_out = total finds, *n_rounds_out = rounds; with uq != NULL also the distinct-k list
- *   (*n_uniq_out entries).  Workspaces: find_id (C, B) int32, counters (>= 8 x u64, device).                                                                            */
+ *   (*n_uniq_out entries).  Workspaces: find_id (C, B) int32, counters (>= 8 x u64, device).
+ *   The on-device loop hands find slots out to its warps in chunks: *n_finds_out counts SLOTS, and a slot f that was
+ *   not used carries find_cj[f] = -1 (skip it); the distinct-k list has no such gaps.                                                                            */
 int qsft_peel(const qsft_peel_desc* d, float* U, int64_t* find_cj, int8_t* find_k, float* find_rho,
               int32_t* find_round, int32_t* find_id, int64_t max_finds, unsigned long long* counters,
               const qsft_uniq* uq /* may be NULL */, int64_t* n_finds_out, int64_t* n_uniq_out, int* n_rounds_out,
               void* stream);
+
+/* The same loop on bins that are NOT one contiguous (C, P, B) array: blocks[c * R + r] (HOST array of C * R DEVICE
+ * pointers, R = P / P_src) -> the (P_src, ldU) complex64 rows of group c, repeat r, bin index contiguous, row stride ldU
+ * elements -- what SubsampledSignal.get_MDU hands to QSFT.transform (qsft/input_signal_subsampled.py:225-262: per-block
+ * row lists in a random group / repeat order; the reference vstacks copies of them, qsft.py:115-121).  The bins are only
+ * read: no private copy, no vstack.  Runs the persistent on-device loop (one cooperative kernel, every round on the
+ * device); returns QSFT_EUNSUPPORTED (-3, nothing done) when the shape does not fit it -- C * R > 16, P_src > 256 or a
+ * tile of 16 bins x P rows beyond the shared memory -- and the caller then assembles U and calls qsft_peel.          */
+int qsft_peel_blocks(const qsft_peel_desc* d, const float* const* blocks, int64_t ldU, int64_t* find_cj, int8_t* find_k,
+                     float* find_rho, int32_t* find_round, int32_t* find_id, int64_t max_finds, unsigned long long* counters,
+                     const qsft_uniq* uq /* may be NULL */, int64_t* n_finds_out, int64_t* n_uniq_out, int* n_rounds_out,
+                     void* stream);
 
 /* The reference's public detector entry point for a batch of columns.  Replaces reconstruct.singleton_detection
  * (qsft/reconstruct.py:132-168): channel stage noiseless (:12-31) / nso1 (:100-113) / nso2 (:116-129), then the

@@ -581,6 +581,30 @@ extern "C" int qsft_peel(const qsft_peel_desc* h, float* U, int64_t* find_cj, in
     return QSFT_OK;
 }
 
+extern "C" int qsft_peel_blocks(const qsft_peel_desc* h, const float* const* blocks, int64_t ldU, int64_t* find_cj, int8_t* find_k,
+                                float* find_rho, int32_t* find_round, int32_t* find_id, int64_t max_finds,
+                                unsigned long long* counters, const qsft_uniq* uq, int64_t* n_finds_out, int64_t* n_uniq_out,
+                                int* n_rounds_out, void* stream) {
+    PeelDev d;
+    if (int rc = make_dev(h, &d)) return rc;
+    QSFT_CHECK_ARG(blocks && find_cj && find_k && find_rho && find_round && find_id && counters && n_finds_out && n_rounds_out,
+                   "null pointer");
+    QSFT_CHECK_ARG(ldU >= d.B, "ldU=%lld smaller than q^b=%lld", (long long)ldU, (long long)d.B);
+    if (d.C * d.R > 16) return QSFT_EUNSUPPORTED;
+    for (int i = 0; i < d.C * d.R; ++i) QSFT_CHECK_ARG(blocks[i] != nullptr, "null block pointer");
+    UniqOut uo{};
+    if (uq) {
+        QSFT_CHECK_ARG(uq->seen0 && uq->uniq_k && uq->uniq_sum && uq->uniq_cnt && uq->uniq_key && uq->uniq_next && uq->max_uniq > 0,
+                       "incomplete qsft_uniq");
+        uo = UniqOut{uq->seen0, uq->uniq_k, uq->uniq_sum, uq->uniq_cnt, (long long*)uq->uniq_key, uq->uniq_next, uq->max_uniq};
+    }
+    int64_t nu = 0;
+    const int rc = qsft_peel_loop(d, blocks, ldU, find_cj, find_k, find_rho, find_round, find_id, max_finds, counters,
+                                  uq ? &uo : nullptr, n_finds_out, &nu, n_rounds_out, (cudaStream_t)stream);
+    if (rc == QSFT_OK && n_uniq_out) *n_uniq_out = nu;
+    return rc;
+}
+
 extern "C" int qsft_singleton_detect(const float* cols, int64_t N, int q, int n, int P, int P_src, int channel, int source,
                                      int rs_t, int rs_s, const int32_t* rs_exp, const int32_t* rs_log, int8_t* k_out,
                                      int ld_out, void* stream) {

@@ -42,9 +42,9 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
     KlMaps hm;
     memset(&hm, 0, sizeof(hm));
     for (int i = 0; i < nblk && use_tma; ++i) {
-        const cuuint64_t dims[3] = {32, (cuuint64_t)d.P_src, (cuuint64_t)(d.B / 16)};
-        const cuuint64_t strides[2] = {(cuuint64_t)ldU * 8, 128};
-        const cuuint32_t box[3] = {32, (cuuint32_t)d.P_src, (cuuint32_t)(a.W >> 4)};
+        const cuuint64_t dims[3] = {32, (cuuint64_t)(d.B / 16), (cuuint64_t)d.P_src};
+        const cuuint64_t strides[2] = {128, (cuuint64_t)ldU * 8};
+        const cuuint32_t box[3] = {32, (cuuint32_t)(a.W >> 4), (cuuint32_t)d.P_src};
         if (tma::make_map(&hm.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, blocks[i], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) !=
             QSFT_OK)
             use_tma = false;                                // a shape the tensor map cannot express: plain copies instead

@@ -10,10 +10,9 @@
 //
 // Classification of one round: the CTA walks over tiles of W bins (W = 128 .. 16) x all P delay rows of one group:
 //   * TMA variant (q^b a multiple of 16): 1 producer warp + 16 consumer warps, ring of 2 .. 6 stages.  A tile is ONE
-//     cp.async.bulk.tensor box {16 bins = 128 B, P_src rows, W / 16 chunks} per repeat block (every delay row contributes
-//     W * 8 contiguous bytes) and lands as [chunk][row][128 B] with the 128-byte swizzle, so that both access patterns are
-//     free of bank conflicts: lanes over bins (energy scan) and lanes over delay rows (detection, rho, residual).  The
-//     bins' ball-list heads travel with the tile (cp.async.bulk).
+//     cp.async.bulk.tensor box {16 bins = 128 B, W / 16 chunks, P_src rows} per repeat block (every delay row contributes
+//     W * 8 contiguous bytes) and lands as [row][chunk][128 B] with the 128-byte swizzle.  The bins' ball-list heads travel
+//     with the tile (cp.async.bulk).
 //   * plain variant (odd q^b, tiny q^b; also what the CPU emulation of tests/emu runs): the 16 consumer warps copy the tile
 //     with coalesced loads into the same layout, single stage.
 //   Step 0 (rounds > 1): bins with listed balls are updated in place by 8-lane groups.  Step 1: energies, 512 threads over
@@ -40,7 +39,7 @@ struct KlBlocks {
 };
 #ifndef QSFT_EMU
 struct KlMaps {
-    CUtensorMap m[KL_MAX_BLOCKS];            // the same blocks as 3-D tensors {32 floats, P_src rows, B / 16 chunks}
+    CUtensorMap m[KL_MAX_BLOCKS];            // the same blocks as 3-D tensors {32 floats, B / 16 chunks, P_src rows}
 };
 #endif
 
@@ -85,13 +84,19 @@ constexpr int KL_MB = 32;                    // mailbox entries per candidate wa
 constexpr int KL_CTRL_BYTES = 256 + KL_MAX_STAGES * 576 + KL_NC * KL_MB * 4 + 128 + KL_NC * 4 * KL_SYM;
 
 // ---- tile access -------------------------------------------------------------------------------------------------
-// stage = [repeat r][chunk ch (16 bins)][row i][128 B: 16 bins, 16-byte chunks xor-swizzled with the line index & 7]
+// stage = [repeat r][row i][chunk ch (16 bins)][128 B: 16 bins, 16-byte chunks xor-swizzled with the line index & 7]: every
+// delay row contributes W * 8 CONTIGUOUS bytes, and the bulk copy walks them in that order (128-byte pieces of a row one
+// after the other, then the next row): long DRAM bursts.  (With the rows as the faster box dimension the copy engine jumps a
+// whole row of U -- megabytes -- between consecutive 128-byte requests and DRAM delivers about half its bandwidth.)
+// Lanes over bins of one row (scan) are conflict free; lanes over rows of one bin (the one-time copy of a candidate bin into
+// registers) share banks, which is the cheaper side to pay on.
 struct TileCol {
     uint8_t* t;
     int P_src, box;
     int lb;                                  // local bin
+    int lgc;                                 // log2(chunks per row) = lgW - 4
     __device__ __forceinline__ int off(int r, int i) const {
-        const int line = (lb >> 4) * P_src + i;
+        const int line = (i << lgc) + (lb >> 4);
         return r * box + line * 128 + (((((lb & 15) >> 1) ^ (line & 7)) << 4) | ((lb & 1) << 3));
     }
     __device__ __forceinline__ float2 ri(int r, int i) const { return *reinterpret_cast<const float2*>(t + off(r, i)); }
@@ -157,6 +162,39 @@ __device__ __forceinline__ void kl_grid_barrier(unsigned int* gbar, unsigned int
     }
 }
 
+// Find slots are handed out to the warps in chunks of KL_CHUNK (one global atomic per chunk: a single counter bumped by every
+// warp of every SM for every group of candidates serialises in L2).  Slots of a chunk that stay unused at the end of a round
+// are marked with find_cj = -1; the link phase and every reader of the find list skip them.
+constexpr int KL_CHUNK = 64;
+struct KlSlots {
+    long long next, end;                     // this warp's chunk: slots [next, end) are free
+};
+
+// reserves `cnt` (<= 4, warp-uniform) consecutive slots; all lanes get the first one
+__device__ __forceinline__ long long kl_take(const KlArgs& a, KlSlots& sl, int cnt) {
+    const int lane = threadIdx.x & 31;
+    if (sl.next + cnt > sl.end) {
+        for (long long f = sl.next + lane; f < sl.end; f += 32)
+            if (f < a.max_finds) a.find_cj[f] = -1;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)KL_CHUNK);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        sl.next = (long long)base;
+        sl.end = sl.next + KL_CHUNK;
+    }
+    const long long f = sl.next;
+    sl.next += cnt;
+    return f;
+}
+
+// end of a round: the rest of the warp's chunk is given up
+__device__ __forceinline__ void kl_close(const KlArgs& a, KlSlots& sl) {
+    const int lane = threadIdx.x & 31;
+    for (long long f = sl.next + lane; f < sl.end; f += 32)
+        if (f < a.max_finds) a.find_cj[f] = -1;
+    sl.next = sl.end = 0;
+}
+
 // phase t = <D[c][r * P_src + i], k> mod q for the k whose digits sit in kb (bytes) / kw (words)
 template <int NW>
 struct KlPhase {
@@ -202,7 +240,7 @@ __device__ __forceinline__ void kl_scan(const KlArgs& a, uint8_t* stage, long lo
     }
     float e0 = 0.f, e1 = 0.f;
     if (valid0 && hd0 == 0) {
-        TileCol tc{stage, P_src, a.box, t};
+        TileCol tc{stage, P_src, a.box, t, a.lgW - 4};
         float ea = 0.f, eb = 0.f;
         for (int r = 0; r < R; ++r) {
             int i = 0;
@@ -219,7 +257,7 @@ __device__ __forceinline__ void kl_scan(const KlArgs& a, uint8_t* stage, long lo
         e0 = ea + eb;
     }
     if (valid1 && hd1 == 0) {
-        TileCol tc{stage, P_src, a.box, t + 64};
+        TileCol tc{stage, P_src, a.box, t + 64, a.lgW - 4};
         float ea = 0.f, eb = 0.f;
         for (int r = 0; r < R; ++r) {
             int i = 0;
@@ -255,7 +293,7 @@ __device__ __forceinline__ void kl_scan(const KlArgs& a, uint8_t* stage, long lo
 template <int NW>
 __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const KlTileInfo* info, int c, long long j0, int round,
                                         int g, uint8_t* s_symw, const float2* s_tw, bool structured,
-                                        const long long (&wgt)[32 / KL_G], unsigned& n_multi) {
+                                        const long long (&wgt)[32 / KL_G], unsigned& n_multi, KlSlots& slots) {
     const PeelDev& d = a.d;
     const int lane = threadIdx.x & 31;
     const int grp = lane / KL_G, gl = lane % KL_G;
@@ -273,7 +311,7 @@ __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const K
         bool act = my >= 0;
         const int lbm = act ? my : 0;
         const long long jb = j0 + lbm;
-        TileCol tc{stage, P_src, a.box, lbm};
+        TileCol tc{stage, P_src, a.box, lbm, a.lgW - 4};
         float e_b = info->e[lbm];
         // bins with peeled balls (qsft.py:223-241 applied to the shared-memory copy), then their energy
         const bool touched = act && round > 1 && ((info->tmask[lbm >> 5] >> (lbm & 31)) & 1u);
@@ -384,8 +422,7 @@ __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const K
         const bool lead = (gl == 0);
         const unsigned sb = __ballot_sync(0xffffffffu, lead && single);
         unsigned long long fbase = 0;
-        if (lane == 0 && sb) fbase = atomicAdd(&a.counters[0], (unsigned long long)__popc(sb));
-        fbase = __shfl_sync(0xffffffffu, fbase, 0);
+        if (sb) fbase = (unsigned long long)kl_take(a, slots, __popc(sb));
         unsigned long long f = fbase + (unsigned long long)__popc(sb & ((1u << lane) - 1u));
         f = __shfl_sync(0xffffffffu, f, lane & ~(KL_G - 1));
         if (single) {
@@ -417,7 +454,7 @@ template <int NW, int RMAX, int MIMAX>
 __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, const KlTileInfo* info, int c, long long j0, int round,
                                              int g, uint8_t* s_symw, const float2* s_tw, bool structured,
                                              const long long (&wgt)[32 / KL_G], unsigned& n_multi, uint64_t* empty_bar,
-                                             KlTileInfo* info_rw) {
+                                             KlTileInfo* info_rw, KlSlots& slots) {
     const PeelDev& d = a.d;
     const int lane = threadIdx.x & 31;
     const int grp = lane / KL_G, gl = lane % KL_G;
@@ -437,7 +474,7 @@ __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, co
         const long long jb = j0 + lbm;
         float2 v[RMAX][MIMAX];
         {
-            TileCol tc{stage, P_src, a.box, lbm};
+            TileCol tc{stage, P_src, a.box, lbm, a.lgW - 4};
 #pragma unroll
             for (int r = 0; r < RMAX; ++r)
 #pragma unroll
@@ -616,8 +653,7 @@ __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, co
         const bool lead = (gl == 0);
         const unsigned sb = __ballot_sync(0xffffffffu, lead && single);
         unsigned long long fbase = 0;
-        if (lane == 0 && sb) fbase = atomicAdd(&a.counters[0], (unsigned long long)__popc(sb));
-        fbase = __shfl_sync(0xffffffffu, fbase, 0);
+        if (sb) fbase = (unsigned long long)kl_take(a, slots, __popc(sb));
         unsigned long long fi = fbase + (unsigned long long)__popc(sb & ((1u << lane) - 1u));
         fi = __shfl_sync(0xffffffffu, fi, lane & ~(KL_G - 1));
         if (single) {
@@ -642,13 +678,13 @@ __device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, co
 template <int NW, int RC>
 __device__ __forceinline__ void kl_cand_any(const KlArgs& a, uint8_t* stage, KlTileInfo* info, int c, long long j0, int round, int g,
                                             uint8_t* s_symw, const float2* s_tw, bool structured, const long long (&wgt)[32 / KL_G],
-                                            unsigned& n_multi, uint64_t* empty_bar) {
+                                            unsigned& n_multi, uint64_t* empty_bar, KlSlots& slots) {
     if (RC == 1) {
-        kl_cand_regs<NW, 1, 7>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, empty_bar, info);
+        kl_cand_regs<NW, 1, 7>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, empty_bar, info, slots);
     } else if (RC == 3) {
-        kl_cand_regs<NW, 3, 6>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, empty_bar, info);
+        kl_cand_regs<NW, 3, 6>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, empty_bar, info, slots);
     } else {
-        kl_cand<NW>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi);
+        kl_cand<NW>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, slots);
 #ifndef QSFT_EMU
         if (empty_bar != nullptr) {
             // done with the stage; in-place updates (generic proxy) are ordered before the next bulk copy
@@ -686,6 +722,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long mine = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     unsigned n_multi = 0;
+    KlSlots slots{0, 0};
     const bool is_cand = warp >= KL_NS && warp < KL_NS + KL_NC;
     bool structured = false;
     long long wgt[32 / KL_G] = {0, 0, 0, 0};
@@ -717,7 +754,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
                     const uint32_t head_bytes = round > 1 ? (uint32_t)((left < W ? left : W) * 4) : 0u;
                     tma::mbar_expect_tx(&full[st], (uint32_t)R * box_bytes + head_bytes);
                     for (int r = 0; r < R; ++r)
-                        tma::load_3d(dst + (size_t)r * a.box, &maps[c * R + r], 0, 0, (int)(j0 >> 4), &full[st]);
+                        tma::load_3d(dst + (size_t)r * a.box, &maps[c * R + r], 0, (int)(j0 >> 4), 0, &full[st]);
                     if (head_bytes) tma::bulk_g2s(dst + (size_t)R * a.box, a.head + (size_t)c * B + j0, head_bytes, &full[st]);
                 }
             }
@@ -776,7 +813,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
                 const int st = (int)((e >> 8) & 7u), g = (int)(e & 0xffu);
                 KlTileInfo* info = &infos[st];
                 kl_cand_any<NW, RC>(a, stages + (size_t)st * a.stage_bytes, info, info->c, info->j0, round, g, s_symw, s_tw, structured,
-                                    wgt, n_multi, &empty[st]);
+                                    wgt, n_multi, &empty[st], slots);
             }
         }
         tiles_done += (unsigned int)mine;
@@ -792,7 +829,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
             {
                 const int lb = threadIdx.x & (W - 1), prt = threadIdx.x >> a.lgW, nparts = (int)blockDim.x >> a.lgW;
                 const long long jf = j0 + lb;
-                TileCol tc{stages, P_src, a.box, lb};
+                TileCol tc{stages, P_src, a.box, lb, a.lgW - 4};
                 for (int r = 0; r < R; ++r) {
                     const float2* src = blk.p[c * R + r] + jf;
                     for (int i = prt; i < P_src; i += nparts) tc.ref(r, i) = (jf < B) ? src[(size_t)i * a.ldU] : make_float2(0.f, 0.f);
@@ -807,11 +844,12 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
             if (is_cand) {
                 const int total = __popc(infos[0].mask[0]) + __popc(infos[0].mask[1]) + __popc(infos[0].mask[2]) + __popc(infos[0].mask[3]);
                 for (int g = (int)((warp - KL_NS + 5u * it) % (unsigned)KL_NC); 4 * g < total; g += KL_NC)
-                    kl_cand_any<NW, RC>(a, stages, &infos[0], c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, nullptr);
+                    kl_cand_any<NW, RC>(a, stages, &infos[0], c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, nullptr, slots);
             }
         }
         tiles_done += (unsigned int)mine;
     }
+    if (is_cand) kl_close(a, slots);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_multi += __shfl_xor_sync(0xffffffffu, n_multi, o);
     if (lane == 0 && n_multi) atomicAdd(&a.multi[round], (unsigned long long)n_multi);
@@ -825,6 +863,7 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, long long f0, long long
     const long long B = d.B;
     for (long long f = f0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; f < f1; f += (long long)gridDim.x * blockDim.x) {
         const long long cj = a.find_cj[f];
+        if (cj < 0) continue;                               // unused slot of a warp's chunk
         const int c = (int)(cj / B);
         uint32_t kw[NW];
         const uint32_t* kin = reinterpret_cast<const uint32_t*>(a.find_k + (size_t)f * d.ld);

@@ -324,7 +324,25 @@ class PeelProblem:
                                   rs_exp=0 if self.rs_exp is None else self.rs_exp.data_ptr(),
                                   rs_log=0 if self.rs_log is None else self.rs_log.data_ptr())
 
-    def alloc(self, max_finds, max_uniq=None):
+    _WORKSPACES = {}
+
+    def alloc(self, max_finds, max_uniq=None, reuse=False):
+        """Find / distinct-k buffers.  reuse=True takes them from a per-shape cache (one set per device and shape, handed
+        to one problem at a time): QSFT.transform peels one signal after the other and ~10 allocations of up to hundreds
+        of MB per transform are pure overhead."""
+        key = (str(self.device), self.C, self.B, self.ld, int(max_finds), int(max_uniq or max_finds))
+        if reuse and key in PeelProblem._WORKSPACES:
+            self.__dict__.update(PeelProblem._WORKSPACES[key])
+            self.counters.zero_()
+            return
+        self._alloc(max_finds, max_uniq)
+        if reuse:
+            names = ("max_finds", "find_cj", "find_k", "find_rho", "find_round", "find_id", "counters", "max_uniq", "seen0",
+                     "uniq_k", "uniq_sum", "uniq_cnt", "uniq_key", "uniq_next", "uniq")
+            PeelProblem._WORKSPACES.clear()            # keep one shape: the buffers are large
+            PeelProblem._WORKSPACES[key] = {nm: getattr(self, nm) for nm in names}
+
+    def _alloc(self, max_finds, max_uniq=None):
         dev = self.device
         self.max_finds = int(max_finds)
         self.find_cj = torch.empty(self.max_finds, dtype=torch.int64, device=dev)
@@ -357,6 +375,42 @@ class PeelProblem:
                                             _ptr(self.find_rho), _ptr(self.find_round), _ptr(self.find_id),
                                             self.max_finds, _ptr(self.counters), C.byref(self.uniq), C.byref(nf),
                                             C.byref(nu), C.byref(nr), _stream()))
+        self.n_uniq = nu.value
+        return nf.value, nr.value
+
+    def finds(self, n_finds):
+        """Host copy of the find list after peel(): (cj, k (F, n), rho, round) of the F valid finds among the first
+        `n_finds` slots (the on-device loop hands slots out in chunks per warp; unused ones carry find_cj = -1)."""
+        cj = self.find_cj[:n_finds].cpu().numpy()
+        ok = cj >= 0
+        return (cj[ok], self.find_k[:n_finds, :self.n].cpu().numpy()[ok], self.find_rho[:n_finds].cpu().numpy()[ok],
+                self.find_round[:n_finds].cpu().numpy()[ok])
+
+    def peel_blocks(self, blocks):
+        """The same loop on bins given as C * R separate (P_src, B) complex64 row blocks (block c * R + r; what get_MDU
+        returns), read in place -- no (C, P, B) copy.  Returns (n_finds, n_rounds), or None when the shape does not fit the
+        on-device loop (the caller then assembles U and uses peel())."""
+        R = self.P // self.P_src
+        if len(blocks) != self.C * R:
+            raise ValueError("expected C * R blocks")
+        ldU = None
+        for t in blocks:
+            _need_cuda(t)
+            if t.dtype != torch.complex64 or t.dim() != 2 or t.shape != (self.P_src, self.B):
+                raise ValueError("every block must be a (P_src, q^b) complex64 tensor")
+            ldU = t.stride(0) if ldU is None else ldU
+            if t.stride(0) != ldU:
+                return None
+        arr = (C.c_void_p * len(blocks))(*[C.c_void_p(t.data_ptr()) for t in blocks])
+        nf, nu, nr = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        with torch.cuda.device(self.device), _timed("k4_peel", self.C * self.P * self.B):
+            rc = _lib.lib().qsft_peel_blocks(C.byref(self.desc), arr, ldU, _ptr(self.find_cj), _ptr(self.find_k),
+                                             _ptr(self.find_rho), _ptr(self.find_round), _ptr(self.find_id), self.max_finds,
+                                             _ptr(self.counters), C.byref(self.uniq), C.byref(nf), C.byref(nu), C.byref(nr),
+                                             _stream())
+        if rc == -3:                                   # QSFT_EUNSUPPORTED
+            return None
+        _lib.check(rc)
         self.n_uniq = nu.value
         return nf.value, nr.value
 

@@ -44,18 +44,22 @@ class QSFT:
             print(f"Transform Time:{transform_time}", flush=True)
         peeling_start = time.time()
         dev = signal.device
-        # (C, P, B) bins; a private copy because peeling subtracts in place (the reference vstacks copies too)
-        # (one copy straight into place: the bins are 1-3 GB at the large configurations)
         C, P, B = len(Us), sum(int(u.shape[0]) for u in Us[0]), int(Us[0][0].shape[-1])
-        U = torch.empty((C, P, B), dtype=torch.complex64, device=dev)
-        for i, us in enumerate(Us):
-            row = 0
-            for u in us:
-                u = torch.as_tensor(u, device=dev)
-                U[i, row:row + u.shape[0]].copy_(u)
-                row += u.shape[0]
-            if row != P:
-                raise ValueError("every subsampling group must carry the same number of delay rows")
+        if any(sum(int(u.shape[0]) for u in us) != P for us in Us):
+            raise ValueError("every subsampling group must carry the same number of delay rows")
+
+        def stacked():
+            # (C, P, B) bins in one array -- a private copy: the host-driven rounds subtract in place (the reference vstacks
+            # copies too, qsft.py:115-121).  One copy straight into place: the bins are 1-3 GB at the large configurations.
+            U = torch.empty((C, P, B), dtype=torch.complex64, device=dev)
+            for i, us in enumerate(Us):
+                row = 0
+                for u in us:
+                    u = torch.as_tensor(u, device=dev)
+                    U[i, row:row + u.shape[0]].copy_(u)
+                    row += u.shape[0]
+            return U
+
         D = np.stack([np.vstack(d) for d in Ds])
         cutoff = 1e-9 + (1 + 0.5) * (signal.noise_sd ** 2) / (q ** b)   # noise threshold, qsft.py:124-125
         cutoff = kwargs.get("cutoff", cutoff)
@@ -73,14 +77,18 @@ class QSFT:
         dist = getattr(signal, "dist", None)
         shard = dist is not None and dist.world_size > 1
         if shard and hasattr(dist, "shard_peel"):
-            shard = dist.shard_peel(U.numel() * 8)
+            shard = dist.shard_peel(C * P * B * 8)
         if shard:
             from .dist import peel_sharded
-            n_rounds = peel_sharded(prob, U, dist)[4]
+            n_rounds = peel_sharded(prob, stacked(), dist)[4]
             n_finds = -1
         else:
-            prob.alloc(max_finds=min(15 * C * B, max(4096, 4 * C * B)), max_uniq=max(4096, C * B))
-            n_finds, n_rounds = prob.peel(U)
+            prob.alloc(max_finds=min(15 * C * B, max(4096, 4 * C * B)), max_uniq=max(4096, C * B), reuse=True)
+            # the on-device loop reads the blocks get_MDU returned where they lie (no copy)
+            blocks = [u if isinstance(u, torch.Tensor) else torch.as_tensor(u, device=dev) for us in Us for u in us]
+            fits = all(t.is_cuda and t.dtype == torch.complex64 and t.is_contiguous() for t in blocks)
+            done = prob.peel_blocks(blocks) if fits else None
+            n_finds, n_rounds = done if done is not None else prob.peel(stacked())
         self.last_stats = {"rounds": int(n_rounds), "finds": int(n_finds), "distinct": int(prob.n_uniq),
                            "cutoff": float(cutoff)}
         output = kwargs.get("output", "dict")

@@ -221,8 +221,7 @@ def test_k4_peel_from_reference_bins(name):
     prob = ops.PeelProblem(q, n, p["trb"], list(g["mdu_Ms"]), D, p["P_src"], p["chan"], p["src"], cutoff, DEV)
     prob.alloc(4 * U.shape[0] * U.shape[2])
     nf, nr = prob.peel(U)
-    gw, keys = qsft_b200.QSFT._finds_to_dict(prob.find_cj[:nf].cpu().numpy(), prob.find_k[:nf, :n].cpu().numpy(),
-                                              prob.find_rho[:nf].cpu().numpy(), prob.find_round[:nf].cpu().numpy())
+    gw, keys = qsft_b200.QSFT._finds_to_dict(*prob.finds(nf))
     want_keys = [tuple(int(v) for v in k) for k in g["res_keys"]]
     assert list(gw.keys()) == want_keys                   # same support, same first-seen order
     got = np.array([gw[k] for k in want_keys])
@@ -303,8 +302,7 @@ def test_peel_large_closed_form_exact_recovery():
     prob = ops.PeelProblem(q, n, b, Ms, D, n + 1, "nso", "identity", 1e-9, DEV)
     prob.alloc(4 * C * q ** b)
     nf, nr = prob.peel(U.contiguous())
-    gw, _ = qsft_b200.QSFT._finds_to_dict(prob.find_cj[:nf].cpu().numpy(), prob.find_k[:nf, :n].cpu().numpy(),
-                                           prob.find_rho[:nf].cpu().numpy(), prob.find_round[:nf].cpu().numpy())
+    gw, _ = qsft_b200.QSFT._finds_to_dict(*prob.finds(nf))
     assert set(gw.keys()) == set(sw.keys())
     err = max(abs(gw[k] - v) for k, v in sw.items())
     assert err < 1e-5, err

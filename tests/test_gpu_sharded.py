@@ -88,8 +88,7 @@ def test_sharded_peel_equals_single_gpu(name, world):
     single.alloc(4 * U0.shape[0] * U0.shape[2])
     U1 = U0.clone()
     nf, nr = single.peel(U1)
-    want, _ = qsft_b200.QSFT._finds_to_dict(single.find_cj[:nf].cpu().numpy(), single.find_k[:nf, :n].cpu().numpy(),
-                                             single.find_rho[:nf].cpu().numpy(), single.find_round[:nf].cpu().numpy())
+    want, _ = qsft_b200.QSFT._finds_to_dict(*single.finds(nf))
     results, distinct = _run_sharded(world, make_problem, U0)
     for dk, dv, dc in distinct:
         assert [tuple(int(v) for v in r) for r in dk] == list(want.keys())

@@ -276,9 +276,11 @@ def test_k4_device_loop_equals_host_driven_rounds(q, n, b, S, R, chan, noise, mo
     U0 = U.clone()
     nf_d, nr_d = prob.peel(U)
     assert torch.equal(U, U0)
+    nf_d = len(prob.finds(nf_d)[0])                          # valid finds (the loop hands slots out in chunks)
     k_d, v_d, c_d = prob.distinct()
     monkeypatch.setenv("QSFT_K4_IMPL", "1")
     nf_h, nr_h = prob.peel(U0)
+    assert len(prob.finds(nf_h)[0]) == nf_h
     k_h, v_h, c_h = prob.distinct()
     assert (nf_d, nr_d) == (nf_h, nr_h) and nf_d > 0
     assert np.array_equal(k_d, k_h) and np.array_equal(c_d, c_h)

@@ -101,6 +101,7 @@ out["k4_classify_kernel round 1 (stand-alone classification, C=3,P=41,B=4^10)"] 
 def peel_sig(Uin):
     nf, nr = prob.peel(Uin)
     torch.cuda.synchronize()
+    nf = int((prob.find_cj[:nf] >= 0).sum())                 # valid finds (slots are handed out in chunks)
     nu = prob.n_uniq
     k = prob.uniq_k[:nu].to(torch.int64)
     w = torch.arange(1, k.shape[1] + 1, device=dev, dtype=torch.int64)
