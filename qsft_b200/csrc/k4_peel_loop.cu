@@ -2,13 +2,11 @@
 // count NW in k4_peel_loop_nw8.cu / _nw16.cu / _nw32.cu so that the translation units compile in parallel).
 #include "k4_peel_loop.cuh"
 
-#include <vector>
-
-int qsft_kl_launch_nw8(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, int rc_form, size_t smem, int grid,
+int qsft_kl_launch_nw8(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, size_t smem, int grid,
                        cudaStream_t st);
-int qsft_kl_launch_nw16(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, int rc_form, size_t smem, int grid,
+int qsft_kl_launch_nw16(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, size_t smem, int grid,
                         cudaStream_t st);
-int qsft_kl_launch_nw32(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, int rc_form, size_t smem, int grid,
+int qsft_kl_launch_nw32(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, size_t smem, int grid,
                         cudaStream_t st);
 
 // Whole peel loop on the device.  blocks[c * R + r] -> (P_src, ldU) complex64 rows of group c, repeat r (device pointers,
@@ -73,6 +71,7 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
     a.has_uniq = uo ? 1 : 0;
     a.counters = counters;
     a.max_rounds = 15;
+    a.chunk = kl_chunk(d, sms);
     if (const char* mr = getenv("QSFT_K4_MAX_ROUNDS"))       // measurement aid (tools/microbench.py): cost of the first rounds alone
         if (atoi(mr) >= 1 && atoi(mr) < 15) a.max_rounds = atoi(mr);
     a.peeling_max = pow((double)d.q, (double)d.n);
@@ -84,34 +83,9 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
     QSFT_LAUNCHED();
     int rc;
     const int nw = d.ld / 4;
-    // candidate bins held in registers when they fit (the stage is released early), else worked on in shared memory
-    int rc_form = (d.R == 1 && d.P_src <= 56) ? 1 : (d.R <= 3 && d.P_src <= 48) ? 3 : 0;
-    if (d.source != 0 || d.P_src != d.n + 1 || getenv("QSFT_K4_NO_REGS") != nullptr) rc_form = 0;   // (env: cross-check in tests)
-    if (rc_form) {
-        // the register form assumes structured delays D[c][r][i] = D[c][r][0] - e_(i-1): look at D (a few KB) on the host
-        static thread_local std::vector<int8_t> hD;
-        hD.resize((size_t)d.C * d.P * d.ld);
-        QSFT_CUDA(cudaMemcpyAsync(hD.data(), d.D, hD.size(), cudaMemcpyDeviceToHost, st));
-        QSFT_CUDA(cudaStreamSynchronize(st));
-        for (int c = 0; c < d.C && rc_form; ++c)
-            for (int p = 0; p < d.P && rc_form; ++p) {
-                const int r = p / d.P_src, i = p - r * d.P_src;
-                if (i == 0) continue;
-                const int8_t* row0 = hD.data() + ((size_t)c * d.P + (size_t)r * d.P_src) * d.ld;
-                const int8_t* row = hD.data() + ((size_t)c * d.P + p) * d.ld;
-                for (int u = 0; u < d.n; ++u) {
-                    int want = row0[u] - (u == i - 1 ? 1 : 0);
-                    if (want < 0) want += d.q;
-                    if (row[u] != want) {
-                        rc_form = 0;
-                        break;
-                    }
-                }
-            }
-    }
-    if (nw <= 8) rc = qsft_kl_launch_nw8(a, blk, hm, use_tma, rc_form, smem, sms, st);
-    else if (nw <= 16) rc = qsft_kl_launch_nw16(a, blk, hm, use_tma, rc_form, smem, sms, st);
-    else rc = qsft_kl_launch_nw32(a, blk, hm, use_tma, rc_form, smem, sms, st);
+    if (nw <= 8) rc = qsft_kl_launch_nw8(a, blk, hm, use_tma, smem, sms, st);
+    else if (nw <= 16) rc = qsft_kl_launch_nw16(a, blk, hm, use_tma, smem, sms, st);
+    else rc = qsft_kl_launch_nw32(a, blk, hm, use_tma, smem, sms, st);
     if (rc != QSFT_OK) {
         cudaFreeAsync(ws, st);
         return rc;

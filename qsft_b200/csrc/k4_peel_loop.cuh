@@ -65,6 +65,7 @@ struct KlArgs {
     int box;                                 // bytes per repeat block of a tile: (W / 16) * P_src * 128 rounded up to 1024
     int stage_bytes;                         // R * box + list heads, rounded up to 1024
     int nstages;
+    int chunk;                               // find slots a warp reserves at a time
     int max_rounds;
     int guard_can_bind;
     double peeling_max;
@@ -165,7 +166,7 @@ __device__ __forceinline__ void kl_grid_barrier(unsigned int* gbar, unsigned int
 // Find slots are handed out to the warps in chunks of KL_CHUNK (one global atomic per chunk: a single counter bumped by every
 // warp of every SM for every group of candidates serialises in L2).  Slots of a chunk that stay unused at the end of a round
 // are marked with find_cj = -1; the link phase and every reader of the find list skip them.
-constexpr int KL_CHUNK = 64;
+constexpr int KL_CHUNK = 64;                 // at most; KlArgs.chunk = 4 .. 64 by problem size (kl_chunk)
 struct KlSlots {
     long long next, end;                     // this warp's chunk: slots [next, end) are free
 };
@@ -177,10 +178,10 @@ __device__ __forceinline__ long long kl_take(const KlArgs& a, KlSlots& sl, int c
         for (long long f = sl.next + lane; f < sl.end; f += 32)
             if (f < a.max_finds) a.find_cj[f] = -1;
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)KL_CHUNK);
+        if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)a.chunk);
         base = __shfl_sync(0xffffffffu, base, 0);
         sl.next = (long long)base;
-        sl.end = sl.next + KL_CHUNK;
+        sl.end = sl.next + a.chunk;
     }
     const long long f = sl.next;
     sl.next += cnt;
@@ -238,40 +239,39 @@ __device__ __forceinline__ void kl_scan(const KlArgs& a, uint8_t* stage, long lo
         if (valid0) hd0 = s_head[t];
         if (valid1) hd1 = s_head[t + 64];
     }
+    // rows in blocks of eight, the two bins side by side: sixteen independent shared-memory loads are in flight before the
+    // first FMA needs one (a row-at-a-time loop spends its time waiting for each load: the scan, not DRAM, then sets the pace)
     float e0 = 0.f, e1 = 0.f;
-    if (valid0 && hd0 == 0) {
-        TileCol tc{stage, P_src, a.box, t, a.lgW - 4};
-        float ea = 0.f, eb = 0.f;
-        for (int r = 0; r < R; ++r) {
-            int i = 0;
-            for (; i + 1 < P_src; i += 2) {
-                const float2 v = tc.ri(r, i), w = tc.ri(r, i + 1);
-                ea = fmaf(v.x, v.x, fmaf(v.y, v.y, ea));
-                eb = fmaf(w.x, w.x, fmaf(w.y, w.y, eb));
-            }
-            if (i < P_src) {
-                const float2 v = tc.ri(r, i);
-                ea = fmaf(v.x, v.x, fmaf(v.y, v.y, ea));
-            }
-        }
-        e0 = ea + eb;
-    }
-    if (valid1 && hd1 == 0) {
-        TileCol tc{stage, P_src, a.box, t + 64, a.lgW - 4};
-        float ea = 0.f, eb = 0.f;
-        for (int r = 0; r < R; ++r) {
-            int i = 0;
-            for (; i + 1 < P_src; i += 2) {
-                const float2 v = tc.ri(r, i), w = tc.ri(r, i + 1);
-                ea = fmaf(v.x, v.x, fmaf(v.y, v.y, ea));
-                eb = fmaf(w.x, w.x, fmaf(w.y, w.y, eb));
-            }
-            if (i < P_src) {
-                const float2 v = tc.ri(r, i);
-                ea = fmaf(v.x, v.x, fmaf(v.y, v.y, ea));
+    {
+        const bool on0 = valid0 && hd0 == 0, on1 = valid1 && hd1 == 0;
+        TileCol tc0{stage, P_src, a.box, on0 ? t : 0, a.lgW - 4};
+        TileCol tc1{stage, P_src, a.box, on1 ? t + 64 : 0, a.lgW - 4};
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (on0 || on1) {
+            for (int r = 0; r < R; ++r) {
+                int i = 0;
+                for (; i + 8 <= P_src; i += 8) {
+                    float2 v0[8], v1[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        v0[u] = tc0.ri(r, i + u);
+                        v1[u] = tc1.ri(r, i + u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        acc[u & 1] = fmaf(v0[u].x, v0[u].x, fmaf(v0[u].y, v0[u].y, acc[u & 1]));
+                        acc[2 + (u & 1)] = fmaf(v1[u].x, v1[u].x, fmaf(v1[u].y, v1[u].y, acc[2 + (u & 1)]));
+                    }
+                }
+                for (; i < P_src; ++i) {
+                    const float2 v0 = tc0.ri(r, i), v1 = tc1.ri(r, i);
+                    acc[0] = fmaf(v0.x, v0.x, fmaf(v0.y, v0.y, acc[0]));
+                    acc[2] = fmaf(v1.x, v1.x, fmaf(v1.y, v1.y, acc[2]));
+                }
             }
         }
-        e1 = ea + eb;
+        if (on0) e0 = acc[0] + acc[1];
+        if (on1) e1 = acc[2] + acc[3];
     }
     info->e[t] = e0;
     info->e[t + 64] = e1;
@@ -357,7 +357,21 @@ __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const K
         }
         uint8_t* kb = sym;
         if (act) {
-            for (int i = 1 + gl; i <= nsym; i += KL_G) sym[i - 1] = (uint8_t)detect_symbol(d, tc, i);
+            // four symbols per trip: their loads are issued together, the byte stores follow (a store per symbol in between
+            // would serialise load -> decision -> store, shared-memory latency each time)
+            for (int i0 = 1 + gl; i0 <= nsym; i0 += 4 * KL_G) {
+                int sv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * KL_G;
+                    sv[u] = detect_symbol(d, tc, i <= nsym ? i : nsym);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * KL_G;
+                    if (i <= nsym) sym[i - 1] = (uint8_t)sv[u];
+                }
+            }
             for (int i = nsym + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) sym[i] = 0;
         }
         __syncwarp();
@@ -388,6 +402,7 @@ __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const K
             }
             for (int r = 0; r < R; ++r) {
                 const int tb = r == 0 ? tb0 : ph.base(r);
+#pragma unroll 4
                 for (int i = gl; i < P_src; i += KL_G) {
                     const float2 w = s_tw[ph.row(r, i, tb)];
                     const float2 v = tc.ri(r, i);
@@ -443,257 +458,20 @@ __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const K
     }
 }
 
-// ---- candidate warps, register-resident form ----------------------------------------------------------------------------
-// For R <= RMAX repeats and P_src <= 8 * MIMAX delay rows: every lane of the 8-lane group copies its rows (r, i = gl + 8 m) of
-// the bin into registers and the warp releases the stage right away, so the producer refills it while the latency-bound rest
-// (symbols, rho, hash, the find's atomics) runs; peeled balls are subtracted from the registers instead of shared memory.
-// Same decisions and the same arithmetic as kl_cand.  Only for identity source decoding with structured delays, D[r][i] =
-// D[r][0] - e_(i-1) (identity / nso delay matrices; the host checks it): the phase of row (r, i) is then base(r) - digit(i-1),
-// no dot product per row.
-template <int NW, int RMAX, int MIMAX>
-__device__ __forceinline__ void kl_cand_regs(const KlArgs& a, uint8_t* stage, const KlTileInfo* info, int c, long long j0, int round,
-                                             int g, uint8_t* s_symw, const float2* s_tw, bool structured,
-                                             const long long (&wgt)[32 / KL_G], unsigned& n_multi, uint64_t* empty_bar,
-                                             KlTileInfo* info_rw, KlSlots& slots) {
-    const PeelDev& d = a.d;
-    const int lane = threadIdx.x & 31;
-    const int grp = lane / KL_G, gl = lane % KL_G;
-    const int R = d.R, P_src = d.P_src;
-    const long long B = d.B;
-    const int32_t* s_head = reinterpret_cast<const int32_t*>(stage + (size_t)R * a.box);
-    const float thresh = (float)d.thresh;
-    const int nsym = P_src - 1;
-    uint8_t* sym = s_symw + grp * KL_SYM;
-    const unsigned mask[4] = {info->mask[0], info->mask[1], info->mask[2], info->mask[3]};
-    const int total = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
-    {
-        const int rank = 4 * g + grp;
-        const int my = rank < total ? kl_pick(mask, rank) : -1;
-        bool act = my >= 0;
-        const int lbm = act ? my : 0;
-        const long long jb = j0 + lbm;
-        float2 v[RMAX][MIMAX];
-        {
-            TileCol tc{stage, P_src, a.box, lbm, a.lgW - 4};
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r)
-#pragma unroll
-                for (int m = 0; m < MIMAX; ++m) {
-                    const int i = gl + KL_G * m;
-                    v[r][m] = (act && r < R && i < P_src) ? tc.ri(r, i) : make_float2(0.f, 0.f);
-                }
-        }
-        float e_b = info->e[lbm];
-        const bool touched = act && round > 1 && ((info->tmask[lbm >> 5] >> (lbm & 31)) & 1u);
-        int f = touched ? s_head[lbm] - 1 : -1;
-#ifndef QSFT_EMU
-        if (empty_bar != nullptr) {
-            // the group is out of the stage; whoever takes the tile's last group hands the stage back to the producer
-            __syncwarp();
-            if (lane == 0 && atomicSub(&info_rw->left, 1) == 1) tma::mbar_arrive(empty_bar);
-        }
-#endif
-        // bins with peeled balls (qsft.py:223-241 applied to the register copy), then their energy
-        if (round > 1 && __ballot_sync(0xffffffffu, touched)) {
-            while (__ballot_sync(0xffffffffu, f >= 0)) {
-                if (f >= 0) {
-                    const uint4* src = reinterpret_cast<const uint4*>(a.find_k + (size_t)f * d.ld);
-                    for (int w = gl; w < d.ld / 16; w += KL_G) reinterpret_cast<uint4*>(sym)[w] = __ldcg(src + w);
-                }
-                __syncwarp();
-                if (f >= 0) {
-                    uint32_t kw[NW];
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) kw[w] = (4 * w < d.ld) ? reinterpret_cast<const uint32_t*>(sym)[w] : 0u;
-                    const float2 rho = __ldcg(a.find_rho + f);
-                    const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, sym, kw, structured};
-#pragma unroll
-                    for (int r = 0; r < RMAX; ++r) {
-                        if (r < R) {
-                            const int tb = ph.base(r);
-#pragma unroll
-                            for (int m = 0; m < MIMAX; ++m) {
-                                const int i = gl + KL_G * m;
-                                if (i < P_src) {
-                                    int t = i == 0 ? tb : tb - (int)sym[i - 1];         // structured delays: base - digit
-                                    t = t < 0 ? t + d.q : t;
-                                    const float2 w = s_tw[t];
-                                    v[r][m].x -= rho.x * w.x - rho.y * w.y;
-                                    v[r][m].y -= rho.x * w.y + rho.y * w.x;
-                                }
-                            }
-                        }
-                    }
-                    f = __ldcg(a.next + (size_t)f * d.C + c) - 1;
-                }
-                __syncwarp();
-            }
-            float e2 = 0.f;
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r)
-#pragma unroll
-                for (int m = 0; m < MIMAX; ++m) e2 = fmaf(v[r][m].x, v[r][m].x, fmaf(v[r][m].y, v[r][m].y, e2));   // unused slots are 0
-            e2 = kl_group_sum(e2);
-            if (touched) {
-                e_b = e2;
-                act = e2 > thresh;                                  // energy test (qsft.py:164)
-            }
-        }
-        // symbols (reconstruct.py:12-31,100-129): rows (r, 0) live in the group's first lane
-        float2 z[RMAX];
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            z[r].x = __shfl_sync(0xffffffffu, v[r][0].x, lane & ~(KL_G - 1));
-            z[r].y = __shfl_sync(0xffffffffu, v[r][0].y, lane & ~(KL_G - 1));
-        }
-        int symreg[MIMAX];
-#pragma unroll
-        for (int m = 0; m < MIMAX; ++m) {
-            const int i = gl + KL_G * m;
-            int sv = 0;
-            if (act && i >= 1 && i <= nsym) {
-                if (d.channel == 0) {
-                    sv = symbol_noiseless(d, z[0], v[0][m]);
-                } else if (d.channel == 1) {
-                    float arf = 0.f, aif = 0.f;
-#pragma unroll
-                    for (int r = 0; r < RMAX; ++r)
-                        if (r < R) {
-                            arf = fmaf(z[r].x, v[r][m].x, fmaf(z[r].y, v[r][m].y, arf));          // z * conj(v)
-                            aif = fmaf(z[r].y, v[r][m].x, fmaf(-z[r].x, v[r][m].y, aif));
-                        }
-                    sv = symbol_nso1_fast(d, arf, aif);
-                    if (sv < 0) {
-                        double ar = 0.0, ai = 0.0;
-#pragma unroll
-                        for (int r = 0; r < RMAX; ++r)
-                            if (r < R) {
-                                ar += (double)z[r].x * v[r][m].x + (double)z[r].y * v[r][m].y;
-                                ai += (double)z[r].y * v[r][m].x - (double)z[r].x * v[r][m].y;
-                            }
-                        sv = symbol_nso1_exact(d.q, ar, ai);
-                    }
-                } else {
-                    long long votes = 0;
-#pragma unroll
-                    for (int r = 0; r < RMAX; ++r)
-                        if (r < R) votes += nso2_vote(d, z[r], v[r][m]);
-                    sv = symbol_nso2(d, votes);
-                }
-                sym[i - 1] = (uint8_t)sv;
-            }
-            symreg[m] = sv;
-        }
-        uint8_t* kb = sym;
-        if (act)
-            for (int i = nsym + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) sym[i] = 0;
-        __syncwarp();
-        if (d.source == 1) {
-            kb = sym + QSFT_MAX_N;
-            if (act) {
-                for (int i = d.n + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) kb[i] = 0;
-                if (gl == 0) rs_decode(rs_params(d), sym, kb);
-            }
-            __syncwarp();
-        }
-        uint32_t kw[NW];
-#pragma unroll
-        for (int w = 0; w < NW; ++w) kw[w] = reinterpret_cast<const uint32_t*>(kb)[w];
-        const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, kb, kw, structured};
-        // rho and the residual in one pass (see kl_cand)
-        float sx = 0.f, sy = 0.f, s2 = 0.f;
-        float2 z0 = make_float2(0.f, 0.f);
-        if (act) {
-            const int tb0 = ph.base(0);
-            {
-                const float2 w = s_tw[tb0];
-                z0 = make_float2(w.x * z[0].x + w.y * z[0].y, w.x * z[0].y - w.y * z[0].x);
-            }
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                if (r < R) {
-                    const int tb = r == 0 ? tb0 : ph.base(r);
-#pragma unroll
-                    for (int m = 0; m < MIMAX; ++m) {
-                        const int i = gl + KL_G * m;
-                        if (i < P_src) {
-                            int t = i == 0 ? tb : tb - symreg[m];                       // structured delays: base - symbol
-                            t = t < 0 ? t + d.q : t;
-                            const float2 w = s_tw[t];
-                            const float dx = (w.x * v[r][m].x + w.y * v[r][m].y) - z0.x;     // conj(sig) * v - z0
-                            const float dy = (w.x * v[r][m].y - w.y * v[r][m].x) - z0.y;
-                            sx += dx;
-                            sy += dy;
-                            s2 = fmaf(dx, dx, fmaf(dy, dy, s2));
-                        }
-                    }
-                }
-            }
-        }
-        sx = kl_group_sum(sx);
-        sy = kl_group_sum(sy);
-        s2 = kl_group_sum(s2);
-        const float invP = (float)d.invP;
-        const float rr = z0.x + sx * invP, ri = z0.y + sy * invP;
-        const float res = s2 - (sx * sx + sy * sy) * invP;
-        // bin hash j = dec(M_c^T k mod q) (qsft.py:178-179)
-        long long hsum = 0;
-        if (act) {
-#pragma unroll
-            for (int u = 0; u < 32 / KL_G; ++u) {
-                const int i = gl + u * KL_G;
-                if (i < d.b)
-                    hsum += wgt[u] * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + i) * d.ld, d.ld, kw), d.q, d.qmagic);
-            }
-        }
-#pragma unroll
-        for (int o = KL_G / 2; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
-        const float lim = fmaxf(thresh, a.rel_floor * e_b);
-        const bool single = act && (hsum == jb) && !(res > lim);
-        const bool lead = (gl == 0);
-        const unsigned sb = __ballot_sync(0xffffffffu, lead && single);
-        unsigned long long fbase = 0;
-        if (sb) fbase = (unsigned long long)kl_take(a, slots, __popc(sb));
-        unsigned long long fi = fbase + (unsigned long long)__popc(sb & ((1u << lane) - 1u));
-        fi = __shfl_sync(0xffffffffu, fi, lane & ~(KL_G - 1));
-        if (single) {
-            if ((long long)fi < a.max_finds) {
-                uint32_t* ko = reinterpret_cast<uint32_t*>(a.find_k + (size_t)fi * d.ld);
-                for (int w = gl; w < d.ld / 4; w += KL_G) ko[w] = (w < NW) ? kw[w] : 0u;
-                if (lead) {
-                    a.find_cj[fi] = (long long)c * B + jb;
-                    a.find_rho[fi] = make_float2(rr, ri);
-                    a.find_round[fi] = round;
-                    a.find_id[(size_t)c * B + jb] = (int32_t)fi;
-                }
-            }
-        } else if (act && lead) {
-            ++n_multi;
-        }
-        __syncwarp();
-    }
-}
-
-// dispatch on the register-resident form: RC = 1: R = 1, P_src <= 56; RC = 3: R <= 3, P_src <= 48; RC = 0: shared memory
-template <int NW, int RC>
+// one group of a tile + hand-back of the stage (TMA variant: empty_bar != nullptr)
+template <int NW>
 __device__ __forceinline__ void kl_cand_any(const KlArgs& a, uint8_t* stage, KlTileInfo* info, int c, long long j0, int round, int g,
                                             uint8_t* s_symw, const float2* s_tw, bool structured, const long long (&wgt)[32 / KL_G],
                                             unsigned& n_multi, uint64_t* empty_bar, KlSlots& slots) {
-    if (RC == 1) {
-        kl_cand_regs<NW, 1, 7>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, empty_bar, info, slots);
-    } else if (RC == 3) {
-        kl_cand_regs<NW, 3, 6>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, empty_bar, info, slots);
-    } else {
-        kl_cand<NW>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, slots);
+    kl_cand<NW>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, slots);
 #ifndef QSFT_EMU
-        if (empty_bar != nullptr) {
-            // done with the stage; in-place updates (generic proxy) are ordered before the next bulk copy
-            if (round > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0 && atomicSub(&info->left, 1) == 1) tma::mbar_arrive(empty_bar);
-        }
-#endif
+    if (empty_bar != nullptr) {
+        // done with the stage; in-place updates (generic proxy) are ordered before the next bulk copy
+        if (round > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0 && atomicSub(&info->left, 1) == 1) tma::mbar_arrive(empty_bar);
     }
+#endif
 }
 
 // ---- one classification round ---------------------------------------------------------------------------------------
@@ -707,7 +485,7 @@ __device__ __forceinline__ void kl_cand_any(const KlArgs& a, uint8_t* stage, KlT
 //   candidates -> producer: the tile's `left` counter; whoever copies the last group out of the stage (or the scanner, when
 //                          the tile has no work) arrives on the stage's `empty` mbarrier.
 // Plain variant: scan and candidate work separated by CTA barriers, groups assigned statically, single stage.
-template <int NW, bool TMA, int RC>
+template <int NW, bool TMA>
 __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk,
 #ifndef QSFT_EMU
                                             const CUtensorMap* maps,
@@ -804,7 +582,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
             for (;;) {
                 volatile unsigned int* slot = &mbox[cw * KL_MB + (mb_head & (KL_MB - 1))];
                 unsigned int e;
-                while ((e = *slot) == 0u) __nanosleep(20);
+                while ((e = *slot) == 0u) __nanosleep(200);
                 __syncwarp();
                 if (lane == 0) *slot = 0u;
                 ++mb_head;
@@ -812,7 +590,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
                 if ((e & 0xffu) == 0xffu) break;
                 const int st = (int)((e >> 8) & 7u), g = (int)(e & 0xffu);
                 KlTileInfo* info = &infos[st];
-                kl_cand_any<NW, RC>(a, stages + (size_t)st * a.stage_bytes, info, info->c, info->j0, round, g, s_symw, s_tw, structured,
+                kl_cand_any<NW>(a, stages + (size_t)st * a.stage_bytes, info, info->c, info->j0, round, g, s_symw, s_tw, structured,
                                     wgt, n_multi, &empty[st], slots);
             }
         }
@@ -844,7 +622,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
             if (is_cand) {
                 const int total = __popc(infos[0].mask[0]) + __popc(infos[0].mask[1]) + __popc(infos[0].mask[2]) + __popc(infos[0].mask[3]);
                 for (int g = (int)((warp - KL_NS + 5u * it) % (unsigned)KL_NC); 4 * g < total; g += KL_NC)
-                    kl_cand_any<NW, RC>(a, stages, &infos[0], c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, nullptr, slots);
+                    kl_cand_any<NW>(a, stages, &infos[0], c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, nullptr, slots);
             }
         }
         tiles_done += (unsigned int)mine;
@@ -915,7 +693,7 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, long long f0, long long
     }
 }
 
-template <int NW, bool TMA, int RC>
+template <int NW, bool TMA>
 __global__ void __launch_bounds__(TMA ? KL_CT + 32 : KL_CT, 1)
 k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
 #ifndef QSFT_EMU
@@ -968,7 +746,7 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
     bool cont = true;
     while (cont && num_peeling < a.peeling_max && round < a.max_rounds) {
         ++round;
-        kl_classify<NW, TMA, RC>(a, blk,
+        kl_classify<NW, TMA>(a, blk,
 #ifndef QSFT_EMU
                              maps.m,
 #endif
@@ -1020,6 +798,13 @@ __global__ void kl_dstruct_kernel(PeelDev d, int* flag) {
     if (threadIdx.x == 0) *flag = bad ? 0 : 1;
 }
 
+// Slots per chunk: large enough that the global counter is touched rarely, small enough that the slots left unused at the end
+// of a round (at most one chunk per candidate warp and round) stay below ~C B / 16 per round.
+inline int kl_chunk(const PeelDev& d, int grid) {
+    const long long c = (long long)d.C * d.B / ((long long)grid * KL_NC * 16);
+    return c < 4 ? 4 : c > KL_CHUNK ? KL_CHUNK : (int)c;
+}
+
 // tile geometry for a shared-memory budget: the widest tile (<= 128 bins, no wider than the group needs) that leaves at
 // least `min_stages` stages.  Returns false when even 16-bin tiles do not fit.
 inline bool kl_geometry(const PeelDev& d, int budget, int min_stages, KlArgs* a) {
@@ -1047,13 +832,9 @@ inline bool kl_geometry(const PeelDev& d, int budget, int min_stages, KlArgs* a)
 namespace {
 
 template <int NW>
-int kl_launch(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, int rc_form, size_t smem, int grid,
-              cudaStream_t st) {
+int kl_launch(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, size_t smem, int grid, cudaStream_t st) {
     void* params[] = {(void*)&a, (void*)&blk, (void*)&maps};
-    const void* fn = !use_tma      ? (const void*)k4_peel_loop_kernel<NW, false, 0>
-                     : rc_form == 1 ? (const void*)k4_peel_loop_kernel<NW, true, 1>
-                     : rc_form == 3 ? (const void*)k4_peel_loop_kernel<NW, true, 3>
-                                    : (const void*)k4_peel_loop_kernel<NW, true, 0>;
+    const void* fn = use_tma ? (const void*)k4_peel_loop_kernel<NW, true> : (const void*)k4_peel_loop_kernel<NW, false>;
     QSFT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QSFT_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(use_tma ? KL_CT + 32 : KL_CT), params, smem, st));
     g_qsft_launches.fetch_add(1, std::memory_order_relaxed);

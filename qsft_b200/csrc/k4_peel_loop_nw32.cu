@@ -1,7 +1,7 @@
 // k4_peel_loop kernels for k digit rows of at most 32 32-bit words (see k4_peel_loop.cuh)
 #include "k4_peel_loop.cuh"
 
-int qsft_kl_launch_nw32(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, int rc_form, size_t smem, int grid,
+int qsft_kl_launch_nw32(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps, bool use_tma, size_t smem, int grid,
                        cudaStream_t st) {
-    return kl_launch<32>(a, blk, maps, use_tma, rc_form, smem, grid, st);
+    return kl_launch<32>(a, blk, maps, use_tma, smem, grid, st);
 }

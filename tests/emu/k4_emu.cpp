@@ -59,6 +59,7 @@ int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, floa
         a.stage_bytes = (d.R * a.box + a.W * 4 + 1023) & ~1023;
     }
     a.nstages = 1;
+    a.chunk = kl_chunk(d, 1);
     KlBlocks blk{};
     for (int c = 0; c < d.C; ++c)
         for (int r = 0; r < d.R; ++r) blk.p[c * d.R + r] = U + ((size_t)c * d.P + (size_t)r * d.P_src) * d.B;
@@ -74,14 +75,8 @@ int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, floa
     a.guard_can_bind = a.peeling_max <= 15.0 * (double)d.C * (double)d.B ? 1 : 0;
     a.rel_floor = 1e-10f;
     const int nw = nw_of(d.ld);
-    const int rc_form = (!regs || !dflag || d.source != 0) ? 0 : (d.R == 1 && d.P_src <= 56) ? 1 : (d.R <= 3 && d.P_src <= 48) ? 3 : 0;
-    if (rc_form == 1) {
-        NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_CT), [&]() { k4_peel_loop_kernel<NW, false, 1>(a, blk); }));
-    } else if (rc_form == 3) {
-        NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_CT), [&]() { k4_peel_loop_kernel<NW, false, 3>(a, blk); }));
-    } else {
-        NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_CT), [&]() { k4_peel_loop_kernel<NW, false, 0>(a, blk); }));
-    }
+    (void)regs;
+    NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_CT), [&]() { k4_peel_loop_kernel<NW, false>(a, blk); }));
     return 0;
 }
 

@@ -123,15 +123,6 @@ try:
     Uz = torch.zeros_like(U0)
     ms = timeit(lambda: prob.peel(Uz), flush=flush)
     out["k4 peel, device loop, all-zeroton bins (1 round)"] = {"ms": ms, "GBps": round_bytes / ms / 1e6, "frac": round_bytes / ms / 1e6 / peak}
-    os.environ["QSFT_K4_NO_REGS"] = "1"
-    sig_nr = peel_sig(U0)
-    ms = timeit(lambda: prob.peel(U0), flush=flush)
-    out["k4 peel, device loop, candidate bins in shared memory (QSFT_K4_NO_REGS=1)"] = {"ms": ms, "same_result": sig_nr[:4] == sig_dev[:4]}
-    os.environ["QSFT_K4_MAX_ROUNDS"] = "1"
-    ms = timeit(lambda: prob.peel(U0), flush=flush)
-    out["k4 peel, device loop, shared-memory form, round 1 only"] = {"ms": ms}
-    os.environ.pop("QSFT_K4_MAX_ROUNDS")
-    os.environ.pop("QSFT_K4_NO_REGS")
     os.environ["QSFT_K4_NO_TMA"] = "1"
     sig_nt = peel_sig(U0)
     ms = timeit(lambda: prob.peel(U0), flush=flush)
