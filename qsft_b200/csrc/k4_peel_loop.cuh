@@ -357,21 +357,7 @@ __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const K
         }
         uint8_t* kb = sym;
         if (act) {
-            // four symbols per trip: their loads are issued together, the byte stores follow (a store per symbol in between
-            // would serialise load -> decision -> store, shared-memory latency each time)
-            for (int i0 = 1 + gl; i0 <= nsym; i0 += 4 * KL_G) {
-                int sv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * KL_G;
-                    sv[u] = detect_symbol(d, tc, i <= nsym ? i : nsym);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * KL_G;
-                    if (i <= nsym) sym[i - 1] = (uint8_t)sv[u];
-                }
-            }
+            for (int i = 1 + gl; i <= nsym; i += KL_G) sym[i - 1] = (uint8_t)detect_symbol(d, tc, i);
             for (int i = nsym + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) sym[i] = 0;
         }
         __syncwarp();
@@ -402,7 +388,6 @@ __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const K
             }
             for (int r = 0; r < R; ++r) {
                 const int tb = r == 0 ? tb0 : ph.base(r);
-#pragma unroll 4
                 for (int i = gl; i < P_src; i += KL_G) {
                     const float2 w = s_tw[ph.row(r, i, tb)];
                     const float2 v = tc.ri(r, i);
@@ -582,7 +567,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
             for (;;) {
                 volatile unsigned int* slot = &mbox[cw * KL_MB + (mb_head & (KL_MB - 1))];
                 unsigned int e;
-                while ((e = *slot) == 0u) __nanosleep(200);
+                while ((e = *slot) == 0u) __nanosleep(64);
                 __syncwarp();
                 if (lane == 0) *slot = 0u;
                 ++mb_head;
