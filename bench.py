@@ -322,9 +322,7 @@ def run_ours(a):
         pass
     bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "2 x measured sustained bf16 (MEASURED_PEAKS.json), no int8 figure measured" if peaks else "2 x fallback 1.4 PF"
-    sparse_mode = int(os.environ.get("QSFT_LATTICE_SPARSE", "2") or 0)
-    if os.environ.get("QSFT_LATTICE_FUSED_A", "0") not in ("", "0") or sparse_mode not in (1, 2):
-        sparse_mode = 0
+    sparse_mode = 0 if os.environ.get("QSFT_LATTICE_SPARSE", "2") == "0" else 2
     peak_mult = 2.0                                # dense int8 = 2 x bf16
     if "k2_eval_lattice" in kt:
         # lattice-factorised evaluation: the GEMM is 2 * (2*4^b1) * 4^b2 * (2S) * 3 limbs = 24 (dense-equivalent) int8 ops per

@@ -66,6 +66,22 @@ int qsft_eval_lattice_supported(int q, int n, int b, int P, int64_t S);
 int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths, int64_t S,
                             int q, int n, int b, int P, int ld, float* out, void* stream);
 
+/* The same with the precision of the strengths stated.  The exact +-1 / +-i operand meets the strengths as three balanced
+ * int8 limbs (20 bits below max|a|: every coefficient comes back with an ABSOLUTE error of ~7e-7 max|a|).  residual_passes
+ * = 1 runs a second GEMM pass over the quantisation residual, accumulated onto the first (41 bits; twice the tensor work):
+ * needed for 1e-5 RELATIVE accuracy of coefficients much smaller than the largest (reference tolerance, qsft/utils.py:161-164
+ * draws |a| in [a_min, a_max]).  0 = never, -1 = decide on the device data (second pass iff min|a| < 0.1 max|a|; reads two
+ * floats back, i.e. synchronises the stream once).  qsft_eval_synth_lattice == residual_passes -1.                       */
+int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths, int64_t S,
+                               int q, int n, int b, int P, int ld, float* out, int residual_passes, void* stream);
+
+/* Measurement noise on the device: U[e] += sd * (N(0,1) + i N(0,1)) for every complex64 bin e < n_bins, Philox4x32-10
+ * keyed by (seed, offset + e / 2): the value added to a bin depends only on (seed, offset, e) -- not on the launch, the
+ * device or the rank.  Replaces the host loop of SyntheticSubsampledSignal.get_MDU
+ * (synt_exp/synt_src/synthetic_signal.py:120-130, sd = noise_sd / sqrt(2 q^b)) when the reference's NumPy random stream
+ * is not required (noise_rng="device"); statistical, not bit, parity with the reference.  U must be 16-byte aligned.   */
+int qsft_add_noise(float* U, int64_t n_bins, float sd, uint64_t seed, uint64_t offset, void* stream);
+
 /* K3 -- batched b-dimensional length-q DFT, forward sign, scaled by 1/q^b, in place.  Replaces
  * SubsampledSignal._compute_subtransform + gwht (qsft/input_signal_subsampled.py:264-266, qsft/utils.py:31-36).
  *   x (batch, q^b) complex64.  Index <-> digits MSB first on both sides (C-order reshape [q]*b).            */

@@ -13,9 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libqsft_b200.so")
 EXPORTS = [
     "qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count",
     "qsft_query_lattice", "qsft_dec_to_qary", "qsft_qary_to_dec", "qsft_eval_synth", "qsft_gwht_batch", "qsft_gwht_batch_bcast",
-    "qsft_eval_lattice_supported", "qsft_eval_synth_lattice",
+    "qsft_eval_lattice_supported", "qsft_eval_synth_lattice", "qsft_eval_synth_lattice_ex",
     "qsft_peel_classify", "qsft_peel_apply", "qsft_peel_reduce", "qsft_peel", "qsft_peel_blocks", "qsft_closed_form_bins",
-    "qsft_singleton_detect", "qsft_detect_mle", "qsft_k3_ticket_decode",
+    "qsft_singleton_detect", "qsft_detect_mle", "qsft_k3_ticket_decode", "qsft_add_noise",
 ]
 
 
@@ -82,6 +82,7 @@ def lib():
     L.qsft_gwht_batch_bcast.argtypes = [vp, i64, i32, i32, C.POINTER(vp), i32, vp]
     L.qsft_eval_lattice_supported.argtypes = [i32, i32, i32, i32, i64]
     L.qsft_eval_synth_lattice.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp]
+    L.qsft_eval_synth_lattice_ex.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, i32, vp]
     pd = C.POINTER(PeelDesc)
     L.qsft_peel_classify.argtypes = [pd, vp, i64, i64, vp, vp, vp, vp, vp, i64, i32, vp, vp]
     L.qsft_peel_apply.argtypes = [pd, vp, i64, i64, vp, vp, vp, vp, i64, i64, i32, vp, vp]
@@ -94,6 +95,7 @@ def lib():
     L.qsft_singleton_detect.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     L.qsft_detect_mle.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
     L.qsft_k3_ticket_decode.argtypes = [C.c_uint32, i64, i32, i32, i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
+    L.qsft_add_noise.argtypes = [vp, i64, C.c_float, C.c_uint64, C.c_uint64, vp]
     for name in EXPORTS:
         fn = getattr(L, name)  # raises AttributeError if a declared symbol is missing
         if name not in ("qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count"):

@@ -144,20 +144,51 @@ __device__ __forceinline__ void limbs3(float x, float scale, int (&l)[3]) {
     l[0] = v; l[1] = l1; l[2] = l2;
 }
 
-// alimb[s] = {re limbs 0..2, im limbs 0..2, pad, pad} as int8x8
+// alimb[s] = {re limbs 0..2, im limbs 0..2, pad, pad} as int8x8.
+// pass 0: v = round(a * scale), scale = (2^20 - 1) / max|a|: absolute error <= 0.5 / scale per component, i.e. ~5e-7 max|a|
+//         -- enough for 1e-5 RELATIVE accuracy of the recovered coefficients only while min|a| >= ~0.1 max|a|.
+// pass 1: the residual a * scale - v (|.| <= 0.5, computed with one fma) scaled by 2^21 and sliced the same way; its GEMM is
+//         accumulated onto the first one with inv_scale / 2^21.  Together 41 bits below max|a|: the error left is the fp32
+//         rounding of the samples themselves.  Only run when the strengths span a wide range (see qsft_eval_synth_lattice_ex).
 __global__ void lt_quant_kernel(const float2* __restrict__ a, long long S, const unsigned int* __restrict__ amax_bits,
-                                float* __restrict__ inv_scale, int2* __restrict__ alimb) {
+                                float* __restrict__ inv_scale /* [2]: pass 0, pass 1 */, int2* __restrict__ alimb, int pass) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const float amax = __uint_as_float(*amax_bits);
-    const float scale = amax > 0.f ? (float)((1 << LT_SCALE_BITS) - 1) / amax : 0.f;
-    if (s == 0) *inv_scale = amax > 0.f ? amax / (float)((1 << LT_SCALE_BITS) - 1) : 0.f;
+    // a power of two: max|a| = m 2^e with m in [0.5, 1) -> scale = 2^(20 - e), |a scale| < 2^20, and 1 / scale is exact (the
+    // two passes then add up to a to ~2^-41 max|a|; with scale = (2^20 - 1) / max|a| the rounding of the reciprocal would
+    // leave a common relative error of 1e-7 on all coefficients)
+    int ex = 0;
+    if (amax > 0.f) (void)frexpf(amax, &ex);
+    const float scale = amax > 0.f ? ldexpf(1.0f, LT_SCALE_BITS - ex) : 0.f;
+    if (s == 0 && pass == 0) {
+        inv_scale[0] = amax > 0.f ? ldexpf(1.0f, ex - LT_SCALE_BITS) : 0.f;
+        inv_scale[1] = amax > 0.f ? ldexpf(1.0f, ex - LT_SCALE_BITS - 21) : 0.f;
+    }
     if (s >= S) return;
+    float x = a[s].x, y = a[s].y, sc = scale;
+    if (pass == 1) {
+        x = fmaf(x, scale, -(float)__float2int_rn(x * scale));          // residual of pass 0 in units of 1 / scale
+        y = fmaf(y, scale, -(float)__float2int_rn(y * scale));
+        sc = 2097152.0f;                                                 // 2^21: |x * sc| <= 2^20
+    }
     int lr[3], li[3];
-    limbs3(a[s].x, scale, lr);
-    limbs3(a[s].y, scale, li);
+    limbs3(x, sc, lr);
+    limbs3(y, sc, li);
     uint32_t w0 = (uint32_t)(lr[0] & 0xff) | ((uint32_t)(lr[1] & 0xff) << 8) | ((uint32_t)(lr[2] & 0xff) << 16);
     uint32_t w1 = (uint32_t)(li[0] & 0xff) | ((uint32_t)(li[1] & 0xff) << 8) | ((uint32_t)(li[2] & 0xff) << 16);
     alimb[s] = make_int2((int)w0, (int)w1);
+}
+
+// smallest non-zero max(|re|, |im|) of the strengths (dynamic range of the signal, decides the residual pass)
+__global__ void lt_amin_kernel(const float2* __restrict__ a, long long S, unsigned int* __restrict__ amin_bits) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 3.0e38f;
+    if (s < S) {
+        const float v = fmaxf(fabsf(a[s].x), fabsf(a[s].y));
+        if (v > 0.f) m = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(amin_bits, __float_as_uint(m));
 }
 
 // A'[(p * Mhi + l_hi) * 2 + part][2 s + comp]:  part 0 (Re row): (er, -ei),  part 1 (Im row): (ei, er),
@@ -354,34 +385,10 @@ __device__ __forceinline__ void ts_phase_expand(uint32_t tw, uint32_t ew, bool i
 }
 
 // ---- the GEMM ---------------------------------------------------------------------------------------------
-// 16 bytes of an A' row pair: eight support elements, t = eight 2-bit phases (bits 0..15 of `t16`)
-//   re chunk = (er, -ei) x 8, im chunk = (ei, er) x 8, (er, ei) = i^t
-__device__ __forceinline__ void lt_a_chunks(uint32_t t16, uint4& re, uint4& im) {
-    uint32_t rw[4], iw[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint32_t v[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const uint32_t t = (t16 >> (4 * j + 2 * h)) & 3u;
-            // selector bytes of i^t as (er, -ei, ei, er) picked from the byte table {0x00, 0x01, 0xFF}
-            const uint32_t sel = __byte_perm(0x10022001u, 0x02200110u, t * 0x11u + 0x40u);
-            v[h] = __byte_perm(0x00FF0100u, 0u, sel);
-        }
-        rw[j] = __byte_perm(v[0], v[1], 0x5410u);
-        iw[j] = __byte_perm(v[0], v[1], 0x7632u);
-    }
-    re = make_uint4(rw[0], rw[1], rw[2], rw[3]);
-    im = make_uint4(iw[0], iw[1], iw[2], iw[3]);
-}
-
-// FUSED_A: the exact operand A' is not read from HBM; the four epilogue warps generate each 128 x 128-byte slab in
-// (128B-swizzled) shared memory from the packed phase tables while the tensor core works on the previous slabs.
-template <bool FUSED_A>
+// Dense cross-check kernel (QSFT_LATTICE_SPARSE=0): A' materialised in HBM by lt_agen_kernel, cta_group::1.
 __global__ void __launch_bounds__(LT_THREADS, 1)
 lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int nkb, int Mhi, int Nlo,
-               const uint32_t* __restrict__ Ttab, const uint32_t* __restrict__ Etab, int Tw,
-               const float* __restrict__ inv_scale_ptr, float2* __restrict__ out) {
+               const float* __restrict__ inv_scale_ptr, float2* __restrict__ out, int accumulate) {
     extern __shared__ uint8_t lt_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)lt_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)LT_STAGES * LT_STAGE_BYTES);
@@ -397,7 +404,7 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < LT_STAGES; ++i) {
-            lt_mbar_init(&full[i], FUSED_A ? 5 : 1);     // TMA thread (+ one elected lane per A-producer warp)
+            lt_mbar_init(&full[i], 1);
             lt_mbar_init(&empty[i], 1);
         }
         lt_mbar_init(tfull, 1);
@@ -420,9 +427,9 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int stage = kb % LT_STAGES;
                 const uint32_t ph = (uint32_t)(kb / LT_STAGES) & 1u;
                 lt_mbar_wait(&empty[stage], ph ^ 1u);
-                lt_mbar_expect_tx(&full[stage], FUSED_A ? (LT_STAGE_BYTES - LT_BM * LT_BK) : LT_STAGE_BYTES);
+                lt_mbar_expect_tx(&full[stage], LT_STAGE_BYTES);
                 uint8_t* st = base + (size_t)stage * LT_STAGE_BYTES;
-                if (!FUSED_A) lt_tma_2d(st, &tmA, kb * LT_BK, mtile * LT_BM, &full[stage]);
+                lt_tma_2d(st, &tmA, kb * LT_BK, mtile * LT_BM, &full[stage]);
 #pragma unroll
                 for (int l = 0; l < LT_LIMBS; ++l)
                     lt_tma_2d(st + LT_BM * LT_BK + l * (LT_BN * LT_BK), &tmB, kb * LT_BK, l * Nlo + ntile * LT_BN, &full[stage]);
@@ -456,47 +463,6 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             lt_commit(tfull);
         }
     } else {
-        if (FUSED_A) {
-            // A' producer: thread (l = 0..63, half = 0..1) writes 32 support elements (4 x 16-byte chunks) of the row
-            // pair (2l, 2l + 1) of every slab.  t = (T + E2) mod 4 on sixteen 2-bit fields at once (no carries between
-            // fields: add without the top bits, xor them back).
-            const int pe = threadIdx.x - 64;
-            const int l = pe >> 1, half = pe & 1;
-            const long long grow0 = (long long)mtile * LT_BM;                 // first global A' row of this CTA
-            const int pp = (int)(grow0 / (2 * Mhi));
-            const int lhi0 = (int)(grow0 - (long long)pp * 2 * Mhi) >> 1;
-            const uint32_t* trow = Ttab + (size_t)(lhi0 + l) * Tw + 2 * half;
-            const uint32_t* erow = Etab + (size_t)pp * Tw + 2 * half;
-            uint2 tw = *reinterpret_cast<const uint2*>(trow), ew = *reinterpret_cast<const uint2*>(erow);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int stage = kb % LT_STAGES;
-                const uint32_t ph = (uint32_t)(kb / LT_STAGES) & 1u;
-                constexpr uint32_t H = 0xAAAAAAAAu;
-                const uint32_t t0 = ((tw.x & ~H) + (ew.x & ~H)) ^ ((tw.x ^ ew.x) & H);
-                const uint32_t t1 = ((tw.y & ~H) + (ew.y & ~H)) ^ ((tw.y ^ ew.y) & H);
-                if (kb + 1 < nkb) {                                            // prefetch the next slab's phases
-                    tw = *reinterpret_cast<const uint2*>(trow + 4 * (kb + 1));
-                    ew = *reinterpret_cast<const uint2*>(erow + 4 * (kb + 1));
-                }
-                lt_mbar_wait(&empty[stage], ph ^ 1u);
-                uint8_t* sa = base + (size_t)stage * LT_STAGE_BYTES;
-                const int r_re = 2 * l, r_im = 2 * l + 1;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t t16 = (c < 2 ? t0 : t1) >> (16 * (c & 1));
-                    uint4 re, im;
-                    lt_a_chunks(t16, re, im);
-                    const int chunk = half * 4 + c;
-                    *reinterpret_cast<uint4*>(sa + r_re * 128 + ((chunk ^ (r_re & 7)) << 4)) = re;
-                    *reinterpret_cast<uint4*>(sa + r_im * 128 + ((chunk ^ (r_im & 7)) << 4)) = im;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lt_smem_u32(&full[stage])) : "memory");
-                }
-            }
-        }
         // epilogue: row r = 2 * l_hi_local + part lives in TMEM lane r; neighbouring lanes hold (Re, Im) of one l_hi
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
@@ -533,7 +499,14 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             float4* dst = reinterpret_cast<float4*>(orow + ch * 16 + (odd ? 8 : 0));
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[2 * j].x, o[2 * j].y, o[2 * j + 1].x, o[2 * j + 1].y);
+            for (int j = 0; j < 4; ++j) {
+                float4 w = make_float4(o[2 * j].x, o[2 * j].y, o[2 * j + 1].x, o[2 * j + 1].y);
+                if (accumulate) {                               // residual pass: onto the first pass's samples
+                    const float4 p = dst[j];
+                    w = make_float4(p.x + w.x, p.y + w.y, p.z + w.z, p.w + w.w);
+                }
+                dst[j] = w;
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -550,16 +523,8 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // The GEMM runs on CTA pairs (cta_group::2): 256 rows of A' x 128 columns x 3 limbs per pair; each CTA stages its own 128
 // compressed rows + metadata, ONE of limbs 0 / 1 and half of the limb-2 columns, so the limb operand is fetched once per pair.
 constexpr int SP_BK = 256;                                   // logical K' bytes per stage (128 support elements)
-constexpr int SP_STAGES = 3;
-constexpr int SP_A_BYTES = 128 * 128;                        // compressed A' slab: 128 rows x 128 bytes
 constexpr int SP_B01_BYTES = 2 * 128 * 128;                  // this CTA's limb (0 or 1), two 128-byte K halves
 constexpr int SP_B2_BYTES = 2 * 64 * 128;                    // this CTA's 64 columns of limb 2, two K halves
-constexpr int SP_E_BYTES = 2 * 2048;                         // metadata: two chunks of 128 rows x 16 bytes
-constexpr int SP_OFF_B01 = SP_A_BYTES, SP_OFF_B2 = SP_OFF_B01 + SP_B01_BYTES, SP_OFF_E = SP_OFF_B2 + SP_B2_BYTES;
-constexpr int SP_STAGE_BYTES = SP_OFF_E + SP_E_BYTES;        // 68 KB
-constexpr size_t SP_SMEM = 1024 + (size_t)SP_STAGES * SP_STAGE_BYTES + 256;
-constexpr uint32_t SP_TMEM_E = 384;                          // metadata columns behind the three limb accumulators
-static_assert(SP_STAGE_BYTES % 1024 == 0, "stage must keep the 1024-byte swizzle alignment");
 
 __device__ __forceinline__ uint32_t sp_cluster_rank() {
     uint32_t r;
@@ -589,208 +554,6 @@ __device__ __forceinline__ void sp_commit_pair(uint64_t* bar) {
                  "h"((uint16_t)3)
                  : "memory");
 }
-__device__ __forceinline__ void sp_umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t e_tmem, uint32_t idesc,
-                                           uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "tcgen05.mma.sp.cta_group::2.kind::i8 [%0], %1, %2, [%3], %4, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(e_tmem), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// un-swizzled K-major descriptor of one metadata chunk: 128 rows x 16 bytes, 8-row core matrices 128 bytes apart
-__device__ __forceinline__ uint64_t sp_edesc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)(128 >> 4) << 16;
-    d |= (uint64_t)(128 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-
-// Compressed A' and its metadata.  Ac[row][s] (row = (p * Mhi + l_hi) * 2 + part, one byte per support element):
-//   Re row (er, -ei): the non-zero sits at pair position r & 1 and is negative iff (r & 1) ^ (r >> 1)
-//   Im row (ei,  er): position 1 - (r & 1), negative iff r >> 1                          (r = rotation, i^r = er + i ei)
-// Metadata nibble of a 4-byte group (support elements 2c, 2c + 1) = idx0 | idx1 << 2 with idx0 = pos(2c), idx1 = 2 + pos(2c+1),
-// i.e. bits 0 and 2 are the two position bits and bit 3 is set; chunks of 128 rows x 16 bytes (128 logical K') in the
-// order (m-tile, k-chunk) so that one TMA box feeds one tcgen05.cp.  One thread = 16 support elements of one l_hi.
-__global__ void __launch_bounds__(256)
-lt_agen_sp_kernel(const uint32_t* __restrict__ hhi, const uint32_t* __restrict__ Etab, long long S, int b1, int P, long long Mhi,
-                  long long Sp /* padded support = bytes per Ac row */, long long Tw, uint8_t* __restrict__ Ac,
-                  uint8_t* __restrict__ Em) {
-    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lhi = blockIdx.y;
-    if (w * 16 >= Sp) return;
-    uint32_t t16 = 0;
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const long long s = 16 * w + i;
-        if (s < S) t16 |= dot4(hhi[s], lhi, b1) << (2 * i);
-    }
-    const long long nk128 = Sp / 64;
-    const long long kc = w >> 2;
-    const int eoff = (int)(w & 3) * 4;
-    for (int p = 0; p < P; ++p) {
-        const uint32_t ew = Etab[(size_t)p * Tw + w];
-        constexpr uint32_t H = 0xAAAAAAAAu;
-        const uint32_t r16 = ((t16 & ~H) + (ew & ~H)) ^ ((t16 ^ ew) & H);      // sixteen 2-bit rotations
-        const uint32_t lo = r16 & 0x55555555u, hi = (r16 >> 1) & 0x55555555u;
-        const uint32_t nre = lo ^ hi, nim = hi;                                 // negative flags, one per 2-bit field
-        uint32_t wre[4], wim[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const uint32_t mr = (((nre >> (8 * g)) & 0x55u) * 0x00041041u) & 0x01010101u;
-            const uint32_t mi = (((nim >> (8 * g)) & 0x55u) * 0x00041041u) & 0x01010101u;
-            wre[g] = 0x01010101u ^ (mr * 0xFEu);
-            wim[g] = 0x01010101u ^ (mi * 0xFEu);
-        }
-        const long long row = ((long long)p * Mhi + lhi) * 2;
-        *reinterpret_cast<uint4*>(Ac + (size_t)row * Sp + 16 * w) = make_uint4(wre[0], wre[1], wre[2], wre[3]);
-        *reinterpret_cast<uint4*>(Ac + (size_t)(row + 1) * Sp + 16 * w) = make_uint4(wim[0], wim[1], wim[2], wim[3]);
-        const uint32_t mre = lo | 0x88888888u;
-        uint8_t* ebase = Em + (((size_t)(row >> 7) * nk128 + kc) * 128 + (size_t)(row & 127)) * 16 + eoff;
-        *reinterpret_cast<uint32_t*>(ebase) = mre;
-        *reinterpret_cast<uint32_t*>(ebase + 16) = mre ^ 0x55555555u;
-    }
-}
-
-__global__ void __launch_bounds__(LT_THREADS, 1)
-lt_gemm_sp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmE, int nkb, int Mhi, int Nlo,
-                  int n_mtiles, const float* __restrict__ inv_scale_ptr, float2* __restrict__ out) {
-    extern __shared__ uint8_t lt_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)lt_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)SP_STAGES * SP_STAGE_BYTES);
-    uint64_t* full = bars;                       // used in the leader CTA only: both CTAs' loads complete on it
-    uint64_t* empty = bars + SP_STAGES;          // one per CTA, released by the leader's multicast commit
-    uint64_t* tfull = bars + 2 * SP_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = sp_cluster_rank();
-    const int ntile = blockIdx.x >> 1;
-    const int mtile = 2 * blockIdx.y + (int)rank;
-
-    if (warp == 0 && lane == 0) {
-        for (int i = 0; i < SP_STAGES; ++i) {
-            lt_mbar_init(&full[i], 1);
-            lt_mbar_init(&empty[i], 1);
-        }
-        lt_mbar_init(tfull, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lt_smem_u32(tmem_slot)), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    sp_cluster_sync();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            const int nk128 = 2 * nkb;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int stage = kb % SP_STAGES;
-                const uint32_t ph = (uint32_t)(kb / SP_STAGES) & 1u;
-                lt_mbar_wait(&empty[stage], ph ^ 1u);
-                if (rank == 0) lt_mbar_expect_tx(&full[stage], 2 * SP_STAGE_BYTES);
-                const uint32_t fl = sp_mapa(lt_smem_u32(&full[stage]), 0);
-                uint8_t* st = base + (size_t)stage * SP_STAGE_BYTES;
-                sp_tma_2d(st, &tmA, kb * 128, mtile * LT_BM, fl);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    sp_tma_2d(st + SP_OFF_B01 + h * 16384, &tmB, kb * SP_BK + h * 128, (int)rank * Nlo + ntile * LT_BN, fl);
-                    sp_tma_2d(st + SP_OFF_B2 + h * 8192, &tmB2, kb * SP_BK + h * 128, 2 * Nlo + ntile * LT_BN + (int)rank * 64, fl);
-                }
-                sp_tma_2d(st + SP_OFF_E, &tmE, 0, (mtile * nk128 + 2 * kb) * 8, fl);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            // D = S32, A = B = signed int8, sparse A, K-major, M = 256 over the CTA pair
-            constexpr uint32_t idesc_base = (1u << 2) | (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 4) << 24);
-            constexpr uint32_t idesc256 = idesc_base | ((256u >> 3) << 17);
-            constexpr uint32_t idesc128 = idesc_base | ((128u >> 3) << 17);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int stage = kb % SP_STAGES;
-                const uint32_t ph = (uint32_t)(kb / SP_STAGES) & 1u;
-                lt_mbar_wait(&full[stage], ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = lt_smem_u32(base + (size_t)stage * SP_STAGE_BYTES);
-                const uint32_t te = tmem_base + SP_TMEM_E + (uint32_t)(kb & 1) * 8u;
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-                    asm volatile("tcgen05.cp.cta_group::2.128x128b [%0], %1;" ::"r"(te + 4u * c), "l"(sp_edesc(sa + SP_OFF_E + c * 2048))
-                                 : "memory");
-                const uint64_t adesc = lt_desc(sa);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
-                    const uint64_t koff = (uint64_t)(4 * (j & 1));                      // 64 bytes of B per MMA
-                    const uint64_t b01 = lt_desc(sa + SP_OFF_B01 + (j >> 1) * 16384) + koff;
-                    const uint64_t b2 = lt_desc(sa + SP_OFF_B2 + (j >> 1) * 8192) + koff;
-                    sp_umma_i8(tmem_base, adesc + (uint64_t)(2 * j), b01, te + 2u * j, idesc256, acc);
-                    sp_umma_i8(tmem_base + 256u, adesc + (uint64_t)(2 * j), b2, te + 2u * j, idesc128, acc);
-                }
-                sp_commit_pair(&empty[stage]);
-            }
-            sp_commit_pair(tfull);
-        }
-    } else {
-        const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;
-        const long long grow = (long long)mtile * LT_BM + row;
-        const int p = (int)(grow / (2 * Mhi));
-        const int lhi = (int)(grow - (long long)p * 2 * Mhi) >> 1;
-        const bool odd = lane & 1;
-        const int llo0 = ntile * LT_BN;
-        const double inv_scale = (double)(*inv_scale_ptr);
-        lt_mbar_wait(tfull, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (mtile < n_mtiles) {
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-            float2* orow = out + ((size_t)p * Mhi + lhi) * Nlo + llo0;
-#pragma unroll 1
-            for (int ch = 0; ch < LT_BN / 16; ++ch) {
-                uint32_t a0[16], a1[16], a2[16];
-                lt_ld16(taddr + (uint32_t)(0 * LT_BN + ch * 16), a0);
-                lt_ld16(taddr + (uint32_t)(1 * LT_BN + ch * 16), a1);
-                lt_ld16(taddr + (uint32_t)(2 * LT_BN + ch * 16), a2);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float val[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const long long v = ((long long)(int)a0[j] * 128 + (long long)(int)a1[j]) * 128 + (long long)(int)a2[j];
-                    val[j] = (float)((double)v * inv_scale);
-                }
-                float2 o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float send = odd ? val[j] : val[8 + j];
-                    const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-                    o[j] = odd ? make_float2(recv, val[8 + j]) : make_float2(val[j], recv);
-                }
-                float4* dst = reinterpret_cast<float4*>(orow + ch * 16 + (odd ? 8 : 0));
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[2 * j].x, o[2 * j].y, o[2 * j + 1].x, o[2 * j + 1].y);
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    sp_cluster_sync();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
 // ---- sparse variant with A' generated straight into tensor memory --------------------------------------------
 // Measured (tools/sp_probe.cu): a sparse MMA pair (N = 256 + N = 128) costs 259 cycles when A' is read from shared memory but
 // 192 = 128 + 64 cycles (the issue floor) when A' sits in tensor memory; tcgen05.cp does not overlap with the MMAs (268).
@@ -834,7 +597,7 @@ template <bool PX>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2, int nkb, int Mhi, int Nlo,
                     int n_mtiles, const uint32_t* __restrict__ Ttab, const uint32_t* __restrict__ Etab, int Tw,
-                    const float* __restrict__ inv_scale_ptr, float2* __restrict__ out) {
+                    const float* __restrict__ inv_scale_ptr, float2* __restrict__ out, int accumulate) {
     extern __shared__ uint8_t lt_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)lt_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)TS_STAGES * TS_STAGE_BYTES);
@@ -996,7 +759,14 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 }
                 float4* dst = reinterpret_cast<float4*>(orow + ch * 16 + (odd ? 8 : 0));
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[2 * j].x, o[2 * j].y, o[2 * j + 1].x, o[2 * j + 1].y);
+                for (int j = 0; j < 4; ++j) {
+                    float4 w = make_float4(o[2 * j].x, o[2 * j].y, o[2 * j + 1].x, o[2 * j + 1].y);
+                    if (accumulate) {                           // residual pass: onto the first pass's samples
+                        const float4 p = dst[j];
+                        w = make_float4(p.x + w.x, p.y + w.y, p.z + w.z, p.w + w.w);
+                    }
+                    dst[j] = w;
+                }
             }
         }
     }
@@ -1051,36 +821,33 @@ extern "C" int qsft_eval_lattice_supported(int q, int n, int b, int P, int64_t S
     return 1;
 }
 
-extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths,
-                                       int64_t S, int q, int n, int b, int P, int ld, float* out, void* stream) {
+// residual_passes: 0 = one GEMM pass (20 bits below max|a|), 1 = a second pass over the quantisation residual accumulated
+// onto the first (41 bits; twice the tensor work), -1 = decide here: second pass iff min|a| < 0.1 max|a| (reads two floats
+// back, i.e. synchronises the stream once).
+extern "C" int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths, int64_t S,
+                                          int q, int n, int b, int P, int ld, float* out, int residual_passes, void* stream) {
     QSFT_CHECK_ARG(qsft_eval_lattice_supported(q, n, b, P, S), "lattice evaluation supports q = 4, 7 <= b <= 14 only");
     QSFT_CHECK_ARG(M && D && loc && strengths && out, "null pointer");
     QSFT_CHECK_ARG(ld >= n && ld % 16 == 0, "bad ld");
+    QSFT_CHECK_ARG(residual_passes >= -1 && residual_passes <= 1, "residual_passes must be -1 (auto), 0 or 1");
     cudaStream_t st = (cudaStream_t)stream;
     const int b1 = b / 2, b2 = b - b1;
     const long long Mhi = ipow64(4, b1), Nlo = ipow64(4, b2);
-    // Default: 2:4 structured-sparse A' (compressed + metadata, tcgen05.mma.sp on CTA pairs).  QSFT_LATTICE_SPARSE=0 selects
-    // the dense kernel: A' materialised in HBM (2 * Mhi * Kp bytes per delay row).  Either way the delay rows are processed in
-    // chunks that keep A' under a scratch budget (default 32 GB, QSFT_LATTICE_SCRATCH_GB overrides).
-    // QSFT_LATTICE_FUSED_A=1 (dense only) generates A' inside the GEMM from packed phase tables instead (no scratch, no HBM
-    // round trip; measured: tensor pipe 63 % instead of 90 % busy because the four producer warps cannot keep up, 38.2 ms vs
-    // 31.6 + 3.2 ms per block of 41 rows).  The limb operand B' is generated once in all variants.
-    bool fused_a = false;
-    int sparse_mode = 2;                                 // 2: A' generated into TMEM, 1: A' compressed in HBM, 0: dense
-    if (const char* env = getenv("QSFT_LATTICE_FUSED_A")) fused_a = atoi(env) != 0;
-    if (const char* env = getenv("QSFT_LATTICE_SPARSE")) sparse_mode = atoi(env);
-    if (fused_a || sparse_mode < 0 || sparse_mode > 2) sparse_mode = 0;
-    const bool sparse = sparse_mode == 1, sparse_ts = sparse_mode == 2;
-    const long long kalign = sparse_mode ? SP_BK : LT_BK;
+    // Default: 2:4 structured-sparse A' generated straight into tensor memory (tcgen05.mma.sp on CTA pairs; A' never exists
+    // in HBM or shared memory).  QSFT_LATTICE_SPARSE=0 selects the dense cross-check kernel: A' materialised in HBM
+    // (2 * Mhi * Kp bytes per delay row), delay rows processed in chunks that keep it under a scratch budget (default 32 GB,
+    // QSFT_LATTICE_SCRATCH_GB overrides).  Both are exact integer arithmetic and produce the same bits.
+    bool sparse_ts = true;
+    if (const char* env = getenv("QSFT_LATTICE_SPARSE")) sparse_ts = atoi(env) != 0;
+    const long long kalign = sparse_ts ? SP_BK : LT_BK;
     const long long Kp = (2 * S + kalign - 1) / kalign * kalign;
-    const long long Sp = Kp / 2;                        // padded support = compressed bytes per A' row
     double budget_gb = 32.0;
     if (const char* env = getenv("QSFT_LATTICE_SCRATCH_GB")) {
         const double v = atof(env);
         if (v > 0.0) budget_gb = v;
     }
-    const double per_row = 2.0 * (double)Mhi * (sparse ? 0.625 * (double)Kp : (double)Kp);
-    long long Pc = (fused_a || sparse_ts) ? P : (long long)(budget_gb * 1e9 / per_row);
+    const double per_row = 2.0 * (double)Mhi * (double)Kp;
+    long long Pc = sparse_ts ? P : (long long)(budget_gb * 1e9 / per_row);
     if (Pc < 1) Pc = 1;
     if (Pc > P) Pc = P;
     while (Pc * 2 * Mhi / LT_BM > 65535) --Pc;          // grid.y limit
@@ -1090,8 +857,7 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     uint8_t* e = nullptr;
     int2* alimb = nullptr;
     unsigned int* amax = nullptr;
-    float* inv_scale = nullptr;
-    uint8_t *A = nullptr, *Bq = nullptr, *Em = nullptr;
+    uint8_t *A = nullptr, *Bq = nullptr;
     int rc = QSFT_OK;
     auto alloc = [&](void** p, size_t bytes) {
         if (rc == QSFT_OK && qsft_scratch_alloc(p, bytes, st) != cudaSuccess) {
@@ -1104,131 +870,108 @@ extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const i
     const long long Se = (S + 3) & ~3ll;     // even row stride so that e[p][s0], e[p][s0+1] is one aligned 16-bit load
     alloc((void**)&e, (size_t)P * Se);
     alloc((void**)&alimb, (size_t)S * 8);
-    alloc((void**)&amax, 8);
-    const long long mt_max = ((Pc * 2 * Mhi / LT_BM) + 1) & ~1ll;      // m-tiles per chunk, padded to whole CTA pairs
-    const long long nk128 = Kp / 128;
-    if (fused_a || sparse_ts) {
+    alloc((void**)&amax, 16);                // [0] max, [1] min (bit patterns), [2..3] inv_scale of pass 0 / 1
+    if (sparse_ts) {
         alloc((void**)&Ttab, (size_t)Mhi * Tw * 4);
         alloc((void**)&Etab, (size_t)P * Tw * 4);
-    } else if (sparse) {
-        alloc((void**)&Etab, (size_t)P * Tw * 4);
-        alloc((void**)&A, (size_t)mt_max * LT_BM * Sp);
-        alloc((void**)&Em, (size_t)mt_max * nk128 * 2048);
     } else {
         alloc((void**)&A, (size_t)Pc * 2 * Mhi * Kp);
     }
     alloc((void**)&Bq, (size_t)LT_LIMBS * Nlo * Kp);
-    inv_scale = amax ? reinterpret_cast<float*>(amax + 1) : nullptr;
+    float* inv_scale = amax ? reinterpret_cast<float*>(amax + 2) : nullptr;
     if (rc == QSFT_OK) {
         const int T = 256;
         const unsigned sb = (unsigned)((S + T - 1) / T);
-        cudaMemsetAsync(amax, 0, 8, st);
+        const unsigned int init[2] = {0u, 0x7f7fffffu};
+        cudaMemcpyAsync(amax, init, 8, cudaMemcpyHostToDevice, st);
         lt_prep_kernel<<<sb, T, (size_t)n * b + (size_t)P * n, st>>>(M, D, loc, S, Se, n, b, b1, P, ld, hhi, hlo, e);
         lt_amax_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax);
-        lt_quant_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax, inv_scale, alimb);
+        g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
+        int passes = 1 + (residual_passes > 0 ? 1 : 0);
+        if (residual_passes < 0) {
+            lt_amin_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax + 1);
+            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+            float mm[2] = {0.f, 0.f};
+            if (cudaMemcpyAsync(mm, amax, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+                qsft_set_error("reading the strength range failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = QSFT_ECUDA;
+            }
+            if (mm[1] < 0.1f * mm[0]) passes = 2;
+        }
         const unsigned pb = (unsigned)((Kp / 4 + T - 1) / T);
-        lt_bgen_kernel<<<dim3(pb, (unsigned)((Nlo + LT_BGEN_LL - 1) / LT_BGEN_LL)), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp,
-                                                                                                 reinterpret_cast<uint32_t*>(Bq));
-        g_qsft_launches.fetch_add(4, std::memory_order_relaxed);
         const unsigned wb = (unsigned)((Tw + T - 1) / T);
-        if (fused_a || sparse_ts) {
+        if (sparse_ts && !rc) {
             lt_ttab_kernel<<<dim3(wb, (unsigned)((Mhi + LT_TTAB_LL - 1) / LT_TTAB_LL)), T, 0, st>>>(hhi, S, b1, Tw, Mhi, Ttab);
-            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
-        }
-        if (fused_a || sparse_mode) {
             lt_etab_kernel<<<dim3(wb, (unsigned)P), T, 0, st>>>(e, S, Se, P, Tw, Etab);
-            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+            g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
         }
-        CUtensorMap ma, mb, mb2, me;
-        rc = lt_make_map(&mb, Bq, LT_LIMBS * Nlo, Kp);
-        if (!rc && sparse_mode) rc = lt_make_map(&mb2, Bq, LT_LIMBS * Nlo, Kp, LT_BK, 64);
+        CUtensorMap ma, mb, mb2;
+        if (!rc) rc = lt_make_map(&mb, Bq, LT_LIMBS * Nlo, Kp);
+        if (!rc && sparse_ts) rc = lt_make_map(&mb2, Bq, LT_LIMBS * Nlo, Kp, LT_BK, 64);
         ma = mb;   // placeholder when A' is generated in the kernel
         if (!rc) {
             static bool attr = false;
             if (!attr) {
-                if (cudaFuncSetAttribute(lt_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
-                    cudaFuncSetAttribute(lt_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
-                    cudaFuncSetAttribute(lt_gemm_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM) != cudaSuccess ||
-                    cudaFuncSetAttribute(lt_gemm_spts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess ||
-                    cudaFuncSetAttribute(lt_gemm_spts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess) {
+                if (cudaFuncSetAttribute(lt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
+                    cudaFuncSetAttribute(lt_gemm_spts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess) {
                     qsft_set_error("cudaFuncSetAttribute failed");
                     rc = QSFT_ECUDA;
                 }
                 attr = true;
             }
         }
-        for (long long p0 = 0; p0 < P && !rc; p0 += Pc) {
-            const long long pc = (P - p0 < Pc) ? (P - p0) : Pc;
-            dim3 grid((unsigned)(Nlo / LT_BN), (unsigned)(pc * 2 * Mhi / LT_BM));
-            float2* o = reinterpret_cast<float2*>(out) + (size_t)p0 * Mhi * Nlo;
-            if (fused_a) {
-                lt_gemm_kernel<true><<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo, Ttab,
-                                                                        Etab + (size_t)p0 * Tw, (int)Tw, inv_scale, o);
-                g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
-            } else if (sparse_ts) {
-                const long long n_mt = pc * 2 * Mhi / LT_BM, n_mt_pad = (n_mt + 1) & ~1ll;
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3((unsigned)n_mt_pad, (unsigned)(Nlo / LT_BN));
-                cfg.blockDim = dim3(TS_THREADS);
-                cfg.dynamicSmemBytes = TS_SMEM;
-                cfg.stream = st;
-                cudaLaunchAttribute cattr[1];
-                cattr[0].id = cudaLaunchAttributeClusterDimension;
-                cattr[0].val.clusterDim.x = 2;
-                cattr[0].val.clusterDim.y = 1;
-                cattr[0].val.clusterDim.z = 1;
-                cfg.attrs = cattr;
-                cfg.numAttrs = 1;
-                const char* px = getenv("QSFT_LATTICE_EXPAND");                  // opt-in A' expansion variant (see ts_expand)
-                cudaLaunchKernelEx(&cfg, (px && atoi(px) == 1) ? lt_gemm_spts_kernel<true> : lt_gemm_spts_kernel<false>, mb, mb2,
-                                   (int)(Kp / SP_BK), (int)Mhi, (int)Nlo, (int)n_mt,
-                                   (const uint32_t*)Ttab, (const uint32_t*)(Etab + (size_t)p0 * Tw), (int)Tw,
-                                   (const float*)inv_scale, o);
-                g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
-            } else if (sparse) {
-                const long long n_mt = pc * 2 * Mhi / LT_BM, n_mt_pad = (n_mt + 1) & ~1ll;
-                if (n_mt_pad != n_mt) {         // odd tile count: give the idle half of the last CTA pair well-formed operands
-                    cudaMemsetAsync(A + (size_t)n_mt * LT_BM * Sp, 0, (size_t)LT_BM * Sp, st);
-                    cudaMemsetAsync(Em + (size_t)n_mt * nk128 * 2048, 0x88, (size_t)nk128 * 2048, st);
+        for (int pass = 0; pass < passes && !rc; ++pass) {
+            // the limb operand B' of this pass (shared by all delay rows)
+            lt_quant_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax, inv_scale, alimb, pass);
+            lt_bgen_kernel<<<dim3(pb, (unsigned)((Nlo + LT_BGEN_LL - 1) / LT_BGEN_LL)), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp,
+                                                                                                     reinterpret_cast<uint32_t*>(Bq));
+            g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
+            for (long long p0 = 0; p0 < P && !rc; p0 += Pc) {
+                const long long pc = (P - p0 < Pc) ? (P - p0) : Pc;
+                float2* o = reinterpret_cast<float2*>(out) + (size_t)p0 * Mhi * Nlo;
+                if (sparse_ts) {
+                    const long long n_mt = pc * 2 * Mhi / LT_BM, n_mt_pad = (n_mt + 1) & ~1ll;
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3((unsigned)n_mt_pad, (unsigned)(Nlo / LT_BN));
+                    cfg.blockDim = dim3(TS_THREADS);
+                    cfg.dynamicSmemBytes = TS_SMEM;
+                    cfg.stream = st;
+                    cudaLaunchAttribute cattr[1];
+                    cattr[0].id = cudaLaunchAttributeClusterDimension;
+                    cattr[0].val.clusterDim.x = 2;
+                    cattr[0].val.clusterDim.y = 1;
+                    cattr[0].val.clusterDim.z = 1;
+                    cfg.attrs = cattr;
+                    cfg.numAttrs = 1;
+                    cudaLaunchKernelEx(&cfg, lt_gemm_spts_kernel<false>, mb, mb2, (int)(Kp / SP_BK), (int)Mhi, (int)Nlo, (int)n_mt,
+                                       (const uint32_t*)Ttab, (const uint32_t*)(Etab + (size_t)p0 * Tw), (int)Tw,
+                                       (const float*)(inv_scale + pass), o, pass);
+                    g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+                } else {
+                    dim3 grid((unsigned)(Nlo / LT_BN), (unsigned)(pc * 2 * Mhi / LT_BM));
+                    lt_agen_kernel<<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, e + (size_t)p0 * Se, S, Se, b1, (int)pc, Mhi, Kp,
+                                                                          reinterpret_cast<uint32_t*>(A));
+                    rc = lt_make_map(&ma, A, pc * 2 * Mhi, Kp);
+                    if (rc) break;
+                    lt_gemm_kernel<<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo,
+                                                                      (const float*)(inv_scale + pass), o, pass);
+                    g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
                 }
-                const unsigned ab = (unsigned)((Sp / 16 + T - 1) / T);
-                lt_agen_sp_kernel<<<dim3(ab, (unsigned)Mhi), T, 0, st>>>(hhi, Etab + (size_t)p0 * Tw, S, b1, (int)pc, Mhi, Sp, Tw, A, Em);
-                rc = lt_make_map(&ma, A, n_mt_pad * LT_BM, Sp);
-                if (!rc) rc = lt_make_map(&me, Em, n_mt_pad * nk128 * 8, 256, 256, 16, false);
-                if (rc) break;
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3((unsigned)(2 * (Nlo / LT_BN)), (unsigned)(n_mt_pad / 2));
-                cfg.blockDim = dim3(LT_THREADS);
-                cfg.dynamicSmemBytes = SP_SMEM;
-                cfg.stream = st;
-                cudaLaunchAttribute cattr[1];
-                cattr[0].id = cudaLaunchAttributeClusterDimension;
-                cattr[0].val.clusterDim.x = 2;
-                cattr[0].val.clusterDim.y = 1;
-                cattr[0].val.clusterDim.z = 1;
-                cfg.attrs = cattr;
-                cfg.numAttrs = 1;
-                cudaLaunchKernelEx(&cfg, lt_gemm_sp_kernel, ma, mb, mb2, me, (int)(Kp / SP_BK), (int)Mhi, (int)Nlo, (int)n_mt,
-                                   (const float*)inv_scale, o);
-                g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
-            } else {
-                lt_agen_kernel<<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, e + (size_t)p0 * Se, S, Se, b1, (int)pc, Mhi, Kp,
-                                                                      reinterpret_cast<uint32_t*>(A));
-                rc = lt_make_map(&ma, A, pc * 2 * Mhi, Kp);
-                if (rc) break;
-                lt_gemm_kernel<false><<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo, nullptr,
-                                                                         nullptr, 0, inv_scale, o);
-                g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
-            }
-            cudaError_t ce = cudaGetLastError();
-            if (ce != cudaSuccess) {
-                qsft_set_error("lattice GEMM launch failed: %s", cudaGetErrorString(ce));
-                rc = QSFT_ECUDA;
+                cudaError_t ce = cudaGetLastError();
+                if (ce != cudaSuccess) {
+                    qsft_set_error("lattice GEMM launch failed: %s", cudaGetErrorString(ce));
+                    rc = QSFT_ECUDA;
+                }
             }
         }
     }
-    void* frees[] = {hhi, hlo, e, alimb, amax, A, Bq, Ttab, Etab, Em};
+    void* frees[] = {hhi, hlo, e, alimb, amax, A, Bq, Ttab, Etab};
     for (void* p : frees)
         if (p) cudaFreeAsync(p, st);
     return rc;
+}
+
+extern "C" int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths,
+                                       int64_t S, int q, int n, int b, int P, int ld, float* out, void* stream) {
+    return qsft_eval_synth_lattice_ex(M, D, loc, strengths, S, q, n, b, P, ld, out, -1, stream);
 }

@@ -182,9 +182,11 @@ def lattice_supported(q, n, b, P, S):
     return bool(_lib.lib().qsft_eval_lattice_supported(q, n, b, P, S))
 
 
-def eval_synth_lattice(M, D, loc, strengths, q, out=None):
+def eval_synth_lattice(M, D, loc, strengths, q, out=None, residual_passes=-1):
     """Fused K1+K2 for the lattice {M l + d_p} (q = 4): M (n, b), D (P, n) integer arrays, loc (S, ld) int8 device,
-    strengths (S,) complex64 device -> samples (P, q^b) complex64."""
+    strengths (S,) complex64 device -> samples (P, q^b) complex64.  residual_passes: 0 = one GEMM pass (absolute error
+    ~7e-7 max|a| per coefficient), 1 = second pass over the quantisation residual (for strengths of very different sizes),
+    -1 = decided from the device data (one stream synchronisation)."""
     _need_cuda(loc, strengths)
     M = np.ascontiguousarray(M, dtype=np.int8)
     D = np.ascontiguousarray(D, dtype=np.int8)
@@ -196,8 +198,8 @@ def eval_synth_lattice(M, D, loc, strengths, q, out=None):
     if out is None:
         out = torch.empty((P, q ** b), dtype=torch.complex64, device=dev)
     with torch.cuda.device(dev), _timed("k2_eval_lattice", P * (q ** b) * S):
-        _lib.check(_lib.lib().qsft_eval_synth_lattice(_ptr(Md), _ptr(Dd), _ptr(loc), _ptr(strengths), S, q, n, b, P, ld,
-                                                      _ptr(out), _stream()))
+        _lib.check(_lib.lib().qsft_eval_synth_lattice_ex(_ptr(Md), _ptr(Dd), _ptr(loc), _ptr(strengths), S, q, n, b, P, ld,
+                                                         _ptr(out), int(residual_passes), _stream()))
     return out
 
 
@@ -209,6 +211,17 @@ def gwht_batch_(x, q, b):
     batch = x.numel() // (q ** b)
     with torch.cuda.device(x.device), _timed("k3_gwht", x.numel()):
         _lib.check(_lib.lib().qsft_gwht_batch(_ptr(x), batch, q, b, _stream()))
+    return x
+
+
+def add_noise_(x, sd, seed, offset=0):
+    """x (complex64 CUDA tensor, contiguous) += sd * (N(0,1) + i N(0,1)) per element, Philox keyed by (seed, offset +
+    element / 2): the same (seed, offset) adds the same noise on every rank."""
+    _need_cuda(x)
+    if x.dtype != torch.complex64:
+        raise ValueError("x must be complex64")
+    with torch.cuda.device(x.device), _timed("k5_noise", x.numel()):
+        _lib.check(_lib.lib().qsft_add_noise(_ptr(x), x.numel(), float(sd), int(seed) & (2 ** 64 - 1), int(offset), _stream()))
     return x
 
 

@@ -74,6 +74,11 @@ class SyntheticSubsampledSignal(SubsampledSignal):
             self._loc_dev = ops.pad_digits(self.locq, self.ld, self.device, transposed=True)
         if self._a_dev is None:
             self._a_dev = torch.from_numpy(self.strengths.astype(np.complex64)).to(self.device)
+        # precision of the lattice GEMM (ops.eval_synth_lattice): strengths of very different sizes need the residual pass for
+        # 1e-5 relative accuracy of the small ones; decided here on the host copy (no device round trip per block)
+        mag = np.maximum(np.abs(self.strengths.real), np.abs(self.strengths.imag)) if len(self.strengths) else np.zeros(1)
+        nz = mag[mag > 0]
+        self._residual_passes = int(len(nz) > 0 and nz.min() < 0.1 * nz.max())
 
     def subsample_device(self, digits):
         """digits (N, ld) int8 on the device -> complex64 samples (N,)."""
@@ -87,7 +92,8 @@ class SyntheticSubsampledSignal(SubsampledSignal):
         if self.eval_impl == 3 and not ok:
             raise ValueError("eval_impl=3 (lattice) supports q = 4 and 7 <= b <= 14 only")
         if ok and (self.eval_impl == 3 or (self.eval_impl == 0 and S >= 512)):
-            return ops.eval_synth_lattice(M, D_rows, self._loc_dev, self._a_dev, self.q, out=out)
+            return ops.eval_synth_lattice(M, D_rows, self._loc_dev, self._a_dev, self.q, out=out,
+                                          residual_passes=self._residual_passes)
         return None
 
     def subsample(self, query_indices):
@@ -107,6 +113,14 @@ class SyntheticSubsampledSignal(SubsampledSignal):
         independent N(0, noise_sd^2 / (2 q^b)) on the real and imaginary part of every bin."""
         mdu = super().get_MDU(ret_num_subsample, ret_num_repeat, b, trans_times)
         nu = self.noise_sd / np.sqrt(2 * self.q ** b)
+        seed = None
+        if self.noise_rng != "numpy" and nu > 0:
+            # device noise (qsft_add_noise, Philox): ONE seed per call from the host RNG; with several ranks rank 0's, so
+            # that every rank adds the same noise to its copy of the bins
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+            if self.dist is not None and self.dist.world_size > 1:
+                seed = int(self.dist.from_rank0(np.array([seed]))[0])
+        offset = 0
         for i in range(len(mdu[2])):
             for j in range(len(mdu[2][i])):
                 u = mdu[2][i][j]
@@ -115,6 +129,6 @@ class SyntheticSubsampledSignal(SubsampledSignal):
                     noise = (noise[..., 0] + 1j * noise[..., 1]).astype(np.complex64)
                     mdu[2][i][j] = u + torch.from_numpy(noise).to(u.device)
                 elif nu > 0:
-                    g = torch.randn(tuple(u.shape) + (2,), dtype=torch.float32, device=u.device) * float(nu)
-                    mdu[2][i][j] = u + torch.view_as_complex(g)
+                    mdu[2][i][j] = ops.add_noise_(u.clone(), nu, seed, offset)     # the stored transforms stay clean
+                    offset += (u.numel() + 1) // 2
         return mdu

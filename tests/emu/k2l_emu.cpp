@@ -15,13 +15,17 @@ int emu_lt_prep(const int8_t* M, const int8_t* D, const int8_t* loc, long long S
     return 0;
 }
 
-int emu_lt_quant(const float* a, long long S, float* inv_scale, int32_t* alimb /* (S, 2) */) {
+// pass 0: limbs of round(a * scale); pass 1: limbs of the quantisation residual (inv_scale holds two floats)
+int emu_lt_quant(const float* a, long long S, float* inv_scale, int32_t* alimb /* (S, 2) */, int pass) {
     const int T = 256;
     unsigned int amax = 0;
     const unsigned sb = (unsigned)((S + T - 1) / T);
     emu::launch(dim3(sb), dim3(T), [&]() { lt_amax_kernel(reinterpret_cast<const float2*>(a), S, &amax); });
     emu::launch(dim3(sb), dim3(T), [&]() {
-        lt_quant_kernel(reinterpret_cast<const float2*>(a), S, &amax, inv_scale, reinterpret_cast<int2*>(alimb));
+        lt_quant_kernel(reinterpret_cast<const float2*>(a), S, &amax, inv_scale, reinterpret_cast<int2*>(alimb), 0);
+    });
+    if (pass == 1) emu::launch(dim3(sb), dim3(T), [&]() {
+        lt_quant_kernel(reinterpret_cast<const float2*>(a), S, &amax, inv_scale, reinterpret_cast<int2*>(alimb), 1);
     });
     return 0;
 }

@@ -21,7 +21,7 @@ def emu():
     L = C.CDLL(build_emu.build(which="k2l"))
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_longlong
     L.emu_lt_prep.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp, vp]
-    L.emu_lt_quant.argtypes = [vp, i64, vp, vp]
+    L.emu_lt_quant.argtypes = [vp, i64, vp, vp, C.c_int]
     L.emu_lt_bgen.argtypes = [vp, vp, i64, i32, i64, i64, vp]
     L.emu_lt_ttab.argtypes = [vp, i64, i32, i64, i64, vp]
     L.emu_lt_etab.argtypes = [vp, i64, i64, i32, i64, vp]
@@ -60,9 +60,19 @@ def test_emulated_lattice_operands_reproduce_the_samples(emu, n, b, S, P, seed):
     assert np.array_equal(e[:, :S], (D @ locq) % q)
     # quantisation: three balanced base-128 limbs
     a32 = np.ascontiguousarray(a.astype(np.complex64))
-    inv_scale = np.zeros(1, dtype=np.float32)
+    inv_scale = np.zeros(2, dtype=np.float32)
     alimb = np.zeros((S, 2), dtype=np.int32)
-    assert emu.emu_lt_quant(_p(a32), S, _p(inv_scale), _p(alimb)) == 0
+    # residual pass: limbs of (a * scale - round(a * scale)) * 2^21; both passes together reproduce a to ~2^-41 max|a|
+    alimb2 = np.zeros((S, 2), dtype=np.int32)
+    assert emu.emu_lt_quant(_p(a32), S, _p(inv_scale), _p(alimb2), 1) == 0
+    assert emu.emu_lt_quant(_p(a32), S, _p(inv_scale), _p(alimb), 0) == 0
+    l2 = alimb2.view(np.int8).reshape(S, 2, 4)[:, :, :3].astype(np.int64)
+    l1 = alimb.view(np.int8).reshape(S, 2, 4)[:, :, :3].astype(np.int64)
+    v1 = (l1[:, :, 0] * 128 + l1[:, :, 1]) * 128 + l1[:, :, 2]
+    v2 = (l2[:, :, 0] * 128 + l2[:, :, 1]) * 128 + l2[:, :, 2]
+    both = (v1[:, 0] + 1j * v1[:, 1]) * float(inv_scale[0]) + (v2[:, 0] + 1j * v2[:, 1]) * float(inv_scale[1])
+    assert np.abs(v2).max() <= 2 ** 20 and abs(float(inv_scale[1]) * 2 ** 21 / float(inv_scale[0]) - 1) < 1e-6
+    assert np.max(np.abs(both - a32)) <= 1e-6 * float(inv_scale[0])
     limbs = alimb.view(np.int8).reshape(S, 2, 4)[:, :, :3].astype(np.int64)     # (S, re/im, limb)
     assert np.abs(limbs[:, :, 1:]).max() <= 64
     vq = (limbs[:, :, 0] * 128 + limbs[:, :, 1]) * 128 + limbs[:, :, 2]

@@ -242,11 +242,6 @@ def test_wide_index_pipeline_matches_reference(name):
     assert np.max(np.abs(dv - g["res_vals"])) <= 1e-5 * np.max(np.abs(g["res_vals"]))
 
 
-# ---- experimental kernels (opt-in, written without GPU time; run with QSFT_TEST_EXPERIMENTAL=1) ---------------------
-experimental = pytest.mark.skipif(os.environ.get("QSFT_TEST_EXPERIMENTAL") != "1",
-                                  reason="opt-in kernels not yet validated on a GPU (set QSFT_TEST_EXPERIMENTAL=1)")
-
-
 @pytest.mark.parametrize("q,n,b,S,R,chan,noise", [(4, 40, 10, 100_000, 1, "nso", 0.0), (4, 20, 7, 1000, 3, "nso", 3.16),
                                                   (4, 10, 4, 100, 1, "identity", 0.0), (3, 12, 5, 60, 2, "nso", 0.0),
                                                   (5, 6, 3, 25, 1, "identity", 0.02), (2, 100, 6, 30, 1, "nso", 0.0),
@@ -304,20 +299,40 @@ def test_dense_gwht_igwht_utils():
             assert shaped.shape == tuple([q] * b) and np.max(np.abs(shaped.ravel() - y)) == 0
 
 
-@experimental
-@pytest.mark.parametrize("n,b,S,P,seed", [(14, 7, 700, 5, 0), (40, 10, 3000, 3, 1), (20, 9, 257, 4, 3)])
-def test_experimental_lattice_expand_variant_bit_identical(n, b, S, P, seed, monkeypatch):
-    """QSFT_LATTICE_EXPAND=1 (PRMT sign-replication A' expansion in the tensor-memory GEMM) produces the same bits."""
-    q = 4
-    rng = np.random.default_rng(seed)
-    M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
-    locq = rng.integers(0, q, (n, S))
-    a = rng.uniform(0.5, 2, S) * np.exp(1j * rng.uniform(0, 2 * np.pi, S))
-    ld = utils.padded_ld(n)
-    loc = ops.pad_digits(locq.T, ld, DEV)
-    ad = torch.from_numpy(a.astype(np.complex64)).to(DEV)
-    monkeypatch.delenv("QSFT_LATTICE_EXPAND", raising=False)
-    ref = ops.eval_synth_lattice(M, D, loc, ad, q).clone()
-    monkeypatch.setenv("QSFT_LATTICE_EXPAND", "1")
-    got = ops.eval_synth_lattice(M, D, loc, ad, q)
-    assert torch.equal(got, ref)
+def test_device_noise_statistics_and_determinism():
+    """qsft_add_noise (Philox): zero mean, the requested variance on both parts, the same values for the same (seed, offset)
+    whatever the buffer split, different values for another seed."""
+    n = 1 << 20
+    base = torch.zeros(n, dtype=torch.complex64, device=DEV)
+    a = ops.add_noise_(base.clone(), 0.5, seed=123)
+    b = ops.add_noise_(base.clone(), 0.5, seed=123)
+    c = ops.add_noise_(base.clone(), 0.5, seed=124)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    re, im = a.real.double(), a.imag.double()
+    assert abs(float(re.mean())) < 3e-3 and abs(float(im.mean())) < 3e-3
+    assert abs(float(re.var()) - 0.25) < 3e-3 and abs(float(im.var()) - 0.25) < 3e-3
+    assert abs(float((re * im).mean())) < 3e-3
+    # two halves with the second offset by the elements of the first = one call over the whole buffer
+    h = n // 2
+    lo = ops.add_noise_(base[:h].clone(), 0.5, seed=123, offset=0)
+    hi = ops.add_noise_(base[h:].clone(), 0.5, seed=123, offset=h // 2)
+    assert torch.equal(torch.cat([lo, hi]), a)
+    odd = ops.add_noise_(torch.zeros(7, dtype=torch.complex64, device=DEV), 1.0, seed=5)
+    assert bool((odd != 0).all())
+
+
+def test_noisy_transform_with_device_noise_nmse():
+    """Config-2 shape with noise drawn on the device: statistical parity with the reference's NMSE at the same SNR
+    (3.393e-6 for the NumPy stream, seed 0) -- the device stream gives another draw of the same law."""
+    n, q, S, b, C, R = 20, 4, 1000, 7, 3, 3
+    qa = {"query_method": "complex", "num_subsample": C, "delays_method_source": "identity", "subsampling_method": "qsft",
+          "delays_method_channel": "nso", "num_repeat": R, "b": b}
+    np.random.seed(0)
+    sig = qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=1, a_max=1, noise_sd=3.1623, query_args=dict(qa),
+                                                  noise_rng="device")
+    got = qsft_b200.QSFT(num_subsample=C, num_repeat=R, b=b, reconstruct_method_source="identity",
+                         reconstruct_method_channel="nso").transform(sig)
+    true = sig.signal_w
+    assert set(got.keys()) == set(true.keys())
+    nmse = sum(abs(got[k] - v) ** 2 for k, v in true.items()) / sum(abs(v) ** 2 for v in true.values())
+    assert 2.0e-6 < nmse < 5.5e-6, nmse
