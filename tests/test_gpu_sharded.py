@@ -80,9 +80,10 @@ def test_sharded_peel_equals_single_gpu(name, world):
     U0 = torch.from_numpy(np.ascontiguousarray(g["mdu_Us"].reshape(p["trC"], -1, q ** p["trb"])).astype(np.complex64)).to(DEV)
     D = g["mdu_Ds"].reshape(p["trC"], -1, n)
     cutoff = 1e-9 + 1.5 * p["noise_sd"] ** 2 / q ** p["trb"]
+    Ms = [np.array(M) for M in g["mdu_Ms"]]                  # read the archive here: NpzFile is not thread safe
 
     def make_problem():
-        return ops.PeelProblem(q, n, p["trb"], list(g["mdu_Ms"]), D, p["P_src"], p["chan"], p["src"], cutoff, DEV)
+        return ops.PeelProblem(q, n, p["trb"], Ms, D, p["P_src"], p["chan"], p["src"], cutoff, DEV)
 
     single = make_problem()
     single.alloc(4 * U0.shape[0] * U0.shape[2])
