@@ -91,6 +91,12 @@ int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stream);
  * symmetric U buffer), i.e. P2P stores over NVLink instead of a separate collective.  peer_x is a HOST array.        */
 int qsft_gwht_batch_bcast(float* x, int64_t batch, int q, int b, float* const* peer_x, int n_peers, void* stream);
 
+/* The same with ONE store per element: mc_x = the address of x in the NVLS MULTICAST mapping of the ranks' symmetric U
+ * buffers (torch.distributed._symmetric_memory: handle.multicast_ptr + the offset of x in the buffer).  The last pass stores
+ * with multimem.st; NVSwitch replicates every store to all ranks of the mapping, this one included, so each byte leaves the
+ * GPU once instead of once per peer.  Callers fall back to qsft_gwht_batch_bcast where no multicast mapping exists.       */
+int qsft_gwht_batch_mcast(float* x, int64_t batch, int q, int b, float* mc_x, void* stream);
+
 /* Verification helper (host only, no device work): work item of ticket number `ticket` in the single-launch two-pass
  * q = 4 transform (k3_q4_twopass_kernel): block, tile inside its pass, and whether it belongs to the strided (second)
  * pass.  A strided tile of block k waits for all tiles1 contiguous tiles of block k; tests check that those always

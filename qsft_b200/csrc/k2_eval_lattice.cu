@@ -159,6 +159,9 @@ __global__ void lt_quant_kernel(const float2* __restrict__ a, long long S, const
     // leave a common relative error of 1e-7 on all coefficients)
     int ex = 0;
     if (amax > 0.f) (void)frexpf(amax, &ex);
+    // three balanced limbs reach +-(64 * 128^2 + 64 * 128 + 64) = 2^20 + 8256: a maximum that is (just above) a power of two
+    // -- unit-modulus strengths, the reference's default -- can take one more bit
+    if (amax > 0.f && ldexpf(amax, LT_SCALE_BITS + 1 - ex) <= 1056832.0f) --ex;
     const float scale = amax > 0.f ? ldexpf(1.0f, LT_SCALE_BITS - ex) : 0.f;
     if (s == 0 && pass == 0) {
         inv_scale[0] = amax > 0.f ? ldexpf(1.0f, ex - LT_SCALE_BITS) : 0.f;

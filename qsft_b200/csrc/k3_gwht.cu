@@ -325,6 +325,7 @@ k3_q4_twopass_kernel(float2* __restrict__ x, long long B, int r1, int r2, long l
     if (t < tiles1) {
         K3Peers none;
         none.n = 0;
+    none.mc = nullptr;
         k3_q4_tile<false>(s, base, t, r1, 0, 1, 0, 1.0f, x, none);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -436,6 +437,10 @@ int launch_pass_q(float2* x, long long B, int q, const PassPlan& p, long long bl
 __global__ void k3_bcast_copy_kernel(const float2* __restrict__ x, long long n, K3Peers peers) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float2 v = x[i];
+        if (peers.mc != nullptr) {
+            asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(peers.mc + i), "f"(v.x), "f"(v.y) : "memory");
+            continue;
+        }
         for (int r = 0; r < peers.n; ++r) peers.p[r][i] = v;
     }
 }
@@ -487,7 +492,7 @@ static int gwht_impl(float* x, int64_t batch, int q, int b, const K3Peers& peers
         if (!(impl && atoi(impl) == 1)) {
             float* pp[7];
             for (int r = 0; r < 7; ++r) pp[r] = r < peers.n ? reinterpret_cast<float*>(peers.p[r]) : nullptr;
-            const int rc = qsft_k3_q4_tma(x, batch, b, pp, peers.n, (cudaStream_t)stream);
+            const int rc = qsft_k3_q4_tma(x, batch, b, pp, peers.n, reinterpret_cast<float*>(peers.mc), (cudaStream_t)stream);
             if (rc != QSFT_EUNSUPPORTED) return rc;
         }
     }
@@ -539,6 +544,7 @@ static int gwht_impl(float* x, int64_t batch, int q, int b, const K3Peers& peers
     }
     K3Peers none;
     none.n = 0;
+    none.mc = nullptr;
     bool all_fused = true;
     for (long long blk0 = 0; blk0 < batch; blk0 += chunk) {
         const long long nblk = (batch - blk0 < chunk) ? (batch - blk0) : chunk;
@@ -559,13 +565,24 @@ static int gwht_impl(float* x, int64_t batch, int q, int b, const K3Peers& peers
 extern "C" int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stream) {
     K3Peers none;
     none.n = 0;
+    none.mc = nullptr;
     return gwht_impl(x, batch, q, b, none, stream);
+}
+
+extern "C" int qsft_gwht_batch_mcast(float* x, int64_t batch, int q, int b, float* mc_x, void* stream) {
+    QSFT_CHECK_ARG(mc_x != nullptr && ((uintptr_t)mc_x & 7) == 0, "bad multicast pointer");
+    K3Peers peers;
+    peers.n = 1;                             // "has peers": selects the kernels' peer-store instantiation
+    for (int r = 0; r < 7; ++r) peers.p[r] = nullptr;
+    peers.mc = reinterpret_cast<float2*>(mc_x);
+    return gwht_impl(x, batch, q, b, peers, stream);
 }
 
 extern "C" int qsft_gwht_batch_bcast(float* x, int64_t batch, int q, int b, float* const* peer_x, int n_peers, void* stream) {
     QSFT_CHECK_ARG(n_peers >= 0 && n_peers <= 7, "n_peers must be in [0, 7]");
     QSFT_CHECK_ARG(n_peers == 0 || peer_x != nullptr, "null peer list");
     K3Peers peers;
+    peers.mc = nullptr;
     peers.n = n_peers;
     for (int r = 0; r < 7; ++r) peers.p[r] = r < n_peers ? reinterpret_cast<float2*>(peer_x[r]) : nullptr;
     for (int r = 0; r < n_peers; ++r) QSFT_CHECK_ARG(peer_x[r] != nullptr, "null peer pointer");

@@ -4,13 +4,22 @@
 namespace {
 
 // Peer copies of the output (fused transform + all-gather): the final store of the last pass also writes the element to
-// the same offset of up to 7 peer buffers (P2P stores over NVLink into the peers' symmetric U buffers).
+// the same offset of the peers' symmetric U buffers -- either with ONE multimem.st to the buffers' NVLS multicast address
+// (`mc` != nullptr: NVSwitch replicates the store to every rank, this one included; the GPU sends each byte once), or, where
+// no multicast mapping exists, with up to 7 unicast P2P stores (each byte leaves the GPU once per peer).
 struct K3Peers {
     float2* p[7];
     int n;
+    float2* mc;                              // multicast alias of xroot (0: unicast peer stores)
 };
 
 __device__ __forceinline__ void k3_store(float2* dst, float2 v, const float2* xroot, const K3Peers& peers) {
+#ifndef QSFT_EMU
+    if (peers.mc != nullptr) {
+        asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(peers.mc + (dst - xroot)), "f"(v.x), "f"(v.y) : "memory");
+        return;
+    }
+#endif
     *dst = v;
     if (peers.n > 0) {
         const long long off = dst - xroot;

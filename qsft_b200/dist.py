@@ -5,6 +5,8 @@ U is all-gathered once; peeling is bin-sharded (each rank classifies and updates
 group) with ONE all-gather of the round's finds per round -- the only collective type on the path."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as td
@@ -28,6 +30,7 @@ class DistContext:
         # symmetric (peer-mapped) U buffers let K3 store its output straight into every peer (fused all-gather);
         # falls back to NCCL all_gather_into_tensor when symmetric memory is not available
         self.symmetric = bool(symmetric) and td.get_backend(group) == "nccl" and self.world_size <= 8
+        self.multicast = os.environ.get("QSFT_NO_MULTICAST") is None       # (env: A/B of multimem.st against unicast stores)
         self._symm_free = {}
 
     def shard_peel(self, u_bytes):
@@ -51,7 +54,14 @@ class DistContext:
             buf = symm_mem.empty(int(nfloats), dtype=torch.float32, device=device)
             hdl = symm_mem.rendezvous(buf, grp)
             ptrs = [int(p) for p in hdl.buffer_ptrs]
-            return (buf, hdl, ptrs)
+            # NVLS multicast alias of the buffer (0 where the platform has none): one multimem.st reaches every rank
+            mc = 0
+            if self.multicast:
+                try:
+                    mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                except Exception:  # pragma: no cover - depends on the platform
+                    mc = 0
+            return (buf, hdl, ptrs, mc)
         except Exception as exc:  # pragma: no cover - depends on the platform
             self.symmetric = False
             self.symmetric_error = repr(exc)

@@ -159,8 +159,11 @@ class SubsampledSignal(Signal):
                             target.copy_(samples)
                         if self._symm is not None:
                             row_off = (g0 + p0) * B * 8          # bytes from the start of the symmetric buffer
-                            peers = [ptr + row_off for r, ptr in enumerate(self._symm[2]) if r != self.dist.rank]
-                            ops.gwht_batch_bcast_(target, self.q, bb, peers)
+                            if self._symm[3]:                    # NVLS multicast mapping: one store reaches every rank
+                                ops.gwht_batch_mcast_(target, self.q, bb, self._symm[3] + row_off)
+                            else:
+                                peers = [ptr + row_off for r, ptr in enumerate(self._symm[2]) if r != self.dist.rank]
+                                ops.gwht_batch_bcast_(target, self.q, bb, peers)
                         else:
                             ops.gwht_batch_(target, self.q, bb)
                     else:

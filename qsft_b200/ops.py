@@ -238,6 +238,19 @@ def gwht_batch_bcast_(x, q, b, peer_ptrs):
     return x
 
 
+def gwht_batch_mcast_(x, q, b, mc_ptr):
+    """K3 fused with the all-gather of its output through the NVLS multicast mapping of the symmetric U buffers: in place
+    on x (rows, q^b); the last pass stores every element once to `mc_ptr` (the multicast address of x), NVSwitch delivers
+    it to every rank including this one."""
+    _need_cuda(x)
+    if x.dtype != torch.complex64 or x.shape[-1] != q ** b:
+        raise ValueError("x must be complex64 with last dimension q^b")
+    batch = x.numel() // (q ** b)
+    with torch.cuda.device(x.device), _timed("k3_gwht", x.numel()):
+        _lib.check(_lib.lib().qsft_gwht_batch_mcast(_ptr(x), batch, q, b, C.c_void_p(int(mc_ptr)), _stream()))
+    return x
+
+
 def channel_code(channel, nso_subtype="nso1"):
     """reconstruct_method_channel (+ nso_subtype) -> the C ABI's channel code (qsft_peel_desc.channel)."""
     if channel == "identity":

@@ -78,6 +78,7 @@ extern "C" int emu_gwht(float* xf, long long batch, int q, int b, int lag, float
     peers.p[0] = reinterpret_cast<float2*>(peer0);
     K3Peers none;
     none.n = 0;
+    none.mc = nullptr;
     if (lag >= 0 && q == 4 && passes == 2 && plans[0].T == 4096 && plans[1].T == 4096 && plans[0].r <= 6 && plans[1].r <= 6) {
         std::vector<unsigned int> done((size_t)batch + 1, 0u);
         const int t1 = (int)plans[0].tiles_per_block, t2 = (int)plans[1].tiles_per_block;
