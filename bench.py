@@ -287,7 +287,8 @@ def run_ours(a):
         for s_ in range(a.warmup, total_steps):
             sig_ = build_signal(inputs[s_], None)
             res_, sft_ = transform(sig_, output)
-            last_ = (res_, inputs[s_][0], sft_.last_stats, getattr(sig_, "_symm", None) is not None)
+            symm_ = getattr(sig_, "_symm", None)
+            last_ = (res_, inputs[s_][0], sft_.last_stats, "mcast" if (symm_ is not None and symm_[3]) else ("p2p" if symm_ is not None else ""))
         e1.record()
         barrier()
         ms = max(e0.elapsed_time(e1), (time.time() - t_wall0) * 1e3)
@@ -397,7 +398,9 @@ def run_ours(a):
                    "l2": "inputs larger than L2 (per-step working set >= 1 GB)", "support_recovered_exactly": recovered,
                    "max_coeff_err": max_err, "eval_impl": a.eval_impl,
                    "parallelism": (f"delay rows sharded over {a.gpus} GPU(s), U exchanged by "
-                                   + ("K3 peer stores into symmetric memory (fused all-gather)" if used_symm else "NCCL all-gather")
+                                   + ({"mcast": "K3 multimem.st into the NVLS multicast mapping of the symmetric U buffers (fused all-gather)",
+                                       "p2p": "K3 unicast peer stores into symmetric memory (fused all-gather)"}.get(used_symm)
+                                      or "NCCL all-gather")
                                    + (", bin-sharded peel with one all-gather of finds per round"
                                       if dist.shard_peel(8 * G * B) else ", peel replicated on every rank (no collective)"))
                    if a.gpus > 1 else "single GPU"},

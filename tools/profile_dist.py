@@ -41,6 +41,10 @@ def one(seed, output):
     return round((t1 - t0) * 1e3, 2), round((t2 - t1) * 1e3, 2)
 
 
+probe = dist.symm_acquire(1024, dev)
+if rank == 0:
+    print("symmetric memory:", probe is not None, "multicast_ptr:", hex(probe[3]) if probe else None, flush=True)
+dist.symm_release(probe)
 for s in range(3):
     r = one(s, "device")
     if rank == 0:
