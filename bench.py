@@ -52,8 +52,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the untimed side checks run in subprocesses after the measurement (N = 1 only)")
-    ap.add_argument("--peel-mode", default="auto", choices=["auto", "sharded", "replicated"],
-                    help="multi-GPU peeling: bin-sharded with one all-gather per round, or replicated on every rank")
+    ap.add_argument("--peel-mode", default="auto", choices=["auto", "sharded", "sharded_host", "replicated"],
+                    help="multi-GPU peeling: bin-sharded on-device loop (finds exchanged inside the kernel), bin-sharded with one "
+                         "NCCL all-gather per round, or replicated on every rank")
     return ap.parse_args()
 
 
@@ -401,8 +402,9 @@ def run_ours(a):
                                    + ({"mcast": "K3 multimem.st into the NVLS multicast mapping of the symmetric U buffers (fused all-gather)",
                                        "p2p": "K3 unicast peer stores into symmetric memory (fused all-gather)"}.get(used_symm)
                                       or "NCCL all-gather")
-                                   + (", bin-sharded peel with one all-gather of finds per round"
-                                      if dist.shard_peel(8 * G * B) else ", peel replicated on every rank (no collective)"))
+                                   + {"device": ", bin-sharded on-device peel loop: the round's finds exchanged inside the kernel over NVLink",
+                                      "host": ", bin-sharded peel with one NCCL all-gather of finds per round",
+                                      "": ", peel replicated on every rank (no collective)"}[dist.shard_peel(8 * G * B)])
                    if a.gpus > 1 else "single GPU"},
         "e2e": {"value": 1e3 / e2e_ms_per_step, "unit": "transforms/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "result": "host arrays (locations, values); output='arrays'",

@@ -183,6 +183,27 @@ int qsft_peel_blocks(const qsft_peel_desc* d, const float* const* blocks, int64_
                      const qsft_uniq* uq /* may be NULL */, int64_t* n_finds_out, int64_t* n_uniq_out, int* n_rounds_out,
                      void* stream);
 
+/* The on-device loop sharded over the GPUs of one box (one process per GPU, every rank holds all of U): rank `rank` of
+ * `world` classifies the bins [rank, rank + 1) * ceil(B / world / 128) * 128 of every group; after every round's
+ * classification the kernel pushes the rank's finds into the peers' copies of the find list over NVLink, waits for theirs
+ * and links the round's finds of ALL ranks -- the per-round exchange of (k, rho) lists (qsft.py:209-241 on shards) happens
+ * inside the one persistent kernel, with no host round trip and no NCCL call.  Every rank ends with the complete
+ * distinct-k list (uq).
+ *   ws: this rank's workspace of qsft_peel_sharded_workspace_bytes(...) bytes in SYMMETRIC (peer-mapped) memory, identical
+ *   layout on every rank, `peers[p]` = address of rank p's workspace as mapped into this process (peers[rank] = ws).  The
+ *   first 8 KB (control block) must be zero before the first call; `epoch` must be the same on all ranks and larger at
+ *   every call on the same workspace.  All ranks of the call must have finished the previous call on the workspace (a
+ *   barrier between peels; in the transform path K3's barrier is one).  Returns QSFT_EUNSUPPORTED like qsft_peel_blocks. */
+typedef struct {
+    int rank, world;
+    void* const* peers;     /* [world] */
+    uint32_t epoch;
+} qsft_shard;
+int64_t qsft_peel_sharded_workspace_bytes(const qsft_peel_desc* d, int64_t max_finds);
+int qsft_peel_blocks_sharded(const qsft_peel_desc* d, const float* const* blocks, int64_t ldU, const qsft_shard* shard,
+                             int64_t max_finds /* slots over all ranks */, unsigned long long* counters,
+                             const qsft_uniq* uq, int64_t* n_uniq_out, int* n_rounds_out, void* stream);
+
 /* The reference's public detector entry point for a batch of columns.  Replaces reconstruct.singleton_detection
  * (qsft/reconstruct.py:132-168): channel stage noiseless (:12-31) / nso1 (:100-113) / nso2 (:116-129), then the
  * optional coded source stage (:34-51 + qsft/ReedSolomon.py:26-48).

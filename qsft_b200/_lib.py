@@ -14,13 +14,18 @@ EXPORTS = [
     "qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count",
     "qsft_query_lattice", "qsft_dec_to_qary", "qsft_qary_to_dec", "qsft_eval_synth", "qsft_gwht_batch", "qsft_gwht_batch_bcast", "qsft_gwht_batch_mcast",
     "qsft_eval_lattice_supported", "qsft_eval_synth_lattice", "qsft_eval_synth_lattice_ex",
-    "qsft_peel_classify", "qsft_peel_apply", "qsft_peel_reduce", "qsft_peel", "qsft_peel_blocks", "qsft_closed_form_bins",
+    "qsft_peel_classify", "qsft_peel_apply", "qsft_peel_reduce", "qsft_peel", "qsft_peel_blocks", "qsft_peel_blocks_sharded", "qsft_peel_sharded_workspace_bytes", "qsft_closed_form_bins",
     "qsft_singleton_detect", "qsft_detect_mle", "qsft_k3_ticket_decode", "qsft_add_noise",
 ]
 
 
 class QsftError(RuntimeError):
     pass
+
+
+class Shard(C.Structure):
+    """Mirror of qsft_shard."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("peers", C.POINTER(C.c_void_p)), ("epoch", C.c_uint32)]
 
 
 class PeelDesc(C.Structure):
@@ -92,6 +97,9 @@ def lib():
     L.qsft_peel.argtypes = [pd, vp, vp, vp, vp, vp, vp, i64, vp, pu, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), vp]
     L.qsft_peel_blocks.argtypes = [pd, C.POINTER(vp), i64, vp, vp, vp, vp, vp, i64, vp, pu, C.POINTER(i64), C.POINTER(i64),
                                    C.POINTER(i32), vp]
+    L.qsft_peel_sharded_workspace_bytes.argtypes = [pd, i64]
+    L.qsft_peel_sharded_workspace_bytes.restype = i64
+    L.qsft_peel_blocks_sharded.argtypes = [pd, C.POINTER(vp), i64, C.POINTER(Shard), i64, vp, pu, C.POINTER(i64), C.POINTER(i32), vp]
     L.qsft_closed_form_bins.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp, i64, vp, vp]
     L.qsft_singleton_detect.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     L.qsft_detect_mle.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
@@ -99,7 +107,8 @@ def lib():
     L.qsft_add_noise.argtypes = [vp, i64, C.c_float, C.c_uint64, C.c_uint64, vp]
     for name in EXPORTS:
         fn = getattr(L, name)  # raises AttributeError if a declared symbol is missing
-        if name not in ("qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count"):
+        if name not in ("qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count",
+                        "qsft_peel_sharded_workspace_bytes"):
             fn.restype = i32
     _lib = L
     return L

@@ -605,6 +605,34 @@ extern "C" int qsft_peel_blocks(const qsft_peel_desc* h, const float* const* blo
     return rc;
 }
 
+extern "C" int64_t qsft_peel_sharded_workspace_bytes(const qsft_peel_desc* h, int64_t max_finds) {
+    PeelDev d;
+    if (make_dev(h, &d) != QSFT_OK || max_finds <= 0) return -1;
+    return qsft_peel_loop_workspace_bytes(d, max_finds);
+}
+
+extern "C" int qsft_peel_blocks_sharded(const qsft_peel_desc* h, const float* const* blocks, int64_t ldU, const qsft_shard* shard,
+                                        int64_t max_finds, unsigned long long* counters, const qsft_uniq* uq, int64_t* n_uniq_out,
+                                        int* n_rounds_out, void* stream) {
+    PeelDev d;
+    if (int rc = make_dev(h, &d)) return rc;
+    QSFT_CHECK_ARG(blocks && shard && shard->peers && counters && uq && n_uniq_out && n_rounds_out, "null pointer");
+    QSFT_CHECK_ARG(shard->world >= 2 && shard->world <= 8 && shard->rank >= 0 && shard->rank < shard->world, "bad rank / world");
+    QSFT_CHECK_ARG(ldU >= d.B && max_finds >= shard->world, "bad ldU / max_finds");
+    if (d.C * d.R > 16) return QSFT_EUNSUPPORTED;
+    for (int i = 0; i < d.C * d.R; ++i) QSFT_CHECK_ARG(blocks[i] != nullptr, "null block pointer");
+    for (int p = 0; p < shard->world; ++p) QSFT_CHECK_ARG(shard->peers[p] != nullptr, "null workspace pointer");
+    QSFT_CHECK_ARG(uq->seen0 && uq->uniq_k && uq->uniq_sum && uq->uniq_cnt && uq->uniq_key && uq->uniq_next && uq->max_uniq > 0,
+                   "incomplete qsft_uniq");
+    UniqOut uo{uq->seen0, uq->uniq_k, uq->uniq_sum, uq->uniq_cnt, (long long*)uq->uniq_key, uq->uniq_next, uq->max_uniq};
+    KlShardHost sh{shard->rank, shard->world, shard->peers, shard->epoch};
+    int64_t nf = 0, nu = 0;
+    const int rc = qsft_peel_loop(d, blocks, ldU, nullptr, nullptr, nullptr, nullptr, nullptr, max_finds, counters, &uo, &nf, &nu,
+                                  n_rounds_out, (cudaStream_t)stream, &sh);
+    if (rc == QSFT_OK) *n_uniq_out = nu;
+    return rc;
+}
+
 extern "C" int qsft_singleton_detect(const float* cols, int64_t N, int q, int n, int P, int P_src, int channel, int source,
                                      int rs_t, int rs_s, const int32_t* rs_exp, const int32_t* rs_log, int8_t* k_out,
                                      int ld_out, void* stream) {

@@ -12,9 +12,30 @@ int qsft_kl_launch_nw32(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps
 // Whole peel loop on the device.  blocks[c * R + r] -> (P_src, ldU) complex64 rows of group c, repeat r (device pointers,
 // host array).  Outputs as qsft_peel.  Returns QSFT_EUNSUPPORTED when the shape does not fit this kernel (C * R > 16,
 // P_src > 256, tile larger than the shared memory).
+// layout of a sharded workspace: control block, then the find list and the find table
+namespace {
+struct KlWsLayout {
+    long long off_ctl, off_cj, off_k, off_rho, off_round, off_id, bytes;
+};
+KlWsLayout kl_ws_layout(const PeelDev& d, long long max_finds) {
+    auto up = [](long long v) { return (v + 255) & ~255ll; };
+    KlWsLayout L;
+    L.off_ctl = 0;
+    L.off_cj = up(8192 > (long long)sizeof(KlCtl) ? 8192 : (long long)sizeof(KlCtl));
+    L.off_k = L.off_cj + up(max_finds * 8);
+    L.off_rho = L.off_k + up(max_finds * d.ld);
+    L.off_round = L.off_rho + up(max_finds * 8);
+    L.off_id = L.off_round + up(max_finds * 4);
+    L.bytes = L.off_id + up((long long)d.C * d.B * 4);
+    return L;
+}
+}  // namespace
+
+int64_t qsft_peel_loop_workspace_bytes(const PeelDev& d, int64_t max_finds) { return kl_ws_layout(d, max_finds).bytes; }
+
 int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, int64_t* find_cj, int8_t* find_k, float* find_rho,
                    int32_t* find_round, int32_t* find_id, int64_t max_finds, unsigned long long* counters, const UniqOut* uo,
-                   int64_t* n_finds_out, int64_t* n_uniq_out, int* n_rounds_out, cudaStream_t st) {
+                   int64_t* n_finds_out, int64_t* n_uniq_out, int* n_rounds_out, cudaStream_t st, const KlShardHost* shard) {
     const int nblk = d.C * d.R;
     if (nblk > KL_MAX_BLOCKS || d.P_src > 256 || d.C > KL_MAX_BLOCKS) return QSFT_EUNSUPPORTED;
     static int sms = 0, smem_max = 0;
@@ -61,6 +82,36 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
     a.dstruct = dflag;
     a.head = reinterpret_cast<int32_t*>(ws + head_off);
     a.next = reinterpret_cast<int32_t*>(ws + next_off);
+    a.rank = 0;
+    a.world = 1;
+    a.jb = 0;
+    a.je = d.B;
+    a.seg = max_finds;
+    if (shard != nullptr && shard->world > 1) {
+        if (shard->world > 8 || shard->rank < 0 || shard->rank >= shard->world) {
+            cudaFreeAsync(ws, st);
+            qsft_set_error("bad shard (rank %d of %d; at most 8 ranks)", shard->rank, shard->world);
+            return QSFT_EINVAL;
+        }
+        // the find list and the find table live in this rank's symmetric workspace (same layout on every rank)
+        const KlWsLayout L = kl_ws_layout(d, max_finds);
+        uint8_t* mine = static_cast<uint8_t*>(shard->peers[shard->rank]);
+        find_cj = reinterpret_cast<int64_t*>(mine + L.off_cj);
+        find_k = reinterpret_cast<int8_t*>(mine + L.off_k);
+        find_rho = reinterpret_cast<float*>(mine + L.off_rho);
+        find_round = reinterpret_cast<int32_t*>(mine + L.off_round);
+        find_id = reinterpret_cast<int32_t*>(mine + L.off_id);
+        a.rank = shard->rank;
+        a.world = shard->world;
+        const long long per = ((d.B + shard->world - 1) / shard->world + 127) & ~127ll;     // whole tiles per rank
+        a.jb = per * shard->rank < d.B ? per * shard->rank : d.B;
+        a.je = a.jb + per < d.B ? a.jb + per : d.B;
+        a.seg = max_finds / shard->world;
+        for (int p = 0; p < 8; ++p) a.sh.peer[p] = p < shard->world ? static_cast<uint8_t*>(shard->peers[p]) : nullptr;
+        a.sh.off_cj = L.off_cj; a.sh.off_k = L.off_k; a.sh.off_rho = L.off_rho; a.sh.off_round = L.off_round;
+        a.sh.off_id = L.off_id; a.sh.off_ctl = L.off_ctl;
+        a.sh.epoch = shard->epoch;
+    }
     a.find_cj = (long long*)find_cj;
     a.find_k = find_k;
     a.find_rho = reinterpret_cast<float2*>(find_rho);

@@ -43,6 +43,25 @@ struct KlMaps {
 };
 #endif
 
+// Bin-sharded loop (one process per GPU, every rank holds all of U): each rank classifies the bins [jb, je) of every group
+// and appends its finds to ITS segment of the find list; the list, the (C, B) find table and a few control words live in a
+// symmetric (peer-mapped) workspace of identical layout on every rank.  After a round's classification every rank PUSHES its
+// new slots into the same places of every peer's workspace with plain stores over NVLink, publishes its counters and a flag
+// (release, system scope), waits for the peers' flags, and runs the link phase on the round's finds of ALL ranks -- so the
+// ball lists, the distinct-k list and the stop rule evolve identically everywhere.  One exchange per round, inside the
+// kernel: the all-gather of (k, rho) lists of the reference's round structure (qsft.py:209-241), fused into the peel.
+struct KlShard {
+    uint8_t* peer[8];                        // base of every rank's workspace (own one included)
+    long long off_cj, off_k, off_rho, off_round, off_id, off_ctl;      // byte offsets of the arrays in a workspace
+    unsigned int epoch;                      // flags hold (epoch << 8) | round: no clearing between peels
+};
+// control block of a workspace: [round 0 .. 15][source rank 0 .. 7]
+struct KlCtl {
+    unsigned long long now[16][8];           // slots used in the source rank's segment after the round
+    unsigned long long multi[16][8];         // multitons the source rank saw in the round
+    unsigned int flag[16][8];
+};
+
 struct KlArgs {
     PeelDev d;
     long long ldU;                           // row stride of every block (elements)
@@ -70,6 +89,11 @@ struct KlArgs {
     int guard_can_bind;
     double peeling_max;
     float rel_floor;                         // residual floor relative to the bin energy (fp32 resolution of U)
+    // ---- bin-sharded loop over several GPUs (world > 1; see KlShard below) ----
+    int rank, world;
+    long long jb, je;                        // this rank classifies bins [jb, je) of every group (jb a multiple of 128)
+    long long seg;                           // find slots per rank: rank r owns slots [r * seg, (r + 1) * seg)
+    KlShard sh;
 };
 
 namespace {
@@ -169,6 +193,7 @@ __device__ __forceinline__ void kl_grid_barrier(unsigned int* gbar, unsigned int
 constexpr int KL_CHUNK = 64;                 // at most; KlArgs.chunk = 4 .. 64 by problem size (kl_chunk)
 struct KlSlots {
     long long next, end;                     // this warp's chunk: slots [next, end) are free
+    long long lim;                           // end of this rank's segment (slots beyond it are counted, not stored)
 };
 
 // reserves `cnt` (<= 4, warp-uniform) consecutive slots; all lanes get the first one
@@ -176,12 +201,13 @@ __device__ __forceinline__ long long kl_take(const KlArgs& a, KlSlots& sl, int c
     const int lane = threadIdx.x & 31;
     if (sl.next + cnt > sl.end) {
         for (long long f = sl.next + lane; f < sl.end; f += 32)
-            if (f < a.max_finds) a.find_cj[f] = -1;
+            if (f < sl.lim) a.find_cj[f] = -1;
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)a.chunk);
+        if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)a.chunk);      // cursor inside this rank's segment
         base = __shfl_sync(0xffffffffu, base, 0);
-        sl.next = (long long)base;
+        sl.next = a.seg * a.rank + (long long)base;
         sl.end = sl.next + a.chunk;
+        sl.lim = a.seg * (a.rank + 1);
     }
     const long long f = sl.next;
     sl.next += cnt;
@@ -192,7 +218,7 @@ __device__ __forceinline__ long long kl_take(const KlArgs& a, KlSlots& sl, int c
 __device__ __forceinline__ void kl_close(const KlArgs& a, KlSlots& sl) {
     const int lane = threadIdx.x & 31;
     for (long long f = sl.next + lane; f < sl.end; f += 32)
-        if (f < a.max_finds) a.find_cj[f] = -1;
+        if (f < sl.lim) a.find_cj[f] = -1;
     sl.next = sl.end = 0;
 }
 
@@ -233,7 +259,7 @@ __device__ __forceinline__ void kl_scan(const KlArgs& a, uint8_t* stage, long lo
     const PeelDev& d = a.d;
     const int R = d.R, P_src = d.P_src;
     const int32_t* s_head = reinterpret_cast<const int32_t*>(stage + (size_t)R * a.box);
-    const bool valid0 = t < a.W && j0 + t < d.B, valid1 = t + 64 < a.W && j0 + t + 64 < d.B;
+    const bool valid0 = t < a.W && j0 + t < a.je, valid1 = t + 64 < a.W && j0 + t + 64 < a.je;
     int hd0 = 0, hd1 = 0;
     if (round > 1) {
         if (valid0) hd0 = s_head[t];
@@ -426,7 +452,7 @@ __device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const K
         unsigned long long f = fbase + (unsigned long long)__popc(sb & ((1u << lane) - 1u));
         f = __shfl_sync(0xffffffffu, f, lane & ~(KL_G - 1));
         if (single) {
-            if ((long long)f < a.max_finds) {
+            if ((long long)f < slots.lim) {
                 uint32_t* ko = reinterpret_cast<uint32_t*>(a.find_k + (size_t)f * d.ld);
                 for (int w = gl; w < d.ld / 4; w += KL_G) ko[w] = (w < NW) ? kw[w] : 0u;
                 if (lead) {
@@ -480,12 +506,12 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
     const PeelDev& d = a.d;
     const int W = a.W, R = d.R, P_src = d.P_src;
     const long long B = d.B;
-    const long long tpg = (B + W - 1) >> a.lgW;                    // tiles per group
+    const long long tpg = (a.je - a.jb + W - 1) >> a.lgW;          // tiles per group (of this rank's bin range)
     const long long n_tiles = tpg * d.C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long mine = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     unsigned n_multi = 0;
-    KlSlots slots{0, 0};
+    KlSlots slots{0, 0, 0};
     const bool is_cand = warp >= KL_NS && warp < KL_NS + KL_NC;
     bool structured = false;
     long long wgt[32 / KL_G] = {0, 0, 0, 0};
@@ -511,9 +537,9 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
                     const uint32_t ph = (it / (unsigned)a.nstages) & 1u;
                     tma::mbar_wait(&empty[st], ph ^ 1u);
                     const int c = (int)(tt / tpg);
-                    const long long j0 = (tt - (long long)c * tpg) << a.lgW;
+                    const long long j0 = a.jb + ((tt - (long long)c * tpg) << a.lgW);
                     uint8_t* dst = stages + (size_t)st * a.stage_bytes;
-                    const long long left = B - j0;
+                    const long long left = a.je - j0;
                     const uint32_t head_bytes = round > 1 ? (uint32_t)((left < W ? left : W) * 4) : 0u;
                     tma::mbar_expect_tx(&full[st], (uint32_t)R * box_bytes + head_bytes);
                     for (int r = 0; r < R; ++r)
@@ -529,7 +555,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
                 const int st = (int)(it % (unsigned)a.nstages);
                 const uint32_t ph = (it / (unsigned)a.nstages) & 1u;
                 const int c = (int)(tt / tpg);
-                const long long j0 = (tt - (long long)c * tpg) << a.lgW;
+                const long long j0 = a.jb + ((tt - (long long)c * tpg) << a.lgW);
                 KlTileInfo* info = &infos[st];
                 tma::mbar_wait(&full[st], ph);
                 kl_scan(a, stages + (size_t)st * a.stage_bytes, j0, round, info, t);
@@ -586,7 +612,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
         unsigned int it = tiles_done;
         for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++it) {
             const int c = (int)(tt / tpg);
-            const long long j0 = (tt - (long long)c * tpg) << a.lgW;
+            const long long j0 = a.jb + ((tt - (long long)c * tpg) << a.lgW);
             // coalesced copy into the tile layout (single stage): the previous tile's readers are done first
             __syncthreads();
             {
@@ -595,11 +621,11 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
                 TileCol tc{stages, P_src, a.box, lb, a.lgW - 4};
                 for (int r = 0; r < R; ++r) {
                     const float2* src = blk.p[c * R + r] + jf;
-                    for (int i = prt; i < P_src; i += nparts) tc.ref(r, i) = (jf < B) ? src[(size_t)i * a.ldU] : make_float2(0.f, 0.f);
+                    for (int i = prt; i < P_src; i += nparts) tc.ref(r, i) = (jf < a.je) ? src[(size_t)i * a.ldU] : make_float2(0.f, 0.f);
                 }
                 if (round > 1 && threadIdx.x < W)
                     reinterpret_cast<int32_t*>(stages + (size_t)R * a.box)[threadIdx.x] =
-                        (j0 + threadIdx.x < B) ? __ldcg(a.head + (size_t)c * B + j0 + threadIdx.x) : 0;
+                        (j0 + threadIdx.x < a.je) ? __ldcg(a.head + (size_t)c * B + j0 + threadIdx.x) : 0;
             }
             __syncthreads();
             if (warp < 2) kl_scan(a, stages, j0, round, &infos[0], (int)threadIdx.x);
@@ -618,21 +644,28 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
     if (lane == 0 && n_multi) atomicAdd(&a.multi[round], (unsigned long long)n_multi);
 }
 
-// ---- link phase: one thread per find of the round ---------------------------------------------------------------------
+// ---- link phase: one thread per find slot of the round ---------------------------------------------------------------
+// lo[p] / hi[p]: the round's slots in rank p's segment.  All reads of the find list go through L2 (__ldcg): with several
+// ranks the peers' entries were written over NVLink during this kernel.
+struct KlRound {
+    long long lo[8], hi[8];
+};
+
 template <int NW>
-__device__ __forceinline__ void kl_link(const KlArgs& a, long long f0, long long f1, int round, bool do_link) {
+__device__ __forceinline__ void kl_link(const KlArgs& a, const KlRound& rd, int p, int round, bool do_link) {
     const PeelDev& d = a.d;
     const int nw = d.ld / 4;
     const long long B = d.B;
+    const long long f0 = rd.lo[p], f1 = rd.hi[p];
     for (long long f = f0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; f < f1; f += (long long)gridDim.x * blockDim.x) {
-        const long long cj = a.find_cj[f];
+        const long long cj = __ldcg(a.find_cj + f);
         if (cj < 0) continue;                               // unused slot of a warp's chunk
         const int c = (int)(cj / B);
         uint32_t kw[NW];
         const uint32_t* kin = reinterpret_cast<const uint32_t*>(a.find_k + (size_t)f * d.ld);
 #pragma unroll
-        for (int w = 0; w < NW; ++w) kw[w] = (w < nw) ? kin[w] : 0u;
-        float2 sum = a.find_rho[f];
+        for (int w = 0; w < NW; ++w) kw[w] = (w < nw) ? __ldcg(kin + w) : 0u;
+        float2 sum = __ldcg(a.find_rho + f);
         int cnt = 1;
         bool first = true, last = true;
         long long jl[KL_MAX_BLOCKS];                       // C <= 16 on this path
@@ -643,20 +676,25 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, long long f0, long long
             }
             const long long j2 = hash_bin<NW>(d, c2, kw);
             jl[c2] = j2;
-            const int32_t f2 = a.find_id[(size_t)c2 * B + j2];
-            // find_id is only written for singletons: an entry is a find of THIS round iff it lies in the round's range and
-            // that find really sits in bin (c2, j2)
-            if ((long long)f2 >= f0 && (long long)f2 < f1 && a.find_cj[f2] == (long long)c2 * B + j2) {
+            const long long f2 = (long long)__ldcg(a.find_id + (size_t)c2 * B + j2);
+            // find_id is only written for singletons: an entry is a find of THIS round iff it lies in the round's range of its
+            // segment and that find really sits in bin (c2, j2)
+            bool cur = false;
+            if (f2 >= 0) {
+                const int own = (int)(f2 / a.seg);
+                cur = own < a.world && f2 >= rd.lo[own] && f2 < rd.hi[own] && __ldcg(a.find_cj + f2) == (long long)c2 * B + j2;
+            }
+            if (cur) {
                 const uint32_t* k2 = reinterpret_cast<const uint32_t*>(a.find_k + (size_t)f2 * d.ld);
                 bool same = true;
 #pragma unroll
-                for (int w = 0; w < NW; ++w) same &= ((w < nw) ? k2[w] : 0u) == kw[w];
+                for (int w = 0; w < NW; ++w) same &= ((w < nw) ? __ldcg(k2 + w) : 0u) == kw[w];
                 if (same) {
                     if (c2 < c) {
                         first = false;                      // an earlier group holds the round's first find of this k
                     } else {
                         last = false;                       // ball_values: a later (i, j) wins (qsft.py:215)
-                        const float2 r2 = a.find_rho[f2];
+                        const float2 r2 = __ldcg(a.find_rho + f2);
                         sum.x += r2.x;
                         sum.y += r2.y;
                         ++cnt;
@@ -677,6 +715,35 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, long long f0, long long
         }
     }
 }
+
+#ifndef QSFT_EMU
+// ---- exchange of a round's finds between the ranks (world > 1) -----------------------------------------------------------
+// Every warp copies slots of this rank's segment into the same slots of every peer's workspace (k row, bin, rho, round) and
+// enters valid finds into the peers' (C, B) find tables.
+__device__ __forceinline__ void kl_push(const KlArgs& a, long long s0, long long s1) {
+    const PeelDev& d = a.d;
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5), w0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int kvec = d.ld / 16;                             // uint4 per k row (2 .. 8)
+    for (long long f = s0 + w0; f < s1; f += warps) {
+        const long long cj = a.find_cj[f];
+        uint4 kv = make_uint4(0u, 0u, 0u, 0u);
+        if (lane < kvec) kv = reinterpret_cast<const uint4*>(a.find_k + (size_t)f * d.ld)[lane];
+        const float2 rho = a.find_rho[f];
+        const int32_t rnd = a.find_round[f];
+        for (int p = 0; p < a.world; ++p) {
+            if (p == a.rank) continue;
+            uint8_t* ws = a.sh.peer[p];
+            if (lane < kvec) reinterpret_cast<uint4*>(ws + a.sh.off_k + (size_t)f * d.ld)[lane] = kv;
+            if (lane == 8) reinterpret_cast<long long*>(ws + a.sh.off_cj)[f] = cj;
+            if (lane == 9) reinterpret_cast<float2*>(ws + a.sh.off_rho)[f] = rho;
+            if (lane == 10) reinterpret_cast<int32_t*>(ws + a.sh.off_round)[f] = rnd;
+            if (lane == 11 && cj >= 0) reinterpret_cast<int32_t*>(ws + a.sh.off_id)[cj] = (int32_t)f;
+        }
+    }
+    __threadfence_system();
+}
+#endif
 
 template <int NW, bool TMA>
 __global__ void __launch_bounds__(TMA ? KL_CT + 32 : KL_CT, 1)
@@ -725,10 +792,12 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
 #endif
     __syncthreads();
     unsigned int epoch = 0, tiles_done = 0, mb_head = 0;
-    long long total = 0;
+    KlRound rd;
+    long long used[8];                                      // slots used so far in every rank's segment
+    for (int p = 0; p < 8; ++p) used[p] = 0;
     double num_peeling = 0;
     int round = 0;
-    bool cont = true;
+    bool cont = true, overflow = false;
     while (cont && num_peeling < a.peeling_max && round < a.max_rounds) {
         ++round;
         kl_classify<NW, TMA>(a, blk,
@@ -737,20 +806,58 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
 #endif
                              round, base, bars, tiles_done, mb_head, infos, mbox, s_sym, s_tw);
         kl_grid_barrier(a.gbar, epoch);
-        const long long now = (long long)__ldcg(a.counters + 0);
-        const long long multis = (long long)__ldcg(a.multi + round);
-        if (now > a.max_finds) {                            // find buffer too small: report, stop (uniform over the grid)
+        long long now[8], multis = 0, nf = 0;
+        now[a.rank] = (long long)__ldcg(a.counters + 0);
+        multis = (long long)__ldcg(a.multi + round);
+#ifndef QSFT_EMU
+        if (a.world > 1) {
+            // this rank's new slots (unused ones included: they carry find_cj = -1) -> every peer, then counters + flag
+            const long long segb = a.seg * a.rank;
+            const long long top = now[a.rank] < a.seg ? now[a.rank] : a.seg;
+            kl_push(a, segb + used[a.rank], segb + top);
+            kl_grid_barrier(a.gbar, epoch);
+            const unsigned int tag = (a.sh.epoch << 8) | (unsigned int)round;
+            if (blockIdx.x == 0 && threadIdx.x < a.world) {
+                KlCtl* ctl = reinterpret_cast<KlCtl*>(a.sh.peer[threadIdx.x] + a.sh.off_ctl);
+                ctl->now[round][a.rank] = (unsigned long long)now[a.rank];
+                ctl->multi[round][a.rank] = (unsigned long long)multis;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&ctl->flag[round][a.rank]), "r"(tag) : "memory");
+            }
+            KlCtl* mine = reinterpret_cast<KlCtl*>(a.sh.peer[a.rank] + a.sh.off_ctl);
+            if (threadIdx.x < a.world) {
+                unsigned int seen;
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(&mine->flag[round][threadIdx.x]) : "memory");
+                    if (seen == tag) break;
+                    __nanosleep(100);
+                }
+            }
+            __syncthreads();
+            multis = 0;
+            for (int p = 0; p < a.world; ++p) {
+                now[p] = (long long)__ldcg(&mine->now[round][p]);
+                multis += (long long)__ldcg(&mine->multi[round][p]);
+            }
+        }
+#endif
+        for (int p = 0; p < a.world; ++p) {
+            if (now[p] > a.seg) overflow = true;            // find buffer too small (uniform over the grid and the ranks)
+            rd.lo[p] = a.seg * p + used[p];
+            rd.hi[p] = a.seg * p + (now[p] < a.seg ? now[p] : a.seg);
+            nf += now[p] - used[p];
+        }
+        if (overflow) {
             if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[6] = 1ull;
-            total = a.max_finds;
             break;
         }
-        const long long nf = now - total;
         if (multis == 0 || nf == 0) cont = false;           // qsft.py:204-205
         // the reference also subtracts after its last round, but nothing reads the bins afterwards: skip unless the q^n
         // guard needs the count
         const bool do_link = cont || a.guard_can_bind;
-        if (nf > 0) kl_link<NW>(a, total, now, round, do_link);
-        total = now;
+        if (nf > 0)
+            for (int p = 0; p < a.world; ++p) kl_link<NW>(a, rd, p, round, do_link);
+        for (int p = 0; p < a.world; ++p) used[p] = now[p];
         if (cont || a.guard_can_bind) {
             kl_grid_barrier(a.gbar, epoch);
             if (a.guard_can_bind) num_peeling = (double)__ldcg(a.counters + 2);
@@ -758,7 +865,7 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.counters[5] = (unsigned long long)round;
-        a.counters[7] = (unsigned long long)total;
+        a.counters[7] = (unsigned long long)used[a.rank];
     }
 }
 

@@ -14,14 +14,16 @@ import torch.distributed as td
 
 class DistContext:
     def __init__(self, group=None, symmetric=True, peel_mode="auto", replicate_peel_max_bytes=8 << 30):
-        """peel_mode: "sharded" = bin-sharded peeling loop with one all-gather of the finds per round (peel_sharded);
-        "replicated" = every rank peels its full copy of U with the single-GPU loop (no collective at all; the whole
-        3-round peel of config 5 is 2.7 ms, less than the latency of the per-round exchanges); "auto" = replicated
-        while U is at most `replicate_peel_max_bytes`."""
+        """peel_mode: "sharded" = bin-sharded on-device loop: every rank classifies its bins, the round's finds are exchanged
+        INSIDE the persistent kernel over NVLink (symmetric workspaces; qsft_peel_blocks_sharded); "sharded_host" = the same
+        sharding driven from the host with one NCCL all-gather of the finds per round (peel_sharded below; also the fallback
+        where symmetric memory is not available); "replicated" = every rank peels its full copy of U with the single-GPU
+        loop (no exchange at all); "auto" = sharded when symmetric memory is available, else replicated while U is at most
+        `replicate_peel_max_bytes`, else sharded_host."""
         if not td.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
-        if peel_mode not in ("auto", "sharded", "replicated"):
-            raise ValueError("peel_mode must be 'auto', 'sharded' or 'replicated'")
+        if peel_mode not in ("auto", "sharded", "sharded_host", "replicated"):
+            raise ValueError("peel_mode must be 'auto', 'sharded', 'sharded_host' or 'replicated'")
         self.peel_mode = peel_mode
         self.replicate_peel_max_bytes = int(replicate_peel_max_bytes)
         self.group = group
@@ -34,10 +36,17 @@ class DistContext:
         self._symm_free = {}
 
     def shard_peel(self, u_bytes):
-        """Whether the peeling loop of a transform whose bins take `u_bytes` is sharded over the ranks."""
+        """Placement of the peeling loop for a transform whose bins take `u_bytes`: "device" (bin-sharded on-device loop),
+        "host" (bin-sharded, NCCL exchange per round) or "" (replicated)."""
         if self.world_size == 1 or self.peel_mode == "replicated":
-            return False
-        return self.peel_mode == "sharded" or u_bytes > self.replicate_peel_max_bytes
+            return ""
+        if self.peel_mode == "sharded_host":
+            return "host"
+        if self.symmetric:
+            return "device"
+        if self.peel_mode == "sharded" or u_bytes > self.replicate_peel_max_bytes:
+            return "host"
+        return ""
 
     # -- symmetric buffers ---------------------------------------------------------------------------------
     def symm_acquire(self, nfloats, device):

@@ -440,6 +440,53 @@ class PeelProblem:
         self.n_uniq = nu.value
         return nf.value, nr.value
 
+    # -- the on-device loop sharded over the ranks of a DistContext -----------------------------------------------------
+    _SHARD_WS = {}
+
+    def peel_blocks_sharded(self, blocks, dist):
+        """Bin-sharded on-device loop (qsft_peel_blocks_sharded): every rank classifies its bins, the round's finds travel
+        between the ranks inside the kernel (NVLink stores into the peers' symmetric workspaces).  Needs alloc() for the
+        distinct-k buffers.  Returns n_rounds, or None when the shape / platform does not fit (caller falls back)."""
+        R = self.P // self.P_src
+        if len(blocks) != self.C * R or dist is None or dist.world_size < 2 or dist.world_size > 8:
+            return None
+        ldU = blocks[0].stride(0)
+        for t in blocks:
+            _need_cuda(t)
+            if t.dtype != torch.complex64 or t.shape != (self.P_src, self.B) or t.stride(0) != ldU:
+                return None
+        max_finds = self.max_finds
+        nbytes = int(_lib.lib().qsft_peel_sharded_workspace_bytes(C.byref(self.desc), max_finds))
+        if nbytes <= 0:
+            return None
+        key = (str(self.device), nbytes, id(dist))
+        ws = PeelProblem._SHARD_WS.get(key)
+        if ws is None:
+            item = dist.symm_acquire((nbytes + 3) // 4, self.device)
+            if item is None:
+                return None
+            item[0][:2048].zero_()                          # control block (8 KB)
+            torch.cuda.current_stream(self.device).synchronize()
+            dist.barrier()
+            ws = {"item": item, "epoch": 0}
+            PeelProblem._SHARD_WS.clear()                   # one shape at a time: the workspace is large
+            PeelProblem._SHARD_WS[key] = ws
+        buf, hdl, ptrs, _mc = ws["item"]
+        ws["epoch"] += 1
+        hdl.barrier()                                       # every rank is done with the previous peel on this workspace
+        peers = (C.c_void_p * dist.world_size)(*[C.c_void_p(int(p)) for p in ptrs])
+        shard = _lib.Shard(rank=dist.rank, world=dist.world_size, peers=peers, epoch=ws["epoch"])
+        arr = (C.c_void_p * len(blocks))(*[C.c_void_p(t.data_ptr()) for t in blocks])
+        nu, nr = C.c_int64(0), C.c_int(0)
+        with torch.cuda.device(self.device), _timed("k4_peel", self.C * self.P * self.B):
+            rc = _lib.lib().qsft_peel_blocks_sharded(C.byref(self.desc), arr, ldU, C.byref(shard), max_finds, _ptr(self.counters),
+                                                     C.byref(self.uniq), C.byref(nu), C.byref(nr), _stream())
+        if rc == -3:
+            return None
+        _lib.check(rc)
+        self.n_uniq = nu.value
+        return nr.value
+
     def distinct(self, n_uniq=None):
         """Host copy of the distinct-k list in the reference's first-seen order:
         (k (K, n) int8, mean rho (K,) complex128, count (K,) int32).  The entries are ordered on the device and come

@@ -75,14 +75,21 @@ class QSFT:
         prob = ops.PeelProblem(q, n, b, Ms, D, signal.get_source_parity(), channel, source, cutoff, dev, rs=rs,
                                nso_subtype=self.nso_subtype)
         dist = getattr(signal, "dist", None)
-        shard = dist is not None and dist.world_size > 1
-        if shard and hasattr(dist, "shard_peel"):
-            shard = dist.shard_peel(C * P * B * 8)
-        if shard:
+        shard = dist.shard_peel(C * P * B * 8) if dist is not None and dist.world_size > 1 else ""
+        n_rounds = None
+        if shard == "device":
+            prob.alloc(max_finds=min(15 * C * B, max(4096, 4 * C * B)), max_uniq=max(4096, C * B), reuse=True)
+            blocks = [u if isinstance(u, torch.Tensor) else torch.as_tensor(u, device=dev) for us in Us for u in us]
+            if all(t.is_cuda and t.dtype == torch.complex64 and t.is_contiguous() for t in blocks):
+                n_rounds = prob.peel_blocks_sharded(blocks, dist)
+            n_finds = -1
+            if n_rounds is None:                         # shape / platform does not fit: every rank agrees (same inputs)
+                shard = "host" if dist.peel_mode == "sharded" else ""
+        if shard == "host":
             from .dist import peel_sharded
             n_rounds = peel_sharded(prob, stacked(), dist)[4]
             n_finds = -1
-        else:
+        elif n_rounds is None:
             prob.alloc(max_finds=min(15 * C * B, max(4096, 4 * C * B)), max_uniq=max(4096, C * B), reuse=True)
             # the on-device loop reads the blocks get_MDU returned where they lie (no copy)
             blocks = [u if isinstance(u, torch.Tensor) else torch.as_tensor(u, device=dev) for us in Us for u in us]

@@ -60,6 +60,7 @@ int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, floa
     }
     a.nstages = 1;
     a.chunk = kl_chunk(d, 1);
+    a.rank = 0; a.world = 1; a.jb = 0; a.je = d.B; a.seg = maxf;
     KlBlocks blk{};
     for (int c = 0; c < d.C; ++c)
         for (int r = 0; r < d.R; ++r) blk.p[c * d.R + r] = U + ((size_t)c * d.P + (size_t)r * d.P_src) * d.B;

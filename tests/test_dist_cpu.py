@@ -45,8 +45,10 @@ def _worker(rank, world, port, out):
     ok3 = bin_range(10, 0, 2) == (0, 5) and bin_range(10, 1, 2) == (5, 10) and bin_range(3, 1, 4) == (1, 2) \
         and bin_range(3, 3, 4) == (3, 3)
     # peel placement policy: replicated while U is small, sharded above the threshold or on request
-    ok4 = (not ctx.shard_peel(1 << 30)) and ctx.shard_peel(9 << 30) and DistContext(peel_mode="sharded").shard_peel(8) \
-        and not DistContext(peel_mode="replicated").shard_peel(1 << 40) and not ctx.symmetric
+    # (gloo: no symmetric memory, so "sharded" falls back to the host-driven exchange)
+    ok4 = ctx.shard_peel(1 << 30) == "" and ctx.shard_peel(9 << 30) == "host" and DistContext(peel_mode="sharded").shard_peel(8) == "host" \
+        and DistContext(peel_mode="sharded_host").shard_peel(8) == "host" \
+        and DistContext(peel_mode="replicated").shard_peel(1 << 40) == "" and not ctx.symmetric
     # agreement of host-side randomness: equal arrays pass, rank-dependent ones raise on every rank; rank 0's indices win
     ctx.assert_same("test arrays", np.arange(6).reshape(2, 3), np.ones(4, dtype=np.int8))
     try:

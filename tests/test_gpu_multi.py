@@ -1,6 +1,7 @@
 """Real multi-GPU parity: two NCCL ranks (one process per GPU) run ONE transform with the delay rows sharded over the ranks
 and must return exactly what a single GPU returns -- same keys in the same first-seen order, values to 1e-5 -- for both
-peel placements (bin-sharded with one exchange of finds per round, and replicated).  Skipped on a box with one GPU."""
+peel placements (bin-sharded on-device loop with the finds exchanged inside the kernel, bin-sharded with one NCCL
+all-gather per round, and replicated).  Skipped on a box with one GPU."""
 import os
 import socket
 
@@ -51,7 +52,7 @@ def _worker(rank, world, port, out):
     try:
         for ci, case in enumerate(CASES):
             want_k, want_v = _transform(case, None)                       # this rank alone, same seed
-            for mode in ("replicated", "sharded"):
+            for mode in ("replicated", "sharded", "sharded_host"):
                 k, v = _transform(case, DistContext(peel_mode=mode))
                 same = k.shape == want_k.shape and np.array_equal(k, want_k)
                 err = float(np.max(np.abs(v - want_v))) if same and len(v) else 0.0
