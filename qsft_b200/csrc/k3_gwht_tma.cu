@@ -29,7 +29,7 @@ constexpr int KT_MAX_STAGES = 6;                    // ring depth is a launch pa
 constexpr int KT_TILE = 4096;                       // complex elements per tile
 constexpr int KT_TILE_BYTES = KT_TILE * 8;
 constexpr int KT_CONSUMERS = 256;
-constexpr int KT_THREADS = KT_CONSUMERS + 32;
+constexpr int KT_THREADS = KT_CONSUMERS + 64;         // + producer warp + publisher warp
 __host__ __device__ constexpr size_t kt_smem(int stages) { return 1024 + (size_t)stages * KT_TILE_BYTES + 256; }
 
 struct KtInfo {
@@ -62,25 +62,11 @@ __device__ __forceinline__ void kt_r16(float2 (&v)[16]) {
     for (int h = 0; h < 4; ++h) kt_r4(v[h], v[h + 4], v[h + 8], v[h + 12]);
 }
 
-// A contiguous-pass tile is "published" (its block's counter of finished tiles bumped, release) by every consumer warp once
-// the warp's stores are visible.  The fence would wait for the stores just issued, so the publish is DEFERRED: it runs right
-// before the stores of the warp's next tile (a whole tile of butterflies later the fence returns at once), or as soon as the
-// warp would otherwise block (the next tile may depend on this very publish), or at the end.
-struct KtPending {
-    unsigned int* ctr;                               // nullptr: nothing pending
-    int nofence;                                     // measurement aid only (QSFT_K3_NOFENCE=1): publish without the fence
-    __device__ __forceinline__ void flush() {
-        if (ctr != nullptr) {
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) {
-                if (!nofence) __threadfence();
-                atomicAdd(ctr, 1u);
-            }
-            ctr = nullptr;
-        }
-    }
-};
-
+// A contiguous-pass tile is "published" -- its block's counter of finished tiles bumped after a gpu-scope fence -- so that
+// the strided pass may load it.  The fence waits for the stores just issued (a microsecond): done by the consumer warps it
+// cost them a fifth of their time.  A dedicated PUBLISHER warp does it instead: every consumer warp arrives on the stage's
+// `stored` mbarrier once its stores of the tile are issued (release at CTA scope, no waiting), the publisher waits for the
+// eight arrivals, fences and bumps the counter.
 template <bool PEERS>
 __device__ __forceinline__ void kt_store(float2* dst, float2 v, const float2* xroot, const K3Peers& peers) {
     if (PEERS) k3_store(dst, v, xroot, peers);
@@ -93,7 +79,7 @@ __device__ __forceinline__ void kt_bar_consumers() { asm volatile("bar.sync 1, %
 // elements) x W = 4^P0 contiguous elements, e = t * W + w; otherwise 4096 contiguous elements.
 template <bool STRIDED, int R, int P0, bool PEERS>
 __device__ __forceinline__ void kt_tile(float2* __restrict__ s, float2* __restrict__ gbase, float scale, const float2* xroot,
-                                        const K3Peers& peers, uint64_t* empty_bar, KtPending& pend) {
+                                        const K3Peers& peers, uint64_t* empty_bar, uint64_t* stored_bar) {
     const int tau = threadIdx.x;                     // consumer threads are 0 .. 255
     constexpr int lgW = STRIDED ? 2 * P0 : 0;
     constexpr int W = 1 << lgW;
@@ -125,7 +111,6 @@ __device__ __forceinline__ void kt_tile(float2* __restrict__ s, float2* __restri
             if (last) {
                 __syncwarp();
                 if ((tau & 31) == 0) tma::mbar_arrive(empty_bar);     // this warp no longer reads the stage
-                pend.flush();
                 float2* g = STRIDED ? gbase + (long long)(eb >> lgW) * KT_TILE + (eb & (W - 1)) : gbase + eb;
 #pragma unroll
                 for (int m = 0; m < 16; ++m) kt_store<PEERS>(g + m * gstep, make_float2(v[m].x * scale, v[m].y * scale), xroot, peers);
@@ -152,7 +137,6 @@ __device__ __forceinline__ void kt_tile(float2* __restrict__ s, float2* __restri
             if (last) {
                 __syncwarp();
                 if ((tau & 31) == 0) tma::mbar_arrive(empty_bar);
-                pend.flush();
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -166,6 +150,8 @@ __device__ __forceinline__ void kt_tile(float2* __restrict__ s, float2* __restri
         }
         if (!last) kt_bar_consumers();
     }
+    __syncwarp();
+    if ((tau & 31) == 0) tma::mbar_arrive(stored_bar);                    // this warp's stores of the tile are issued
 }
 
 template <bool PEERS>
@@ -177,7 +163,8 @@ k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant_
     uint8_t* base = kt_raw + ((1024u - (tma::smem_u32(kt_raw) & 1023u)) & 1023u);      // 1024-byte aligned (TMA swizzle atom)
     uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)nstages * KT_TILE_BYTES);
     uint64_t* empty = full + KT_MAX_STAGES;
-    KtInfo* info = reinterpret_cast<KtInfo*>(empty + KT_MAX_STAGES);
+    uint64_t* stored = empty + KT_MAX_STAGES;
+    KtInfo* info = reinterpret_cast<KtInfo*>(stored + KT_MAX_STAGES);
     const int warp = threadIdx.x >> 5;
     const int rows = (int)(B / KT_TILE);                                     // 4096-element runs per block = 4^r2
     const int lgW = 2 * (6 - r2);
@@ -186,13 +173,32 @@ k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int i = 0; i < nstages; ++i) {
             tma::mbar_init(&full[i], 1);
-            tma::mbar_init(&empty[i], KT_CONSUMERS / 32);
+            tma::mbar_init(&empty[i], KT_CONSUMERS / 32 + 1);               // the consumer warps + the publisher
+            tma::mbar_init(&stored[i], KT_CONSUMERS / 32);
         }
         tma::mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == KT_CONSUMERS / 32) {
+    if (warp == KT_CONSUMERS / 32 + 1) {
+        // ---- publisher ------------------------------------------------------------------------------------------
+        if ((threadIdx.x & 31) == 0) {
+            for (unsigned it = 0;; ++it) {
+                const int stage = (int)(it % (unsigned)nstages);
+                const uint32_t ph = (it / (unsigned)nstages) & 1u;
+                tma::mbar_wait(&full[stage], ph);
+                const long long blk = info[stage].blk;
+                const bool contiguous = info[stage].strided == 0;
+                if (blk < 0) break;
+                tma::mbar_arrive(&empty[stage]);                       // the stage's description has been read
+                tma::mbar_wait(&stored[stage], ph);
+                if (contiguous && tiles2 != 0) {
+                    if (!nofence) __threadfence();
+                    atomicAdd(done + blk, (unsigned int)(KT_CONSUMERS / 32));
+                }
+            }
+        }
+    } else if (warp == KT_CONSUMERS / 32) {
         // ---- producer --------------------------------------------------------------------------------------------
         if ((threadIdx.x & 31) == 0) {
             tma::prefetch_map(&tm1);
@@ -243,14 +249,10 @@ k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant_
         }
     } else {
         // ---- consumers -------------------------------------------------------------------------------------------
-        KtPending pend{nullptr, nofence};
         for (unsigned it = 0;; ++it) {
             const int stage = (int)(it % (unsigned)nstages);
             const uint32_t ph = (it / (unsigned)nstages) & 1u;
-            if (!tma::mbar_try_wait(&full[stage], ph)) {
-                pend.flush();                        // about to block: the producer may be waiting for this publish
-                tma::mbar_wait(&full[stage], ph);
-            }
+            tma::mbar_wait(&full[stage], ph);
             const long long blk = info[stage].blk;
             if (blk < 0) break;
             const int t = info[stage].t;
@@ -258,23 +260,20 @@ k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant_
             float2* s = reinterpret_cast<float2*>(base + (size_t)stage * KT_TILE_BYTES);
             float2* xb = x + blk * B;
             if (!strided) {
-                if (tiles2 == 0) {
-                    kt_tile<false, 6, 0, PEERS>(s, xb + (long long)t * KT_TILE, scale1, x, peers, &empty[stage], pend);
-                } else {
-                    kt_tile<false, 6, 0, false>(s, xb + (long long)t * KT_TILE, scale1, x, peers, &empty[stage], pend);
-                    pend.ctr = done + blk;           // publish later: this warp's part of the tile is written
-                }
+                if (tiles2 == 0)
+                    kt_tile<false, 6, 0, PEERS>(s, xb + (long long)t * KT_TILE, scale1, x, peers, &empty[stage], &stored[stage]);
+                else
+                    kt_tile<false, 6, 0, false>(s, xb + (long long)t * KT_TILE, scale1, x, peers, &empty[stage], &stored[stage]);
             } else {
                 float2* gb = xb + ((long long)t << lgW);
                 switch (r2) {
-                    case 4: kt_tile<true, 4, 2, PEERS>(s, gb, scale2, x, peers, &empty[stage], pend); break;
-                    case 3: kt_tile<true, 3, 3, PEERS>(s, gb, scale2, x, peers, &empty[stage], pend); break;
-                    case 2: kt_tile<true, 2, 4, PEERS>(s, gb, scale2, x, peers, &empty[stage], pend); break;
-                    default: kt_tile<true, 1, 5, PEERS>(s, gb, scale2, x, peers, &empty[stage], pend); break;
+                    case 4: kt_tile<true, 4, 2, PEERS>(s, gb, scale2, x, peers, &empty[stage], &stored[stage]); break;
+                    case 3: kt_tile<true, 3, 3, PEERS>(s, gb, scale2, x, peers, &empty[stage], &stored[stage]); break;
+                    case 2: kt_tile<true, 2, 4, PEERS>(s, gb, scale2, x, peers, &empty[stage], &stored[stage]); break;
+                    default: kt_tile<true, 1, 5, PEERS>(s, gb, scale2, x, peers, &empty[stage], &stored[stage]); break;
                 }
             }
         }
-        pend.flush();
     }
 }
 
