@@ -16,10 +16,23 @@ import types
 
 import numpy as np
 
+import os
+
 REFERENCE_ROOT = "/root/reference"
+# the unmodified copy made by oracle/make_ref.py (git-ignored; what exists on the GPU box)
+REF_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
-def install():
+def reference_root():
+    """/root/reference where it exists (this container), else the copy under oracle/_ref, else None."""
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "qsft")):
+        return REFERENCE_ROOT
+    if os.path.isdir(os.path.join(REF_COPY, "qsft")):
+        return REF_COPY
+    return None
+
+
+def install(root=None):
     if not hasattr(np, "complex"):
         np.complex = complex
     if not hasattr(np, "int"):
@@ -43,5 +56,6 @@ def install():
         g = stub("galois", ReedSolomon=object, GF=lambda *a, **k: None)
         g._codes = stub("galois._codes")
         g._codes._reed_solomon = stub("galois._codes._reed_solomon", decode_jit=lambda *a, **k: None)
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = root or reference_root() or REFERENCE_ROOT
+    if root not in sys.path:
+        sys.path.insert(0, root)
