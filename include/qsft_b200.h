@@ -97,6 +97,14 @@ int qsft_gwht_batch_bcast(float* x, int64_t batch, int q, int b, float* const* p
  * GPU once instead of once per peer.  Callers fall back to qsft_gwht_batch_bcast where no multicast mapping exists.       */
 int qsft_gwht_batch_mcast(float* x, int64_t batch, int q, int b, float* mc_x, void* stream);
 
+/* ... and the scatter form for the bin-sharded peel (qsft_peel_blocks_sharded): rank r only reads the bins
+ * [r * per_bins, (r + 1) * per_bins) of every row, so the last pass stores each element to the ONE rank that owns its bin --
+ * rank_x[r] = the address of these rows in rank r's symmetric buffer (rank_x[rank] = x) -- an all-to-all with 1 / world of
+ * the all-gather's NVLink traffic.  After it this rank's buffer holds ITS bins of every rank's rows (other bins of other
+ * ranks' rows are not written).  per_bins must be the peel's: ceil(q^b / world / 128) * 128.                               */
+int qsft_gwht_batch_scatter(float* x, int64_t batch, int q, int b, float* const* rank_x, int world, int rank, int64_t per_bins,
+                            void* stream);
+
 /* Verification helper (host only, no device work): work item of ticket number `ticket` in the single-launch two-pass
  * q = 4 transform (k3_q4_twopass_kernel): block, tile inside its pass, and whether it belongs to the strided (second)
  * pass.  A strided tile of block k waits for all tiles1 contiguous tiles of block k; tests check that those always

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libqsft_b200.so")
 
 EXPORTS = [
     "qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count",
-    "qsft_query_lattice", "qsft_dec_to_qary", "qsft_qary_to_dec", "qsft_eval_synth", "qsft_gwht_batch", "qsft_gwht_batch_bcast", "qsft_gwht_batch_mcast",
+    "qsft_query_lattice", "qsft_dec_to_qary", "qsft_qary_to_dec", "qsft_eval_synth", "qsft_gwht_batch", "qsft_gwht_batch_bcast", "qsft_gwht_batch_mcast", "qsft_gwht_batch_scatter",
     "qsft_eval_lattice_supported", "qsft_eval_synth_lattice", "qsft_eval_synth_lattice_ex",
     "qsft_peel_classify", "qsft_peel_apply", "qsft_peel_reduce", "qsft_peel", "qsft_peel_blocks", "qsft_peel_blocks_sharded", "qsft_peel_sharded_workspace_bytes", "qsft_closed_form_bins",
     "qsft_singleton_detect", "qsft_detect_mle", "qsft_k3_ticket_decode", "qsft_add_noise",
@@ -86,6 +86,7 @@ def lib():
     L.qsft_gwht_batch.argtypes = [vp, i64, i32, i32, vp]
     L.qsft_gwht_batch_bcast.argtypes = [vp, i64, i32, i32, C.POINTER(vp), i32, vp]
     L.qsft_gwht_batch_mcast.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.qsft_gwht_batch_scatter.argtypes = [vp, i64, i32, i32, C.POINTER(vp), i32, i32, i64, vp]
     L.qsft_eval_lattice_supported.argtypes = [i32, i32, i32, i32, i64]
     L.qsft_eval_synth_lattice.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp]
     L.qsft_eval_synth_lattice_ex.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, i32, vp]

@@ -86,5 +86,3 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
                    int32_t* find_round, int32_t* find_id, int64_t max_finds, unsigned long long* counters, const UniqOut* uo,
                    int64_t* n_finds_out, int64_t* n_uniq_out, int* n_rounds_out, cudaStream_t st, const KlShardHost* shard = nullptr);
 int64_t qsft_peel_loop_workspace_bytes(const PeelDev& d, int64_t max_finds);
-// K3, q = 4, 6 <= b <= 10: TMA pipeline (k3_gwht_tma.cu); QSFT_EUNSUPPORTED when the shape is not handled
-int qsft_k3_q4_tma(float* x, int64_t batch, int b, float* const* peer_x, int n_peers, float* mc_x, cudaStream_t st);

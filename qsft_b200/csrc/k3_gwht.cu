@@ -326,6 +326,9 @@ k3_q4_twopass_kernel(float2* __restrict__ x, long long B, int r1, int r2, long l
         K3Peers none;
         none.n = 0;
     none.mc = nullptr;
+    none.per = 0;
+    none.B = 0;
+    none.lgB = none.lgper = -1;
         k3_q4_tile<false>(s, base, t, r1, 0, 1, 0, 1.0f, x, none);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -437,6 +440,12 @@ int launch_pass_q(float2* x, long long B, int q, const PassPlan& p, long long bl
 __global__ void k3_bcast_copy_kernel(const float2* __restrict__ x, long long n, K3Peers peers) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float2 v = x[i];
+        if (peers.per > 0) {
+            const long long jj = peers.lgB >= 0 ? (i & (peers.B - 1)) : i % peers.B;
+            const int own = (int)(peers.lgper >= 0 ? (jj >> peers.lgper) : jj / peers.per);
+            if (peers.p[own] != x) peers.p[own][i] = v;
+            continue;
+        }
         if (peers.mc != nullptr) {
             asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(peers.mc + i), "f"(v.x), "f"(v.y) : "memory");
             continue;
@@ -490,9 +499,7 @@ static int gwht_impl(float* x, int64_t batch, int q, int b, const K3Peers& peers
     if (q == 4 && b >= 6 && b <= 10) {
         const char* impl = getenv("QSFT_K3_IMPL");
         if (!(impl && atoi(impl) == 1)) {
-            float* pp[7];
-            for (int r = 0; r < 7; ++r) pp[r] = r < peers.n ? reinterpret_cast<float*>(peers.p[r]) : nullptr;
-            const int rc = qsft_k3_q4_tma(x, batch, b, pp, peers.n, reinterpret_cast<float*>(peers.mc), (cudaStream_t)stream);
+            const int rc = qsft_k3_q4_tma(x, batch, b, peers, (cudaStream_t)stream);
             if (rc != QSFT_EUNSUPPORTED) return rc;
         }
     }
@@ -545,6 +552,9 @@ static int gwht_impl(float* x, int64_t batch, int q, int b, const K3Peers& peers
     K3Peers none;
     none.n = 0;
     none.mc = nullptr;
+    none.per = 0;
+    none.B = 0;
+    none.lgB = none.lgper = -1;
     bool all_fused = true;
     for (long long blk0 = 0; blk0 < batch; blk0 += chunk) {
         const long long nblk = (batch - blk0 < chunk) ? (batch - blk0) : chunk;
@@ -566,6 +576,9 @@ extern "C" int qsft_gwht_batch(float* x, int64_t batch, int q, int b, void* stre
     K3Peers none;
     none.n = 0;
     none.mc = nullptr;
+    none.per = 0;
+    none.B = 0;
+    none.lgB = none.lgper = -1;
     return gwht_impl(x, batch, q, b, none, stream);
 }
 
@@ -573,8 +586,29 @@ extern "C" int qsft_gwht_batch_mcast(float* x, int64_t batch, int q, int b, floa
     QSFT_CHECK_ARG(mc_x != nullptr && ((uintptr_t)mc_x & 7) == 0, "bad multicast pointer");
     K3Peers peers;
     peers.n = 1;                             // "has peers": selects the kernels' peer-store instantiation
-    for (int r = 0; r < 7; ++r) peers.p[r] = nullptr;
+    for (int r = 0; r < 8; ++r) peers.p[r] = nullptr;
+    peers.per = 0;
+    peers.B = 0;
+    peers.lgB = peers.lgper = -1;
     peers.mc = reinterpret_cast<float2*>(mc_x);
+    return gwht_impl(x, batch, q, b, peers, stream);
+}
+
+extern "C" int qsft_gwht_batch_scatter(float* x, int64_t batch, int q, int b, float* const* rank_x, int world, int rank,
+                                       int64_t per_bins, void* stream) {
+    QSFT_CHECK_ARG(world >= 2 && world <= 8 && rank >= 0 && rank < world && rank_x != nullptr, "bad rank / world");
+    QSFT_CHECK_ARG(per_bins > 0 && per_bins * world >= ipow64(q, b), "per_bins * world must cover q^b");
+    K3Peers peers;
+    peers.n = 1;                             // "has peers": selects the kernels' peer-store instantiation
+    peers.mc = nullptr;
+    peers.B = ipow64(q, b);
+    peers.per = per_bins;
+    auto lg2 = [](long long v) { int l = 0; while ((1ll << l) < v) ++l; return (1ll << l) == v ? l : -1; };
+    peers.lgB = lg2(peers.B);
+    peers.lgper = lg2(per_bins);
+    for (int r = 0; r < 8; ++r) peers.p[r] = r < world ? reinterpret_cast<float2*>(rank_x[r]) : nullptr;
+    for (int r = 0; r < world; ++r) QSFT_CHECK_ARG(rank_x[r] != nullptr, "null buffer pointer");
+    QSFT_CHECK_ARG(rank_x[rank] == x, "rank_x[rank] must be x itself");
     return gwht_impl(x, batch, q, b, peers, stream);
 }
 
@@ -583,6 +617,10 @@ extern "C" int qsft_gwht_batch_bcast(float* x, int64_t batch, int q, int b, floa
     QSFT_CHECK_ARG(n_peers == 0 || peer_x != nullptr, "null peer list");
     K3Peers peers;
     peers.mc = nullptr;
+    peers.per = 0;
+    peers.B = 0;
+    peers.lgB = peers.lgper = -1;
+    peers.p[7] = nullptr;
     peers.n = n_peers;
     for (int r = 0; r < 7; ++r) peers.p[r] = r < n_peers ? reinterpret_cast<float2*>(peer_x[r]) : nullptr;
     for (int r = 0; r < n_peers; ++r) QSFT_CHECK_ARG(peer_x[r] != nullptr, "null peer pointer");

@@ -281,7 +281,8 @@ k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant_
 
 // x (batch, 4^b) complex64 in place, 6 <= b <= 10, batch * 4^b / 4096 < 2^31.  Returns QSFT_EUNSUPPORTED when the shape is
 // outside that range (the caller falls back to the register-staged kernels of k3_gwht.cu).
-int qsft_k3_q4_tma(float* xf, int64_t batch, int b, float* const* peer_x, int n_peers, float* mc_x, cudaStream_t st) {
+int qsft_k3_q4_tma(float* xf, int64_t batch, int b, const K3Peers& peers_in, cudaStream_t st) {
+    const int n_peers = peers_in.n;
     if (b < 6 || b > 10) return QSFT_EUNSUPPORTED;
     const long long B = ipow64(4, b);
     const long long runs = batch * (B / KT_TILE);
@@ -335,10 +336,7 @@ int qsft_k3_q4_tma(float* xf, int64_t batch, int b, float* const* peer_x, int n_
     unsigned int* done = nullptr;
     QSFT_CUDA(qsft_scratch_alloc((void**)&done, (size_t)(batch + 1) * sizeof(unsigned int), st));
     QSFT_CUDA(cudaMemsetAsync(done, 0, (size_t)(batch + 1) * sizeof(unsigned int), st));
-    K3Peers peers;
-    peers.n = n_peers;
-    peers.mc = reinterpret_cast<float2*>(mc_x);
-    for (int r = 0; r < 7; ++r) peers.p[r] = r < n_peers ? reinterpret_cast<float2*>(peer_x[r]) : nullptr;
+    const K3Peers peers = peers_in;
     const float inv = (float)(1.0 / (double)B);
     if (n_peers > 0)
         k3_q4_tma_kernel<true><<<grid, KT_THREADS, smem, st>>>(tm1, tm2, reinterpret_cast<float2*>(xf), B, r1, r2, tiles1, tiles2, done,

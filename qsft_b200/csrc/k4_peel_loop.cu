@@ -132,6 +132,16 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
     if (uo) QSFT_CUDA(cudaMemsetAsync(uo->seen0, 0, (size_t)d.B * sizeof(int32_t), st));
     kl_dstruct_kernel<<<1, 256, 0, st>>>(d, dflag);
     QSFT_LAUNCHED();
+    // QSFT_K4_TIMING=1 (measurement aid): duration of the cooperative kernel alone on stderr, once the call has synchronised
+    static thread_local cudaEvent_t tev[2] = {nullptr, nullptr};
+    const bool timing = getenv("QSFT_K4_TIMING") != nullptr;
+    if (timing) {
+        if (!tev[0]) {
+            QSFT_CUDA(cudaEventCreate(&tev[0]));
+            QSFT_CUDA(cudaEventCreate(&tev[1]));
+        }
+        QSFT_CUDA(cudaEventRecord(tev[0], st));
+    }
     int rc;
     const int nw = d.ld / 4;
     if (nw <= 8) rc = qsft_kl_launch_nw8(a, blk, hm, use_tma, smem, sms, st);
@@ -145,7 +155,13 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
     if (!host) QSFT_CUDA(cudaMallocHost(&host, 8 * sizeof(unsigned long long)));
     QSFT_CUDA(cudaMemcpyAsync(host, counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     QSFT_CUDA(cudaFreeAsync(ws, st));
+    if (timing) QSFT_CUDA(cudaEventRecord(tev[1], st));
     QSFT_CUDA(cudaStreamSynchronize(st));                   // the only synchronisation of the peel: result sizes
+    if (timing) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, tev[0], tev[1]);
+        fprintf(stderr, "[qsft_peel_loop] rank %d/%d kernel %.3f ms, rounds %llu, slots %llu\n", a.rank, a.world, ms, host[5], host[7]);
+    }
     if (host[6]) {
         qsft_set_error("find buffer too small: %llu finds > max_finds=%lld", host[0], (long long)max_finds);
         return QSFT_EINVAL;

@@ -109,6 +109,12 @@ class SubsampledSignal(Signal):
         self._symm = None
         if world > 1 and len(self.all_bs) == 1 and self.all_bs[0] == self.b:
             self._symm = self.dist.symm_acquire(2 * rows_alloc * B, dev)
+        # With the bin-sharded on-device peel (DistContext.shard_peel == "device") a rank only ever reads ITS bins of every
+        # row: K3 then scatters its output (all-to-all) instead of replicating it (all-gather), and Us hold this rank's bins
+        # only (`Us_complete` False).  Shapes the on-device loop does not take keep the gather.
+        self._U_scattered = bool(self._symm is not None and self.dist.shard_peel(8 * G * B) == "device"
+                                 and C * R <= 16 and P_src <= 256 and self.q == 4 and 6 <= self.b <= 10)
+        self.Us_complete = not self._U_scattered
         if self._symm is not None:
             ubuf = torch.view_as_complex(self._symm[0].view(rows_alloc, B, 2))
             self._symm[1].barrier()             # every rank is done with the previous contents of the (reused) buffer
@@ -159,7 +165,10 @@ class SubsampledSignal(Signal):
                             target.copy_(samples)
                         if self._symm is not None:
                             row_off = (g0 + p0) * B * 8          # bytes from the start of the symmetric buffer
-                            if self._symm[3]:                    # NVLS multicast mapping: one store reaches every rank
+                            if self._U_scattered:                # bin-sharded peel: every element to the rank owning its bin
+                                ops.gwht_batch_scatter_(target, self.q, bb, [ptr + row_off for ptr in self._symm[2]],
+                                                        self.dist.rank)
+                            elif self._symm[3]:                  # NVLS multicast mapping: one store reaches every rank
                                 ops.gwht_batch_mcast_(target, self.q, bb, self._symm[3] + row_off)
                             else:
                                 peers = [ptr + row_off for r, ptr in enumerate(self._symm[2]) if r != self.dist.rank]

@@ -251,6 +251,26 @@ def gwht_batch_mcast_(x, q, b, mc_ptr):
     return x
 
 
+def bins_per_rank(B, world):
+    """Bins of a group every rank classifies in the bin-sharded peel: whole 128-bin tiles (the library's rule)."""
+    return ((B + world - 1) // world + 127) // 128 * 128
+
+
+def gwht_batch_scatter_(x, q, b, rank_ptrs, rank):
+    """K3 whose last pass stores every element to the ONE rank that owns its bin in the bin-sharded peel: in place on x
+    (rows, q^b); rank_ptrs[r] = device address of these rows in rank r's symmetric buffer (rank_ptrs[rank] = x)."""
+    _need_cuda(x)
+    if x.dtype != torch.complex64 or x.shape[-1] != q ** b:
+        raise ValueError("x must be complex64 with last dimension q^b")
+    batch = x.numel() // (q ** b)
+    world = len(rank_ptrs)
+    arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in rank_ptrs])
+    with torch.cuda.device(x.device), _timed("k3_gwht", x.numel()):
+        _lib.check(_lib.lib().qsft_gwht_batch_scatter(_ptr(x), batch, q, b, arr, world, int(rank), bins_per_rank(q ** b, world),
+                                                      _stream()))
+    return x
+
+
 def channel_code(channel, nso_subtype="nso1"):
     """reconstruct_method_channel (+ nso_subtype) -> the C ABI's channel code (qsft_peel_desc.channel)."""
     if channel == "identity":

@@ -84,6 +84,9 @@ class QSFT:
                 n_rounds = prob.peel_blocks_sharded(blocks, dist)
             n_finds = -1
             if n_rounds is None:                         # shape / platform does not fit: every rank agrees (same inputs)
+                if not getattr(signal, "Us_complete", True):
+                    raise RuntimeError("the bins were scattered for the bin-sharded on-device peel, which does not take this "
+                                       "shape; build the signal with DistContext(peel_mode='replicated' or 'sharded_host')")
                 shard = "host" if dist.peel_mode == "sharded" else ""
         if shard == "host":
             from .dist import peel_sharded

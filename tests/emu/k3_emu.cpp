@@ -74,11 +74,18 @@ extern "C" int emu_gwht(float* xf, long long batch, int q, int b, int lag, float
     }
     K3Peers peers;
     peers.n = peer0 ? 1 : 0;
-    for (int r = 0; r < 7; ++r) peers.p[r] = nullptr;
+    peers.mc = nullptr;
+    peers.per = 0;
+    peers.B = 0;
+    peers.lgB = peers.lgper = -1;
+    for (int r = 0; r < 8; ++r) peers.p[r] = nullptr;
     peers.p[0] = reinterpret_cast<float2*>(peer0);
     K3Peers none;
     none.n = 0;
     none.mc = nullptr;
+    none.per = 0;
+    none.B = 0;
+    none.lgB = none.lgper = -1;
     if (lag >= 0 && q == 4 && passes == 2 && plans[0].T == 4096 && plans[1].T == 4096 && plans[0].r <= 6 && plans[1].r <= 6) {
         std::vector<unsigned int> done((size_t)batch + 1, 0u);
         const int t1 = (int)plans[0].tiles_per_block, t2 = (int)plans[1].tiles_per_block;
