@@ -367,7 +367,8 @@ def run_ours(a):
             sig_ = build_signal(inputs[s_], None)
             res_, sft_ = transform(sig_, output)
             symm_ = getattr(sig_, "_symm", None)
-            last_ = (res_, inputs[s_][0], sft_.last_stats, "mcast" if (symm_ is not None and symm_[3]) else ("p2p" if symm_ is not None else ""))
+            xch_ = "" if symm_ is None else ("scatter" if getattr(sig_, "_U_scattered", False) else ("mcast" if symm_[3] else "p2p"))
+            last_ = (res_, inputs[s_][0], sft_.last_stats, xch_)
         e1.record()
         barrier()
         ms = max(e0.elapsed_time(e1), (time.time() - t_wall0) * 1e3)
@@ -482,7 +483,8 @@ def run_ours(a):
                    "l2": "inputs larger than L2 (per-step working set >= 1 GB)", "support_recovered_exactly": recovered,
                    "max_coeff_err": max_err, "eval_impl": a.eval_impl,
                    "parallelism": (f"delay rows sharded over {a.gpus} GPU(s), U exchanged by "
-                                   + ({"mcast": "K3 multimem.st into the NVLS multicast mapping of the symmetric U buffers (fused all-gather)",
+                                   + ({"scatter": "K3 scatter stores into the peers' symmetric U buffers: every element to the ONE rank that owns its bin (fused all-to-all)",
+                                       "mcast": "K3 multimem.st into the NVLS multicast mapping of the symmetric U buffers (fused all-gather)",
                                        "p2p": "K3 unicast peer stores into symmetric memory (fused all-gather)"}.get(used_symm)
                                       or "NCCL all-gather")
                                    + {"device": ", bin-sharded on-device peel loop: the round's finds exchanged inside the kernel over NVLink",

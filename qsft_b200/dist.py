@@ -34,6 +34,7 @@ class DistContext:
         self.symmetric = bool(symmetric) and td.get_backend(group) == "nccl" and self.world_size <= 8
         self.multicast = os.environ.get("QSFT_NO_MULTICAST") is None       # (env: A/B of multimem.st against unicast stores)
         self._symm_free = {}
+        self._pending_checks = []
 
     def shard_peel(self, u_bytes):
         """Placement of the peeling loop for a transform whose bins take `u_bytes`: "device" (bin-sharded on-device loop),
@@ -147,6 +148,28 @@ class DistContext:
         if not bool((everyone == everyone[0]).all()):
             raise RuntimeError(f"{what} differ between ranks: seed the NumPy RNG identically on every rank (or pass the same "
                                f"Ms= / Ds=), the delay rows of ONE transform are sharded over the ranks")
+
+    def post_check(self, what, *arrays):
+        """assert_same without the wait: the hash all-gather is queued now, the comparison happens in verify()."""
+        import hashlib
+        h = hashlib.blake2b(digest_size=8)
+        for a in arrays:
+            a = np.ascontiguousarray(a)
+            h.update(str(a.shape).encode())
+            h.update(a.tobytes())
+        mine = torch.tensor([int.from_bytes(h.digest(), "little", signed=True)], dtype=torch.int64).to(self._device(), non_blocking=True)
+        everyone = torch.empty(self.world_size, dtype=torch.int64, device=mine.device)
+        td.all_gather_into_tensor(everyone, mine, group=self.group)
+        self._pending_checks.append((what, everyone))
+
+    def verify(self):
+        """Reads the verdicts of all post_check calls (one small device-to-host copy each); raises on a mismatch."""
+        pending, self._pending_checks = self._pending_checks, []
+        for what, everyone in pending:
+            v = everyone.cpu()
+            if not bool((v == v[0]).all()):
+                raise RuntimeError(f"{what} differ between ranks: seed the NumPy RNG identically on every rank (or pass the same "
+                                   f"Ms= / Ds=), the delay rows of ONE transform are sharded over the ranks")
 
     def from_rank0(self, arr):
         """The int64 array `arr` of rank 0, on every rank (same shape everywhere)."""

@@ -82,8 +82,9 @@ class SubsampledSignal(Signal):
         else:
             self.Ms, self.Ds = get_Ms_and_Ds(self.n, self.q, **self.query_args)
         if self.dist is not None and self.dist.world_size > 1:
-            self.dist.assert_same("the subsampling / delay matrices (Ms, Ds)", *[np.asarray(M) for M in self.Ms],
-                                  *[np.asarray(D) for Dc in self.Ds for D in Dc])
+            # compared across the ranks without waiting; a mismatch raises at the next DistContext.verify (end of transform)
+            self.dist.post_check("the subsampling / delay matrices (Ms, Ds)", *[np.asarray(M) for M in self.Ms],
+                                 *[np.asarray(D) for Dc in self.Ds for D in Dc])
 
     def _row_shard(self, total_rows):
         """Contiguous slice of the flattened (c, r, p) delay rows owned by this rank."""
@@ -145,7 +146,7 @@ class SubsampledSignal(Signal):
                     Us_ij, Ts_ij = load_data(transform_file)
                     for bb in self.all_bs:
                         self._Ubuf[bb][g0:g0 + P_src] = torch.from_numpy(np.asarray(Us_ij[bb]).astype(np.complex64)).to(dev)
-                        self.transformTimes[i][j][bb] = Ts_ij[bb]
+                        self._times[i][j][bb] = Ts_ij[bb]
                     continue
                 # with a single b the samples are produced straight into their rows of the U buffer and transformed
                 # in place (no staging copy)
@@ -186,25 +187,43 @@ class SubsampledSignal(Signal):
             else:
                 for bb in self.all_bs:
                     self.dist.all_gather_rows_(self._Ubuf[bb], per)
-        torch.cuda.synchronize(dev)
-        fft_total = 0.0
         for i in range(C):
             for j in range(R):
                 g0 = (i * R + j) * P_src
                 for bb in self.all_bs:
                     self.Us[i][j][bb] = self._Ubuf[bb][g0:g0 + P_src]
-                    self.transformTimes[i][j].setdefault(bb, 0.0)
-        fresh = set()
-        for (i, j, bb, ev0, ev1) in events:
-            dt = ev0.elapsed_time(ev1) * 1e-3
-            self.transformTimes[i][j][bb] += dt
-            fft_total += dt
-            fresh.add((i, j))
+                    self._times[i][j].setdefault(bb, 0.0)
+        # NO host synchronisation here: the transform seconds (CUDA events) are read when somebody asks for them
+        # (`transformTimes`), so that the caller's next launches -- the peel -- are queued while K2 / K3 still run.
+        self._pending_events = events
+        self._t_sample0 = t_sample0
         if cache:
+            fresh = {(i, j) for (i, j, bb, ev0, ev1) in events}
+            times = self.transformTimes                     # synchronises
             for (i, j) in fresh:
                 save_data(({bb: list(self.Us[i][j][bb].cpu().numpy().astype(complex)) for bb in self.all_bs},
-                           dict(self.transformTimes[i][j])), Path(f"{self.foldername}/transforms/U{i}_{j}.pickle"))
-        self.sample_time = time.time() - t_sample0 - fft_total
+                           dict(times[i][j])), Path(f"{self.foldername}/transforms/U{i}_{j}.pickle"))
+
+    @property
+    def transformTimes(self):
+        """Seconds spent in the transform of every block, `transformTimes[i][j][b]` like the reference
+        (input_signal_subsampled.py:148-151).  Measured with CUDA events; reading them waits for the device once."""
+        events = getattr(self, "_pending_events", None)
+        if events:
+            self._pending_events = None
+            torch.cuda.synchronize(self.device)
+            fft_total = 0.0
+            for (i, j, bb, ev0, ev1) in events:
+                dt = ev0.elapsed_time(ev1) * 1e-3
+                self._times[i][j][bb] += dt
+                fft_total += dt
+            self.sample_time = time.time() - self._t_sample0 - fft_total
+        return self._times
+
+    @transformTimes.setter
+    def transformTimes(self, value):
+        self._pending_events = None
+        self._times = value
 
     def __del__(self):
         symm = getattr(self, "_symm", None)
@@ -291,9 +310,10 @@ class SubsampledSignal(Signal):
             subsample_idx = np.random.choice(self.num_subsample, ret_num_subsample, replace=False)
             delay_idx = np.random.choice(self.num_repeat, ret_num_repeat, replace=False)
             if self.dist is not None and self.dist.world_size > 1:
-                # every rank consumed the RNG like the reference; the selection itself is rank 0's on all ranks
-                both = self.dist.from_rank0(np.concatenate([subsample_idx, delay_idx]))
-                subsample_idx, delay_idx = both[:len(subsample_idx)], both[len(subsample_idx):]
+                # every rank consumed the RNG like the reference and must have drawn the same selection: compared across the
+                # ranks without waiting (the verdict is read after the peel, DistContext.verify)
+                self.dist.post_check("the group / repeat selection of get_MDU (host RNG state)", subsample_idx, delay_idx)
+            times = self.transformTimes if trans_times else None
             for i in subsample_idx:
                 Ms_ret.append(self.Ms[i][:, :b])
                 Ds_ret.append([])
@@ -302,7 +322,7 @@ class SubsampledSignal(Signal):
                 for j in delay_idx:
                     Ds_ret[-1].append(self.Ds[i][j])
                     Us_ret[-1].append(self.Us[i][j][b])
-                    Ts_ret[-1].append(self.transformTimes[i][j][b])
+                    Ts_ret[-1].append(times[i][j][b] if trans_times else 0.0)
             if trans_times:
                 return Ms_ret, Ds_ret, Us_ret, Ts_ret
             return Ms_ret, Ds_ret, Us_ret

@@ -38,8 +38,11 @@ class QSFT:
         q, n, b = signal.q, signal.n, self.b
         if not isinstance(signal, SubsampledSignal):
             raise NotImplementedError("QSFT currently only supports signals that inherit from SubsampledSignal")
-        Ms, Ds, Us, Ts = signal.get_MDU(self.num_subsample, self.num_repeat, b, trans_times=True)
-        transform_time = float(np.sum(Ts))
+        # the transform seconds are CUDA-event times: asking for them waits for the device, so only when they are reported
+        want_times = bool(report or timing_verbose)
+        mdu = signal.get_MDU(self.num_subsample, self.num_repeat, b, trans_times=want_times)
+        Ms, Ds, Us = mdu[0], mdu[1], mdu[2]
+        transform_time = float(np.sum(mdu[3])) if want_times else 0.0
         if timing_verbose:
             print(f"Transform Time:{transform_time}", flush=True)
         peeling_start = time.time()
@@ -99,6 +102,8 @@ class QSFT:
             fits = all(t.is_cuda and t.dtype == torch.complex64 and t.is_contiguous() for t in blocks)
             done = prob.peel_blocks(blocks) if fits else None
             n_finds, n_rounds = done if done is not None else prob.peel(stacked())
+        if dist is not None and dist.world_size > 1:
+            dist.verify()                                 # deferred rank-agreement checks (Ms / Ds, selections, noise seed)
         self.last_stats = {"rounds": int(n_rounds), "finds": int(n_finds), "distinct": int(prob.n_uniq),
                            "cutoff": float(cutoff)}
         output = kwargs.get("output", "dict")

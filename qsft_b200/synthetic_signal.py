@@ -115,11 +115,11 @@ class SyntheticSubsampledSignal(SubsampledSignal):
         nu = self.noise_sd / np.sqrt(2 * self.q ** b)
         seed = None
         if self.noise_rng != "numpy" and nu > 0:
-            # device noise (qsft_add_noise, Philox): ONE seed per call from the host RNG; with several ranks rank 0's, so
-            # that every rank adds the same noise to its copy of the bins
+            # device noise (qsft_add_noise, Philox): ONE seed per call from the host RNG; with several ranks it must be the same
+            # everywhere (checked), so that every rank adds the same noise to its copy of the bins
             seed = int(np.random.randint(0, 2 ** 31 - 1))
             if self.dist is not None and self.dist.world_size > 1:
-                seed = int(self.dist.from_rank0(np.array([seed]))[0])
+                self.dist.post_check("the device noise seed (host RNG state)", np.array([seed]))
         offset = 0
         for i in range(len(mdu[2])):
             for j in range(len(mdu[2][i])):

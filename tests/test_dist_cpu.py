@@ -57,6 +57,15 @@ def _worker(rank, world, port, out):
     except RuntimeError as exc:
         ok5 = "differ between ranks" in str(exc)
     ok5 = ok5 and ctx.from_rank0(np.array([3 + rank, 1, 2 * rank])).tolist() == [3, 1, 0]
+    ctx.post_check("equal", np.arange(5))                   # deferred form: queued now, read in verify()
+    ctx.verify()
+    ctx.post_check("unequal", np.arange(5) * (rank + 1))
+    try:
+        ctx.verify()
+        ok5 = False
+    except RuntimeError as exc:
+        ok5 = ok5 and "differ between ranks" in str(exc)
+    ctx.verify()                                            # nothing pending any more
     out[rank] = int(ok1 and ok2 and ok3 and ok4 and ok5)
     td.destroy_process_group()
 

@@ -65,8 +65,9 @@ def _worker(rank, world, port, out):
         qa = {"query_method": "complex", "num_subsample": C, "delays_method_source": "identity", "subsampling_method": "qsft",
               "delays_method_channel": chan, "num_repeat": R, "b": b}
         try:
-            qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=1, a_max=1, noise_sd=0, query_args=dict(qa),
-                                                    dist=DistContext())
+            dc = DistContext()
+            qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=1, a_max=1, noise_sd=0, query_args=dict(qa), dist=dc)
+            dc.verify()                       # the comparison is queued at construction and read here / at the end of transform
             ok, msg = False, "differently seeded ranks were not refused"
         except RuntimeError as exc:
             if "differ between ranks" not in str(exc):
