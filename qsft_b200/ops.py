@@ -74,6 +74,15 @@ def _pinned(tag, shape, dtype):
     return buf[:n].view(shape)
 
 
+def _upload(arr, device):
+    """Small host array -> device without stalling the host: a pageable `.to(device)` is a synchronous copy ordered behind
+    everything already queued on the stream (the host then sleeps through the previous block's GEMM and launches the next
+    kernels late); a pinned staging block + non_blocking copy returns at once (torch's pinned allocator keeps the block
+    until the copy has run)."""
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    return t.pin_memory().to(device, non_blocking=True)
+
+
 def _ptr(t):
     return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
 
@@ -194,7 +203,7 @@ def eval_synth_lattice(M, D, loc, strengths, q, out=None, residual_passes=-1):
     P = D.shape[0]
     S, ld = loc.shape
     dev = loc.device
-    Md, Dd = torch.from_numpy(M).to(dev), torch.from_numpy(D).to(dev)
+    Md, Dd = _upload(M, dev), _upload(D, dev)
     if out is None:
         out = torch.empty((P, q ** b), dtype=torch.complex64, device=dev)
     with torch.cuda.device(dev), _timed("k2_eval_lattice", P * (q ** b) * S):
@@ -350,15 +359,15 @@ class PeelProblem:
             MT[c, :, :n] = np.asarray(M).T
         Dp = np.zeros((self.C, self.P, self.ld), dtype=np.int8)
         Dp[:, :, :n] = Ds
-        self.MT = torch.from_numpy(MT).to(device)
-        self.D = torch.from_numpy(Dp).to(device)
+        self.MT = _upload(MT, device)
+        self.D = _upload(Dp, device)
         self.rs_exp = self.rs_log = None
         rs_t = rs_s = 0
         if source == "coded":
             if rs is None:
                 raise ValueError("coded source decoding needs the ReedSolomon object (source_decoder)")
             e, l = rs.device_tables()
-            self.rs_exp, self.rs_log = torch.from_numpy(e).to(device), torch.from_numpy(l).to(device)
+            self.rs_exp, self.rs_log = _upload(e, device), _upload(l, device)
             rs_t, rs_s = rs.t, rs.s
         chan = channel_code(channel, nso_subtype)
         src = {"identity": 0, "coded": 1}.get(source)
