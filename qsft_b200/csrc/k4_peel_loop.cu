@@ -55,7 +55,8 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
     for (int i = 0; i < nblk; ++i)
         if ((uintptr_t)blocks[i] & 15) use_tma = false;
     const int budget = smem_max - 1024 - 2048;             // alignment slack + the kernel's static shared memory
-    if (!kl_geometry(d, budget, use_tma ? 2 : 1, &a)) return QSFT_EUNSUPPORTED;
+    // QSFT_K4_NO_PRIV=1 (measurement aid / cross-check): candidate work in the stage instead of the warps' private copies
+    if (!kl_geometry(d, budget, use_tma ? 2 : 1, &a, getenv("QSFT_K4_NO_PRIV") == nullptr)) return QSFT_EUNSUPPORTED;
     KlBlocks blk{};
     for (int i = 0; i < nblk; ++i) blk.p[i] = reinterpret_cast<const float2*>(blocks[i]);
     KlMaps hm;
@@ -69,7 +70,7 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
             use_tma = false;                                // a shape the tensor map cannot express: plain copies instead
     }
     if (!use_tma) a.nstages = 1;
-    const size_t smem = (size_t)a.nstages * a.stage_bytes + KL_CTRL_BYTES + 1024;
+    const size_t smem = (size_t)a.nstages * a.stage_bytes + KL_CTRL_BYTES + (size_t)KL_NC * a.priv_bytes + 1024;
     // workspace: ball lists, grid barrier, delay-structure flag
     const size_t head_b = (size_t)d.C * d.B * 4, next_b = (size_t)max_finds * d.C * 4;
     uint8_t* ws = nullptr;

@@ -84,6 +84,7 @@ struct KlArgs {
     int box;                                 // bytes per repeat block of a tile: (W / 16) * P_src * 128 rounded up to 1024
     int stage_bytes;                         // R * box + list heads, rounded up to 1024
     int nstages;
+    int priv_bytes;                          // per candidate warp: private copy of its four bins' columns (0 = work in the stage)
     int chunk;                               // find slots a warp reserves at a time
     int max_rounds;
     int guard_can_bind;
@@ -126,6 +127,16 @@ struct TileCol {
     }
     __device__ __forceinline__ float2 ri(int r, int i) const { return *reinterpret_cast<const float2*>(t + off(r, i)); }
     __device__ __forceinline__ float2& ref(int r, int i) const { return *reinterpret_cast<float2*>(t + off(r, i)); }
+};
+
+// A candidate warp's private copy of the columns of its four work items: [row r * P_src + i][item 0 .. 3] complex64.  The
+// eight lanes of an item walk rows i = gl, gl + 8, ...: a warp access covers 256 contiguous bytes (conflict free), and the
+// address is a shift and an add instead of the swizzle arithmetic of the stage.
+struct PrivCol {
+    float2* p;                               // + item
+    int P_src;
+    __device__ __forceinline__ float2 ri(int r, int i) const { return p[(r * P_src + i) << 2]; }
+    __device__ __forceinline__ float2& ref(int r, int i) const { return p[(r * P_src + i) << 2]; }
 };
 
 __device__ __forceinline__ float kl_group_sum(float v) {
@@ -316,173 +327,197 @@ __device__ __forceinline__ void kl_scan(const KlArgs& a, uint8_t* stage, long lo
 }
 
 // ---- candidate warps (cw = 0 .. KL_NC - 1): this warp's share of the tile's work items, four at a time ------------------
+// kl_cand_body works on the columns of the warp's four items through `col` -- the stage itself (TileCol) or the warp's private
+// copy (PrivCol); `f` = the bin's first listed ball (-1: none).
+template <int NW, class Col>
+__device__ __forceinline__ void kl_cand_body(const KlArgs& a, const Col& col, int c, long long jb, int round, bool act, bool touched,
+                                             int f, float e_b, uint8_t* sym, const float2* s_tw, bool structured,
+                                             const long long (&wgt)[32 / KL_G], unsigned& n_multi, KlSlots& slots) {
+    const PeelDev& d = a.d;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % KL_G;
+    const int R = d.R, P_src = d.P_src;
+    const long long B = d.B;
+    const float thresh = (float)d.thresh;
+    const int nsym = P_src - 1;
+    // bins with peeled balls (qsft.py:223-241 applied to the copy in shared memory), then their energy
+    if (round > 1 && __ballot_sync(0xffffffffu, touched)) {
+        while (__ballot_sync(0xffffffffu, f >= 0)) {
+            // the ball's k, rho and list link are independent loads (L2): all in flight before the first is needed
+            float2 rho = make_float2(0.f, 0.f);
+            int fn = -1;
+            if (f >= 0) {
+                const uint4* src = reinterpret_cast<const uint4*>(a.find_k + (size_t)f * d.ld);
+                for (int w = gl; w < d.ld / 16; w += KL_G) reinterpret_cast<uint4*>(sym)[w] = __ldcg(src + w);
+                rho = __ldcg(a.find_rho + f);
+                fn = __ldcg(a.next + (size_t)f * d.C + c) - 1;
+            }
+            __syncwarp();
+            if (f >= 0) {
+                uint32_t kw[NW];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) kw[w] = (4 * w < d.ld) ? reinterpret_cast<const uint32_t*>(sym)[w] : 0u;
+                const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, sym, kw, structured};
+                for (int r = 0; r < R; ++r) {
+                    const int tb = ph.base(r);
+                    for (int i = gl; i < P_src; i += KL_G) {
+                        const float2 w = s_tw[ph.row(r, i, tb)];
+                        float2& v = col.ref(r, i);
+                        v.x -= rho.x * w.x - rho.y * w.y;
+                        v.y -= rho.x * w.y + rho.y * w.x;
+                    }
+                }
+            }
+            f = fn;
+            __syncwarp();
+        }
+        float e2 = 0.f;
+        if (touched)
+            for (int r = 0; r < R; ++r)
+                for (int i = gl; i < P_src; i += KL_G) {
+                    const float2 v = col.ri(r, i);
+                    e2 = fmaf(v.x, v.x, fmaf(v.y, v.y, e2));
+                }
+        e2 = kl_group_sum(e2);
+        if (touched) {
+            e_b = e2;
+            act = e2 > thresh;                                  // energy test (qsft.py:164)
+        }
+    }
+    uint8_t* kb = sym;
+    if (act) {
+        for (int i = 1 + gl; i <= nsym; i += KL_G) sym[i - 1] = (uint8_t)detect_symbol(d, col, i);
+        for (int i = nsym + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) sym[i] = 0;
+    }
+    __syncwarp();
+    if (d.source == 1) {
+        kb = sym + QSFT_MAX_N;
+        if (act) {
+            for (int i = d.n + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) kb[i] = 0;
+            if (gl == 0) rs_decode(rs_params(d), sym, kb);
+        }
+        __syncwarp();
+    }
+    uint32_t kw[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) kw[w] = reinterpret_cast<const uint32_t*>(kb)[w];
+    const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, kb, kw, structured};
+    // rho = <signature, col> / P (qsft.py:174-175) and the residual ||col - rho sig||^2 (qsft.py:176,183) in one pass:
+    // with z_i = conj(sig_i) col_i and the shift z0 = z of row (0, 0),  rho = z0 + mean(z_i - z0)  and
+    // residual = sum |z_i - z0|^2 - |sum (z_i - z0)|^2 / P.  For a singleton every z_i - z0 is at rounding level, so the
+    // subtraction cancels nothing that matters; for a multiton the residual is large either way.
+    float sx = 0.f, sy = 0.f, s2 = 0.f;
+    float2 z0 = make_float2(0.f, 0.f);
+    if (act) {
+        const int tb0 = ph.base(0);
+        {
+            const float2 w = s_tw[tb0];
+            const float2 v = col.ri(0, 0);
+            z0 = make_float2(w.x * v.x + w.y * v.y, w.x * v.y - w.y * v.x);
+        }
+        for (int r = 0; r < R; ++r) {
+            const int tb = r == 0 ? tb0 : ph.base(r);
+            for (int i = gl; i < P_src; i += KL_G) {
+                const float2 w = s_tw[ph.row(r, i, tb)];
+                const float2 v = col.ri(r, i);
+                const float dx = (w.x * v.x + w.y * v.y) - z0.x;            // conj(sig) * v - z0
+                const float dy = (w.x * v.y - w.y * v.x) - z0.y;
+                sx += dx;
+                sy += dy;
+                s2 = fmaf(dx, dx, fmaf(dy, dy, s2));
+            }
+        }
+    }
+    sx = kl_group_sum(sx);
+    sy = kl_group_sum(sy);
+    s2 = kl_group_sum(s2);
+    const float invP = (float)d.invP;
+    const float rr = z0.x + sx * invP, ri = z0.y + sy * invP;
+    const float res = s2 - (sx * sx + sy * sy) * invP;
+    // bin hash j = dec(M_c^T k mod q) (qsft.py:178-179)
+    long long hsum = 0;
+    if (act) {
+#pragma unroll
+        for (int u = 0; u < 32 / KL_G; ++u) {
+            const int i = gl + u * KL_G;
+            if (i < d.b)
+                hsum += wgt[u] * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + i) * d.ld, d.ld, kw), d.q, d.qmagic);
+        }
+    }
+#pragma unroll
+    for (int o = KL_G / 2; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
+    const float lim = fmaxf(thresh, a.rel_floor * e_b);
+    const bool single = act && (hsum == jb) && !(res > lim);
+    const bool lead = (gl == 0);
+    const unsigned sb = __ballot_sync(0xffffffffu, lead && single);
+    unsigned long long fbase = 0;
+    if (sb) fbase = (unsigned long long)kl_take(a, slots, __popc(sb));
+    unsigned long long fs = fbase + (unsigned long long)__popc(sb & ((1u << lane) - 1u));
+    fs = __shfl_sync(0xffffffffu, fs, lane & ~(KL_G - 1));
+    if (single) {
+        if ((long long)fs < slots.lim) {
+            uint32_t* ko = reinterpret_cast<uint32_t*>(a.find_k + (size_t)fs * d.ld);
+            for (int w = gl; w < d.ld / 4; w += KL_G) ko[w] = (w < NW) ? kw[w] : 0u;
+            if (lead) {
+                a.find_cj[fs] = (long long)c * B + jb;
+                a.find_rho[fs] = make_float2(rr, ri);
+                a.find_round[fs] = round;
+                a.find_id[(size_t)c * B + jb] = (int32_t)fs;
+            }
+        }
+    } else if (act && lead) {
+        ++n_multi;
+    }
+    __syncwarp();
+}
+
+// group g of a tile.  With a private buffer (priv != nullptr) the warp first copies the columns of its four items out of the
+// stage and hands the stage back at once -- the ring slot is then held for the copy, not for the microseconds of
+// latency-bound work per item that follow (with in-stage work the ring, 4 .. 6 tiles deep, stalled behind its slowest tile:
+// ncu showed the candidate warps idle at their mailboxes for a quarter of all samples and the scanners waiting for data).
+// Without one (rows too long for the shared memory left) the work is done in the stage, which is released afterwards.
 template <int NW>
-__device__ __forceinline__ void kl_cand(const KlArgs& a, uint8_t* stage, const KlTileInfo* info, int c, long long j0, int round,
-                                        int g, uint8_t* s_symw, const float2* s_tw, bool structured,
-                                        const long long (&wgt)[32 / KL_G], unsigned& n_multi, KlSlots& slots) {
+__device__ __forceinline__ void kl_cand_any(const KlArgs& a, uint8_t* stage, KlTileInfo* info, int c, long long j0, int round, int g,
+                                            uint8_t* s_symw, float2* priv, const float2* s_tw, bool structured,
+                                            const long long (&wgt)[32 / KL_G], unsigned& n_multi, uint64_t* empty_bar, KlSlots& slots) {
     const PeelDev& d = a.d;
     const int lane = threadIdx.x & 31;
     const int grp = lane / KL_G, gl = lane % KL_G;
     const int R = d.R, P_src = d.P_src;
-    const long long B = d.B;
     const int32_t* s_head = reinterpret_cast<const int32_t*>(stage + (size_t)R * a.box);
-    const float thresh = (float)d.thresh;
-    const int nsym = P_src - 1;
     uint8_t* sym = s_symw + grp * KL_SYM;
     const unsigned mask[4] = {info->mask[0], info->mask[1], info->mask[2], info->mask[3]};
     const int total = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
-    {
-        const int rank = 4 * g + grp;
-        const int my = rank < total ? kl_pick(mask, rank) : -1;
-        bool act = my >= 0;
-        const int lbm = act ? my : 0;
-        const long long jb = j0 + lbm;
-        TileCol tc{stage, P_src, a.box, lbm, a.lgW - 4};
-        float e_b = info->e[lbm];
-        // bins with peeled balls (qsft.py:223-241 applied to the shared-memory copy), then their energy
-        const bool touched = act && round > 1 && ((info->tmask[lbm >> 5] >> (lbm & 31)) & 1u);
-        if (round > 1 && __ballot_sync(0xffffffffu, touched)) {
-            int f = touched ? s_head[lbm] - 1 : -1;
-            while (__ballot_sync(0xffffffffu, f >= 0)) {
-                if (f >= 0) {
-                    const uint4* src = reinterpret_cast<const uint4*>(a.find_k + (size_t)f * d.ld);
-                    for (int w = gl; w < d.ld / 16; w += KL_G) reinterpret_cast<uint4*>(sym)[w] = __ldcg(src + w);
-                }
-                __syncwarp();
-                if (f >= 0) {
-                    uint32_t kw[NW];
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) kw[w] = (4 * w < d.ld) ? reinterpret_cast<const uint32_t*>(sym)[w] : 0u;
-                    const float2 rho = __ldcg(a.find_rho + f);
-                    const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, sym, kw, structured};
-                    for (int r = 0; r < R; ++r) {
-                        const int tb = ph.base(r);
-                        for (int i = gl; i < P_src; i += KL_G) {
-                            const float2 w = s_tw[ph.row(r, i, tb)];
-                            float2& v = tc.ref(r, i);
-                            v.x -= rho.x * w.x - rho.y * w.y;
-                            v.y -= rho.x * w.y + rho.y * w.x;
-                        }
-                    }
-                    f = __ldcg(a.next + (size_t)f * d.C + c) - 1;
-                }
-                __syncwarp();
-            }
-            float e2 = 0.f;
-            if (touched)
-                for (int r = 0; r < R; ++r)
-                    for (int i = gl; i < P_src; i += KL_G) {
-                        const float2 v = tc.ri(r, i);
-                        e2 = fmaf(v.x, v.x, fmaf(v.y, v.y, e2));
-                    }
-            e2 = kl_group_sum(e2);
-            if (touched) {
-                e_b = e2;
-                act = e2 > thresh;                                  // energy test (qsft.py:164)
-            }
-        }
-        uint8_t* kb = sym;
-        if (act) {
-            for (int i = 1 + gl; i <= nsym; i += KL_G) sym[i - 1] = (uint8_t)detect_symbol(d, tc, i);
-            for (int i = nsym + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) sym[i] = 0;
-        }
+    const int rank = 4 * g + grp;
+    const int my = rank < total ? kl_pick(mask, rank) : -1;
+    const bool act = my >= 0;
+    const int lbm = act ? my : 0;
+    const long long jb = j0 + lbm;
+    const TileCol tc{stage, P_src, a.box, lbm, a.lgW - 4};
+    const float e_b = info->e[lbm];
+    const bool touched = act && round > 1 && ((info->tmask[lbm >> 5] >> (lbm & 31)) & 1u);
+    const int f = touched ? s_head[lbm] - 1 : -1;
+    if (priv != nullptr) {
+        const PrivCol pc{priv + grp, P_src};
+        if (act)
+            for (int r = 0; r < R; ++r)
+                for (int i = gl; i < P_src; i += KL_G) pc.ref(r, i) = tc.ri(r, i);
         __syncwarp();
-        if (d.source == 1) {
-            kb = sym + QSFT_MAX_N;
-            if (act) {
-                for (int i = d.n + gl; i < 4 * NW && i < QSFT_MAX_N; i += KL_G) kb[i] = 0;
-                if (gl == 0) rs_decode(rs_params(d), sym, kb);
-            }
-            __syncwarp();
-        }
-        uint32_t kw[NW];
-#pragma unroll
-        for (int w = 0; w < NW; ++w) kw[w] = reinterpret_cast<const uint32_t*>(kb)[w];
-        const KlPhase<NW> ph{d, d.D + (size_t)c * d.P * d.ld, kb, kw, structured};
-        // rho = <signature, col> / P (qsft.py:174-175) and the residual ||col - rho sig||^2 (qsft.py:176,183) in one pass:
-        // with z_i = conj(sig_i) col_i and the shift z0 = z of row (0, 0),  rho = z0 + mean(z_i - z0)  and
-        // residual = sum |z_i - z0|^2 - |sum (z_i - z0)|^2 / P.  For a singleton every z_i - z0 is at rounding level, so the
-        // subtraction cancels nothing that matters; for a multiton the residual is large either way.
-        float sx = 0.f, sy = 0.f, s2 = 0.f;
-        float2 z0 = make_float2(0.f, 0.f);
-        if (act) {
-            const int tb0 = ph.base(0);
-            {
-                const float2 w = s_tw[tb0];
-                const float2 v = tc.ri(0, 0);
-                z0 = make_float2(w.x * v.x + w.y * v.y, w.x * v.y - w.y * v.x);
-            }
-            for (int r = 0; r < R; ++r) {
-                const int tb = r == 0 ? tb0 : ph.base(r);
-                for (int i = gl; i < P_src; i += KL_G) {
-                    const float2 w = s_tw[ph.row(r, i, tb)];
-                    const float2 v = tc.ri(r, i);
-                    const float dx = (w.x * v.x + w.y * v.y) - z0.x;            // conj(sig) * v - z0
-                    const float dy = (w.x * v.y - w.y * v.x) - z0.y;
-                    sx += dx;
-                    sy += dy;
-                    s2 = fmaf(dx, dx, fmaf(dy, dy, s2));
-                }
-            }
-        }
-        sx = kl_group_sum(sx);
-        sy = kl_group_sum(sy);
-        s2 = kl_group_sum(s2);
-        const float invP = (float)d.invP;
-        const float rr = z0.x + sx * invP, ri = z0.y + sy * invP;
-        const float res = s2 - (sx * sx + sy * sy) * invP;
-        // bin hash j = dec(M_c^T k mod q) (qsft.py:178-179)
-        long long hsum = 0;
-        if (act) {
-#pragma unroll
-            for (int u = 0; u < 32 / KL_G; ++u) {
-                const int i = gl + u * KL_G;
-                if (i < d.b)
-                    hsum += wgt[u] * fast_mod(dot_raw<NW>(d.MT + ((size_t)c * d.b + i) * d.ld, d.ld, kw), d.q, d.qmagic);
-            }
-        }
-#pragma unroll
-        for (int o = KL_G / 2; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
-        const float lim = fmaxf(thresh, a.rel_floor * e_b);
-        const bool single = act && (hsum == jb) && !(res > lim);
-        const bool lead = (gl == 0);
-        const unsigned sb = __ballot_sync(0xffffffffu, lead && single);
-        unsigned long long fbase = 0;
-        if (sb) fbase = (unsigned long long)kl_take(a, slots, __popc(sb));
-        unsigned long long f = fbase + (unsigned long long)__popc(sb & ((1u << lane) - 1u));
-        f = __shfl_sync(0xffffffffu, f, lane & ~(KL_G - 1));
-        if (single) {
-            if ((long long)f < slots.lim) {
-                uint32_t* ko = reinterpret_cast<uint32_t*>(a.find_k + (size_t)f * d.ld);
-                for (int w = gl; w < d.ld / 4; w += KL_G) ko[w] = (w < NW) ? kw[w] : 0u;
-                if (lead) {
-                    a.find_cj[f] = (long long)c * B + jb;
-                    a.find_rho[f] = make_float2(rr, ri);
-                    a.find_round[f] = round;
-                    a.find_id[(size_t)c * B + jb] = (int32_t)f;
-                }
-            }
-        } else if (act && lead) {
-            ++n_multi;
-        }
-        __syncwarp();
-    }
-}
-
-// one group of a tile + hand-back of the stage (TMA variant: empty_bar != nullptr)
-template <int NW>
-__device__ __forceinline__ void kl_cand_any(const KlArgs& a, uint8_t* stage, KlTileInfo* info, int c, long long j0, int round, int g,
-                                            uint8_t* s_symw, const float2* s_tw, bool structured, const long long (&wgt)[32 / KL_G],
-                                            unsigned& n_multi, uint64_t* empty_bar, KlSlots& slots) {
-    kl_cand<NW>(a, stage, info, c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, slots);
 #ifndef QSFT_EMU
-    if (empty_bar != nullptr) {
-        // done with the stage; in-place updates (generic proxy) are ordered before the next bulk copy
-        if (round > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0 && atomicSub(&info->left, 1) == 1) tma::mbar_arrive(empty_bar);
-    }
+        if (empty_bar != nullptr && lane == 0 && atomicSub(&info->left, 1) == 1) tma::mbar_arrive(empty_bar);
 #endif
+        kl_cand_body<NW>(a, pc, c, jb, round, act, touched, f, e_b, sym, s_tw, structured, wgt, n_multi, slots);
+    } else {
+        kl_cand_body<NW>(a, tc, c, jb, round, act, touched, f, e_b, sym, s_tw, structured, wgt, n_multi, slots);
+#ifndef QSFT_EMU
+        if (empty_bar != nullptr) {
+            // done with the stage; in-place updates (generic proxy) are ordered before the next bulk copy
+            if (round > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && atomicSub(&info->left, 1) == 1) tma::mbar_arrive(empty_bar);
+        }
+#endif
+    }
 }
 
 // ---- one classification round ---------------------------------------------------------------------------------------
@@ -502,7 +537,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
                                             const CUtensorMap* maps,
 #endif
                                             int round, uint8_t* stages, uint64_t* bars, unsigned int& tiles_done, unsigned int& mb_head,
-                                            KlTileInfo* infos, unsigned int* mbox, uint8_t* s_sym, const float2* s_tw) {
+                                            KlTileInfo* infos, unsigned int* mbox, uint8_t* s_sym, uint8_t* s_priv, const float2* s_tw) {
     const PeelDev& d = a.d;
     const int W = a.W, R = d.R, P_src = d.P_src;
     const long long B = d.B;
@@ -521,6 +556,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
         for (int u = 0; u < 32 / KL_G; ++u) wgt[u] = hash_weight(d, (lane % KL_G) + u * KL_G);
     }
     uint8_t* s_symw = s_sym + (size_t)(is_cand ? warp - KL_NS : 0) * 4 * KL_SYM;
+    float2* s_privw = a.priv_bytes ? reinterpret_cast<float2*>(s_priv + (size_t)(is_cand ? warp - KL_NS : 0) * a.priv_bytes) : nullptr;
 #ifndef QSFT_EMU
     if (TMA) {
         uint64_t* full = bars;
@@ -601,7 +637,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
                 if ((e & 0xffu) == 0xffu) break;
                 const int st = (int)((e >> 8) & 7u), g = (int)(e & 0xffu);
                 KlTileInfo* info = &infos[st];
-                kl_cand_any<NW>(a, stages + (size_t)st * a.stage_bytes, info, info->c, info->j0, round, g, s_symw, s_tw, structured,
+                kl_cand_any<NW>(a, stages + (size_t)st * a.stage_bytes, info, info->c, info->j0, round, g, s_symw, s_privw, s_tw, structured,
                                     wgt, n_multi, &empty[st], slots);
             }
         }
@@ -633,7 +669,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
             if (is_cand) {
                 const int total = __popc(infos[0].mask[0]) + __popc(infos[0].mask[1]) + __popc(infos[0].mask[2]) + __popc(infos[0].mask[3]);
                 for (int g = (int)((warp - KL_NS + 5u * it) % (unsigned)KL_NC); 4 * g < total; g += KL_NC)
-                    kl_cand_any<NW>(a, stages, &infos[0], c, j0, round, g, s_symw, s_tw, structured, wgt, n_multi, nullptr, slots);
+                    kl_cand_any<NW>(a, stages, &infos[0], c, j0, round, g, s_symw, s_privw, s_tw, structured, wgt, n_multi, nullptr, slots);
             }
         }
         tiles_done += (unsigned int)mine;
@@ -777,7 +813,8 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
     KlTileInfo* infos = reinterpret_cast<KlTileInfo*>(ctrl + 256);                // [KL_MAX_STAGES], at most 576 bytes each
     unsigned int* mbox = reinterpret_cast<unsigned int*>(ctrl + 256 + KL_MAX_STAGES * 576);   // mailboxes, tails, s_pub
     uint8_t* s_sym = ctrl + 256 + KL_MAX_STAGES * 576 + KL_NC * KL_MB * 4 + 128;  // [KL_NC][4][KL_SYM]
-    static_assert(sizeof(KlTileInfo) <= 576 && KL_NC * 4 + 4 <= 128, "control block layout");
+    uint8_t* s_priv = ctrl + KL_CTRL_BYTES;                                       // [KL_NC][priv_bytes]
+    static_assert(sizeof(KlTileInfo) <= 576 && KL_NC * 4 + 4 <= 128 && KL_CTRL_BYTES % 128 == 0, "control block layout");
 #ifndef QSFT_EMU
     if (TMA) {
         for (int i = threadIdx.x; i < KL_NC * KL_MB + 32; i += blockDim.x) mbox[i] = 0u;
@@ -804,7 +841,7 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
 #ifndef QSFT_EMU
                              maps.m,
 #endif
-                             round, base, bars, tiles_done, mb_head, infos, mbox, s_sym, s_tw);
+                             round, base, bars, tiles_done, mb_head, infos, mbox, s_sym, s_priv, s_tw);
         kl_grid_barrier(a.gbar, epoch);
         long long now[8], multis = 0, nf = 0;
         now[a.rank] = (long long)__ldcg(a.counters + 0);
@@ -898,20 +935,27 @@ inline int kl_chunk(const PeelDev& d, int grid) {
 }
 
 // tile geometry for a shared-memory budget: the widest tile (<= 128 bins, no wider than the group needs) that leaves at
-// least `min_stages` stages.  Returns false when even 16-bin tiles do not fit.
-inline bool kl_geometry(const PeelDev& d, int budget, int min_stages, KlArgs* a) {
-    for (int W = KL_MAXW; W >= 16; W >>= 1) {
-        if (W > 16 && (long long)(W >> 1) >= d.B) continue;
-        const int box = ((W >> 4) * d.P_src * 128 + 1023) & ~1023;
-        const long long stage = ((long long)d.R * box + W * 4 + 1023) & ~1023ll;
-        const long long n = ((long long)budget - KL_CTRL_BYTES) / stage;
-        if (n >= min_stages) {
-            a->W = W;
-            a->lgW = W == 128 ? 7 : W == 64 ? 6 : W == 32 ? 5 : 4;
-            a->box = box;
-            a->stage_bytes = (int)stage;
-            a->nstages = n > KL_MAX_STAGES ? KL_MAX_STAGES : (int)n;
-            return true;
+// least `min_stages` stages.  The candidate warps get private column buffers (KlArgs.priv_bytes each: four items x all delay
+// rows) when at least max(min_stages, 3) stages fit beside them.  Returns false when even 16-bin tiles do not fit.
+inline bool kl_geometry(const PeelDev& d, int budget, int min_stages, KlArgs* a, bool allow_priv = true) {
+    const long long priv = (((long long)d.R * d.P_src * 4 * 8) + 127) & ~127ll;
+    for (int with_priv = allow_priv ? 1 : 0; with_priv >= 0; --with_priv) {
+        const long long avail = (long long)budget - KL_CTRL_BYTES - (with_priv ? priv * KL_NC : 0);
+        const int need = with_priv && min_stages < 3 ? 3 : min_stages;
+        for (int W = KL_MAXW; W >= 16; W >>= 1) {
+            if (W > 16 && (long long)(W >> 1) >= d.B) continue;
+            const int box = ((W >> 4) * d.P_src * 128 + 1023) & ~1023;
+            const long long stage = ((long long)d.R * box + W * 4 + 1023) & ~1023ll;
+            const long long n = avail / stage;
+            if (n >= (min_stages == 1 ? 1 : need)) {
+                a->W = W;
+                a->lgW = W == 128 ? 7 : W == 64 ? 6 : W == 32 ? 5 : 4;
+                a->box = box;
+                a->stage_bytes = (int)stage;
+                a->nstages = n > KL_MAX_STAGES ? KL_MAX_STAGES : (int)n;
+                a->priv_bytes = with_priv ? (int)priv : 0;
+                return true;
+            }
         }
     }
     return false;

@@ -46,12 +46,12 @@ void classify(const PeelDev& d, const float2* U, long long jb, long long je, lon
 // The persistent loop kernel (k4_peel_loop.cu, plain-copy variant) as ONE block: mirrors the host side of qsft_peel_loop.
 // maxW caps the tile width (128 = the product's choice) so that the narrower tile shapes are exercised too.
 int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, float2* rho, int32_t* frd, int32_t* fid,
-              long long maxf, const UniqOut& uo, unsigned long long* counters, int maxW, bool regs) {
+              long long maxf, const UniqOut& uo, unsigned long long* counters, int maxW, bool in_stage) {
     if (d.C * d.R > KL_MAX_BLOCKS || d.P_src > 256) return -3;
     KlArgs a{};
     a.d = d;
     a.ldU = d.B;
-    if (!kl_geometry(d, 228 * 1024, 1, &a)) return -3;
+    if (!kl_geometry(d, 228 * 1024, 1, &a, !in_stage)) return -3;
     while (a.W > maxW) {                                       // narrower tiles on request
         a.W >>= 1;
         a.lgW -= 1;
@@ -76,7 +76,6 @@ int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, floa
     a.guard_can_bind = a.peeling_max <= 15.0 * (double)d.C * (double)d.B ? 1 : 0;
     a.rel_floor = 1e-10f;
     const int nw = nw_of(d.ld);
-    (void)regs;
     NW_SWITCH(nw, emu::launch(dim3(1), dim3(KL_CT), [&]() { k4_peel_loop_kernel<NW, false>(a, blk); }));
     return 0;
 }
@@ -111,7 +110,7 @@ int emu_peel(int q, int n, int b, int C, int P, int P_src, int channel, int sour
     memset(seen0, 0, (size_t)d.B * sizeof(int32_t));
     const int nw = nw_of(d.ld);
     if (impl >= 2) {            // on-device loop: 2 = product's tile width, bins in shared memory; 3 = 32-bin tiles;
-                                // 4 = product's tile width, candidate bins in registers when the shape allows
+                                // 4 = product's tile width, candidate work in the stage (no private column copies)
         UniqOut uo{seen0, uk, usum, ucnt, ukey, unext, max_uniq};
         if (int rc = peel_loop(d, reinterpret_cast<const float2*>(U), find_cj, find_k, reinterpret_cast<float2*>(find_rho), find_round,
                                find_id, max_finds, uo, counters, impl == 3 ? 32 : 128, impl == 4))
