@@ -106,8 +106,8 @@ constexpr int KL_G = 8;                      // lanes per bin in the group phase
 constexpr int KL_MAXW = 128;                 // bins per tile, at most
 constexpr int KL_MAX_STAGES = 6;
 constexpr int KL_SYM = 2 * QSFT_MAX_N;       // per group: detected symbols + decoded k
-constexpr int KL_MB = 32;                    // mailbox entries per candidate warp (at most 6 stages x 3 groups pending)
-constexpr int KL_CTRL_BYTES = 256 + KL_MAX_STAGES * 576 + KL_NC * KL_MB * 4 + 128 + KL_NC * 4 * KL_SYM;
+constexpr int KL_QN = 256;                   // entries of the CTA's work queue (at most 6 stages x 32 item groups + KL_NC sentinels pending)
+constexpr int KL_CTRL_BYTES = 256 + KL_MAX_STAGES * 576 + KL_QN * 4 + 128 + KL_NC * 4 * KL_SYM;
 
 // ---- tile access -------------------------------------------------------------------------------------------------
 // stage = [repeat r][row i][chunk ch (16 bins)][128 B: 16 bins, 16-byte chunks xor-swizzled with the line index & 7]: every
@@ -121,7 +121,15 @@ struct TileCol {
     int P_src, box;
     int lb;                                  // local bin
     int lgc;                                 // log2(chunks per row) = lgW - 4
+    // With eight or more chunks per row (W = 128) the swizzle term does not depend on the row: line & 7 = (lb >> 4) & 7, and
+    // the offset is r * box + i * (W * 8) + a per-bin constant -- one multiply-add per element instead of eight instructions
+    // (the scan's address arithmetic was 10 % of all instructions of the kernel).
     __device__ __forceinline__ int off(int r, int i) const {
+        if (lgc >= 3) {
+            const int c0 = lb >> 4;
+            const int k = c0 * 128 + (((((lb & 15) >> 1) ^ (c0 & 7)) << 4) | ((lb & 1) << 3));
+            return r * box + (i << (lgc + 7)) + k;
+        }
         const int line = (i << lgc) + (lb >> 4);
         return r * box + line * 128 + (((((lb & 15) >> 1) ^ (line & 7)) << 4) | ((lb & 1) << 3));
     }
@@ -523,11 +531,14 @@ __device__ __forceinline__ void kl_cand_any(const KlArgs& a, uint8_t* stage, KlT
 // ---- one classification round ---------------------------------------------------------------------------------------
 // TMA variant, warp roles: 1 producer warp; 2 scanner teams of 2 warps (alternate tiles); KL_NC candidate warps.
 //   producer -> scanners : the stage's `full` mbarrier (bulk copies landed)
-//   scanners -> candidates: per-warp MAILBOXES in shared memory.  After its scan the team's leader hands the tile's groups of
-//                          four work items round-robin to the candidate warps, in tile order (the two teams take turns
-//                          through `s_pub`), and after the CTA's last tile of the round a sentinel.  A candidate warp only
-//                          ever touches tiles it has work in, so a warp busy with one tile's candidates (microseconds of
-//                          latency-bound work) never holds up the stages of other tiles.
+//   scanners -> candidates: ONE work queue per CTA in shared memory.  After its scan the team's leader appends the tile's groups
+//                          of four work items, in tile order (the two teams take turns through `s_pub`), and after the CTA's
+//                          last tile of the round one sentinel per candidate warp.  A candidate warp draws a ticket (atomic
+//                          on the queue head) and waits for that entry: whichever warp is free takes the next group, so no
+//                          group -- and with it no ring slot -- waits behind a warp that is busy with another tile's items
+//                          (with a mailbox per warp, filled round-robin, ncu still showed the candidate warps idle for 23 %
+//                          of their time while the scanners waited for ring slots).  Entries carry the lap number of the
+//                          ring in their generation field, so a slot is never cleared.
 //   candidates -> producer: the tile's `left` counter; whoever copies the last group out of the stage (or the scanner, when
 //                          the tile has no work) arrives on the stage's `empty` mbarrier.
 // Plain variant: scan and candidate work separated by CTA barriers, groups assigned statically, single stage.
@@ -536,7 +547,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
 #ifndef QSFT_EMU
                                             const CUtensorMap* maps,
 #endif
-                                            int round, uint8_t* stages, uint64_t* bars, unsigned int& tiles_done, unsigned int& mb_head,
+                                            int round, uint8_t* stages, uint64_t* bars, unsigned int& tiles_done,
                                             KlTileInfo* infos, unsigned int* mbox, uint8_t* s_sym, uint8_t* s_priv, const float2* s_tw) {
     const PeelDev& d = a.d;
     const int W = a.W, R = d.R, P_src = d.P_src;
@@ -561,8 +572,9 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
     if (TMA) {
         uint64_t* full = bars;
         uint64_t* empty = bars + KL_MAX_STAGES;
-        unsigned int* mb_tail = mbox + KL_NC * KL_MB;              // [KL_NC] entries handed to each warp so far
-        volatile unsigned int* s_pub = mbox + KL_NC * KL_MB + KL_NC;   // tiles published so far (CTA-wide sequence number)
+        volatile unsigned int* q_tail = mbox + KL_QN;              // entries appended so far (only the publishing leader writes)
+        unsigned int* q_head = mbox + KL_QN + 1;                   // tickets drawn so far
+        volatile unsigned int* s_pub = mbox + KL_QN + 2;           // tiles published so far (CTA-wide sequence number)
         unsigned int it = tiles_done;
         if (warp == KL_NS + KL_NC) {
             // ---- producer warp --------------------------------------------------------------------------------------
@@ -607,34 +619,30 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
                     info->left = ng;
                     __threadfence_block();
                     if (ng == 0) tma::mbar_arrive(&empty[st]);
-                    unsigned int w = (5u * it) % (unsigned)KL_NC;
-                    for (int g = 0; g < ng; ++g) {
-                        const unsigned int slot = mb_tail[w]++;
-                        *reinterpret_cast<volatile unsigned int*>(&mbox[w * KL_MB + (slot & (KL_MB - 1))]) =
-                            0x80000000u | ((unsigned)st << 8) | (unsigned)g;
-                        w = w + 1 == (unsigned)KL_NC ? 0u : w + 1;
-                    }
+                    unsigned int tail = *q_tail;
+                    for (int g = 0; g < ng; ++g, ++tail)
+                        mbox[tail & (KL_QN - 1)] = 0x80000000u | (((tail / KL_QN) & 0x7fu) << 16) | ((unsigned)st << 8) | (unsigned)g;
                     if (tt + gridDim.x >= n_tiles)                   // the CTA's last tile of the round: everybody goes home
-                        for (int cw = 0; cw < KL_NC; ++cw) {
-                            const unsigned int slot = mb_tail[cw]++;
-                            *reinterpret_cast<volatile unsigned int*>(&mbox[cw * KL_MB + (slot & (KL_MB - 1))]) = 0x800000ffu;
-                        }
+                        for (int cw = 0; cw < KL_NC; ++cw, ++tail)
+                            mbox[tail & (KL_QN - 1)] = 0x80000000u | (((tail / KL_QN) & 0x7fu) << 16) | 0xffffu;
+                    *q_tail = tail;
                     __threadfence_block();
                     *s_pub = it + 1;
                 }
             }
         } else if (mine > 0) {
             // ---- candidate warps ------------------------------------------------------------------------------------
-            const int cw = warp - KL_NS;
             for (;;) {
-                volatile unsigned int* slot = &mbox[cw * KL_MB + (mb_head & (KL_MB - 1))];
+                unsigned int ticket = 0;
+                if (lane == 0) ticket = atomicAdd(q_head, 1u);
+                ticket = __shfl_sync(0xffffffffu, ticket, 0);
+                volatile unsigned int* slot = &mbox[ticket & (KL_QN - 1)];
+                const unsigned int want = 0x8000u | ((ticket / KL_QN) & 0x7fu);
                 unsigned int e;
-                while ((e = *slot) == 0u) __nanosleep(64);
+                while (((e = *slot) >> 16) != want) __nanosleep(32);
                 __syncwarp();
-                if (lane == 0) *slot = 0u;
-                ++mb_head;
                 __threadfence_block();
-                if ((e & 0xffu) == 0xffu) break;
+                if ((e & 0xffffu) == 0xffffu) break;
                 const int st = (int)((e >> 8) & 7u), g = (int)(e & 0xffu);
                 KlTileInfo* info = &infos[st];
                 kl_cand_any<NW>(a, stages + (size_t)st * a.stage_bytes, info, info->c, info->j0, round, g, s_symw, s_privw, s_tw, structured,
@@ -811,13 +819,13 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
     uint8_t* ctrl = base + (size_t)a.nstages * a.stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);                           // full[6], empty[6]
     KlTileInfo* infos = reinterpret_cast<KlTileInfo*>(ctrl + 256);                // [KL_MAX_STAGES], at most 576 bytes each
-    unsigned int* mbox = reinterpret_cast<unsigned int*>(ctrl + 256 + KL_MAX_STAGES * 576);   // mailboxes, tails, s_pub
-    uint8_t* s_sym = ctrl + 256 + KL_MAX_STAGES * 576 + KL_NC * KL_MB * 4 + 128;  // [KL_NC][4][KL_SYM]
+    unsigned int* mbox = reinterpret_cast<unsigned int*>(ctrl + 256 + KL_MAX_STAGES * 576);   // work queue, its tail / head, s_pub
+    uint8_t* s_sym = ctrl + 256 + KL_MAX_STAGES * 576 + KL_QN * 4 + 128;          // [KL_NC][4][KL_SYM]
     uint8_t* s_priv = ctrl + KL_CTRL_BYTES;                                       // [KL_NC][priv_bytes]
-    static_assert(sizeof(KlTileInfo) <= 576 && KL_NC * 4 + 4 <= 128 && KL_CTRL_BYTES % 128 == 0, "control block layout");
+    static_assert(sizeof(KlTileInfo) <= 576 && KL_CTRL_BYTES % 128 == 0, "control block layout");
 #ifndef QSFT_EMU
     if (TMA) {
-        for (int i = threadIdx.x; i < KL_NC * KL_MB + 32; i += blockDim.x) mbox[i] = 0u;
+        for (int i = threadIdx.x; i < KL_QN + 32; i += blockDim.x) mbox[i] = 0u;
         if (threadIdx.x == 0) {
             for (int i = 0; i < KL_MAX_STAGES; ++i) {
                 tma::mbar_init(&bars[i], 1);
@@ -828,7 +836,7 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
     }
 #endif
     __syncthreads();
-    unsigned int epoch = 0, tiles_done = 0, mb_head = 0;
+    unsigned int epoch = 0, tiles_done = 0;
     KlRound rd;
     long long used[8];                                      // slots used so far in every rank's segment
     for (int p = 0; p < 8; ++p) used[p] = 0;
@@ -841,7 +849,7 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
 #ifndef QSFT_EMU
                              maps.m,
 #endif
-                             round, base, bars, tiles_done, mb_head, infos, mbox, s_sym, s_priv, s_tw);
+                             round, base, bars, tiles_done, infos, mbox, s_sym, s_priv, s_tw);
         kl_grid_barrier(a.gbar, epoch);
         long long now[8], multis = 0, nf = 0;
         now[a.rank] = (long long)__ldcg(a.counters + 0);

@@ -11,6 +11,4 @@ cat $out/${tag}_microbench.json
 tail -3 $out/${tag}_microbench.err
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k4_peel_loop' -s 2 -c 1 -o $out/${tag}_k4loop \
     python tools/microbench.py --only k4 > /dev/null 2>&1
-timeout 300 python bench.py --steps 6 --warmup 3 --no-extras --no-cpu-baseline > $out/${tag}_bench_N1.json 2> $out/${tag}_bench_N1.err
-tail -4 $out/${tag}_bench_N1.err
 ls -la $out | tail -5
