@@ -185,7 +185,11 @@ int qsft_peel(const qsft_peel_desc* d, float* U, int64_t* find_cj, int8_t* find_
  * row lists in a random group / repeat order; the reference vstacks copies of them, qsft.py:115-121).  The bins are only
  * read: no private copy, no vstack.  Runs the persistent on-device loop (one cooperative kernel, every round on the
  * device); returns QSFT_EUNSUPPORTED (-3, nothing done) when the shape does not fit it -- C * R > 16, P_src > 256 or a
- * tile of 16 bins x P rows beyond the shared memory -- and the caller then assembles U and calls qsft_peel.          */
+ * tile of 16 bins x P rows beyond the shared memory -- and the caller then assembles U and calls qsft_peel.
+ *   ASYNCHRONOUS form: n_finds_out == n_rounds_out == NULL -- the loop is queued on `stream` and the call returns at once
+ *   (nothing is read back, so a stream of transforms keeps the GPU busy while the host prepares the next one); the caller
+ *   reads `counters` (device) when it needs the outcome: [4] distinct k, [5] rounds, [6] != 0: find buffer too small,
+ *   [7] find slots used.                                                                                             */
 int qsft_peel_blocks(const qsft_peel_desc* d, const float* const* blocks, int64_t ldU, int64_t* find_cj, int8_t* find_k,
                      float* find_rho, int32_t* find_round, int32_t* find_id, int64_t max_finds, unsigned long long* counters,
                      const qsft_uniq* uq /* may be NULL */, int64_t* n_finds_out, int64_t* n_uniq_out, int* n_rounds_out,
@@ -201,7 +205,8 @@ int qsft_peel_blocks(const qsft_peel_desc* d, const float* const* blocks, int64_
  *   layout on every rank, `peers[p]` = address of rank p's workspace as mapped into this process (peers[rank] = ws).  The
  *   first 8 KB (control block) must be zero before the first call; `epoch` must be the same on all ranks and larger at
  *   every call on the same workspace.  All ranks of the call must have finished the previous call on the workspace (a
- *   barrier between peels; in the transform path K3's barrier is one).  Returns QSFT_EUNSUPPORTED like qsft_peel_blocks. */
+ *   barrier between peels; in the transform path K3's barrier is one).  Returns QSFT_EUNSUPPORTED like qsft_peel_blocks;
+ *   n_uniq_out == n_rounds_out == NULL selects the asynchronous form described there.                                  */
 typedef struct {
     int rank, world;
     void* const* peers;     /* [world] */

@@ -596,7 +596,10 @@ __device__ __forceinline__ void ts_st4(uint32_t taddr, const uint32_t (&r)[4]) {
                  : "memory");
 }
 
-template <bool PX>
+// PROBE (measurement aid, QSFT_LT_PROBE; results are garbage when non-zero): bit 0 = after the first ring lap no limb slabs are
+// loaded (the MMAs re-read what the ring holds), bit 1 = after the first TMEM lap the producers write nothing: which of the
+// two feeds keeps a stage above the 768-cycle issue floor of its eight MMAs.
+template <int PROBE>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2, int nkb, int Mhi, int Nlo,
                     int n_mtiles, const uint32_t* __restrict__ Ttab, const uint32_t* __restrict__ Etab, int Tw,
@@ -649,6 +652,10 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 const int stage = kb % TS_STAGES;
                 const uint32_t ph = (uint32_t)(kb / TS_STAGES) & 1u;
                 lt_mbar_wait(&empty[stage], ph ^ 1u);
+                if ((PROBE & 1) && kb >= TS_STAGES) {
+                    if (rank == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lt_smem_u32(&full[stage])) : "memory");
+                    continue;
+                }
                 if (rank == 0) lt_mbar_expect_tx(&full[stage], 2 * TS_STAGE_BYTES);
                 const uint32_t fl = sp_mapa(lt_smem_u32(&full[stage]), 0);
                 uint8_t* st = base + (size_t)stage * TS_STAGE_BYTES;
@@ -715,13 +722,15 @@ lt_gemm_spts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 }
                 uint32_t av[16], ev[4];
 #pragma unroll
-                for (int wi = 0; wi < 4; ++wi) ts_phase_expand<PX>(tw[wi], ew[wi], odd, &av[4 * wi], ev[wi]);
+                for (int wi = 0; wi < 4; ++wi) ts_phase_expand<false>(tw[wi], ew[wi], odd, &av[4 * wi], ev[wi]);
                 lt_mbar_wait(&tfree[buf], ((uint32_t)(kb / TS_NBUF) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ta = lane_addr + TS_TMEM_A + TS_TMEM_BUF * (uint32_t)buf;
-                ts_st16(ta + 16u * (uint32_t)half, av);
-                ts_st4(ta + 32u + 4u * (uint32_t)half, ev);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                if (!((PROBE & 2) && kb >= TS_NBUF)) {
+                    ts_st16(ta + 16u * (uint32_t)half, av);
+                    ts_st4(ta + 32u + 4u * (uint32_t)half, ev);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 // relaxed: the TMEM writes are ordered by wait::st + fence::before_thread_sync; a releasing arrive would also
@@ -916,7 +925,10 @@ extern "C" int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, cons
             static bool attr = false;
             if (!attr) {
                 if (cudaFuncSetAttribute(lt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
-                    cudaFuncSetAttribute(lt_gemm_spts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess) {
+                    cudaFuncSetAttribute(lt_gemm_spts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess ||
+                    cudaFuncSetAttribute(lt_gemm_spts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess ||
+                    cudaFuncSetAttribute(lt_gemm_spts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess ||
+                    cudaFuncSetAttribute(lt_gemm_spts_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess) {
                     qsft_set_error("cudaFuncSetAttribute failed");
                     rc = QSFT_ECUDA;
                 }
@@ -946,7 +958,11 @@ extern "C" int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, cons
                     cattr[0].val.clusterDim.z = 1;
                     cfg.attrs = cattr;
                     cfg.numAttrs = 1;
-                    cudaLaunchKernelEx(&cfg, lt_gemm_spts_kernel<false>, mb, mb2, (int)(Kp / SP_BK), (int)Mhi, (int)Nlo, (int)n_mt,
+                    int probe = 0;
+                    if (const char* env = getenv("QSFT_LT_PROBE")) probe = atoi(env) & 3;
+                    auto kern = probe == 0 ? lt_gemm_spts_kernel<0> : probe == 1 ? lt_gemm_spts_kernel<1>
+                              : probe == 2 ? lt_gemm_spts_kernel<2> : lt_gemm_spts_kernel<3>;
+                    cudaLaunchKernelEx(&cfg, kern, mb, mb2, (int)(Kp / SP_BK), (int)Mhi, (int)Nlo, (int)n_mt,
                                        (const uint32_t*)Ttab, (const uint32_t*)(Etab + (size_t)p0 * Tw), (int)Tw,
                                        (const float*)(inv_scale + pass), o, pass);
                     g_qsft_launches.fetch_add(1, std::memory_order_relaxed);

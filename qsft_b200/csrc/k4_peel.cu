@@ -587,8 +587,8 @@ extern "C" int qsft_peel_blocks(const qsft_peel_desc* h, const float* const* blo
                                 int* n_rounds_out, void* stream) {
     PeelDev d;
     if (int rc = make_dev(h, &d)) return rc;
-    QSFT_CHECK_ARG(blocks && find_cj && find_k && find_rho && find_round && find_id && counters && n_finds_out && n_rounds_out,
-                   "null pointer");
+    QSFT_CHECK_ARG(blocks && find_cj && find_k && find_rho && find_round && find_id && counters, "null pointer");
+    QSFT_CHECK_ARG((n_finds_out != nullptr) == (n_rounds_out != nullptr), "n_finds_out and n_rounds_out: both or neither (asynchronous)");
     QSFT_CHECK_ARG(ldU >= d.B, "ldU=%lld smaller than q^b=%lld", (long long)ldU, (long long)d.B);
     if (d.C * d.R > 16) return QSFT_EUNSUPPORTED;
     for (int i = 0; i < d.C * d.R; ++i) QSFT_CHECK_ARG(blocks[i] != nullptr, "null block pointer");
@@ -598,10 +598,10 @@ extern "C" int qsft_peel_blocks(const qsft_peel_desc* h, const float* const* blo
                        "incomplete qsft_uniq");
         uo = UniqOut{uq->seen0, uq->uniq_k, uq->uniq_sum, uq->uniq_cnt, (long long*)uq->uniq_key, uq->uniq_next, uq->max_uniq};
     }
-    int64_t nu = 0;
+    int64_t nu = 0, nf_dummy = 0;
     const int rc = qsft_peel_loop(d, blocks, ldU, find_cj, find_k, find_rho, find_round, find_id, max_finds, counters,
-                                  uq ? &uo : nullptr, n_finds_out, &nu, n_rounds_out, (cudaStream_t)stream);
-    if (rc == QSFT_OK && n_uniq_out) *n_uniq_out = nu;
+                                  uq ? &uo : nullptr, n_finds_out ? n_finds_out : &nf_dummy, &nu, n_rounds_out, (cudaStream_t)stream);
+    if (rc == QSFT_OK && n_uniq_out && n_rounds_out) *n_uniq_out = nu;
     return rc;
 }
 
@@ -616,7 +616,8 @@ extern "C" int qsft_peel_blocks_sharded(const qsft_peel_desc* h, const float* co
                                         int* n_rounds_out, void* stream) {
     PeelDev d;
     if (int rc = make_dev(h, &d)) return rc;
-    QSFT_CHECK_ARG(blocks && shard && shard->peers && counters && uq && n_uniq_out && n_rounds_out, "null pointer");
+    QSFT_CHECK_ARG(blocks && shard && shard->peers && counters && uq, "null pointer");
+    QSFT_CHECK_ARG((n_uniq_out != nullptr) == (n_rounds_out != nullptr), "n_uniq_out and n_rounds_out: both or neither (asynchronous)");
     QSFT_CHECK_ARG(shard->world >= 2 && shard->world <= 8 && shard->rank >= 0 && shard->rank < shard->world, "bad rank / world");
     QSFT_CHECK_ARG(ldU >= d.B && max_finds >= shard->world, "bad ldU / max_finds");
     if (d.C * d.R > 16) return QSFT_EUNSUPPORTED;
@@ -629,7 +630,7 @@ extern "C" int qsft_peel_blocks_sharded(const qsft_peel_desc* h, const float* co
     int64_t nf = 0, nu = 0;
     const int rc = qsft_peel_loop(d, blocks, ldU, nullptr, nullptr, nullptr, nullptr, nullptr, max_finds, counters, &uo, &nf, &nu,
                                   n_rounds_out, (cudaStream_t)stream, &sh);
-    if (rc == QSFT_OK) *n_uniq_out = nu;
+    if (rc == QSFT_OK && n_uniq_out) *n_uniq_out = nu;
     return rc;
 }
 

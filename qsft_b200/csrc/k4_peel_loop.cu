@@ -152,6 +152,12 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
         cudaFreeAsync(ws, st);
         return rc;
     }
+    if (n_rounds_out == nullptr) {
+        // asynchronous call: queued, not waited for.  The caller reads `counters` (device) when it needs the outcome:
+        // [4] distinct k, [5] rounds, [6] != 0: find buffer too small, [7] find slots used
+        QSFT_CUDA(cudaFreeAsync(ws, st));
+        return QSFT_OK;
+    }
     static thread_local unsigned long long* host = nullptr;
     if (!host) QSFT_CUDA(cudaMallocHost(&host, 8 * sizeof(unsigned long long)));
     QSFT_CUDA(cudaMemcpyAsync(host, counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

@@ -26,6 +26,8 @@ from .query import get_Ms_and_Ds
 from .utils import index_limbs, limbs_to_ints, load_data, padded_ld, qary_ints, save_data
 
 
+_SHARD_CACHE = {}     # (rows, rows per block, world, cost table) -> shard boundaries (see _balanced_shard)
+
 class SubsampledSignal(Signal):
     device_subsample = False
 
@@ -94,6 +96,51 @@ class SubsampledSignal(Signal):
         lo = min(total_rows, self.dist.rank * per)
         return lo, min(total_rows, lo + per), per
 
+    def _block_cost(self, rows):
+        """Relative cost of sampling `rows` delay rows of ONE (M, D) block on this rank (drives `_balanced_shard`); the
+        default is proportional.  Samplers with a per-block set-up or a wave-quantised kernel override it."""
+        return float(rows)
+
+    def _balanced_shard(self, total_rows, block_rows):
+        """Contiguous row ranges [lo, hi) for every rank that minimise the cost of the most loaded rank (then the total), where
+        a range costs the sum of `_block_cost` over the (M, D) blocks it touches -- a rank whose rows straddle a block boundary
+        pays two set-ups and two kernel tails.  Deterministic: every rank computes the same boundaries.  No range is longer
+        than the uniform share, so the row buffer keeps its size."""
+        world, rank = self.dist.world_size, self.dist.rank
+        per = -(-total_rows // world)
+        nblk = -(-total_rows // block_rows)
+        table = tuple(0.0 if r == 0 else self._block_cost(r) for r in range(min(per, block_rows) + 1))
+        key = (total_rows, block_rows, world, table)
+        bounds = _SHARD_CACHE.get(key)
+        if bounds is None:
+            def cost(lo, hi):
+                c = 0.0
+                for k in range(lo // block_rows, min(nblk, -(-hi // block_rows))):
+                    c += table[max(0, min(hi, (k + 1) * block_rows) - max(lo, k * block_rows))]
+                return c
+
+            inf = (float("inf"), float("inf"))
+            best = [[inf] * (total_rows + 1) for _ in range(world + 1)]
+            arg = [[0] * (total_rows + 1) for _ in range(world + 1)]
+            best[0][0] = (0.0, 0.0)
+            for r in range(1, world + 1):
+                for e in range(total_rows + 1):
+                    for s0 in range(max(0, e - per), e + 1):
+                        prev = best[r - 1][s0]
+                        if prev[0] == float("inf"):
+                            continue
+                        c = cost(s0, e)
+                        v = (max(prev[0], c), prev[1] + c)
+                        if v < best[r][e]:
+                            best[r][e], arg[r][e] = v, s0
+            bounds, e = [total_rows], total_rows
+            for r in range(world, 0, -1):
+                e = arg[r][e]
+                bounds.append(e)
+            bounds.reverse()
+            _SHARD_CACHE[key] = bounds
+        return bounds[rank], bounds[rank + 1]
+
     def _subsample_qsft(self):
         """Sample + transform every (M_i, D_ij) block (input_signal_subsampled.py:107-155)."""
         C, R = len(self.Ms), len(self.Ds[0])
@@ -117,6 +164,9 @@ class SubsampledSignal(Signal):
                                  and C * R <= 16 and P_src <= 256 and self.q == 4 and 6 <= self.b <= 10)
         self.Us_complete = not self._U_scattered
         if self._symm is not None:
+            # K3's stores address rows of the symmetric buffers directly, so the row ranges need not be equal: balance them
+            # (the NCCL all-gather fallback below needs the uniform split)
+            lo, hi = self._balanced_shard(G, P_src)
             ubuf = torch.view_as_complex(self._symm[0].view(rows_alloc, B, 2))
             self._symm[1].barrier()             # every rank is done with the previous contents of the (reused) buffer
             self._Ubuf = {self.b: ubuf}

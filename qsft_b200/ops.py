@@ -441,10 +441,11 @@ class PeelProblem:
         return (cj[ok], self.find_k[:n_finds, :self.n].cpu().numpy()[ok], self.find_rho[:n_finds].cpu().numpy()[ok],
                 self.find_round[:n_finds].cpu().numpy()[ok])
 
-    def peel_blocks(self, blocks):
+    def peel_blocks(self, blocks, wait=True):
         """The same loop on bins given as C * R separate (P_src, B) complex64 row blocks (block c * R + r; what get_MDU
         returns), read in place -- no (C, P, B) copy.  Returns (n_finds, n_rounds), or None when the shape does not fit the
-        on-device loop (the caller then assembles U and uses peel())."""
+        on-device loop (the caller then assembles U and uses peel()).  wait=False: the loop is only queued (returns
+        (-1, -1), n_uniq stays unknown); the outcome is in self.counters -- see PeelOutcome."""
         R = self.P // self.P_src
         if len(blocks) != self.C * R:
             raise ValueError("expected C * R blocks")
@@ -458,21 +459,24 @@ class PeelProblem:
                 return None
         arr = (C.c_void_p * len(blocks))(*[C.c_void_p(t.data_ptr()) for t in blocks])
         nf, nu, nr = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        outs = (C.byref(nf), C.byref(nu), C.byref(nr)) if wait else (None, None, None)
         with torch.cuda.device(self.device), _timed("k4_peel", self.C * self.P * self.B):
             rc = _lib.lib().qsft_peel_blocks(C.byref(self.desc), arr, ldU, _ptr(self.find_cj), _ptr(self.find_k),
                                              _ptr(self.find_rho), _ptr(self.find_round), _ptr(self.find_id), self.max_finds,
-                                             _ptr(self.counters), C.byref(self.uniq), C.byref(nf), C.byref(nu), C.byref(nr),
-                                             _stream())
+                                             _ptr(self.counters), C.byref(self.uniq), outs[0], outs[1], outs[2], _stream())
         if rc == -3:                                   # QSFT_EUNSUPPORTED
             return None
         _lib.check(rc)
+        if not wait:
+            self.n_uniq = -1
+            return -1, -1
         self.n_uniq = nu.value
         return nf.value, nr.value
 
     # -- the on-device loop sharded over the ranks of a DistContext -----------------------------------------------------
     _SHARD_WS = {}
 
-    def peel_blocks_sharded(self, blocks, dist):
+    def peel_blocks_sharded(self, blocks, dist, wait=True):
         """Bin-sharded on-device loop (qsft_peel_blocks_sharded): every rank classifies its bins, the round's finds travel
         between the ranks inside the kernel (NVLink stores into the peers' symmetric workspaces).  Needs alloc() for the
         distinct-k buffers.  Returns n_rounds, or None when the shape / platform does not fit (caller falls back)."""
@@ -507,12 +511,16 @@ class PeelProblem:
         shard = _lib.Shard(rank=dist.rank, world=dist.world_size, peers=peers, epoch=ws["epoch"])
         arr = (C.c_void_p * len(blocks))(*[C.c_void_p(t.data_ptr()) for t in blocks])
         nu, nr = C.c_int64(0), C.c_int(0)
+        outs = (C.byref(nu), C.byref(nr)) if wait else (None, None)
         with torch.cuda.device(self.device), _timed("k4_peel", self.C * self.P * self.B):
             rc = _lib.lib().qsft_peel_blocks_sharded(C.byref(self.desc), arr, ldU, C.byref(shard), max_finds, _ptr(self.counters),
-                                                     C.byref(self.uniq), C.byref(nu), C.byref(nr), _stream())
+                                                     C.byref(self.uniq), outs[0], outs[1], _stream())
         if rc == -3:
             return None
         _lib.check(rc)
+        if not wait:                                        # queued only: the outcome is in self.counters (PeelOutcome)
+            self.n_uniq = -1
+            return -1
         self.n_uniq = nu.value
         return nr.value
 

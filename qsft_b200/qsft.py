@@ -13,7 +13,7 @@ import torch
 
 from . import ops
 from .input_signal_subsampled import SubsampledSignal
-from .result import SparseSpectrum
+from .result import PendingSpectrum, SparseSpectrum
 from .utils import calc_hamming_weight, sort_qary_vecs
 
 
@@ -80,11 +80,15 @@ class QSFT:
         dist = getattr(signal, "dist", None)
         shard = dist.shard_peel(C * P * B * 8) if dist is not None and dist.world_size > 1 else ""
         n_rounds = None
+        output = kwargs.get("output", "dict")
+        # output="device_async": nothing is read back -- the peel is queued behind the sampling and transform kernels and the
+        # call returns a PendingSpectrum; a stream of transforms then keeps the GPU busy while the host prepares the next one
+        wait = output != "device_async"
         if shard == "device":
             prob.alloc(max_finds=min(15 * C * B, max(4096, 4 * C * B)), max_uniq=max(4096, C * B), reuse=True)
             blocks = [u if isinstance(u, torch.Tensor) else torch.as_tensor(u, device=dev) for us in Us for u in us]
             if all(t.is_cuda and t.dtype == torch.complex64 and t.is_contiguous() for t in blocks):
-                n_rounds = prob.peel_blocks_sharded(blocks, dist)
+                n_rounds = prob.peel_blocks_sharded(blocks, dist, wait=wait)
             n_finds = -1
             if n_rounds is None:                         # shape / platform does not fit: every rank agrees (same inputs)
                 if not getattr(signal, "Us_complete", True):
@@ -100,13 +104,20 @@ class QSFT:
             # the on-device loop reads the blocks get_MDU returned where they lie (no copy)
             blocks = [u if isinstance(u, torch.Tensor) else torch.as_tensor(u, device=dev) for us in Us for u in us]
             fits = all(t.is_cuda and t.dtype == torch.complex64 and t.is_contiguous() for t in blocks)
-            done = prob.peel_blocks(blocks) if fits else None
+            done = prob.peel_blocks(blocks, wait=wait) if fits else None
+            if done is None and not wait:
+                raise ValueError("output='device_async' needs bins the on-device loop can read in place (C * R <= 16, "
+                                 "contiguous complex64 CUDA blocks)")
             n_finds, n_rounds = done if done is not None else prob.peel(stacked())
+        if not wait:
+            if shard == "host":
+                raise ValueError("output='device_async' is not available with the host-driven sharded peel")
+            self.last_stats = {"cutoff": float(cutoff)}
+            return PendingSpectrum(prob, n, dist if dist is not None and dist.world_size > 1 else None)
         if dist is not None and dist.world_size > 1:
             dist.verify()                                 # deferred rank-agreement checks (Ms / Ds, selections, noise seed)
         self.last_stats = {"rounds": int(n_rounds), "finds": int(n_finds), "distinct": int(prob.n_uniq),
                            "cutoff": float(cutoff)}
-        output = kwargs.get("output", "dict")
         if output == "device":
             # distinct k left in HBM (no host copy): k int8 (K, n), sum of rho complex64, find counts, first-seen keys
             nu = prob.n_uniq

@@ -131,3 +131,43 @@ class SparseSpectrum(dict):
 
     def copy(self):
         return dict(self._fill())
+
+
+class PendingSpectrum:
+    """Result of `QSFT.transform(..., output="device_async")`: the peel has been QUEUED on the device, nothing was read back.
+
+    `wait()` blocks until this transform is done, raises what the synchronous call would have raised (find buffer too
+    small, ranks seeded differently) and returns the statistics; `device()` then gives the distinct-k list as device
+    tensors like output="device".  The tensors live in the peel workspace that the next transform of the same shape on this
+    device reuses: read them (or queue the reads on the stream) before starting that one -- the statistics stay valid."""
+
+    def __init__(self, prob, n, dist):
+        import torch
+        self._prob, self._n, self._dist = prob, n, dist
+        self._host = torch.empty(8, dtype=torch.int64, pin_memory=True)
+        self._host.copy_(prob.counters, non_blocking=True)          # stream ordered: the counters of THIS transform
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(prob.device))
+        self._buffers = (prob.uniq_k, prob.uniq_sum, prob.uniq_cnt, prob.uniq_key, prob.max_uniq)
+        self.stats = None
+
+    def done(self):
+        return self._event.query()
+
+    def wait(self):
+        if self.stats is None:
+            self._event.synchronize()
+            c = self._host.tolist()
+            if c[6]:
+                raise RuntimeError(f"find buffer too small: {c[0]} finds")
+            if c[4] > self._buffers[4]:
+                raise RuntimeError(f"unique buffer too small: {c[4]} > {self._buffers[4]}")
+            if self._dist is not None:
+                self._dist.verify()
+            self.stats = {"rounds": int(c[5]), "finds": int(c[7]), "distinct": int(c[4])}
+        return self.stats
+
+    def device(self):
+        nu = self.wait()["distinct"]
+        uk, us, uc, ukey, _ = self._buffers
+        return {"k": uk[:nu, :self._n], "sum": us[:nu], "count": uc[:nu], "key": ukey[:nu]}

@@ -44,6 +44,8 @@ def get_random_subsampled_signal(n, q, noise_sd, sparsity, a_min, a_max, query_a
                                      n=n, q=q, query_args=query_args, **kwargs)
 
 
+_SM_COUNT = {}
+
 class SyntheticSubsampledSignal(SubsampledSignal):
     """SubsampledSignal whose samples are computed on the fly from a known sparse spectrum
     (synthetic_signal.py:88-130)."""
@@ -83,6 +85,18 @@ class SyntheticSubsampledSignal(SubsampledSignal):
     def subsample_device(self, digits):
         """digits (N, ld) int8 on the device -> complex64 samples (N,)."""
         return ops.eval_synth(digits, self._loc_dev, self._a_dev, self.q, self.n, impl=min(self.eval_impl, 2))
+
+    def _block_cost(self, rows):
+        """Lattice GEMM: one CTA pair per 256 x 128 tile of samples, each walking the whole support; the pairs run in waves of
+        (SMs / 2), and every block a rank touches costs one operand preparation (~0.6 of a wave at config 5)."""
+        B, S = self.q ** self.b, self._loc_dev.shape[0]
+        if not (ops.lattice_supported(self.q, self.n, self.b, rows, S) and self.eval_impl in (0, 3) and S >= 512):
+            return float(rows)
+        sms = _SM_COUNT.get(self.device)
+        if sms is None:
+            sms = _SM_COUNT[self.device] = torch.cuda.get_device_properties(self.device).multi_processor_count
+        pairs = -(-rows * 2 * B // (256 * 128))
+        return float(-(-pairs // max(1, sms // 2))) + 0.6
 
     def subsample_lattice_device(self, M, D_rows, out=None):
         """Lattice-factorised evaluation (K = S tensor-core GEMM) when the shape supports it; eval_impl: 0 = auto,

@@ -58,6 +58,22 @@ def _worker(rank, world, port, out):
                 err = float(np.max(np.abs(v - want_v))) if same and len(v) else 0.0
                 if not same or err > 1e-5 * max(1.0, float(np.max(np.abs(want_v)))) or len(k) < 0.9 * case[2]:
                     ok, msg = False, f"case {ci} mode {mode}: same={same} err={err} found={len(k)}"
+        # asynchronous result (nothing read back inside the call): two transforms queued, both report the right support size
+        import qsft_b200 as qb
+        n, q, S, b, C, R, chan, noise_sd = CASES[0]
+        qa = {"query_method": "complex", "num_subsample": C, "delays_method_source": "identity", "subsampling_method": "qsft",
+              "delays_method_channel": chan, "num_repeat": R, "b": b}
+        dc = DistContext(peel_mode="sharded")
+        pend = []
+        for seed in (5, 6):
+            np.random.seed(seed)
+            sig = qb.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=1, a_max=1, noise_sd=0.0, query_args=dict(qa), dist=dc)
+            pend.append((len(sig.signal_w), qb.QSFT(num_subsample=C, num_repeat=R, b=b, reconstruct_method_source="identity",
+                                                    reconstruct_method_channel=chan).transform(sig, output="device_async")))
+        for want_n, h in pend:
+            st = h.wait()
+            if st["distinct"] != want_n:
+                ok, msg = False, f"device_async: {st} but the support has {want_n} coefficients"
         # ranks seeded differently must be refused, not silently mixed
         np.random.seed(1000 + rank)
         import qsft_b200

@@ -370,6 +370,33 @@ def test_construct_and_transform_all_eval_impls_agree(impl):
     assert np.allclose(arr["values"], np.array(list(res.values())), rtol=0, atol=1e-6)
 
 
+def test_transform_device_async_pipelined_equals_synchronous():
+    """output="device_async": three transforms queued back to back without any read-back; each PendingSpectrum, waited for
+    afterwards, reports the statistics of ITS transform, and the last one's device list equals the synchronous result."""
+    n, q, b, C, R = 16, 4, 7, 3, 1
+    qa = {"query_method": "complex", "num_subsample": C, "delays_method_source": "identity", "subsampling_method": "qsft",
+          "delays_method_channel": "nso", "num_repeat": R, "b": b}
+    sigs = []
+    for seed, S in ((21, 400), (22, 900), (23, 650)):
+        np.random.seed(seed)
+        sigs.append(qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=1, a_max=1, noise_sd=0.0, query_args=dict(qa)))
+
+    def run(sig, output):
+        return qsft_b200.QSFT(num_subsample=C, num_repeat=R, b=b, reconstruct_method_source="identity",
+                              reconstruct_method_channel="nso").transform(sig, output=output)
+
+    pend = [run(sig, "device_async") for sig in sigs]
+    stats = [p.wait() for p in pend]
+    assert [st["distinct"] for st in stats] == [len(sig.signal_w) for sig in sigs]
+    assert all(st["rounds"] >= 1 for st in stats)
+    dev = pend[-1].device()                                 # the workspace still holds the last transform
+    got_k, got_sum, got_cnt = dev["k"].cpu().numpy(), dev["sum"].cpu().numpy(), dev["count"].cpu().numpy()
+    order = np.argsort(dev["key"].cpu().numpy(), kind="stable")
+    want = run(sigs[-1], "arrays")
+    assert np.array_equal(got_k[order].astype(np.int64), np.asarray(want["locations"]).astype(np.int64))
+    assert np.allclose((got_sum / got_cnt)[order], want["values"], rtol=0, atol=1e-6)
+
+
 # ---- BASELINE configs at full size ----------------------------------------------------------------------------
 def test_config2_full_size_noisy_nmse_matches_reference_run():
     """BASELINE config 2 at full size (q=4 n=20 b=7 S=1000 C=3 nso R=3, 20 dB, seed 0).  The unmodified reference

@@ -406,3 +406,35 @@ def test_sparse_spectrum_behaves_like_the_reference_dict():
     assert np.array_equal(fresh().locations, loc) and np.array_equal(fresh().coefficients, val)
     empty = SparseSpectrum(np.zeros((0, 7), dtype=np.int8), np.zeros(0, dtype=complex))
     assert len(empty) == 0 and not empty and empty == {} and list(empty.items()) == []
+
+
+def test_balanced_row_shards_cover_all_rows_and_never_cost_more_than_the_uniform_split():
+    """Multi-GPU row placement (input_signal_subsampled.py: _balanced_shard): contiguous, complete, no range longer than
+    the uniform share (the row buffer keeps its size), and the most loaded rank never costs more than with the uniform
+    split; with a proportional cost the split is the uniform one up to where the remainder goes."""
+    from qsft_b200.input_signal_subsampled import SubsampledSignal
+
+    class _Dist:
+        def __init__(self, world, rank):
+            self.world_size, self.rank = world, rank
+
+    class _Waves(SubsampledSignal):
+        def __init__(self, world, rank):
+            self.dist = _Dist(world, rank)
+
+        def _block_cost(self, rows):                       # wave-quantised kernel + a set-up per block touched
+            return float(-(-rows * 64 // 74)) + 0.6
+
+    def cost(sig, lo, hi, block):
+        return sum(sig._block_cost(min(hi, k + block) - max(lo, k)) for k in range(0, 1000, block) if min(hi, k + block) > max(lo, k))
+
+    for total, block, world in [(123, 41, 8), (123, 41, 4), (123, 41, 2), (63, 21, 8), (10, 5, 3), (7, 7, 8)]:
+        shards = [_Waves(world, r)._balanced_shard(total, block) for r in range(world)]
+        per = -(-total // world)
+        assert shards[0][0] == 0 and shards[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(shards, shards[1:]))
+        assert all(0 <= hi - lo <= per for lo, hi in shards)
+        sig = _Waves(world, 0)
+        uniform = [(min(total, r * per), min(total, (r + 1) * per)) for r in range(world)]
+        assert max(cost(sig, lo, hi, block) for lo, hi in shards) <= max(cost(sig, lo, hi, block) for lo, hi in uniform)
+    assert max(cost(_Waves(8, 0), lo, hi, 41) for lo, hi in [_Waves(8, r)._balanced_shard(123, 41) for r in range(8)]) == 14.6
