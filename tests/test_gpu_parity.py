@@ -391,10 +391,11 @@ def test_transform_device_async_pipelined_equals_synchronous():
     assert all(st["rounds"] >= 1 for st in stats)
     dev = pend[-1].device()                                 # the workspace still holds the last transform
     got_k, got_sum, got_cnt = dev["k"].cpu().numpy(), dev["sum"].cpu().numpy(), dev["count"].cpu().numpy()
-    order = np.argsort(dev["key"].cpu().numpy(), kind="stable")
-    want = run(sigs[-1], "arrays")
-    assert np.array_equal(got_k[order].astype(np.int64), np.asarray(want["locations"]).astype(np.int64))
-    assert np.allclose((got_sum / got_cnt)[order], want["values"], rtol=0, atol=1e-6)
+    want = run(sigs[-1], "arrays")          # (get_MDU draws a new group order from the host RNG: compare as mappings)
+    got = {tuple(int(v) for v in k): val for k, val in zip(got_k, got_sum / got_cnt)}
+    ref = {tuple(int(v) for v in k): val for k, val in zip(want["locations"], want["values"])}
+    assert got.keys() == ref.keys() == sigs[-1].signal_w.keys()
+    assert max(abs(got[k] - ref[k]) for k in ref) < 1e-6
 
 
 # ---- BASELINE configs at full size ----------------------------------------------------------------------------
