@@ -15,7 +15,7 @@ int qsft_kl_launch_nw32(const KlArgs& a, const KlBlocks& blk, const KlMaps& maps
 // layout of a sharded workspace: control block, then the find list and the find table
 namespace {
 struct KlWsLayout {
-    long long off_ctl, off_cj, off_k, off_rho, off_round, off_id, bytes;
+    long long off_ctl, off_cj, off_k, off_rho, off_round, off_id, off_res, bytes;
 };
 KlWsLayout kl_ws_layout(const PeelDev& d, long long max_finds) {
     auto up = [](long long v) { return (v + 255) & ~255ll; };
@@ -26,7 +26,8 @@ KlWsLayout kl_ws_layout(const PeelDev& d, long long max_finds) {
     L.off_rho = L.off_k + up(max_finds * d.ld);
     L.off_round = L.off_rho + up(max_finds * 8);
     L.off_id = L.off_round + up(max_finds * 4);
-    L.bytes = L.off_id + up((long long)d.C * d.B * 4);
+    L.off_res = L.off_id + up((long long)d.C * d.B * 4);
+    L.bytes = L.off_res + up(max_finds * 4);
     return L;
 }
 }  // namespace
@@ -55,8 +56,7 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
     for (int i = 0; i < nblk; ++i)
         if ((uintptr_t)blocks[i] & 15) use_tma = false;
     const int budget = smem_max - 1024 - 2048;             // alignment slack + the kernel's static shared memory
-    // QSFT_K4_NO_PRIV=1 (measurement aid / cross-check): candidate work in the stage instead of the warps' private copies
-    if (!kl_geometry(d, budget, use_tma ? 2 : 1, &a, getenv("QSFT_K4_NO_PRIV") == nullptr)) return QSFT_EUNSUPPORTED;
+    if (!kl_geometry(d, budget, use_tma ? 2 : 1, &a)) return QSFT_EUNSUPPORTED;
     KlBlocks blk{};
     for (int i = 0; i < nblk; ++i) blk.p[i] = reinterpret_cast<const float2*>(blocks[i]);
     KlMaps hm;
@@ -71,18 +71,27 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
     }
     if (!use_tma) a.nstages = 1;
     const size_t smem = (size_t)a.nstages * a.stage_bytes + KL_CTRL_BYTES + (size_t)KL_NC * a.priv_bytes + 1024;
-    // workspace: ball lists, grid barrier, delay-structure flag
-    const size_t head_b = (size_t)d.C * d.B * 4, next_b = (size_t)max_finds * d.C * 4;
+    // workspace: grid barrier, dirty-list counters, delay-structure flag, round counters | list heads | zres | bin classes
+    // (all of these zeroed) | list links | dirty list | residuals of the finds
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t CB = (size_t)d.C * d.B;
+    const size_t head_off = 256, zres_off = head_off + up(CB * 4), cls_off = zres_off + up(CB * 4), next_off = cls_off + up(CB);
+    const size_t dirty_off = next_off + up((size_t)max_finds * d.C * 4), res_off = dirty_off + up(CB * 8);
     uint8_t* ws = nullptr;
-    const size_t head_off = 256, next_off = head_off + ((head_b + 255) & ~(size_t)255);
-    QSFT_CUDA(qsft_scratch_alloc((void**)&ws, next_off + next_b, st));
-    QSFT_CUDA(cudaMemsetAsync(ws, 0, head_off + head_b, st));                  // barrier, flag, round counters, list heads
+    QSFT_CUDA(qsft_scratch_alloc((void**)&ws, res_off + up((size_t)max_finds * 4), st));
+    QSFT_CUDA(cudaMemsetAsync(ws, 0, next_off, st));
     a.gbar = reinterpret_cast<unsigned int*>(ws);
+    a.dcount = reinterpret_cast<unsigned long long*>(ws + 8);
     int* dflag = reinterpret_cast<int*>(ws + 64);
     a.multi = reinterpret_cast<unsigned long long*>(ws + 128);                 // 16 slots
     a.dstruct = dflag;
     a.head = reinterpret_cast<int32_t*>(ws + head_off);
+    a.zres = reinterpret_cast<unsigned int*>(ws + zres_off);
+    a.cls = ws + cls_off;
     a.next = reinterpret_cast<int32_t*>(ws + next_off);
+    a.dirty = reinterpret_cast<long long*>(ws + dirty_off);
+    a.max_dirty = (long long)CB;
+    a.find_res = reinterpret_cast<float*>(ws + res_off);
     a.rank = 0;
     a.world = 1;
     a.jb = 0;
@@ -102,6 +111,7 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
         find_rho = reinterpret_cast<float*>(mine + L.off_rho);
         find_round = reinterpret_cast<int32_t*>(mine + L.off_round);
         find_id = reinterpret_cast<int32_t*>(mine + L.off_id);
+        a.find_res = reinterpret_cast<float*>(mine + L.off_res);
         a.rank = shard->rank;
         a.world = shard->world;
         const long long per = ((d.B + shard->world - 1) / shard->world + 127) & ~127ll;     // whole tiles per rank
@@ -110,7 +120,7 @@ int qsft_peel_loop(const PeelDev& d, const float* const* blocks, int64_t ldU, in
         a.seg = max_finds / shard->world;
         for (int p = 0; p < 8; ++p) a.sh.peer[p] = p < shard->world ? static_cast<uint8_t*>(shard->peers[p]) : nullptr;
         a.sh.off_cj = L.off_cj; a.sh.off_k = L.off_k; a.sh.off_rho = L.off_rho; a.sh.off_round = L.off_round;
-        a.sh.off_id = L.off_id; a.sh.off_ctl = L.off_ctl;
+        a.sh.off_id = L.off_id; a.sh.off_res = L.off_res; a.sh.off_ctl = L.off_ctl;
         a.sh.epoch = shard->epoch;
     }
     a.find_cj = (long long*)find_cj;

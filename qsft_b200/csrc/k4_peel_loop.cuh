@@ -21,6 +21,17 @@
 //   rho and residual in ONE pass over the rows (qsft.py:174-183), bin hash check (qsft.py:178-179).
 // Link phase of a round: one thread per find: duplicate gathering / averaging exactly like k4_reduce_kernel, and the
 // "last (i, j) wins" find of every k (qsft.py:215) links the ball into its C bins.
+//
+// Rounds after the first do NOT scan U again.  A bin whose ball list did not change in the previous link phase holds what it
+// held when it was last classified -- a zeroton or a multiton (a singleton's own ball is always linked into it) -- and would
+// be classified the same way, so only the bins the link phase touched ("dirty" bins, listed as they are touched) are looked
+// at, and the multiton count of the stop rule (qsft.py:204-205) is carried from round to round (per-bin class byte: the
+// count changes by the dirty bins that stop / start being multitons).  Most dirty bins are the singletons themselves: the bin
+// where k was found with value rho and residual res, after the ball (k, rho_last) has been subtracted, has the energy
+// res + P |rho - rho_last|^2 EXACTLY (the residual of a least-squares fit is orthogonal to the signature), which the link
+// phase knows without touching the bin (`zres`).  Only dirty bins that received a ball of a k they were not themselves found
+// with (multitons of the previous round, or several balls at once) are gathered from U (column reads into a warp's private
+// buffer), get all their listed balls subtracted and are classified like a bin of the first round.
 #pragma once
 #include "common.cuh"
 
@@ -52,7 +63,7 @@ struct KlMaps {
 // kernel: the all-gather of (k, rho) lists of the reference's round structure (qsft.py:209-241), fused into the peel.
 struct KlShard {
     uint8_t* peer[8];                        // base of every rank's workspace (own one included)
-    long long off_cj, off_k, off_rho, off_round, off_id, off_ctl;      // byte offsets of the arrays in a workspace
+    long long off_cj, off_k, off_rho, off_round, off_id, off_res, off_ctl;      // byte offsets of the arrays in a workspace
     unsigned int epoch;                      // flags hold (epoch << 8) | round: no clearing between peels
 };
 // control block of a workspace: [round 0 .. 15][source rank 0 .. 7]
@@ -70,9 +81,17 @@ struct KlArgs {
     float2* find_rho;
     int32_t* find_round;
     int32_t* find_id;                        // (C, B): written for singletons only; validated through find_cj
+    float* find_res;                         // residual of the singleton test of every find (see `zres`)
     long long max_finds;
     int32_t* head;                           // (C, B): last ball linked into the bin + 1 (0 = none); zeroed by the host
     int32_t* next;                           // (max_finds, C): previous ball of the same bin + 1
+    unsigned int* zres;                      // (C, B) float bits, 0 = untouched since the bin was last looked at: energy left in the
+                                             // bin once the round's ball is subtracted, when that is known without reading the
+                                             // bin (the bin's own find carries the same k), +inf when it is not; atomic max
+    uint8_t* cls;                            // (C, B): 2 = the bin was a multiton when it was last classified
+    long long* dirty;                        // (max_dirty) c * B + j of the bins (of this rank's range) touched by the last link phase
+    long long max_dirty;
+    unsigned long long* dcount;              // [2]: entries of `dirty` written by the link phase of round r -> dcount[r & 1]
     UniqOut uo;
     int has_uniq;
     unsigned long long* counters;            // [0] finds, [2] balls peeled, [4] distinct k, [5] rounds, [6] error flags,
@@ -84,7 +103,7 @@ struct KlArgs {
     int box;                                 // bytes per repeat block of a tile: (W / 16) * P_src * 128 rounded up to 1024
     int stage_bytes;                         // R * box + list heads, rounded up to 1024
     int nstages;
-    int priv_bytes;                          // per candidate warp: private copy of its four bins' columns (0 = work in the stage)
+    int priv_bytes;                          // per candidate warp: private copy of its four bins' columns
     int chunk;                               // find slots a warp reserves at a time
     int max_rounds;
     int guard_can_bind;
@@ -335,12 +354,13 @@ __device__ __forceinline__ void kl_scan(const KlArgs& a, uint8_t* stage, long lo
 }
 
 // ---- candidate warps (cw = 0 .. KL_NC - 1): this warp's share of the tile's work items, four at a time ------------------
-// kl_cand_body works on the columns of the warp's four items through `col` -- the stage itself (TileCol) or the warp's private
-// copy (PrivCol); `f` = the bin's first listed ball (-1: none).
+// kl_cand_body works on the columns of the warp's four items through `col` (the warp's private copy, PrivCol); `f` = the bin's
+// first listed ball (-1: none).  Returns the bin's class to all lanes of its group: 0 zeroton, 1 singleton (find recorded),
+// 2 multiton.
 template <int NW, class Col>
-__device__ __forceinline__ void kl_cand_body(const KlArgs& a, const Col& col, int c, long long jb, int round, bool act, bool touched,
-                                             int f, float e_b, uint8_t* sym, const float2* s_tw, bool structured,
-                                             const long long (&wgt)[32 / KL_G], unsigned& n_multi, KlSlots& slots) {
+__device__ __forceinline__ int kl_cand_body(const KlArgs& a, const Col& col, int c, long long jb, int round, bool act, bool touched,
+                                            int f, float e_b, uint8_t* sym, const float2* s_tw, bool structured,
+                                            const long long (&wgt)[32 / KL_G], KlSlots& slots) {
     const PeelDev& d = a.d;
     const int lane = threadIdx.x & 31;
     const int gl = lane % KL_G;
@@ -470,20 +490,20 @@ __device__ __forceinline__ void kl_cand_body(const KlArgs& a, const Col& col, in
                 a.find_cj[fs] = (long long)c * B + jb;
                 a.find_rho[fs] = make_float2(rr, ri);
                 a.find_round[fs] = round;
+                a.find_res[fs] = res;
                 a.find_id[(size_t)c * B + jb] = (int32_t)fs;
             }
         }
-    } else if (act && lead) {
-        ++n_multi;
     }
     __syncwarp();
+    return single ? 1 : act ? 2 : 0;
 }
 
-// group g of a tile.  With a private buffer (priv != nullptr) the warp first copies the columns of its four items out of the
-// stage and hands the stage back at once -- the ring slot is then held for the copy, not for the microseconds of
-// latency-bound work per item that follow (with in-stage work the ring, 4 .. 6 tiles deep, stalled behind its slowest tile:
-// ncu showed the candidate warps idle at their mailboxes for a quarter of all samples and the scanners waiting for data).
-// Without one (rows too long for the shared memory left) the work is done in the stage, which is released afterwards.
+// group g of a tile (first round: no bin carries a ball yet).  The warp copies the columns of its four items out of the stage
+// into its private buffer and hands the stage back at once -- the ring slot is then held for the copy, not for the
+// microseconds of latency-bound work per item that follow (with in-stage work the ring, 4 .. 6 tiles deep, stalled behind
+// its slowest tile: ncu showed the candidate warps idle at their mailboxes for a quarter of all samples and the scanners
+// waiting for data).
 template <int NW>
 __device__ __forceinline__ void kl_cand_any(const KlArgs& a, uint8_t* stage, KlTileInfo* info, int c, long long j0, int round, int g,
                                             uint8_t* s_symw, float2* priv, const float2* s_tw, bool structured,
@@ -492,7 +512,6 @@ __device__ __forceinline__ void kl_cand_any(const KlArgs& a, uint8_t* stage, KlT
     const int lane = threadIdx.x & 31;
     const int grp = lane / KL_G, gl = lane % KL_G;
     const int R = d.R, P_src = d.P_src;
-    const int32_t* s_head = reinterpret_cast<const int32_t*>(stage + (size_t)R * a.box);
     uint8_t* sym = s_symw + grp * KL_SYM;
     const unsigned mask[4] = {info->mask[0], info->mask[1], info->mask[2], info->mask[3]};
     const int total = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
@@ -503,29 +522,79 @@ __device__ __forceinline__ void kl_cand_any(const KlArgs& a, uint8_t* stage, KlT
     const long long jb = j0 + lbm;
     const TileCol tc{stage, P_src, a.box, lbm, a.lgW - 4};
     const float e_b = info->e[lbm];
-    const bool touched = act && round > 1 && ((info->tmask[lbm >> 5] >> (lbm & 31)) & 1u);
-    const int f = touched ? s_head[lbm] - 1 : -1;
-    if (priv != nullptr) {
-        const PrivCol pc{priv + grp, P_src};
-        if (act)
-            for (int r = 0; r < R; ++r)
-                for (int i = gl; i < P_src; i += KL_G) pc.ref(r, i) = tc.ri(r, i);
-        __syncwarp();
+    const PrivCol pc{priv + grp, P_src};
+    if (act)
+        for (int r = 0; r < R; ++r)
+            for (int i = gl; i < P_src; i += KL_G) pc.ref(r, i) = tc.ri(r, i);
+    __syncwarp();
 #ifndef QSFT_EMU
-        if (empty_bar != nullptr && lane == 0 && atomicSub(&info->left, 1) == 1) tma::mbar_arrive(empty_bar);
+    if (empty_bar != nullptr && lane == 0 && atomicSub(&info->left, 1) == 1) tma::mbar_arrive(empty_bar);
+#else
+    (void)empty_bar;
 #endif
-        kl_cand_body<NW>(a, pc, c, jb, round, act, touched, f, e_b, sym, s_tw, structured, wgt, n_multi, slots);
-    } else {
-        kl_cand_body<NW>(a, tc, c, jb, round, act, touched, f, e_b, sym, s_tw, structured, wgt, n_multi, slots);
-#ifndef QSFT_EMU
-        if (empty_bar != nullptr) {
-            // done with the stage; in-place updates (generic proxy) are ordered before the next bulk copy
-            if (round > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0 && atomicSub(&info->left, 1) == 1) tma::mbar_arrive(empty_bar);
-        }
-#endif
+    const int cls = kl_cand_body<NW>(a, pc, c, jb, round, act, false, -1, e_b, sym, s_tw, structured, wgt, slots);
+    if (gl == 0 && cls == 2) {
+        ++n_multi;
+        a.cls[(size_t)c * d.B + jb] = 2;
     }
+}
+
+// ---- rounds after the first: the bins the last link phase touched ------------------------------------------------------------
+// Candidate warps take the dirty list four entries at a time.  An entry whose `zres` proves it a zeroton costs two loads; the
+// others are gathered from U (one 8-byte read per delay row: these are few), get their listed balls subtracted and are
+// classified.  Returns nothing; the round's change of the multiton count is added to a.multi[round] (two's complement).
+template <int NW>
+__device__ __forceinline__ void kl_dirty_round(const KlArgs& a, const KlBlocks& blk, int round, long long nd, uint8_t* s_sym,
+                                               uint8_t* s_priv, const float2* s_tw) {
+    const PeelDev& d = a.d;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < KL_NS || warp >= KL_NS + KL_NC) return;
+    const int cw = warp - KL_NS;
+    const int grp = lane / KL_G, gl = lane % KL_G;
+    const int R = d.R, P_src = d.P_src;
+    const long long B = d.B;
+    const float thresh = (float)d.thresh;
+    const bool structured = (*a.dstruct != 0);
+    long long wgt[32 / KL_G];
+#pragma unroll
+    for (int u = 0; u < 32 / KL_G; ++u) wgt[u] = hash_weight(d, gl + u * KL_G);
+    uint8_t* sym = s_sym + (size_t)cw * 4 * KL_SYM + grp * KL_SYM;
+    const PrivCol pc{reinterpret_cast<float2*>(s_priv + (size_t)cw * a.priv_bytes) + grp, P_src};
+    KlSlots slots{0, 0, 0};
+    int delta = 0;
+    const long long ngroups = (nd + 3) >> 2;
+    for (long long g = (long long)blockIdx.x * KL_NC + cw; g < ngroups; g += (long long)gridDim.x * KL_NC) {
+        const long long e = 4 * g + grp;
+        const bool have = e < nd;
+        const long long cj = have ? __ldcg(a.dirty + e) : 0;
+        float z = 0.f;
+        if (have) z = __uint_as_float(__ldcg(a.zres + cj));
+        const bool heavy = have && z > thresh;                  // energy test (qsft.py:164) on the known residual
+        const unsigned any_heavy = __ballot_sync(0xffffffffu, heavy);
+        if (have && gl == 0) a.zres[cj] = 0u;                   // looked at (by all lanes: after the ballot) -> ready for the next link phase
+        if (!any_heavy) continue;
+        const int c = (int)(cj / B);
+        const long long j = cj - (long long)c * B;
+        int hd = 0, was = 0;
+        if (heavy) {
+            hd = __ldcg(a.head + cj);
+            was = a.cls[cj];
+            for (int r = 0; r < R; ++r) {
+                const float2* src = blk.p[c * R + r] + j;
+                for (int i = gl; i < P_src; i += KL_G) pc.ref(r, i) = __ldcg(src + (size_t)i * a.ldU);
+            }
+        }
+        __syncwarp();
+        const int cls = kl_cand_body<NW>(a, pc, c, j, round, heavy, heavy, hd - 1, 0.f, sym, s_tw, structured, wgt, slots);
+        if (heavy && gl == 0) {
+            delta += (cls == 2 ? 1 : 0) - (was == 2 ? 1 : 0);
+            if ((cls == 2) != (was == 2)) a.cls[cj] = (uint8_t)(cls == 2 ? 2 : 0);
+        }
+    }
+    kl_close(a, slots);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
+    if (lane == 0 && delta != 0) atomicAdd(&a.multi[round], (unsigned long long)(long long)delta);
 }
 
 // ---- one classification round ---------------------------------------------------------------------------------------
@@ -567,7 +636,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
         for (int u = 0; u < 32 / KL_G; ++u) wgt[u] = hash_weight(d, (lane % KL_G) + u * KL_G);
     }
     uint8_t* s_symw = s_sym + (size_t)(is_cand ? warp - KL_NS : 0) * 4 * KL_SYM;
-    float2* s_privw = a.priv_bytes ? reinterpret_cast<float2*>(s_priv + (size_t)(is_cand ? warp - KL_NS : 0) * a.priv_bytes) : nullptr;
+    float2* s_privw = reinterpret_cast<float2*>(s_priv + (size_t)(is_cand ? warp - KL_NS : 0) * a.priv_bytes);
 #ifndef QSFT_EMU
     if (TMA) {
         uint64_t* full = bars;
@@ -701,6 +770,7 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, const KlRound& rd, int 
     const int nw = d.ld / 4;
     const long long B = d.B;
     const long long f0 = rd.lo[p], f1 = rd.hi[p];
+    const float Pf = (float)d.P;
     for (long long f = f0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; f < f1; f += (long long)gridDim.x * blockDim.x) {
         const long long cj = __ldcg(a.find_cj + f);
         if (cj < 0) continue;                               // unused slot of a warp's chunk
@@ -709,13 +779,17 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, const KlRound& rd, int 
         const uint32_t* kin = reinterpret_cast<const uint32_t*>(a.find_k + (size_t)f * d.ld);
 #pragma unroll
         for (int w = 0; w < NW; ++w) kw[w] = (w < nw) ? __ldcg(kin + w) : 0u;
-        float2 sum = __ldcg(a.find_rho + f);
+        const float2 rho = __ldcg(a.find_rho + f);
+        float2 sum = rho;
         int cnt = 1;
         bool first = true, last = true;
         long long jl[KL_MAX_BLOCKS];                       // C <= 16 on this path
+        float zl[KL_MAX_BLOCKS];                           // energy left in bin (c2, jl[c2]) once (k, rho) is subtracted, if known
         for (int c2 = 0; c2 < d.C; ++c2) {
+            zl[c2] = __uint_as_float(0x7f800000u);           // +inf: not known without reading the bin
             if (c2 == c) {
                 jl[c2] = cj - (long long)c * B;
+                zl[c2] = __ldcg(a.find_res + f);            // this find's own bin: its residual
                 continue;
             }
             const long long j2 = hash_bin<NW>(d, c2, kw);
@@ -734,11 +808,14 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, const KlRound& rd, int 
 #pragma unroll
                 for (int w = 0; w < NW; ++w) same &= ((w < nw) ? __ldcg(k2 + w) : 0u) == kw[w];
                 if (same) {
+                    const float2 r2 = __ldcg(a.find_rho + f2);
+                    // bin (c2, j2) was found with the same k, value r2, residual res2: minus (k, rho) it holds res2 + P |r2 - rho|^2
+                    const float dx = r2.x - rho.x, dy = r2.y - rho.y;
+                    zl[c2] = fmaf(Pf, fmaf(dx, dx, dy * dy), __ldcg(a.find_res + f2));
                     if (c2 < c) {
                         first = false;                      // an earlier group holds the round's first find of this k
                     } else {
                         last = false;                       // ball_values: a later (i, j) wins (qsft.py:215)
-                        const float2 r2 = __ldcg(a.find_rho + f2);
                         sum.x += r2.x;
                         sum.y += r2.y;
                         ++cnt;
@@ -750,10 +827,19 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, const KlRound& rd, int 
             k4_uniq_commit<NW>(d, kw, sum, cnt, cj, jl[0], round, a.uo.seen0, a.uo.uk, a.uo.usum, a.uo.ucnt, a.uo.ukey, a.uo.unext,
                                a.uo.max_uniq, a.counters);
         if (last && do_link) {
-            // peel: the ball joins the list of every bin it hashes to (qsft.py:223-241)
+            // peel: the ball joins the list of every bin it hashes to (qsft.py:223-241); bins of this rank's range are entered
+            // into the dirty list by whoever touches them first in this round
             for (int l = 0; l < d.C; ++l) {
-                const int32_t prev = atomicExch(a.head + (size_t)l * B + jl[l], (int32_t)(f + 1));
+                const size_t bin = (size_t)l * B + jl[l];
+                const int32_t prev = atomicExch(a.head + bin, (int32_t)(f + 1));
                 a.next[(size_t)f * d.C + l] = prev;
+                if (jl[l] >= a.jb && jl[l] < a.je) {
+                    const float z = fmaxf(zl[l], 1e-37f);   // never 0 (0 = untouched); negative rounding noise and NaN -> tiny
+                    if (atomicMax(a.zres + bin, __float_as_uint(z)) == 0u) {
+                        const unsigned long long slot = atomicAdd(a.dcount + (round & 1), 1ull);
+                        if ((long long)slot < a.max_dirty) a.dirty[slot] = (long long)bin;
+                    }
+                }
             }
             atomicAdd(&a.counters[2], 1ull);                // num_peeling (qsft.py:224)
         }
@@ -775,6 +861,7 @@ __device__ __forceinline__ void kl_push(const KlArgs& a, long long s0, long long
         if (lane < kvec) kv = reinterpret_cast<const uint4*>(a.find_k + (size_t)f * d.ld)[lane];
         const float2 rho = a.find_rho[f];
         const int32_t rnd = a.find_round[f];
+        const float res = a.find_res[f];
         for (int p = 0; p < a.world; ++p) {
             if (p == a.rank) continue;
             uint8_t* ws = a.sh.peer[p];
@@ -783,6 +870,7 @@ __device__ __forceinline__ void kl_push(const KlArgs& a, long long s0, long long
             if (lane == 9) reinterpret_cast<float2*>(ws + a.sh.off_rho)[f] = rho;
             if (lane == 10) reinterpret_cast<int32_t*>(ws + a.sh.off_round)[f] = rnd;
             if (lane == 11 && cj >= 0) reinterpret_cast<int32_t*>(ws + a.sh.off_id)[cj] = (int32_t)f;
+            if (lane == 12) reinterpret_cast<float*>(ws + a.sh.off_res)[f] = res;
         }
     }
     __threadfence_system();
@@ -843,17 +931,25 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
     double num_peeling = 0;
     int round = 0;
     bool cont = true, overflow = false;
+    long long my_multi = 0;                                 // multiton bins of this rank's range (carried from round to round)
+    long long nd = 0;                                       // dirty bins left by the last link phase
     while (cont && num_peeling < a.peeling_max && round < a.max_rounds) {
         ++round;
-        kl_classify<NW, TMA>(a, blk,
+        if (round == 1)
+            kl_classify<NW, TMA>(a, blk,
 #ifndef QSFT_EMU
-                             maps.m,
+                                 maps.m,
 #endif
-                             round, base, bars, tiles_done, infos, mbox, s_sym, s_priv, s_tw);
+                                 1, base, bars, tiles_done, infos, mbox, s_sym, s_priv, s_tw);
+        else
+            kl_dirty_round<NW>(a, blk, round, nd, s_sym, s_priv, s_tw);
         kl_grid_barrier(a.gbar, epoch);
+        // everybody has read `nd`: its counter is free for the link phase of the next round
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.dcount[(round + 1) & 1] = 0ull;
         long long now[8], multis = 0, nf = 0;
         now[a.rank] = (long long)__ldcg(a.counters + 0);
-        multis = (long long)__ldcg(a.multi + round);
+        my_multi += (long long)__ldcg(a.multi + round);      // round 1: the count; later rounds: the change
+        multis = my_multi;
 #ifndef QSFT_EMU
         if (a.world > 1) {
             // this rank's new slots (unused ones included: they carry find_cj = -1) -> every peer, then counters + flag
@@ -906,6 +1002,8 @@ k4_peel_loop_kernel(const KlArgs a, const KlBlocks blk
         if (cont || a.guard_can_bind) {
             kl_grid_barrier(a.gbar, epoch);
             if (a.guard_can_bind) num_peeling = (double)__ldcg(a.counters + 2);
+            const long long listed = (long long)__ldcg(a.dcount + (round & 1));
+            nd = listed < a.max_dirty ? listed : a.max_dirty;
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -943,27 +1041,25 @@ inline int kl_chunk(const PeelDev& d, int grid) {
 }
 
 // tile geometry for a shared-memory budget: the widest tile (<= 128 bins, no wider than the group needs) that leaves at
-// least `min_stages` stages.  The candidate warps get private column buffers (KlArgs.priv_bytes each: four items x all delay
-// rows) when at least max(min_stages, 3) stages fit beside them.  Returns false when even 16-bin tiles do not fit.
-inline bool kl_geometry(const PeelDev& d, int budget, int min_stages, KlArgs* a, bool allow_priv = true) {
+// least `min_stages` stages beside the candidate warps' private column buffers (KlArgs.priv_bytes each: four items x all
+// delay rows).  Returns false when even 16-bin tiles do not fit (very long delay-row lists: the caller uses the host-driven
+// rounds).
+inline bool kl_geometry(const PeelDev& d, int budget, int min_stages, KlArgs* a) {
     const long long priv = (((long long)d.R * d.P_src * 4 * 8) + 127) & ~127ll;
-    for (int with_priv = allow_priv ? 1 : 0; with_priv >= 0; --with_priv) {
-        const long long avail = (long long)budget - KL_CTRL_BYTES - (with_priv ? priv * KL_NC : 0);
-        const int need = with_priv && min_stages < 3 ? 3 : min_stages;
-        for (int W = KL_MAXW; W >= 16; W >>= 1) {
-            if (W > 16 && (long long)(W >> 1) >= d.B) continue;
-            const int box = ((W >> 4) * d.P_src * 128 + 1023) & ~1023;
-            const long long stage = ((long long)d.R * box + W * 4 + 1023) & ~1023ll;
-            const long long n = avail / stage;
-            if (n >= (min_stages == 1 ? 1 : need)) {
-                a->W = W;
-                a->lgW = W == 128 ? 7 : W == 64 ? 6 : W == 32 ? 5 : 4;
-                a->box = box;
-                a->stage_bytes = (int)stage;
-                a->nstages = n > KL_MAX_STAGES ? KL_MAX_STAGES : (int)n;
-                a->priv_bytes = with_priv ? (int)priv : 0;
-                return true;
-            }
+    const long long avail = (long long)budget - KL_CTRL_BYTES - priv * KL_NC;
+    for (int W = KL_MAXW; W >= 16; W >>= 1) {
+        if (W > 16 && (long long)(W >> 1) >= d.B) continue;
+        const int box = ((W >> 4) * d.P_src * 128 + 1023) & ~1023;
+        const long long stage = ((long long)d.R * box + W * 4 + 1023) & ~1023ll;
+        const long long n = avail / stage;
+        if (n >= min_stages) {
+            a->W = W;
+            a->lgW = W == 128 ? 7 : W == 64 ? 6 : W == 32 ? 5 : 4;
+            a->box = box;
+            a->stage_bytes = (int)stage;
+            a->nstages = n > KL_MAX_STAGES ? KL_MAX_STAGES : (int)n;
+            a->priv_bytes = (int)priv;
+            return true;
         }
     }
     return false;

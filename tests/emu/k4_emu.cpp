@@ -51,7 +51,8 @@ int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, floa
     KlArgs a{};
     a.d = d;
     a.ldU = d.B;
-    if (!kl_geometry(d, 228 * 1024, 1, &a, !in_stage)) return -3;
+    (void)in_stage;
+    if (!kl_geometry(d, 228 * 1024, 1, &a)) return -3;
     while (a.W > maxW) {                                       // narrower tiles on request
         a.W >>= 1;
         a.lgW -= 1;
@@ -65,6 +66,13 @@ int peel_loop(const PeelDev& d, const float2* U, long long* cj, int8_t* fk, floa
     for (int c = 0; c < d.C; ++c)
         for (int r = 0; r < d.R; ++r) blk.p[c * d.R + r] = U + ((size_t)c * d.P + (size_t)r * d.P_src) * d.B;
     std::vector<int32_t> head((size_t)d.C * d.B, 0), next((size_t)maxf * d.C, 0);
+    std::vector<unsigned int> zres((size_t)d.C * d.B, 0u);
+    std::vector<uint8_t> cls((size_t)d.C * d.B, 0);
+    std::vector<long long> dirty((size_t)d.C * d.B, 0);
+    std::vector<float> fres((size_t)maxf, 0.f);
+    unsigned long long dcount[2] = {0ull, 0ull};
+    a.zres = zres.data(); a.cls = cls.data(); a.dirty = dirty.data(); a.max_dirty = (long long)d.C * d.B;
+    a.find_res = fres.data(); a.dcount = dcount;
     std::vector<unsigned long long> multi(16, 0);
     unsigned int gbar = 0;
     int dflag = 0;
@@ -110,7 +118,7 @@ int emu_peel(int q, int n, int b, int C, int P, int P_src, int channel, int sour
     memset(seen0, 0, (size_t)d.B * sizeof(int32_t));
     const int nw = nw_of(d.ld);
     if (impl >= 2) {            // on-device loop: 2 = product's tile width, bins in shared memory; 3 = 32-bin tiles;
-                                // 4 = product's tile width, candidate work in the stage (no private column copies)
+                                // 4 = as 2 (kept for the tests' parametrisation)
         UniqOut uo{seen0, uk, usum, ucnt, ukey, unext, max_uniq};
         if (int rc = peel_loop(d, reinterpret_cast<const float2*>(U), find_cj, find_k, reinterpret_cast<float2*>(find_rho), find_round,
                                find_id, max_finds, uo, counters, impl == 3 ? 32 : 128, impl == 4))

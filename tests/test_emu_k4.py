@@ -1,5 +1,5 @@
 """CPU: the DEVICE source of the K4 kernels (qsft_b200/csrc/k4_peel.cu: classification, reduce, apply, the stand-alone
-detectors; k4_peel_loop.cu: the persistent on-device round loop as impl 2 / 3 = 128- / 32-bin tiles, 4 = candidate work in the stage instead of the private column copies; one block) executed by the SIMT emulation in tests/emu (g++, one OS thread per CUDA thread) and
+detectors; k4_peel_loop.cu: the persistent on-device round loop as impl 2 / 3 = 128- / 32-bin tiles, 4 = as 2; one block) executed by the SIMT emulation in tests/emu (g++, one OS thread per CUDA thread) and
 compared with the fixtures of the unmodified reference.  This checks the kernels' LOGIC without a GPU -- indexing,
 reductions, decisions, the round loop; it says nothing about the memory model or speed, and it is test infrastructure:
 the product has no CPU path."""

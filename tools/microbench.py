@@ -123,12 +123,6 @@ try:
     Uz = torch.zeros_like(U0)
     ms = timeit(lambda: prob.peel(Uz), flush=flush)
     out["k4 peel, device loop, all-zeroton bins (1 round)"] = {"ms": ms, "GBps": round_bytes / ms / 1e6, "frac": round_bytes / ms / 1e6 / peak}
-    os.environ["QSFT_K4_NO_PRIV"] = "1"
-    sig_np = peel_sig(U0)
-    ms = timeit(lambda: prob.peel(U0), flush=flush)
-    out["k4 peel, device loop, candidate work in the stage (QSFT_K4_NO_PRIV=1: ring slots held until a tile's last item is done)"] = {
-        "ms": ms, "same_result": sig_np[:4] == sig_dev[:4]}
-    os.environ.pop("QSFT_K4_NO_PRIV")
     os.environ["QSFT_K4_NO_TMA"] = "1"
     sig_nt = peel_sig(U0)
     ms = timeit(lambda: prob.peel(U0), flush=flush)
