@@ -771,9 +771,15 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, const KlRound& rd, int 
     const long long B = d.B;
     const long long f0 = rd.lo[p], f1 = rd.hi[p];
     const float Pf = (float)d.P;
-    for (long long f = f0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; f < f1; f += (long long)gridDim.x * blockDim.x) {
-        const long long cj = __ldcg(a.find_cj + f);
-        if (cj < 0) continue;                               // unused slot of a warp's chunk
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count: the dirty-list appends below are aggregated per warp (one atomic per warp and group instead of
+    // one per bin: hundreds of thousands of atomics on ONE counter cost more than the rest of the link phase)
+    for (long long fb = f0 + (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); fb < f1; fb += (long long)gridDim.x * blockDim.x) {
+        const long long f = fb + lane;
+        const long long cj = f < f1 ? __ldcg(a.find_cj + f) : -1;
+        unsigned fresh = 0;                                 // bit l: this thread touched bin (l, jl[l]) first in this round
+        long long jl[KL_MAX_BLOCKS];                       // C <= 16 on this path
+        if (cj >= 0) {                                      // (unused slots of a warp's chunk carry -1)
         const int c = (int)(cj / B);
         uint32_t kw[NW];
         const uint32_t* kin = reinterpret_cast<const uint32_t*>(a.find_k + (size_t)f * d.ld);
@@ -783,7 +789,6 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, const KlRound& rd, int 
         float2 sum = rho;
         int cnt = 1;
         bool first = true, last = true;
-        long long jl[KL_MAX_BLOCKS];                       // C <= 16 on this path
         float zl[KL_MAX_BLOCKS];                           // energy left in bin (c2, jl[c2]) once (k, rho) is subtracted, if known
         for (int c2 = 0; c2 < d.C; ++c2) {
             zl[c2] = __uint_as_float(0x7f800000u);           // +inf: not known without reading the bin
@@ -835,13 +840,25 @@ __device__ __forceinline__ void kl_link(const KlArgs& a, const KlRound& rd, int 
                 a.next[(size_t)f * d.C + l] = prev;
                 if (jl[l] >= a.jb && jl[l] < a.je) {
                     const float z = fmaxf(zl[l], 1e-37f);   // never 0 (0 = untouched); negative rounding noise and NaN -> tiny
-                    if (atomicMax(a.zres + bin, __float_as_uint(z)) == 0u) {
-                        const unsigned long long slot = atomicAdd(a.dcount + (round & 1), 1ull);
-                        if ((long long)slot < a.max_dirty) a.dirty[slot] = (long long)bin;
-                    }
+                    if (atomicMax(a.zres + bin, __float_as_uint(z)) == 0u) fresh |= 1u << l;
                 }
             }
-            atomicAdd(&a.counters[2], 1ull);                // num_peeling (qsft.py:224)
+            fresh |= 0x80000000u;                           // a ball was peeled
+        }
+        }
+        {
+            const unsigned m = __ballot_sync(0xffffffffu, (fresh & 0x80000000u) != 0u);
+            if (lane == 0 && m) atomicAdd(&a.counters[2], (unsigned long long)__popc(m));   // num_peeling (qsft.py:224)
+        }
+        for (int l = 0; l < d.C; ++l) {
+            const bool mine = (fresh >> l) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, mine);
+            if (m == 0u) continue;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.dcount + (round & 1), (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const long long slot = (long long)base + __popc(m & ((1u << lane) - 1u));
+            if (mine && slot < a.max_dirty) a.dirty[slot] = (long long)l * B + jl[l];
         }
     }
 }
