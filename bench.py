@@ -482,6 +482,13 @@ def run_ours(a):
         roofline["k4_peel_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                                    "bytes_per_bin_and_round": 8, "rounds": rounds, "ms_per_step": k4_ms / a.steps,
                                    "host_syncs_per_peel": 0}
+        try:                                               # DRAM bytes of one peel from the committed ncu capture (config 5 only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2", "r2z_k4_traffic.json")))
+            if (a.n, a.b, a.sparsity, a.repeat, a.gpus) == (N_DIM, B_DIM, SPARSITY, 1, 1):
+                roofline["k4_peel_hbm"]["traffic"] = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+                roofline["k4_peel_hbm"]["traffic_note"] = tj["note"]
+        except Exception:
+            pass
 
     line = {
         "metric": "q-SFT transforms/sec (sample + FFT + peel)", "value": 1e3 / ms_per_step, "unit": "transforms/s",
