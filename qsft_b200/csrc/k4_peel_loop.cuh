@@ -118,8 +118,8 @@ struct KlArgs {
 
 namespace {
 
-constexpr int KL_NS = 2;                     // scanner warps: teams of two (64 threads x two bins = a tile of 128 bins)
-constexpr int KL_NC = 13;                    // candidate warps (16 warps with the producer: 128 registers per thread; 24 warps at 80 registers measured slower -- scan 0.38 instead of 0.27 ms, whole peel 2.0 instead of 1.7 ms)
+constexpr int KL_NS = 4;                     // scanner warps: two teams of two (64 threads x two bins = a tile of 128 bins)
+constexpr int KL_NC = 11;                    // candidate warps (16 warps with the producer: 128 registers per thread; 24 warps at 80 registers measured slower -- scan 0.38 instead of 0.27 ms, whole peel 2.0 instead of 1.7 ms)
 constexpr int KL_CT = (KL_NS + KL_NC) * 32;  // threads without the TMA producer warp
 constexpr int KL_G = 8;                      // lanes per bin in the group phases
 constexpr int KL_MAXW = 128;                 // bins per tile, at most
@@ -668,7 +668,7 @@ __device__ __forceinline__ void kl_classify(const KlArgs& a, const KlBlocks& blk
             // ---- scanner warps: team = warp / 2 takes the tiles of its parity ----------------------------------------
             const int team = warp >> 1, t = threadIdx.x & 63;
             for (long long tt = blockIdx.x; tt < n_tiles; tt += gridDim.x, ++it) {
-                if ((int)(it % (unsigned)(KL_NS / 2)) != team) continue;
+                if ((int)(it & 1u) != team) continue;
                 const int st = (int)(it % (unsigned)a.nstages);
                 const uint32_t ph = (it / (unsigned)a.nstages) & 1u;
                 const int c = (int)(tt / tpg);
