@@ -119,7 +119,7 @@ struct KlArgs {
 namespace {
 
 constexpr int KL_NS = 4;                     // scanner warps: two teams of two (64 threads x two bins = a tile of 128 bins)
-constexpr int KL_NC = 11;                    // candidate warps (16 warps with the producer: 128 registers per thread; 24 warps at 80 registers measured slower -- scan 0.38 instead of 0.27 ms, whole peel 2.0 instead of 1.7 ms)
+constexpr int KL_NC = 11;                    // candidate warps (16 warps with the producer: 128 registers per thread).  Measured slower: 24 warps at 80 registers (scan 0.38 instead of 0.27 ms, whole peel 2.0 instead of 1.7 ms); one scanner team + 13 candidate warps (scan 0.47 instead of 0.31 ms, whole peel 1.12 instead of 1.05 ms)
 constexpr int KL_CT = (KL_NS + KL_NC) * 32;  // threads without the TMA producer warp
 constexpr int KL_G = 8;                      // lanes per bin in the group phases
 constexpr int KL_MAXW = 128;                 // bins per tile, at most
