@@ -1,4 +1,5 @@
-// K2L: lattice-factorised synthetic evaluation (fused K1 + K2) for q = 4 -- SURVEY section 7, option (b).
+// K2L: lattice-factorised synthetic evaluation (fused K1 + K2) for q = 4 (and q = 3, see "q = 3" below) -- SURVEY section 7,
+// option (b).
 //
 // For the query lattice m = M l + d_p the phase splits as  <k_s, M l + d_p> = <h_s, l> + <k_s, d_p>,  h_s = M^T k_s mod q.
 // With l = (l_hi, l_lo) (b1 + b2 digits) the samples of delay row p are a complex matrix product
@@ -98,7 +99,7 @@ __device__ __forceinline__ uint32_t dot4(uint32_t a, uint32_t b, int nd) {
 // per support element: bin hash halves (h_hi, h_lo) and the delay phases e[p][s] = <d_p, k_s> mod 4
 __global__ void lt_prep_kernel(const int8_t* __restrict__ M, const int8_t* __restrict__ D, const int8_t* __restrict__ loc,
                                long long S, long long Se, int n, int b, int b1, int P, int ld, uint32_t* __restrict__ hhi,
-                               uint32_t* __restrict__ hlo, uint8_t* __restrict__ e /* (P, Se), Se even */) {
+                               uint32_t* __restrict__ hlo, uint8_t* __restrict__ e /* (P, Se), Se even */, int q) {
     extern __shared__ int8_t lt_sm[];
     int8_t* sM = lt_sm;             // (n, b)
     int8_t* sD = lt_sm + n * b;     // (P, n)
@@ -114,15 +115,15 @@ __global__ void lt_prep_kernel(const int8_t* __restrict__ M, const int8_t* __res
     for (int i = 0; i < b; ++i) {
         int acc = 0;
         for (int u = 0; u < n; ++u) acc += (int)sM[u * b + i] * (int)k[u];
-        if (i < b1) hi = (hi << 2) | (uint32_t)(acc & 3);
-        else lo = (lo << 2) | (uint32_t)(acc & 3);
+        if (i < b1) hi = (hi << 2) | (uint32_t)(acc % q);
+        else lo = (lo << 2) | (uint32_t)(acc % q);
     }
     hhi[s] = hi;
     hlo[s] = lo;
     for (int p = 0; p < P; ++p) {
         int acc = 0;
         for (int u = 0; u < n; ++u) acc += (int)sD[p * n + u] * (int)k[u];
-        e[(size_t)p * Se + s] = (uint8_t)(acc & 3);
+        e[(size_t)p * Se + s] = (uint8_t)(acc % q);
     }
 }
 
@@ -387,11 +388,110 @@ __device__ __forceinline__ void ts_phase_expand(uint32_t tw, uint32_t ew, bool i
     }
 }
 
+// ---- q = 3 ---------------------------------------------------------------------------------------------------
+// The cube roots of unity are integers of Z[w], w^2 = -1 - w: w^t = (1, 0), (0, 1), (-1, -1) in the basis (1, w), and the
+// product of (a1 + b1 w) with (u + v w) is (a1 u - b1 v) + (b1 u + (a1 - b1) v) w -- a 2 x 2 integer matrix with entries
+// 0, +-1.  With that matrix in place of the real embedding of i^t, the SAME dense GEMM evaluates
+//     C_p[l_hi, l_lo] = sum_s  w^(<h_hi(s), l_hi> + e_ps)  *  x_s w^<h_lo(s), l_lo>          (a number c_1 + c_w w)
+// for a REAL strength x_s: A' rows = (1-part, w-part) per l_hi, K' = (u, v) per support element, limbs of x_s as for q = 4.
+// Two launches (x = Re a, x = Im a) give the complex coefficients c_1, c_w, and
+//     X = c_1 + c_w w,  w = -1/2 + i sqrt(3)/2
+// is formed by lt_combine3_kernel.  No 2:4 structure here (three of the four matrix entries can be non-zero): dense MMA.
+__device__ __forceinline__ uint32_t lt_pack3(uint32_t l, int nd) {        // base-3 digits of l, two bits each, digit 0 lowest
+    uint32_t out = 0;
+    for (int i = 0; i < nd; ++i) {
+        out |= (l % 3u) << (2 * i);
+        l /= 3u;
+    }
+    return out;
+}
+__device__ __forceinline__ uint32_t lt_dot3(uint32_t a, uint32_t b, int nd) {   // sum of digit products mod 3
+    uint32_t acc = 0;
+    for (int i = 0; i < nd; ++i) acc += ((a >> (2 * i)) & 3u) * ((b >> (2 * i)) & 3u);
+    return acc % 3u;
+}
+
+// A'[(p * Mhi + l_hi) * 2 + e][2 s + k']: row e of the matrix of w^t, t = (<h_hi(s), l_hi> + e[p][s]) mod 3:
+//   t = 0: (1, 0 | 0, 1)   t = 1: (0, -1 | 1, -1)   t = 2: (-1, 1 | -1, 0)
+__global__ void __launch_bounds__(256)
+lt_agen3_kernel(const uint32_t* __restrict__ hhi, const uint8_t* __restrict__ e, long long S, long long Se, int b1, int P,
+                long long Mhi, long long Kp, uint32_t* __restrict__ A) {
+    const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // two support elements = 4 K' bytes
+    const uint32_t lhi = blockIdx.y;
+    if (pair * 4 >= Kp) return;
+    const long long s0 = 2 * pair;
+    const bool live0 = s0 < S, live1 = s0 + 1 < S;
+    const uint32_t lp = lt_pack3(lhi, b1);
+    const uint32_t t0 = live0 ? lt_dot3(hhi[s0], lp, b1) : 0u;
+    const uint32_t t1 = live1 ? lt_dot3(hhi[s0 + 1], lp, b1) : 0u;
+    // byte pairs (k' = 0 low byte) per t: row 0 = 01 00 | 00 FF | FF 01, row 1 = 00 01 | 01 FF | FF 00
+    constexpr unsigned long long kR0 = 0x000001FFFF000001ull, kR1 = 0x000000FFFF010100ull;
+    const size_t row_words = (size_t)Kp / 4;
+    uint32_t* out = A + ((size_t)(2 * lhi)) * row_words + pair;
+    for (int p = 0; p < P; ++p) {
+        uint32_t w0 = 0, w1 = 0;
+        if (live0) {
+            const uint32_t r0 = (t0 + e[(size_t)p * Se + s0]) % 3u;
+            w0 = (uint32_t)(kR0 >> (16 * r0)) & 0xffffu;
+            w1 = (uint32_t)(kR1 >> (16 * r0)) & 0xffffu;
+            if (live1) {
+                const uint32_t r1 = (t1 + e[(size_t)p * Se + s0 + 1]) % 3u;
+                w0 |= ((uint32_t)(kR0 >> (16 * r1)) & 0xffffu) << 16;
+                w1 |= ((uint32_t)(kR1 >> (16 * r1)) & 0xffffu) << 16;
+            }
+        }
+        uint32_t* o = out + (size_t)p * (size_t)(2 * Mhi) * row_words;
+        o[0] = w0;
+        o[row_words] = w1;
+    }
+}
+
+// B'_l[l_lo][2 s + k'] = limb l of x_s * (alpha, beta)[k'], (alpha, beta) = w^<h_lo(s), l_lo> in the basis (1, w);
+// x_s = Re a_s (part 0) or Im a_s (part 1).  Balanced limbs negate digit by digit, so -x has the negated limbs.
+__global__ void __launch_bounds__(256)
+lt_bgen3_kernel(const uint32_t* __restrict__ hlo, const int2* __restrict__ alimb, long long S, int b2, long long Nlo,
+                long long Kp, int part, uint32_t* __restrict__ Bq) {
+    const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long llo = blockIdx.y;
+    if (pair * 4 >= Kp) return;
+    const long long s0 = 2 * pair;
+    const uint32_t lp = lt_pack3((uint32_t)llo, b2);
+    uint32_t words[3] = {0u, 0u, 0u};
+    for (int h = 0; h < 2; ++h) {
+        const long long s = s0 + h;
+        if (s >= S) break;
+        const int2 w = alimb[s];
+        const uint32_t lw = part ? (uint32_t)w.y : (uint32_t)w.x;
+        const uint32_t t = lt_dot3(hlo[s], lp, b2);
+        const int al = t == 0 ? 1 : t == 1 ? 0 : -1, be = t == 0 ? 0 : t == 1 ? 1 : -1;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const int limb = (int)(int8_t)((lw >> (8 * l)) & 0xffu);
+            words[l] |= (((uint32_t)(al * limb) & 0xffu) | (((uint32_t)(be * limb) & 0xffu) << 8)) << (16 * h);
+        }
+    }
+    const size_t row_words = (size_t)Kp / 4;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) Bq[((size_t)l * Nlo + (size_t)llo) * row_words + pair] = words[l];
+}
+
+// X = c_1 + c_w w with cre = (Re c_1, Re c_w) and cim = (Im c_1, Im c_w) per sample
+__global__ void lt_combine3_kernel(const float2* __restrict__ cre, const float2* __restrict__ cim, long long N, float2* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float2 r = cre[i], m = cim[i];
+    const float h = 0.86602540378443864676f;
+    out[i] = make_float2(r.x - 0.5f * r.y - h * m.y, m.x - 0.5f * m.y + h * r.y);
+}
+
 // ---- the GEMM ---------------------------------------------------------------------------------------------
 // Dense cross-check kernel (QSFT_LATTICE_SPARSE=0): A' materialised in HBM by lt_agen_kernel, cta_group::1.
+// RAGGED (q = 3: 2 * Mhi and Nlo are powers of three): the row / column counts need not be multiples of the tile; the TMA
+// boxes read zeros (or, between the limb blocks of B', a neighbour's rows) beyond the edge and the epilogue masks its stores.
+template <bool RAGGED>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int nkb, int Mhi, int Nlo,
-               const float* __restrict__ inv_scale_ptr, float2* __restrict__ out, int accumulate) {
+               const float* __restrict__ inv_scale_ptr, float2* __restrict__ out, int accumulate, long long total_rows) {
     extern __shared__ uint8_t lt_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)lt_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)LT_STAGES * LT_STAGE_BYTES);
@@ -479,6 +579,7 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         float2* orow = out + ((size_t)p * Mhi + lhi) * Nlo + llo0;
+        const bool row_ok = !RAGGED || grow < total_rows;
 #pragma unroll 1
         for (int ch = 0; ch < LT_BN / 16; ++ch) {
             uint32_t a0[16], a1[16], a2[16];
@@ -500,15 +601,31 @@ lt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
                 o[j] = odd ? make_float2(recv, val[8 + j]) : make_float2(val[j], recv);
             }
-            float4* dst = reinterpret_cast<float4*>(orow + ch * 16 + (odd ? 8 : 0));
+            if (RAGGED) {
+                const int col0 = llo0 + ch * 16 + (odd ? 8 : 0);
+                float2* dst = orow + ch * 16 + (odd ? 8 : 0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 w = make_float4(o[2 * j].x, o[2 * j].y, o[2 * j + 1].x, o[2 * j + 1].y);
-                if (accumulate) {                               // residual pass: onto the first pass's samples
-                    const float4 p = dst[j];
-                    w = make_float4(p.x + w.x, p.y + w.y, p.z + w.z, p.w + w.w);
+                for (int j = 0; j < 8; ++j) {
+                    if (row_ok && col0 + j < Nlo) {
+                        float2 w = o[j];
+                        if (accumulate) {
+                            const float2 pv = dst[j];
+                            w = make_float2(pv.x + w.x, pv.y + w.y);
+                        }
+                        dst[j] = w;
+                    }
                 }
-                dst[j] = w;
+            } else {
+                float4* dst = reinterpret_cast<float4*>(orow + ch * 16 + (odd ? 8 : 0));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 w = make_float4(o[2 * j].x, o[2 * j].y, o[2 * j + 1].x, o[2 * j + 1].y);
+                    if (accumulate) {                               // residual pass: onto the first pass's samples
+                        const float4 p = dst[j];
+                        w = make_float4(p.x + w.x, p.y + w.y, p.z + w.z, p.w + w.w);
+                    }
+                    dst[j] = w;
+                }
             }
         }
     }
@@ -826,23 +943,143 @@ int lt_make_map(CUtensorMap* map, const void* ptr, long long rows, long long kby
 }  // namespace
 
 extern "C" int qsft_eval_lattice_supported(int q, int n, int b, int P, int64_t S) {
-    if (q != 4 || n < 1 || n > QSFT_MAX_N || P < 1 || S < 1) return 0;
+    if (n < 1 || n > QSFT_MAX_N || P < 1 || S < 1) return 0;
     const int b1 = b / 2, b2 = b - b1;
+    if (q == 3) {                                            // dense Z[w] variant, ragged tiles
+        if (b1 < 3 || b2 < 4 || b2 > 10 || b > 20) return 0;   // packed digits fit 32 bits; 3 * 3^b2 >= 128 rows of B'
+        const long long Mhi = ipow64(3, b1), Nlo = ipow64(3, b2);
+        if ((long long)P * Mhi * 2 < LT_BM || (long long)P * Mhi * 2 >= 0x7fffffffLL || Nlo > 65535) return 0;
+        return 1;
+    }
+    if (q != 4) return 0;
     if (b1 < 3 || b2 < 4 || b > 14) return 0;                // 2 * 4^b1 >= 128 rows, 4^b2 >= 256 columns, grid.y limits
     if ((long long)P * ipow64(4, b1) * 2 >= 0x7fffffffLL) return 0;
     return 1;
 }
+
+namespace {
+
+// q = 3 (see "q = 3" above): prep as for q = 4, A' materialised in HBM per chunk of delay rows, two dense GEMM launches per
+// pass (real / imaginary parts of the strengths) into two scratch planes, then the combination X = c_1 + c_w w.
+int lt_eval_q3(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths, int64_t S, int n, int b, int P, int ld,
+               float* out, int residual_passes, cudaStream_t st) {
+    const int q = 3, b1 = b / 2, b2 = b - b1;
+    const long long Mhi = ipow64(3, b1), Nlo = ipow64(3, b2), Bn = Mhi * Nlo;
+    const long long Kp = (2 * S + LT_BK - 1) / LT_BK * LT_BK;
+    double budget_gb = 8.0;
+    if (const char* env = getenv("QSFT_LATTICE_SCRATCH_GB")) {
+        const double v = atof(env);
+        if (v > 0.0) budget_gb = v;
+    }
+    long long Pc = (long long)(budget_gb * 1e9 / (2.0 * (double)Mhi * (double)Kp));
+    if (Pc < 1) Pc = 1;
+    if (Pc > P) Pc = P;
+    while ((Pc * 2 * Mhi + LT_BM - 1) / LT_BM > 65535) --Pc;
+    uint32_t *hhi = nullptr, *hlo = nullptr;
+    uint8_t *e = nullptr, *A = nullptr, *Bq = nullptr;
+    int2* alimb = nullptr;
+    unsigned int* amax = nullptr;
+    float2* planes = nullptr;
+    int rc = QSFT_OK;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (rc == QSFT_OK && qsft_scratch_alloc(p, bytes, st) != cudaSuccess) {
+            qsft_set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+            rc = QSFT_ECUDA;
+        }
+    };
+    const long long Se = (S + 3) & ~3ll;
+    alloc((void**)&hhi, (size_t)S * 4);
+    alloc((void**)&hlo, (size_t)S * 4);
+    alloc((void**)&e, (size_t)P * Se);
+    alloc((void**)&alimb, (size_t)S * 8);
+    alloc((void**)&amax, 16);
+    alloc((void**)&A, (size_t)Pc * 2 * Mhi * Kp);
+    alloc((void**)&Bq, (size_t)2 * LT_LIMBS * Nlo * Kp);                     // real-part and imaginary-part operand
+    alloc((void**)&planes, (size_t)2 * Pc * Bn * sizeof(float2));
+    float* inv_scale = amax ? reinterpret_cast<float*>(amax + 2) : nullptr;
+    if (rc == QSFT_OK) {
+        const int T = 256;
+        const unsigned sb = (unsigned)((S + T - 1) / T);
+        const unsigned int init[2] = {0u, 0x7f7fffffu};
+        cudaMemcpyAsync(amax, init, 8, cudaMemcpyHostToDevice, st);
+        lt_prep_kernel<<<sb, T, (size_t)n * b + (size_t)P * n, st>>>(M, D, loc, S, Se, n, b, b1, P, ld, hhi, hlo, e, q);
+        lt_amax_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax);
+        g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
+        int passes = 1 + (residual_passes > 0 ? 1 : 0);
+        if (residual_passes < 0) {
+            lt_amin_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax + 1);
+            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+            float mm[2] = {0.f, 0.f};
+            if (cudaMemcpyAsync(mm, amax, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+                qsft_set_error("reading the strength range failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = QSFT_ECUDA;
+            }
+            if (mm[1] < 0.1f * mm[0]) passes = 2;
+        }
+        static bool attr = false;
+        if (!attr && !rc) {
+            if (cudaFuncSetAttribute(lt_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess) {
+                qsft_set_error("cudaFuncSetAttribute failed");
+                rc = QSFT_ECUDA;
+            }
+            attr = true;
+        }
+        const unsigned pb = (unsigned)((Kp / 4 + T - 1) / T);
+        uint8_t* Bre = Bq;
+        uint8_t* Bim = Bq + (size_t)LT_LIMBS * Nlo * Kp;
+        CUtensorMap ma, mbr, mbi;
+        if (!rc) rc = lt_make_map(&mbr, Bre, LT_LIMBS * Nlo, Kp);
+        if (!rc) rc = lt_make_map(&mbi, Bim, LT_LIMBS * Nlo, Kp);
+        for (long long p0 = 0; p0 < P && !rc; p0 += Pc) {
+            const long long pc = (P - p0 < Pc) ? (P - p0) : Pc;
+            const long long rows = pc * 2 * Mhi;
+            lt_agen3_kernel<<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, e + (size_t)p0 * Se, S, Se, b1, (int)pc, Mhi, Kp,
+                                                                   reinterpret_cast<uint32_t*>(A));
+            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+            rc = lt_make_map(&ma, A, rows, Kp);
+            if (rc) break;
+            float2* cre = planes;
+            float2* cim = planes + (size_t)pc * Bn;
+            for (int pass = 0; pass < passes && !rc; ++pass) {
+                lt_quant_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax, inv_scale, alimb, pass);
+                lt_bgen3_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp, 0, reinterpret_cast<uint32_t*>(Bre));
+                lt_bgen3_kernel<<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp, 1, reinterpret_cast<uint32_t*>(Bim));
+                dim3 grid((unsigned)((Nlo + LT_BN - 1) / LT_BN), (unsigned)((rows + LT_BM - 1) / LT_BM));
+                lt_gemm_kernel<true><<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mbr, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo,
+                                                                          (const float*)(inv_scale + pass), cre, pass, rows);
+                lt_gemm_kernel<true><<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mbi, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo,
+                                                                          (const float*)(inv_scale + pass), cim, pass, rows);
+                g_qsft_launches.fetch_add(5, std::memory_order_relaxed);
+            }
+            const long long N = pc * Bn;
+            lt_combine3_kernel<<<(unsigned)((N + T - 1) / T), T, 0, st>>>(cre, cim, N, reinterpret_cast<float2*>(out) + (size_t)p0 * Bn);
+            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+            cudaError_t ce = cudaGetLastError();
+            if (ce != cudaSuccess) {
+                qsft_set_error("lattice GEMM (q = 3) launch failed: %s", cudaGetErrorString(ce));
+                rc = QSFT_ECUDA;
+            }
+        }
+    }
+    void* frees[] = {hhi, hlo, e, alimb, amax, A, Bq, planes};
+    for (void* p : frees)
+        if (p) cudaFreeAsync(p, st);
+    return rc;
+}
+
+}  // namespace
 
 // residual_passes: 0 = one GEMM pass (20 bits below max|a|), 1 = a second pass over the quantisation residual accumulated
 // onto the first (41 bits; twice the tensor work), -1 = decide here: second pass iff min|a| < 0.1 max|a| (reads two floats
 // back, i.e. synchronises the stream once).
 extern "C" int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths, int64_t S,
                                           int q, int n, int b, int P, int ld, float* out, int residual_passes, void* stream) {
-    QSFT_CHECK_ARG(qsft_eval_lattice_supported(q, n, b, P, S), "lattice evaluation supports q = 4, 7 <= b <= 14 only");
+    QSFT_CHECK_ARG(qsft_eval_lattice_supported(q, n, b, P, S), "lattice evaluation supports q = 4 with 7 <= b <= 14 and q = 3 with 7 <= b <= 20 only");
     QSFT_CHECK_ARG(M && D && loc && strengths && out, "null pointer");
     QSFT_CHECK_ARG(ld >= n && ld % 16 == 0, "bad ld");
     QSFT_CHECK_ARG(residual_passes >= -1 && residual_passes <= 1, "residual_passes must be -1 (auto), 0 or 1");
     cudaStream_t st = (cudaStream_t)stream;
+    if (q == 3) return lt_eval_q3(M, D, loc, strengths, S, n, b, P, ld, out, residual_passes, st);
     const int b1 = b / 2, b2 = b - b1;
     const long long Mhi = ipow64(4, b1), Nlo = ipow64(4, b2);
     // Default: 2:4 structured-sparse A' generated straight into tensor memory (tcgen05.mma.sp on CTA pairs; A' never exists
@@ -896,7 +1133,7 @@ extern "C" int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, cons
         const unsigned sb = (unsigned)((S + T - 1) / T);
         const unsigned int init[2] = {0u, 0x7f7fffffu};
         cudaMemcpyAsync(amax, init, 8, cudaMemcpyHostToDevice, st);
-        lt_prep_kernel<<<sb, T, (size_t)n * b + (size_t)P * n, st>>>(M, D, loc, S, Se, n, b, b1, P, ld, hhi, hlo, e);
+        lt_prep_kernel<<<sb, T, (size_t)n * b + (size_t)P * n, st>>>(M, D, loc, S, Se, n, b, b1, P, ld, hhi, hlo, e, q);
         lt_amax_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax);
         g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
         int passes = 1 + (residual_passes > 0 ? 1 : 0);
@@ -924,7 +1161,7 @@ extern "C" int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, cons
         if (!rc) {
             static bool attr = false;
             if (!attr) {
-                if (cudaFuncSetAttribute(lt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
+                if (cudaFuncSetAttribute(lt_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess ||
                     cudaFuncSetAttribute(lt_gemm_spts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess ||
                     cudaFuncSetAttribute(lt_gemm_spts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess ||
                     cudaFuncSetAttribute(lt_gemm_spts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess ||
@@ -972,8 +1209,8 @@ extern "C" int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, cons
                                                                           reinterpret_cast<uint32_t*>(A));
                     rc = lt_make_map(&ma, A, pc * 2 * Mhi, Kp);
                     if (rc) break;
-                    lt_gemm_kernel<<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo,
-                                                                      (const float*)(inv_scale + pass), o, pass);
+                    lt_gemm_kernel<false><<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo,
+                                                                             (const float*)(inv_scale + pass), o, pass, pc * 2 * Mhi);
                     g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
                 }
                 cudaError_t ce = cudaGetLastError();

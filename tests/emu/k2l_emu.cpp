@@ -9,9 +9,31 @@
 extern "C" {
 
 int emu_lt_prep(const int8_t* M, const int8_t* D, const int8_t* loc, long long S, long long Se, int n, int b, int b1, int P,
-                int ld, uint32_t* hhi, uint32_t* hlo, uint8_t* e) {
+                int ld, uint32_t* hhi, uint32_t* hlo, uint8_t* e, int q) {
     const int T = 256;
-    emu::launch(dim3((unsigned)((S + T - 1) / T)), dim3(T), [&]() { lt_prep_kernel(M, D, loc, S, Se, n, b, b1, P, ld, hhi, hlo, e); });
+    emu::launch(dim3((unsigned)((S + T - 1) / T)), dim3(T), [&]() { lt_prep_kernel(M, D, loc, S, Se, n, b, b1, P, ld, hhi, hlo, e, q); });
+    return 0;
+}
+
+// q = 3: dense operands over Z[w] and the final combination
+int emu_lt_agen3(const uint32_t* hhi, const uint8_t* e, long long S, long long Se, int b1, int P, long long Mhi, long long Kp,
+                 uint32_t* A) {
+    const int T = 256;
+    emu::launch(dim3((unsigned)((Kp / 4 + T - 1) / T), (unsigned)Mhi), dim3(T),
+                [&]() { lt_agen3_kernel(hhi, e, S, Se, b1, P, Mhi, Kp, A); });
+    return 0;
+}
+int emu_lt_bgen3(const uint32_t* hlo, const int32_t* alimb, long long S, int b2, long long Nlo, long long Kp, int part, uint32_t* Bq) {
+    const int T = 256;
+    emu::launch(dim3((unsigned)((Kp / 4 + T - 1) / T), (unsigned)Nlo), dim3(T),
+                [&]() { lt_bgen3_kernel(hlo, reinterpret_cast<const int2*>(alimb), S, b2, Nlo, Kp, part, Bq); });
+    return 0;
+}
+int emu_lt_combine3(const float* cre, const float* cim, long long N, float* out) {
+    const int T = 256;
+    emu::launch(dim3((unsigned)((N + T - 1) / T)), dim3(T), [&]() {
+        lt_combine3_kernel(reinterpret_cast<const float2*>(cre), reinterpret_cast<const float2*>(cim), N, reinterpret_cast<float2*>(out));
+    });
     return 0;
 }
 

@@ -20,7 +20,10 @@ import build_emu  # noqa: E402
 def emu():
     L = C.CDLL(build_emu.build(which="k2l"))
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_longlong
-    L.emu_lt_prep.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.emu_lt_prep.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp, vp, i32]
+    L.emu_lt_agen3.argtypes = [vp, vp, i64, i64, i32, i32, i64, i64, vp]
+    L.emu_lt_bgen3.argtypes = [vp, vp, i64, i32, i64, i64, i32, vp]
+    L.emu_lt_combine3.argtypes = [vp, vp, i64, vp]
     L.emu_lt_quant.argtypes = [vp, i64, vp, vp, C.c_int]
     L.emu_lt_bgen.argtypes = [vp, vp, i64, i32, i64, i64, vp]
     L.emu_lt_ttab.argtypes = [vp, i64, i32, i64, i64, vp]
@@ -51,7 +54,7 @@ def test_emulated_lattice_operands_reproduce_the_samples(emu, n, b, S, P, seed):
     loc[:, :n] = locq.T
     hhi, hlo = np.zeros(S, dtype=np.uint32), np.zeros(S, dtype=np.uint32)
     e = np.zeros((P, Se), dtype=np.uint8)
-    assert emu.emu_lt_prep(_p(M8), _p(D8), _p(loc), S, Se, n, b, b1, P, ld, _p(hhi), _p(hlo), _p(e)) == 0
+    assert emu.emu_lt_prep(_p(M8), _p(D8), _p(loc), S, Se, n, b, b1, P, ld, _p(hhi), _p(hlo), _p(e), q) == 0
     # bin-hash halves and delay phases against their definitions
     H = (M.T @ locq) % q                                                   # (b, S) digits of M^T k, MSB first
     want_hi = sum(H[i].astype(np.int64) << (2 * (b1 - 1 - i)) for i in range(b1))
@@ -110,6 +113,57 @@ def test_emulated_lattice_operands_reproduce_the_samples(emu, n, b, S, P, seed):
     assert np.array_equal(pairs[:, :, 1, :, 0], ei) and np.array_equal(pairs[:, :, 1, :, 1], er)
     lhi_d = np.stack([(np.arange(Mhi) >> (2 * (b1 - 1 - i))) & 3 for i in range(b1)])     # (b1, Mhi) MSB first
     assert np.array_equal(Tf, (lhi_d.T @ H[:b1]) % 4)
+
+
+@pytest.mark.parametrize("n,b,S,P,seed", [(12, 5, 37, 4, 0), (30, 6, 61, 3, 1), (9, 4, 8, 2, 2)])
+def test_emulated_q3_lattice_operands_reproduce_the_samples(emu, n, b, S, P, seed):
+    """q = 3: the Z[w] operands (lt_agen3 / lt_bgen3) with an exact integer matrix product in place of the tensor-core GEMM,
+    the two real launches and lt_combine3 reproduce the samples of the lattice {M l + d_p} from the definition."""
+    q = 3
+    rng = np.random.default_rng(seed)
+    M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
+    locq = rng.integers(0, q, (n, S))
+    a = rng.uniform(0.3, 2, S) * np.exp(1j * rng.uniform(0, 2 * np.pi, S))
+    b1, b2 = b // 2, b - b // 2
+    Mhi, Nlo = q ** b1, q ** b2
+    ld = max(32, (n + 31) // 32 * 32)
+    Kp = (2 * S + 127) // 128 * 128
+    Se = (S + 3) & ~3
+    M8, D8 = np.ascontiguousarray(M, dtype=np.int8), np.ascontiguousarray(D, dtype=np.int8)
+    loc = np.zeros((S, ld), dtype=np.int8)
+    loc[:, :n] = locq.T
+    hhi, hlo = np.zeros(S, dtype=np.uint32), np.zeros(S, dtype=np.uint32)
+    e = np.zeros((P, Se), dtype=np.uint8)
+    assert emu.emu_lt_prep(_p(M8), _p(D8), _p(loc), S, Se, n, b, b1, P, ld, _p(hhi), _p(hlo), _p(e), q) == 0
+    H = (M.T @ locq) % q
+    assert np.array_equal(hhi, sum(H[i].astype(np.int64) << (2 * (b1 - 1 - i)) for i in range(b1)))
+    assert np.array_equal(hlo, sum(H[b1 + i].astype(np.int64) << (2 * (b2 - 1 - i)) for i in range(b2)))
+    assert np.array_equal(e[:, :S], (D @ locq) % q)
+    a32 = np.ascontiguousarray(a.astype(np.complex64))
+    inv_scale = np.zeros(2, dtype=np.float32)
+    alimb = np.zeros((S, 2), dtype=np.int32)
+    assert emu.emu_lt_quant(_p(a32), S, _p(inv_scale), _p(alimb), 0) == 0
+    limbs = alimb.view(np.int8).reshape(S, 2, 4)[:, :, :3].astype(np.int64)
+    vq = (limbs[:, :, 0] * 128 + limbs[:, :, 1]) * 128 + limbs[:, :, 2]
+    aq = (vq[:, 0] + 1j * vq[:, 1]) * float(inv_scale[0])
+    A = np.zeros((P, Mhi, 2, Kp), dtype=np.int8)
+    assert emu.emu_lt_agen3(_p(hhi), _p(e), S, Se, b1, P, Mhi, Kp, _p(A)) == 0
+    assert set(np.unique(A)) <= {-1, 0, 1} and not A[..., 2 * S:].any()
+    planes = []
+    for part in (0, 1):
+        Bq = np.zeros((3, Nlo, Kp), dtype=np.int8)
+        assert emu.emu_lt_bgen3(_p(hlo), _p(alimb), S, b2, Nlo, Kp, part, _p(Bq)) == 0
+        assert not Bq[..., 2 * S:].any() and np.abs(Bq).max() <= 64
+        acc = np.einsum("pmrk,lnk->lpmrn", A.astype(np.int64), Bq.astype(np.int64))
+        val = ((acc[0] * 128 + acc[1]) * 128 + acc[2]) * float(inv_scale[0])        # (P, Mhi, 2 = (1, w) parts, Nlo)
+        planes.append(np.ascontiguousarray(np.moveaxis(val, 2, 3).reshape(-1, 2).astype(np.float32)))   # float2 = (c_1, c_w)
+    N = P * Mhi * Nlo
+    out = np.zeros((N, 2), dtype=np.float32)
+    assert emu.emu_lt_combine3(_p(planes[0]), _p(planes[1]), N, _p(out)) == 0
+    got = (out[:, 0] + 1j * out[:, 1]).reshape(P, Mhi * Nlo)
+    dig = orc.query_digits(M, D, q)
+    want = np.stack([orc.synth_eval_digits(dig[p].T, locq, aq, q) for p in range(P)])
+    assert np.max(np.abs(got - want)) <= 2e-6 * np.sqrt(S) * float(np.max(np.abs(a)))        # fp32 planes + combination
 
 
 def test_ts_expand_variants_match_the_definition(emu):

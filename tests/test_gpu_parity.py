@@ -337,8 +337,38 @@ def test_k2_lattice_matches_plain_path_and_oracle(n, b, S, P, seed, mode, monkey
     assert np.max(np.abs(got[P - 1].cpu().numpy()[ls] - want)) <= 3e-6 * scale + 2e-6 * float(np.max(np.abs(a))) * np.sqrt(S)
 
 
+@pytest.mark.parametrize("n,b,S,P,seed,a_lo", [(12, 7, 300, 4, 0, 1.0), (30, 8, 5000, 9, 1, 1.0), (20, 9, 777, 3, 2, 0.01), (16, 8, 1, 5, 3, 1.0)])
+def test_k2_lattice_q3_matches_oracle_and_plain_path(n, b, S, P, seed, a_lo):
+    """q = 3 lattice evaluation (dense tcgen05 GEMM over Z[w] coefficients, ragged tiles, two real launches + combination)
+    against the plain K1 + K2 path on the whole lattice and against the fp64 oracle on a sample of it; a_lo = 0.01 takes the
+    residual pass."""
+    q = 3
+    rng = np.random.RandomState(seed)
+    M = rng.randint(0, q, size=(n, b))
+    D = rng.randint(0, q, size=(P, n))
+    loc = rng.randint(0, q, size=(S, n))
+    a = (rng.uniform(a_lo, 1.0, S) * np.exp(2j * np.pi * rng.uniform(0, 1, S))).astype(np.complex64)
+    ld = utils.padded_ld(n)
+    loc_d = ops.pad_digits(loc, ld, DEV)
+    a_d = torch.from_numpy(a).to(DEV)
+    assert ops.lattice_supported(q, n, b, P, S)
+    got = ops.eval_synth_lattice(M, D, loc_d, a_d, q).cpu().numpy()
+    _, dig = ops.query_lattice(M, D, q, device=DEV, want_idx=False, want_digits=True, ld=ld)
+    plain = ops.eval_synth(dig.view(P * q ** b, ld), loc_d, a_d, q, n).view(P, q ** b).cpu().numpy()
+    scale = float(np.sqrt(np.sum(np.abs(a) ** 2)))
+    assert np.max(np.abs(got - plain)) <= 3e-6 * scale + 2e-6 * float(np.max(np.abs(a))) * np.sqrt(S)
+    ls = rng.randint(0, q ** b, size=400)
+    L = np.array([[(l // q ** (b - 1 - i)) % q for i in range(b)] for l in ls]).T
+    for p in (0, P - 1):
+        qd = (((M @ L) % q + D[p][:, None]) % q).T
+        want = orc.synth_eval_digits(qd, loc.T, a, q)
+        assert np.max(np.abs(got[p][ls] - want)) <= 3e-6 * scale + 2e-6 * float(np.max(np.abs(a))) * np.sqrt(S)
+
+
 def test_k2_lattice_unsupported_shapes():
-    assert not ops.lattice_supported(3, 10, 8, 3, 100)       # q != 4
+    assert not ops.lattice_supported(5, 10, 8, 3, 100)       # q = 3 and q = 4 only
+    assert not ops.lattice_supported(3, 10, 6, 3, 100)       # q = 3: b too small
+    assert ops.lattice_supported(3, 10, 8, 3, 100)
     assert not ops.lattice_supported(4, 10, 4, 3, 100)       # b too small
     loc = torch.zeros((4, 32), dtype=torch.int8, device=DEV)
     a = torch.ones(4, dtype=torch.complex64, device=DEV)
