@@ -61,7 +61,10 @@ int qsft_eval_synth(const int8_t* qdig, int64_t N, const int8_t* loc, const floa
  * <= 2^-21 max|a| per coefficient), int32 accumulation (UTCIMMA kind::i8), limbs recombined in the epilogue.
  *   M (n, b) int8, D (P, n) int8 (unpadded, as for qsft_query_lattice), loc (S, ld) int8, strengths (S) complex64,
  *   out (P, q^b) complex64.  Allocates stream-ordered scratch (cudaMallocAsync): ~ 6 S P q^ceil(b/2) bytes.
- * qsft_eval_lattice_supported returns 1 when the shape is handled (q == 4, 7 <= b <= 14). */
+ * q = 3 (7 <= b <= 20): the cube roots of unity are integers of Z[w] (w^2 = -1 - w), i.e. 2 x 2 integer matrices with entries
+ * 0, +-1 in the basis (1, w): the same factorisation runs as a DENSE int8 GEMM (no 2:4 structure), once for the real and once
+ * for the imaginary parts of the strengths, and X = c_1 + c_w w is formed afterwards.
+ * qsft_eval_lattice_supported returns 1 when the shape is handled (q == 4: 7 <= b <= 14; q == 3: 7 <= b <= 20). */
 int qsft_eval_lattice_supported(int q, int n, int b, int P, int64_t S);
 int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths, int64_t S,
                             int q, int n, int b, int P, int ld, float* out, void* stream);
