@@ -11,7 +11,7 @@ import time
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .input_signal_subsampled import SubsampledSignal
 from .result import PendingSpectrum, SparseSpectrum
 from .utils import calc_hamming_weight, sort_qary_vecs
@@ -84,11 +84,28 @@ class QSFT:
         # output="device_async": nothing is read back -- the peel is queued behind the sampling and transform kernels and the
         # call returns a PendingSpectrum; a stream of transforms then keeps the GPU busy while the host prepares the next one
         wait = output != "device_async"
+        # find list: 4 C B slots cover every case seen; the reference has no limit (up to C B singletons per round, 15 rounds),
+        # so a peel that runs out of slots is repeated once with the true bound -- the on-device loop never modifies the bins
+        # (asynchronous calls report the overflow from PendingSpectrum.wait() instead)
+        small, full = min(15 * C * B, max(4096, 4 * C * B)), 15 * C * B
+        small = min(full, int(kwargs.get("max_finds", small)))       # (kwarg: first allocation of the find list)
+
+        def with_retry(run):
+            try:
+                prob.alloc(max_finds=small, max_uniq=max(4096, C * B), reuse=True)
+                return run()
+            except _lib.QsftError as exc:
+                if "find buffer too small" not in str(exc) or small == full or not wait:
+                    raise
+                prob.alloc(max_finds=full, max_uniq=max(4096, C * B), reuse=True)
+                return run()
+
         if shard == "device":
-            prob.alloc(max_finds=min(15 * C * B, max(4096, 4 * C * B)), max_uniq=max(4096, C * B), reuse=True)
             blocks = [u if isinstance(u, torch.Tensor) else torch.as_tensor(u, device=dev) for us in Us for u in us]
             if all(t.is_cuda and t.dtype == torch.complex64 and t.is_contiguous() for t in blocks):
-                n_rounds = prob.peel_blocks_sharded(blocks, dist, wait=wait)
+                n_rounds = with_retry(lambda: prob.peel_blocks_sharded(blocks, dist, wait=wait))
+            else:
+                prob.alloc(max_finds=small, max_uniq=max(4096, C * B), reuse=True)
             n_finds = -1
             if n_rounds is None:                         # shape / platform does not fit: every rank agrees (same inputs)
                 if not getattr(signal, "Us_complete", True):
@@ -100,11 +117,11 @@ class QSFT:
             n_rounds = peel_sharded(prob, stacked(), dist)[4]
             n_finds = -1
         elif n_rounds is None:
-            prob.alloc(max_finds=min(15 * C * B, max(4096, 4 * C * B)), max_uniq=max(4096, C * B), reuse=True)
             # the on-device loop reads the blocks get_MDU returned where they lie (no copy)
             blocks = [u if isinstance(u, torch.Tensor) else torch.as_tensor(u, device=dev) for us in Us for u in us]
             fits = all(t.is_cuda and t.dtype == torch.complex64 and t.is_contiguous() for t in blocks)
-            done = prob.peel_blocks(blocks, wait=wait) if fits else None
+            prob.alloc(max_finds=small, max_uniq=max(4096, C * B), reuse=True)
+            done = with_retry(lambda: prob.peel_blocks(blocks, wait=wait)) if fits else None
             if done is None and not wait:
                 raise ValueError("output='device_async' needs bins the on-device loop can read in place (C * R <= 16, "
                                  "contiguous complex64 CUDA blocks)")

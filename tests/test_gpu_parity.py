@@ -400,6 +400,23 @@ def test_construct_and_transform_all_eval_impls_agree(impl):
     assert np.allclose(arr["values"], np.array(list(res.values())), rtol=0, atol=1e-6)
 
 
+def test_transform_repeats_the_peel_when_the_find_list_is_too_small():
+    """The reference has no limit on the number of singletons; a find list that runs out of slots is grown to the true bound
+    (15 C B) and the peel repeated -- the on-device loop leaves the bins untouched, so the second run sees the same data."""
+    n, q, b, C, R, S = 14, 4, 5, 3, 1, 400
+    qa = {"query_method": "complex", "num_subsample": C, "delays_method_source": "identity", "subsampling_method": "qsft",
+          "delays_method_channel": "nso", "num_repeat": R, "b": b}
+    np.random.seed(31)
+    sig = qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=1, a_max=1, noise_sd=0.0, query_args=dict(qa))
+    sft = qsft_b200.QSFT(num_subsample=C, num_repeat=R, b=b, reconstruct_method_source="identity", reconstruct_method_channel="nso")
+    tight = sft.transform(sig, output="arrays", max_finds=64)
+    assert sft.last_stats["finds"] > 64
+    np.random.seed(31)
+    sig2 = qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=1, a_max=1, noise_sd=0.0, query_args=dict(qa))
+    roomy = sft.transform(sig2, output="arrays")
+    assert {tuple(k) for k in tight["locations"].tolist()} == {tuple(k) for k in roomy["locations"].tolist()} == set(sig.signal_w.keys())
+
+
 def test_transform_device_async_pipelined_equals_synchronous():
     """output="device_async": three transforms queued back to back without any read-back; each PendingSpectrum, waited for
     afterwards, reports the statistics of ITS transform, and the last one's device list equals the synchronous result."""
