@@ -150,24 +150,32 @@ class DistContext:
                                f"Ms= / Ds=), the delay rows of ONE transform are sharded over the ranks")
 
     def post_check(self, what, *arrays):
-        """assert_same without the wait: the hash all-gather is queued now, the comparison happens in verify()."""
+        """assert_same without a collective: only the hash is taken now; verify() compares the hashes of ALL pending checks
+        across the ranks with one small all-gather (no NCCL kernels between the sampling, transform and peel kernels)."""
         import hashlib
         h = hashlib.blake2b(digest_size=8)
         for a in arrays:
             a = np.ascontiguousarray(a)
             h.update(str(a.shape).encode())
             h.update(a.tobytes())
-        mine = torch.tensor([int.from_bytes(h.digest(), "little", signed=True)], dtype=torch.int64).to(self._device(), non_blocking=True)
-        everyone = torch.empty(self.world_size, dtype=torch.int64, device=mine.device)
-        td.all_gather_into_tensor(everyone, mine, group=self.group)
-        self._pending_checks.append((what, everyone))
+        self._pending_checks.append((what, int.from_bytes(h.digest(), "little", signed=True)))
 
     def verify(self):
-        """Reads the verdicts of all post_check calls (one small device-to-host copy each); raises on a mismatch."""
+        """Compares the pending checks across the ranks (every rank must have queued the same number: they come from the
+        same code path); raises on a mismatch."""
         pending, self._pending_checks = self._pending_checks, []
-        for what, everyone in pending:
-            v = everyone.cpu()
-            if not bool((v == v[0]).all()):
+        if not pending:
+            return
+        mine = torch.tensor([len(pending)] + [v for _, v in pending], dtype=torch.int64).to(self._device())
+        counts = torch.empty(self.world_size, dtype=torch.int64, device=mine.device)
+        td.all_gather_into_tensor(counts, mine[:1].clone(), group=self.group)
+        if not bool((counts == counts[0]).all()):
+            raise RuntimeError("the ranks queued different numbers of agreement checks: they are not running the same transforms")
+        everyone = torch.empty(self.world_size * mine.numel(), dtype=torch.int64, device=mine.device)
+        td.all_gather_into_tensor(everyone, mine, group=self.group)
+        v = everyone.cpu().view(self.world_size, -1)[:, 1:]
+        for i, (what, _) in enumerate(pending):
+            if not bool((v[:, i] == v[0, i]).all()):
                 raise RuntimeError(f"{what} differ between ranks: seed the NumPy RNG identically on every rank (or pass the same "
                                    f"Ms= / Ds=), the delay rows of ONE transform are sharded over the ranks")
 

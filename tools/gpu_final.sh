@@ -1,0 +1,12 @@
+#!/bin/bash
+# End-of-round check on one GPU: whole GPU suite, smoke(), the default bench (with extras) and the reference arm.
+tag=${1:-final}
+out=gpurun_out
+mkdir -p $out
+timeout 1200 python -m pytest tests -m gpu -q > $out/${tag}_pytest.log 2>&1; echo "exit $?" >> $out/${tag}_pytest.log
+tail -5 $out/${tag}_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $out/${tag}_smoke.log 2>&1; tail -2 $out/${tag}_smoke.log
+timeout 900 python bench.py > $out/${tag}_bench_N1.json 2> $out/${tag}_bench_N1.err
+tail -5 $out/${tag}_bench_N1.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 0 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
+tail -2 $out/${tag}_bench_reference.err; cut -c1-400 $out/${tag}_bench_reference.json
