@@ -301,9 +301,9 @@ int qsft_k3_q4_tma(float* xf, int64_t batch, int b, const K3Peers& peers_in, cud
     const cuuint32_t box2[3] = {32, (cuuint32_t)W16, (cuuint32_t)(r2 ? (256 / W16) : 1)};
     if (int rc = tma::make_map(&tm2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, xf, dims, strides, r2 ? box2 : box1, CU_TENSOR_MAP_SWIZZLE_128B))
         return rc;
-    // ring depth: 2 tiles per CTA, two CTAs per SM measured best (r2c sweep: 0.258 ms for 41 x 4^10 against 0.275 / 0.286 ms
-    // with 3 / 4 stages; QSFT_K3_STAGES = 2 .. 6 for measurements)
-    int nstages = 2, nofence = 0;
+    // ring depth (QSFT_K3_STAGES = 2 .. 6 for measurements), measured per shape with the publisher warp in place (r3g):
+    //   4^6: 0.052 / 0.054 ms   4^7: 0.086 / 0.080   4^8: 0.169 / 0.151   4^9: 0.173 / 0.165   4^10: 0.182 / 0.190   (2 / 3 tiles)
+    int nstages = (b >= 7 && b <= 9) ? 3 : 2, nofence = 0;
     if (const char* e = getenv("QSFT_K3_STAGES"))
         if (atoi(e) >= 2 && atoi(e) <= KT_MAX_STAGES) nstages = atoi(e);
     if (const char* e = getenv("QSFT_K3_NOFENCE")) nofence = atoi(e) != 0;
