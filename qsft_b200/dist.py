@@ -56,12 +56,25 @@ class DistContext:
         if not self.symmetric:
             return None
         pool = self._symm_free.setdefault(int(nfloats), [])
+        # a rank that reuses a pooled buffer while a peer sets up a fresh one would miss the peer's rendezvous: the choice
+        # goes into the deferred agreement checks (verify() names it instead of leaving wrong bins behind)
+        self.post_check("symmetric buffer reuse (pooled / fresh)", np.array([int(nfloats), 1 if pool else 0], dtype=np.int64))
         if pool:
             return pool.pop()
+        buf, err = None, None
         try:
             import torch.distributed._symmetric_memory as symm_mem
             grp = self.group if self.group is not None else td.group.WORLD
             buf = symm_mem.empty(int(nfloats), dtype=torch.float32, device=device)
+        except Exception as exc:  # pragma: no cover - depends on the platform
+            err = repr(exc)
+        # the fallback is decided by ALL ranks together (the rendezvous below is collective): one rank on the NCCL
+        # all-gather path while its peers wait in the fused K3 store path would hang
+        if not self._all_ok(buf is not None, device):
+            self.symmetric = False
+            self.symmetric_error = err or "symmetric allocation failed on a peer rank"
+            return None
+        try:
             hdl = symm_mem.rendezvous(buf, grp)
             ptrs = [int(p) for p in hdl.buffer_ptrs]
             # NVLS multicast alias of the buffer (0 where the platform has none): one multimem.st reaches every rank
@@ -71,11 +84,20 @@ class DistContext:
                     mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
                 except Exception:  # pragma: no cover - depends on the platform
                     mc = 0
-            return (buf, hdl, ptrs, mc)
+            ok = True
         except Exception as exc:  # pragma: no cover - depends on the platform
+            err, ok = repr(exc), False
+        if not self._all_ok(ok, device):
             self.symmetric = False
-            self.symmetric_error = repr(exc)
+            self.symmetric_error = err or "symmetric rendezvous failed on a peer rank"
             return None
+        return (buf, hdl, ptrs, mc)
+
+    def _all_ok(self, ok, device):
+        """True iff `ok` holds on every rank (one small all-reduce; only on the set-up path of a NEW symmetric buffer)."""
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        td.all_reduce(t, op=td.ReduceOp.MIN, group=self.group)
+        return bool(t.item())
 
     def symm_release(self, item):
         if item is not None:
