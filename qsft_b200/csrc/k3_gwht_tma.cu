@@ -154,8 +154,8 @@ __device__ __forceinline__ void kt_tile(float2* __restrict__ s, float2* __restri
     if ((tau & 31) == 0) tma::mbar_arrive(stored_bar);                    // this warp's stores of the tile are issued
 }
 
-template <bool PEERS, int CTAS_PER_SM>
-__global__ void __launch_bounds__(KT_THREADS, CTAS_PER_SM)
+template <bool PEERS>
+__global__ void __launch_bounds__(KT_THREADS, 2)
 k3_q4_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2, float2* __restrict__ x,
                  long long B, int r1, int r2, int tiles1, int tiles2, unsigned int* __restrict__ done /* [nblocks] + ticket */,
                  long long nblocks, int lag, int nstages, int nofence, float scale1, float scale2, K3Peers peers) {
@@ -303,27 +303,21 @@ int qsft_k3_q4_tma(float* xf, int64_t batch, int b, const K3Peers& peers_in, cud
         return rc;
     // ring depth (QSFT_K3_STAGES = 2 .. 6 for measurements), measured per shape with the publisher warp in place (r3g):
     //   4^6: 0.052 / 0.054 ms   4^7: 0.086 / 0.080   4^8: 0.169 / 0.151   4^9: 0.173 / 0.165   4^10: 0.182 / 0.190   (2 / 3 tiles)
+    // Three CTAs per SM (64 registers, no spills) with two-tile rings, measured on one box (r4b): 4^7 0.078, 4^8 0.151, 4^9 0.168
+    // -- what the third stage already gives -- and 4^10 0.200 against 0.177 ms: more tiles in flight do not help the two-pass
+    // shape, whose tile rate is set by the shared-memory traffic of the butterfly steps (160 KB per 32 KB tile).  Not kept.
     int nstages = (b >= 7 && b <= 9) ? 3 : 2, nofence = 0;
     if (const char* e = getenv("QSFT_K3_STAGES"))
         if (atoi(e) >= 2 && atoi(e) <= KT_MAX_STAGES) nstages = atoi(e);
     if (const char* e = getenv("QSFT_K3_NOFENCE")) nofence = atoi(e) != 0;
-    // CTAs per SM: 2 (90 registers) or 3 (64 registers, no spills; two-tile rings only: 3 x 66 KB of shared memory)
-    int per_sm_want = 2;
-    if (const char* e = getenv("QSFT_K3_CTAS"))
-        if (atoi(e) == 3 && nstages == 2) per_sm_want = 3;
-    static int ctas_by_cfg[KT_MAX_STAGES + 1][4] = {{0}};
-    int& ctas = ctas_by_cfg[nstages][per_sm_want];
+    static int ctas_by_stages[KT_MAX_STAGES + 1] = {0};
+    int& ctas = ctas_by_stages[nstages];
     const size_t smem = kt_smem(nstages);
     if (ctas == 0) {
-        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kt_smem(KT_MAX_STAGES)));
-        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kt_smem(KT_MAX_STAGES)));
-        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kt_smem(2)));
-        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kt_smem(2)));
+        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kt_smem(KT_MAX_STAGES)));
+        QSFT_CUDA(cudaFuncSetAttribute(k3_q4_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kt_smem(KT_MAX_STAGES)));
         int per_sm = 0;
-        const cudaError_t oe = per_sm_want == 3
-            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_tma_kernel<true, 3>, KT_THREADS, smem)
-            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_tma_kernel<true, 2>, KT_THREADS, smem);
-        if (oe != cudaSuccess || per_sm < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_q4_tma_kernel<true>, KT_THREADS, smem) != cudaSuccess || per_sm < 1) {
             (void)cudaGetLastError();
             per_sm = 1;
         }
@@ -347,17 +341,12 @@ int qsft_k3_q4_tma(float* xf, int64_t batch, int b, const K3Peers& peers_in, cud
     QSFT_CUDA(cudaMemsetAsync(done, 0, (size_t)(batch + 1) * sizeof(unsigned int), st));
     const K3Peers peers = peers_in;
     const float inv = (float)(1.0 / (double)B);
-#define KT_LAUNCH(PEERS_, N_)                                                                                                  \
-    k3_q4_tma_kernel<PEERS_, N_><<<grid, KT_THREADS, smem, st>>>(tm1, tm2, reinterpret_cast<float2*>(xf), B, r1, r2, tiles1, tiles2, \
-                                                                 done, (long long)batch, lag, nstages, nofence, r2 ? 1.0f : inv, inv, peers)
-    if (n_peers > 0) {
-        if (per_sm_want == 3) KT_LAUNCH(true, 3);
-        else KT_LAUNCH(true, 2);
-    } else {
-        if (per_sm_want == 3) KT_LAUNCH(false, 3);
-        else KT_LAUNCH(false, 2);
-    }
-#undef KT_LAUNCH
+    if (n_peers > 0)
+        k3_q4_tma_kernel<true><<<grid, KT_THREADS, smem, st>>>(tm1, tm2, reinterpret_cast<float2*>(xf), B, r1, r2, tiles1, tiles2, done,
+                                                               (long long)batch, lag, nstages, nofence, r2 ? 1.0f : inv, inv, peers);
+    else
+        k3_q4_tma_kernel<false><<<grid, KT_THREADS, smem, st>>>(tm1, tm2, reinterpret_cast<float2*>(xf), B, r1, r2, tiles1, tiles2, done,
+                                                                (long long)batch, lag, nstages, nofence, r2 ? 1.0f : inv, inv, peers);
     QSFT_LAUNCHED();
     QSFT_CUDA(cudaFreeAsync(done, st));
     return QSFT_OK;
