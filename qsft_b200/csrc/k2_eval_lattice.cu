@@ -95,6 +95,20 @@ __device__ __forceinline__ uint32_t dot4(uint32_t a, uint32_t b, int nd) {
     return ((uint32_t)__popc(a0 & b0) + 2u * (uint32_t)__popc((a1 & b0) ^ (a0 & b1))) & 3u;
 }
 
+// q = 2 runs through the same machinery as q = 4: (-1)^t = i^(2 t), so lt_prep stores the bin-hash digits and delay phases
+// DOUBLED (0 / 2) in the two-bit fields, and a lattice index l in [0, 2^nd) -- one BIT per digit -- is spread to one two-bit
+// field per digit (values 0 / 1) before the dot product: dot4(2 h, spread(l)) = 2 <h, l> mod 4.  Row / column counts are
+// 2^b1 / 2^b2 instead of 4^b1 / 4^b2; the GEMM kernels only ever see counts and tables.
+__device__ __forceinline__ uint32_t lt_digits(uint32_t idx, int spread) {
+    if (!spread) return idx;
+    uint32_t x = idx & 0xffffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
 // ---- operand generation -----------------------------------------------------------------------------------
 // per support element: bin hash halves (h_hi, h_lo) and the delay phases e[p][s] = <d_p, k_s> mod 4
 __global__ void lt_prep_kernel(const int8_t* __restrict__ M, const int8_t* __restrict__ D, const int8_t* __restrict__ loc,
@@ -112,18 +126,19 @@ __global__ void lt_prep_kernel(const int8_t* __restrict__ M, const int8_t* __res
     const int8_t* row = loc + (size_t)s * ld;
     for (int u = 0; u < n; ++u) k[u] = row[u];
     uint32_t hi = 0, lo = 0;
+    const int mul = (q == 2) ? 2 : 1;                 // q = 2: phases in quarter turns (see lt_digits)
     for (int i = 0; i < b; ++i) {
         int acc = 0;
         for (int u = 0; u < n; ++u) acc += (int)sM[u * b + i] * (int)k[u];
-        if (i < b1) hi = (hi << 2) | (uint32_t)(acc % q);
-        else lo = (lo << 2) | (uint32_t)(acc % q);
+        if (i < b1) hi = (hi << 2) | (uint32_t)(acc % q * mul);
+        else lo = (lo << 2) | (uint32_t)(acc % q * mul);
     }
     hhi[s] = hi;
     hlo[s] = lo;
     for (int p = 0; p < P; ++p) {
         int acc = 0;
         for (int u = 0; u < n; ++u) acc += (int)sD[p * n + u] * (int)k[u];
-        e[(size_t)p * Se + s] = (uint8_t)(acc % q);
+        e[(size_t)p * Se + s] = (uint8_t)(acc % q * mul);
     }
 }
 
@@ -200,14 +215,15 @@ __global__ void lt_amin_kernel(const float2* __restrict__ a, long long S, unsign
 // delay rows; the four possible byte pairs of a row are packed in a 64-bit constant and picked by a shift.
 __global__ void __launch_bounds__(256)
 lt_agen_kernel(const uint32_t* __restrict__ hhi, const uint8_t* __restrict__ e, long long S, long long Se, int b1, int P,
-               long long Mhi, long long Kp, uint32_t* __restrict__ A) {
+               long long Mhi, long long Kp, uint32_t* __restrict__ A, int spread) {
     const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // two support elements = 4 K' bytes
     const uint32_t lhi = blockIdx.y;
     if (pair * 4 >= Kp) return;
     const long long s0 = 2 * pair;
     const bool live0 = s0 < S, live1 = s0 + 1 < S;
-    const uint32_t t0 = live0 ? dot4(hhi[s0], lhi, b1) : 0u;
-    const uint32_t t1 = live1 ? dot4(hhi[s0 + 1], lhi, b1) : 0u;
+    const uint32_t ldig = lt_digits(lhi, spread);
+    const uint32_t t0 = live0 ? dot4(hhi[s0], ldig, b1) : 0u;
+    const uint32_t t1 = live1 ? dot4(hhi[s0 + 1], ldig, b1) : 0u;
     // byte pairs (lo byte first) for rotation r = 0..3:  Re row (er, -ei) = 01 00 | 00 FF | FF 00 | 00 01
     //                                                    Im row (ei,  er) = 00 01 | 01 00 | 00 FF | FF 00
     constexpr unsigned long long kRe = 0x010000FFFF000001ull, kIm = 0x00FFFF0000010100ull;
@@ -247,7 +263,7 @@ lt_agen_kernel(const uint32_t* __restrict__ hhi, const uint8_t* __restrict__ e, 
 constexpr int LT_BGEN_LL = 8;
 __global__ void __launch_bounds__(256)
 lt_bgen_kernel(const uint32_t* __restrict__ hlo, const int2* __restrict__ alimb, long long S, int b2, long long Nlo,
-               long long Kp, uint32_t* __restrict__ Bq) {
+               long long Kp, uint32_t* __restrict__ Bq, int spread) {
     const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (pair * 4 >= Kp) return;
     const long long s0 = 2 * pair;
@@ -275,7 +291,8 @@ lt_bgen_kernel(const uint32_t* __restrict__ hlo, const int2* __restrict__ alimb,
         const long long llo = llo_begin + j;
         if (llo >= Nlo) break;
         // dead elements have zero limbs: their rotation does not matter
-        const uint32_t r0 = dot4(h0w, (uint32_t)llo, b2), r1 = dot4(h1w, (uint32_t)llo, b2);
+        const uint32_t ldig = lt_digits((uint32_t)llo, spread);
+        const uint32_t r0 = dot4(h0w, ldig, b2), r1 = dot4(h1w, ldig, b2);
         // rotation r: swap (x, y) iff r & 1; negate byte 0 iff (r & 1) ^ (r >> 1); negate byte 1 iff r >> 1
         const uint32_t b0 = r0 & 1u, h0 = r0 >> 1, b1 = r1 & 1u, h1 = r1 >> 1;
         const uint32_t sel = (b0 ? 0x01u : 0x10u) | ((b1 ? 0x23u : 0x32u) << 8);
@@ -296,7 +313,8 @@ lt_bgen_kernel(const uint32_t* __restrict__ hlo, const int2* __restrict__ alimb,
 // are loaded once); blockIdx.y enumerates groups of LT_TTAB_LL rows.
 constexpr int LT_TTAB_LL = 8;
 __global__ void __launch_bounds__(256)
-lt_ttab_kernel(const uint32_t* __restrict__ hhi, long long S, int b1, long long Tw, long long Mhi, uint32_t* __restrict__ T) {
+lt_ttab_kernel(const uint32_t* __restrict__ hhi, long long S, int b1, long long Tw, long long Mhi, uint32_t* __restrict__ T,
+               int spread) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= Tw) return;
     uint32_t h[16];
@@ -310,8 +328,9 @@ lt_ttab_kernel(const uint32_t* __restrict__ hhi, long long S, int b1, long long 
         const long long lhi = l0 + j;
         if (lhi >= Mhi) break;
         uint32_t word = 0;
+        const uint32_t ldig = lt_digits((uint32_t)lhi, spread);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) word |= dot4(h[i], (uint32_t)lhi, b1) << (2 * i);
+        for (int i = 0; i < 16; ++i) word |= dot4(h[i], ldig, b1) << (2 * i);
         T[(size_t)lhi * Tw + w] = word;
     }
 }
@@ -942,13 +961,21 @@ int lt_make_map(CUtensorMap* map, const void* ptr, long long rows, long long kby
 
 }  // namespace
 
+// split of the b lattice digits into row (b1) and column (b2) digits of the GEMM
+static inline int lt_split_b1(int q, int b) { return q == 2 ? (b - 1) / 2 : b / 2; }
+
 extern "C" int qsft_eval_lattice_supported(int q, int n, int b, int P, int64_t S) {
-    if (n < 1 || n > QSFT_MAX_N || P < 1 || S < 1) return 0;
-    const int b1 = b / 2, b2 = b - b1;
+    if (n < 1 || n > QSFT_MAX_N || P < 1 || S < 1 || b < 1) return 0;
+    const int b1 = lt_split_b1(q, b), b2 = b - b1;
     if (q == 3) {                                            // dense Z[w] variant, ragged tiles
         if (b1 < 3 || b2 < 4 || b2 > 10 || b > 20) return 0;   // packed digits fit 32 bits; 3 * 3^b2 >= 128 rows of B'
         const long long Mhi = ipow64(3, b1), Nlo = ipow64(3, b2);
         if ((long long)P * Mhi * 2 < LT_BM || (long long)P * Mhi * 2 >= 0x7fffffffLL || Nlo > 65535) return 0;
+        return 1;
+    }
+    if (q == 2) {                                            // q = 4 machinery on 2^b1 x 2^b2 lattices (lt_digits)
+        if (b1 < 6 || b2 < 8 || b > 28) return 0;            // 2 * 2^b1 >= 128 rows, 2^b2 >= 256 columns
+        if ((long long)P * ipow64(2, b1) * 2 >= 0x7fffffffLL) return 0;
         return 1;
     }
     if (q != 4) return 0;
@@ -1074,14 +1101,15 @@ int lt_eval_q3(const int8_t* M, const int8_t* D, const int8_t* loc, const float*
 // back, i.e. synchronises the stream once).
 extern "C" int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths, int64_t S,
                                           int q, int n, int b, int P, int ld, float* out, int residual_passes, void* stream) {
-    QSFT_CHECK_ARG(qsft_eval_lattice_supported(q, n, b, P, S), "lattice evaluation supports q = 4 with 7 <= b <= 14 and q = 3 with 7 <= b <= 20 only");
+    QSFT_CHECK_ARG(qsft_eval_lattice_supported(q, n, b, P, S), "lattice evaluation supports q = 4 with 7 <= b <= 14, q = 3 with 7 <= b <= 20 and q = 2 with 14 <= b <= 28 only");
     QSFT_CHECK_ARG(M && D && loc && strengths && out, "null pointer");
     QSFT_CHECK_ARG(ld >= n && ld % 16 == 0, "bad ld");
     QSFT_CHECK_ARG(residual_passes >= -1 && residual_passes <= 1, "residual_passes must be -1 (auto), 0 or 1");
     cudaStream_t st = (cudaStream_t)stream;
     if (q == 3) return lt_eval_q3(M, D, loc, strengths, S, n, b, P, ld, out, residual_passes, st);
-    const int b1 = b / 2, b2 = b - b1;
-    const long long Mhi = ipow64(4, b1), Nlo = ipow64(4, b2);
+    const int b1 = lt_split_b1(q, b), b2 = b - b1;
+    const int spread = (q == 2) ? 1 : 0;                 // q = 2: one bit per lattice digit (lt_digits)
+    const long long Mhi = ipow64(q, b1), Nlo = ipow64(q, b2);
     // Default: 2:4 structured-sparse A' generated straight into tensor memory (tcgen05.mma.sp on CTA pairs; A' never exists
     // in HBM or shared memory).  QSFT_LATTICE_SPARSE=0 selects the dense cross-check kernel: A' materialised in HBM
     // (2 * Mhi * Kp bytes per delay row), delay rows processed in chunks that keep it under a scratch budget (default 32 GB,
@@ -1150,7 +1178,7 @@ extern "C" int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, cons
         const unsigned pb = (unsigned)((Kp / 4 + T - 1) / T);
         const unsigned wb = (unsigned)((Tw + T - 1) / T);
         if (sparse_ts && !rc) {
-            lt_ttab_kernel<<<dim3(wb, (unsigned)((Mhi + LT_TTAB_LL - 1) / LT_TTAB_LL)), T, 0, st>>>(hhi, S, b1, Tw, Mhi, Ttab);
+            lt_ttab_kernel<<<dim3(wb, (unsigned)((Mhi + LT_TTAB_LL - 1) / LT_TTAB_LL)), T, 0, st>>>(hhi, S, b1, Tw, Mhi, Ttab, spread);
             lt_etab_kernel<<<dim3(wb, (unsigned)P), T, 0, st>>>(e, S, Se, P, Tw, Etab);
             g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
         }
@@ -1176,7 +1204,7 @@ extern "C" int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, cons
             // the limb operand B' of this pass (shared by all delay rows)
             lt_quant_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax, inv_scale, alimb, pass);
             lt_bgen_kernel<<<dim3(pb, (unsigned)((Nlo + LT_BGEN_LL - 1) / LT_BGEN_LL)), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp,
-                                                                                                     reinterpret_cast<uint32_t*>(Bq));
+                                                                                                     reinterpret_cast<uint32_t*>(Bq), spread);
             g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
             for (long long p0 = 0; p0 < P && !rc; p0 += Pc) {
                 const long long pc = (P - p0 < Pc) ? (P - p0) : Pc;
@@ -1206,7 +1234,7 @@ extern "C" int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, cons
                 } else {
                     dim3 grid((unsigned)(Nlo / LT_BN), (unsigned)(pc * 2 * Mhi / LT_BM));
                     lt_agen_kernel<<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, e + (size_t)p0 * Se, S, Se, b1, (int)pc, Mhi, Kp,
-                                                                          reinterpret_cast<uint32_t*>(A));
+                                                                          reinterpret_cast<uint32_t*>(A), spread);
                     rc = lt_make_map(&ma, A, pc * 2 * Mhi, Kp);
                     if (rc) break;
                     lt_gemm_kernel<false><<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mb, (int)(Kp / LT_BK), (int)Mhi, (int)Nlo,

@@ -52,17 +52,18 @@ int emu_lt_quant(const float* a, long long S, float* inv_scale, int32_t* alimb /
     return 0;
 }
 
-int emu_lt_bgen(const uint32_t* hlo, const int32_t* alimb, long long S, int b2, long long Nlo, long long Kp, uint32_t* Bq) {
+int emu_lt_bgen(const uint32_t* hlo, const int32_t* alimb, long long S, int b2, long long Nlo, long long Kp, uint32_t* Bq,
+                int spread) {
     const int T = 256;
     emu::launch(dim3((unsigned)((Kp / 4 + T - 1) / T), (unsigned)((Nlo + LT_BGEN_LL - 1) / LT_BGEN_LL)), dim3(T),
-                [&]() { lt_bgen_kernel(hlo, reinterpret_cast<const int2*>(alimb), S, b2, Nlo, Kp, Bq); });
+                [&]() { lt_bgen_kernel(hlo, reinterpret_cast<const int2*>(alimb), S, b2, Nlo, Kp, Bq, spread); });
     return 0;
 }
 
-int emu_lt_ttab(const uint32_t* hhi, long long S, int b1, long long Tw, long long Mhi, uint32_t* T_) {
+int emu_lt_ttab(const uint32_t* hhi, long long S, int b1, long long Tw, long long Mhi, uint32_t* T_, int spread) {
     const int T = 256;
     emu::launch(dim3((unsigned)((Tw + T - 1) / T), (unsigned)((Mhi + LT_TTAB_LL - 1) / LT_TTAB_LL)), dim3(T),
-                [&]() { lt_ttab_kernel(hhi, S, b1, Tw, Mhi, T_); });
+                [&]() { lt_ttab_kernel(hhi, S, b1, Tw, Mhi, T_, spread); });
     return 0;
 }
 
@@ -73,10 +74,10 @@ int emu_lt_etab(const uint8_t* e, long long S, long long Se, int P, long long Tw
 }
 
 int emu_lt_agen(const uint32_t* hhi, const uint8_t* e, long long S, long long Se, int b1, int P, long long Mhi, long long Kp,
-                uint32_t* A) {
+                uint32_t* A, int spread) {
     const int T = 256;
     emu::launch(dim3((unsigned)((Kp / 4 + T - 1) / T), (unsigned)Mhi), dim3(T),
-                [&]() { lt_agen_kernel(hhi, e, S, Se, b1, P, Mhi, Kp, A); });
+                [&]() { lt_agen_kernel(hhi, e, S, Se, b1, P, Mhi, Kp, A, spread); });
     return 0;
 }
 

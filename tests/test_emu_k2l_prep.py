@@ -25,10 +25,10 @@ def emu():
     L.emu_lt_bgen3.argtypes = [vp, vp, i64, i32, i64, i64, i32, vp]
     L.emu_lt_combine3.argtypes = [vp, vp, i64, vp]
     L.emu_lt_quant.argtypes = [vp, i64, vp, vp, C.c_int]
-    L.emu_lt_bgen.argtypes = [vp, vp, i64, i32, i64, i64, vp]
-    L.emu_lt_ttab.argtypes = [vp, i64, i32, i64, i64, vp]
+    L.emu_lt_bgen.argtypes = [vp, vp, i64, i32, i64, i64, vp, i32]
+    L.emu_lt_ttab.argtypes = [vp, i64, i32, i64, i64, vp, i32]
     L.emu_lt_etab.argtypes = [vp, i64, i64, i32, i64, vp]
-    L.emu_lt_agen.argtypes = [vp, vp, i64, i64, i32, i32, i64, i64, vp]
+    L.emu_lt_agen.argtypes = [vp, vp, i64, i64, i32, i32, i64, i64, vp, i32]
     return L
 
 
@@ -36,14 +36,17 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-@pytest.mark.parametrize("n,b,S,P,seed", [(12, 7, 37, 5, 0), (40, 8, 90, 3, 1), (9, 7, 64, 2, 2)])
-def test_emulated_lattice_operands_reproduce_the_samples(emu, n, b, S, P, seed):
-    q = 4
+@pytest.mark.parametrize("q,n,b,S,P,seed", [(4, 12, 7, 37, 5, 0), (4, 40, 8, 90, 3, 1), (4, 9, 7, 64, 2, 2),
+                                            (2, 20, 9, 50, 4, 3), (2, 64, 12, 33, 3, 4)])
+def test_emulated_lattice_operands_reproduce_the_samples(emu, q, n, b, S, P, seed):
+    """q = 4, and q = 2 through the same kernels (digits doubled, lattice indices spread to one field per bit)."""
+    spread, mul = (1, 2) if q == 2 else (0, 1)
     rng = np.random.default_rng(seed)
     M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
     locq = rng.integers(0, q, (n, S))
     a = rng.uniform(0.3, 2, S) * np.exp(1j * rng.uniform(0, 2 * np.pi, S))
-    b1, b2 = b // 2, b - b // 2
+    b1 = (b - 1) // 2 if q == 2 else b // 2              # lt_split_b1
+    b2 = b - b1
     Mhi, Nlo = q ** b1, q ** b2
     ld = max(32, (n + 31) // 32 * 32)
     Kp = (2 * S + 127) // 128 * 128
@@ -56,11 +59,11 @@ def test_emulated_lattice_operands_reproduce_the_samples(emu, n, b, S, P, seed):
     e = np.zeros((P, Se), dtype=np.uint8)
     assert emu.emu_lt_prep(_p(M8), _p(D8), _p(loc), S, Se, n, b, b1, P, ld, _p(hhi), _p(hlo), _p(e), q) == 0
     # bin-hash halves and delay phases against their definitions
-    H = (M.T @ locq) % q                                                   # (b, S) digits of M^T k, MSB first
+    H = (M.T @ locq) % q * mul                                             # (b, S) digits of M^T k (quarter turns), MSB first
     want_hi = sum(H[i].astype(np.int64) << (2 * (b1 - 1 - i)) for i in range(b1))
     want_lo = sum(H[b1 + i].astype(np.int64) << (2 * (b2 - 1 - i)) for i in range(b2))
     assert np.array_equal(hhi, want_hi) and np.array_equal(hlo, want_lo)
-    assert np.array_equal(e[:, :S], (D @ locq) % q)
+    assert np.array_equal(e[:, :S], (D @ locq) % q * mul)
     # quantisation: three balanced base-128 limbs
     a32 = np.ascontiguousarray(a.astype(np.complex64))
     inv_scale = np.zeros(2, dtype=np.float32)
@@ -83,9 +86,9 @@ def test_emulated_lattice_operands_reproduce_the_samples(emu, n, b, S, P, seed):
     assert np.max(np.abs(aq - a32)) <= 0.75 * float(inv_scale[0]) * np.sqrt(2)
     # materialised operands
     A = np.zeros((P, Mhi, 2, Kp), dtype=np.int8)
-    assert emu.emu_lt_agen(_p(hhi), _p(e), S, Se, b1, P, Mhi, Kp, _p(A)) == 0
+    assert emu.emu_lt_agen(_p(hhi), _p(e), S, Se, b1, P, Mhi, Kp, _p(A), spread) == 0
     Bq = np.zeros((3, Nlo, Kp), dtype=np.int8)
-    assert emu.emu_lt_bgen(_p(hlo), _p(alimb), S, b2, Nlo, Kp, _p(Bq)) == 0
+    assert emu.emu_lt_bgen(_p(hlo), _p(alimb), S, b2, Nlo, Kp, _p(Bq), spread) == 0
     assert not A[..., 2 * S:].any() and not Bq[..., 2 * S:].any()          # K padding is zero
     assert set(np.unique(A)) <= {-1, 0, 1}
     pairs = A[..., :2 * S].reshape(P, Mhi, 2, S, 2)
@@ -102,7 +105,7 @@ def test_emulated_lattice_operands_reproduce_the_samples(emu, n, b, S, P, seed):
     # packed phase tables == the rotations the materialised operand was built from
     Ttab = np.zeros((Mhi, Tw), dtype=np.uint32)
     Etab = np.zeros((P, Tw), dtype=np.uint32)
-    assert emu.emu_lt_ttab(_p(hhi), S, b1, Tw, Mhi, _p(Ttab)) == 0
+    assert emu.emu_lt_ttab(_p(hhi), S, b1, Tw, Mhi, _p(Ttab), spread) == 0
     assert emu.emu_lt_etab(_p(e), S, Se, P, Tw, _p(Etab)) == 0
     f = np.arange(16)
     Tf = ((Ttab[:, :, None] >> (2 * f)) & 3).reshape(Mhi, -1)[:, :S]       # (Mhi, S)
@@ -111,7 +114,8 @@ def test_emulated_lattice_operands_reproduce_the_samples(emu, n, b, S, P, seed):
     er, ei = np.array([1, 0, -1, 0])[rot], np.array([0, 1, 0, -1])[rot]
     assert np.array_equal(pairs[:, :, 0, :, 0], er) and np.array_equal(pairs[:, :, 0, :, 1], -ei)
     assert np.array_equal(pairs[:, :, 1, :, 0], ei) and np.array_equal(pairs[:, :, 1, :, 1], er)
-    lhi_d = np.stack([(np.arange(Mhi) >> (2 * (b1 - 1 - i))) & 3 for i in range(b1)])     # (b1, Mhi) MSB first
+    w = 1 if q == 2 else 2                                                  # bits per lattice digit in the row index
+    lhi_d = np.stack([(np.arange(Mhi) >> (w * (b1 - 1 - i))) & (q - 1) for i in range(b1)])   # (b1, Mhi) MSB first
     assert np.array_equal(Tf, (lhi_d.T @ H[:b1]) % 4)
 
 

@@ -310,12 +310,13 @@ def test_peel_large_closed_form_exact_recovery():
 
 # ---- K2L: lattice-factorised evaluation (q = 4) -----------------------------------------------------------
 @pytest.mark.parametrize("mode", [2, 0])
-@pytest.mark.parametrize("n,b,S,P,seed", [(14, 7, 700, 5, 0), (40, 8, 3000, 3, 1), (40, 10, 257, 2, 2), (20, 9, 64, 4, 3),
-                                          (33, 7, 1, 1, 4)])
-def test_k2_lattice_matches_plain_path_and_oracle(n, b, S, P, seed, mode, monkeypatch):
-    """mode = QSFT_LATTICE_SPARSE: 2 (default) 2:4-sparse A' generated in tensor memory, 0 dense A' materialised in HBM."""
+@pytest.mark.parametrize("q,n,b,S,P,seed", [(4, 14, 7, 700, 5, 0), (4, 40, 8, 3000, 3, 1), (4, 40, 10, 257, 2, 2),
+                                            (4, 20, 9, 64, 4, 3), (4, 33, 7, 1, 1, 4),
+                                            (2, 30, 14, 600, 3, 5), (2, 64, 15, 2000, 2, 6), (2, 20, 16, 513, 1, 7), (2, 100, 14, 1, 2, 8)])
+def test_k2_lattice_matches_plain_path_and_oracle(q, n, b, S, P, seed, mode, monkeypatch):
+    """mode = QSFT_LATTICE_SPARSE: 2 (default) 2:4-sparse A' generated in tensor memory, 0 dense A' materialised in HBM.
+    q = 2 runs through the q = 4 kernels (phases doubled, one bit per lattice digit)."""
     monkeypatch.setenv("QSFT_LATTICE_SPARSE", str(mode))
-    q = 4
     rng = np.random.default_rng(seed)
     M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
     loc = rng.integers(0, q, (n, S))
@@ -366,7 +367,8 @@ def test_k2_lattice_q3_matches_oracle_and_plain_path(n, b, S, P, seed, a_lo):
 
 
 def test_k2_lattice_unsupported_shapes():
-    assert not ops.lattice_supported(5, 10, 8, 3, 100)       # q = 3 and q = 4 only
+    assert not ops.lattice_supported(5, 10, 8, 3, 100)       # q = 2, 3 and 4 only
+    assert not ops.lattice_supported(2, 20, 13, 3, 100) and ops.lattice_supported(2, 20, 14, 3, 100)   # q = 2: 14 <= b <= 28
     assert not ops.lattice_supported(3, 10, 6, 3, 100)       # q = 3: b too small
     assert ops.lattice_supported(3, 10, 8, 3, 100)
     assert not ops.lattice_supported(4, 10, 4, 3, 100)       # b too small
@@ -374,6 +376,25 @@ def test_k2_lattice_unsupported_shapes():
     a = torch.ones(4, dtype=torch.complex64, device=DEV)
     with pytest.raises(qsft_b200.QsftError):
         ops.eval_synth_lattice(np.zeros((10, 4), int), np.zeros((2, 10), int), loc, a, 4)
+
+
+def test_q2_large_lattice_transform_uses_the_lattice_gemm_and_recovers_the_support():
+    """q = 2, b = 14 (2^14 bins): sampled by the lattice GEMM (eval_impl 3 raises if the shape were unsupported), transformed
+    and peeled; the result equals the signal and the run that samples with K1 + K2 (eval_impl 2)."""
+    n, q, b, S, C = 40, 2, 14, 2000, 3
+    qa = {"query_method": "complex", "num_subsample": C, "delays_method_source": "identity", "subsampling_method": "qsft",
+          "delays_method_channel": "identity", "num_repeat": 1, "b": b}
+    res = {}
+    for impl in (3, 2):
+        np.random.seed(21)
+        sig = qsft_b200.get_random_subsampled_signal(n=n, q=q, sparsity=S, a_min=0.5, a_max=1, noise_sd=0.0,
+                                                      query_args=dict(qa), eval_impl=impl)
+        res[impl] = (qsft_b200.QSFT(num_subsample=C, num_repeat=1, b=b, reconstruct_method_source="identity",
+                                    reconstruct_method_channel="identity").transform(sig), sig.signal_w)
+    got, sw = res[3]
+    assert list(got.keys()) == list(res[2][0].keys()) and set(got.keys()) == set(sw.keys())
+    assert max(abs(got[k] - sw[k]) for k in sw) <= 1e-5
+    assert max(abs(got[k] - res[2][0][k]) for k in sw) <= 1e-5
 
 
 @pytest.mark.parametrize("impl", [2, 3, 0])
