@@ -31,6 +31,14 @@ int qsft_version(void);
 int64_t qsft_launch_count(void);
 void qsft_reset_launch_count(void);
 
+/* Host staging of a digit table for upload (host logic, no device work).  Replaces the int64 -> small-integer handling the
+ * reference leaves to NumPy when it keeps the support as locq (n, S) int64 (synt_exp/synt_src/synthetic_signal.py:43-44, 93):
+ * `rows` rows of n integer digits (elem_bytes 1 / 2 / 4 / 8; row_stride / col_stride in elements, so either orientation of
+ * locq works) -> dst (rows, ld) int8, zero padded, typically page-locked memory that one cudaMemcpyAsync then uploads in the
+ * layout qsft_eval_synth* / qsft_peel* expect.  `threads` (1..16) host threads of its own.                                   */
+int qsft_host_pack_digits(const void* src, int elem_bytes, int64_t rows, int n, int64_t row_stride, int64_t col_stride,
+                          int8_t* dst, int ld, int threads);
+
 /* K1 -- query lattice.  Replaces SubsampledSignal._get_qsft_query_indices (qsft/input_signal_subsampled.py:183-206)
  * + qary_ints (qsft/utils.py:107-108) + qary_vec_to_dec (qsft/utils.py:74-76).
  *   M (n, b) int8 row-major, D (P, n) int8.  For every delay row p and every l in Z_q^b (column index = base-q value

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqsft_b200.so")
 
 EXPORTS = [
-    "qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count",
+    "qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count", "qsft_host_pack_digits",
     "qsft_query_lattice", "qsft_dec_to_qary", "qsft_qary_to_dec", "qsft_eval_synth", "qsft_gwht_batch", "qsft_gwht_batch_bcast", "qsft_gwht_batch_mcast", "qsft_gwht_batch_scatter",
     "qsft_eval_lattice_supported", "qsft_eval_synth_lattice", "qsft_eval_synth_lattice_ex",
     "qsft_peel_classify", "qsft_peel_apply", "qsft_peel_reduce", "qsft_peel", "qsft_peel_blocks", "qsft_peel_blocks_sharded", "qsft_peel_sharded_workspace_bytes", "qsft_closed_form_bins",
@@ -79,6 +79,7 @@ def lib():
     L.qsft_version.restype = i32
     L.qsft_launch_count.restype = i64
     L.qsft_reset_launch_count.restype = None
+    L.qsft_host_pack_digits.argtypes = [vp, i32, i64, i32, i64, i64, vp, i32, i32]
     L.qsft_query_lattice.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp]
     L.qsft_dec_to_qary.argtypes = [vp, i32, i64, i32, i32, vp, i32, vp]
     L.qsft_qary_to_dec.argtypes = [vp, i32, i64, i32, i32, vp, i32, vp]
@@ -108,7 +109,7 @@ def lib():
     L.qsft_add_noise.argtypes = [vp, i64, C.c_float, C.c_uint64, C.c_uint64, vp]
     for name in EXPORTS:
         fn = getattr(L, name)  # raises AttributeError if a declared symbol is missing
-        if name not in ("qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count",
+        if name not in ("qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count", "qsft_host_pack_digits",
                         "qsft_peel_sharded_workspace_bytes"):
             fn.restype = i32
     _lib = L

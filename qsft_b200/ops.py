@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 
 import numpy as np
@@ -74,6 +75,14 @@ def _pinned(tag, shape, dtype):
     return buf[:n].view(shape)
 
 
+def _pinned_upload_block(shape, dtype):
+    """Page-locked block for ONE host -> device copy, from torch's caching host allocator: unlike the reusable buffers above
+    it is not handed out again before the asynchronous copy that reads it has run (the allocator records the stream), so a
+    host that runs ahead of the GPU -- QSFT.transform(output="device_async") -- cannot overwrite data still waiting for its
+    DMA.  After the first use of a size this costs microseconds."""
+    return torch.empty(tuple(int(d) for d in shape), dtype=dtype, pin_memory=True)
+
+
 def _upload(arr, device):
     """Small host array -> device without stalling the host: a pageable `.to(device)` is a synchronous copy ordered behind
     everything already queued on the stream (the host then sleeps through the previous block's GEMM and launches the next
@@ -93,37 +102,34 @@ def _need_cuda(*tensors):
             raise ValueError("expected contiguous CUDA tensors")
 
 
-def narrow_int8(rows):
-    """Integer digit array -> contiguous CPU int8 tensor.  The narrowing cast runs in torch (vectorised: 0.8 ms for the
-    (40, 1e5) int64 support of config 5, against 4-6 ms for ndarray.astype on the same host)."""
-    a = np.asarray(rows)
-    if a.dtype == np.int8:
-        return torch.from_numpy(np.ascontiguousarray(a))
-    if a.dtype.kind not in "iu" or not a.flags.c_contiguous or not a.flags.writeable or a.dtype.byteorder not in "=|<":
-        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int8))
-    if a.dtype.kind == "u" and a.dtype.itemsize > 1:        # torch has no uint32 / uint64 arithmetic: view as signed
-        a = a.view(a.dtype.str.replace("u", "i"))
-    return torch.from_numpy(a).to(torch.int8)
+def _pack_threads():
+    # host threads of the packer: the ranks of one box share its cores
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(1, min(4, (os.cpu_count() or 2) // ranks))
 
 
 def pad_digits(rows, ld, device, transposed=False):
     """Integer digit rows -> zero padded int8 device tensor (N, ld).  `rows` is (N, n), or (n, N) with transposed=True
-    (the reference keeps the support as columns: locq (n, S)).  The narrowing cast runs on the host on whichever of the
-    array / its transpose is contiguous (locq is the transposed view of a sorted (S, n) array: casting that view directly
-    would first copy 8-byte digits into a contiguous block, 11 ms at S = 1e5, n = 40), the copy goes through a reusable
-    pinned buffer, transposition (if still needed) and padding happen on the device."""
+    (the reference keeps the support as columns: locq (n, S)).  The narrowing cast, the transposition and the padding are
+    done by the library's host packer (qsft_host_pack_digits: strided reads, its own threads -- under torchrun
+    OMP_NUM_THREADS=1 makes the same cast in torch / NumPy take 3-4 ms at S = 1e5, n = 40, serial host time in front of every
+    synchronous transform) straight into a pinned block, which ONE asynchronous copy uploads in the device layout."""
     a = np.asarray(rows)
-    if transposed and a.ndim == 2 and a.T.flags.c_contiguous:
-        a, transposed = a.T, False
-    t8 = narrow_int8(a)
-    stage = _pinned("pad_digits", tuple(t8.shape), torch.int8)
-    stage.copy_(t8)
-    t = stage.to(device, non_blocking=True)
+    if a.ndim != 2:
+        raise ValueError("digit rows must be a 2-D array")
+    if a.dtype.kind not in "iu" or a.dtype.itemsize not in (1, 2, 4, 8) or a.dtype.byteorder not in "=|<":
+        a = np.ascontiguousarray(a, dtype=np.int64)
     if transposed:
-        t = t.t()
-    out = torch.zeros((t.shape[0], ld), dtype=torch.int8, device=device)
-    out[:, : t.shape[1]] = t
-    return out
+        a = a.T
+    N, n = a.shape
+    if ld < n:
+        raise ValueError("ld must be at least the number of digits")
+    stage = _pinned_upload_block((N, ld), torch.int8)
+    if N:
+        isz = a.dtype.itemsize
+        _lib.check(_lib.lib().qsft_host_pack_digits(C.c_void_p(a.ctypes.data), isz, N, n, a.strides[0] // isz, a.strides[1] // isz,
+                                                    C.c_void_p(stage.data_ptr()), ld, _pack_threads()))
+    return stage.to(device, non_blocking=True)
 
 
 def query_lattice(M, D, q, *, device, want_idx=True, want_digits=False, limbs=None, ld=None):

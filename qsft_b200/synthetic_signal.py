@@ -75,7 +75,10 @@ class SyntheticSubsampledSignal(SubsampledSignal):
         if self._loc_dev is None:
             self._loc_dev = ops.pad_digits(self.locq, self.ld, self.device, transposed=True)
         if self._a_dev is None:
-            self._a_dev = torch.from_numpy(self.strengths.astype(np.complex64)).to(self.device)
+            # through a pinned block: a pageable .to(device) is a synchronous staged copy
+            stage = ops._pinned_upload_block((len(self.strengths),), torch.complex64)
+            stage.numpy()[...] = self.strengths
+            self._a_dev = stage.to(self.device, non_blocking=True)
         # precision of the lattice GEMM (ops.eval_synth_lattice): strengths of very different sizes need the residual pass for
         # 1e-5 relative accuracy of the small ones; decided here on the host copy (no device round trip per block)
         mag = np.maximum(np.abs(self.strengths.real), np.abs(self.strengths.imag)) if len(self.strengths) else np.zeros(1)

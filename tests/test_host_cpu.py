@@ -212,22 +212,36 @@ def test_k3_twopass_ticket_order_is_deadlock_free():
     assert L.qsft_k3_ticket_decode(8, 1, 4, 4, 0, C.byref(blk), C.byref(tile), C.byref(strided)) != 0   # out of range
 
 
-def test_narrow_int8_matches_numpy_cast():
-    """Host-side digit narrowing (ops.narrow_int8, the torch fast path of pad_digits) == ndarray.astype(int8)."""
-    import torch  # noqa: F401
-    from qsft_b200.ops import narrow_int8
-    rng = np.random.default_rng(0)
-    for dt in [np.int64, np.int32, np.int16, np.int8, np.uint8, np.uint16, np.uint32, np.uint64, np.float64]:
-        a = rng.integers(0, 100, (7, 13)).astype(dt)
-        for arr in [a, a.T, a[:, ::2], np.asfortranarray(a)]:
-            got = narrow_int8(arr).numpy()
-            assert got.dtype == np.int8 and got.flags.c_contiguous and np.array_equal(got, arr.astype(np.int8)), dt
-    ro = rng.integers(0, 4, (5, 5))
-    ro.setflags(write=False)
-    assert np.array_equal(narrow_int8(ro).numpy(), ro)
-    assert np.array_equal(narrow_int8([[1, 2], [3, 0]]).numpy(), [[1, 2], [3, 0]])
-    assert narrow_int8(np.zeros((0, 4), dtype=np.int64)).shape == (0, 4)
+def test_host_pack_digits_matches_numpy_cast():
+    """The library's host packer (qsft_host_pack_digits, what ops.pad_digits stages the support with): narrowing cast,
+    either orientation / any stride, zero padding -- against ndarray.astype(int8); a large table exercises the threads."""
+    import ctypes as C
+    from qsft_b200 import _lib
+    L = _lib.lib()
 
+    def pack(arr, ld, threads):
+        N, n = arr.shape
+        out = np.full((N, ld), 77, dtype=np.int8)
+        isz = arr.dtype.itemsize
+        rc = L.qsft_host_pack_digits(C.c_void_p(arr.ctypes.data), isz, N, n, arr.strides[0] // isz, arr.strides[1] // isz,
+                                     C.c_void_p(out.ctypes.data), ld, threads)
+        assert rc == 0, L.qsft_last_error()
+        return out
+
+    rng = np.random.default_rng(0)
+    for dt in [np.int64, np.int32, np.int16, np.int8, np.uint8, np.uint16, np.uint32, np.uint64]:
+        a = rng.integers(0, 100, (7, 13)).astype(dt)
+        for arr in [a, a.T, a[:, ::2], a[::-1], np.asfortranarray(a)]:
+            got = pack(arr, 16, 3)
+            assert np.array_equal(got[:, :arr.shape[1]], arr.astype(np.int8)) and not got[:, arr.shape[1]:].any(), dt
+    big = rng.integers(0, 4, (40, 50_001))                                # locq as the reference keeps it: (n, S) int64
+    for threads in (1, 4, 16):
+        got = pack(big.T, 64, threads)
+        assert np.array_equal(got[:, :40], big.T.astype(np.int8)) and not got[:, 40:].any()
+    assert pack(np.zeros((0, 4), dtype=np.int64), 16, 2).shape == (0, 16)
+    a = np.zeros((2, 20), dtype=np.int64)
+    assert L.qsft_host_pack_digits(C.c_void_p(a.ctypes.data), 8, 2, 20, 20, 1, C.c_void_p(a.ctypes.data), 16, 1) == -1   # ld < n
+    assert L.qsft_host_pack_digits(C.c_void_p(a.ctypes.data), 3, 2, 20, 20, 1, C.c_void_p(a.ctypes.data), 32, 1) == -1   # elem_bytes
 
 def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     """Every entry point validates its arguments before the first CUDA call: QSFT_EINVAL (-1) + a message, on any host."""
