@@ -73,7 +73,8 @@ int qsft_eval_synth(const int8_t* qdig, int64_t N, const int8_t* loc, const floa
  * 0, +-1 in the basis (1, w): the same factorisation runs as a DENSE int8 GEMM (no 2:4 structure), once for the real and once
  * for the imaginary parts of the strengths, and X = c_1 + c_w w is formed afterwards.
  * qsft_eval_lattice_supported returns 1 when the shape is handled (q == 4: 7 <= b <= 14; q == 3: 7 <= b <= 20;
- * q == 2: 14 <= b <= 28, through the q = 4 kernels with doubled phases). */
+ * q == 2: 14 <= b <= 28, through the q = 4 kernels with doubled phases; q == 5 / 7: the q = 3 construction with q - 1
+ * coordinates, 3 * q^(b - b/2) >= 128 and q^(b - b/2) <= 65535). */
 int qsft_eval_lattice_supported(int q, int n, int b, int P, int64_t S);
 int qsft_eval_synth_lattice(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths, int64_t S,
                             int q, int n, int b, int P, int ld, float* out, void* stream);

@@ -113,7 +113,7 @@ __device__ __forceinline__ uint32_t lt_digits(uint32_t idx, int spread) {
 // per support element: bin hash halves (h_hi, h_lo) and the delay phases e[p][s] = <d_p, k_s> mod 4
 __global__ void lt_prep_kernel(const int8_t* __restrict__ M, const int8_t* __restrict__ D, const int8_t* __restrict__ loc,
                                long long S, long long Se, int n, int b, int b1, int P, int ld, uint32_t* __restrict__ hhi,
-                               uint32_t* __restrict__ hlo, uint8_t* __restrict__ e /* (P, Se), Se even */, int q) {
+                               uint32_t* __restrict__ hlo, uint8_t* __restrict__ e /* (P, Se), Se even */, int q, int fw = 2) {
     extern __shared__ int8_t lt_sm[];
     int8_t* sM = lt_sm;             // (n, b)
     int8_t* sD = lt_sm + n * b;     // (P, n)
@@ -130,8 +130,8 @@ __global__ void lt_prep_kernel(const int8_t* __restrict__ M, const int8_t* __res
     for (int i = 0; i < b; ++i) {
         int acc = 0;
         for (int u = 0; u < n; ++u) acc += (int)sM[u * b + i] * (int)k[u];
-        if (i < b1) hi = (hi << 2) | (uint32_t)(acc % q * mul);
-        else lo = (lo << 2) | (uint32_t)(acc % q * mul);
+        if (i < b1) hi = (hi << fw) | (uint32_t)(acc % q * mul);       // fw bits per digit: 2, or 3 for q = 5 / 7
+        else lo = (lo << fw) | (uint32_t)(acc % q * mul);
     }
     hhi[s] = hi;
     hlo[s] = lo;
@@ -501,6 +501,132 @@ __global__ void lt_combine3_kernel(const float2* __restrict__ cre, const float2*
     const float2 r = cre[i], m = cim[i];
     const float h = 0.86602540378443864676f;
     out[i] = make_float2(r.x - 0.5f * r.y - h * m.y, m.x - 0.5f * m.y + h * r.y);
+}
+
+
+// ---- odd primes q = 5, 7 (and, same construction, 3) -----------------------------------------------------------------------
+// The q = 3 idea for any odd prime: Z[w] with basis (1, w, ..., w^(d-1)), d = q - 1, and w^d = -(1 + w + ... + w^(d-1)).  The
+// coordinates of w^m are e_m for m < d and (-1, ..., -1) for m = d, so multiplication by w^t is the d x d integer matrix
+//     M_t[r][c] = [(t + c) mod q == r] - [(t + c) mod q == d]            (entries 0, +-1),
+// A' carries d rows per l_hi and d bytes per support element, B' the limbs of x_s times the coordinates of w^<h_lo, l_lo>, and
+// the same dense GEMM gives the d coordinates of every sample for a REAL strength; two launches (Re a, Im a) and
+// lt_combineq_kernel form X = sum_m (cre_m + i cim_m) w^m.  d is even, so rows (2 j, 2 j + 1) of one l_hi are one float2 of the
+// GEMM's output and the kernel runs unchanged with Mhi * d / 2 "row pairs" per delay row: planes [p][l_hi][j][l_lo].
+// 4 d^2 int8 MACs per pair and limb: 96 x 3 for q = 5, 216 x 3 for q = 7 (q = 3: 24 x 3) -- still far below the per-pair
+// epilogue of the plain K = n kernel for q = 5, about even for q = 7.
+template <int Q> struct LtQ {
+    static constexpr int D = Q - 1;
+    static constexpr int FW = Q <= 4 ? 2 : 3;                     // bits per packed digit
+};
+template <int Q>
+__device__ __forceinline__ uint32_t lt_packq(uint32_t l, int nd) {          // base-q digits of l, FW bits each, digit 0 lowest
+    uint32_t out = 0;
+    for (int i = 0; i < nd; ++i) {
+        out |= (l % (uint32_t)Q) << (LtQ<Q>::FW * i);
+        l /= (uint32_t)Q;
+    }
+    return out;
+}
+template <int Q>
+__device__ __forceinline__ uint32_t lt_dotq(uint32_t a, uint32_t b, int nd) {   // sum of digit products mod q
+    constexpr int FW = LtQ<Q>::FW;
+    constexpr uint32_t MK = (1u << FW) - 1u;
+    uint32_t acc = 0;
+    for (int i = 0; i < nd; ++i) acc += ((a >> (FW * i)) & MK) * ((b >> (FW * i)) & MK);
+    return acc % (uint32_t)Q;
+}
+
+// A'[(p * Mhi + l_hi) * d + r][d s + c] = M_t[r][c], t = (<h_hi(s), l_hi> + e[p][s]) mod q.  One thread owns one 4-byte word of
+// the K' range (its bytes belong to at most three support elements) of one l_hi and walks over the delay rows and the d rows.
+template <int Q>
+__global__ void __launch_bounds__(256)
+lt_agenq_kernel(const uint32_t* __restrict__ hhi, const uint8_t* __restrict__ e, long long S, long long Se, int b1, int P,
+                long long Mhi, long long Kp, uint32_t* __restrict__ A) {
+    constexpr int D = LtQ<Q>::D;
+    const long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lhi = blockIdx.y;
+    if (word * 4 >= Kp) return;
+    const uint32_t lp = lt_packq<Q>(lhi, b1);
+    long long sb[4];
+    int cb[4], tb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long kb = word * 4 + i;
+        sb[i] = kb / D;
+        cb[i] = (int)(kb - sb[i] * D);
+        tb[i] = sb[i] < S ? (int)lt_dotq<Q>(hhi[sb[i]], lp, b1) : -1;
+    }
+    const size_t row_words = (size_t)Kp / 4;
+    for (int p = 0; p < P; ++p) {
+        int m[4];                                                  // (t + c) mod q per byte, -1 for K padding
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m[i] = tb[i] < 0 ? -1 : (tb[i] + (int)e[(size_t)p * Se + sb[i]] + cb[i]) % Q;
+        uint32_t* o = A + ((size_t)p * (size_t)Mhi + lhi) * D * row_words + word;
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int v = m[i] < 0 ? 0 : (m[i] == r ? 1 : 0) - (m[i] == D ? 1 : 0);
+                w |= ((uint32_t)v & 0xffu) << (8 * i);
+            }
+            o[(size_t)r * row_words] = w;
+        }
+    }
+}
+
+// B'_l[l_lo][d s + c] = limb l of x_s times coordinate c of w^<h_lo(s), l_lo>; x_s = Re a_s (part 0) or Im a_s (part 1).
+template <int Q>
+__global__ void __launch_bounds__(256)
+lt_bgenq_kernel(const uint32_t* __restrict__ hlo, const int2* __restrict__ alimb, long long S, int b2, long long Nlo,
+                long long Kp, int part, uint32_t* __restrict__ Bq) {
+    constexpr int D = LtQ<Q>::D;
+    const long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long llo = blockIdx.y;
+    if (word * 4 >= Kp) return;
+    const uint32_t lp = lt_packq<Q>((uint32_t)llo, b2);
+    uint32_t words[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long kb = word * 4 + i;
+        const long long s = kb / D;
+        if (s >= S) break;
+        const int c = (int)(kb - s * D);
+        const int t = (int)lt_dotq<Q>(hlo[s], lp, b2);
+        const int coef = (t == c ? 1 : 0) - (t == D ? 1 : 0);
+        const int2 w = alimb[s];
+        const uint32_t lw = part ? (uint32_t)w.y : (uint32_t)w.x;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const int limb = (int)(int8_t)((lw >> (8 * l)) & 0xffu);
+            words[l] |= ((uint32_t)(coef * limb) & 0xffu) << (8 * i);
+        }
+    }
+    const size_t row_words = (size_t)Kp / 4;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) Bq[((size_t)l * Nlo + (size_t)llo) * row_words + word] = words[l];
+}
+
+// X = sum_m (cre_m + i cim_m) w^m, w = exp(2 pi i / q); planes [(p, l_hi)][j][l_lo] float2 = coordinates (2 j, 2 j + 1)
+template <int Q>
+__global__ void lt_combineq_kernel(const float2* __restrict__ cre, const float2* __restrict__ cim, long long rows /* P * Mhi */,
+                                   long long Nlo, float2* __restrict__ out) {
+    constexpr int D = LtQ<Q>::D;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * Nlo) return;
+    const long long row = i / Nlo, llo = i - row * Nlo;
+    float xr = 0.f, xi = 0.f;
+#pragma unroll
+    for (int j = 0; j < D / 2; ++j) {
+        const size_t at = ((size_t)row * (D / 2) + j) * (size_t)Nlo + (size_t)llo;
+        const float2 r = cre[at], m = cim[at];
+        float s0, c0, s1, c1;
+        sincospif(2.0f * (float)(2 * j) / (float)Q, &s0, &c0);
+        sincospif(2.0f * (float)(2 * j + 1) / (float)Q, &s1, &c1);
+        xr += r.x * c0 - m.x * s0 + r.y * c1 - m.y * s1;
+        xi += r.x * s0 + m.x * c0 + r.y * s1 + m.y * c1;
+    }
+    out[i] = make_float2(xr, xi);
 }
 
 // ---- the GEMM ---------------------------------------------------------------------------------------------
@@ -973,6 +1099,13 @@ extern "C" int qsft_eval_lattice_supported(int q, int n, int b, int P, int64_t S
         if ((long long)P * Mhi * 2 < LT_BM || (long long)P * Mhi * 2 >= 0x7fffffffLL || Nlo > 65535) return 0;
         return 1;
     }
+    if (q == 5 || q == 7) {                                  // dense Z[w] variant with d = q - 1 rows / bytes per element
+        const long long Mhi = ipow64(q, b1), Nlo = ipow64(q, b2);
+        if (b1 < 1 || b2 > 10 || LT_LIMBS * Nlo < LT_BN || Nlo > 65535) return 0;   // 3-bit digits fit 32 bits; B' rows >= one tile
+        if ((long long)P * Mhi * (q - 1) < LT_BM || (long long)P * Mhi * (q - 1) >= 0x7fffffffLL) return 0;
+        if (Mhi * (q - 1) / 2 >= 0x7fffffffLL) return 0;
+        return 1;
+    }
     if (q == 2) {                                            // q = 4 machinery on 2^b1 x 2^b2 lattices (lt_digits)
         if (b1 < 6 || b2 < 8 || b > 28) return 0;            // 2 * 2^b1 >= 128 rows, 2^b2 >= 256 columns
         if ((long long)P * ipow64(2, b1) * 2 >= 0x7fffffffLL) return 0;
@@ -1094,6 +1227,116 @@ int lt_eval_q3(const int8_t* M, const int8_t* D, const int8_t* loc, const float*
     return rc;
 }
 
+// odd primes q = 5, 7 ("odd primes" above): as lt_eval_q3 with d = q - 1 rows per l_hi and d bytes per support element
+template <int Q>
+int lt_eval_qodd(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths, int64_t S, int n, int b, int P, int ld,
+               float* out, int residual_passes, cudaStream_t st) {
+    constexpr int DQ = LtQ<Q>::D;
+    const int q = Q, b1 = b / 2, b2 = b - b1;
+    const long long Mhi = ipow64(Q, b1), Nlo = ipow64(Q, b2), Bn = Mhi * Nlo;
+    const long long Kp = ((long long)DQ * S + LT_BK - 1) / LT_BK * LT_BK;
+    double budget_gb = 8.0;
+    if (const char* env = getenv("QSFT_LATTICE_SCRATCH_GB")) {
+        const double v = atof(env);
+        if (v > 0.0) budget_gb = v;
+    }
+    long long Pc = (long long)(budget_gb * 1e9 / ((double)DQ * (double)Mhi * (double)Kp + 8.0 * (double)DQ * (double)Bn));
+    if (Pc < 1) Pc = 1;
+    if (Pc > P) Pc = P;
+    while ((Pc * DQ * Mhi + LT_BM - 1) / LT_BM > 65535) --Pc;
+    uint32_t *hhi = nullptr, *hlo = nullptr;
+    uint8_t *e = nullptr, *A = nullptr, *Bq = nullptr;
+    int2* alimb = nullptr;
+    unsigned int* amax = nullptr;
+    float2* planes = nullptr;
+    int rc = QSFT_OK;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (rc == QSFT_OK && qsft_scratch_alloc(p, bytes, st) != cudaSuccess) {
+            qsft_set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+            rc = QSFT_ECUDA;
+        }
+    };
+    const long long Se = (S + 3) & ~3ll;
+    alloc((void**)&hhi, (size_t)S * 4);
+    alloc((void**)&hlo, (size_t)S * 4);
+    alloc((void**)&e, (size_t)P * Se);
+    alloc((void**)&alimb, (size_t)S * 8);
+    alloc((void**)&amax, 16);
+    alloc((void**)&A, (size_t)Pc * DQ * Mhi * Kp);
+    alloc((void**)&Bq, (size_t)2 * LT_LIMBS * Nlo * Kp);                     // real-part and imaginary-part operand
+    alloc((void**)&planes, (size_t)2 * Pc * Bn * (DQ / 2) * sizeof(float2));
+    float* inv_scale = amax ? reinterpret_cast<float*>(amax + 2) : nullptr;
+    if (rc == QSFT_OK) {
+        const int T = 256;
+        const unsigned sb = (unsigned)((S + T - 1) / T);
+        const unsigned int init[2] = {0u, 0x7f7fffffu};
+        cudaMemcpyAsync(amax, init, 8, cudaMemcpyHostToDevice, st);
+        lt_prep_kernel<<<sb, T, (size_t)n * b + (size_t)P * n, st>>>(M, D, loc, S, Se, n, b, b1, P, ld, hhi, hlo, e, q, LtQ<Q>::FW);
+        lt_amax_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax);
+        g_qsft_launches.fetch_add(2, std::memory_order_relaxed);
+        int passes = 1 + (residual_passes > 0 ? 1 : 0);
+        if (residual_passes < 0) {
+            lt_amin_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax + 1);
+            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+            float mm[2] = {0.f, 0.f};
+            if (cudaMemcpyAsync(mm, amax, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+                qsft_set_error("reading the strength range failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = QSFT_ECUDA;
+            }
+            if (mm[1] < 0.1f * mm[0]) passes = 2;
+        }
+        static bool attr = false;   // (one flag per instantiation; setting the attribute twice is harmless)
+        if (!attr && !rc) {
+            if (cudaFuncSetAttribute(lt_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess) {
+                qsft_set_error("cudaFuncSetAttribute failed");
+                rc = QSFT_ECUDA;
+            }
+            attr = true;
+        }
+        const unsigned pb = (unsigned)((Kp / 4 + T - 1) / T);
+        uint8_t* Bre = Bq;
+        uint8_t* Bim = Bq + (size_t)LT_LIMBS * Nlo * Kp;
+        CUtensorMap ma, mbr, mbi;
+        if (!rc) rc = lt_make_map(&mbr, Bre, LT_LIMBS * Nlo, Kp);
+        if (!rc) rc = lt_make_map(&mbi, Bim, LT_LIMBS * Nlo, Kp);
+        for (long long p0 = 0; p0 < P && !rc; p0 += Pc) {
+            const long long pc = (P - p0 < Pc) ? (P - p0) : Pc;
+            const long long rows = pc * DQ * Mhi;
+            lt_agenq_kernel<Q><<<dim3(pb, (unsigned)Mhi), T, 0, st>>>(hhi, e + (size_t)p0 * Se, S, Se, b1, (int)pc, Mhi, Kp,
+                                                                   reinterpret_cast<uint32_t*>(A));
+            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+            rc = lt_make_map(&ma, A, rows, Kp);
+            if (rc) break;
+            float2* cre = planes;
+            float2* cim = planes + (size_t)pc * Bn * (DQ / 2);
+            for (int pass = 0; pass < passes && !rc; ++pass) {
+                lt_quant_kernel<<<sb, T, 0, st>>>(reinterpret_cast<const float2*>(strengths), S, amax, inv_scale, alimb, pass);
+                lt_bgenq_kernel<Q><<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp, 0, reinterpret_cast<uint32_t*>(Bre));
+                lt_bgenq_kernel<Q><<<dim3(pb, (unsigned)Nlo), T, 0, st>>>(hlo, alimb, S, b2, Nlo, Kp, 1, reinterpret_cast<uint32_t*>(Bim));
+                dim3 grid((unsigned)((Nlo + LT_BN - 1) / LT_BN), (unsigned)((rows + LT_BM - 1) / LT_BM));
+                lt_gemm_kernel<true><<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mbr, (int)(Kp / LT_BK), (int)(Mhi * (DQ / 2)), (int)Nlo,
+                                                                          (const float*)(inv_scale + pass), cre, pass, rows);
+                lt_gemm_kernel<true><<<grid, LT_THREADS, LT_SMEM, st>>>(ma, mbi, (int)(Kp / LT_BK), (int)(Mhi * (DQ / 2)), (int)Nlo,
+                                                                          (const float*)(inv_scale + pass), cim, pass, rows);
+                g_qsft_launches.fetch_add(5, std::memory_order_relaxed);
+            }
+            const long long N = pc * Bn;
+            lt_combineq_kernel<Q><<<(unsigned)((N + T - 1) / T), T, 0, st>>>(cre, cim, pc * Mhi, Nlo, reinterpret_cast<float2*>(out) + (size_t)p0 * Bn);
+            g_qsft_launches.fetch_add(1, std::memory_order_relaxed);
+            cudaError_t ce = cudaGetLastError();
+            if (ce != cudaSuccess) {
+                qsft_set_error("lattice GEMM (odd prime q) launch failed: %s", cudaGetErrorString(ce));
+                rc = QSFT_ECUDA;
+            }
+        }
+    }
+    void* frees[] = {hhi, hlo, e, alimb, amax, A, Bq, planes};
+    for (void* p : frees)
+        if (p) cudaFreeAsync(p, st);
+    return rc;
+}
+
+
 }  // namespace
 
 // residual_passes: 0 = one GEMM pass (20 bits below max|a|), 1 = a second pass over the quantisation residual accumulated
@@ -1101,12 +1344,14 @@ int lt_eval_q3(const int8_t* M, const int8_t* D, const int8_t* loc, const float*
 // back, i.e. synchronises the stream once).
 extern "C" int qsft_eval_synth_lattice_ex(const int8_t* M, const int8_t* D, const int8_t* loc, const float* strengths, int64_t S,
                                           int q, int n, int b, int P, int ld, float* out, int residual_passes, void* stream) {
-    QSFT_CHECK_ARG(qsft_eval_lattice_supported(q, n, b, P, S), "lattice evaluation supports q = 4 with 7 <= b <= 14, q = 3 with 7 <= b <= 20 and q = 2 with 14 <= b <= 28 only");
+    QSFT_CHECK_ARG(qsft_eval_lattice_supported(q, n, b, P, S), "lattice evaluation supports q = 4 (7 <= b <= 14), q = 3 (7 <= b <= 20), q = 2 (14 <= b <= 28) and q = 5 / 7 (see qsft_eval_lattice_supported) only");
     QSFT_CHECK_ARG(M && D && loc && strengths && out, "null pointer");
     QSFT_CHECK_ARG(ld >= n && ld % 16 == 0, "bad ld");
     QSFT_CHECK_ARG(residual_passes >= -1 && residual_passes <= 1, "residual_passes must be -1 (auto), 0 or 1");
     cudaStream_t st = (cudaStream_t)stream;
     if (q == 3) return lt_eval_q3(M, D, loc, strengths, S, n, b, P, ld, out, residual_passes, st);
+    if (q == 5) return lt_eval_qodd<5>(M, D, loc, strengths, S, n, b, P, ld, out, residual_passes, st);
+    if (q == 7) return lt_eval_qodd<7>(M, D, loc, strengths, S, n, b, P, ld, out, residual_passes, st);
     const int b1 = lt_split_b1(q, b), b2 = b - b1;
     const int spread = (q == 2) ? 1 : 0;                 // q = 2: one bit per lattice digit (lt_digits)
     const long long Mhi = ipow64(q, b1), Nlo = ipow64(q, b2);

@@ -107,7 +107,8 @@ class SyntheticSubsampledSignal(SubsampledSignal):
         P, S = D_rows.shape[0], self._loc_dev.shape[0]
         ok = ops.lattice_supported(self.q, self.n, self.b, P, S)
         if self.eval_impl == 3 and not ok:
-            raise ValueError("eval_impl=3 (lattice) supports q = 4 with 7 <= b <= 14, q = 3 with 7 <= b <= 20 and q = 2 with 14 <= b <= 28 only")
+            raise ValueError("eval_impl=3 (lattice) supports q = 4 (7 <= b <= 14), q = 3 (7 <= b <= 20), q = 2 (14 <= b <= 28) and q = 5 / 7 "
+                             "(ops.lattice_supported) only")
         if ok and (self.eval_impl == 3 or (self.eval_impl == 0 and S >= 512)):
             return ops.eval_synth_lattice(M, D_rows, self._loc_dev, self._a_dev, self.q, out=out,
                                           residual_passes=self._residual_passes)

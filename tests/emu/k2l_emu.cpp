@@ -6,12 +6,36 @@
 #include "../../qsft_b200/csrc/common.cuh"
 #include "_gen/k2l_device.inc"
 
+// odd primes through the generic Z[w] generators (q = 3 as well: cross-check of the specialised q = 3 kernels)
+template <int Q>
+static int emu_agenq(const uint32_t* hhi, const uint8_t* e, long long S, long long Se, int b1, int P, long long Mhi, long long Kp, uint32_t* A) {
+    const int T = 256;
+    emu::launch(dim3((unsigned)((Kp / 4 + T - 1) / T), (unsigned)Mhi), dim3(T), [&]() { lt_agenq_kernel<Q>(hhi, e, S, Se, b1, P, Mhi, Kp, A); });
+    return 0;
+}
+template <int Q>
+static int emu_bgenq(const uint32_t* hlo, const int32_t* alimb, long long S, int b2, long long Nlo, long long Kp, int part, uint32_t* Bq) {
+    const int T = 256;
+    emu::launch(dim3((unsigned)((Kp / 4 + T - 1) / T), (unsigned)Nlo), dim3(T),
+                [&]() { lt_bgenq_kernel<Q>(hlo, reinterpret_cast<const int2*>(alimb), S, b2, Nlo, Kp, part, Bq); });
+    return 0;
+}
+template <int Q>
+static int emu_combineq(const float* cre, const float* cim, long long rows, long long Nlo, float* out) {
+    const int T = 256;
+    emu::launch(dim3((unsigned)((rows * Nlo + T - 1) / T)), dim3(T), [&]() {
+        lt_combineq_kernel<Q>(reinterpret_cast<const float2*>(cre), reinterpret_cast<const float2*>(cim), rows, Nlo, reinterpret_cast<float2*>(out));
+    });
+    return 0;
+}
+
 extern "C" {
 
 int emu_lt_prep(const int8_t* M, const int8_t* D, const int8_t* loc, long long S, long long Se, int n, int b, int b1, int P,
                 int ld, uint32_t* hhi, uint32_t* hlo, uint8_t* e, int q) {
     const int T = 256;
-    emu::launch(dim3((unsigned)((S + T - 1) / T)), dim3(T), [&]() { lt_prep_kernel(M, D, loc, S, Se, n, b, b1, P, ld, hhi, hlo, e, q); });
+    const int fw = q <= 4 ? 2 : 3;
+    emu::launch(dim3((unsigned)((S + T - 1) / T)), dim3(T), [&]() { lt_prep_kernel(M, D, loc, S, Se, n, b, b1, P, ld, hhi, hlo, e, q, fw); });
     return 0;
 }
 
@@ -35,6 +59,20 @@ int emu_lt_combine3(const float* cre, const float* cim, long long N, float* out)
         lt_combine3_kernel(reinterpret_cast<const float2*>(cre), reinterpret_cast<const float2*>(cim), N, reinterpret_cast<float2*>(out));
     });
     return 0;
+}
+
+int emu_lt_agenq(int q, const uint32_t* hhi, const uint8_t* e, long long S, long long Se, int b1, int P, long long Mhi, long long Kp,
+                 uint32_t* A) {
+    return q == 3 ? emu_agenq<3>(hhi, e, S, Se, b1, P, Mhi, Kp, A) : q == 5 ? emu_agenq<5>(hhi, e, S, Se, b1, P, Mhi, Kp, A)
+                  : q == 7 ? emu_agenq<7>(hhi, e, S, Se, b1, P, Mhi, Kp, A) : -1;
+}
+int emu_lt_bgenq(int q, const uint32_t* hlo, const int32_t* alimb, long long S, int b2, long long Nlo, long long Kp, int part, uint32_t* Bq) {
+    return q == 3 ? emu_bgenq<3>(hlo, alimb, S, b2, Nlo, Kp, part, Bq) : q == 5 ? emu_bgenq<5>(hlo, alimb, S, b2, Nlo, Kp, part, Bq)
+                  : q == 7 ? emu_bgenq<7>(hlo, alimb, S, b2, Nlo, Kp, part, Bq) : -1;
+}
+int emu_lt_combineq(int q, const float* cre, const float* cim, long long rows, long long Nlo, float* out) {
+    return q == 3 ? emu_combineq<3>(cre, cim, rows, Nlo, out) : q == 5 ? emu_combineq<5>(cre, cim, rows, Nlo, out)
+                  : q == 7 ? emu_combineq<7>(cre, cim, rows, Nlo, out) : -1;
 }
 
 // pass 0: limbs of round(a * scale); pass 1: limbs of the quantisation residual (inv_scale holds two floats)

@@ -24,6 +24,9 @@ def emu():
     L.emu_lt_agen3.argtypes = [vp, vp, i64, i64, i32, i32, i64, i64, vp]
     L.emu_lt_bgen3.argtypes = [vp, vp, i64, i32, i64, i64, i32, vp]
     L.emu_lt_combine3.argtypes = [vp, vp, i64, vp]
+    L.emu_lt_agenq.argtypes = [i32, vp, vp, i64, i64, i32, i32, i64, i64, vp]
+    L.emu_lt_bgenq.argtypes = [i32, vp, vp, i64, i32, i64, i64, i32, vp]
+    L.emu_lt_combineq.argtypes = [i32, vp, vp, i64, i64, vp]
     L.emu_lt_quant.argtypes = [vp, i64, vp, vp, C.c_int]
     L.emu_lt_bgen.argtypes = [vp, vp, i64, i32, i64, i64, vp, i32]
     L.emu_lt_ttab.argtypes = [vp, i64, i32, i64, i64, vp, i32]
@@ -168,6 +171,66 @@ def test_emulated_q3_lattice_operands_reproduce_the_samples(emu, n, b, S, P, see
     dig = orc.query_digits(M, D, q)
     want = np.stack([orc.synth_eval_digits(dig[p].T, locq, aq, q) for p in range(P)])
     assert np.max(np.abs(got - want)) <= 2e-6 * np.sqrt(S) * float(np.max(np.abs(a)))        # fp32 planes + combination
+
+
+@pytest.mark.parametrize("q,n,b,S,P,seed", [(5, 10, 4, 37, 3, 0), (7, 8, 3, 29, 4, 1), (5, 30, 5, 16, 2, 2), (3, 12, 5, 37, 4, 3),
+                                            (7, 20, 4, 11, 2, 4)])
+def test_emulated_odd_prime_lattice_operands_reproduce_the_samples(emu, q, n, b, S, P, seed):
+    """Odd primes (q = 5, 7; q = 3 through the same generic kernels): Z[w] operands with d = q - 1 rows per l_hi and d bytes
+    per support element (lt_agenq / lt_bgenq), an exact integer matrix product in place of the tensor-core GEMM, the GEMM's
+    output layout (row pairs = float2, planes [p][l_hi][j][l_lo]) and lt_combineq reproduce the samples of the lattice."""
+    d, fw = q - 1, (2 if q <= 4 else 3)
+    rng = np.random.default_rng(seed)
+    M, D = rng.integers(0, q, (n, b)), rng.integers(0, q, (P, n))
+    locq = rng.integers(0, q, (n, S))
+    a = rng.uniform(0.3, 2, S) * np.exp(1j * rng.uniform(0, 2 * np.pi, S))
+    b1, b2 = b // 2, b - b // 2
+    Mhi, Nlo = q ** b1, q ** b2
+    ld = max(32, (n + 31) // 32 * 32)
+    Kp = (d * S + 127) // 128 * 128
+    Se = (S + 3) & ~3
+    M8, D8 = np.ascontiguousarray(M, dtype=np.int8), np.ascontiguousarray(D, dtype=np.int8)
+    loc = np.zeros((S, ld), dtype=np.int8)
+    loc[:, :n] = locq.T
+    hhi, hlo = np.zeros(S, dtype=np.uint32), np.zeros(S, dtype=np.uint32)
+    e = np.zeros((P, Se), dtype=np.uint8)
+    assert emu.emu_lt_prep(_p(M8), _p(D8), _p(loc), S, Se, n, b, b1, P, ld, _p(hhi), _p(hlo), _p(e), q) == 0
+    H = (M.T @ locq) % q
+    assert np.array_equal(hhi, sum(H[i].astype(np.int64) << (fw * (b1 - 1 - i)) for i in range(b1)))
+    assert np.array_equal(hlo, sum(H[b1 + i].astype(np.int64) << (fw * (b2 - 1 - i)) for i in range(b2)))
+    a32 = np.ascontiguousarray(a.astype(np.complex64))
+    inv_scale = np.zeros(2, dtype=np.float32)
+    alimb = np.zeros((S, 2), dtype=np.int32)
+    assert emu.emu_lt_quant(_p(a32), S, _p(inv_scale), _p(alimb), 0) == 0
+    limbs = alimb.view(np.int8).reshape(S, 2, 4)[:, :, :3].astype(np.int64)
+    vq = (limbs[:, :, 0] * 128 + limbs[:, :, 1]) * 128 + limbs[:, :, 2]
+    aq = (vq[:, 0] + 1j * vq[:, 1]) * float(inv_scale[0])
+    A = np.zeros((P, Mhi, d, Kp), dtype=np.int8)
+    assert emu.emu_lt_agenq(q, _p(hhi), _p(e), S, Se, b1, P, Mhi, Kp, _p(A)) == 0
+    assert set(np.unique(A)) <= {-1, 0, 1} and not A[..., d * S:].any()
+    # the d x d blocks are the multiplication matrices of w^t: column c = coordinates of w^(t + c)
+    lhi_d = np.stack([(np.arange(Mhi) // q ** (b1 - 1 - i)) % q for i in range(b1)])          # (b1, Mhi) MSB first
+    t = ((lhi_d.T @ H[:b1])[None, :, :] + ((D @ locq) % q)[:, None, :]) % q                   # (P, Mhi, S)
+    blocks = A[..., :d * S].reshape(P, Mhi, d, S, d)                                          # [p][l_hi][r][s][c]
+    m = (t[:, :, None, :, None] + np.arange(d)[None, None, None, None, :]) % q
+    want_blocks = (m == np.arange(d)[None, None, :, None, None]).astype(np.int8) - (m == d).astype(np.int8)
+    assert np.array_equal(blocks, want_blocks)
+    planes = []
+    for part in (0, 1):
+        Bq = np.zeros((3, Nlo, Kp), dtype=np.int8)
+        assert emu.emu_lt_bgenq(q, _p(hlo), _p(alimb), S, b2, Nlo, Kp, part, _p(Bq)) == 0
+        assert not Bq[..., d * S:].any() and np.abs(Bq[1:]).max() <= 64
+        acc = np.einsum("pmrk,lnk->lpmrn", A.astype(np.int64), Bq.astype(np.int64))
+        val = ((acc[0] * 128 + acc[1]) * 128 + acc[2]) * float(inv_scale[0])        # (P, Mhi, d coordinates, Nlo)
+        # what the GEMM kernel writes: rows (2 j, 2 j + 1) of one l_hi -> one float2 at [(p, l_hi)][j][l_lo]
+        pl = val.reshape(P * Mhi, d // 2, 2, Nlo).transpose(0, 1, 3, 2)
+        planes.append(np.ascontiguousarray(pl.astype(np.float32)))
+    out = np.zeros((P * Mhi * Nlo, 2), dtype=np.float32)
+    assert emu.emu_lt_combineq(q, _p(planes[0]), _p(planes[1]), P * Mhi, Nlo, _p(out)) == 0
+    got = (out[:, 0] + 1j * out[:, 1]).reshape(P, Mhi * Nlo)
+    dig = orc.query_digits(M, D, q)
+    want = np.stack([orc.synth_eval_digits(dig[p].T, locq, aq, q) for p in range(P)])
+    assert np.max(np.abs(got - want)) <= 4e-6 * np.sqrt(S) * float(np.max(np.abs(a)))        # fp32 planes + combination
 
 
 def test_ts_expand_variants_match_the_definition(emu):

@@ -338,12 +338,14 @@ def test_k2_lattice_matches_plain_path_and_oracle(q, n, b, S, P, seed, mode, mon
     assert np.max(np.abs(got[P - 1].cpu().numpy()[ls] - want)) <= 3e-6 * scale + 2e-6 * float(np.max(np.abs(a))) * np.sqrt(S)
 
 
-@pytest.mark.parametrize("n,b,S,P,seed,a_lo", [(12, 7, 300, 4, 0, 1.0), (30, 8, 5000, 9, 1, 1.0), (20, 9, 777, 3, 2, 0.01), (16, 8, 1, 5, 3, 1.0)])
-def test_k2_lattice_q3_matches_oracle_and_plain_path(n, b, S, P, seed, a_lo):
-    """q = 3 lattice evaluation (dense tcgen05 GEMM over Z[w] coefficients, ragged tiles, two real launches + combination)
-    against the plain K1 + K2 path on the whole lattice and against the fp64 oracle on a sample of it; a_lo = 0.01 takes the
-    residual pass."""
-    q = 3
+@pytest.mark.parametrize("q,n,b,S,P,seed,a_lo", [(3, 12, 7, 300, 4, 0, 1.0), (3, 30, 8, 5000, 9, 1, 1.0), (3, 20, 9, 777, 3, 2, 0.01),
+                                                 (3, 16, 8, 1, 5, 3, 1.0),
+                                                 (5, 12, 5, 300, 4, 4, 1.0), (5, 20, 6, 2000, 7, 5, 1.0), (5, 9, 7, 513, 2, 6, 0.01),
+                                                 (7, 10, 4, 400, 6, 7, 1.0), (7, 16, 5, 1500, 3, 8, 1.0), (7, 8, 3, 1, 5, 9, 1.0)])
+def test_k2_lattice_odd_q_matches_oracle_and_plain_path(q, n, b, S, P, seed, a_lo):
+    """Odd-prime lattice evaluation (dense tcgen05 GEMM over Z[w] coefficients, ragged tiles, two real launches + combination;
+    q = 3 specialised kernels, q = 5 / 7 the generic d = q - 1 construction) against the plain K1 + K2 path on the whole lattice
+    and against the fp64 oracle on a sample of it; a_lo = 0.01 takes the residual pass."""
     rng = np.random.RandomState(seed)
     M = rng.randint(0, q, size=(n, b))
     D = rng.randint(0, q, size=(P, n))
@@ -367,7 +369,8 @@ def test_k2_lattice_q3_matches_oracle_and_plain_path(n, b, S, P, seed, a_lo):
 
 
 def test_k2_lattice_unsupported_shapes():
-    assert not ops.lattice_supported(5, 10, 8, 3, 100)       # q = 2, 3 and 4 only
+    assert not ops.lattice_supported(11, 10, 4, 3, 100) and not ops.lattice_supported(6, 10, 4, 3, 100)   # q = 2, 3, 4, 5, 7 only
+    assert ops.lattice_supported(5, 10, 6, 3, 100) and not ops.lattice_supported(5, 10, 2, 3, 100)          # q = 5: 5^b2 >= 43 columns
     assert not ops.lattice_supported(2, 20, 13, 3, 100) and ops.lattice_supported(2, 20, 14, 3, 100)   # q = 2: 14 <= b <= 28
     assert not ops.lattice_supported(3, 10, 6, 3, 100)       # q = 3: b too small
     assert ops.lattice_supported(3, 10, 8, 3, 100)
