@@ -271,7 +271,10 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     assert L.qsft_eval_lattice_supported(4, 40, 10, 41, 100000) == 1
     assert L.qsft_eval_lattice_supported(3, 40, 10, 41, 100000) == 1   # q = 3: dense Z[w] variant
     assert L.qsft_eval_lattice_supported(3, 40, 6, 41, 100000) == 0    # ... needs b >= 7
-    assert L.qsft_eval_lattice_supported(5, 40, 10, 41, 100000) == 0
+    assert L.qsft_eval_lattice_supported(5, 40, 10, 41, 100000) == 1   # q = 5 / 7: generic Z[w] variant
+    assert L.qsft_eval_lattice_supported(7, 40, 3, 41, 100000) == 1 and L.qsft_eval_lattice_supported(5, 40, 14, 41, 100000) == 0
+    assert L.qsft_eval_lattice_supported(11, 40, 6, 41, 100000) == 0 and L.qsft_eval_lattice_supported(6, 40, 6, 41, 100000) == 0
+    assert L.qsft_eval_lattice_supported(2, 40, 14, 41, 100000) == 1 and L.qsft_eval_lattice_supported(2, 40, 13, 41, 100000) == 0
     assert L.qsft_eval_lattice_supported(4, 40, 6, 41, 100000) == 0
     bad(L.qsft_eval_synth_lattice(one, one, one, one, 100, 5, 10, 8, 3, 32, one, null), "q = 4")
     desc = _lib.PeelDesc(q=4, n=10, b=4, C=3, P=11, P_src=11, channel=0, source=0, rs_t=0, rs_s=0, ld=32, cutoff=1e-9,
