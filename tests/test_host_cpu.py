@@ -276,7 +276,7 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     assert L.qsft_eval_lattice_supported(11, 40, 6, 41, 100000) == 0 and L.qsft_eval_lattice_supported(6, 40, 6, 41, 100000) == 0
     assert L.qsft_eval_lattice_supported(2, 40, 14, 41, 100000) == 1 and L.qsft_eval_lattice_supported(2, 40, 13, 41, 100000) == 0
     assert L.qsft_eval_lattice_supported(4, 40, 6, 41, 100000) == 0
-    bad(L.qsft_eval_synth_lattice(one, one, one, one, 100, 5, 10, 8, 3, 32, one, null), "q = 4")
+    bad(L.qsft_eval_synth_lattice(one, one, one, one, 100, 11, 10, 8, 3, 32, one, null), "q = 4")
     desc = _lib.PeelDesc(q=4, n=10, b=4, C=3, P=11, P_src=11, channel=0, source=0, rs_t=0, rs_s=0, ld=32, cutoff=1e-9,
                          MT=16, D=16, rs_exp=0, rs_log=0)
     cnt = C.c_int64(0)
