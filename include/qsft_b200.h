@@ -174,6 +174,13 @@ typedef struct {
     int64_t max_uniq;
 } qsft_uniq;
 
+/* The distinct-k list in the result layout of QSFT.transform (qsft/qsft.py:247-255: first-seen order, mean over the finds of
+ * a k): entry i of the outputs is list entry order[i] (`order` = the entries sorted by uniq_key, device pointer, n_uniq int64)
+ * -- k_out (n_uniq, n) int8 without padding, mean_out (n_uniq) complex128 = uniq_sum / uniq_cnt, cnt_out (n_uniq) int32.
+ * One kernel in place of the gathers, the slice copy and the host-side division.                                          */
+int qsft_peel_distinct(const qsft_uniq* uq, const int64_t* order, int64_t n_uniq, int n, int ld, int8_t* k_out,
+                       double* mean_out, int32_t* cnt_out, void* stream);
+
 /* Collapse finds [f_begin, f_begin + n_finds) of round `round` (find_id must be the table of that round) into the
  * distinct-k list; counters[4] is the running number of distinct k (atomic).                                     */
 int qsft_peel_reduce(const qsft_peel_desc* d, const int64_t* find_cj, const int8_t* find_k, const float* find_rho,

@@ -14,7 +14,7 @@ EXPORTS = [
     "qsft_last_error", "qsft_version", "qsft_launch_count", "qsft_reset_launch_count", "qsft_host_pack_digits",
     "qsft_query_lattice", "qsft_dec_to_qary", "qsft_qary_to_dec", "qsft_eval_synth", "qsft_gwht_batch", "qsft_gwht_batch_bcast", "qsft_gwht_batch_mcast", "qsft_gwht_batch_scatter",
     "qsft_eval_lattice_supported", "qsft_eval_synth_lattice", "qsft_eval_synth_lattice_ex",
-    "qsft_peel_classify", "qsft_peel_apply", "qsft_peel_reduce", "qsft_peel", "qsft_peel_blocks", "qsft_peel_blocks_sharded", "qsft_peel_sharded_workspace_bytes", "qsft_closed_form_bins",
+    "qsft_peel_classify", "qsft_peel_apply", "qsft_peel_reduce", "qsft_peel_distinct", "qsft_peel", "qsft_peel_blocks", "qsft_peel_blocks_sharded", "qsft_peel_sharded_workspace_bytes", "qsft_closed_form_bins",
     "qsft_singleton_detect", "qsft_detect_mle", "qsft_k3_ticket_decode", "qsft_add_noise",
 ]
 
@@ -96,6 +96,7 @@ def lib():
     L.qsft_peel_apply.argtypes = [pd, vp, i64, i64, vp, vp, vp, vp, i64, i64, i32, vp, vp]
     pu = C.POINTER(Uniq)
     L.qsft_peel_reduce.argtypes = [pd, vp, vp, vp, vp, i64, i64, i32, pu, vp, vp]
+    L.qsft_peel_distinct.argtypes = [pu, vp, i64, i32, i32, vp, vp, vp, vp]
     L.qsft_peel.argtypes = [pd, vp, vp, vp, vp, vp, vp, i64, vp, pu, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), vp]
     L.qsft_peel_blocks.argtypes = [pd, C.POINTER(vp), i64, vp, vp, vp, vp, vp, i64, vp, pu, C.POINTER(i64), C.POINTER(i64),
                                    C.POINTER(i32), vp]

@@ -481,6 +481,43 @@ extern "C" int qsft_peel_reduce(const qsft_peel_desc* h, const int64_t* find_cj,
                      n_finds, f_begin + n_finds, round, o, counters, (cudaStream_t)stream);
 }
 
+namespace {
+// distinct-k list -> the host's result layout, in the order `order` gives (sorted first-seen keys): compact digit rows
+// (n bytes each, no padding), mean = sum / count in double (what the host did after the copy), counts
+__global__ void __launch_bounds__(256)
+k4_distinct_gather_kernel(const long long* __restrict__ order, long long nu, int n, int ld, const int8_t* __restrict__ uniq_k,
+                          const float2* __restrict__ uniq_sum, const int* __restrict__ uniq_cnt, int8_t* __restrict__ k_out,
+                          double2* __restrict__ mean_out, int* __restrict__ cnt_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one output digit
+    if (i >= nu * n) return;
+    const long long row = i / n;
+    const int u = (int)(i - row * n);
+    const long long src = order[row];
+    k_out[i] = uniq_k[(size_t)src * ld + u];
+    if (u == 0) {
+        const float2 s = uniq_sum[src];
+        const int c = uniq_cnt[src];
+        mean_out[row] = make_double2((double)s.x / (double)c, (double)s.y / (double)c);
+        cnt_out[row] = c;
+    }
+}
+}  // namespace
+
+extern "C" int qsft_peel_distinct(const qsft_uniq* uq, const int64_t* order, int64_t n_uniq, int n, int ld, int8_t* k_out,
+                                  double* mean_out, int32_t* cnt_out, void* stream) {
+    QSFT_CHECK_ARG(uq && uq->uniq_k && uq->uniq_sum && uq->uniq_cnt, "incomplete qsft_uniq");
+    QSFT_CHECK_ARG(n_uniq >= 0 && n_uniq <= uq->max_uniq && n >= 1 && ld >= n, "bad shape");
+    if (n_uniq == 0) return QSFT_OK;
+    QSFT_CHECK_ARG(order && k_out && mean_out && cnt_out, "null pointer");
+    QSFT_CHECK_ARG(((uintptr_t)mean_out & 15) == 0, "mean_out must be 16-byte aligned");
+    const long long total = (long long)n_uniq * n;
+    k4_distinct_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)order, (long long)n_uniq, n, ld, uq->uniq_k, reinterpret_cast<const float2*>(uq->uniq_sum), uq->uniq_cnt,
+        k_out, reinterpret_cast<double2*>(mean_out), cnt_out);
+    QSFT_LAUNCHED();
+    return QSFT_OK;
+}
+
 extern "C" int qsft_peel(const qsft_peel_desc* h, float* U, int64_t* find_cj, int8_t* find_k, float* find_rho,
                          int32_t* find_round, int32_t* find_id, int64_t max_finds, unsigned long long* counters,
                          const qsft_uniq* uq, int64_t* n_finds_out, int64_t* n_uniq_out, int* n_rounds_out, void* stream) {

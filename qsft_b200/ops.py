@@ -4,7 +4,6 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-import threading
 
 import numpy as np
 import torch
@@ -58,28 +57,12 @@ class _timed:
         return False
 
 
-_PINNED = threading.local()
-
-
-def _pinned(tag, shape, dtype):
-    """Reusable page-locked staging buffer (cudaHostAlloc synchronises the device and costs milliseconds, so buffers are
-    kept for the life of the thread and only grow; one set per host thread)."""
-    n = 1
-    for d in shape:
-        n *= int(d)
-    cache = _PINNED.__dict__.setdefault("buffers", {})
-    buf = cache.get((tag, dtype))
-    if buf is None or buf.numel() < n:
-        buf = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
-        cache[(tag, dtype)] = buf
-    return buf[:n].view(shape)
-
-
-def _pinned_upload_block(shape, dtype):
-    """Page-locked block for ONE host -> device copy, from torch's caching host allocator: unlike the reusable buffers above
-    it is not handed out again before the asynchronous copy that reads it has run (the allocator records the stream), so a
-    host that runs ahead of the GPU -- QSFT.transform(output="device_async") -- cannot overwrite data still waiting for its
-    DMA.  After the first use of a size this costs microseconds."""
+def _pinned_block(shape, dtype):
+    """Page-locked block for ONE copy to or from the device, from torch's caching host allocator: it is not handed out again
+    before the asynchronous copy that uses it has run (the allocator records the stream), so a host that runs ahead of the GPU
+    -- QSFT.transform(output="device_async") -- cannot overwrite data still waiting for its DMA, and results can be handed to
+    the caller as views of the block.  After the first use of a size this costs microseconds (cudaHostAlloc itself
+    synchronises the device and costs milliseconds)."""
     return torch.empty(tuple(int(d) for d in shape), dtype=dtype, pin_memory=True)
 
 
@@ -124,7 +107,7 @@ def pad_digits(rows, ld, device, transposed=False):
     N, n = a.shape
     if ld < n:
         raise ValueError("ld must be at least the number of digits")
-    stage = _pinned_upload_block((N, ld), torch.int8)
+    stage = _pinned_block((N, ld), torch.int8)
     if N:
         isz = a.dtype.itemsize
         _lib.check(_lib.lib().qsft_host_pack_digits(C.c_void_p(a.ctypes.data), isz, N, n, a.strides[0] // isz, a.strides[1] // isz,
@@ -532,26 +515,28 @@ class PeelProblem:
 
     def distinct(self, n_uniq=None):
         """Host copy of the distinct-k list in the reference's first-seen order:
-        (k (K, n) int8, mean rho (K,) complex128, count (K,) int32).  The entries are ordered on the device and come
-        back through pinned buffers with one synchronisation."""
+        (k (K, n) int8, mean rho (K,) complex128, count (K,) int32).  The entries are ordered, gathered and averaged on the
+        device (qsft_peel_distinct) and come back through pinned blocks with one synchronisation."""
         nu = self.n_uniq if n_uniq is None else n_uniq
         if nu == 0:
             return np.zeros((0, self.n), dtype=np.int8), np.zeros(0, dtype=np.complex128), np.zeros(0, dtype=np.int32)
         order = torch.argsort(self.uniq_key[:nu])                       # keys are unique: (round << 48) | (c B + j)
-        k_d = self.uniq_k[:nu].index_select(0, order)[:, :self.n].contiguous()
-        s_d = torch.view_as_real(self.uniq_sum[:nu].index_select(0, order))
-        c_d = self.uniq_cnt[:nu].index_select(0, order)
-        k_h = _pinned("distinct_k", k_d.shape, k_d.dtype)
-        s_h = _pinned("distinct_sum", s_d.shape, s_d.dtype)
-        c_h = _pinned("distinct_cnt", c_d.shape, c_d.dtype)
+        dev = self.device
+        k_d = torch.empty((nu, self.n), dtype=torch.int8, device=dev)
+        m_d = torch.empty((nu, 2), dtype=torch.float64, device=dev)
+        c_d = torch.empty(nu, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().qsft_peel_distinct(C.byref(self.uniq), _ptr(order), nu, self.n, self.ld, _ptr(k_d), _ptr(m_d),
+                                                     _ptr(c_d), _stream()))
+        # page-locked blocks of their own (caching host allocator): the arrays handed out are views of them, no host copy
+        k_h = _pinned_block(k_d.shape, k_d.dtype)
+        m_h = _pinned_block(m_d.shape, m_d.dtype)
+        c_h = _pinned_block(c_d.shape, c_d.dtype)
         k_h.copy_(k_d, non_blocking=True)
-        s_h.copy_(s_d, non_blocking=True)
+        m_h.copy_(m_d, non_blocking=True)
         c_h.copy_(c_d, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        cnt = c_h.numpy().copy()
-        sums = s_h.numpy().astype(np.float64)
-        mean = (sums[:, 0] + 1j * sums[:, 1]) / cnt
-        return k_h.numpy().copy(), mean, cnt
+        torch.cuda.current_stream(dev).synchronize()
+        return k_h.numpy(), m_h.numpy().view(np.complex128).reshape(nu), c_h.numpy()
 
     def reduce(self, find_cj, find_k, find_rho, find_id, f_begin, n_finds, round_no):
         with torch.cuda.device(self.device):

@@ -76,7 +76,7 @@ class SyntheticSubsampledSignal(SubsampledSignal):
             self._loc_dev = ops.pad_digits(self.locq, self.ld, self.device, transposed=True)
         if self._a_dev is None:
             # through a pinned block: a pageable .to(device) is a synchronous staged copy
-            stage = ops._pinned_upload_block((len(self.strengths),), torch.complex64)
+            stage = ops._pinned_block((len(self.strengths),), torch.complex64)
             stage.numpy()[...] = self.strengths
             self._a_dev = stage.to(self.device, non_blocking=True)
         # precision of the lattice GEMM (ops.eval_synth_lattice): strengths of very different sizes need the residual pass for
