@@ -73,7 +73,11 @@ class SyntheticSubsampledSignal(SubsampledSignal):
         self._loc_dev = kwargs.get("loc_dev")
         self._a_dev = kwargs.get("a_dev")
         if self._loc_dev is None:
-            self._loc_dev = ops.pad_digits(self.locq, self.ld, self.device, transposed=True)
+            S_rows = np.asarray(self.locq).shape[1]
+            if self.dist is not None and self.dist.world_size > 1 and S_rows >= ops.SHARD_PACK_MIN_ROWS:
+                self._loc_dev = ops.pad_digits_sharded(self.locq, self.ld, self.device, self.dist, transposed=True)
+            else:
+                self._loc_dev = ops.pad_digits(self.locq, self.ld, self.device, transposed=True)
         if self._a_dev is None:
             # through a pinned block: a pageable .to(device) is a synchronous staged copy
             stage = ops._pinned_block((len(self.strengths),), torch.complex64)

@@ -58,6 +58,17 @@ def _worker(rank, world, port, out):
                 err = float(np.max(np.abs(v - want_v))) if same and len(v) else 0.0
                 if not same or err > 1e-5 * max(1.0, float(np.max(np.abs(want_v)))) or len(k) < 0.9 * case[2]:
                     ok, msg = False, f"case {ci} mode {mode}: same={same} err={err} found={len(k)}"
+        # the support staged by the ranks together (each packs and uploads its slice, one all-gather): same result
+        from qsft_b200 import ops as _ops
+        keep, _ops.SHARD_PACK_MIN_ROWS = _ops.SHARD_PACK_MIN_ROWS, 1
+        try:
+            for ci in (0, 2):                                              # S = 1000 (even split) and S = 60 over two ranks
+                want_k, want_v = _transform(CASES[ci], None)
+                k, v = _transform(CASES[ci], DistContext(peel_mode="sharded"))
+                if not (k.shape == want_k.shape and np.array_equal(k, want_k) and float(np.max(np.abs(v - want_v))) <= 1e-5):
+                    ok, msg = False, f"sharded support staging, case {ci}: result differs"
+        finally:
+            _ops.SHARD_PACK_MIN_ROWS = keep
         # asynchronous result (nothing read back inside the call): two transforms queued, both report the right support size
         import qsft_b200 as qb
         n, q, S, b, C, R, chan, noise_sd = CASES[0]
