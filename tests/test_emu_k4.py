@@ -261,3 +261,42 @@ def test_emulated_classify_bin_ranges(emu, impl):
     assert parts["nf"] == full["nf"] and parts["nm"] == full["nm"]
     assert np.array_equal(parts["cj"], full["cj"]) and np.array_equal(parts["k"], full["k"])
     assert np.array_equal(parts["fid"] >= 0, full["fid"] >= 0) and not (parts["fid"] == -7).any()
+
+
+@pytest.mark.parametrize("q,n,b,Cn", [(2, 3, 3, 4), (2, 4, 2, 3), (3, 2, 2, 2), (2, 5, 4, 4)])
+def test_emulated_peel_tiny_alphabet_guard_vs_oracle(emu, q, n, b, Cn):
+    """q^n <= 15 C B: the loop of qsft.py:151 can stop on `num_peeling < q^n` before the round limit (a fuzz of
+    the emulated host-driven loop had diverged there).  Host-driven rounds (impl 1) and the on-device loop kernel (impl 2)
+    on the oracle's bins == the oracle's transform: same keys in the same order, same number of rounds."""
+    import qsft_oracle as orc
+    for seed in range(8):
+        np.random.seed(300 + seed)
+        S = max(1, min(q ** n // 2, 2 + seed % 4))
+        qa = {"query_method": "complex", "num_subsample": Cn, "delays_method_source": "identity", "subsampling_method": "qsft",
+              "delays_method_channel": "identity", "num_repeat": 1, "b": b}
+        signal_w, locq, strengths = orc.generate_signal_w(n, q, S, 1, 1)
+        sig = orc.OracleSignal(n, q, qa, locq, strengths, noise_sd=0.0, signal_w=signal_w)
+        Ms, Ds, Us = sig.get_MDU(Cn, 1, b)
+
+        class Fixed:
+            noise_sd = 0.0
+
+            def __init__(self):
+                self.q, self.n = q, n
+
+            def get_source_parity(self):
+                return sig.get_source_parity()
+
+            def get_MDU(self, *a, **k):
+                return Ms, Ds, [[np.array(u) for u in us] for us in Us], None
+
+        want = orc.transform(Fixed(), Cn, 1, b, "identity", "identity", report=True)
+        U = np.ascontiguousarray(np.array([np.vstack(us) for us in Us]).astype(np.complex64))
+        D = np.array([np.vstack(d) for d in Ds])
+        prob = Problem(q, n, b, Ms, D, sig.get_source_parity(), 0, 1e-9)
+        for impl in (1, 2):
+            keys, vals, _, rounds = prob.peel(emu, U.copy(), impl)
+            assert keys == list(want["gwht"].keys()), (seed, impl)
+            assert rounds == want["rounds"], (seed, impl, rounds, want["rounds"])
+            if keys:
+                assert np.max(np.abs(vals - np.array(list(want["gwht"].values())))) <= 1e-5, (seed, impl)
