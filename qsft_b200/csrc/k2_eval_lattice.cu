@@ -261,6 +261,7 @@ lt_agen_kernel(const uint32_t* __restrict__ hhi, const uint8_t* __restrict__ e, 
 // ((w ^ m) - m with SIMD-in-word subtract).  One thread owns two support elements and walks over LT_BGEN_LL consecutive
 // l_lo: the limb bytes are loaded and packed once, only the two rotations change per l_lo.
 constexpr int LT_BGEN_LL = 8;
+static_assert(LT_BGEN_LL == 8, "lt_bgen_kernel steps through the three low bits of l_lo");
 __global__ void __launch_bounds__(256)
 lt_bgen_kernel(const uint32_t* __restrict__ hlo, const int2* __restrict__ alimb, long long S, int b2, long long Nlo,
                long long Kp, uint32_t* __restrict__ Bq, int spread) {
@@ -286,13 +287,21 @@ lt_bgen_kernel(const uint32_t* __restrict__ hlo, const int2* __restrict__ alimb,
     }
     const size_t row_words = (size_t)Kp / 4;
     const long long llo_begin = (long long)blockIdx.y * LT_BGEN_LL;
-#pragma unroll 4
+    // <h_lo, l_lo> is additive in the three low bits of l_lo (llo_begin is a multiple of eight): two dot products per group of
+    // rows instead of two per row (q = 4: bits 0 / 1 are digit 0, bit 2 the low bit of digit 1; q = 2: one digit per bit)
+    const uint32_t ldig0 = lt_digits((uint32_t)llo_begin, spread);
+    const uint32_t rb0 = dot4(h0w, ldig0, b2), rb1 = dot4(h1w, ldig0, b2);
+    const uint32_t f00 = h0w & 3u, f01 = (h0w >> 2) & 3u, f02 = (h0w >> 4) & 3u;
+    const uint32_t f10 = h1w & 3u, f11 = (h1w >> 2) & 3u, f12 = (h1w >> 4) & 3u;
+    const uint32_t c00 = f00, c01 = spread ? f01 : 2u * f00, c02 = spread ? f02 : f01;
+    const uint32_t c10 = f10, c11 = spread ? f11 : 2u * f10, c12 = spread ? f12 : f11;
+#pragma unroll
     for (int j = 0; j < LT_BGEN_LL; ++j) {
         const long long llo = llo_begin + j;
         if (llo >= Nlo) break;
         // dead elements have zero limbs: their rotation does not matter
-        const uint32_t ldig = lt_digits((uint32_t)llo, spread);
-        const uint32_t r0 = dot4(h0w, ldig, b2), r1 = dot4(h1w, ldig, b2);
+        const uint32_t r0 = (rb0 + ((j & 1) ? c00 : 0u) + ((j & 2) ? c01 : 0u) + ((j & 4) ? c02 : 0u)) & 3u;
+        const uint32_t r1 = (rb1 + ((j & 1) ? c10 : 0u) + ((j & 2) ? c11 : 0u) + ((j & 4) ? c12 : 0u)) & 3u;
         // rotation r: swap (x, y) iff r & 1; negate byte 0 iff (r & 1) ^ (r >> 1); negate byte 1 iff r >> 1
         const uint32_t b0 = r0 & 1u, h0 = r0 >> 1, b1 = r1 & 1u, h1 = r1 >> 1;
         const uint32_t sel = (b0 ? 0x01u : 0x10u) | ((b1 ? 0x23u : 0x32u) << 8);
@@ -311,7 +320,16 @@ lt_bgen_kernel(const uint32_t* __restrict__ hlo, const int2* __restrict__ alimb,
 // the same way.  A' is then a pure function of (T + E2) mod 4, generated slab by slab in shared memory by the GEMM CTAs.
 // One thread owns the sixteen support elements of word w and walks over LT_TTAB_LL consecutive l_hi (the bin-hash words
 // are loaded once); blockIdx.y enumerates groups of LT_TTAB_LL rows.
-constexpr int LT_TTAB_LL = 8;
+constexpr int LT_TTAB_LL = 64;
+// field-wise (a + b) mod 4 on sixteen packed two-bit fields
+__device__ __forceinline__ uint32_t lt_add4(uint32_t x, uint32_t y) {
+    constexpr uint32_t H = 0xAAAAAAAAu;
+    return ((x & ~H) + (y & ~H)) ^ ((x ^ y) & H);
+}
+// The sixty-four rows of a group differ from its first row l0 (a multiple of 64) only in the six low BITS of the lattice index,
+// and <h, l> is additive in them: bit k of the index adds the word G[k] -- for q = 4 bits (2 d, 2 d + 1) belong to digit d and
+// add H_d and 2 H_d, H_d = the sixteen elements' field d of h; for q = 2 (one bit per digit, lt_digits) bit d adds H_d -- so one
+// row costs one packed add instead of sixteen popcount dot products (ncu r4l: 56 us per config-5 block before).
 __global__ void __launch_bounds__(256)
 lt_ttab_kernel(const uint32_t* __restrict__ hhi, long long S, int b1, long long Tw, long long Mhi, uint32_t* __restrict__ T,
                int spread) {
@@ -324,14 +342,40 @@ lt_ttab_kernel(const uint32_t* __restrict__ hhi, long long S, int b1, long long 
         h[i] = s < S ? hhi[s] : 0u;                     // dead elements: rotation 0, like the per-element guard before
     }
     const long long l0 = (long long)blockIdx.y * LT_TTAB_LL;
-    for (int j = 0; j < LT_TTAB_LL; ++j) {
-        const long long lhi = l0 + j;
-        if (lhi >= Mhi) break;
-        uint32_t word = 0;
-        const uint32_t ldig = lt_digits((uint32_t)lhi, spread);
+    uint32_t base = 0;
+    {
+        const uint32_t ldig = lt_digits((uint32_t)l0, spread);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) word |= dot4(h[i], ldig, b1) << (2 * i);
-        T[(size_t)lhi * Tw + w] = word;
+        for (int i = 0; i < 16; ++i) base |= dot4(h[i], ldig, b1) << (2 * i);
+    }
+    uint32_t G[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        uint32_t Hd = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) Hd |= ((h[i] >> (2 * d)) & 3u) << (2 * i);
+        G[d] = Hd;
+    }
+    if (!spread) {                                      // digits 0 .. 2: (H_0, 2 H_0, H_1, 2 H_1, H_2, 2 H_2)
+        const uint32_t H0 = G[0], H1 = G[1], H2 = G[2];
+        G[0] = H0; G[1] = lt_add4(H0, H0);
+        G[2] = H1; G[3] = lt_add4(H1, H1);
+        G[4] = H2; G[5] = lt_add4(H2, H2);
+    }
+    uint32_t L[8];
+    L[0] = 0u; L[1] = G[0]; L[2] = G[1]; L[3] = lt_add4(G[0], G[1]);
+    L[4] = G[2]; L[5] = lt_add4(G[2], G[0]); L[6] = lt_add4(G[2], G[1]); L[7] = lt_add4(L[6], G[0]);
+#pragma unroll
+    for (int hi = 0; hi < 8; ++hi) {
+        uint32_t th = base;
+        if (hi & 1) th = lt_add4(th, G[3]);
+        if (hi & 2) th = lt_add4(th, G[4]);
+        if (hi & 4) th = lt_add4(th, G[5]);
+#pragma unroll
+        for (int lo = 0; lo < 8; ++lo) {
+            const long long lhi = l0 + hi * 8 + lo;
+            if (lhi < Mhi) T[(size_t)lhi * Tw + w] = lt_add4(th, L[lo]);
+        }
     }
 }
 

@@ -40,7 +40,7 @@ def _p(a):
 
 
 @pytest.mark.parametrize("q,n,b,S,P,seed", [(4, 12, 7, 37, 5, 0), (4, 40, 8, 90, 3, 1), (4, 9, 7, 64, 2, 2),
-                                            (2, 20, 9, 50, 4, 3), (2, 64, 12, 33, 3, 4)])
+                                            (2, 20, 9, 50, 4, 3), (2, 64, 12, 33, 3, 4), (2, 24, 15, 21, 2, 5)])
 def test_emulated_lattice_operands_reproduce_the_samples(emu, q, n, b, S, P, seed):
     """q = 4, and q = 2 through the same kernels (digits doubled, lattice indices spread to one field per bit)."""
     spread, mul = (1, 2) if q == 2 else (0, 1)
