@@ -334,6 +334,9 @@ int qsft_k3_q4_tma(float* xf, int64_t batch, int b, const K3Peers& peers_in, cud
         const long long l2_rows = (48ll << 20) / (B * 8);
         if (l > l2_rows) l = l2_rows;
         if (l < 1) l = 1;
+        // 4^10 (two tiles per CTA in flight cover 1.16 blocks): one more block of lead measured 0.176 against 0.181 ms (r4n: lag
+        // 1 / 2 / 3 / 4 / 6 = 0.212 / 0.181 / 0.176 / 0.190 / 0.208 ms for 41 rows; the producer's poll interval made no difference)
+        if (b == 10 && l == 2) l = 3;
         lag = (int)l;
     }
     unsigned int* done = nullptr;
