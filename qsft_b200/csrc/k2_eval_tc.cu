@@ -302,10 +302,11 @@ k2_eval_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
-// q = 4 fast path: support digit rows scaled by 8 (see the epilogue)
-__global__ void scale8_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, long long words) {
+// q = 4 fast path: support digit rows scaled by 8 (see the epilogue).  q = 2 takes the same path with the digits scaled by 16:
+// (-1)^t = i^(2 t), so (16 t) & 24 = 16 (t & 1) selects a or -a in the same table.
+__global__ void scale8_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, long long words, int shift) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < words) out[i] = in[i] << 3;     // bytes are <= 3, no carry across byte lanes
+    if (i < words) out[i] = in[i] << shift;     // bytes are <= 3 (q = 4, shift 3) or <= 1 (q = 2, shift 4): no carry across byte lanes
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -376,13 +377,13 @@ int qsft_eval_synth_tc(const int8_t* qdig, int64_t N, const int8_t* loc, const f
     (void)n;
     QSFT_CHECK_ARG(((uintptr_t)qdig & 15) == 0 && ((uintptr_t)loc & 15) == 0, "digit buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const bool q4 = (q == 4);
+    const bool q4 = (q == 4 || q == 2);          // quarter-turn phases: the LOP3 + LDS.64 + 2 FADD epilogue
     int8_t* loc8 = nullptr;
-    if (q4) {  // stream-ordered scratch copy of the support digits, scaled by 8
+    if (q4) {  // stream-ordered scratch copy of the support digits, scaled by 8 (q = 4) / 16 (q = 2)
         const long long words = S * (long long)ld / 4;
         QSFT_CUDA(qsft_scratch_alloc((void**)&loc8, (size_t)S * ld, st));
         scale8_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(loc),
-                                                                       reinterpret_cast<uint32_t*>(loc8), words);
+                                                                       reinterpret_cast<uint32_t*>(loc8), words, q == 4 ? 3 : 4);
         QSFT_LAUNCHED();
     }
     CUtensorMap ma, mb;
