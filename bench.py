@@ -365,7 +365,11 @@ def run_ours(a):
     # ---- loop B: end to end through the public API with host buffers (H2D + D2H inside) -------------------
     # result container: host arrays (locations (K, n) int8, values (K,) complex128) -- output="arrays"; the
     # reference-compatible dict {tuple(k): complex} is timed separately below (pure-Python object construction).
-    h2d = S * ld + S * 8 + C_SUB * (n * b + P * ld + b * ld)
+    # bytes uploaded per step by ONE rank: the support digits (its 1 / N slice when the ranks stage the table together,
+    # ops.pad_digits_sharded; the rest arrives over NVLink), the strengths, Ms / Ds / M^T rows
+    from qsft_b200 import ops as _ops
+    shared_staging = world > 1 and S >= _ops.SHARD_PACK_MIN_ROWS
+    h2d = (-(-S // world) if shared_staging else S) * ld + S * 8 + C_SUB * (n * b + P * ld + b * ld)
 
     def e2e_loop(output):
         barrier()
@@ -400,7 +404,7 @@ def run_ours(a):
     e2e_dict_ms_per_step, last_d = e2e_loop("dict")
     log(f"end-to-end loop (dict result): {e2e_dict_ms_per_step:.1f} ms/step")
     res, sw, stats, used_symm = last
-    d2h = stats["distinct"] * (n + 8 + 4 + 8)
+    d2h = stats["distinct"] * (n + 16 + 4)          # digit rows, complex128 means, counts (qsft_peel_distinct)
     got = dict(zip(map(tuple, res["locations"].tolist()), res["values"].tolist()))
     recovered = set(got.keys()) == set(sw.keys()) and set(last_d[0].keys()) == set(sw.keys())
     max_err = max(abs(got[k] - v) for k, v in sw.items()) if recovered else None
@@ -511,7 +515,8 @@ def run_ours(a):
                                       "": ", peel replicated on every rank (no collective)"}[dist.shard_peel(8 * G * B)])
                    if a.gpus > 1 else "single GPU"},
         "e2e": {"value": 1e3 / e2e_ms_per_step, "unit": "transforms/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "result": "host arrays (locations, values); output='arrays'",
+                "d2h_bytes_per_step": int(d2h), "bytes_are": "per rank (every rank uploads its inputs and reads the result back)",
+                "result": "host arrays (locations, values); output='arrays'",
                 "value_with_reference_dict_result": 1e3 / e2e_dict_ms_per_step},
         "gpu_launches": int(launches),
         "clocks": clocks,
