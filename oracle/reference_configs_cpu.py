@@ -1,7 +1,7 @@
 """BASELINE configs 1 and 2 run IN FULL by the UNMODIFIED reference (no extrapolation): constructor (= query indices + sampling
 + FFT, input_signal_subsampled.py:107-155) and QSFT.transform, timed on this host's cores, with the same seeds, shapes and
-noise levels as tools/bench_configs.py.  CPU only -- run where a copy of the reference exists (/root/reference or oracle/_ref).
-    python tools/reference_configs_cpu.py > profiles/r2/reference_cpu_configs_1_2.json"""
+noise levels as tools/bench_configs.py.  TEST INFRASTRUCTURE (like gen_golden.py), CPU only -- run where a copy of the reference exists (/root/reference or oracle/_ref).
+    python oracle/reference_configs_cpu.py > profiles/r2/reference_cpu_configs_1_2.json"""
 import json
 import os
 import sys
@@ -10,7 +10,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import ref_shim  # noqa: E402
 
 root = ref_shim.reference_root()
