@@ -22,6 +22,24 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert L.qsft_version() >= 100
 
 
+def test_ctypes_bindings_match_the_header_prototypes():
+    """Every prototype of include/qsft_b200.h is bound with the same number of arguments in qsft_b200/_lib.py (a binding that
+    drifts from the header passes garbage in registers without any error)."""
+    import qsft_b200
+    L = qsft_b200.lib()
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "qsft_b200.h")).read(), flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|void|const char\*)\s+(qsft_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= 25
+    for name, args in protos:
+        args = args.strip()
+        n_args = 0 if args in ("", "void") else args.count(",") + 1
+        bound = getattr(L, name).argtypes
+        if n_args == 0:
+            assert not bound, name
+        else:
+            assert bound is not None and len(bound) == n_args, (name, n_args, None if bound is None else len(bound))
+
+
 def test_no_cpu_fallback_without_cuda():
     import torch
     import qsft_b200
