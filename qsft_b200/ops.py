@@ -119,6 +119,13 @@ def pad_digits(rows, ld, device, transposed=False):
 SHARD_PACK_MIN_ROWS = 32768
 
 
+def shard_rows(N, world, rank):
+    """Equal row blocks for an all-gather: (rows per rank, first row, one past the last row) of `rank`; the last blocks may be
+    short or empty (their padding rows are zero)."""
+    per = -(-int(N) // int(world)) if N > 0 else 0
+    return per, min(N, rank * per), min(N, (rank + 1) * per)
+
+
 def pad_digits_sharded(rows, ld, device, dist, transposed=False):
     """pad_digits for a table every rank of `dist` holds (the support): rank r stages and uploads only rows
     [r N / world, (r + 1) N / world) and one NCCL all-gather over NVLink completes the table on every GPU -- the host-side
@@ -130,8 +137,7 @@ def pad_digits_sharded(rows, ld, device, dist, transposed=False):
         a = a.T
     N = a.shape[0]
     world, rank = dist.world_size, dist.rank
-    per = -(-N // world)
-    lo, hi = min(N, rank * per), min(N, (rank + 1) * per)
+    per, lo, hi = shard_rows(N, world, rank)
     full = torch.empty((per * world, ld), dtype=torch.int8, device=device)
     mine = torch.zeros((per, ld), dtype=torch.int8, device=device) if hi - lo < per else torch.empty((per, ld), dtype=torch.int8, device=device)
     if hi > lo:

@@ -40,6 +40,21 @@ def test_ctypes_bindings_match_the_header_prototypes():
             assert bound is not None and len(bound) == n_args, (name, n_args, None if bound is None else len(bound))
 
 
+def test_shard_rows_cover_the_table_exactly_once():
+    """Row blocks of the rank-shared support staging (ops.pad_digits_sharded): equal block size, every row in exactly one block,
+    ragged and empty tails."""
+    from qsft_b200.ops import shard_rows
+    for N in (0, 1, 5, 8, 60, 1000, 100_000, 100_003):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for rank in range(world):
+                per, lo, hi = shard_rows(N, world, rank)
+                assert 0 <= lo <= hi <= N and hi - lo <= per and per * world >= N
+                assert lo == min(N, rank * per)
+                seen.extend(range(lo, hi))
+            assert seen == list(range(N)), (N, world)
+
+
 def test_no_cpu_fallback_without_cuda():
     import torch
     import qsft_b200
